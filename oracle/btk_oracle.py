@@ -1,0 +1,397 @@
+"""oracle/btk_oracle.py -- CPU oracle, TEST INFRASTRUCTURE ONLY.
+
+numpy (float64 / complex128) restatement of the reference's subband front end:
+analysis bank -> SubbandDS / SubbandMVDR -> synthesis bank.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
+leg may import this module; the product (``distantspeechrecognition-mirror_b200``)
+never does and has no CPU fallback.
+
+Pinning: the reference ships no golden vectors, so this
+restatement is pinned against the reference ITSELF -- its own .cc files compiled
+in place by ``oracle/Makefile`` into ``oracle/_ref/libbtk_ref.so`` -- in
+``tests/test_oracle_vs_ref.py`` and through the committed fixtures under
+``tests/golden/`` (made by ``tests/golden/make_golden.py`` from that library).
+
+Every function cites the reference lines it restates (paths relative to
+/root/reference/btk).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+SSPEED = 343740.0  # mm/s, beamformer/beamformer.h:47
+
+
+# --------------------------------------------------------------------------- geometry
+@dataclass(frozen=True)
+class BankGeometry:
+    """Derived sizes of OverSampledDFTFilterBank (modulated/modulated.cc:101-104, 262-300)."""
+
+    M: int
+    m: int
+    r: int
+    dct: int = 0
+
+    @property
+    def R(self) -> int:
+        return 1 << self.r
+
+    @property
+    def D(self) -> int:
+        return self.M >> self.r
+
+    @property
+    def N(self) -> int:
+        return self.M * self.m
+
+    @property
+    def B(self) -> int:
+        return self.M // 2 + 1
+
+    @property
+    def pd_analysis(self) -> int:
+        # modulated.cc:278-296 (synthesis == false)
+        return {0: 2 * self.m - 1, 1: self.m * self.R - 1, 2: self.m * self.R - 1}.get(self.dct, 2 * self.m - 1)
+
+    @property
+    def pd_synthesis(self) -> int:
+        # modulated.cc:278-296 (synthesis == true)
+        return {0: 2 * self.m - 1, 1: self.m * self.R - 1, 2: self.m * self.R // 2}.get(self.dct, 2 * self.m - 1)
+
+    @property
+    def laN(self) -> int:
+        return (self.m * self.R // 2 - 1) if self.dct == 2 else 0
+
+    def nblk(self, T: int) -> int:
+        # SampleFeature::next: ceil(T / D) blocks, last one zero padded (feature/feature.cc:627-641)
+        return -(-T // self.D)
+
+    def analysis_frames(self, T: int) -> int:
+        # modulated.cc:461-516: nblk real + pd padded frames, first laN internal frames skipped
+        return self.nblk(T) + self.pd_analysis - self.laN
+
+    def synthesis_frames(self, F: int) -> int:
+        # modulated.cc:626-642: pd frames are consumed by priming, then one output per input frame
+        return max(F - self.pd_synthesis, 0)
+
+
+# --------------------------------------------------------------------------- analysis
+def analysis(x: np.ndarray, h: np.ndarray, geo: BankGeometry) -> np.ndarray:
+    """OverSampledDFTAnalysisBank::next over a whole recording (modulated/modulated.cc:412-516).
+
+    x: float samples [T] (converted to double exactly like _RealBuffer::nextSample(float),
+    modulated.h:121-130).  Returns complex128 [F][M] with F = nblk + pd - laN.
+      u_i[q] = sum_k h[q + M k] * x[(i+1) D - 1 - q - M k]     (:419-434, zero before t=0 and after the data)
+      X_i[s] = sum_q u_i[q] exp(+j 2 pi s q / M)                (:439, unnormalised backward FFT)
+    """
+    x = np.asarray(x, dtype=np.float64)
+    h = np.asarray(h, dtype=np.float64)
+    M, m, D, N = geo.M, geo.m, geo.D, geo.N
+    assert h.shape == (N,)
+    T = x.shape[0]
+    nblk = geo.nblk(T)
+    nint = nblk + geo.pd_analysis  # internal frames i = 0 .. nint-1
+    xx = np.zeros(N + (nint + 1) * D, dtype=np.float64)
+    xx[N : N + T] = x
+    # window of frame i is xx[i*D + D : i*D + D + N] reversed (newest sample first)
+    n0 = N + (np.arange(nint) + 1) * D - 1  # index of the newest sample of frame i
+    idx = n0[:, None] - np.arange(N)[None, :]
+    win = xx[idx] * h[None, :]
+    u = win.reshape(nint, m, M).sum(axis=1)
+    X = np.fft.ifft(u, axis=1) * M
+    return X[geo.laN :]
+
+
+# --------------------------------------------------------------------------- delay-and-sum
+def ds_weights(delays: np.ndarray, fs: float, M: int) -> np.ndarray:
+    """beamformerWeights::calcMainlobe, halfBandShift == false (beamformer/beamformer.cc:531-594).
+
+    Returns wq [B][C] complex128: wq[0] = 1/C; wq[s] = exp(-j 2 pi s tau fs / M)/C for 1 <= s < M/2;
+    wq[M/2] = exp(-j pi fs tau)/C.
+    """
+    tau = np.asarray(delays, dtype=np.float64)
+    C = tau.shape[0]
+    B = M // 2 + 1
+    s = np.arange(B, dtype=np.float64)
+    ph = -2.0 * np.pi * s[:, None] * tau[None, :] * fs / M
+    ph[M // 2] = -np.pi * fs * tau
+    w = np.exp(1j * ph) / C
+    w[0] = 1.0 / C
+    return w
+
+
+def beamform(X: np.ndarray, W: np.ndarray) -> np.ndarray:
+    """SubbandDS::next / SubbandMVDR::next (beamformer.cc:1137-1200, 2583-2635).
+
+    X: [F][C][M] per-channel full spectra (only bins 0..M/2 are read, like the reference's
+    snapshot loop), W: [B][C].  Y[s] = sum_c conj(W[s,c]) X_c[s] (gsl_blas_zdotc conjugates its
+    first argument), Y[M-s] = conj(Y[s]).  Returns [F][M].
+    """
+    F, C, M = X.shape
+    B = M // 2 + 1
+    Yh = np.einsum("sc,fcs->fs", np.conj(W), X[:, :, :B])
+    Y = np.empty((F, M), dtype=np.complex128)
+    Y[:, :B] = Yh
+    Y[:, B:] = np.conj(Yh[:, 1 : M // 2][:, ::-1])
+    return Y
+
+
+# --------------------------------------------------------------------------- MVDR
+def diffuse_coherence(micpos_mm: np.ndarray, fs: float, M: int, sspeed: float = SSPEED) -> np.ndarray:
+    """SubbandMVDR::setDiffuseNoiseModel (beamformer.cc:2486-2553): Gamma_mn = sinc(2 fs s d_mn/(M c)),
+    GSL's normalised sinc == numpy's, unit diagonal.  Returns [B][C][C] complex128."""
+    p = np.asarray(micpos_mm, dtype=np.float64)
+    d = np.sqrt(((p[:, None, :3] - p[None, :, :3]) ** 2).sum(-1))
+    B = M // 2 + 1
+    s = np.arange(B, dtype=np.float64)
+    G = np.sinc((2.0 * fs * s / (M * sspeed))[:, None, None] * d[None])
+    i = np.arange(p.shape[0])
+    G[:, i, i] = 1.0
+    return G.astype(np.complex128)
+
+
+def divide_nondiagonal(Rn: np.ndarray, mu: float) -> np.ndarray:
+    """SubbandMVDR::divideAllNonDiagonalElements (beamformer.h:362-378); mu passes through float."""
+    out = np.array(Rn, dtype=np.complex128, copy=True)
+    C = out.shape[-1]
+    off = ~np.eye(C, dtype=bool)
+    out[:, off] = out[:, off] / (1.0 + float(np.float32(mu)))
+    return out
+
+
+def diagonal_load(Rn: np.ndarray, load: float) -> np.ndarray:
+    """SubbandMVDR::setAllLevelsOfDiagonalLoading (beamformer.cc:2555-2568): the weight is stored in a
+    float array (_diagonalWeights) before it is added, so it is rounded to float32 first."""
+    out = np.array(Rn, dtype=np.complex128, copy=True)
+    i = np.arange(out.shape[-1])
+    out[:, i, i] += float(np.float32(load))
+    return out
+
+
+def mvdr_weights(Rn: np.ndarray, wq: np.ndarray) -> np.ndarray:
+    """SubbandMVDR::calcMVDRWeights (beamformer.cc:2392-2446) with an exact inverse ("oracle B").
+
+    w[0] = ones (NOT 1/C, :2410-2415); for s >= 1: t = Rinv^H d, lam = t^H d, w = t / (lam * C)
+    with d = wq[s] (already divided by C).  Rn: [B][C][C], wq: [B][C]."""
+    B, C = wq.shape
+    w = np.ones((B, C), dtype=np.complex128)
+    for s in range(1, B):
+        Rinv = np.linalg.inv(Rn[s])
+        t = Rinv.conj().T @ wq[s]
+        lam = np.vdot(t, wq[s])  # conj(t) . d
+        w[s] = t / (lam * C)
+    return w
+
+
+# --------------------------------------------------------------------------- covariance
+def spectral_matrix_cpp(X: np.ndarray, mu: float = 0.95) -> np.ndarray:
+    """SpectralMatrixArray::update over all frames (beamformer.cc:142-163): R <- mu R + (1-mu) x x^T,
+    NO conjugate, all M bins, R starts at zero.  X: [F][C][M].  Returns [M][C][C]."""
+    F, C, M = X.shape
+    wts = (1.0 - mu) * mu ** np.arange(F - 1, -1, -1, dtype=np.float64)
+    return np.einsum("f,fis,fjs->sij", wts, X, X)
+
+
+def spectral_matrix_py(X: np.ndarray, ff: float = 0.99, nbins: int | None = None) -> np.ndarray:
+    """SubbandBeamformerMVDR.updateSx (lib/subbandBeamforming.py:1170-1175): frame 0: S = x x^H, then
+    S <- ff S + (1-ff) x x^H.  X: [F][C][M].  Returns [nbins][C][C] (default bins 0..M/2)."""
+    F, C, M = X.shape
+    nb = M // 2 + 1 if nbins is None else nbins
+    wts = (1.0 - ff) * ff ** np.arange(F - 1, -1, -1, dtype=np.float64)
+    wts[0] = ff ** (F - 1)
+    Xb = X[:, :, :nb]
+    return np.einsum("f,fis,fjs->sij", wts, Xb, np.conj(Xb))
+
+
+# --------------------------------------------------------------------------- synthesis
+def synthesis(Y: np.ndarray, g: np.ndarray, geo: BankGeometry, gain: int = 1) -> np.ndarray:
+    """OverSampledDFTSynthesisBank::next over a whole stream (modulated/modulated.cc:595-664).
+
+    Y: [F][M] full spectra.  Returns float32 [nout][D] with nout = F - pd.
+      v_tau[q]  = Re sum_s Y_tau[s] exp(-j 2 pi s q / M)                       (:603-607)
+      w_j[q]    = sum_k g[M-1-q + M k] v_{j+pd-R k}[q]   (v of frames < 0 is 0) (:646-651)
+      out_j[D-1-d] = sum_{s<R} w_{j-(R-1-s)}[d + s D],  w_{j'<0} = 0            (:655-658, priming quirk:
+                     the pd priming frames never produce a w, so the first R-1 outputs miss terms)
+    The reference accumulates the R terms into a float vector (gsl_vector_float_set of float + double),
+    so the sum is rounded to float32 after every term; that order is kept here.
+    """
+    Y = np.asarray(Y, dtype=np.complex128)
+    g = np.asarray(g, dtype=np.float64)
+    M, m, R, D = geo.M, geo.m, geo.R, geo.D
+    F = Y.shape[0]
+    pd = geo.pd_synthesis
+    nout = geo.synthesis_frames(F)
+    if nout == 0:
+        return np.zeros((0, D), dtype=np.float32)
+    v = np.real(np.fft.fft(Y, axis=1))
+    vp = np.concatenate([np.zeros((m * R, M)), v], axis=0)  # vp[m*R + tau] = v_tau
+    gp = g.reshape(m, M)[:, ::-1]  # gp[k, q] = g[M-1-q + M k]
+    j = np.arange(nout)
+    w = np.zeros((nout, M))
+    for k in range(m):
+        w += gp[k][None, :] * vp[m * R + j + pd - R * k]
+    wp = np.concatenate([np.zeros((R, M)), w], axis=0)  # wp[R + j] = w_j
+    out = np.zeros((nout, D), dtype=np.float32)
+    for s in range(R):  # sampX order of modulated.cc:655-658
+        term = wp[R + j - (R - 1 - s)][:, s * D : (s + 1) * D]
+        out = (out.astype(np.float64) + term).astype(np.float32)
+    out = out[:, ::-1]
+    if gain > 0:
+        out = (out * np.float32(gain)).astype(np.float32)
+    return np.ascontiguousarray(out)
+
+
+# --------------------------------------------------------------------------- geometry helpers (G1)
+def farfield_delays(micpos_mm: np.ndarray, azimuth: float, elevation: float, sspeed: float = SSPEED) -> np.ndarray:
+    """calcDelaysPolar2-style far-field delays (src/superdirectiveBeamformer.cc:118-137,
+    lib/subbandBeamforming.py:227-246): tau_c = (c . p_c)/sspeed with
+    c = -(sin(el) cos(az), sin(el) sin(az), cos(el)); geometry in mm."""
+    p = np.asarray(micpos_mm, dtype=np.float64)
+    c = -np.array([np.sin(elevation) * np.cos(azimuth), np.sin(elevation) * np.sin(azimuth), np.cos(elevation)])
+    return (p[:, :3] @ c) / sspeed
+
+
+# --------------------------------------------------------------------------- whole chain
+def chain(pcm: np.ndarray, h: np.ndarray, g: np.ndarray, geo: BankGeometry, W: np.ndarray, gain: int = 1):
+    """analysis (per channel) -> beamform with weights W [B][C] -> synthesis.
+    pcm: [T][C] float32.  Returns (X [F][C][M], Y [F][M], out float32 [nblk*D])."""
+    pcm = np.asarray(pcm)
+    C = pcm.shape[1]
+    X = np.stack([analysis(pcm[:, c], h, geo) for c in range(C)], axis=1)
+    Y = beamform(X, W)
+    out = synthesis(Y, g, geo, gain)
+    return X, Y, out.reshape(-1)
+
+
+# --------------------------------------------------------------------------- compiled reference (oracle/_ref)
+class _ChainCfg(ctypes.Structure):
+    _fields_ = [
+        ("M", ctypes.c_int), ("m", ctypes.c_int), ("r", ctypes.c_int), ("dct", ctypes.c_int), ("C", ctypes.c_int),
+        ("fs", ctypes.c_double), ("mode", ctypes.c_int), ("inverse_kind", ctypes.c_int), ("noise_model", ctypes.c_int),
+        ("dThreshold", ctypes.c_double), ("diag_load", ctypes.c_float), ("divide_mu", ctypes.c_float),
+        ("sspeed", ctypes.c_double), ("gain", ctypes.c_int),
+    ]
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class CompiledReference:
+    """ctypes view of oracle/_ref/libbtk_ref.so (the reference's own code; see oracle/ref_driver.cc)."""
+
+    def __init__(self, path: str | None = None):
+        here = os.path.dirname(os.path.abspath(__file__))
+        self.path = path or os.path.join(here, "_ref", "libbtk_ref.so")
+        if not os.path.exists(self.path):
+            raise FileNotFoundError(self.path)
+        self.lib = ctypes.CDLL(self.path)
+        L = self.lib
+        vp, cl, ci, cd = ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_double
+        L.btkref_analysis.restype = cl
+        L.btkref_analysis.argtypes = [vp, cl, vp, ci, ci, ci, ci, vp, cl]
+        L.btkref_synthesis.restype = cl
+        L.btkref_synthesis.argtypes = [vp, cl, vp, ci, ci, ci, ci, ci, vp, cl]
+        L.btkref_chain.restype = cl
+        L.btkref_chain.argtypes = [ctypes.POINTER(_ChainCfg), vp, cl, vp, vp, vp, vp, vp, vp, vp, cl, vp, cl,
+                                   ctypes.POINTER(cl), vp]
+        L.btkref_spectral_matrix.restype = cl
+        L.btkref_spectral_matrix.argtypes = [vp, cl, ci, vp, ci, ci, ci, ci, cd, vp]
+        L.btkref_error_probe.restype = ci
+        L.btkref_error_probe.argtypes = [ci]
+
+    @staticmethod
+    def available(path: str | None = None) -> bool:
+        here = os.path.dirname(os.path.abspath(__file__))
+        return os.path.exists(path or os.path.join(here, "_ref", "libbtk_ref.so"))
+
+    def analysis(self, x, h, geo: BankGeometry) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        h = np.ascontiguousarray(h, dtype=np.float64)
+        cap = geo.analysis_frames(x.shape[0]) + 4
+        X = np.zeros((cap, geo.M, 2), dtype=np.float64)
+        n = self.lib.btkref_analysis(_dp(x), x.shape[0], _dp(h), geo.M, geo.m, geo.r, geo.dct, _dp(X), cap)
+        if n < 0 or n > cap:
+            raise RuntimeError(f"btkref_analysis returned {n}")
+        return X[:n].view(np.complex128)[..., 0]
+
+    def synthesis(self, Y, g, geo: BankGeometry, gain: int = 1) -> np.ndarray:
+        Y = np.ascontiguousarray(Y, dtype=np.complex128)
+        g = np.ascontiguousarray(g, dtype=np.float64)
+        cap = Y.shape[0] + 4
+        out = np.zeros((cap, geo.D), dtype=np.float32)
+        n = self.lib.btkref_synthesis(_dp(Y), Y.shape[0], _dp(g), geo.M, geo.m, geo.r, geo.dct, gain, _dp(out), cap)
+        if n < 0 or n > cap:
+            raise RuntimeError(f"btkref_synthesis returned {n}")
+        return out[:n]
+
+    def chain(self, pcm, h, g, geo: BankGeometry, delays, fs=16000.0, mode="ds", Rn=None, micpos=None,
+              diag_load=0.0, divide_mu=-1.0, dThreshold=1e-8, inverse="double", want_snap=True, want_Y=True,
+              gain=1, sspeed=SSPEED):
+        """Run the reference chain.  Returns dict(X=[F][C][M], Y=[F][M], out=[nblk*D], W=[B][C], frames, out_frames)."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.float32)
+        T, C = pcm.shape
+        h = np.ascontiguousarray(h, dtype=np.float64)
+        g = None if g is None else np.ascontiguousarray(g, dtype=np.float64)
+        delays = np.ascontiguousarray(delays, dtype=np.float64)
+        cfg = _ChainCfg(geo.M, geo.m, geo.r, geo.dct, C, fs, 1 if mode == "mvdr" else 0,
+                        1 if inverse == "double" else 0, 1 if (micpos is not None) else 0, dThreshold,
+                        diag_load, divide_mu, sspeed, gain)
+        cap = geo.analysis_frames(T) + 4
+        snap = np.zeros((cap, geo.M, C, 2), dtype=np.float64) if want_snap else None
+        Y = np.zeros((cap, geo.M, 2), dtype=np.float64) if want_Y else None
+        cap_out = geo.nblk(T) + 4
+        out = np.zeros((cap_out, geo.D), dtype=np.float32) if g is not None else None
+        W = np.zeros((geo.B, C, 2), dtype=np.float64)
+        Rn_c = None if Rn is None else np.ascontiguousarray(Rn, dtype=np.complex128)
+        mp = None if micpos is None else np.ascontiguousarray(micpos, dtype=np.float64)
+        nout = ctypes.c_long(0)
+        n = self.lib.btkref_chain(ctypes.byref(cfg), _dp(pcm), T, _dp(h), _dp(g), _dp(delays), _dp(Rn_c), _dp(mp),
+                                  _dp(snap), _dp(Y), cap, _dp(out), cap_out, ctypes.byref(nout), _dp(W))
+        if n < 0 or n > cap:
+            raise RuntimeError(f"btkref_chain returned {n}")
+        res = {"frames": int(n), "out_frames": int(nout.value), "W": W.view(np.complex128)[..., 0]}
+        if want_snap:
+            res["X"] = np.ascontiguousarray(snap[:n].view(np.complex128)[..., 0].transpose(0, 2, 1))  # [F][C][M]
+        if want_Y:
+            res["Y"] = Y[:n].view(np.complex128)[..., 0]
+        if g is not None:
+            res["out"] = out[: nout.value].reshape(-1)
+        return res
+
+    def spectral_matrix(self, pcm, h, geo: BankGeometry, mu=0.95) -> np.ndarray:
+        pcm = np.ascontiguousarray(pcm, dtype=np.float32)
+        T, C = pcm.shape
+        h = np.ascontiguousarray(h, dtype=np.float64)
+        R = np.zeros((geo.M, C, C, 2), dtype=np.float64)
+        n = self.lib.btkref_spectral_matrix(_dp(pcm), T, C, _dp(h), geo.M, geo.m, geo.r, geo.dct, mu, _dp(R))
+        if n < 0:
+            raise RuntimeError(f"btkref_spectral_matrix returned {n}")
+        return R.view(np.complex128)[..., 0]
+
+    def error_probe(self, which: int) -> int:
+        return int(self.lib.btkref_error_probe(which))
+
+
+# --------------------------------------------------------------------------- metrics
+def rel_l2(a: np.ndarray, b: np.ndarray) -> float:
+    """||a - b||_2 / ||b||_2 (b is the reference)."""
+    a = np.asarray(a)
+    b = np.asarray(b)
+    den = np.linalg.norm(b.ravel())
+    return float(np.linalg.norm((a - b).ravel()) / (den if den > 0 else 1.0))
+
+
+def snr_db(test: np.ndarray, ref: np.ndarray) -> float:
+    """10 log10(||ref||^2 / ||test - ref||^2)."""
+    ref = np.asarray(ref, dtype=np.float64)
+    err = np.asarray(test, dtype=np.float64) - ref
+    pe = float((err**2).sum())
+    ps = float((ref**2).sum())
+    if pe == 0:
+        return float("inf")
+    return 10.0 * np.log10(ps / pe)

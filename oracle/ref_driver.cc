@@ -1,0 +1,412 @@
+// oracle/ref_driver.cc
+//
+// TEST INFRASTRUCTURE ONLY -- never linked into the product library.
+//
+// Thin extern "C" harness around the UNMODIFIED reference classes, compiled by
+// oracle/Makefile together with the reference's own sources (read in place from
+// /root/reference/btk) into oracle/_ref/libbtk_ref.so.  Everything numerical
+// below is done by the reference:
+//   OverSampledDFTAnalysisBank   btk/modulated/modulated.cc:359-516
+//   OverSampledDFTSynthesisBank  btk/modulated/modulated.cc:521-674
+//   SubbandDS                    btk/beamformer/beamformer.cc:1057-1212
+//   SubbandMVDR                  btk/beamformer/beamformer.cc:2321-2635
+//   SpectralMatrixArray          btk/beamformer/beamformer.cc:119-163
+// This file only feeds them from memory and copies their per-frame outputs out.
+// The in-memory source reproduces SampleFeature::next's block/pad rule
+// (btk/feature/feature.cc:610-659) because feature.cc itself needs libsndfile.
+
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+#include <exception>
+
+#include "stream/stream.h"
+#include "modulated/modulated.h"
+#include "beamformer/beamformer.h"
+
+// ---------------------------------------------------------------------------
+// Symbols the reference's beamformer.cc references from postfilter.cc (only via
+// SubbandMMI, which is never instantiated here).  Defining them keeps the .so
+// free of undefined symbols without building postfilter.cc.
+// ---------------------------------------------------------------------------
+#include "postfilter/postfilter.h"
+void ZelinskiFilter(gsl_vector_complex**, SnapShotArrayPtr, bool, gsl_vector_complex*, gsl_vector_complex**,
+                    gsl_vector_complex*, double, int) {
+  throw j_error("ZelinskiFilter is not part of the oracle build");
+}
+void ApabFilter(gsl_vector_complex**, SnapShotArrayPtr, int, int, bool, gsl_vector_complex*, int) {
+  throw j_error("ApabFilter is not part of the oracle build");
+}
+
+namespace {
+
+// In-memory block source: one channel of a (possibly interleaved) float buffer.
+// Block/pad semantics follow SampleFeature::next (feature.cc:610-659) with
+// blockLen == shiftLen == D and padZeros == true.
+class MemorySampleFeature : public VectorFloatFeatureStream {
+ public:
+  MemorySampleFeature(const float* base, long T, unsigned stride, unsigned D)
+      : VectorFloatFeatureStream(D, "MemorySampleFeature"), _base(base), _T(T), _stride(stride), _cur(0) {}
+
+  virtual const gsl_vector_float* next(int frameX = -5) {
+    if (_endOfSamples) throw jiterator_error("end of samples!");
+    if (frameX == _frameX) return _vector;
+    if (frameX >= 0 && frameX - 1 != _frameX)
+      throw jindex_error("Problem in Feature %s: %d != %d\n", name().c_str(), frameX - 1, _frameX);
+    if (_cur >= _T) { _endOfSamples = true; throw jiterator_error("end of samples!"); }
+    const long n = (long)size();
+    if (_cur + n >= _T) {
+      gsl_vector_float_set_zero(_vector);
+      for (long i = 0; i < _T - _cur; i++) gsl_vector_float_set(_vector, i, _base[(_cur + i) * _stride]);
+    } else {
+      for (long i = 0; i < n; i++) gsl_vector_float_set(_vector, i, _base[(_cur + i) * _stride]);
+    }
+    _cur += n;
+    _increment();
+    return _vector;
+  }
+  virtual void reset() { _cur = 0; VectorFloatFeatureStream::reset(); }
+
+ private:
+  const float* _base;
+  const long _T;
+  const unsigned _stride;
+  long _cur;
+};
+
+// Complex stream fed from a memory buffer of full-M spectra (for synthesis-only runs).
+class MemoryComplexFeature : public VectorComplexFeatureStream {
+ public:
+  MemoryComplexFeature(const double* Y, long F, unsigned M)
+      : VectorComplexFeatureStream(M, "MemoryComplexFeature"), _Y(Y), _F(F) {}
+  virtual const gsl_vector_complex* next(int frameX = -5) {
+    if (frameX == _frameX) return _vector;
+    long f = (long)_frameX + 1;
+    if (f >= _F) { _endOfSamples = true; throw jiterator_error("end of samples!"); }
+    for (unsigned s = 0; s < size(); s++)
+      gsl_vector_complex_set(_vector, s, gsl_complex_rect(_Y[2 * (f * size() + s)], _Y[2 * (f * size() + s) + 1]));
+    _increment();
+    return _vector;
+  }
+
+ private:
+  const double* _Y;
+  const long _F;
+};
+
+// Pass-through node that records what the beamformer emitted (and its snapshots).
+class RecordingTee : public VectorComplexFeatureStream {
+ public:
+  RecordingTee(SubbandDS* bf, unsigned M, unsigned C, double* Y, double* snap, long cap)
+      : VectorComplexFeatureStream(M, "RecordingTee"), _bf(bf), _C(C), _Y(Y), _snap(snap), _cap(cap), _n(0) {}
+  virtual const gsl_vector_complex* next(int frameX = -5) {
+    if (frameX == _frameX) return _vector;
+    const gsl_vector_complex* y = _bf->next(frameX);
+    const unsigned M = size();
+    gsl_vector_complex_memcpy(_vector, y);
+    if (_n < _cap) {
+      if (_Y) for (unsigned s = 0; s < M; s++) {
+        gsl_complex z = gsl_vector_complex_get(y, s);
+        _Y[2 * (_n * M + s)] = GSL_REAL(z); _Y[2 * (_n * M + s) + 1] = GSL_IMAG(z);
+      }
+      if (_snap) for (unsigned s = 0; s < M; s++) {
+        const gsl_vector_complex* x = _bf->snapShotArray_f(s);
+        for (unsigned c = 0; c < _C; c++) {
+          gsl_complex z = gsl_vector_complex_get(x, c);
+          double* p = _snap + 2 * ((_n * M + s) * _C + c);
+          p[0] = GSL_REAL(z); p[1] = GSL_IMAG(z);
+        }
+      }
+    }
+    _n++;
+    _increment();
+    return _vector;
+  }
+  virtual void reset() { _bf->reset(); VectorComplexFeatureStream::reset(); }
+  long frames() const { return _n; }
+
+ private:
+  SubbandDS* _bf;
+  const unsigned _C;
+  double* _Y;
+  double* _snap;
+  const long _cap;
+  long _n;
+};
+
+// Oracle "B" (SURVEY 8c): the reference's calcMVDRWeights with the float-SVD
+// pseudoinverse (beamformer.cc:253-305) replaced by a double-precision inverse.
+// _invR is protected, so a subclass fills it and calls calcMVDRWeights(...,false),
+// which is the reference's own "inverse already supplied" path (beamformer.cc:2422).
+class MVDRDoubleInverse : public SubbandMVDR {
+ public:
+  MVDRDoubleInverse(unsigned fftLen) : SubbandMVDR(fftLen, false, "SubbandMVDR") {}
+  bool fillDoubleInverses() {
+    const unsigned C = chanN();
+    bool ok = true;
+    for (unsigned s = 1; s <= _fftLen / 2; s++) {
+      if (_R[s] == NULL) return false;
+      if (_invR[s] == NULL) _invR[s] = gsl_matrix_complex_alloc(C, C);
+      ok = invert(_R[s], _invR[s], C) && ok;
+    }
+    return ok;
+  }
+
+ private:
+  // Gauss-Jordan with partial pivoting in long double complex arithmetic.
+  static bool invert(const gsl_matrix_complex* A, gsl_matrix_complex* inv, unsigned n) {
+    typedef long double ld;
+    std::vector<ld> ar(n * 2 * n), ai(n * 2 * n);
+    for (unsigned i = 0; i < n; i++) for (unsigned j = 0; j < n; j++) {
+      gsl_complex z = gsl_matrix_complex_get(A, i, j);
+      ar[i * 2 * n + j] = GSL_REAL(z); ai[i * 2 * n + j] = GSL_IMAG(z);
+      ar[i * 2 * n + n + j] = (i == j) ? 1.0L : 0.0L; ai[i * 2 * n + n + j] = 0.0L;
+    }
+    for (unsigned col = 0; col < n; col++) {
+      unsigned piv = col; ld best = -1;
+      for (unsigned i = col; i < n; i++) {
+        ld a = ar[i * 2 * n + col] * ar[i * 2 * n + col] + ai[i * 2 * n + col] * ai[i * 2 * n + col];
+        if (a > best) { best = a; piv = i; }
+      }
+      if (best <= 0) return false;
+      if (piv != col) for (unsigned j = 0; j < 2 * n; j++) {
+        std::swap(ar[piv * 2 * n + j], ar[col * 2 * n + j]); std::swap(ai[piv * 2 * n + j], ai[col * 2 * n + j]);
+      }
+      ld pr = ar[col * 2 * n + col], pi = ai[col * 2 * n + col], d = pr * pr + pi * pi;
+      ld ir = pr / d, ii = -pi / d;
+      for (unsigned j = 0; j < 2 * n; j++) {
+        ld xr = ar[col * 2 * n + j], xi = ai[col * 2 * n + j];
+        ar[col * 2 * n + j] = xr * ir - xi * ii; ai[col * 2 * n + j] = xr * ii + xi * ir;
+      }
+      for (unsigned i = 0; i < n; i++) {
+        if (i == col) continue;
+        ld fr = ar[i * 2 * n + col], fi = ai[i * 2 * n + col];
+        if (fr == 0 && fi == 0) continue;
+        for (unsigned j = 0; j < 2 * n; j++) {
+          ld xr = ar[col * 2 * n + j], xi = ai[col * 2 * n + j];
+          ar[i * 2 * n + j] -= fr * xr - fi * xi; ai[i * 2 * n + j] -= fr * xi + fi * xr;
+        }
+      }
+    }
+    for (unsigned i = 0; i < n; i++) for (unsigned j = 0; j < n; j++)
+      gsl_matrix_complex_set(inv, i, j, gsl_complex_rect((double)ar[i * 2 * n + n + j], (double)ai[i * 2 * n + n + j]));
+    return true;
+  }
+};
+
+gsl_vector* make_vector(const double* src, size_t n) {
+  gsl_vector* v = gsl_vector_alloc(n);
+  for (size_t i = 0; i < n; i++) gsl_vector_set(v, i, src[i]);
+  return v;
+}
+
+}  // namespace
+
+extern "C" {
+
+struct btkref_chain_cfg {
+  int M, m, r, dct, C;
+  double fs;
+  int mode;          // 0 = SubbandDS, 1 = SubbandMVDR
+  int inverse_kind;  // MVDR: 0 = reference float-SVD pseudoinverse (oracle A), 1 = double inverse (oracle B)
+  int noise_model;   // MVDR: 0 = explicit Rn per bin, 1 = setDiffuseNoiseModel(micpos)
+  double dThreshold;
+  float diag_load;   // applied with setAllLevelsOfDiagonalLoading when != 0
+  float divide_mu;   // applied with divideAllNonDiagonalElements when >= 0
+  double sspeed;
+  int gain;          // synthesis gainFactor
+};
+
+// Single-channel analysis.  X: [cap][M][2] doubles.  Returns frames emitted (may exceed cap), <0 on error.
+long btkref_analysis(const float* x, long T, const double* h, int M, int m, int r, int dct, double* X, long cap) {
+  try {
+    const unsigned D = M >> r;
+    gsl_vector* proto = make_vector(h, (size_t)M * m);
+    VectorFloatFeatureStreamPtr src(new MemorySampleFeature(x, T, 1, D));
+    OverSampledDFTAnalysisBankPtr bank(new OverSampledDFTAnalysisBank(src, proto, M, m, r, dct));
+    gsl_vector_free(proto);
+    long n = 0;
+    try {
+      for (;;) {
+        const gsl_vector_complex* f = bank->next();
+        if (n < cap) for (int s = 0; s < M; s++) {
+          gsl_complex z = gsl_vector_complex_get(f, s);
+          X[2 * (n * M + s)] = GSL_REAL(z); X[2 * (n * M + s) + 1] = GSL_IMAG(z);
+        }
+        n++;
+      }
+    } catch (jiterator_error&) {}
+    return n;
+  } catch (std::exception& e) { fprintf(stderr, "btkref_analysis: %s\n", e.what()); return -1; }
+}
+
+// Synthesis of a stored complex stream.  Y: [F][M][2]; out: [cap*D] floats.  Returns frames emitted.
+long btkref_synthesis(const double* Y, long F, const double* g, int M, int m, int r, int dct, int gain, float* out, long cap) {
+  try {
+    const unsigned D = M >> r;
+    gsl_vector* proto = make_vector(g, (size_t)M * m);
+    VectorComplexFeatureStreamPtr src(new MemoryComplexFeature(Y, F, M));
+    OverSampledDFTSynthesisBankPtr bank(new OverSampledDFTSynthesisBank(src, proto, M, m, r, dct, gain));
+    gsl_vector_free(proto);
+    long n = 0;
+    try {
+      for (;;) {
+        const gsl_vector_float* f = bank->next();
+        if (n < cap) for (unsigned d = 0; d < D; d++) out[n * D + d] = gsl_vector_float_get(f, d);
+        n++;
+      }
+    } catch (jiterator_error&) {}
+    return n;
+  } catch (std::exception& e) { fprintf(stderr, "btkref_synthesis: %s\n", e.what()); return -1; }
+}
+
+// Full chain: C analysis banks -> SubbandDS/SubbandMVDR -> (optional) synthesis.
+//   pcm   : interleaved [T][C] floats
+//   delays: [C] seconds;  Rn: [B][C][C][2] (noise_model 0) ; micpos: [C][3] mm (noise_model 1)
+//   snap  : [cap][M][C][2] or NULL;  Y: [cap][M][2] or NULL;  out: [cap_out*D] or NULL (no synthesis when g==NULL)
+//   W     : [B][C][2] weights actually used (wq for DS, wmvdr for MVDR) or NULL
+// Returns beamformer frames emitted; *n_out = synthesis frames emitted.
+long btkref_chain(const btkref_chain_cfg* cfg, const float* pcm, long T, const double* h, const double* g,
+                  const double* delays, const double* Rn, const double* micpos,
+                  double* snap, double* Y, long cap, float* out, long cap_out, long* n_out, double* W) {
+  try {
+    const int M = cfg->M, m = cfg->m, r = cfg->r, C = cfg->C;
+    const unsigned D = M >> r, B = M / 2 + 1;
+    gsl_vector* hp = make_vector(h, (size_t)M * m);
+    SubbandDS* bf;
+    MVDRDoubleInverse* mv = NULL;
+    if (cfg->mode == 1) { mv = new MVDRDoubleInverse(M); bf = mv; } else { bf = new SubbandDS(M, false); }
+    for (int c = 0; c < C; c++) {
+      VectorFloatFeatureStreamPtr src(new MemorySampleFeature(pcm + c, T, C, D));
+      VectorComplexFeatureStreamPtr bank(new OverSampledDFTAnalysisBank(src, hp, M, m, r, cfg->dct));
+      bf->setChannel(bank);
+    }
+    gsl_vector_free(hp);
+    gsl_vector* dv = make_vector(delays, C);
+    bf->calcArrayManifoldVectors(cfg->fs, dv);
+    gsl_vector_free(dv);
+    if (mv) {
+      if (cfg->noise_model == 1) {
+        gsl_matrix* mp = gsl_matrix_alloc(C, 3);
+        for (int c = 0; c < C; c++) for (int k = 0; k < 3; k++) gsl_matrix_set(mp, c, k, micpos[c * 3 + k]);
+        if (!mv->setDiffuseNoiseModel(mp, cfg->fs, cfg->sspeed)) { gsl_matrix_free(mp); return -2; }
+        gsl_matrix_free(mp);
+      } else {
+        gsl_matrix_complex* Rm = gsl_matrix_complex_alloc(C, C);
+        for (unsigned s = 0; s < B; s++) {
+          for (int i = 0; i < C; i++) for (int j = 0; j < C; j++) {
+            const double* p = Rn + 2 * ((size_t)(s * C + i) * C + j);
+            gsl_matrix_complex_set(Rm, i, j, gsl_complex_rect(p[0], p[1]));
+          }
+          if (!mv->setNoiseSpatialSpectralMatrix(s, Rm)) { gsl_matrix_complex_free(Rm); return -3; }
+        }
+        gsl_matrix_complex_free(Rm);
+      }
+      if (cfg->divide_mu >= 0.0f) mv->divideAllNonDiagonalElements(cfg->divide_mu);
+      if (cfg->diag_load != 0.0f) mv->setAllLevelsOfDiagonalLoading(cfg->diag_load);
+      if (cfg->inverse_kind == 1) {
+        if (!mv->fillDoubleInverses()) return -4;
+        mv->calcMVDRWeights(cfg->fs, cfg->dThreshold, false);
+      } else {
+        mv->calcMVDRWeights(cfg->fs, cfg->dThreshold, true);
+      }
+    }
+    if (W) for (unsigned s = 0; s < B; s++) {
+      const gsl_vector_complex* w = mv ? mv->getMVDRWeights(s) : bf->getWeights(s);
+      for (int c = 0; c < C; c++) {
+        gsl_complex z = gsl_vector_complex_get(w, c);
+        W[2 * (s * C + c)] = GSL_REAL(z); W[2 * (s * C + c) + 1] = GSL_IMAG(z);
+      }
+    }
+    RecordingTee* tee = new RecordingTee(bf, M, C, Y, snap, cap);
+    VectorComplexFeatureStreamPtr teep(tee);
+    long nsyn = 0;
+    if (g) {
+      gsl_vector* gp = make_vector(g, (size_t)M * m);
+      OverSampledDFTSynthesisBankPtr syn(new OverSampledDFTSynthesisBank(teep, gp, M, m, r, cfg->dct, cfg->gain));
+      gsl_vector_free(gp);
+      try {
+        for (;;) {
+          const gsl_vector_float* f = syn->next();
+          if (out && nsyn < cap_out) for (unsigned d = 0; d < D; d++) out[nsyn * D + d] = gsl_vector_float_get(f, d);
+          nsyn++;
+        }
+      } catch (jiterator_error&) {}
+    } else {
+      try { for (;;) teep->next(); } catch (jiterator_error&) {}
+    }
+    if (n_out) *n_out = nsyn;
+    long nf = tee->frames();
+    // bf is owned by nobody's smart pointer (the tee holds a raw pointer): release it here.
+    bf->clearChannel();
+    delete bf;
+    return nf;
+  } catch (std::exception& e) { fprintf(stderr, "btkref_chain: %s\n", e.what()); return -1; }
+}
+
+// SpectralMatrixArray recursion (beamformer.cc:142-163) over all frames of a recording.
+// Rout: [M][C][C][2].  Returns frames consumed.
+long btkref_spectral_matrix(const float* pcm, long T, int C, const double* h, int M, int m, int r, int dct,
+                            double mu, double* Rout) {
+  try {
+    const unsigned D = M >> r;
+    gsl_vector* hp = make_vector(h, (size_t)M * m);
+    std::vector<VectorComplexFeatureStreamPtr> banks;
+    for (int c = 0; c < C; c++) {
+      VectorFloatFeatureStreamPtr src(new MemorySampleFeature(pcm + c, T, C, D));
+      banks.push_back(VectorComplexFeatureStreamPtr(new OverSampledDFTAnalysisBank(src, hp, M, m, r, dct)));
+    }
+    gsl_vector_free(hp);
+    SpectralMatrixArray sma(M, C, mu);
+    sma.zero();
+    long n = 0;
+    try {
+      for (;;) {
+        for (int c = 0; c < C; c++) sma.newSample(banks[c]->next(), c);
+        sma.update();
+        n++;
+      }
+    } catch (jiterator_error&) {}
+    for (int s = 0; s < M; s++) {
+      const gsl_matrix_complex* Rm = sma.getSpecMatrix(s);
+      for (int i = 0; i < C; i++) for (int j = 0; j < C; j++) {
+        gsl_complex z = gsl_matrix_complex_get(Rm, i, j);
+        double* p = Rout + 2 * ((size_t)(s * C + i) * C + j);
+        p[0] = GSL_REAL(z); p[1] = GSL_IMAG(z);
+      }
+    }
+    return n;
+  } catch (std::exception& e) { fprintf(stderr, "btkref_spectral_matrix: %s\n", e.what()); return -1; }
+}
+
+// Error-path probes used by the parity tests of the drop-in classes' exception behaviour.
+//   which: 0 = prototype size mismatch (modulated.cc:269-271)  -> expect jconsistency_error
+//          1 = delays size mismatch   (beamformer.cc:533-535)  -> expect jdimension_error
+//          2 = SubbandDS::next before weights (beamformer.cc:1140-1143) -> j_error
+// Returns the j_error code thrown, or -1 when nothing was thrown.
+int btkref_error_probe(int which) {
+  try {
+    if (which == 0) {
+      gsl_vector* p = gsl_vector_calloc(10);
+      float x[8] = {0};
+      VectorFloatFeatureStreamPtr src(new MemorySampleFeature(x, 8, 1, 4));
+      OverSampledDFTAnalysisBankPtr bank(new OverSampledDFTAnalysisBank(src, p, 8, 2, 1, 0));
+    } else if (which == 1) {
+      SubbandDS bf(8, false);
+      gsl_vector* p = gsl_vector_calloc(16);
+      float x[8] = {0};
+      VectorFloatFeatureStreamPtr src(new MemorySampleFeature(x, 8, 1, 4));
+      VectorComplexFeatureStreamPtr bank(new OverSampledDFTAnalysisBank(src, p, 8, 2, 1, 0));
+      bf.setChannel(bank);
+      gsl_vector* d = gsl_vector_calloc(3);
+      bf.calcArrayManifoldVectors(16000.0, d);
+    } else if (which == 2) {
+      SubbandDS bf(8, false);
+      bf.next();
+    }
+  } catch (j_error& e) { return (int)e.getCode(); }
+  catch (std::exception&) { return -2; }
+  return -1;
+}
+
+}  // extern "C"
