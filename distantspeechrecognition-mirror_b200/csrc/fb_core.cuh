@@ -1,0 +1,235 @@
+// fb_core.cuh -- register/shared-memory FFT building blocks of the oversampled DFT filter bank.
+//
+// Everything here is __host__ __device__ so the exact same code runs (a) inside the sm_100a
+// kernels and (b) under the sequential host emulator used by the CPU-only tests
+// (tests/emu/): there is no GPU in the build container, so index arithmetic is validated on
+// the host before any GPU time is spent.  The emulator is a test harness for THIS code, not a
+// fallback: the product library only ever launches the CUDA kernels.
+//
+// Math restated (reference btk/modulated/modulated.cc:412-452, 595-664):
+//   analysis  X_i[s] = sum_q u_i[q] e^{+j 2 pi s q / M}   ("backward", SIGN=+1)
+//   synthesis v[q]   = Re sum_s Y[s] e^{-j 2 pi s q / M}  ("forward",  SIGN=-1)
+// Two real sequences are packed into one complex transform (frames i and i+1 of one channel
+// on the analysis side; two Hermitian spectra on the synthesis side), see DESIGN.md.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define BTK_HD __host__ __device__ __forceinline__
+#define BTK_UNROLL _Pragma("unroll")
+#else
+#define BTK_HD inline
+#define BTK_UNROLL
+#ifndef BTK_HOST_VECTOR_TYPES
+#define BTK_HOST_VECTOR_TYPES
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+struct double2 { double x, y; };
+#endif
+static inline float fmaf_host(float a, float b, float c) { return fmaf(a, b, c); }
+#endif
+
+namespace btk {
+
+typedef float2 cf;
+
+BTK_HD cf mk(float x, float y) { cf r; r.x = x; r.y = y; return r; }
+BTK_HD cf cadd(cf a, cf b) { return mk(a.x + b.x, a.y + b.y); }
+BTK_HD cf csub(cf a, cf b) { return mk(a.x - b.x, a.y - b.y); }
+BTK_HD cf cmul(cf a, cf b) { return mk(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x)); }
+// a * conj(b)
+BTK_HD cf cmulc(cf a, cf b) { return mk(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y)); }
+// acc += a * b
+BTK_HD void cfma(cf& acc, cf a, cf b) {
+  acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(-a.y, b.y, acc.x);
+  acc.y = fmaf(a.x, b.y, acc.y); acc.y = fmaf(a.y, b.x, acc.y);
+}
+// multiply by (j*S)
+template <int S> BTK_HD cf mulj(cf a) { return S > 0 ? mk(-a.y, a.x) : mk(a.y, -a.x); }
+// multiply by (c + j*S*s)
+template <int S> BTK_HD cf mulw(cf a, float c, float s) {
+  return S > 0 ? mk(fmaf(a.x, c, -a.y * s), fmaf(a.x, s, a.y * c)) : mk(fmaf(a.x, c, a.y * s), fmaf(a.y, c, -a.x * s));
+}
+// multiply by table twiddle w = e^{+j theta}; for S<0 use conj(w)
+template <int S> BTK_HD cf multw(cf a, cf w) { return S > 0 ? cmul(a, w) : cmulc(a, w); }
+
+#define BTK_SQRT1_2 0.70710678118654752440f
+#define BTK_COS_PI_8 0.92387953251128675613f
+#define BTK_SIN_PI_8 0.38268343236508977173f
+
+// ---------------------------------------------------------------------------------------------
+// Small in-register DFTs, natural-order in and out:  X[k] = sum_n x[n] e^{S j 2 pi n k / R}.
+// ---------------------------------------------------------------------------------------------
+template <int S> BTK_HD void dft2(cf& a, cf& b) { cf t = csub(a, b); a = cadd(a, b); b = t; }
+
+template <int S> BTK_HD void dft4(cf& x0, cf& x1, cf& x2, cf& x3) {
+  cf t0 = cadd(x0, x2), t1 = csub(x0, x2), t2 = cadd(x1, x3), t3 = mulj<S>(csub(x1, x3));
+  x0 = cadd(t0, t2); x1 = cadd(t1, t3); x2 = csub(t0, t2); x3 = csub(t1, t3);
+}
+
+template <int S> BTK_HD void dft8(cf* v) {
+  // decimation in time: even/odd 4-point DFTs, then W8^{S k}
+  cf e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
+  cf o0 = v[1], o1 = v[3], o2 = v[5], o3 = v[7];
+  dft4<S>(e0, e1, e2, e3);
+  dft4<S>(o0, o1, o2, o3);
+  // W8^1 = (1 + jS)/sqrt2 ; W8^2 = jS ; W8^3 = (-1 + jS)/sqrt2
+  cf t1 = S > 0 ? mk((o1.x - o1.y) * BTK_SQRT1_2, (o1.x + o1.y) * BTK_SQRT1_2)
+                : mk((o1.x + o1.y) * BTK_SQRT1_2, (o1.y - o1.x) * BTK_SQRT1_2);
+  cf t2 = mulj<S>(o2);
+  cf t3 = S > 0 ? mk((-o3.x - o3.y) * BTK_SQRT1_2, (o3.x - o3.y) * BTK_SQRT1_2)
+                : mk((o3.y - o3.x) * BTK_SQRT1_2, (-o3.x - o3.y) * BTK_SQRT1_2);
+  v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+  v[1] = cadd(e1, t1); v[5] = csub(e1, t1);
+  v[2] = cadd(e2, t2); v[6] = csub(e2, t2);
+  v[3] = cadd(e3, t3); v[7] = csub(e3, t3);
+}
+
+template <int S> BTK_HD void dft16(cf* v) {
+  // n = 4 n1 + n2, k = k1 + 4 k2
+  cf a[4][4];  // a[n2][k1]
+  BTK_UNROLL
+  for (int n2 = 0; n2 < 4; n2++) {
+    cf x0 = v[n2], x1 = v[4 + n2], x2 = v[8 + n2], x3 = v[12 + n2];
+    dft4<S>(x0, x1, x2, x3);
+    a[n2][0] = x0; a[n2][1] = x1; a[n2][2] = x2; a[n2][3] = x3;
+  }
+  // twiddles W16^{S n2 k1}
+  a[1][1] = mulw<S>(a[1][1], BTK_COS_PI_8, BTK_SIN_PI_8);                    // W^1
+  a[1][2] = mulw<S>(a[1][2], BTK_SQRT1_2, BTK_SQRT1_2);                      // W^2
+  a[1][3] = mulw<S>(a[1][3], BTK_SIN_PI_8, BTK_COS_PI_8);                    // W^3
+  a[2][1] = mulw<S>(a[2][1], BTK_SQRT1_2, BTK_SQRT1_2);                      // W^2
+  a[2][2] = mulj<S>(a[2][2]);                                               // W^4
+  a[2][3] = mulw<S>(a[2][3], -BTK_SQRT1_2, BTK_SQRT1_2);                     // W^6
+  a[3][1] = mulw<S>(a[3][1], BTK_SIN_PI_8, BTK_COS_PI_8);                    // W^3
+  a[3][2] = mulw<S>(a[3][2], -BTK_SQRT1_2, BTK_SQRT1_2);                     // W^6
+  a[3][3] = mulw<S>(a[3][3], -BTK_COS_PI_8, -BTK_SIN_PI_8);                  // W^9
+  BTK_UNROLL
+  for (int k1 = 0; k1 < 4; k1++) {
+    cf x0 = a[0][k1], x1 = a[1][k1], x2 = a[2][k1], x3 = a[3][k1];
+    dft4<S>(x0, x1, x2, x3);
+    v[k1] = x0; v[k1 + 4] = x1; v[k1 + 8] = x2; v[k1 + 12] = x3;
+  }
+}
+
+template <int R, int S> struct Dft;
+template <int S> struct Dft<1, S> { static BTK_HD void run(cf*) {} };
+template <int S> struct Dft<2, S> { static BTK_HD void run(cf* v) { dft2<S>(v[0], v[1]); } };
+template <int S> struct Dft<4, S> { static BTK_HD void run(cf* v) { dft4<S>(v[0], v[1], v[2], v[3]); } };
+template <int S> struct Dft<8, S> { static BTK_HD void run(cf* v) { dft8<S>(v); } };
+template <int S> struct Dft<16, S> { static BTK_HD void run(cf* v) { dft16<S>(v); } };
+
+// ---------------------------------------------------------------------------------------------
+// M-point transform shared by the L lanes of a group, V = M/L values per lane.
+//   M = Ra * Rb * Rc  with Rc == Ra (so the output register layout equals the input layout):
+//   n = na*(Rb*Rc) + nb*Rc + nc ,  k = ka + Ra*kb + Ra*Rb*kc
+//   pass A: radix-Ra over na   (owner: j  = nb*Rc + nc  = gl + L*rep)   * W_{Ra Rb}^{nb ka}
+//   pass B: radix-Rb over nb   (owner: iB = ka*Rc + nc  = gl + L*rep)   * W_M^{nc (ka + Ra kb)}
+//   pass C: radix-Rc over nc   (owner: iC = ka + Ra*kb  = gl + L*rep)
+// Register layout (input and output): value r = rep*Ra + e  <->  index  (gl + L*rep) + (M/Ra)*e.
+// Passes exchange data through a per-group shared-memory buffer of XBUF complex words.
+// ---------------------------------------------------------------------------------------------
+template <int M_> struct FFTPlan;
+template <> struct FFTPlan<64>   { static constexpr int M = 64,   Ra = 8,  Rb = 1, Rc = 8,  V = 8,  L = 8;  };
+template <> struct FFTPlan<128>  { static constexpr int M = 128,  Ra = 8,  Rb = 2, Rc = 8,  V = 8,  L = 16; };
+template <> struct FFTPlan<256>  { static constexpr int M = 256,  Ra = 16, Rb = 1, Rc = 16, V = 16, L = 16; };
+template <> struct FFTPlan<512>  { static constexpr int M = 512,  Ra = 16, Rb = 2, Rc = 16, V = 16, L = 32; };
+template <> struct FFTPlan<1024> { static constexpr int M = 1024, Ra = 16, Rb = 4, Rc = 16, V = 32, L = 32; };
+
+template <int M_> struct FFTGeom {
+  typedef FFTPlan<M_> P;
+  static constexpr int M = P::M, Ra = P::Ra, Rb = P::Rb, Rc = P::Rc, V = P::V, L = P::L;
+  static constexpr int NG = 32 / L;            // groups per warp
+  static constexpr int JA = M / Ra;            // owners of pass A per transform (= Rb*Rc)
+  static constexpr int RepA = V / Ra;          // radix-Ra DFTs per lane in pass A (and C)
+  static constexpr int RepB = (Rb > 1) ? V / Rb : 0;
+  static constexpr int PadA = (Rc % 32 == 0) ? 0 : Rc;  // S1 == Rc (mod 32) keeps pass-B reads conflict free
+  static constexpr int S1 = JA + PadA;         // row stride (complex words) of exchange 1: idx = ka*S1 + j
+  static constexpr int S2 = Rc + 1;            // row stride of exchange 2: idx = iC*S2 + nc
+  static constexpr int X1 = (Rb > 1) ? Ra * S1 : 0;
+  static constexpr int X2 = (M / Rc) * S2;
+  static constexpr int XBUF = X1 > X2 ? X1 : X2;   // complex words per group
+  // register <-> transform index
+  static BTK_HD int index_of(int gl, int r) { return (gl + L * (r / Ra)) + JA * (r % Ra); }
+};
+
+// One lane's share of the pass structure.  `tw` is the table tw[t] = e^{+j 2 pi t / M}, t in [0, M).
+// The three steps must be separated by a group-wide barrier (__syncwarp on the device).
+template <int M_, int S> struct GroupFFT {
+  typedef FFTGeom<M_> G;
+
+  // step 1: pass A (+ twiddle) and scatter into the exchange buffer.
+  static BTK_HD void step1(cf* v, int gl, cf* xb, const cf* tw) {
+    BTK_UNROLL
+    for (int rep = 0; rep < G::RepA; rep++) {
+      cf* p = v + rep * G::Ra;
+      Dft<G::Ra, S>::run(p);
+      const int j = gl + G::L * rep;
+      if (G::Rb > 1) {
+        const int nb = j / G::Rc;
+        // W_{Ra Rb}^{nb ka} = W_M^{nb ka Rc}
+        BTK_UNROLL
+        for (int ka = 1; ka < G::Ra; ka++) p[ka] = multw<S>(p[ka], tw[(nb * ka * G::Rc) & (G::M - 1)]);
+        BTK_UNROLL
+        for (int ka = 0; ka < G::Ra; ka++) xb[ka * G::S1 + j] = p[ka];
+      } else {
+        // two-factor case: nc == j, twiddle W_M^{nc ka}, straight to exchange 2 (iC == ka)
+        const cf w1 = tw[j];
+        cf w[G::Ra];
+        w[1] = w1;
+        BTK_UNROLL
+        for (int ka = 2; ka < G::Ra; ka++) w[ka] = (ka & 1) ? cmul(w[ka - 1], w1) : cmul(w[ka / 2], w[ka / 2]);
+        BTK_UNROLL
+        for (int ka = 1; ka < G::Ra; ka++) p[ka] = multw<S>(p[ka], w[ka]);
+        BTK_UNROLL
+        for (int ka = 0; ka < G::Ra; ka++) xb[ka * G::S2 + j] = p[ka];
+      }
+    }
+  }
+
+  // step 2 (only when Rb > 1): gather for pass B, radix-Rb, twiddle, scatter into exchange 2.
+  // Reads complete before the caller's barrier; writes must come after it (same buffer is reused),
+  // hence the split into step2_load / step2_store.
+  static BTK_HD void step2_load(cf* v, int gl, const cf* xb, const cf* tw) {
+    if (G::Rb > 1) {
+      BTK_UNROLL
+      for (int rep = 0; rep < G::RepB; rep++) {
+        const int iB = gl + G::L * rep;
+        const int ka = iB / G::Rc, nc = iB % G::Rc;
+        cf* p = v + rep * G::Rb;
+        BTK_UNROLL
+        for (int nb = 0; nb < G::Rb; nb++) p[nb] = xb[ka * G::S1 + nb * G::Rc + nc];
+        Dft<G::Rb, S>::run(p);
+        BTK_UNROLL
+        for (int kb = 0; kb < G::Rb; kb++) p[kb] = multw<S>(p[kb], tw[(nc * (ka + G::Ra * kb)) & (G::M - 1)]);
+      }
+    }
+  }
+  static BTK_HD void step2_store(const cf* v, int gl, cf* xb) {
+    if (G::Rb > 1) {
+      BTK_UNROLL
+      for (int rep = 0; rep < G::RepB; rep++) {
+        const int iB = gl + G::L * rep;
+        const int ka = iB / G::Rc, nc = iB % G::Rc;
+        BTK_UNROLL
+        for (int kb = 0; kb < G::Rb; kb++) xb[(ka + G::Ra * kb) * G::S2 + nc] = v[rep * G::Rb + kb];
+      }
+    }
+  }
+
+  // step 3: gather for pass C and radix-Rc; result in the canonical register layout.
+  static BTK_HD void step3(cf* v, int gl, const cf* xb) {
+    BTK_UNROLL
+    for (int rep = 0; rep < G::RepA; rep++) {
+      const int iC = gl + G::L * rep;
+      cf* p = v + rep * G::Rc;
+      BTK_UNROLL
+      for (int nc = 0; nc < G::Rc; nc++) p[nc] = xb[iC * G::S2 + nc];
+      Dft<G::Rc, S>::run(p);
+    }
+  }
+};
+
+}  // namespace btk

@@ -1,0 +1,120 @@
+// host_tables.h -- host-side (plain C++) preparation of the constant tables the kernels consume and
+// of the reference's setup-time formulas.  No CUDA here; shared by the C-ABI layer (capi.cu) and by the
+// CPU-only emulation tests.  Paths cited are relative to /root/reference/btk.
+#pragma once
+
+#include <math.h>
+#include <complex>
+#include <vector>
+
+#include "chain_tile.cuh"
+
+namespace btk {
+
+typedef std::complex<double> zd;
+
+// OverSampledDFTFilterBank ctor (modulated/modulated.cc:262-300): processing delay / look-ahead.
+struct BankGeom {
+  int M, m, r, dct, R, D, N, B, pd_a, pd_s, laN;
+  BankGeom() {}
+  BankGeom(int M_, int m_, int r_, int dct_) : M(M_), m(m_), r(r_), dct(dct_) {
+    R = 1 << r; D = M / R; N = M * m; B = M / 2 + 1;
+    laN = 0;
+    switch (dct) {
+      case 1: pd_a = pd_s = m * R - 1; break;
+      case 2: pd_a = m * R - 1; pd_s = m * R / 2; laN = m * R / 2 - 1; break;
+      default: pd_a = pd_s = 2 * m - 1; break;
+    }
+  }
+  // SampleFeature::next (feature/feature.cc:627-641): ceil(T/D) blocks, last zero padded
+  int nblk(long long T) const { return (int)((T + D - 1) / D); }
+  // modulated.cc:461-516: nblk real + pd padded frames, laN internal frames skipped
+  int analysis_frames(long long T) const { return nblk(T) + pd_a - laN; }
+  // modulated.cc:626-642: pd_s frames consumed by priming, then one output per input frame
+  int synthesis_frames(int F) const { return F > pd_s ? F - pd_s : 0; }
+};
+
+inline void build_twiddles(int M, std::vector<cf>& tw) {
+  tw.resize(M);
+  for (int t = 0; t < M; t++) {
+    const double a = 2.0 * M_PI * (double)t / (double)M;
+    tw[t] = mk((float)cos(a), (float)sin(a));
+  }
+}
+
+// gp[k][q] = g[M-1-q + M k]  (polyphase(_M - m - 1, k), modulated.cc:649)
+inline void build_synthesis_taps(const double* g, int M, int m, std::vector<float>& gp) {
+  gp.resize((size_t)M * m);
+  for (int k = 0; k < m; k++)
+    for (int q = 0; q < M; q++) gp[(size_t)k * M + q] = (float)g[M - 1 - q + M * k];
+}
+
+// beamformerWeights::calcMainlobe, halfBandShift == false (beamformer/beamformer.cc:531-594).
+// w: [B][C].
+inline void ds_weights(const double* delays, double fs, int M, int C, std::vector<zd>& w) {
+  const int B = M / 2 + 1;
+  w.assign((size_t)B * C, zd(0, 0));
+  for (int c = 0; c < C; c++) w[c] = zd(1.0 / C, 0.0);
+  for (int s = 1; s < M / 2; s++)
+    for (int c = 0; c < C; c++) {
+      const double val = -2.0 * M_PI * s * delays[c] * fs / M;
+      w[(size_t)s * C + c] = zd(cos(val) / C, sin(val) / C);
+    }
+  for (int c = 0; c < C; c++) {
+    const double val = -M_PI * fs * delays[c];
+    w[(size_t)(M / 2) * C + c] = zd(cos(val) / C, sin(val) / C);
+  }
+}
+
+// Hermitian-extended conjugate weight table for the fused chain (see chain_tile.cuh header):
+//   gam[c][k] = conj(w[k][c]) for 0 < k < M/2 ; gam[c][M-k] = w[k][c] ; real part only at k = 0, M/2.
+inline void build_chain_weight_table(const zd* w, int M, int C, int Cpad, std::vector<cf>& gam) {
+  gam.assign((size_t)Cpad * M, mk(0.f, 0.f));
+  for (int c = 0; c < C; c++) {
+    cf* row = &gam[(size_t)c * M];
+    row[0] = mk((float)w[c].real(), 0.f);
+    row[M / 2] = mk((float)w[(size_t)(M / 2) * C + c].real(), 0.f);
+    for (int k = 1; k < M / 2; k++) {
+      const zd v = w[(size_t)k * C + c];
+      row[k] = mk((float)v.real(), (float)-v.imag());
+      row[M - k] = mk((float)v.real(), (float)v.imag());
+    }
+  }
+}
+
+// SubbandMVDR::setDiffuseNoiseModel (beamformer/beamformer.cc:2486-2553): Gamma_mn = sinc(2 fs s d_mn/(M c)),
+// normalised sinc, unit diagonal.  Rn: [B][C][C].
+inline double norm_sinc(double x) {
+  if (fabs(x) < 1e-8) return 1.0 - (M_PI * M_PI * x * x) / 6.0;
+  return sin(M_PI * x) / (M_PI * x);
+}
+inline void diffuse_model(const double* micpos, int C, double fs, double sspeed, int M, std::vector<zd>& Rn) {
+  const int B = M / 2 + 1;
+  Rn.assign((size_t)B * C * C, zd(0, 0));
+  for (int s = 0; s < B; s++) {
+    const double omega_d_c = 2.0 * fs * s / (M * sspeed);
+    for (int a = 0; a < C; a++)
+      for (int b = 0; b < C; b++) {
+        double v = 1.0;
+        if (a != b) {
+          const double dx = micpos[a * 3] - micpos[b * 3], dy = micpos[a * 3 + 1] - micpos[b * 3 + 1],
+                       dz = micpos[a * 3 + 2] - micpos[b * 3 + 2];
+          v = norm_sinc(omega_d_c * sqrt(dx * dx + dy * dy + dz * dz));
+        }
+        Rn[((size_t)s * C + a) * C + b] = zd(v, 0.0);
+      }
+  }
+}
+
+// Split every recording's nblk output frames into chunks of at most `chunk` frames.
+inline void build_work(const std::vector<RecDesc>& recs, int chunk, std::vector<WorkItem>& work) {
+  work.clear();
+  for (size_t r = 0; r < recs.size(); r++)
+    for (int j0 = 0; j0 < recs[r].nblk; j0 += chunk) {
+      WorkItem w;
+      w.rec = (int)r; w.j0 = j0; w.nj = recs[r].nblk - j0 < chunk ? recs[r].nblk - j0 : chunk;
+      work.push_back(w);
+    }
+}
+
+}  // namespace btk

@@ -1,0 +1,154 @@
+// staged_tiles.cuh -- the reference's stage boundaries materialised: analysis bank -> snapshots,
+// and beamformer output -> synthesis bank, built from the same pieces as the fused chain
+// (chain_tile.cuh).  Used when a caller asks for the subband snapshots / beamformer outputs
+// themselves (the drop-in stream nodes, covariance estimation, the parity tests on X and Y).
+//
+//   analysis_tile : pcm [T][C]  -> snapshots [F][B][C] complex64, channel innermost -- the layout
+//                   SnapShotArray::update produces (reference beamformer/beamformer.cc:82-90)
+//   synthesis_tile: Y [F][B] complex64 (bins 0..M/2; the upper half is the conjugate mirror the
+//                   reference's beamformers write, beamformer.cc:1189-1194) -> float PCM
+#pragma once
+
+#include "chain_tile.cuh"
+
+namespace btk {
+
+struct AnalysisParams {
+  const float* pcm;
+  cf* snap;               // [F][B][C] per recording at recs[].out_off (complex elements)
+  const RecDesc* recs;    // nblk field = number of emitted analysis frames F
+  const WorkItem* work;   // j0/nj = first emitted frame / count (multiple of W except the last)
+  const float* taps_h;
+  const cf* tw;
+  int C, Cpad, m, laN;
+};
+
+template <int M_, int R_, class Ctx>
+BTK_HD void analysis_tile(Ctx& ctx, const AnalysisParams& p, unsigned char* smem, int work_id) {
+  typedef ChainCfg<M_, R_> K;
+  typedef typename K::G G;
+  typedef ChainThreadState<M_> TS;
+  const int m = p.m, N = M_ * m, B = M_ / 2 + 1;
+  const ChainSmem L = chain_smem_layout<M_, R_>(m);
+  cf* s_tw = reinterpret_cast<cf*>(smem + L.tw);
+  float* s_taps = reinterpret_cast<float*>(smem + L.taps);
+  float* s_xs = reinterpret_cast<float*>(smem + L.xs);
+  cf* s_xbuf = reinterpret_cast<cf*>(smem + L.xbuf);
+
+  const WorkItem wk = p.work[work_id];
+  const RecDesc rec = p.recs[wk.rec];
+  const float* pcm = p.pcm + rec.pcm_off;
+  cf* snap = p.snap + rec.out_off;
+  const int C = p.C, F = rec.nblk;
+  const int n_it = (wk.nj + K::W - 1) / K::W;
+  const bool vec4 = (C % 4 == 0) && (rec.pcm_off % 4 == 0);
+
+  ctx.par([&](int tid, TS&) {
+    for (int i = tid; i < M_; i += K::NT) s_tw[i] = p.tw[i];
+    for (int i = tid; i < N; i += K::NT) s_taps[i] = p.taps_h[i];
+  });
+  ctx.sync();
+
+  for (int it = 0; it < n_it; it++) {
+    const int f_base = wk.j0 + it * K::W;          // emitted frame index t; internal frame i = t + laN
+    const long long t_lo = (long long)(f_base + p.laN + 1) * K::D - N;
+    for (int cg0 = 0; cg0 < p.Cpad; cg0 += K::CG) {
+      stage_window<M_, R_>(ctx, L, s_xs, pcm, C, rec.T, t_lo, cg0, vec4);
+      ctx.sync();
+      for (int round = 0; round < K::CG / K::NG; round++) {
+        analysis_round<M_, R_>(ctx, L, s_xs, s_taps, s_xbuf, s_tw, m, round);
+        ctx.syncwarp();
+        // Z = X_f0 + j X_f1 in natural order through the exchange buffer, so every lane can reach Z[M-k]
+        ctx.par([&](int tid, TS& ts) {
+          const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+          cf* xb = s_xbuf + (warp * K::NG + grp) * G::XBUF;
+          BTK_UNROLL
+          for (int r = 0; r < G::V; r++) xb[G::index_of(gl, r)] = ts.z[r];
+        });
+        ctx.syncwarp();
+        ctx.par([&](int tid, TS& ts) {
+          const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+          const cf* xb = s_xbuf + (warp * K::NG + grp) * G::XBUF;
+          const int c = cg0 + round * K::NG + grp;
+          const int f0 = f_base + 2 * warp, f1 = f0 + 1;
+          const bool ok0 = c < C && f0 < wk.j0 + wk.nj && f0 < F, ok1 = c < C && f1 < wk.j0 + wk.nj && f1 < F;
+          BTK_UNROLL
+          for (int r = 0; r < G::V; r++) {
+            const int k = G::index_of(gl, r);
+            if (k > M_ / 2) continue;
+            const cf zk = ts.z[r];
+            const cf zm = xb[(M_ - k) & (M_ - 1)];
+            // X_f0[k] = (Z[k] + conj Z[M-k]) / 2 ;  X_f1[k] = (Z[k] - conj Z[M-k]) / (2j)
+            if (ok0) snap[((long long)f0 * B + k) * C + c] = mk(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+            if (ok1) snap[((long long)f1 * B + k) * C + c] = mk(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x));
+          }
+        });
+        ctx.syncwarp();
+      }
+      ctx.sync();
+    }
+  }
+}
+
+struct SynthesisParams {
+  const cf* Y;            // [F][B] per recording at recs[].pcm_off (complex elements)
+  float* out;
+  const RecDesc* recs;    // T field = F (frames available), nblk = number of output frames
+  const WorkItem* work;
+  const float* taps_g;
+  const cf* tw;
+  int m, pd_s, gain;
+};
+
+template <int M_, int R_, class Ctx>
+BTK_HD void synthesis_tile(Ctx& ctx, const SynthesisParams& p, unsigned char* smem, int work_id) {
+  typedef ChainCfg<M_, R_> K;
+  typedef typename K::G G;
+  typedef ChainThreadState<M_> TS;
+  const int m = p.m, B = M_ / 2 + 1;
+  const int H = m * R_ - 1;
+  const ChainSmem L = chain_smem_layout<M_, R_>(m);
+  cf* s_tw = reinterpret_cast<cf*>(smem + L.tw);
+  cf* s_xbuf = reinterpret_cast<cf*>(smem + L.xbuf);
+  float* s_v = reinterpret_cast<float*>(smem + L.vbuf);
+
+  const WorkItem wk = p.work[work_id];
+  const RecDesc rec = p.recs[wk.rec];
+  const cf* Y = p.Y + rec.pcm_off;
+  float* out = p.out + rec.out_off;
+  const int F = rec.T;
+  const int a_start = wk.j0 + p.pd_s - H;
+  const int n_it = (wk.nj + H + K::W - 1) / K::W;
+
+  ctx.par([&](int tid, TS&) {
+    for (int i = tid; i < M_; i += K::NT) s_tw[i] = p.tw[i];
+  });
+  ctx.sync();
+
+  for (int it = 0; it < n_it; it++) {
+    const int tau_base = a_start + it * K::W;
+    // G = Y_tau0 + j Y_tau1 over all M bins, Hermitian-extended, real at k = 0 and M/2
+    ctx.par([&](int tid, TS& ts) {
+      const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+      if (grp != 0) return;
+      const int tau0 = tau_base + 2 * warp, tau1 = tau0 + 1;
+      const bool ok0 = tau0 >= 0 && tau0 < F, ok1 = tau1 >= 0 && tau1 < F;
+      BTK_UNROLL
+      for (int r = 0; r < G::V; r++) {
+        const int k = G::index_of(gl, r);
+        const int kk = k <= M_ / 2 ? k : M_ - k;
+        cf a = ok0 ? Y[(long long)tau0 * B + kk] : mk(0.f, 0.f);
+        cf b = ok1 ? Y[(long long)tau1 * B + kk] : mk(0.f, 0.f);
+        if (k > M_ / 2) { a.y = -a.y; b.y = -b.y; }
+        if (k == 0 || k == M_ / 2) { a.y = 0.f; b.y = 0.f; }
+        ts.g[r] = mk(a.x - b.y, a.y + b.x);
+      }
+    });
+    synth_transform_store<M_, R_>(ctx, L, s_xbuf, s_tw, s_v, it, tau_base);
+    ctx.sync();
+    synth_emit<M_, R_>(ctx, L, p.taps_g, s_v, out, m, p.pd_s, p.gain, it, tau_base, wk.j0, wk.nj);
+    ctx.sync();
+  }
+}
+
+}  // namespace btk
