@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the hot path (analysis -> SubbandDS -> synthesis) in channel-audio-seconds/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the fused chain over this rank's batch of synthetic array recordings
+(BASELINE.json configs[1] by default: 8-mic circular array, SubbandDS, M=256 m=4 r=1, 16 kHz, 60 s).
+Recordings are independent, so ranks share nothing on the data path (weak scaling: fixed batch per GPU);
+torch.distributed is only used for the barrier and the max-over-ranks time.
+
+  value      device-resident: inputs already in HBM, CUDA events around K launches on the launching stream
+  e2e        through the host-buffer C-ABI call (btkb200_chain_batch): pinned host buffers, H2D of every
+             input and D2H of every output inside the timed region
+  roofline   algorithmic bytes of the fused chain (4 C T + 4 nblk D per recording) / launch time,
+             against the measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline  the reference's own CPU chain (oracle/_ref, compiled from /root/reference) on the host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+FS = 16000.0
+METRIC = "channel-audio-seconds/sec (analysis+beamform+synthesis)"
+UNIT = "channel-s/s"
+
+WORKLOADS = {
+    # name: (M, m, r, C, seconds, utterances per GPU, geometry, description)
+    "cfg2": dict(M=256, m=4, r=1, C=8, seconds=60.0, batch=16, geom="circular",
+                 desc="BASELINE configs[1]: 8-mic circular array SubbandDS, M=256 m=4 r=1, 16 kHz, 60 s source at known DOA"),
+    "cfg3": dict(M=512, m=2, r=2, C=16, seconds=10.0, batch=64, geom="linear41",
+                 desc="BASELINE configs[2] geometry: 16-mic linear array, fixed-weight MVDR/DS apply, M=512 m=2 r=2, 16 kHz, 10 s"),
+    "cfg4": dict(M=512, m=2, r=2, C=64, seconds=10.0, batch=32, geom="linear20",
+                 desc="BASELINE configs[3] geometry: 64-ch Mark-III-style array, M=512 m=2 r=2, 16 kHz, 10 s utterances"),
+}
+
+
+def prototypes(M, m, r):
+    import btk_b200
+
+    P = np.load(os.path.join(ROOT, "tests", "golden", "prototypes.npz"))
+    key = f"h_{M}_{m}_{r}"
+    if key in P.files:
+        return P[key], P[f"g_{M}_{m}_{r}"]
+    return btk_b200.workloads.kaiser_prototype(M, m, r)
+
+
+def geometry(wl_cfg):
+    import btk_b200
+
+    wl = btk_b200.workloads
+    C = wl_cfg["C"]
+    if wl_cfg["geom"] == "circular":
+        mp_ = wl.circular_array(C, 100.0)
+        tau = wl.farfield_delays(mp_, np.deg2rad(60.0), np.deg2rad(90.0))
+    else:
+        mp_ = wl.linear_array(C, 41.0 if wl_cfg["geom"] == "linear41" else 20.0)
+        tau = wl.farfield_delays(mp_, np.deg2rad(30.0), np.deg2rad(90.0))
+    return mp_, tau
+
+
+def make_recording(wl_cfg, tau, index, config_id=2):
+    import btk_b200
+
+    T = int(round(wl_cfg["seconds"] * FS))
+    return btk_b200.workloads.array_recording(T, tau, seed=20240 + 1000 * config_id + index)
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md clocks line)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for row in self.rows:
+            f = [x.strip() for x in row.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- CPU reference arm
+def _cpu_worker(args):
+    """One single-threaded process per host core (the reference has no threading and global pools)."""
+    wl_cfg, indices, use_ref = args
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull, 1)   # the reference's constructors chat on stdout
+    os.dup2(devnull, 2)
+    import btk_oracle as bo
+
+    M, m, r, C = wl_cfg["M"], wl_cfg["m"], wl_cfg["r"], wl_cfg["C"]
+    h, g = prototypes(M, m, r)
+    geo = bo.BankGeometry(M, m, r, 0)
+    _, tau = geometry(wl_cfg)
+    ref = bo.CompiledReference() if use_ref else None
+    W = None if use_ref else bo.ds_weights(tau, FS, M)
+    pcms = [make_recording(wl_cfg, tau, i) for i in indices]
+    t0 = time.perf_counter()
+    for pcm in pcms:
+        if use_ref:
+            ref.chain(pcm, h, g, geo, tau, want_snap=False, want_Y=False)
+        else:
+            bo.chain(pcm, h, g, geo, W)
+    return time.perf_counter() - t0, len(pcms)
+
+
+def cpu_chain_rate(wl_cfg, seconds_per_rec, recs_per_core, cores, pool):
+    """channel-audio-seconds per second of the reference CPU chain using `cores` processes."""
+    import btk_oracle as bo
+
+    use_ref = bo.CompiledReference.available()
+    sample_cfg = dict(wl_cfg, seconds=seconds_per_rec)
+    jobs = [(sample_cfg, list(range(k * recs_per_core, (k + 1) * recs_per_core)), use_ref) for k in range(cores)]
+    t0 = time.perf_counter()
+    res = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    busy = max(r[0] for r in res)          # generation of the inputs is outside each worker's timer
+    units = sum(r[1] for r in res) * wl_cfg["C"] * seconds_per_rec
+    return units / busy, ("reference" if use_ref else "port"), wall
+
+
+def run_reference_arm(args, wl_cfg, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    secs = wl_cfg["seconds"]
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        for _ in range(args.warmup):
+            cpu_chain_rate(wl_cfg, 1.0, 1, cores, pool)
+        rates, kind = [], "port"
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            rate, kind, _ = cpu_chain_rate(wl_cfg, secs, 1, cores, pool)
+            rates.append(rate)
+        total = time.perf_counter() - t0
+    value = float(np.mean(rates))
+    sample = f"{cores} processes x 1 recording of {wl_cfg['C']} ch x {secs:g} s per step ({kind}: " + (
+        "oracle/_ref = reference .cc files compiled -O2, GSL-radix-2 branch" if kind == "reference" else "numpy restatement") + ")"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * total / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(wl_cfg, args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(wl_cfg, args):
+    return {"workload": wl_cfg["desc"], "channels": wl_cfg["C"], "M": wl_cfg["M"], "m": wl_cfg["m"], "r": wl_cfg["r"],
+            "fs": FS, "seconds_per_utterance": wl_cfg["seconds"], "utterances_per_gpu": wl_cfg["batch"],
+            "beamformer": "SubbandDS (delay-and-sum at the true DOA)", "parallelism": f"{args.gpus} independent shards, no collective",
+            "l2": "per-step input+output exceeds the 126 MB L2 (no flush needed)"}
+
+
+# --------------------------------------------------------------------------------------------- our arm
+def run_ours(args, wl_cfg, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    import btk_b200
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device visible; the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    M, m, r, C, nb = wl_cfg["M"], wl_cfg["m"], wl_cfg["r"], wl_cfg["C"], wl_cfg["batch"]
+    T = int(round(wl_cfg["seconds"] * FS))
+    h, g = prototypes(M, m, r)
+    _, tau = geometry(wl_cfg)
+    plan = btk_b200.Plan(M, m, r, C, h, g, device=local_rank)
+    plan.set_ds_weights(FS, tau)
+    nblk, D = plan.nblk(T), plan.D
+    n_in, n_out = T * C, nblk * D
+
+    # this rank's shard of the job: recordings rank*nb .. rank*nb+nb-1 (weak scaling), a few distinct signals reused
+    distinct = min(nb, 4)
+    base = [make_recording(wl_cfg, tau, rank * nb + i) for i in range(distinct)]
+    h_in = torch.empty((nb, n_in), dtype=torch.float32, pin_memory=True)
+    h_out = torch.empty((nb, n_out), dtype=torch.float32, pin_memory=True)
+    for i in range(nb):
+        h_in[i].copy_(torch.from_numpy(base[i % distinct].reshape(-1)))
+    d_in = h_in.to(dev)
+    d_out = torch.zeros((nb, n_out), dtype=torch.float32, device=dev)
+    pcm_off = np.arange(nb, dtype=np.int64) * n_in
+    out_off = np.arange(nb, dtype=np.int64) * n_out
+    Ts = np.full(nb, T, dtype=np.int64)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_dev():
+        plan.chain_batch_dev(d_in.data_ptr(), pcm_off, Ts, out_off, d_out.data_ptr(), stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    units_per_step = nb * C * wl_cfg["seconds"]              # channel-audio-seconds this rank processes per step
+    alg_bytes = nb * (4.0 * C * T + 4.0 * nblk * D)           # SURVEY 8d fused-chain bytes per launch
+
+    # ---- device-resident timing
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = plan.launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_begin.record()
+    for a, b in evs:
+        a.record()
+        step_dev()
+        b.record()
+    t_end.record()
+    barrier()
+    launches = plan.launch_count() - l0
+    total_ms = t_begin.elapsed_time(t_end)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    clocks = sampler.stop()
+
+    # ---- end to end through the host-buffer C-ABI call (H2D + kernels + D2H inside)
+    xs = [h_in[i].numpy().reshape(T, C) for i in range(nb)]
+    outs = [h_out[i].numpy() for i in range(nb)]
+    e2e_steps = max(2, min(args.steps, 5))
+    plan.chain_batch_into(xs, outs)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        plan.chain_batch_into(xs, outs)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    checksum = float(h_out[0, : 4 * D].double().abs().sum())
+    if not np.isfinite(checksum) or checksum == 0.0:
+        raise SystemExit("bench.py: end-to-end output is empty or not finite")
+    same = bool(torch.allclose(d_out[0].cpu(), h_out[0], rtol=0, atol=0))
+
+    # ---- max over ranks
+    tt = torch.tensor([total_ms, kern_ms, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms, kern_ms, e2e_s = [float(v) for v in tt.tolist()]
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "of measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "of fallback (B200_PROFILING.md)"
+        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+        ms_per_step = total_ms / args.steps
+        value = world * units_per_step / (ms_per_step * 1e-3)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(args.workload)
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(wl_cfg, args),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms,
+                         "kernel": f"btk_chain_kernel<{M},{1 << r}>",
+                         "fp32_note": "fused chain is FP32-issue bound before HBM for M>=256 (SURVEY 8d); see DESIGN.md"},
+            "e2e": {"value": world * units_per_step / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(nb * n_in * 4),
+                    "d2h_bytes_per_step": int(nb * n_out * 4), "ms_per_step": e2e_s * 1e3,
+                    "matches_device_resident_output": same},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            ctx = mp.get_context("spawn")
+            with ctx.Pool(cores) as pool:
+                secs = wl_cfg["seconds"]
+                rate, kind, wall = cpu_chain_rate(wl_cfg, secs, 2, cores, pool)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": f"{cores} single-threaded processes x 2 recordings of {C} ch x {secs:g} s "
+                                              f"(same chain, same prototype; {wall:.1f} s wall)"}
+        print(json.dumps(line), flush=True)
+    plan.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="utterances per GPU (default: per workload)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl_cfg = dict(WORKLOADS[args.workload])
+    if args.batch > 0:
+        wl_cfg["batch"] = args.batch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, wl_cfg, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args, wl_cfg, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

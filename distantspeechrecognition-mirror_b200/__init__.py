@@ -1,0 +1,11 @@
+"""distantspeechrecognition-mirror_b200: B200-native (sm_100a) subband front end of the Beamforming Toolkit --
+OverSampledDFTAnalysisBank -> SubbandDS / SubbandMVDR -> OverSampledDFTSynthesisBank -- behind the
+reference's stream API.
+
+The directory name carries a hyphen (it mirrors the upstream repository name); import it through the
+``btk_b200`` shim at the repository root:  ``import btk_b200``.
+"""
+from . import _capi, workloads  # noqa: F401
+from ._capi import BtkError, Plan, device_count, lib  # noqa: F401
+
+__all__ = ["Plan", "BtkError", "device_count", "lib", "workloads"]

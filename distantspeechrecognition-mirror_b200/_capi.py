@@ -1,0 +1,316 @@
+"""ctypes binding of include/btkb200.h (libbtkb200.so, built in-tree by csrc/Makefile).
+
+This is plumbing only: every number is produced by the sm_100a kernels behind the C ABI.  There is no
+CPU fallback -- if the library is missing or no GPU is visible the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_long, c_longlong, c_size_t, c_uint, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbtkb200.so")
+
+OK, EINVAL, ESTATE, ECUDA, ENOMEM, EUNSUPPORTED = 0, 1, 2, 3, 4, 5
+
+# every symbol include/btkb200.h declares (checked by tests/test_capi_symbols.py)
+SYMBOLS = [
+    "btkb200_device_count", "btkb200_version", "btkb200_last_error", "btkb200_plan_create", "btkb200_plan_destroy",
+    "btkb200_plan_info", "btkb200_nblk", "btkb200_analysis_frames", "btkb200_synthesis_frames",
+    "btkb200_set_ds_weights", "btkb200_set_weights", "btkb200_get_weights", "btkb200_get_manifold",
+    "btkb200_set_covariance", "btkb200_get_covariance", "btkb200_set_diffuse_noise_model", "btkb200_diag_load",
+    "btkb200_diag_load_bin", "btkb200_divide_nondiagonal", "btkb200_solve_mvdr", "btkb200_analysis",
+    "btkb200_beamform", "btkb200_synthesis", "btkb200_covariance", "btkb200_chain", "btkb200_chain_batch",
+    "btkb200_chain_batch_multi", "btkb200_chain_batch_dev", "btkb200_analysis_dev", "btkb200_beamform_dev",
+    "btkb200_synthesis_dev", "btkb200_launch_count", "btkb200_sync", "btkb200_host_alloc", "btkb200_host_free",
+]
+
+
+class Info(ctypes.Structure):
+    _fields_ = [(n, c_uint) for n in ("M", "m", "r", "R", "D", "N", "B", "C", "dct", "pd_analysis", "pd_synthesis",
+                                      "laN")] + [("device", c_int), ("has_weights", c_int)]
+
+
+class BtkError(RuntimeError):
+    """A non-zero status from the C ABI.  ``code`` is one of EINVAL/ESTATE/ECUDA/ENOMEM/EUNSUPPORTED."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"btkb200 status {code}: {msg}")
+        self.code = code
+        self.msg = msg
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load libbtkb200.so (once).  Fails loudly when the extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `make -C {os.path.join(_HERE, 'csrc')}` "
+                          "(or __graft_entry__.build()).  There is no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    vp = c_void_p
+    L.btkb200_device_count.restype = c_int
+    L.btkb200_version.restype = c_char_p
+    L.btkb200_last_error.restype = c_char_p
+    L.btkb200_last_error.argtypes = [vp]
+    L.btkb200_plan_create.restype = c_int
+    L.btkb200_plan_create.argtypes = [POINTER(vp), c_uint, c_uint, c_uint, c_uint, c_uint, vp, vp, c_int, c_int]
+    L.btkb200_plan_destroy.restype = None
+    L.btkb200_plan_destroy.argtypes = [vp]
+    L.btkb200_plan_info.argtypes = [vp, POINTER(Info)]
+    for f in ("btkb200_nblk", "btkb200_analysis_frames", "btkb200_synthesis_frames"):
+        getattr(L, f).restype = c_long
+        getattr(L, f).argtypes = [vp, c_long]
+    L.btkb200_set_ds_weights.argtypes = [vp, c_double, vp, c_uint]
+    L.btkb200_set_weights.argtypes = [vp, vp]
+    L.btkb200_get_weights.argtypes = [vp, vp]
+    L.btkb200_get_manifold.argtypes = [vp, vp]
+    L.btkb200_set_covariance.argtypes = [vp, c_uint, vp, c_uint, c_uint]
+    L.btkb200_get_covariance.argtypes = [vp, c_uint, vp]
+    L.btkb200_set_diffuse_noise_model.argtypes = [vp, vp, c_uint, c_double, c_double]
+    L.btkb200_diag_load.argtypes = [vp, c_float]
+    L.btkb200_diag_load_bin.argtypes = [vp, c_uint, c_float]
+    L.btkb200_divide_nondiagonal.argtypes = [vp, c_float]
+    L.btkb200_solve_mvdr.argtypes = [vp, c_double, c_double, POINTER(c_int)]
+    L.btkb200_analysis.argtypes = [vp, vp, c_long, vp, POINTER(c_long)]
+    L.btkb200_beamform.argtypes = [vp, vp, c_long, vp]
+    L.btkb200_synthesis.argtypes = [vp, vp, c_long, vp, POINTER(c_long)]
+    L.btkb200_covariance.argtypes = [vp, vp, c_long, vp, c_int, vp]
+    L.btkb200_chain.argtypes = [vp, vp, c_long, vp]
+    L.btkb200_chain_batch.argtypes = [vp, POINTER(vp), POINTER(c_long), c_int, POINTER(vp)]
+    L.btkb200_chain_batch_multi.argtypes = [POINTER(vp), c_int, POINTER(vp), POINTER(c_long), c_int, POINTER(vp)]
+    L.btkb200_chain_batch_dev.argtypes = [vp, vp, POINTER(c_longlong), POINTER(c_longlong), POINTER(c_longlong), c_int,
+                                          vp, vp]
+    L.btkb200_analysis_dev.argtypes = [vp, vp, c_long, vp, vp]
+    L.btkb200_beamform_dev.argtypes = [vp, vp, c_long, vp, vp]
+    L.btkb200_synthesis_dev.argtypes = [vp, vp, c_long, vp, vp]
+    L.btkb200_launch_count.restype = c_long
+    L.btkb200_launch_count.argtypes = [vp]
+    L.btkb200_sync.argtypes = [vp]
+    L.btkb200_host_alloc.restype = vp
+    L.btkb200_host_alloc.argtypes = [c_size_t]
+    L.btkb200_host_free.restype = None
+    L.btkb200_host_free.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(c_void_p)
+
+
+class Plan:
+    """Owner of one ``btkb200_plan`` (geometry + prototypes + beamformer weights on one device)."""
+
+    def __init__(self, M: int, m: int, r: int, C: int, h=None, g=None, dct: int = 0, gain: int = 1, device: int = 0):
+        self._L = lib()
+        self._h = c_void_p()
+        hh = None if h is None else np.ascontiguousarray(h, dtype=np.float64)
+        gg = None if g is None else np.ascontiguousarray(g, dtype=np.float64)
+        for name, a in (("analysis", hh), ("synthesis", gg)):
+            if a is not None and a.size != M * m:
+                # OverSampledDFTFilterBank ctor: jconsistency_error (reference modulated/modulated.cc:269-271)
+                raise BtkError(EINVAL, f"Prototype sizes do not match ({a.size} vs. {M * m}).")
+        rc = self._L.btkb200_plan_create(ctypes.byref(self._h), M, m, r, dct, C, _p(hh), _p(gg), gain, device)
+        if rc != OK:
+            raise BtkError(rc, (self._L.btkb200_last_error(None) or b"").decode())
+        inf = Info()
+        self._L.btkb200_plan_info(self._h, ctypes.byref(inf))
+        self.info = inf
+        self.M, self.m, self.r, self.R, self.D, self.N, self.B, self.C = (inf.M, inf.m, inf.r, inf.R, inf.D, inf.N,
+                                                                          inf.B, inf.C)
+        self.pd_analysis, self.pd_synthesis, self.laN, self.device = inf.pd_analysis, inf.pd_synthesis, inf.laN, device
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.btkb200_plan_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc: int):
+        if rc != OK:
+            raise BtkError(rc, (self._L.btkb200_last_error(self._h) or b"").decode())
+
+    # -- geometry
+    def nblk(self, T: int) -> int:
+        return int(self._L.btkb200_nblk(self._h, T))
+
+    def analysis_frames(self, T: int) -> int:
+        return int(self._L.btkb200_analysis_frames(self._h, T))
+
+    def synthesis_frames(self, F: int) -> int:
+        return int(self._L.btkb200_synthesis_frames(self._h, F))
+
+    # -- weights
+    def set_ds_weights(self, fs: float, delays):
+        d = np.ascontiguousarray(delays, dtype=np.float64)
+        self._ck(self._L.btkb200_set_ds_weights(self._h, fs, _p(d), d.size))
+
+    def set_weights(self, W):
+        w = np.ascontiguousarray(W, dtype=np.complex128)
+        if w.shape != (self.B, self.C):
+            raise BtkError(EINVAL, f"weights must be [{self.B}][{self.C}], got {w.shape}")
+        self._ck(self._L.btkb200_set_weights(self._h, _p(w)))
+
+    def get_weights(self) -> np.ndarray:
+        w = np.zeros((self.B, self.C), dtype=np.complex128)
+        self._ck(self._L.btkb200_get_weights(self._h, _p(w)))
+        return w
+
+    def get_manifold(self) -> np.ndarray:
+        w = np.zeros((self.B, self.C), dtype=np.complex128)
+        self._ck(self._L.btkb200_get_manifold(self._h, _p(w)))
+        return w
+
+    # -- MVDR
+    def set_covariance(self, bin_: int, R):
+        Rm = np.ascontiguousarray(R, dtype=np.complex128)
+        if Rm.ndim != 2:
+            raise BtkError(EINVAL, "covariance must be a matrix")
+        self._ck(self._L.btkb200_set_covariance(self._h, bin_, _p(Rm), Rm.shape[0], Rm.shape[1]))
+
+    def get_covariance(self, bin_: int) -> np.ndarray:
+        R = np.zeros((self.C, self.C), dtype=np.complex128)
+        self._ck(self._L.btkb200_get_covariance(self._h, bin_, _p(R)))
+        return R
+
+    def set_diffuse_noise_model(self, micpos_mm, fs: float, sspeed: float = 343740.0):
+        mp = np.ascontiguousarray(micpos_mm, dtype=np.float64)
+        if mp.ndim != 2 or mp.shape[1] < 3:
+            raise BtkError(EINVAL, "The microphone positions should be described in the three dimensions")
+        mp = np.ascontiguousarray(mp[:, :3])
+        self._ck(self._L.btkb200_set_diffuse_noise_model(self._h, _p(mp), mp.shape[0], fs, sspeed))
+
+    def diag_load(self, w: float, bin_: int | None = None):
+        if bin_ is None:
+            self._ck(self._L.btkb200_diag_load(self._h, w))
+        else:
+            self._ck(self._L.btkb200_diag_load_bin(self._h, bin_, w))
+
+    def divide_nondiagonal(self, mu: float):
+        self._ck(self._L.btkb200_divide_nondiagonal(self._h, mu))
+
+    def solve_mvdr(self, fs: float = 16000.0, dThreshold: float = 1e-8) -> int:
+        nfb = c_int(0)
+        self._ck(self._L.btkb200_solve_mvdr(self._h, fs, dThreshold, ctypes.byref(nfb)))
+        return int(nfb.value)
+
+    # -- staged path (host numpy buffers)
+    def analysis(self, pcm) -> np.ndarray:
+        """pcm float32 [T][C] -> snapshots complex64 [F][B][C]."""
+        x = np.ascontiguousarray(pcm, dtype=np.float32)
+        if x.ndim == 1:
+            x = x[:, None]
+        if x.shape[1] != self.C:
+            raise BtkError(EINVAL, f"pcm has {x.shape[1]} channels, plan has {self.C}")
+        T = x.shape[0]
+        F = self.analysis_frames(T)
+        snap = np.empty((F, self.B, self.C), dtype=np.complex64)
+        n = c_long(0)
+        self._ck(self._L.btkb200_analysis(self._h, _p(x), T, _p(snap), ctypes.byref(n)))
+        return snap
+
+    def beamform(self, snap) -> np.ndarray:
+        s = np.ascontiguousarray(snap, dtype=np.complex64)
+        F = s.shape[0]
+        Y = np.empty((F, self.B), dtype=np.complex64)
+        self._ck(self._L.btkb200_beamform(self._h, _p(s), F, _p(Y)))
+        return Y
+
+    def synthesis(self, Y) -> np.ndarray:
+        y = np.ascontiguousarray(Y, dtype=np.complex64)
+        F = y.shape[0]
+        nout = self.synthesis_frames(F)
+        out = np.empty(nout * self.D, dtype=np.float32)
+        n = c_long(0)
+        self._ck(self._L.btkb200_synthesis(self._h, _p(y), F, _p(out), ctypes.byref(n)))
+        return out
+
+    def covariance(self, snap, frame_weights, conjugate: bool = True) -> np.ndarray:
+        s = np.ascontiguousarray(snap, dtype=np.complex64)
+        F = s.shape[0]
+        w = np.ascontiguousarray(frame_weights, dtype=np.float64)
+        if w.shape != (F,):
+            raise BtkError(EINVAL, "one weight per frame expected")
+        R = np.zeros((self.B, self.C, self.C), dtype=np.complex128)
+        self._ck(self._L.btkb200_covariance(self._h, _p(s), F, _p(w), 1 if conjugate else 0, _p(R)))
+        return R
+
+    # -- fused path (host numpy buffers)
+    def chain(self, pcm) -> np.ndarray:
+        x = np.ascontiguousarray(pcm, dtype=np.float32)
+        if x.ndim == 1:
+            x = x[:, None]
+        if x.shape[1] != self.C:
+            raise BtkError(EINVAL, f"pcm has {x.shape[1]} channels, plan has {self.C}")
+        out = np.empty(self.nblk(x.shape[0]) * self.D, dtype=np.float32)
+        self._ck(self._L.btkb200_chain(self._h, _p(x), x.shape[0], _p(out)))
+        return out
+
+    def chain_batch(self, pcms) -> list:
+        xs = [np.ascontiguousarray(x, dtype=np.float32) for x in pcms]
+        outs = [np.empty(self.nblk(x.shape[0]) * self.D, dtype=np.float32) for x in xs]
+        self.chain_batch_into(xs, outs)
+        return outs
+
+    def chain_batch_into(self, xs, outs):
+        """xs / outs: lists of C-contiguous float32 arrays (outs preallocated); no allocation here."""
+        n = len(xs)
+        pp = (c_void_p * n)(*[x.ctypes.data for x in xs])
+        oo = (c_void_p * n)(*[o.ctypes.data for o in outs])
+        TT = (c_long * n)(*[x.shape[0] for x in xs])
+        self._ck(self._L.btkb200_chain_batch(self._h, pp, TT, n, oo))
+
+    # -- device-resident variants (raw device pointers as ints, e.g. torch.Tensor.data_ptr())
+    def chain_batch_dev(self, d_pcm: int, pcm_off, T, out_off, d_out: int, stream: int = 0):
+        po = np.ascontiguousarray(pcm_off, dtype=np.int64)
+        tt = np.ascontiguousarray(T, dtype=np.int64)
+        oo = np.ascontiguousarray(out_off, dtype=np.int64)
+        LL = POINTER(c_longlong)
+        self._ck(self._L.btkb200_chain_batch_dev(self._h, d_pcm, po.ctypes.data_as(LL), tt.ctypes.data_as(LL),
+                                                 oo.ctypes.data_as(LL), po.size, d_out, stream))
+
+    def analysis_dev(self, d_pcm: int, T: int, d_snap: int, stream: int = 0):
+        self._ck(self._L.btkb200_analysis_dev(self._h, d_pcm, T, d_snap, stream))
+
+    def beamform_dev(self, d_snap: int, F: int, d_Y: int, stream: int = 0):
+        self._ck(self._L.btkb200_beamform_dev(self._h, d_snap, F, d_Y, stream))
+
+    def synthesis_dev(self, d_Y: int, F: int, d_out: int, stream: int = 0):
+        self._ck(self._L.btkb200_synthesis_dev(self._h, d_Y, F, d_out, stream))
+
+    def launch_count(self) -> int:
+        return int(self._L.btkb200_launch_count(self._h))
+
+    def sync(self):
+        self._ck(self._L.btkb200_sync(self._h))
+
+
+def device_count() -> int:
+    return int(lib().btkb200_device_count())
+
+
+def chain_batch_multi(plans, xs, outs):
+    """Round-robin the recordings over several plans (one per device); no inter-GPU traffic."""
+    L = lib()
+    n, npl = len(xs), len(plans)
+    hp = (c_void_p * npl)(*[p._h.value for p in plans])
+    pp = (c_void_p * n)(*[x.ctypes.data for x in xs])
+    oo = (c_void_p * n)(*[o.ctypes.data for o in outs])
+    TT = (c_long * n)(*[x.shape[0] for x in xs])
+    rc = L.btkb200_chain_batch_multi(hp, npl, pp, TT, n, oo)
+    if rc != OK:
+        raise BtkError(rc, "chain_batch_multi failed: " + "; ".join((L.btkb200_last_error(p._h) or b"").decode() for p in plans))

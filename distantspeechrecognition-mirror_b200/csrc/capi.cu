@@ -1,0 +1,586 @@
+// capi.cu -- the C ABI declared in include/btkb200.h: plan object, setup-time formulas (host, double),
+// buffer management and kernel launches.  No CPU compute path exists for the hot loops: every
+// analysis / beamform / synthesis / chain / covariance / solve call runs the sm_100a kernels or fails.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/btkb200.h"
+#include "host_tables.h"
+#include "launch.h"
+
+using namespace btk;
+
+static thread_local std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+    cudaError_t e = cudaMallocHost(&p, bytes + 256);
+    if (e == cudaSuccess) cap = bytes + 256;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct btkb200_plan {
+  BankGeom geo;
+  int C = 0, Cpad = 0, gain = 1, device = 0;
+  bool has_h = false, has_g = false;
+  int has_weights = 0;      // 0 none, 1 DS, 2 user/MVDR
+  bool has_manifold = false;
+  std::vector<zd> w, wq, Rn;
+  std::vector<char> Rn_set;
+  // device constants
+  float* d_taps_h = nullptr;
+  float* d_taps_g = nullptr;
+  cf* d_tw = nullptr;
+  cf* d_wts_chain = nullptr;   // [Cpad][M]
+  cf* d_w = nullptr;           // [B][C]
+  // scratch
+  DevBuf d_recs, d_work, d_in, d_out, d_aux, d_aux2;
+  PinBuf h_desc;
+  std::vector<long long> sig;  // signature of the cached chain work list
+  int cached_n_work = 0;
+  cudaStream_t stream = nullptr;
+  long launches = 0;
+  std::string err;
+};
+
+static int fail(btkb200_plan* p, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (p) p->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CK(plan, call)                                                                             \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail(plan, BTKB200_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+static int upload_weights(btkb200_plan* p) {
+  const int M = p->geo.M, B = p->geo.B, C = p->C;
+  CK(p, cudaSetDevice(p->device));
+  std::vector<cf> gam;
+  build_chain_weight_table(p->w.data(), M, C, p->Cpad, gam);
+  std::vector<cf> plain((size_t)B * C);
+  for (size_t i = 0; i < plain.size(); i++) plain[i] = mk((float)p->w[i].real(), (float)p->w[i].imag());
+  // ordered after any kernel still reading the previous tables
+  CK(p, cudaStreamSynchronize(p->stream));
+  CK(p, cudaMemcpy(p->d_wts_chain, gam.data(), gam.size() * sizeof(cf), cudaMemcpyHostToDevice));
+  CK(p, cudaMemcpy(p->d_w, plain.data(), plain.size() * sizeof(cf), cudaMemcpyHostToDevice));
+  return BTKB200_OK;
+}
+
+// chunk of output frames per CTA: enough CTAs to fill 148 SMs several times over, but long enough
+// that the (m R - 1)-frame warm-up of the synthesis history stays a small fraction.
+static int choose_chunk(long long total_frames, int H, int W) {
+  const long long target_ctas = 148LL * 2 * 4;
+  long long chunk = (total_frames + target_ctas - 1) / target_ctas;
+  if (chunk < 3LL * W) chunk = 3LL * W;
+  if (chunk > 64LL * W) chunk = 64LL * W;
+  // make chunk + H a multiple of W so no iteration is partly wasted
+  long long its = (chunk + H + W - 1) / W;
+  chunk = its * W - H;
+  if (chunk < 1) chunk = W;
+  return (int)chunk;
+}
+
+extern "C" {
+
+int btkb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return -1;
+  return n;
+}
+
+const char* btkb200_version(void) { return "btkb200 0.1 (sm_100a)"; }
+
+const char* btkb200_last_error(const btkb200_plan* plan) { return plan ? plan->err.c_str() : g_create_error.c_str(); }
+
+int btkb200_plan_create(btkb200_plan** out, unsigned M, unsigned m, unsigned r, unsigned dct, unsigned C,
+                        const double* h, const double* g, int gain, int device) {
+  if (!out) return fail(nullptr, BTKB200_EINVAL, "plan pointer is NULL");
+  *out = nullptr;
+  if (M == 0 || m == 0 || C == 0 || r > 8) return fail(nullptr, BTKB200_EINVAL, "bad geometry M=%u m=%u r=%u C=%u", M, m, r, C);
+  const int R = 1 << r;
+  if (!fb_supported((int)M, R) || (M % R) != 0)
+    return fail(nullptr, BTKB200_EUNSUPPORTED, "no kernel for M=%u, R=%d (supported: M in {64,128,256,512,1024}, r in 0..3)", M, R);
+  const int smem = fb_smem_bytes((int)M, R, (int)m);
+  if (smem < 0 || smem > 227 * 1024)
+    return fail(nullptr, BTKB200_EUNSUPPORTED, "prototype too long for shared memory staging: M=%u m=%u needs %d bytes", M, m, smem);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return fail(nullptr, BTKB200_ECUDA, "no CUDA device available (this library has no CPU path)");
+  if (device < 0 || device >= ndev) return fail(nullptr, BTKB200_EINVAL, "device %d out of range (%d visible)", device, ndev);
+  btkb200_plan* p = new btkb200_plan();
+  p->geo = BankGeom((int)M, (int)m, (int)r, (int)dct);
+  p->C = (int)C;
+  p->Cpad = ((int)C + 3) / 4 * 4;
+  p->gain = gain;
+  p->device = device;
+  const int N = p->geo.N, B = p->geo.B;
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_taps_h, N * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_taps_g, N * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_tw, M * sizeof(cf));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_wts_chain, (size_t)p->Cpad * M * sizeof(cf));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_w, (size_t)B * C * sizeof(cf));
+  if (e == cudaSuccess) {
+    std::vector<float> hf(N, 0.f), gp(N, 0.f);
+    std::vector<cf> tw;
+    if (h) { for (int i = 0; i < N; i++) hf[i] = (float)h[i]; p->has_h = true; }
+    if (g) { build_synthesis_taps(g, (int)M, (int)m, gp); p->has_g = true; }
+    build_twiddles((int)M, tw);
+    e = cudaMemcpy(p->d_taps_h, hf.data(), N * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_taps_g, gp.data(), N * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_tw, tw.data(), M * sizeof(cf), cudaMemcpyHostToDevice);
+  }
+  if (e != cudaSuccess) {
+    fail(nullptr, BTKB200_ECUDA, "plan_create: %s", cudaGetErrorString(e));
+    btkb200_plan_destroy(p);
+    return BTKB200_ECUDA;
+  }
+  p->w.assign((size_t)B * C, zd(0, 0));
+  p->wq.assign((size_t)B * C, zd(0, 0));
+  p->Rn.assign((size_t)B * C * C, zd(0, 0));
+  p->Rn_set.assign(B, 0);
+  *out = p;
+  return BTKB200_OK;
+}
+
+void btkb200_plan_destroy(btkb200_plan* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  if (p->stream) cudaStreamSynchronize(p->stream);
+  cudaFree(p->d_taps_h); cudaFree(p->d_taps_g); cudaFree(p->d_tw); cudaFree(p->d_wts_chain); cudaFree(p->d_w);
+  p->d_recs.release(); p->d_work.release(); p->d_in.release(); p->d_out.release(); p->d_aux.release(); p->d_aux2.release();
+  p->h_desc.release();
+  if (p->stream) cudaStreamDestroy(p->stream);
+  delete p;
+}
+
+int btkb200_plan_info(const btkb200_plan* p, btkb200_info* info) {
+  if (!p || !info) return BTKB200_EINVAL;
+  info->M = p->geo.M; info->m = p->geo.m; info->r = p->geo.r; info->R = p->geo.R; info->D = p->geo.D;
+  info->N = p->geo.N; info->B = p->geo.B; info->C = p->C; info->dct = p->geo.dct;
+  info->pd_analysis = p->geo.pd_a; info->pd_synthesis = p->geo.pd_s; info->laN = p->geo.laN;
+  info->device = p->device; info->has_weights = p->has_weights;
+  return BTKB200_OK;
+}
+
+long btkb200_nblk(const btkb200_plan* p, long T) { return p ? p->geo.nblk(T) : -1; }
+long btkb200_analysis_frames(const btkb200_plan* p, long T) { return p ? p->geo.analysis_frames(T) : -1; }
+long btkb200_synthesis_frames(const btkb200_plan* p, long F) { return p ? p->geo.synthesis_frames((int)F) : -1; }
+
+// ------------------------------------------------------------------------------------------- weights
+int btkb200_set_ds_weights(btkb200_plan* p, double fs, const double* delays, unsigned n) {
+  if (!p || !delays) return BTKB200_EINVAL;
+  if ((int)n != p->C)
+    return fail(p, BTKB200_EINVAL, "Number of delays does not match number of channels (%u vs. %d).", n, p->C);
+  ds_weights(delays, fs, p->geo.M, p->C, p->wq);
+  p->has_manifold = true;
+  p->w = p->wq;
+  p->has_weights = 1;
+  return upload_weights(p);
+}
+
+int btkb200_set_weights(btkb200_plan* p, const double* w) {
+  if (!p || !w) return BTKB200_EINVAL;
+  for (size_t i = 0; i < p->w.size(); i++) p->w[i] = zd(w[2 * i], w[2 * i + 1]);
+  p->has_weights = 2;
+  return upload_weights(p);
+}
+
+int btkb200_get_weights(const btkb200_plan* p, double* w) {
+  if (!p || !w) return BTKB200_EINVAL;
+  if (!p->has_weights) return fail(const_cast<btkb200_plan*>(p), BTKB200_ESTATE, "no weights installed");
+  for (size_t i = 0; i < p->w.size(); i++) { w[2 * i] = p->w[i].real(); w[2 * i + 1] = p->w[i].imag(); }
+  return BTKB200_OK;
+}
+
+int btkb200_get_manifold(const btkb200_plan* p, double* w) {
+  if (!p || !w) return BTKB200_EINVAL;
+  if (!p->has_manifold) return fail(const_cast<btkb200_plan*>(p), BTKB200_ESTATE, "call calcArrayManifoldVectorsX() once");
+  for (size_t i = 0; i < p->wq.size(); i++) { w[2 * i] = p->wq[i].real(); w[2 * i + 1] = p->wq[i].imag(); }
+  return BTKB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------- MVDR setup
+int btkb200_set_covariance(btkb200_plan* p, unsigned bin, const double* R, unsigned rows, unsigned cols) {
+  if (!p || !R) return BTKB200_EINVAL;
+  if ((int)rows != p->C || (int)cols != p->C)
+    return fail(p, BTKB200_EINVAL, "The spatial spectral matrix must be %d x %d but it is %u x %u", p->C, p->C, rows, cols);
+  if ((int)bin >= p->geo.B) return fail(p, BTKB200_EINVAL, "bin %u out of range (0..%d)", bin, p->geo.B - 1);
+  const size_t CC = (size_t)p->C * p->C;
+  for (size_t i = 0; i < CC; i++) p->Rn[bin * CC + i] = zd(R[2 * i], R[2 * i + 1]);
+  p->Rn_set[bin] = 1;
+  return BTKB200_OK;
+}
+
+int btkb200_get_covariance(const btkb200_plan* p, unsigned bin, double* R) {
+  if (!p || !R || (int)bin >= p->geo.B) return BTKB200_EINVAL;
+  if (!p->Rn_set[bin]) return fail(const_cast<btkb200_plan*>(p), BTKB200_ESTATE, "no spatial spectral matrix for bin %u", bin);
+  const size_t CC = (size_t)p->C * p->C;
+  for (size_t i = 0; i < CC; i++) { R[2 * i] = p->Rn[bin * CC + i].real(); R[2 * i + 1] = p->Rn[bin * CC + i].imag(); }
+  return BTKB200_OK;
+}
+
+int btkb200_set_diffuse_noise_model(btkb200_plan* p, const double* micpos, unsigned n_mics, double fs, double sspeed) {
+  if (!p || !micpos) return BTKB200_EINVAL;
+  if ((int)n_mics != p->C)
+    return fail(p, BTKB200_EINVAL, "The number of microphones must be %d but it is %u", p->C, n_mics);
+  diffuse_model(micpos, p->C, fs, sspeed, p->geo.M, p->Rn);
+  std::fill(p->Rn_set.begin(), p->Rn_set.end(), 1);
+  return BTKB200_OK;
+}
+
+int btkb200_diag_load_bin(btkb200_plan* p, unsigned bin, float w) {
+  if (!p || (int)bin >= p->geo.B) return BTKB200_EINVAL;
+  if (!p->Rn_set[bin]) return fail(p, BTKB200_ESTATE, "Construct first a noise covariance matrix");
+  const size_t C = p->C;
+  // the weight is stored as float before it is added (beamformer.cc:2342, 2562-2565)
+  for (size_t c = 0; c < C; c++) p->Rn[(bin * C + c) * C + c] += zd((double)w, 0.0);
+  return BTKB200_OK;
+}
+
+int btkb200_diag_load(btkb200_plan* p, float w) {
+  if (!p) return BTKB200_EINVAL;
+  for (int s = 0; s < p->geo.B; s++) {
+    int rc = btkb200_diag_load_bin(p, (unsigned)s, w);
+    if (rc != BTKB200_OK) return rc;
+  }
+  return BTKB200_OK;
+}
+
+int btkb200_divide_nondiagonal(btkb200_plan* p, float mu) {
+  if (!p) return BTKB200_EINVAL;
+  const size_t C = p->C;
+  const double den = 1.0 + (double)mu;   // (1.0+myu) with a float myu, beamformer.h:371-376
+  for (int s = 0; s < p->geo.B; s++) {
+    if (!p->Rn_set[s]) return fail(p, BTKB200_ESTATE, "Construct first a noise covariance matrix");
+    for (size_t a = 0; a < C; a++)
+      for (size_t b = 0; b < C; b++)
+        if (a != b) p->Rn[((size_t)s * C + a) * C + b] /= den;
+  }
+  return BTKB200_OK;
+}
+
+int btkb200_solve_mvdr(btkb200_plan* p, double /*sample_rate: unused by the reference too*/, double dThreshold,
+                       int* n_fallback) {
+  if (!p) return BTKB200_EINVAL;
+  if (!p->Rn_set[0]) return fail(p, BTKB200_ESTATE, "Set a spatial spectral matrix before calling calcMVDRWeights()");
+  if (!p->has_manifold) return fail(p, BTKB200_ESTATE, "call calcArrayManifoldVectorsX() once");
+  const int B = p->geo.B, C = p->C;
+  for (int s = 1; s < B; s++)
+    if (!p->Rn_set[s]) return fail(p, BTKB200_ESTATE, "no spatial spectral matrix for bin %d", s);
+  if (C > 64) return fail(p, BTKB200_EUNSUPPORTED, "MVDR solve supports at most 64 channels (got %d)", C);
+  CK(p, cudaSetDevice(p->device));
+  const size_t nR = (size_t)B * C * C, nW = (size_t)B * C;
+  CK(p, p->d_aux.reserve(nR * sizeof(double2) + 2 * nW * sizeof(double2) + B * sizeof(int)));
+  double2* dR = (double2*)p->d_aux.p;
+  double2* dd = dR + nR;
+  double2* dw = dd + nW;
+  int* dfb = (int*)(dw + nW);
+  CK(p, cudaMemcpyAsync(dR, p->Rn.data(), nR * sizeof(double2), cudaMemcpyHostToDevice, p->stream));
+  CK(p, cudaMemcpyAsync(dd, p->wq.data(), nW * sizeof(double2), cudaMemcpyHostToDevice, p->stream));
+  CK(p, launch_mvdr_solve(dR, dd, dw, dfb, B, C, dThreshold, p->stream));
+  p->launches++;
+  std::vector<zd> wnew(nW);
+  std::vector<int> fb(B);
+  CK(p, cudaMemcpyAsync(wnew.data(), dw, nW * sizeof(double2), cudaMemcpyDeviceToHost, p->stream));
+  CK(p, cudaMemcpyAsync(fb.data(), dfb, B * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+  CK(p, cudaStreamSynchronize(p->stream));
+  int nfb = 0;
+  for (int s = 0; s < B; s++) nfb += fb[s];
+  if (n_fallback) *n_fallback = nfb;
+  p->w = wnew;
+  p->has_weights = 2;
+  return upload_weights(p);
+}
+
+// ------------------------------------------------------------------------------------------- staged (device)
+static int upload_desc(btkb200_plan* p, const std::vector<RecDesc>& recs, const std::vector<WorkItem>& work,
+                       cudaStream_t st) {
+  const size_t br = recs.size() * sizeof(RecDesc), bw = work.size() * sizeof(WorkItem);
+  CK(p, p->d_recs.reserve(br));
+  CK(p, p->d_work.reserve(bw));
+  CK(p, p->h_desc.reserve(br + bw));
+  memcpy(p->h_desc.p, recs.data(), br);
+  memcpy((char*)p->h_desc.p + br, work.data(), bw);
+  CK(p, cudaMemcpyAsync(p->d_recs.p, p->h_desc.p, br, cudaMemcpyHostToDevice, st));
+  CK(p, cudaMemcpyAsync(p->d_work.p, (char*)p->h_desc.p + br, bw, cudaMemcpyHostToDevice, st));
+  // the pinned staging area is reused by the next call: make sure the copies have left it
+  CK(p, cudaStreamSynchronize(st));
+  return BTKB200_OK;
+}
+
+int btkb200_analysis_dev(btkb200_plan* p, const float* d_pcm, long T, float* d_snap, void* stream) {
+  if (!p || !d_pcm || !d_snap || T < 0) return BTKB200_EINVAL;
+  if (!p->has_h) return fail(p, BTKB200_ESTATE, "plan was created without an analysis prototype");
+  CK(p, cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int F = p->geo.analysis_frames(T);
+  std::vector<RecDesc> recs(1);
+  recs[0].pcm_off = 0; recs[0].out_off = 0; recs[0].T = (int)T; recs[0].nblk = F;
+  std::vector<WorkItem> work;
+  const int W = fb_frames_per_iter(p->geo.M, p->geo.R);
+  long long chunk = ((long long)F + 148 * 4 - 1) / (148 * 4);
+  chunk = (chunk + W - 1) / W * W;
+  if (chunk < W) chunk = W;
+  build_work(recs, (int)chunk, work);
+  p->sig.clear();
+  int rc = upload_desc(p, recs, work, st);
+  if (rc) return rc;
+  AnalysisParams a;
+  a.pcm = d_pcm; a.snap = (cf*)d_snap; a.recs = (const RecDesc*)p->d_recs.p; a.work = (const WorkItem*)p->d_work.p;
+  a.taps_h = p->d_taps_h; a.tw = p->d_tw; a.C = p->C; a.Cpad = p->Cpad; a.m = p->geo.m; a.laN = p->geo.laN;
+  if (!work.empty()) { CK(p, launch_analysis(p->geo.M, p->geo.R, a, (int)work.size(), st)); p->launches++; }
+  return BTKB200_OK;
+}
+
+int btkb200_beamform_dev(btkb200_plan* p, const float* d_snap, long F, float* d_Y, void* stream) {
+  if (!p || !d_snap || !d_Y || F < 0) return BTKB200_EINVAL;
+  if (!p->has_weights) return fail(p, BTKB200_ESTATE, "call calcArrayManifoldVectorsX() once");
+  CK(p, cudaSetDevice(p->device));
+  if (F > 0) { CK(p, launch_beamform((const cf*)d_snap, p->d_w, (cf*)d_Y, F, p->geo.B, p->C, (cudaStream_t)stream)); p->launches++; }
+  return BTKB200_OK;
+}
+
+int btkb200_synthesis_dev(btkb200_plan* p, const float* d_Y, long F, float* d_out, void* stream) {
+  if (!p || !d_Y || !d_out || F < 0) return BTKB200_EINVAL;
+  if (!p->has_g) return fail(p, BTKB200_ESTATE, "plan was created without a synthesis prototype");
+  CK(p, cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nout = p->geo.synthesis_frames((int)F);
+  if (nout == 0) return BTKB200_OK;
+  std::vector<RecDesc> recs(1);
+  recs[0].pcm_off = 0; recs[0].out_off = 0; recs[0].T = (int)F; recs[0].nblk = nout;
+  std::vector<WorkItem> work;
+  const int W = fb_frames_per_iter(p->geo.M, p->geo.R), H = p->geo.m * p->geo.R - 1;
+  build_work(recs, choose_chunk(nout, H, W), work);
+  p->sig.clear();
+  int rc = upload_desc(p, recs, work, st);
+  if (rc) return rc;
+  SynthesisParams s;
+  s.Y = (const cf*)d_Y; s.out = d_out; s.recs = (const RecDesc*)p->d_recs.p; s.work = (const WorkItem*)p->d_work.p;
+  s.taps_g = p->d_taps_g; s.tw = p->d_tw; s.m = p->geo.m; s.pd_s = p->geo.pd_s; s.gain = p->gain;
+  CK(p, launch_synthesis(p->geo.M, p->geo.R, s, (int)work.size(), st));
+  p->launches++;
+  return BTKB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------- fused (device)
+int btkb200_chain_batch_dev(btkb200_plan* p, const float* d_pcm, const long long* pcm_off, const long long* T,
+                            const long long* out_off, int n, float* d_out, void* stream) {
+  if (!p || !d_pcm || !d_out || !pcm_off || !T || !out_off || n < 0) return BTKB200_EINVAL;
+  if (!p->has_weights) return fail(p, BTKB200_ESTATE, "call calcArrayManifoldVectorsX() once");
+  if (!p->has_h || !p->has_g) return fail(p, BTKB200_ESTATE, "the fused chain needs both prototypes");
+  if (n == 0) return BTKB200_OK;
+  CK(p, cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<long long> sig;
+  sig.reserve(3 * (size_t)n + 1);
+  sig.push_back(n);
+  for (int i = 0; i < n; i++) { sig.push_back(pcm_off[i]); sig.push_back(T[i]); sig.push_back(out_off[i]); }
+  if (sig != p->sig) {
+    std::vector<RecDesc> recs(n);
+    long long total = 0;
+    for (int i = 0; i < n; i++) {
+      if (T[i] < 0 || T[i] > 0x7fffffffLL) return fail(p, BTKB200_EINVAL, "recording %d: bad length %lld", i, T[i]);
+      recs[i].pcm_off = pcm_off[i]; recs[i].out_off = out_off[i]; recs[i].T = (int)T[i]; recs[i].nblk = p->geo.nblk(T[i]);
+      total += recs[i].nblk;
+    }
+    std::vector<WorkItem> work;
+    const int W = fb_frames_per_iter(p->geo.M, p->geo.R), H = p->geo.m * p->geo.R - 1;
+    build_work(recs, choose_chunk(total, H, W), work);
+    int rc = upload_desc(p, recs, work, st);
+    if (rc) return rc;
+    p->sig = sig;
+    p->cached_n_work = (int)work.size();
+  }
+  if (p->cached_n_work == 0) return BTKB200_OK;
+  ChainParams c;
+  c.pcm = d_pcm; c.out = d_out; c.recs = (const RecDesc*)p->d_recs.p; c.work = (const WorkItem*)p->d_work.p;
+  c.taps_h = p->d_taps_h; c.taps_g = p->d_taps_g; c.wts = p->d_wts_chain; c.tw = p->d_tw;
+  c.C = p->C; c.Cpad = p->Cpad; c.m = p->geo.m; c.pd_s = p->geo.pd_s; c.laN = p->geo.laN; c.gain = p->gain;
+  CK(p, launch_chain(p->geo.M, p->geo.R, c, p->cached_n_work, st));
+  p->launches++;
+  return BTKB200_OK;
+}
+
+long btkb200_launch_count(const btkb200_plan* p) { return p ? p->launches : -1; }
+
+int btkb200_sync(btkb200_plan* p) {
+  if (!p) return BTKB200_EINVAL;
+  CK(p, cudaSetDevice(p->device));
+  CK(p, cudaDeviceSynchronize());
+  return BTKB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------- host-buffer entry points
+int btkb200_analysis(btkb200_plan* p, const float* pcm, long T, float* snap, long* n_frames) {
+  if (!p || !pcm || !snap || T < 0) return BTKB200_EINVAL;
+  CK(p, cudaSetDevice(p->device));
+  const long F = p->geo.analysis_frames(T);
+  const size_t bin = (size_t)T * p->C * sizeof(float), bout = (size_t)F * p->geo.B * p->C * sizeof(cf);
+  CK(p, p->d_in.reserve(bin ? bin : 16));
+  CK(p, p->d_out.reserve(bout ? bout : 16));
+  if (bin) CK(p, cudaMemcpyAsync(p->d_in.p, pcm, bin, cudaMemcpyHostToDevice, p->stream));
+  int rc = btkb200_analysis_dev(p, (const float*)p->d_in.p, T, (float*)p->d_out.p, p->stream);
+  if (rc) return rc;
+  if (bout) CK(p, cudaMemcpyAsync(snap, p->d_out.p, bout, cudaMemcpyDeviceToHost, p->stream));
+  CK(p, cudaStreamSynchronize(p->stream));
+  if (n_frames) *n_frames = F;
+  return BTKB200_OK;
+}
+
+int btkb200_beamform(btkb200_plan* p, const float* snap, long F, float* Y) {
+  if (!p || !snap || !Y || F < 0) return BTKB200_EINVAL;
+  if (!p->has_weights) return fail(p, BTKB200_ESTATE, "call calcArrayManifoldVectorsX() once");
+  CK(p, cudaSetDevice(p->device));
+  const size_t bin = (size_t)F * p->geo.B * p->C * sizeof(cf), bout = (size_t)F * p->geo.B * sizeof(cf);
+  if (F == 0) return BTKB200_OK;
+  CK(p, p->d_in.reserve(bin));
+  CK(p, p->d_out.reserve(bout));
+  CK(p, cudaMemcpyAsync(p->d_in.p, snap, bin, cudaMemcpyHostToDevice, p->stream));
+  int rc = btkb200_beamform_dev(p, (const float*)p->d_in.p, F, (float*)p->d_out.p, p->stream);
+  if (rc) return rc;
+  CK(p, cudaMemcpyAsync(Y, p->d_out.p, bout, cudaMemcpyDeviceToHost, p->stream));
+  CK(p, cudaStreamSynchronize(p->stream));
+  return BTKB200_OK;
+}
+
+int btkb200_synthesis(btkb200_plan* p, const float* Y, long F, float* out, long* n_out_frames) {
+  if (!p || !Y || !out || F < 0) return BTKB200_EINVAL;
+  CK(p, cudaSetDevice(p->device));
+  const long nout = p->geo.synthesis_frames((int)F);
+  if (n_out_frames) *n_out_frames = nout;
+  if (nout == 0) return p->has_g ? BTKB200_OK : fail(p, BTKB200_ESTATE, "plan was created without a synthesis prototype");
+  const size_t bin = (size_t)F * p->geo.B * sizeof(cf), bout = (size_t)nout * p->geo.D * sizeof(float);
+  CK(p, p->d_in.reserve(bin));
+  CK(p, p->d_out.reserve(bout));
+  CK(p, cudaMemcpyAsync(p->d_in.p, Y, bin, cudaMemcpyHostToDevice, p->stream));
+  int rc = btkb200_synthesis_dev(p, (const float*)p->d_in.p, F, (float*)p->d_out.p, p->stream);
+  if (rc) return rc;
+  CK(p, cudaMemcpyAsync(out, p->d_out.p, bout, cudaMemcpyDeviceToHost, p->stream));
+  CK(p, cudaStreamSynchronize(p->stream));
+  return BTKB200_OK;
+}
+
+int btkb200_covariance(btkb200_plan* p, const float* snap, long F, const double* frame_weights, int conjugate, double* R) {
+  if (!p || !snap || !frame_weights || !R || F < 0) return BTKB200_EINVAL;
+  if (p->C > 64) return fail(p, BTKB200_EUNSUPPORTED, "covariance supports at most 64 channels (got %d)", p->C);
+  CK(p, cudaSetDevice(p->device));
+  const int B = p->geo.B, C = p->C;
+  const size_t bsnap = (size_t)F * B * C * sizeof(cf), bw = (size_t)F * sizeof(double), bR = (size_t)B * C * C * sizeof(double2);
+  CK(p, p->d_in.reserve(bsnap ? bsnap : 16));
+  CK(p, p->d_aux2.reserve(bw + 16 + bR));
+  double* dwt = (double*)p->d_aux2.p;
+  double2* dR = (double2*)((char*)p->d_aux2.p + ((bw + 15) / 16) * 16);
+  CK(p, cudaMemsetAsync(dR, 0, bR, p->stream));
+  if (F > 0) {
+    CK(p, cudaMemcpyAsync(p->d_in.p, snap, bsnap, cudaMemcpyHostToDevice, p->stream));
+    CK(p, cudaMemcpyAsync(dwt, frame_weights, bw, cudaMemcpyHostToDevice, p->stream));
+    CK(p, launch_covariance((const cf*)p->d_in.p, dwt, dR, F, B, C, conjugate ? 1 : 0, p->stream));
+    p->launches++;
+  }
+  CK(p, cudaMemcpyAsync(R, dR, bR, cudaMemcpyDeviceToHost, p->stream));
+  CK(p, cudaStreamSynchronize(p->stream));
+  return BTKB200_OK;
+}
+
+int btkb200_chain_batch(btkb200_plan* p, const float* const* pcm, const long* T, int n, float* const* out) {
+  if (!p || !pcm || !T || !out || n < 0) return BTKB200_EINVAL;
+  if (!p->has_weights) return fail(p, BTKB200_ESTATE, "call calcArrayManifoldVectorsX() once");
+  if (n == 0) return BTKB200_OK;
+  CK(p, cudaSetDevice(p->device));
+  std::vector<long long> poff(n), ooff(n), Tl(n);
+  long long pin = 0, pout = 0;
+  for (int i = 0; i < n; i++) {
+    if (T[i] < 0 || !pcm[i] || !out[i]) return fail(p, BTKB200_EINVAL, "recording %d: bad buffer or length", i);
+    poff[i] = pin; ooff[i] = pout; Tl[i] = T[i];
+    pin += ((long long)T[i] * p->C + 3) / 4 * 4;            // keep every recording 16-byte aligned for float4 loads
+    pout += ((long long)p->geo.nblk(T[i]) * p->geo.D + 3) / 4 * 4;
+  }
+  CK(p, p->d_in.reserve((size_t)(pin ? pin : 4) * sizeof(float)));
+  CK(p, p->d_out.reserve((size_t)(pout ? pout : 4) * sizeof(float)));
+  for (int i = 0; i < n; i++)
+    if (T[i] > 0)
+      CK(p, cudaMemcpyAsync((float*)p->d_in.p + poff[i], pcm[i], (size_t)T[i] * p->C * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+  int rc = btkb200_chain_batch_dev(p, (const float*)p->d_in.p, poff.data(), Tl.data(), ooff.data(), n, (float*)p->d_out.p, p->stream);
+  if (rc) return rc;
+  for (int i = 0; i < n; i++) {
+    const size_t b = (size_t)p->geo.nblk(T[i]) * p->geo.D * sizeof(float);
+    if (b) CK(p, cudaMemcpyAsync(out[i], (float*)p->d_out.p + ooff[i], b, cudaMemcpyDeviceToHost, p->stream));
+  }
+  CK(p, cudaStreamSynchronize(p->stream));
+  return BTKB200_OK;
+}
+
+int btkb200_chain(btkb200_plan* p, const float* pcm, long T, float* out) {
+  const float* pp[1] = {pcm};
+  float* oo[1] = {out};
+  long TT[1] = {T};
+  return btkb200_chain_batch(p, pp, TT, 1, oo);
+}
+
+int btkb200_chain_batch_multi(btkb200_plan* const* plans, int n_plans, const float* const* pcm, const long* T, int n,
+                              float* const* out) {
+  if (!plans || n_plans <= 0 || !pcm || !T || !out || n < 0) return BTKB200_EINVAL;
+  // round-robin partition; every device's share is enqueued before any is waited for
+  std::vector<std::vector<const float*> > sp(n_plans);
+  std::vector<std::vector<float*> > so(n_plans);
+  std::vector<std::vector<long> > sT(n_plans);
+  for (int i = 0; i < n; i++) { sp[i % n_plans].push_back(pcm[i]); so[i % n_plans].push_back(out[i]); sT[i % n_plans].push_back(T[i]); }
+  // Host-buffer entry points synchronise their own stream at the end, so issue the shares from
+  // one host thread per device.
+  int rc_all = BTKB200_OK;
+#pragma omp parallel for num_threads(n_plans) if (n_plans > 1)
+  for (int d = 0; d < n_plans; d++) {
+    if (sp[d].empty()) continue;
+    int rc = btkb200_chain_batch(plans[d], sp[d].data(), sT[d].data(), (int)sp[d].size(), so[d].data());
+    if (rc != BTKB200_OK) {
+#pragma omp critical
+      rc_all = rc;
+    }
+  }
+  return rc_all;
+}
+
+void* btkb200_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+  return p;
+}
+
+void btkb200_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

@@ -1,0 +1,3 @@
+// kern_m1024.cu -- filter-bank kernels for M = 1024 (all decimation factors R = 1, 2, 4, 8).
+#include "kern_fb.cuh"
+BTK_DEFINE_M_LAUNCHERS(1024)

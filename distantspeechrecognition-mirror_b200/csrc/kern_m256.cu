@@ -1,0 +1,3 @@
+// kern_m256.cu -- filter-bank kernels for M = 256 (all decimation factors R = 1, 2, 4, 8).
+#include "kern_fb.cuh"
+BTK_DEFINE_M_LAUNCHERS(256)

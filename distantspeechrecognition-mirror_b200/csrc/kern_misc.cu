@@ -1,0 +1,257 @@
+// kern_misc.cu -- per-M dispatch glue + the subband-domain kernels that are not filter banks:
+// weight apply on stored snapshots, weighted spatial covariance accumulation, per-bin MVDR solve.
+#include "launch.h"
+
+namespace btk {
+
+#define BTK_DECL_M(MM)                                                                                \
+  cudaError_t launch_chain_m##MM(int R, const ChainParams& p, int n_work, cudaStream_t st);           \
+  cudaError_t launch_analysis_m##MM(int R, const AnalysisParams& p, int n_work, cudaStream_t st);     \
+  cudaError_t launch_synthesis_m##MM(int R, const SynthesisParams& p, int n_work, cudaStream_t st);   \
+  int fb_smem_bytes_m##MM(int R, int m);
+BTK_DECL_M(64) BTK_DECL_M(128) BTK_DECL_M(256) BTK_DECL_M(512) BTK_DECL_M(1024)
+#undef BTK_DECL_M
+
+bool fb_supported(int M, int R) {
+  if (R != 1 && R != 2 && R != 4 && R != 8) return false;
+  switch (M) {
+    case 64: case 128: return R <= 8;       // first radix 8
+    case 256: case 512: case 1024: return R <= 8;
+  }
+  return false;
+}
+
+#define BTK_DISPATCH(fn, ...)                               \
+  switch (M) {                                              \
+    case 64: return fn##_m64(__VA_ARGS__);                  \
+    case 128: return fn##_m128(__VA_ARGS__);                \
+    case 256: return fn##_m256(__VA_ARGS__);                \
+    case 512: return fn##_m512(__VA_ARGS__);                \
+    case 1024: return fn##_m1024(__VA_ARGS__);              \
+  }
+
+cudaError_t launch_chain(int M, int R, const ChainParams& p, int n_work, cudaStream_t st) {
+  if (!fb_supported(M, R)) return cudaErrorInvalidValue;
+  BTK_DISPATCH(launch_chain, R, p, n_work, st)
+  return cudaErrorInvalidValue;
+}
+cudaError_t launch_analysis(int M, int R, const AnalysisParams& p, int n_work, cudaStream_t st) {
+  if (!fb_supported(M, R)) return cudaErrorInvalidValue;
+  BTK_DISPATCH(launch_analysis, R, p, n_work, st)
+  return cudaErrorInvalidValue;
+}
+cudaError_t launch_synthesis(int M, int R, const SynthesisParams& p, int n_work, cudaStream_t st) {
+  if (!fb_supported(M, R)) return cudaErrorInvalidValue;
+  BTK_DISPATCH(launch_synthesis, R, p, n_work, st)
+  return cudaErrorInvalidValue;
+}
+int fb_smem_bytes(int M, int R, int m) {
+  if (!fb_supported(M, R)) return -1;
+  BTK_DISPATCH(fb_smem_bytes, R, m)
+  return -1;
+}
+int fb_frames_per_iter(int, int) { return 16; }  // ChainCfg::W (2 * NW), identical for every instantiation
+
+// ---------------------------------------------------------------------------------------------
+// Weight apply on stored snapshots: one thread per (frame, bin), channels innermost and contiguous.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) btk_beamform_kernel(const cf* __restrict__ snap, const cf* __restrict__ w,
+                                                          cf* __restrict__ Y, long long FB, int B, int C) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < FB;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int s = (int)(idx % B);
+    const cf* x = snap + idx * C;
+    const cf* ws = w + (long long)s * C;
+    float re = 0.f, im = 0.f;
+    for (int c = 0; c < C; c++) {
+      const cf a = ws[c], b = x[c];     // conj(a) * b
+      re = fmaf(a.x, b.x, re); re = fmaf(a.y, b.y, re);
+      im = fmaf(a.x, b.y, im); im = fmaf(-a.y, b.x, im);
+    }
+    Y[idx] = mk(re, im);
+  }
+}
+
+cudaError_t launch_beamform(const cf* snap, const cf* w, cf* Y, long long F, int B, int C, cudaStream_t st) {
+  const long long FB = F * B;
+  if (FB == 0) return cudaSuccess;
+  long long blocks = (FB + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  btk_beamform_kernel<<<(int)blocks, 256, 0, st>>>(snap, w, Y, FB, B, C);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weighted Gram matrices.  grid = (B bins, SPLIT frame slices); each CTA stages FB frames of its bin in
+// shared memory and every thread owns a strided set of (i, j) pairs with double accumulators; slices are
+// merged with double atomics into Rout (zeroed by the caller).
+// ---------------------------------------------------------------------------------------------
+#define BTK_COV_FB 32
+#define BTK_COV_MAXPAIRS 16
+__global__ void __launch_bounds__(256) btk_covariance_kernel(const cf* __restrict__ snap, const double* __restrict__ wt,
+                                                            double2* __restrict__ Rout, long long F, int B, int C,
+                                                            int conj) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cf* sx = reinterpret_cast<cf*>(smem_raw);              // [FB][C]
+  float* sw = reinterpret_cast<float*>(sx + BTK_COV_FB * C);
+  const int s = blockIdx.x;
+  const long long per = (F + gridDim.y - 1) / gridDim.y;
+  const long long f_lo = per * blockIdx.y, f_hi = (f_lo + per < F) ? f_lo + per : F;
+  const int npair = C * C;
+  double ar[BTK_COV_MAXPAIRS], ai[BTK_COV_MAXPAIRS];
+#pragma unroll
+  for (int k = 0; k < BTK_COV_MAXPAIRS; k++) { ar[k] = 0.0; ai[k] = 0.0; }
+  for (long long f0 = f_lo; f0 < f_hi; f0 += BTK_COV_FB) {
+    const int nf = (int)((f_hi - f0 < BTK_COV_FB) ? f_hi - f0 : BTK_COV_FB);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nf * C; i += blockDim.x) {
+      const int ff = i / C, c = i % C;
+      sx[i] = snap[((f0 + ff) * B + s) * C + c];
+    }
+    for (int i = threadIdx.x; i < nf; i += blockDim.x) sw[i] = (float)wt[f0 + i];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BTK_COV_MAXPAIRS; k++) {
+      const int pr = threadIdx.x + k * 256;
+      if (pr < npair) {
+        const int i = pr / C, j = pr % C;
+        float pre = 0.f, pim = 0.f;   // fp32 partial over <= 32 frames, promoted to double per batch
+        for (int ff = 0; ff < nf; ff++) {
+          const cf a = sx[ff * C + i];
+          cf b = sx[ff * C + j];
+          if (conj) b.y = -b.y;
+          const float wgt = sw[ff];
+          pre = fmaf(wgt, fmaf(a.x, b.x, -a.y * b.y), pre);
+          pim = fmaf(wgt, fmaf(a.x, b.y, a.y * b.x), pim);
+        }
+        ar[k] += (double)pre; ai[k] += (double)pim;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < BTK_COV_MAXPAIRS; k++) {
+    const int pr = threadIdx.x + k * 256;
+    if (pr < npair) {
+      double2* dst = Rout + (long long)s * npair + pr;
+      atomicAdd(&dst->x, ar[k]);
+      atomicAdd(&dst->y, ai[k]);
+    }
+  }
+}
+
+cudaError_t launch_covariance(const cf* snap, const double* wt, double2* Rout, long long F, int B, int C, int conj,
+                              cudaStream_t st) {
+  if (C * C > 256 * BTK_COV_MAXPAIRS) return cudaErrorInvalidValue;   // C <= 64
+  if (F == 0) return cudaSuccess;
+  int split = (int)((F + 511) / 512);
+  if (split < 1) split = 1;
+  if (split > 64) split = 64;
+  const size_t smem = (size_t)BTK_COV_FB * C * sizeof(cf) + BTK_COV_FB * sizeof(float);
+  btk_covariance_kernel<<<dim3(B, split), 256, smem, st>>>(snap, wt, Rout, F, B, C, conj);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// MVDR weights, one CTA per bin (beamformer.cc:2392-2446):  t = (R^H)^{-1} d ; lam = t^H d ; w = t/(lam C).
+// Pivoted Gaussian elimination on the augmented system [R^H | d] in complex double in shared memory.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 zmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ double2 zdiv(double2 a, double2 b) {
+  const double d = b.x * b.x + b.y * b.y;
+  return make_double2((a.x * b.x + a.y * b.y) / d, (a.y * b.x - a.x * b.y) / d);
+}
+
+__global__ void __launch_bounds__(128) btk_mvdr_solve_kernel(const double2* __restrict__ Rn, const double2* __restrict__ dvec,
+                                                            double2* __restrict__ w, int* __restrict__ fallback, int C,
+                                                            double dThreshold) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* A = reinterpret_cast<double2*>(smem_raw);       // [C][C+1]
+  __shared__ int s_piv;
+  __shared__ int s_bad;
+  const int s = blockIdx.x, ld = C + 1, tid = threadIdx.x, nt = blockDim.x;
+  const double2* d = dvec + (long long)s * C;
+  double2* ws = w + (long long)s * C;
+  if (s == 0) {   // w[0] = (1, ..., 1), beamformer.cc:2410-2415
+    for (int c = tid; c < C; c += nt) ws[c] = make_double2(1.0, 0.0);
+    if (tid == 0) fallback[0] = 0;
+    return;
+  }
+  const double2* Rs = Rn + (long long)s * C * C;
+  for (int i = tid; i < C * C; i += nt) {
+    const int r = i / C, c = i % C;
+    const double2 v = Rs[c * C + r];                        // (R^H)[r][c] = conj(R[c][r])
+    A[r * ld + c] = make_double2(v.x, -v.y);
+  }
+  for (int r = tid; r < C; r += nt) A[r * ld + C] = d[r];
+  if (tid == 0) s_bad = 0;
+  __syncthreads();
+  for (int k = 0; k < C; k++) {
+    if (tid == 0) {
+      int piv = k; double best = -1.0;
+      for (int r = k; r < C; r++) {
+        const double2 v = A[r * ld + k];
+        const double a = v.x * v.x + v.y * v.y;
+        if (a > best) { best = a; piv = r; }
+      }
+      s_piv = piv;
+      if (!(best > dThreshold * dThreshold) || !isfinite(best)) s_bad = 1;
+    }
+    __syncthreads();
+    if (s_bad) break;
+    const int piv = s_piv;
+    if (piv != k) {
+      for (int c = k + tid; c <= C; c += nt) {
+        const double2 t = A[k * ld + c]; A[k * ld + c] = A[piv * ld + c]; A[piv * ld + c] = t;
+      }
+    }
+    __syncthreads();
+    const double2 pv = A[k * ld + k];
+    const int rows = C - 1 - k, cols = C - k;      // eliminate rows k+1.., columns k+1..C (incl. rhs)
+    // factors are read from column k, which this step does not overwrite
+    for (int i = tid; i < rows * cols; i += nt) {
+      const int r = k + 1 + i / cols, c = k + 1 + i % cols;
+      const double2 f = zdiv(A[r * ld + k], pv);
+      const double2 t = zmul(f, A[k * ld + c]);
+      A[r * ld + c].x -= t.x; A[r * ld + c].y -= t.y;
+    }
+    __syncthreads();
+  }
+  if (s_bad) {
+    // identity fallback (beamformer.cc:2425-2427): t = d
+    __syncthreads();
+    if (tid == 0) {
+      double lr = 0.0;
+      for (int c = 0; c < C; c++) lr += d[c].x * d[c].x + d[c].y * d[c].y;
+      for (int c = 0; c < C; c++) ws[c] = make_double2(d[c].x / (lr * C), d[c].y / (lr * C));
+      fallback[s] = 1;
+    }
+    return;
+  }
+  if (tid == 0) {
+    for (int r = C - 1; r >= 0; r--) {
+      double2 acc = A[r * ld + C];
+      for (int c = r + 1; c < C; c++) { const double2 t = zmul(A[r * ld + c], A[c * ld + C]); acc.x -= t.x; acc.y -= t.y; }
+      A[r * ld + C] = zdiv(acc, A[r * ld + r]);           // t_r overwrites the rhs
+    }
+    double2 lam = make_double2(0.0, 0.0);                  // lam = t^H d  (gsl_blas_zdotc(tmpH, d))
+    for (int c = 0; c < C; c++) {
+      const double2 t = A[c * ld + C];
+      lam.x += t.x * d[c].x + t.y * d[c].y;
+      lam.y += t.x * d[c].y - t.y * d[c].x;
+    }
+    const double2 nrm = make_double2(lam.x * C, lam.y * C);
+    for (int c = 0; c < C; c++) ws[c] = zdiv(A[c * ld + C], nrm);
+    fallback[s] = 0;
+  }
+}
+
+cudaError_t launch_mvdr_solve(const double2* Rn, const double2* d, double2* w, int* fallback, int B, int C,
+                              double dThreshold, cudaStream_t st) {
+  const size_t smem = (size_t)C * (C + 1) * sizeof(double2);
+  cudaError_t e = cudaFuncSetAttribute(btk_mvdr_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  btk_mvdr_solve_kernel<<<B, 128, smem, st>>>(Rn, d, w, fallback, C, dThreshold);
+  return cudaGetLastError();
+}
+
+}  // namespace btk

@@ -1,0 +1,28 @@
+// launch.h -- host-callable launchers of the sm_100a kernels (defined in kern_m*.cu / kern_misc.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "staged_tiles.cuh"
+
+namespace btk {
+
+// Returns cudaSuccess or the launch error; cudaErrorInvalidValue when (M, R) is not compiled in.
+cudaError_t launch_chain(int M, int R, const ChainParams& p, int n_work, cudaStream_t st);
+cudaError_t launch_analysis(int M, int R, const AnalysisParams& p, int n_work, cudaStream_t st);
+cudaError_t launch_synthesis(int M, int R, const SynthesisParams& p, int n_work, cudaStream_t st);
+bool fb_supported(int M, int R);
+// dynamic shared memory the filter-bank kernels need for (M, R, m); <0 when unsupported
+int fb_smem_bytes(int M, int R, int m);
+int fb_frames_per_iter(int M, int R);
+
+// Y[f][s] = sum_c conj(w[s][c]) X[f][s][c]        (beamformer.cc:1181-1194)
+cudaError_t launch_beamform(const cf* snap, const cf* w, cf* Y, long long F, int B, int C, cudaStream_t st);
+// R[s] += sum_f wt[f] x x^H (conj) or x x^T     (beamformer.cc:142-163 / subbandBeamforming.py:1170-1175)
+cudaError_t launch_covariance(const cf* snap, const double* wt, double2* Rout, long long F, int B, int C, int conj,
+                              cudaStream_t st);
+// per-bin MVDR solve (beamformer.cc:2392-2446); Rn [B][C][C], d [B][C] -> w [B][C]; fallback[B] flags
+cudaError_t launch_mvdr_solve(const double2* Rn, const double2* d, double2* w, int* fallback, int B, int C,
+                              double dThreshold, cudaStream_t st);
+
+}  // namespace btk

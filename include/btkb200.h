@@ -1,0 +1,142 @@
+/* btkb200.h -- C ABI of the B200-native subband front end (analysis bank -> SubbandDS / SubbandMVDR ->
+ * synthesis bank).  Plain pointers and sizes only; no C++/torch types; no exceptions cross this boundary
+ * (status codes + btkb200_last_error).  The drop-in C++ stream classes (host/btk_streams.h), the Python
+ * module and bench.py all sit on top of exactly these entry points.
+ *
+ * The reference has no FFI of its own: its boundary is the C++ virtual-class contract of btk/stream,
+ * btk/modulated and btk/beamformer plus the SWIG projection of it.  Each entry point below
+ * cites the reference interface it replaces (paths relative to /root/reference/btk).
+ *
+ * Layouts
+ *   pcm      interleaved float32 [T][C]          (IterativeSampleFeature's buffer, feature/feature.cc:868-896;
+ *                                                  values un-normalised, int16 range, feature.cc:273)
+ *   snap     complex64 [F][B][C], B = M/2+1      (SnapShotArray::update layout, beamformer/beamformer.cc:82-90;
+ *                                                  bins above M/2 are the conjugate mirror and are not stored)
+ *   Y        complex64 [F][B]                    (SubbandDS/SubbandMVDR::next output, beamformer.cc:1181-1194)
+ *   out      float32 [nblk*D]                    (OverSampledDFTSynthesisBank::next output, concatenated)
+ *   weights  complex128 [B][C] as (re, im) pairs (beamformerWeights::_wq / SubbandMVDR::_wmvdr)
+ *   R        complex128 [C][C] row-major per bin (SubbandMVDR::_R[fbinX])
+ */
+#ifndef BTKB200_H
+#define BTKB200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BTKB200_OK 0
+#define BTKB200_EINVAL 1       /* bad argument / size mismatch  -> jdimension_error / jconsistency_error upstream */
+#define BTKB200_ESTATE 2       /* call-order error              -> j_error upstream (beamformer.cc:1140-1143,2587-2594) */
+#define BTKB200_ECUDA 3        /* CUDA runtime failure; message in btkb200_last_error */
+#define BTKB200_ENOMEM 4
+#define BTKB200_EUNSUPPORTED 5 /* (M, r) outside the compiled kernel set */
+
+typedef struct btkb200_plan btkb200_plan;
+
+typedef struct btkb200_info {
+  unsigned M, m, r, R, D, N, B, C, dct;
+  unsigned pd_analysis, pd_synthesis, laN; /* modulated/modulated.cc:278-296 */
+  int device;
+  int has_weights; /* 0 none, 1 delay-and-sum, 2 user / MVDR */
+} btkb200_info;
+
+/* Number of CUDA devices visible; <0 on error. */
+int btkb200_device_count(void);
+const char* btkb200_version(void);
+/* Message of the last failure on this plan (or of the last failed plan_create when plan == NULL). */
+const char* btkb200_last_error(const btkb200_plan* plan);
+
+/* OverSampledDFTFilterBank ctor pair (modulated/modulated.cc:262-300, 359-390, 521-569): one plan holds the
+ * analysis prototype h[N], the synthesis prototype g[N] (either may be NULL if that side is not used), the
+ * geometry (M, m, r, delayCompensationType) and the channel count C of the beamformer
+ * (SubbandBeamformer::setChannel, beamformer.cc:1017-1020).  gain = synthesis gainFactor (modulated.h:331-338).
+ * Prototypes are copied (modulated.cc:275-276). */
+int btkb200_plan_create(btkb200_plan** plan, unsigned M, unsigned m, unsigned r, unsigned dct, unsigned C,
+                        const double* h, const double* g, int gain, int device);
+void btkb200_plan_destroy(btkb200_plan* plan);
+int btkb200_plan_info(const btkb200_plan* plan, btkb200_info* info);
+/* ceil(T/D): SampleFeature::next block rule (feature/feature.cc:627-641). */
+long btkb200_nblk(const btkb200_plan* plan, long T);
+/* nblk + pd - laN frames (modulated.cc:461-516). */
+long btkb200_analysis_frames(const btkb200_plan* plan, long T);
+/* F - pd_s (modulated.cc:626-642). */
+long btkb200_synthesis_frames(const btkb200_plan* plan, long F);
+
+/* ---- weights ------------------------------------------------------------------------------------------ */
+/* SubbandDS::calcArrayManifoldVectors -> beamformerWeights::calcMainlobe, halfBandShift=false
+ * (beamformer.cc:1087-1091, 531-594).  EINVAL if n_delays != C (jdimension_error, :533-535). */
+int btkb200_set_ds_weights(btkb200_plan* plan, double sample_rate, const double* delays, unsigned n_delays);
+/* Install arbitrary per-bin weights [B][C] (re,im): what SubbandMVDR::next applies (beamformer.cc:2616-2630). */
+int btkb200_set_weights(btkb200_plan* plan, const double* w);
+/* Weights currently applied by beamform/chain ([B][C] re,im): SubbandDS::getWeights / SubbandMVDR::getMVDRWeights. */
+int btkb200_get_weights(const btkb200_plan* plan, double* w);
+/* The delay-and-sum manifold wq ([B][C]) kept beside MVDR weights (beamformerWeights::wq_f). */
+int btkb200_get_manifold(const btkb200_plan* plan, double* w);
+
+/* ---- MVDR --------------------------------------------------------------------------------------------- */
+/* SubbandMVDR::setNoiseSpatialSpectralMatrix (beamformer.cc:2454-2477); EINVAL on a shape mismatch (the
+ * reference returns false). */
+int btkb200_set_covariance(btkb200_plan* plan, unsigned bin, const double* R, unsigned rows, unsigned cols);
+int btkb200_get_covariance(const btkb200_plan* plan, unsigned bin, double* R);
+/* SubbandMVDR::setDiffuseNoiseModel (beamformer.cc:2486-2553); micpos [n_mics][3] in mm. */
+int btkb200_set_diffuse_noise_model(btkb200_plan* plan, const double* micpos, unsigned n_mics, double sample_rate,
+                                    double sspeed);
+/* SubbandMVDR::setAllLevelsOfDiagonalLoading / setLevelOfDiagonalLoading (beamformer.cc:2555-2581). */
+int btkb200_diag_load(btkb200_plan* plan, float w);
+int btkb200_diag_load_bin(btkb200_plan* plan, unsigned bin, float w);
+/* SubbandMVDR::divideAllNonDiagonalElements (beamformer.h:362-378). */
+int btkb200_divide_nondiagonal(btkb200_plan* plan, float mu);
+/* SubbandMVDR::calcMVDRWeights (beamformer.cc:2392-2446): w[0] = ones; for s >= 1
+ * w_s = Rinv^H d / (d^H Rinv d) (d = wq[s]).  The per-bin systems are solved on the device in double
+ * precision (pivoted LU) instead of the reference's single-precision SVD pseudoinverse (:253-305); a bin
+ * whose smallest pivot magnitude is below dThreshold falls back to the identity like the reference does
+ * when pseudoinverse() reports failure (:2425-2427).  *n_fallback (optional) = bins that fell back.
+ * ESTATE if no covariance (jallocation_error, :2394-2397) or no manifold (j_error, :2398-2401). */
+int btkb200_solve_mvdr(btkb200_plan* plan, double sample_rate, double dThreshold, int* n_fallback);
+
+/* ---- staged path, HOST buffers (copies inside) ---------------------------------------------------------- */
+/* C x OverSampledDFTAnalysisBank::next over a whole recording + SnapShotArray::update
+ * (modulated.cc:412-516, beamformer.cc:82-90).  snap must hold analysis_frames(T)*B*C complex64. */
+int btkb200_analysis(btkb200_plan* plan, const float* pcm, long T, float* snap, long* n_frames);
+/* SubbandDS::next / SubbandMVDR::next zdotc loop (beamformer.cc:1181-1194, 2616-2630). */
+int btkb200_beamform(btkb200_plan* plan, const float* snap, long F, float* Y);
+/* OverSampledDFTSynthesisBank::next over a whole stream (modulated.cc:595-664). */
+int btkb200_synthesis(btkb200_plan* plan, const float* Y, long F, float* out, long* n_out_frames);
+/* Weighted Gram matrices R[s] = sum_f wt[f] x_f x_f^H (conjugate != 0; lib/subbandBeamforming.py:1170-1175)
+ * or x_f x_f^T (conjugate == 0; SpectralMatrixArray::update, beamformer.cc:142-163) for bins 0..M/2.
+ * R: [B][C][C] complex128. */
+int btkb200_covariance(btkb200_plan* plan, const float* snap, long F, const double* frame_weights, int conjugate,
+                       double* R);
+
+/* ---- fused path ---------------------------------------------------------------------------------------- */
+/* pcm -> out through analysis -> weight apply -> synthesis in ONE kernel; out holds nblk(T)*D floats.
+ * ESTATE if no weights are installed (j_error, beamformer.cc:1140-1143). */
+int btkb200_chain(btkb200_plan* plan, const float* pcm, long T, float* out);
+/* n independent recordings (ragged lengths allowed), host buffers. */
+int btkb200_chain_batch(btkb200_plan* plan, const float* const* pcm, const long* T, int n, float* const* out);
+/* Same, recordings spread round-robin over n_plans plans living on different devices (no inter-GPU traffic). */
+int btkb200_chain_batch_multi(btkb200_plan* const* plans, int n_plans, const float* const* pcm, const long* T, int n,
+                              float* const* out);
+
+/* ---- device-resident variants (pointers are DEVICE pointers on the plan's device; stream is a cudaStream_t
+ *      passed as void*, NULL = the legacy default stream).  Asynchronous: return after enqueueing. -------- */
+int btkb200_chain_batch_dev(btkb200_plan* plan, const float* d_pcm, const long long* pcm_off, const long long* T,
+                            const long long* out_off, int n, float* d_out, void* stream);
+int btkb200_analysis_dev(btkb200_plan* plan, const float* d_pcm, long T, float* d_snap, void* stream);
+int btkb200_beamform_dev(btkb200_plan* plan, const float* d_snap, long F, float* d_Y, void* stream);
+int btkb200_synthesis_dev(btkb200_plan* plan, const float* d_Y, long F, float* d_out, void* stream);
+/* Kernels enqueued by this plan so far (for launch accounting in bench.py). */
+long btkb200_launch_count(const btkb200_plan* plan);
+/* Block until all work enqueued by this plan has finished. */
+int btkb200_sync(btkb200_plan* plan);
+
+/* Page-locked host buffers for the host-buffer entry points (optional; pageable memory also works). */
+void* btkb200_host_alloc(size_t bytes);
+void btkb200_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BTKB200_H */

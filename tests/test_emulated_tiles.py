@@ -1,0 +1,79 @@
+"""CPU tier: run the library's own tile programs (csrc/chain_tile.cuh, staged_tiles.cuh -- the code the
+sm_100a kernels execute) sequentially on the host through tests/emu/emu_chain.cc and compare with the
+oracle.  Checks index arithmetic / framing for every transform size without a GPU.  The emulator is a test
+harness only; the product never links it."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import btk_b200
+import btk_oracle as bo
+from conftest import ROOT, proto
+
+wl = btk_b200.workloads
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    out = tmp_path_factory.mktemp("emu") / "libbtk_emu.so"
+    src = os.path.join(ROOT, "tests", "emu", "emu_chain.cc")
+    inc = os.path.join(ROOT, "distantspeechrecognition-mirror_b200", "csrc")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", f"-I{inc}", "-x", "c++", src, "-o", str(out)],
+                   check=True)
+    return ctypes.CDLL(str(out))
+
+
+def vp(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+CASES = [  # M, m, r, dct, C, T, chunk
+    (256, 4, 1, 0, 1, 2000, 64),
+    (256, 4, 1, 0, 8, 3000, 20),
+    (256, 4, 1, 2, 3, 1500, 100),
+    (512, 2, 2, 0, 4, 2200, 33),
+    (512, 2, 3, 1, 2, 1700, 50),
+    (128, 2, 1, 0, 5, 900, 25),
+    (64, 2, 1, 0, 6, 500, 25),
+    (1024, 2, 2, 0, 2, 4000, 32),
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_emulated_chain_matches_oracle(case, emu, prototypes):
+    M, m, r, dct, C, T, chunk = case
+    h, g = proto(prototypes, M, m, r)
+    geo = bo.BankGeometry(M, m, r, dct)
+    pcm = wl.noise_recording(T, C, seed=7)
+    mp = wl.circular_array(C) if C > 1 else np.zeros((1, 3))
+    W = bo.ds_weights(wl.farfield_delays(mp, 1.0, 1.4), 16000.0, M)
+    _, _, ref = bo.chain(pcm, h, g, geo, W)
+    out = np.zeros(geo.nblk(T) * geo.D, np.float32)
+    Ts, z = np.array([T], np.int64), np.array([0], np.int64)
+    Wc = np.ascontiguousarray(W, dtype=np.complex128)
+    n = emu.emu_chain(M, m, r, dct, C, 1, vp(Ts), vp(pcm), vp(z), vp(out), vp(z), vp(h), vp(g), vp(Wc), 1, chunk)
+    assert n > 0
+    assert bo.snr_db(out, ref) > 100.0   # north_star gate is 70 dB
+
+
+@pytest.mark.parametrize("case", CASES[:6])
+def test_emulated_staged_tiles_match_oracle(case, emu, prototypes):
+    M, m, r, dct, C, T, chunk = case
+    chunk = (chunk + 15) // 16 * 16
+    h, g = proto(prototypes, M, m, r)
+    geo = bo.BankGeometry(M, m, r, dct)
+    pcm = wl.noise_recording(T, C, seed=11)
+    X = np.stack([bo.analysis(pcm[:, c], h, geo) for c in range(C)], axis=1)
+    F, B = X.shape[0], geo.B
+    snap = np.zeros((F, B, C, 2), np.float32)
+    assert emu.emu_analysis(M, m, r, dct, C, T, vp(pcm), vp(snap), vp(h), chunk) == F
+    assert bo.rel_l2(snap.view(np.complex64)[..., 0], X[:, :, :B].transpose(0, 2, 1)) < 1e-5   # gate: 1e-4
+    Y = X[:, 0, :]
+    ref = bo.synthesis(Y, g, geo).reshape(-1)
+    Yh = np.ascontiguousarray(Y[:, :B]).astype(np.complex64)
+    out = np.zeros(geo.synthesis_frames(F) * geo.D, np.float32)
+    emu.emu_synthesis(M, m, r, dct, F, vp(Yh), vp(out), vp(g), 1, chunk)
+    assert bo.snr_db(out, ref) > 100.0
