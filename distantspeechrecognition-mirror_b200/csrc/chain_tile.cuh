@@ -58,7 +58,8 @@ template <int M_, int R_>
 struct ChainCfg {
   typedef FFTGeom<M_> G;
   static constexpr int M = M_, R = R_, D = M_ / R_;
-  static constexpr int NW = 8;                 // warps per CTA, one frame PAIR per warp per iteration
+  static constexpr int NW = (M_ >= 1024) ? 4 : 8;   // warps per CTA, one frame PAIR per warp per iteration
+                                                    // (M = 1024 would not fit 227 KB of shared memory with 8)
   static constexpr int NT = NW * 32;
   static constexpr int W = 2 * NW;             // analysis frames per iteration
   static constexpr int CG = 4;                 // channels staged per pass (one float4 per time step)

@@ -50,7 +50,7 @@ int fb_smem_bytes(int M, int R, int m) {
   BTK_DISPATCH(fb_smem_bytes, R, m)
   return -1;
 }
-int fb_frames_per_iter(int, int) { return 16; }  // ChainCfg::W (2 * NW), identical for every instantiation
+int fb_frames_per_iter(int M, int) { return M >= 1024 ? 8 : 16; }  // ChainCfg::W = 2 * NW
 
 // ---------------------------------------------------------------------------------------------
 // Weight apply on stored snapshots: one thread per (frame, bin), channels innermost and contiguous.
