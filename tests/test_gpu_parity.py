@@ -210,9 +210,9 @@ def test_roundtrip_property_full_size(prototypes):
     plan = btk_b200.Plan(M, m, r, 1, h, g)
     plan.set_weights(np.ones((geo.B, 1), dtype=np.complex128))
     y = plan.chain(x[:, None]) * geo.D
-    lag = np.argmax(np.correlate(y[:4096].astype(np.float64), x[:2048].astype(np.float64), "valid"))
-    n = T - 4096
-    assert bo.snr_db(y[lag : lag + n], x[:n]) > 50.0
+    # for the (256,4,1) Nyquist(M) pair the bank delay equals the synthesis priming (7 frames): lag 0 after the
+    # start-up transient
+    assert bo.snr_db(y[2048 : T - 4096], x[2048 : T - 4096]) > 50.0
     W = np.ones((geo.B, 1), dtype=np.complex128)
     _, _, ref = bo.chain(x[:, None], h, g, geo, W)
     assert bo.snr_db(y / geo.D, ref) >= TOL_SNR
