@@ -52,9 +52,10 @@ struct btkb200_plan {
   std::vector<zd> w, wq, Rn;
   std::vector<char> Rn_set;
   // device constants
-  float* d_taps_h = nullptr;
-  float* d_taps_g = nullptr;
-  cf* d_tw = nullptr;
+  float* d_taps_h = nullptr;   // residue-major [D][TS]
+  float* d_taps_g = nullptr;   // [m][M]
+  cf* d_twa = nullptr;         // lane-contiguous twiddles (fb_core.cuh, FFTTables)
+  cf* d_twb = nullptr;
   cf* d_wts_chain = nullptr;   // [Cpad][M]
   cf* d_w = nullptr;           // [B][C]
   // scratch
@@ -88,7 +89,7 @@ static int upload_weights(btkb200_plan* p) {
   const int M = p->geo.M, B = p->geo.B, C = p->C;
   CK(p, cudaSetDevice(p->device));
   std::vector<cf> gam;
-  build_chain_weight_table(p->w.data(), M, C, p->Cpad, gam);
+  if (!build_chain_weight_table(p->w.data(), M, C, p->Cpad, gam)) return fail(p, BTKB200_EUNSUPPORTED, "no weight layout for M=%d", M);
   std::vector<cf> plain((size_t)B * C);
   for (size_t i = 0; i < plain.size(); i++) plain[i] = mk((float)p->w[i].real(), (float)p->w[i].imag());
   // ordered after any kernel still reading the previous tables
@@ -148,20 +149,23 @@ int btkb200_plan_create(btkb200_plan** out, unsigned M, unsigned m, unsigned r, 
   const int N = p->geo.N, B = p->geo.B;
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_taps_h, N * sizeof(float));
+  std::vector<float> hf, gp(N, 0.f);
+  std::vector<cf> twa, twb;
+  build_analysis_taps(h, (int)M, (int)m, R, hf);
+  build_fft_tables((int)M, twa, twb);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_taps_h, hf.size() * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_taps_g, N * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_tw, M * sizeof(cf));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_twa, twa.size() * sizeof(cf));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_twb, twb.size() * sizeof(cf));
   if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_wts_chain, (size_t)p->Cpad * M * sizeof(cf));
   if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_w, (size_t)B * C * sizeof(cf));
   if (e == cudaSuccess) {
-    std::vector<float> hf(N, 0.f), gp(N, 0.f);
-    std::vector<cf> tw;
-    if (h) { for (int i = 0; i < N; i++) hf[i] = (float)h[i]; p->has_h = true; }
+    if (h) p->has_h = true;
     if (g) { build_synthesis_taps(g, (int)M, (int)m, gp); p->has_g = true; }
-    build_twiddles((int)M, tw);
-    e = cudaMemcpy(p->d_taps_h, hf.data(), N * sizeof(float), cudaMemcpyHostToDevice);
+    e = cudaMemcpy(p->d_taps_h, hf.data(), hf.size() * sizeof(float), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(p->d_taps_g, gp.data(), N * sizeof(float), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(p->d_tw, tw.data(), M * sizeof(cf), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_twa, twa.data(), twa.size() * sizeof(cf), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_twb, twb.data(), twb.size() * sizeof(cf), cudaMemcpyHostToDevice);
   }
   if (e != cudaSuccess) {
     fail(nullptr, BTKB200_ECUDA, "plan_create: %s", cudaGetErrorString(e));
@@ -180,7 +184,7 @@ void btkb200_plan_destroy(btkb200_plan* p) {
   if (!p) return;
   cudaSetDevice(p->device);
   if (p->stream) cudaStreamSynchronize(p->stream);
-  cudaFree(p->d_taps_h); cudaFree(p->d_taps_g); cudaFree(p->d_tw); cudaFree(p->d_wts_chain); cudaFree(p->d_w);
+  cudaFree(p->d_taps_h); cudaFree(p->d_taps_g); cudaFree(p->d_twa); cudaFree(p->d_twb); cudaFree(p->d_wts_chain); cudaFree(p->d_w);
   p->d_recs.release(); p->d_work.release(); p->d_in.release(); p->d_out.release(); p->d_aux.release(); p->d_aux2.release();
   p->h_desc.release();
   if (p->stream) cudaStreamDestroy(p->stream);
@@ -361,7 +365,7 @@ int btkb200_analysis_dev(btkb200_plan* p, const float* d_pcm, long T, float* d_s
   if (rc) return rc;
   AnalysisParams a;
   a.pcm = d_pcm; a.snap = (cf*)d_snap; a.recs = (const RecDesc*)p->d_recs.p; a.work = (const WorkItem*)p->d_work.p;
-  a.taps_h = p->d_taps_h; a.tw = p->d_tw; a.C = p->C; a.Cpad = p->Cpad; a.m = p->geo.m; a.laN = p->geo.laN;
+  a.taps_h = p->d_taps_h; a.twa = p->d_twa; a.twb = p->d_twb; a.C = p->C; a.Cpad = p->Cpad; a.m = p->geo.m; a.laN = p->geo.laN;
   if (!work.empty()) { CK(p, launch_analysis(p->geo.M, p->geo.R, a, (int)work.size(), st)); p->launches++; }
   return BTKB200_OK;
 }
@@ -391,7 +395,7 @@ int btkb200_synthesis_dev(btkb200_plan* p, const float* d_Y, long F, float* d_ou
   if (rc) return rc;
   SynthesisParams s;
   s.Y = (const cf*)d_Y; s.out = d_out; s.recs = (const RecDesc*)p->d_recs.p; s.work = (const WorkItem*)p->d_work.p;
-  s.taps_g = p->d_taps_g; s.tw = p->d_tw; s.m = p->geo.m; s.pd_s = p->geo.pd_s; s.gain = p->gain;
+  s.taps_g = p->d_taps_g; s.twa = p->d_twa; s.twb = p->d_twb; s.m = p->geo.m; s.pd_s = p->geo.pd_s; s.gain = p->gain;
   CK(p, launch_synthesis(p->geo.M, p->geo.R, s, (int)work.size(), st));
   p->launches++;
   return BTKB200_OK;
@@ -429,7 +433,7 @@ int btkb200_chain_batch_dev(btkb200_plan* p, const float* d_pcm, const long long
   if (p->cached_n_work == 0) return BTKB200_OK;
   ChainParams c;
   c.pcm = d_pcm; c.out = d_out; c.recs = (const RecDesc*)p->d_recs.p; c.work = (const WorkItem*)p->d_work.p;
-  c.taps_h = p->d_taps_h; c.taps_g = p->d_taps_g; c.wts = p->d_wts_chain; c.tw = p->d_tw;
+  c.taps_h = p->d_taps_h; c.taps_g = p->d_taps_g; c.wts = p->d_wts_chain; c.twa = p->d_twa; c.twb = p->d_twb;
   c.C = p->C; c.Cpad = p->Cpad; c.m = p->geo.m; c.pd_s = p->geo.pd_s; c.laN = p->geo.laN; c.gain = p->gain;
   CK(p, launch_chain(p->geo.M, p->geo.R, c, p->cached_n_work, st));
   p->launches++;

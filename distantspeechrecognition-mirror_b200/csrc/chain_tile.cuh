@@ -16,6 +16,12 @@
 //     G[k] = sum_c gam_c[k] Z_c[k] = Y_i[k] + j Y_{i+1}[k] for ALL k with Y Hermitian;
 //   * one forward transform of G yields v_i + j v_{i+1} (both real) -- no split/unsplit pass at all.
 //
+// Shared-memory layouts are chosen for the measured B200 issue rates (tools/ubench):
+// every table a lane reads is contiguous per lane (vector LDS with immediate offsets, no index
+// arithmetic in the inner loops), the staged sample window is stored residue-major so that the
+// m*R+1 samples one lane needs are consecutive floats, and the prototype length factor m is a
+// compile-time constant (MT) for the common cases so that the polyphase loops unroll completely.
+//
 // The tile program is written against a context (par / sync / syncwarp) so that the CPU-only
 // tests can execute the very same code sequentially (tests/emu); the library itself only
 // instantiates the device context.
@@ -43,10 +49,11 @@ struct ChainParams {
   float* out;
   const RecDesc* recs;
   const WorkItem* work;
-  const float* taps_h;   // [N] analysis prototype
-  const float* taps_g;   // [m][M]  gp[k][q] = g[M-1-q + M k]
-  const cf* wts;         // [Cpad][M] Hermitian-extended conj weights (zero rows for c >= C)
-  const cf* tw;          // [M] e^{+j 2 pi t / M}
+  const float* taps_h;   // [D][TS]   taps_h[rho*TS + t] = h[rho + D t]            (host_tables.h)
+  const float* taps_g;   // [m][M]    gp[k][q] = g[M-1-q + M k]
+  const cf* wts;         // [Cpad][V/2][L][2] Hermitian-extended conj weights in register order
+  const cf* twa;         // pass-A twiddles, lane-contiguous (FFTTables)
+  const cf* twb;         // pass-B twiddles (three-pass transforms only)
   int C, Cpad;
   int m;                 // prototype length factor
   int pd_s;              // synthesis processing delay (frames)
@@ -54,10 +61,11 @@ struct ChainParams {
   int gain;              // synthesis gainFactor
 };
 
-template <int M_, int R_>
+template <int M_, int R_, int MT_ = 0>
 struct ChainCfg {
   typedef FFTGeom<M_> G;
   static constexpr int M = M_, R = R_, D = M_ / R_;
+  static constexpr int MT = MT_;               // compile-time prototype length factor, 0 = runtime
   static constexpr int NW = (M_ >= 1024) ? 4 : 8;   // warps per CTA, one frame PAIR per warp per iteration
                                                     // (M = 1024 would not fit 227 KB of shared memory with 8)
   static constexpr int NT = NW * 32;
@@ -65,35 +73,60 @@ struct ChainCfg {
   static constexpr int CG = 4;                 // channels staged per pass (one float4 per time step)
   static constexpr int NG = G::NG;             // lane groups per warp = channels processed concurrently
   static constexpr int E = G::Ra / R_;         // registers between members of one residue class
+  // emit: frames per thread (register blocking of the synthesis polyphase)
+  static constexpr int FPT_RAW = (W * D) / NT;
+  static constexpr int FPT = FPT_RAW >= 8 ? 8 : (FPT_RAW >= 4 ? 4 : (FPT_RAW >= 2 ? 2 : 1));
   static_assert(G::Ra % R_ == 0, "decimation factor must divide the first radix");
   static_assert(CG % NG == 0, "channel group must be a multiple of the lane groups per warp");
+  static_assert(W % FPT == 0, "frames per thread must divide the iteration");
 };
 
 struct ChainSmem {
   // offsets in BYTES from the dynamic shared memory base
-  int tw, taps, xs, xbuf, vbuf, total;
-  int RL;      // row length (floats) of one staged channel
-  int win;     // samples per staged window
-  int VR;      // slots in the v ring
+  int taps, twa, twb, xs, wts, xbuf, vhist, total;
+  int TS;      // floats per residue row of the tap table (m R padded: conflict-free vector loads)
+  int TV;      // vector width (floats) of the tap loads
+  int NB;      // D-blocks in the staged window
+  int SB;      // floats per residue row of the staged window (NB padded, SB/2 odd)
+  int CS;      // floats per staged channel
+  int H;       // v history frames kept between iterations (m R - 1)
 };
 
+BTK_HD constexpr int tap_vec(int mR) { return (mR % 4 == 0) ? 4 : ((mR % 2 == 0) ? 2 : 1); }
+BTK_HD constexpr int tap_stride(int mR) {
+  const int tv = tap_vec(mR);
+  int ts = mR;
+  while (((ts / tv) & 1) == 0) ts += tv;
+  return ts;
+}
+
 template <int M_, int R_>
-BTK_HD ChainSmem chain_smem_layout(int m) {
-  typedef ChainCfg<M_, R_> K;
-  ChainSmem s;
-  const int N = M_ * m;
-  s.win = (K::W - 1) * K::D + N;
-  int rl = (s.win + 31) & ~31;
-  if (K::NG > 1) rl += 32 / K::NG;             // rows of concurrently-read channels land in disjoint banks
-  s.RL = rl;
-  s.VR = K::W + m * R_ - 1;
+BTK_HD constexpr ChainSmem chain_smem_layout(int m) {
+  typedef ChainCfg<M_, R_, 0> K;
+  typedef FFTTables<M_> FT;
+  ChainSmem s = ChainSmem();
+  const int mR = m * R_;
+  s.TV = tap_vec(mR);
+  s.TS = tap_stride(mR);
+  s.NB = K::W - 1 + mR;
+  int sb = (s.NB + 1) & ~1;
+  if (((sb / 2) & 1) == 0) sb += 2;
+  s.SB = sb;
+  int cs = K::D * sb;
+  if (K::G::L < 16) cs += (16 - (cs & 31) + 32) & 31;   // two lane groups per LDS.64 phase land in disjoint banks
+  s.CS = cs;
+  s.H = mR - 1;
   int off = 0;
-  s.tw = off;   off += M_ * 8;
-  s.taps = off; off += N * 4;
-  s.xs = off;   off += K::CG * rl * 4;
-  off = (off + 15) & ~15;
+  s.taps = off; off += K::D * s.TS * 4;          off = (off + 15) & ~15;
+  s.twa = off;  off += FT::TWA_WORDS * 8;        off = (off + 15) & ~15;
+  s.twb = off;  off += FT::TWB_WORDS * 8;        off = (off + 15) & ~15;
+  // staged window; the W current v frames of the synthesis side alias it (the window is dead by then)
+  int xs_bytes = K::CG * cs * 4;
+  if (xs_bytes < K::W * M_ * 4) xs_bytes = K::W * M_ * 4;
+  s.xs = off;   off += xs_bytes;                 off = (off + 15) & ~15;
+  s.wts = off;  off += K::CG * M_ * 8;
   s.xbuf = off; off += K::NW * K::NG * K::G::XBUF * 8;
-  s.vbuf = off; off += s.VR * M_ * 4;
+  s.vhist = off; off += (s.H > 0 ? s.H : 1) * M_ * 4;
   s.total = off;
   return s;
 }
@@ -103,68 +136,100 @@ template <int M_> struct ChainThreadState {
   cf g[FFTGeom<M_>::V];
 };
 
+// N consecutive floats, the first one aligned to VEC*4 bytes
+template <int N, int VEC>
+BTK_HD void load_floats(float* dst, const float* src) {
+  if (VEC >= 4) {
+    BTK_UNROLL
+    for (int i = 0; i + 4 <= N; i += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(src + i);
+      dst[i] = v.x; dst[i + 1] = v.y; dst[i + 2] = v.z; dst[i + 3] = v.w;
+    }
+    BTK_UNROLL
+    for (int i = N & ~3; i < N; i++) dst[i] = src[i];
+  } else if (VEC >= 2) {
+    BTK_UNROLL
+    for (int i = 0; i + 2 <= N; i += 2) {
+      const float2 v = *reinterpret_cast<const float2*>(src + i);
+      dst[i] = v.x; dst[i + 1] = v.y;
+    }
+    if (N & 1) dst[N - 1] = src[N - 1];
+  } else {
+    BTK_UNROLL
+    for (int i = 0; i < N; i++) dst[i] = src[i];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Polyphase windowing of one frame pair of one staged channel (modulated.cc:419-434), using the
 // overlap between the two frames: for the residue class rho (mod D)
 //     s_t = x[(i1+1) D - 1 - rho - D t],  h_t = h[rho + D t],  t = a + R k
 //     u_{i1}[rho + D a] = sum_k h_t s_t ,   u_{i0}[rho + D a] = sum_k h_t s_{t+1}
-// i.e. m R + 1 sample loads and m R tap loads feed 2 m R multiply-adds.
+// i.e. m R + 1 sample loads and m R tap loads feed 2 m R multiply-adds.  In the staged window the
+// samples of one residue are consecutive (xrow[(D-1-rho) SB + b], b = block index) and so are the taps.
 // z[r].x <- u_{i0}, z[r].y <- u_{i1} in the canonical register layout.
 // ---------------------------------------------------------------------------------------------
-template <int M_, int R_>
-BTK_HD void polyphase_pair(cf* z, int gl, const float* row, int n1, const float* taps, int m) {
-  typedef ChainCfg<M_, R_> K;
+template <class K>
+BTK_HD void polyphase_pair(cf* z, int gl, const float* xrow, const float* taps, const ChainSmem& L, int m) {
   typedef typename K::G G;
+  constexpr int R_ = K::R;
   BTK_UNROLL
   for (int rep = 0; rep < G::RepA; rep++) {
     BTK_UNROLL
     for (int e0 = 0; e0 < K::E; e0++) {
       const int rho = gl + G::L * rep + G::JA * e0;
-      const float* xp = row + (n1 - rho);
-      const float* hp = taps + rho;
+      const float* xp = xrow + (K::D - 1 - rho) * L.SB;   // xp[b]: block b of this warp's span; s_t = xp[mR - t]
+      const float* hp = taps + rho * L.TS;
       float u0[R_], u1[R_];
       BTK_UNROLL
       for (int a = 0; a < R_; a++) { u0[a] = 0.f; u1[a] = 0.f; }
-      float hprev = 0.f;
-      for (int k = 0; k < m; k++) {
+      if (K::MT > 0) {
+        constexpr int mR = (K::MT > 0 ? K::MT : 1) * R_;
+        float xb[mR + 1], h[mR];
+        load_floats<mR + 1, 2>(xb, xp);
+        load_floats<mR, tap_vec(mR)>(h, hp);
         BTK_UNROLL
-        for (int a = 0; a < R_; a++) {
-          const int t = a + R_ * k;
-          const float s = xp[-K::D * t];
-          const float h = hp[K::D * t];
-          u1[a] = fmaf(h, s, u1[a]);
-          u0[(a + R_ - 1) % R_] = fmaf(hprev, s, u0[(a + R_ - 1) % R_]);
-          hprev = h;
+        for (int t = 0; t < mR; t++) {
+          u1[t % R_] = fmaf(h[t], xb[mR - t], u1[t % R_]);
+          u0[t % R_] = fmaf(h[t], xb[mR - t - 1], u0[t % R_]);
+        }
+      } else {
+        const int mR = m * R_;
+        for (int k = 0; k < m; k++) {
+          BTK_UNROLL
+          for (int a = 0; a < R_; a++) {
+            const int t = a + R_ * k;
+            const float h = hp[t];
+            u1[a] = fmaf(h, xp[mR - t], u1[a]);
+            u0[a] = fmaf(h, xp[mR - t - 1], u0[a]);
+          }
         }
       }
-      u0[R_ - 1] = fmaf(hprev, xp[-K::D * (R_ * m)], u0[R_ - 1]);
       BTK_UNROLL
       for (int a = 0; a < R_; a++) z[rep * G::Ra + e0 + K::E * a] = mk(u0[a], u1[a]);
     }
   }
 }
 
-
 // ---------------------------------------------------------------------------------------------
 // Forward transform of the packed pair held in ts.g by lane group 0 of every warp, real parts into
-// the v ring:  v_{tau0} + j v_{tau0+1} = FFT_fwd(G)   (modulated.cc:603-607, Re taken implicitly
+// the current-v area:  v_{tau0} + j v_{tau0+1} = FFT_fwd(G)   (modulated.cc:603-607, Re taken implicitly
 // because G is the sum of two Hermitian spectra).
 // ---------------------------------------------------------------------------------------------
-template <int M_, int R_, class Ctx>
-BTK_HD void synth_transform_store(Ctx& ctx, const ChainSmem& L, cf* s_xbuf, const cf* s_tw, float* s_v, int it,
-                                  int tau_base) {
-  typedef ChainCfg<M_, R_> K;
+template <class K, class Ctx>
+BTK_HD void synth_transform_store(Ctx& ctx, cf* s_xbuf, const cf* s_twa, const cf* s_twb, float* s_vcur, int tau_base) {
   typedef typename K::G G;
+  constexpr int M_ = K::M;
   typedef ChainThreadState<M_> TS;
   ctx.par([&](int tid, TS& ts) {
     const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
-    if (grp == 0) GroupFFT<M_, -1>::step1(ts.g, gl, s_xbuf + (warp * K::NG) * G::XBUF, s_tw);
+    if (grp == 0) GroupFFT<M_, -1>::step1(ts.g, gl, s_xbuf + (warp * K::NG) * G::XBUF, s_twa);
   });
   ctx.syncwarp();
   if (G::Rb > 1) {
     ctx.par([&](int tid, TS& ts) {
       const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
-      if (grp == 0) GroupFFT<M_, -1>::step2_load(ts.g, gl, s_xbuf + (warp * K::NG) * G::XBUF, s_tw);
+      if (grp == 0) GroupFFT<M_, -1>::step2_load(ts.g, gl, s_xbuf + (warp * K::NG) * G::XBUF, s_twb);
     });
     ctx.syncwarp();
     ctx.par([&](int tid, TS& ts) {
@@ -180,79 +245,110 @@ BTK_HD void synth_transform_store(Ctx& ctx, const ChainSmem& L, cf* s_xbuf, cons
       const int tau0 = tau_base + 2 * warp;
       // v of frames before the stream start is zero (the synthesis buffer starts zeroed, modulated.cc:666-674)
       const float k0 = tau0 >= 0 ? 1.f : 0.f, k1 = tau0 + 1 >= 0 ? 1.f : 0.f;
-      const int slot0 = (it * K::W + 2 * warp) % L.VR;
-      const int slot1 = slot0 + 1 == L.VR ? 0 : slot0 + 1;
+      float* v0 = s_vcur + (2 * warp) * M_;
       BTK_UNROLL
       for (int r = 0; r < G::V; r++) {
         const int q = G::index_of(gl, r);
-        s_v[slot0 * M_ + q] = ts.g[r].x * k0;
-        s_v[slot1 * M_ + q] = ts.g[r].y * k1;
+        v0[q] = ts.g[r].x * k0;
+        v0[M_ + q] = ts.g[r].y * k1;
       }
     }
   });
 }
 
+// v frame f of the iteration (f in [-H, W)): history frames live in s_vhist, current ones in s_vcur
+BTK_HD const float* v_frame(const float* s_vhist, const float* s_vcur, int H, int M, int f) {
+  return f >= 0 ? s_vcur + f * M : s_vhist + (H + f) * M;
+}
+
 // ---------------------------------------------------------------------------------------------
-// Polyphase with g + overlap-add (modulated.cc:646-661), one output sample per (frame, d):
+// Polyphase with g + overlap-add (modulated.cc:646-661):
 //   out_j[D-1-d] = sum_{s<R} w_{j-(R-1-s)}[d + s D],  w_j[q] = sum_k g[M-1-q+M k] v_{j+pd-R k}[q],
 //   w_{j'<0} = 0 (the pd priming frames never produce a w: the reference's priming quirk).
-// Emits the frames of this iteration that fall inside [j0, j0+nj).
+// One thread owns one d and FPT consecutive frames, so every v value and every tap is loaded once per
+// thread.  Emits the frames of this iteration that fall inside [j0, j0+nj).
 // ---------------------------------------------------------------------------------------------
-template <int M_, int R_, class Ctx>
-BTK_HD void synth_emit(Ctx& ctx, const ChainSmem& L, const float* taps_g, const float* s_v, float* out, int m,
-                       int pd_s, int gain, int it, int tau_base, int j0, int nj) {
-  typedef ChainCfg<M_, R_> K;
+template <class K, class Ctx>
+BTK_HD void synth_emit(Ctx& ctx, const ChainSmem& L, const float* taps_g, const float* s_vhist, const float* s_vcur,
+                       float* out, int m, int pd_s, int gain, int tau_base, int j0, int nj) {
+  constexpr int M_ = K::M, R_ = K::R, D = K::D, FPT = K::FPT;
   typedef ChainThreadState<M_> TS;
+  const float gf = gain > 0 ? (float)gain : 1.f;
   ctx.par([&](int tid, TS&) {
-    for (int idx = tid; idx < K::W * K::D; idx += K::NT) {
-      const int fo = idx / K::D, d = idx % K::D;
-      const int tau = tau_base + fo;
-      const int j = tau - pd_s;
-      if (j < j0 || j >= j0 + nj) continue;
-      float acc = 0.f;
+    for (int u = tid; u < D * (K::W / FPT); u += K::NT) {
+      const int d = u % D, f0 = (u / D) * FPT;        // frames f0 .. f0+FPT-1 of this iteration
+      const int jb = tau_base + f0 - pd_s;            // output frame index of f0
+      if (jb + FPT <= j0 || jb >= j0 + nj) continue;
+      float acc[FPT];
+      BTK_UNROLL
+      for (int f = 0; f < FPT; f++) acc[f] = 0.f;
       BTK_UNROLL
       for (int s = 0; s < R_; s++) {
-        const int back = R_ - 1 - s;                    // w_{j-back} contributes block s
-        if (j - back < 0) continue;
-        const int q = d + s * K::D;
-        int slot = (it * K::W + fo - back) % L.VR;      // >= 0 for every emitted frame
-        if (slot < 0) slot += L.VR;
-        float w = 0.f;
-        for (int k = 0; k < m; k++) {
-          w = fmaf(taps_g[k * M_ + q], s_v[slot * M_ + q], w);
-          slot -= R_;
-          if (slot < 0) slot += L.VR;
+        const int back = R_ - 1 - s;                  // w_{j-back} contributes block s
+        const int q = d + s * D;
+        if (K::MT > 0) {
+          constexpr int mm = K::MT > 0 ? K::MT : 1;
+          constexpr int NV = FPT + R_ * (mm - 1);      // v frames f0-back-R(m-1) .. f0-back+FPT-1
+          float g[mm], v[NV];
+          BTK_UNROLL
+          for (int k = 0; k < mm; k++) g[k] = taps_g[k * M_ + q];
+          BTK_UNROLL
+          for (int i = 0; i < NV; i++) v[i] = v_frame(s_vhist, s_vcur, L.H, M_, f0 - back - R_ * (mm - 1) + i)[q];
+          BTK_UNROLL
+          for (int f = 0; f < FPT; f++) {
+            float w = 0.f;
+            BTK_UNROLL
+            for (int k = 0; k < mm; k++) w = fmaf(g[k], v[f + R_ * (mm - 1) - R_ * k], w);
+            if (jb + f - back >= 0) acc[f] += w;
+          }
+        } else {
+          BTK_UNROLL
+          for (int f = 0; f < FPT; f++) {
+            if (jb + f - back < 0) continue;
+            float w = 0.f;
+            for (int k = 0; k < m; k++)
+              w = fmaf(taps_g[k * M_ + q], v_frame(s_vhist, s_vcur, L.H, M_, f0 + f - back - R_ * k)[q], w);
+            acc[f] += w;
+          }
         }
-        acc += w;
       }
-      if (gain > 0) acc *= (float)gain;
-      out[(long long)j * K::D + (K::D - 1 - d)] = acc;
+      BTK_UNROLL
+      for (int f = 0; f < FPT; f++) {
+        const int j = jb + f;
+        if (j >= j0 && j < j0 + nj) out[(long long)j * D + (D - 1 - d)] = acc[f] * gf;
+      }
     }
+  });
+}
+
+// the last H current v frames become the history of the next iteration
+template <class K, class Ctx>
+BTK_HD void synth_roll_history(Ctx& ctx, const ChainSmem& L, float* s_vhist, const float* s_vcur) {
+  typedef ChainThreadState<K::M> TS;
+  ctx.par([&](int tid, TS&) {
+    for (int i = tid; i < L.H * K::M; i += K::NT) s_vhist[i] = s_vcur[(K::W - L.H) * K::M + i];
   });
 }
 
 // One analysis round of a warp: polyphase of the staged channel + backward transform, leaving
 // Z = X_{tau0} + j X_{tau0+1} of channel (round*NG + grp) in ts.z (canonical layout).
-template <int M_, int R_, class Ctx>
+template <class K, class Ctx>
 BTK_HD void analysis_round(Ctx& ctx, const ChainSmem& L, const float* s_xs, const float* s_taps, cf* s_xbuf,
-                           const cf* s_tw, int m, int round) {
-  typedef ChainCfg<M_, R_> K;
+                           const cf* s_twa, const cf* s_twb, int m, int round) {
   typedef typename K::G G;
+  constexpr int M_ = K::M;
   typedef ChainThreadState<M_> TS;
-  const int N = M_ * m;
   ctx.par([&](int tid, TS& ts) {
     const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
     const int c_local = round * K::NG + grp;
-    // newest sample of the second frame of the pair, as an index into the staged row
-    const int n1 = (2 * warp + 1) * K::D + N - 1;
-    polyphase_pair<M_, R_>(ts.z, gl, s_xs + c_local * L.RL, n1, s_taps, m);
-    GroupFFT<M_, +1>::step1(ts.z, gl, s_xbuf + (warp * K::NG + grp) * G::XBUF, s_tw);
+    polyphase_pair<K>(ts.z, gl, s_xs + c_local * L.CS + 2 * warp, s_taps, L, m);
+    GroupFFT<M_, +1>::step1(ts.z, gl, s_xbuf + (warp * K::NG + grp) * G::XBUF, s_twa);
   });
   ctx.syncwarp();
   if (G::Rb > 1) {
     ctx.par([&](int tid, TS& ts) {
       const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
-      GroupFFT<M_, +1>::step2_load(ts.z, gl, s_xbuf + (warp * K::NG + grp) * G::XBUF, s_tw);
+      GroupFFT<M_, +1>::step2_load(ts.z, gl, s_xbuf + (warp * K::NG + grp) * G::XBUF, s_twb);
     });
     ctx.syncwarp();
     ctx.par([&](int tid, TS& ts) {
@@ -267,15 +363,23 @@ BTK_HD void analysis_round(Ctx& ctx, const ChainSmem& L, const float* s_xs, cons
   });
 }
 
-// Stage CG channels [cg0, cg0+CG) of the window starting at sample t_lo: [t][C] -> s_xs[c][t].
-template <int M_, int R_, class Ctx>
+// Stage CG channels [cg0, cg0+CG) of the window starting at sample t_lo: pcm [t][C] -> s_xs[c][t mod D][t div D].
+// A warp covers 16 consecutive residues of two consecutive D-blocks per step: the global reads are two
+// coalesced runs and the residue-major stores hit 32 distinct banks (SB/2 is odd).
+template <class K, class Ctx>
 BTK_HD void stage_window(Ctx& ctx, const ChainSmem& L, float* s_xs, const float* pcm, int C, int T, long long t_lo,
                          int cg0, bool vec4) {
-  typedef ChainCfg<M_, R_> K;
-  typedef ChainThreadState<M_> TS;
+  typedef ChainThreadState<K::M> TS;
+  constexpr int D = K::D;
+  constexpr int RT = (D + 15) / 16;
   ctx.par([&](int tid, TS&) {
-    for (int tt = tid; tt < L.win; tt += K::NT) {
-      const long long t = t_lo + tt;
+    const int warp = tid >> 5, lane = tid & 31, sub = lane & 15, hb = lane >> 4;
+    const int ntile = ((L.NB + 1) / 2) * RT;
+    BTK_UNROLL_N(4)
+    for (int tile = warp; tile < ntile; tile += K::NW) {
+      const int res = (tile % RT) * 16 + sub, blk = 2 * (tile / RT) + hb;
+      if (res >= D || blk >= L.NB) continue;
+      const long long t = t_lo + (long long)blk * D + res;
       float x[K::CG];
       BTK_UNROLL
       for (int c = 0; c < K::CG; c++) x[c] = 0.f;
@@ -290,8 +394,24 @@ BTK_HD void stage_window(Ctx& ctx, const ChainSmem& L, float* s_xs, const float*
         }
       }
       BTK_UNROLL
-      for (int c = 0; c < K::CG; c++) s_xs[c * L.RL + tt] = x[c];
+      for (int c = 0; c < K::CG; c++) s_xs[c * L.CS + res * L.SB + blk] = x[c];
     }
+  });
+}
+
+// tables every tile program needs: residue-major taps and the lane-contiguous twiddles
+template <class K, class Ctx>
+BTK_HD void load_tables(Ctx& ctx, const ChainSmem& L, unsigned char* smem, const float* taps_h, const cf* twa,
+                        const cf* twb) {
+  typedef ChainThreadState<K::M> TS;
+  typedef FFTTables<K::M> FT;
+  float* s_taps = reinterpret_cast<float*>(smem + L.taps);
+  cf* s_twa = reinterpret_cast<cf*>(smem + L.twa);
+  cf* s_twb = reinterpret_cast<cf*>(smem + L.twb);
+  ctx.par([&](int tid, TS&) {
+    if (taps_h) for (int i = tid; i < K::D * L.TS; i += K::NT) s_taps[i] = taps_h[i];
+    for (int i = tid; i < FT::TWA_WORDS; i += K::NT) s_twa[i] = twa[i];
+    for (int i = tid; i < FT::TWB_WORDS; i += K::NT) s_twb[i] = twb[i];
   });
 }
 
@@ -301,20 +421,23 @@ BTK_HD void stage_window(Ctx& ctx, const ChainSmem& L, float* s_xs, const float*
 //   void sync()                       CTA barrier;   void syncwarp()   warp barrier
 // Every cross-thread shared-memory dependency crosses a par() boundary followed by a barrier.
 // ---------------------------------------------------------------------------------------------
-template <int M_, int R_, class Ctx>
+template <int M_, int R_, int MT_, class Ctx>
 BTK_HD void chain_tile(Ctx& ctx, const ChainParams& p, unsigned char* smem, int work_id) {
-  typedef ChainCfg<M_, R_> K;
+  typedef ChainCfg<M_, R_, MT_> K;
   typedef typename K::G G;
   typedef ChainThreadState<M_> TS;
-  const int m = p.m;
+  const int m = MT_ > 0 ? MT_ : p.m;
   const int N = M_ * m;
-  const int H = m * R_ - 1;                                 // v history needed before a frame
   const ChainSmem L = chain_smem_layout<M_, R_>(m);
-  cf* s_tw = reinterpret_cast<cf*>(smem + L.tw);
+  const int H = L.H;                                        // v history needed before a frame
   float* s_taps = reinterpret_cast<float*>(smem + L.taps);
+  cf* s_twa = reinterpret_cast<cf*>(smem + L.twa);
+  cf* s_twb = reinterpret_cast<cf*>(smem + L.twb);
   float* s_xs = reinterpret_cast<float*>(smem + L.xs);
+  float* s_vcur = s_xs;                                     // alias: the window is dead when v is produced
+  float4* s_wts = reinterpret_cast<float4*>(smem + L.wts);
   cf* s_xbuf = reinterpret_cast<cf*>(smem + L.xbuf);
-  float* s_v = reinterpret_cast<float*>(smem + L.vbuf);
+  float* s_vhist = reinterpret_cast<float*>(smem + L.vhist);
 
   const WorkItem wk = p.work[work_id];
   const RecDesc rec = p.recs[wk.rec];
@@ -325,9 +448,9 @@ BTK_HD void chain_tile(Ctx& ctx, const ChainParams& p, unsigned char* smem, int 
   const int n_it = (wk.nj + H + K::W - 1) / K::W;
   const bool vec4 = (C % 4 == 0) && (rec.pcm_off % 4 == 0);
 
+  load_tables<K>(ctx, L, smem, p.taps_h, p.twa, p.twb);
   ctx.par([&](int tid, TS&) {
-    for (int i = tid; i < M_; i += K::NT) s_tw[i] = p.tw[i];
-    for (int i = tid; i < N; i += K::NT) s_taps[i] = p.taps_h[i];
+    for (int i = tid; i < H * M_; i += K::NT) s_vhist[i] = 0.f;
   });
   ctx.sync();
 
@@ -342,18 +465,26 @@ BTK_HD void chain_tile(Ctx& ctx, const ChainParams& p, unsigned char* smem, int 
     });
 
     for (int cg0 = 0; cg0 < p.Cpad; cg0 += K::CG) {
-      stage_window<M_, R_>(ctx, L, s_xs, pcm, C, rec.T, t_lo, cg0, vec4);
+      stage_window<K>(ctx, L, s_xs, pcm, C, rec.T, t_lo, cg0, vec4);
+      // the weights of these CG channels, already in register order: [c][V/2][L] float4 = 2 complex
+      ctx.par([&](int tid, TS&) {
+        const float4* src = reinterpret_cast<const float4*>(p.wts + (long long)cg0 * M_);
+        for (int i = tid; i < K::CG * M_ / 2; i += K::NT) s_wts[i] = src[i];
+      });
       ctx.sync();
 
       // ---- per warp: frame pair (tau0, tau0+1); per lane group: one channel per round
       for (int round = 0; round < K::CG / K::NG; round++) {
-        analysis_round<M_, R_>(ctx, L, s_xs, s_taps, s_xbuf, s_tw, m, round);
+        analysis_round<K>(ctx, L, s_xs, s_taps, s_xbuf, s_twa, s_twb, m, round);
         ctx.par([&](int tid, TS& ts) {
           const int lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
-          const int c = cg0 + round * K::NG + grp;
-          const cf* wrow = p.wts + (long long)c * M_;
+          const float4* w4 = s_wts + (round * K::NG + grp) * (G::V / 2) * G::L + gl;
           BTK_UNROLL
-          for (int r = 0; r < G::V; r++) cfma(ts.g[r], ts.z[r], wrow[G::index_of(gl, r)]);
+          for (int r2 = 0; r2 < G::V / 2; r2++) {
+            const float4 w = w4[r2 * G::L];
+            cfma(ts.g[2 * r2], ts.z[2 * r2], mk(w.x, w.y));
+            cfma(ts.g[2 * r2 + 1], ts.z[2 * r2 + 1], mk(w.z, w.w));
+          }
         });
         ctx.syncwarp();
       }
@@ -384,9 +515,11 @@ BTK_HD void chain_tile(Ctx& ctx, const ChainParams& p, unsigned char* smem, int 
       ctx.syncwarp();
     }
 
-    synth_transform_store<M_, R_>(ctx, L, s_xbuf, s_tw, s_v, it, tau_base);
+    synth_transform_store<K>(ctx, s_xbuf, s_twa, s_twb, s_vcur, tau_base);
     ctx.sync();
-    synth_emit<M_, R_>(ctx, L, p.taps_g, s_v, out, m, p.pd_s, p.gain, it, tau_base, wk.j0, wk.nj);
+    synth_emit<K>(ctx, L, p.taps_g, s_vhist, s_vcur, out, m, p.pd_s, p.gain, tau_base, wk.j0, wk.nj);
+    ctx.sync();
+    synth_roll_history<K>(ctx, L, s_vhist, s_vcur);
     ctx.sync();
   }
 }

@@ -19,9 +19,12 @@
 #if defined(__CUDACC__)
 #define BTK_HD __host__ __device__ __forceinline__
 #define BTK_UNROLL _Pragma("unroll")
+#define BTK_UNROLL_N(n) _Pragma(BTK_STR(unroll n))
+#define BTK_STR(x) #x
 #else
 #define BTK_HD inline
 #define BTK_UNROLL
+#define BTK_UNROLL_N(n)
 #ifndef BTK_HOST_VECTOR_TYPES
 #define BTK_HOST_VECTOR_TYPES
 struct float2 { float x, y; };
@@ -155,44 +158,56 @@ template <int M_> struct FFTGeom {
   static BTK_HD int index_of(int gl, int r) { return (gl + L * (r / Ra)) + JA * (r % Ra); }
 };
 
-// One lane's share of the pass structure.  `tw` is the table tw[t] = e^{+j 2 pi t / M}, t in [0, M).
+// Lane-contiguous twiddle tables (built on the host by host_tables.h::build_fft_tables, copied to shared
+// memory by every tile program): a lane reads its pass-A / pass-B twiddles as float4 pairs at immediate
+// offsets instead of indexing a natural-order table.
+//   pass A, owner j = gl + L rep in [0, JA):  twa[j*TA + (ka-1)] = W_M^{j ka}            (two-pass transforms)
+//                                                                  W_M^{(j / Rc) ka Rc}   (three-pass transforms)
+//   pass B, owner iB = gl + L rep in [0, M/Rb): twb[iB*TB + kb]  = W_M^{nc (ka + Ra kb)},  ka = iB / Rc, nc = iB % Rc
+// with W_M = e^{+j 2 pi / M}.  TA (TB) complex words per owner, even with an odd half so that the 16-byte
+// loads of 8 consecutive lanes fall into distinct bank groups.
+template <int M_> struct FFTTables {
+  typedef FFTGeom<M_> G;
+  static constexpr int ta_() { int t = (G::Ra - 1 + 1) & ~1; if (((t / 2) & 1) == 0) t += 2; return t; }
+  static constexpr int TA = ta_();
+  static constexpr int TWA_WORDS = G::JA * TA;
+  static constexpr int TB = G::Rb > 1 ? (G::Rb == 2 ? 2 : 6) : 0;
+  static constexpr int TWB_WORDS = G::Rb > 1 ? (G::M / G::Rb) * TB : 0;
+  static_assert(G::Rb == 1 || G::Rb == 2 || G::Rb == 4, "pass B radix");
+};
+
+// One lane's share of the pass structure.
 // The three steps must be separated by a group-wide barrier (__syncwarp on the device).
 template <int M_, int S> struct GroupFFT {
   typedef FFTGeom<M_> G;
+  typedef FFTTables<M_> FT;
 
   // step 1: pass A (+ twiddle) and scatter into the exchange buffer.
-  static BTK_HD void step1(cf* v, int gl, cf* xb, const cf* tw) {
+  static BTK_HD void step1(cf* v, int gl, cf* xb, const cf* twa) {
     BTK_UNROLL
     for (int rep = 0; rep < G::RepA; rep++) {
       cf* p = v + rep * G::Ra;
       Dft<G::Ra, S>::run(p);
       const int j = gl + G::L * rep;
-      if (G::Rb > 1) {
-        const int nb = j / G::Rc;
-        // W_{Ra Rb}^{nb ka} = W_M^{nb ka Rc}
-        BTK_UNROLL
-        for (int ka = 1; ka < G::Ra; ka++) p[ka] = multw<S>(p[ka], tw[(nb * ka * G::Rc) & (G::M - 1)]);
-        BTK_UNROLL
-        for (int ka = 0; ka < G::Ra; ka++) xb[ka * G::S1 + j] = p[ka];
-      } else {
-        // two-factor case: nc == j, twiddle W_M^{nc ka}, straight to exchange 2 (iC == ka)
-        const cf w1 = tw[j];
-        cf w[G::Ra];
-        w[1] = w1;
-        BTK_UNROLL
-        for (int ka = 2; ka < G::Ra; ka++) w[ka] = (ka & 1) ? cmul(w[ka - 1], w1) : cmul(w[ka / 2], w[ka / 2]);
-        BTK_UNROLL
-        for (int ka = 1; ka < G::Ra; ka++) p[ka] = multw<S>(p[ka], w[ka]);
-        BTK_UNROLL
-        for (int ka = 0; ka < G::Ra; ka++) xb[ka * G::S2 + j] = p[ka];
+      const float4* t4 = reinterpret_cast<const float4*>(twa + j * FT::TA);
+      cf w[G::Ra + 1];
+      BTK_UNROLL
+      for (int i = 0; i < G::Ra / 2; i++) {
+        const float4 t = t4[i];
+        w[2 * i + 1] = mk(t.x, t.y);
+        w[2 * i + 2] = mk(t.z, t.w);
       }
+      BTK_UNROLL
+      for (int ka = 1; ka < G::Ra; ka++) p[ka] = multw<S>(p[ka], w[ka]);
+      BTK_UNROLL
+      for (int ka = 0; ka < G::Ra; ka++) xb[ka * (G::Rb > 1 ? G::S1 : G::S2) + j] = p[ka];
     }
   }
 
   // step 2 (only when Rb > 1): gather for pass B, radix-Rb, twiddle, scatter into exchange 2.
   // Reads complete before the caller's barrier; writes must come after it (same buffer is reused),
   // hence the split into step2_load / step2_store.
-  static BTK_HD void step2_load(cf* v, int gl, const cf* xb, const cf* tw) {
+  static BTK_HD void step2_load(cf* v, int gl, const cf* xb, const cf* twb) {
     if (G::Rb > 1) {
       BTK_UNROLL
       for (int rep = 0; rep < G::RepB; rep++) {
@@ -202,8 +217,13 @@ template <int M_, int S> struct GroupFFT {
         BTK_UNROLL
         for (int nb = 0; nb < G::Rb; nb++) p[nb] = xb[ka * G::S1 + nb * G::Rc + nc];
         Dft<G::Rb, S>::run(p);
+        const float4* t4 = reinterpret_cast<const float4*>(twb + iB * FT::TB);
         BTK_UNROLL
-        for (int kb = 0; kb < G::Rb; kb++) p[kb] = multw<S>(p[kb], tw[(nc * (ka + G::Ra * kb)) & (G::M - 1)]);
+        for (int i = 0; i < G::Rb / 2; i++) {
+          const float4 t = t4[i];
+          p[2 * i] = multw<S>(p[2 * i], mk(t.x, t.y));
+          p[2 * i + 1] = multw<S>(p[2 * i + 1], mk(t.z, t.w));
+        }
       }
     }
   }

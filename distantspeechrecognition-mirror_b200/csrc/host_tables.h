@@ -34,12 +34,44 @@ struct BankGeom {
   int synthesis_frames(int F) const { return F > pd_s ? F - pd_s : 0; }
 };
 
-inline void build_twiddles(int M, std::vector<cf>& tw) {
-  tw.resize(M);
-  for (int t = 0; t < M; t++) {
-    const double a = 2.0 * M_PI * (double)t / (double)M;
-    tw[t] = mk((float)cos(a), (float)sin(a));
+// Lane-contiguous twiddle tables of the M-point transform (layout: fb_core.cuh, FFTTables).
+template <int M_>
+inline void build_fft_tables_m(std::vector<cf>& twa, std::vector<cf>& twb) {
+  typedef FFTGeom<M_> G;
+  typedef FFTTables<M_> FT;
+  auto W = [](long long e) {
+    const double a = 2.0 * M_PI * (double)(((e % M_) + M_) % M_) / (double)M_;
+    return mk((float)cos(a), (float)sin(a));
+  };
+  twa.assign(FT::TWA_WORDS > 0 ? FT::TWA_WORDS : 1, mk(1.f, 0.f));
+  for (int j = 0; j < G::JA; j++)
+    for (int ka = 1; ka < G::Ra; ka++)
+      twa[(size_t)j * FT::TA + (ka - 1)] = G::Rb > 1 ? W((long long)(j / G::Rc) * ka * G::Rc) : W((long long)j * ka);
+  twb.assign(FT::TWB_WORDS > 0 ? FT::TWB_WORDS : 1, mk(1.f, 0.f));
+  if (G::Rb > 1)
+    for (int iB = 0; iB < M_ / G::Rb; iB++) {
+      const int ka = iB / G::Rc, nc = iB % G::Rc;
+      for (int kb = 0; kb < G::Rb; kb++) twb[(size_t)iB * FT::TB + kb] = W((long long)nc * (ka + G::Ra * kb));
+    }
+}
+inline bool build_fft_tables(int M, std::vector<cf>& twa, std::vector<cf>& twb) {
+  switch (M) {
+    case 64: build_fft_tables_m<64>(twa, twb); return true;
+    case 128: build_fft_tables_m<128>(twa, twb); return true;
+    case 256: build_fft_tables_m<256>(twa, twb); return true;
+    case 512: build_fft_tables_m<512>(twa, twb); return true;
+    case 1024: build_fft_tables_m<1024>(twa, twb); return true;
   }
+  return false;
+}
+
+// Residue-major analysis taps: th[rho*TS + t] = h[rho + D t], t in [0, m R)  (chain_tile.cuh, polyphase_pair).
+inline void build_analysis_taps(const double* h, int M, int m, int R, std::vector<float>& th) {
+  const int D = M / R, mR = m * R, TS = tap_stride(mR);
+  th.assign((size_t)D * TS, 0.f);
+  if (!h) return;
+  for (int rho = 0; rho < D; rho++)
+    for (int t = 0; t < mR; t++) th[(size_t)rho * TS + t] = (float)h[rho + D * t];
 }
 
 // gp[k][q] = g[M-1-q + M k]  (polyphase(_M - m - 1, k), modulated.cc:649)
@@ -67,11 +99,17 @@ inline void ds_weights(const double* delays, double fs, int M, int C, std::vecto
 }
 
 // Hermitian-extended conjugate weight table for the fused chain (see chain_tile.cuh header):
-//   gam[c][k] = conj(w[k][c]) for 0 < k < M/2 ; gam[c][M-k] = w[k][c] ; real part only at k = 0, M/2.
-inline void build_chain_weight_table(const zd* w, int M, int C, int Cpad, std::vector<cf>& gam) {
+//   gam[c][k] = conj(w[k][c]) for 0 < k < M/2 ; gam[c][M-k] = w[k][c] ; real part only at k = 0, M/2,
+// stored in the register order of the transform: element ((c*(V/2) + r2)*L + gl)*2 + i holds bin
+// index_of(gl, 2 r2 + i), so that a lane's two consecutive registers are one 16-byte load and the lanes of a
+// group read consecutive 16-byte words.
+template <int M_>
+inline void build_chain_weight_table_m(const zd* w, int C, int Cpad, std::vector<cf>& gam) {
+  typedef FFTGeom<M_> G;
+  const int M = M_;
   gam.assign((size_t)Cpad * M, mk(0.f, 0.f));
+  std::vector<cf> row(M);
   for (int c = 0; c < C; c++) {
-    cf* row = &gam[(size_t)c * M];
     row[0] = mk((float)w[c].real(), 0.f);
     row[M / 2] = mk((float)w[(size_t)(M / 2) * C + c].real(), 0.f);
     for (int k = 1; k < M / 2; k++) {
@@ -79,7 +117,20 @@ inline void build_chain_weight_table(const zd* w, int M, int C, int Cpad, std::v
       row[k] = mk((float)v.real(), (float)-v.imag());
       row[M - k] = mk((float)v.real(), (float)v.imag());
     }
+    for (int gl = 0; gl < G::L; gl++)
+      for (int r = 0; r < G::V; r++)
+        gam[(((size_t)c * (G::V / 2) + r / 2) * G::L + gl) * 2 + (r & 1)] = row[G::index_of(gl, r)];
   }
+}
+inline bool build_chain_weight_table(const zd* w, int M, int C, int Cpad, std::vector<cf>& gam) {
+  switch (M) {
+    case 64: build_chain_weight_table_m<64>(w, C, Cpad, gam); return true;
+    case 128: build_chain_weight_table_m<128>(w, C, Cpad, gam); return true;
+    case 256: build_chain_weight_table_m<256>(w, C, Cpad, gam); return true;
+    case 512: build_chain_weight_table_m<512>(w, C, Cpad, gam); return true;
+    case 1024: build_chain_weight_table_m<1024>(w, C, Cpad, gam); return true;
+  }
+  return false;
 }
 
 // SubbandMVDR::setDiffuseNoiseModel (beamformer/beamformer.cc:2486-2553): Gamma_mn = sinc(2 fs s d_mn/(M c)),

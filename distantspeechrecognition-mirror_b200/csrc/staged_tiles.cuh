@@ -18,20 +18,23 @@ struct AnalysisParams {
   cf* snap;               // [F][B][C] per recording at recs[].out_off (complex elements)
   const RecDesc* recs;    // nblk field = number of emitted analysis frames F
   const WorkItem* work;   // j0/nj = first emitted frame / count (multiple of W except the last)
-  const float* taps_h;
-  const cf* tw;
+  const float* taps_h;    // residue-major taps (host_tables.h::build_analysis_taps)
+  const cf* twa;
+  const cf* twb;
   int C, Cpad, m, laN;
 };
 
-template <int M_, int R_, class Ctx>
+template <int M_, int R_, int MT_, class Ctx>
 BTK_HD void analysis_tile(Ctx& ctx, const AnalysisParams& p, unsigned char* smem, int work_id) {
-  typedef ChainCfg<M_, R_> K;
+  typedef ChainCfg<M_, R_, MT_> K;
   typedef typename K::G G;
   typedef ChainThreadState<M_> TS;
-  const int m = p.m, N = M_ * m, B = M_ / 2 + 1;
+  const int m = MT_ > 0 ? MT_ : p.m;
+  const int N = M_ * m, B = M_ / 2 + 1;
   const ChainSmem L = chain_smem_layout<M_, R_>(m);
-  cf* s_tw = reinterpret_cast<cf*>(smem + L.tw);
   float* s_taps = reinterpret_cast<float*>(smem + L.taps);
+  cf* s_twa = reinterpret_cast<cf*>(smem + L.twa);
+  cf* s_twb = reinterpret_cast<cf*>(smem + L.twb);
   float* s_xs = reinterpret_cast<float*>(smem + L.xs);
   cf* s_xbuf = reinterpret_cast<cf*>(smem + L.xbuf);
 
@@ -43,20 +46,17 @@ BTK_HD void analysis_tile(Ctx& ctx, const AnalysisParams& p, unsigned char* smem
   const int n_it = (wk.nj + K::W - 1) / K::W;
   const bool vec4 = (C % 4 == 0) && (rec.pcm_off % 4 == 0);
 
-  ctx.par([&](int tid, TS&) {
-    for (int i = tid; i < M_; i += K::NT) s_tw[i] = p.tw[i];
-    for (int i = tid; i < N; i += K::NT) s_taps[i] = p.taps_h[i];
-  });
+  load_tables<K>(ctx, L, smem, p.taps_h, p.twa, p.twb);
   ctx.sync();
 
   for (int it = 0; it < n_it; it++) {
     const int f_base = wk.j0 + it * K::W;          // emitted frame index t; internal frame i = t + laN
     const long long t_lo = (long long)(f_base + p.laN + 1) * K::D - N;
     for (int cg0 = 0; cg0 < p.Cpad; cg0 += K::CG) {
-      stage_window<M_, R_>(ctx, L, s_xs, pcm, C, rec.T, t_lo, cg0, vec4);
+      stage_window<K>(ctx, L, s_xs, pcm, C, rec.T, t_lo, cg0, vec4);
       ctx.sync();
       for (int round = 0; round < K::CG / K::NG; round++) {
-        analysis_round<M_, R_>(ctx, L, s_xs, s_taps, s_xbuf, s_tw, m, round);
+        analysis_round<K>(ctx, L, s_xs, s_taps, s_xbuf, s_twa, s_twb, m, round);
         ctx.syncwarp();
         // Z = X_f0 + j X_f1 in natural order through the exchange buffer, so every lane can reach Z[M-k]
         ctx.par([&](int tid, TS& ts) {
@@ -96,21 +96,25 @@ struct SynthesisParams {
   const RecDesc* recs;    // T field = F (frames available), nblk = number of output frames
   const WorkItem* work;
   const float* taps_g;
-  const cf* tw;
+  const cf* twa;
+  const cf* twb;
   int m, pd_s, gain;
 };
 
-template <int M_, int R_, class Ctx>
+template <int M_, int R_, int MT_, class Ctx>
 BTK_HD void synthesis_tile(Ctx& ctx, const SynthesisParams& p, unsigned char* smem, int work_id) {
-  typedef ChainCfg<M_, R_> K;
+  typedef ChainCfg<M_, R_, MT_> K;
   typedef typename K::G G;
   typedef ChainThreadState<M_> TS;
-  const int m = p.m, B = M_ / 2 + 1;
-  const int H = m * R_ - 1;
+  const int m = MT_ > 0 ? MT_ : p.m;
+  const int B = M_ / 2 + 1;
   const ChainSmem L = chain_smem_layout<M_, R_>(m);
-  cf* s_tw = reinterpret_cast<cf*>(smem + L.tw);
+  const int H = L.H;
+  cf* s_twa = reinterpret_cast<cf*>(smem + L.twa);
+  cf* s_twb = reinterpret_cast<cf*>(smem + L.twb);
   cf* s_xbuf = reinterpret_cast<cf*>(smem + L.xbuf);
-  float* s_v = reinterpret_cast<float*>(smem + L.vbuf);
+  float* s_vcur = reinterpret_cast<float*>(smem + L.xs);
+  float* s_vhist = reinterpret_cast<float*>(smem + L.vhist);
 
   const WorkItem wk = p.work[work_id];
   const RecDesc rec = p.recs[wk.rec];
@@ -120,8 +124,9 @@ BTK_HD void synthesis_tile(Ctx& ctx, const SynthesisParams& p, unsigned char* sm
   const int a_start = wk.j0 + p.pd_s - H;
   const int n_it = (wk.nj + H + K::W - 1) / K::W;
 
+  load_tables<K>(ctx, L, smem, (const float*)0, p.twa, p.twb);
   ctx.par([&](int tid, TS&) {
-    for (int i = tid; i < M_; i += K::NT) s_tw[i] = p.tw[i];
+    for (int i = tid; i < H * M_; i += K::NT) s_vhist[i] = 0.f;
   });
   ctx.sync();
 
@@ -144,9 +149,11 @@ BTK_HD void synthesis_tile(Ctx& ctx, const SynthesisParams& p, unsigned char* sm
         ts.g[r] = mk(a.x - b.y, a.y + b.x);
       }
     });
-    synth_transform_store<M_, R_>(ctx, L, s_xbuf, s_tw, s_v, it, tau_base);
+    synth_transform_store<K>(ctx, s_xbuf, s_twa, s_twb, s_vcur, tau_base);
     ctx.sync();
-    synth_emit<M_, R_>(ctx, L, p.taps_g, s_v, out, m, p.pd_s, p.gain, it, tau_base, wk.j0, wk.nj);
+    synth_emit<K>(ctx, L, p.taps_g, s_vhist, s_vcur, out, m, p.pd_s, p.gain, tau_base, wk.j0, wk.nj);
+    ctx.sync();
+    synth_roll_history<K>(ctx, L, s_vhist, s_vcur);
     ctx.sync();
   }
 }

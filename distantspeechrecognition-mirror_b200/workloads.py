@@ -47,8 +47,9 @@ def array_recording(T: int, delays_s: np.ndarray, seed: int, noise_sigma: float 
     f = np.fft.rfftfreq(nfft, 1.0 / fs)
     out = np.empty((T, C), dtype=np.float32)
     for c in range(C):
-        # channel c hears s(t + tau_c) so that steering with tau_c (beamformer.cc:566-574) re-aligns it
-        sc = np.fft.irfft(S * np.exp(2j * np.pi * f * delays_s[c]), nfft)[:T]
+        # channel c hears s(t - tau_c) (tau_c = -(u . p_c)/v is negative for microphones nearer the
+        # source), so Y = sum_c conj(wq_c) X_c with wq_c = exp(-j w tau_c)/C (beamformer.cc:566-574) re-aligns it
+        sc = np.fft.irfft(S * np.exp(-2j * np.pi * f * delays_s[c]), nfft)[:T]
         out[:, c] = (sc + noise_sigma * rng.standard_normal(T)).astype(np.float32)
     return out
 

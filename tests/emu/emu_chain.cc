@@ -11,6 +11,8 @@
 
 using namespace btk;
 
+#define BTK_EMU_CASES(X) X(64, 2) X(128, 2) X(128, 4) X(256, 1) X(256, 2) X(256, 4) X(512, 2) X(512, 4) X(512, 8) X(1024, 2) X(1024, 4)
+
 template <int M> struct HostCtx {
   std::vector<ChainThreadState<M> > ts;
   int nt;
@@ -20,20 +22,20 @@ template <int M> struct HostCtx {
   void syncwarp() {}
 };
 
-template <int M, int R>
+template <int M, int R, int MT>
 static int run_chain(int m, int dct, int C, int n_rec, const long long* Ts, const float* pcm, const long long* pcm_off,
                      float* out, const long long* out_off, const double* h, const double* g, const double* w_re_im,
                      int gain, int chunk) {
-  typedef ChainCfg<M, R> K;
+  typedef ChainCfg<M, R, MT> K;
   BankGeom geo(M, m, /*r=*/0, dct);
   geo.r = 0; for (int x = R; x > 1; x >>= 1) geo.r++;
   geo = BankGeom(M, m, geo.r, dct);
   const int Cpad = (C + K::CG - 1) / K::CG * K::CG;
-  std::vector<cf> tw, gam;
-  std::vector<float> gp, hf(geo.N);
-  build_twiddles(M, tw);
+  std::vector<cf> twa, twb, gam;
+  std::vector<float> gp, hf;
+  build_fft_tables(M, twa, twb);
   build_synthesis_taps(g, M, m, gp);
-  for (int i = 0; i < geo.N; i++) hf[i] = (float)h[i];
+  build_analysis_taps(h, M, m, R, hf);
   std::vector<zd> w((size_t)geo.B * C);
   for (size_t i = 0; i < w.size(); i++) w[i] = zd(w_re_im[2 * i], w_re_im[2 * i + 1]);
   build_chain_weight_table(w.data(), M, C, Cpad, gam);
@@ -45,61 +47,66 @@ static int run_chain(int m, int dct, int C, int n_rec, const long long* Ts, cons
   build_work(recs, chunk, work);
   ChainParams p;
   p.pcm = pcm; p.out = out; p.recs = recs.data(); p.work = work.data();
-  p.taps_h = hf.data(); p.taps_g = gp.data(); p.wts = gam.data(); p.tw = tw.data();
+  p.taps_h = hf.data(); p.taps_g = gp.data(); p.wts = gam.data(); p.twa = twa.data(); p.twb = twb.data();
   p.C = C; p.Cpad = Cpad; p.m = m; p.pd_s = geo.pd_s; p.laN = geo.laN; p.gain = gain;
   const ChainSmem L = chain_smem_layout<M, R>(m);
   std::vector<unsigned char> smem(L.total + 64, 0xA5);   // poison: every read must have been written
   for (size_t wi = 0; wi < work.size(); wi++) {
     HostCtx<M> ctx(K::NT);
     memset(smem.data(), 0xA5, smem.size());
-    chain_tile<M, R>(ctx, p, smem.data(), (int)wi);
+    chain_tile<M, R, MT>(ctx, p, smem.data(), (int)wi);
   }
   return (int)work.size();
 }
 
 extern "C" int emu_chain(int M, int m, int r, int dct, int C, int n_rec, const long long* Ts, const float* pcm,
                          const long long* pcm_off, float* out, const long long* out_off, const double* h,
-                         const double* g, const double* w_re_im, int gain, int chunk) {
+                         const double* g, const double* w_re_im, int gain, int chunk, int fast) {
+  // fast != 0: the compile-time-m instantiation (MT = m) where one exists, like the library's dispatch
 #define CASE(MM, RR) \
-  if (M == MM && (1 << r) == RR) return run_chain<MM, RR>(m, dct, C, n_rec, Ts, pcm, pcm_off, out, out_off, h, g, w_re_im, gain, chunk);
-  CASE(64, 2) CASE(128, 2) CASE(128, 4) CASE(256, 1) CASE(256, 2) CASE(256, 4) CASE(512, 2) CASE(512, 4) CASE(512, 8) CASE(1024, 2) CASE(1024, 4)
+  if (M == MM && (1 << r) == RR) { \
+    if (fast && m == 2) return run_chain<MM, RR, 2>(m, dct, C, n_rec, Ts, pcm, pcm_off, out, out_off, h, g, w_re_im, gain, chunk); \
+    if (fast && m == 4) return run_chain<MM, RR, 4>(m, dct, C, n_rec, Ts, pcm, pcm_off, out, out_off, h, g, w_re_im, gain, chunk); \
+    return run_chain<MM, RR, 0>(m, dct, C, n_rec, Ts, pcm, pcm_off, out, out_off, h, g, w_re_im, gain, chunk); \
+  }
+  BTK_EMU_CASES(CASE)
 #undef CASE
   return -1;
 }
 
-template <int M, int R>
+template <int M, int R, int MT>
 static int run_analysis(int m, int dct, int C, long long T, const float* pcm, float* snap, const double* h, int chunk) {
-  typedef ChainCfg<M, R> K;
+  typedef ChainCfg<M, R, MT> K;
   int r = 0; for (int x = R; x > 1; x >>= 1) r++;
   BankGeom geo(M, m, r, dct);
   const int Cpad = (C + K::CG - 1) / K::CG * K::CG;
-  std::vector<cf> tw; std::vector<float> hf(geo.N);
-  build_twiddles(M, tw);
-  for (int i = 0; i < geo.N; i++) hf[i] = (float)h[i];
+  std::vector<cf> twa, twb; std::vector<float> hf;
+  build_fft_tables(M, twa, twb);
+  build_analysis_taps(h, M, m, R, hf);
   std::vector<RecDesc> recs(1);
   recs[0].pcm_off = 0; recs[0].out_off = 0; recs[0].T = (int)T; recs[0].nblk = geo.analysis_frames(T);
   std::vector<WorkItem> work;
   build_work(recs, chunk, work);
   AnalysisParams p;
   p.pcm = pcm; p.snap = reinterpret_cast<cf*>(snap); p.recs = recs.data(); p.work = work.data();
-  p.taps_h = hf.data(); p.tw = tw.data(); p.C = C; p.Cpad = Cpad; p.m = m; p.laN = geo.laN;
+  p.taps_h = hf.data(); p.twa = twa.data(); p.twb = twb.data(); p.C = C; p.Cpad = Cpad; p.m = m; p.laN = geo.laN;
   const ChainSmem L = chain_smem_layout<M, R>(m);
   std::vector<unsigned char> smem(L.total + 64);
   for (size_t wi = 0; wi < work.size(); wi++) {
     HostCtx<M> ctx(K::NT);
     memset(smem.data(), 0xA5, smem.size());
-    analysis_tile<M, R>(ctx, p, smem.data(), (int)wi);
+    analysis_tile<M, R, MT>(ctx, p, smem.data(), (int)wi);
   }
   return recs[0].nblk;
 }
 
-template <int M, int R>
+template <int M, int R, int MT>
 static int run_synthesis(int m, int dct, int F, const float* Y, float* out, const double* g, int gain, int chunk) {
-  typedef ChainCfg<M, R> K;
+  typedef ChainCfg<M, R, MT> K;
   int r = 0; for (int x = R; x > 1; x >>= 1) r++;
   BankGeom geo(M, m, r, dct);
-  std::vector<cf> tw; std::vector<float> gp;
-  build_twiddles(M, tw);
+  std::vector<cf> twa, twb; std::vector<float> gp;
+  build_fft_tables(M, twa, twb);
   build_synthesis_taps(g, M, m, gp);
   std::vector<RecDesc> recs(1);
   recs[0].pcm_off = 0; recs[0].out_off = 0; recs[0].T = F; recs[0].nblk = geo.synthesis_frames(F);
@@ -107,30 +114,34 @@ static int run_synthesis(int m, int dct, int F, const float* Y, float* out, cons
   build_work(recs, chunk, work);
   SynthesisParams p;
   p.Y = reinterpret_cast<const cf*>(Y); p.out = out; p.recs = recs.data(); p.work = work.data();
-  p.taps_g = gp.data(); p.tw = tw.data(); p.m = m; p.pd_s = geo.pd_s; p.gain = gain;
+  p.taps_g = gp.data(); p.twa = twa.data(); p.twb = twb.data(); p.m = m; p.pd_s = geo.pd_s; p.gain = gain;
   const ChainSmem L = chain_smem_layout<M, R>(m);
   std::vector<unsigned char> smem(L.total + 64);
   for (size_t wi = 0; wi < work.size(); wi++) {
     HostCtx<M> ctx(K::NT);
     memset(smem.data(), 0xA5, smem.size());
-    synthesis_tile<M, R>(ctx, p, smem.data(), (int)wi);
+    synthesis_tile<M, R, MT>(ctx, p, smem.data(), (int)wi);
   }
   return recs[0].nblk;
 }
 
-#define BTK_EMU_CASES(X) X(64, 2) X(128, 2) X(128, 4) X(256, 1) X(256, 2) X(256, 4) X(512, 2) X(512, 4) X(512, 8) X(1024, 2) X(1024, 4)
-
 extern "C" int emu_analysis(int M, int m, int r, int dct, int C, long long T, const float* pcm, float* snap,
-                            const double* h, int chunk) {
-#define CASE(MM, RR) if (M == MM && (1 << r) == RR) return run_analysis<MM, RR>(m, dct, C, T, pcm, snap, h, chunk);
+                            const double* h, int chunk, int fast) {
+#define CASE(MM, RR) if (M == MM && (1 << r) == RR) { \
+    if (fast && m == 2) return run_analysis<MM, RR, 2>(m, dct, C, T, pcm, snap, h, chunk); \
+    if (fast && m == 4) return run_analysis<MM, RR, 4>(m, dct, C, T, pcm, snap, h, chunk); \
+    return run_analysis<MM, RR, 0>(m, dct, C, T, pcm, snap, h, chunk); }
   BTK_EMU_CASES(CASE)
 #undef CASE
   return -1;
 }
 
 extern "C" int emu_synthesis(int M, int m, int r, int dct, int F, const float* Y, float* out, const double* g,
-                             int gain, int chunk) {
-#define CASE(MM, RR) if (M == MM && (1 << r) == RR) return run_synthesis<MM, RR>(m, dct, F, Y, out, g, gain, chunk);
+                             int gain, int chunk, int fast) {
+#define CASE(MM, RR) if (M == MM && (1 << r) == RR) { \
+    if (fast && m == 2) return run_synthesis<MM, RR, 2>(m, dct, F, Y, out, g, gain, chunk); \
+    if (fast && m == 4) return run_synthesis<MM, RR, 4>(m, dct, F, Y, out, g, gain, chunk); \
+    return run_synthesis<MM, RR, 0>(m, dct, F, Y, out, g, gain, chunk); }
   BTK_EMU_CASES(CASE)
 #undef CASE
   return -1;

@@ -42,8 +42,9 @@ CASES = [  # M, m, r, dct, C, T, chunk
 ]
 
 
+@pytest.mark.parametrize("fast", [1, 0])
 @pytest.mark.parametrize("case", CASES)
-def test_emulated_chain_matches_oracle(case, emu, prototypes):
+def test_emulated_chain_matches_oracle(case, fast, emu, prototypes):
     M, m, r, dct, C, T, chunk = case
     h, g = proto(prototypes, M, m, r)
     geo = bo.BankGeometry(M, m, r, dct)
@@ -54,13 +55,14 @@ def test_emulated_chain_matches_oracle(case, emu, prototypes):
     out = np.zeros(geo.nblk(T) * geo.D, np.float32)
     Ts, z = np.array([T], np.int64), np.array([0], np.int64)
     Wc = np.ascontiguousarray(W, dtype=np.complex128)
-    n = emu.emu_chain(M, m, r, dct, C, 1, vp(Ts), vp(pcm), vp(z), vp(out), vp(z), vp(h), vp(g), vp(Wc), 1, chunk)
+    n = emu.emu_chain(M, m, r, dct, C, 1, vp(Ts), vp(pcm), vp(z), vp(out), vp(z), vp(h), vp(g), vp(Wc), 1, chunk, fast)
     assert n > 0
     assert bo.snr_db(out, ref) > 100.0   # north_star gate is 70 dB
 
 
+@pytest.mark.parametrize("fast", [1, 0])
 @pytest.mark.parametrize("case", CASES[:6])
-def test_emulated_staged_tiles_match_oracle(case, emu, prototypes):
+def test_emulated_staged_tiles_match_oracle(case, fast, emu, prototypes):
     M, m, r, dct, C, T, chunk = case
     chunk = (chunk + 15) // 16 * 16
     h, g = proto(prototypes, M, m, r)
@@ -69,11 +71,11 @@ def test_emulated_staged_tiles_match_oracle(case, emu, prototypes):
     X = np.stack([bo.analysis(pcm[:, c], h, geo) for c in range(C)], axis=1)
     F, B = X.shape[0], geo.B
     snap = np.zeros((F, B, C, 2), np.float32)
-    assert emu.emu_analysis(M, m, r, dct, C, T, vp(pcm), vp(snap), vp(h), chunk) == F
+    assert emu.emu_analysis(M, m, r, dct, C, T, vp(pcm), vp(snap), vp(h), chunk, fast) == F
     assert bo.rel_l2(snap.view(np.complex64)[..., 0], X[:, :, :B].transpose(0, 2, 1)) < 1e-5   # gate: 1e-4
     Y = X[:, 0, :]
     ref = bo.synthesis(Y, g, geo).reshape(-1)
     Yh = np.ascontiguousarray(Y[:, :B]).astype(np.complex64)
     out = np.zeros(geo.synthesis_frames(F) * geo.D, np.float32)
-    emu.emu_synthesis(M, m, r, dct, F, vp(Yh), vp(out), vp(g), 1, chunk)
+    emu.emu_synthesis(M, m, r, dct, F, vp(Yh), vp(out), vp(g), 1, chunk, fast)
     assert bo.snr_db(out, ref) > 100.0
