@@ -363,39 +363,81 @@ BTK_HD void analysis_round(Ctx& ctx, const ChainSmem& L, const float* s_xs, cons
   });
 }
 
-// Stage CG channels [cg0, cg0+CG) of the window starting at sample t_lo: pcm [t][C] -> s_xs[c][t mod D][t div D].
+// Stage CG channels [cg0, cg0+CG) of the window starting at sample t_lo: pcm [t][C] -> s_xs[c][t mod D][t div D],
+// and (when wts != 0) the weights of those channels, already in register order, into s_wts.
 // A warp covers 16 consecutive residues of two consecutive D-blocks per step: the global reads are two
-// coalesced runs and the residue-major stores hit 32 distinct banks (SB/2 is odd).
+// coalesced runs and the residue-major stores hit 32 distinct banks (SB/2 is odd).  All global loads of a
+// thread are issued before its first shared-memory store (one DRAM/L2 round trip per stage, not one per step).
 template <class K, class Ctx>
 BTK_HD void stage_window(Ctx& ctx, const ChainSmem& L, float* s_xs, const float* pcm, int C, int T, long long t_lo,
-                         int cg0, bool vec4) {
+                         int cg0, bool vec4, float4* s_wts, const cf* wts) {
   typedef ChainThreadState<K::M> TS;
   constexpr int D = K::D;
   constexpr int RT = (D + 15) / 16;
+  constexpr int WPT = (K::CG * K::M / 2 + K::NT - 1) / K::NT;   // weight float4 per thread
+  constexpr int STEPS = 6;                                      // tiles in flight per thread
   ctx.par([&](int tid, TS&) {
     const int warp = tid >> 5, lane = tid & 31, sub = lane & 15, hb = lane >> 4;
     const int ntile = ((L.NB + 1) / 2) * RT;
-    BTK_UNROLL_N(4)
-    for (int tile = warp; tile < ntile; tile += K::NW) {
-      const int res = (tile % RT) * 16 + sub, blk = 2 * (tile / RT) + hb;
-      if (res >= D || blk >= L.NB) continue;
-      const long long t = t_lo + (long long)blk * D + res;
-      float x[K::CG];
+    float4 wv[WPT];
+    if (wts) {
+      const float4* src = reinterpret_cast<const float4*>(wts + (long long)cg0 * K::M);
       BTK_UNROLL
-      for (int c = 0; c < K::CG; c++) x[c] = 0.f;
-      if (t >= 0 && t < T) {
-        const float* src = pcm + t * C + cg0;
-        if (vec4 && cg0 + K::CG <= C) {
-          const float4 q = *reinterpret_cast<const float4*>(src);
-          x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
-        } else {
-          BTK_UNROLL
-          for (int c = 0; c < K::CG; c++) if (cg0 + c < C) x[c] = src[c];
+      for (int i = 0; i < WPT; i++) {
+        const int idx = tid + i * K::NT;
+        if (idx < K::CG * K::M / 2) wv[i] = src[idx];
+      }
+    }
+    for (int tile0 = warp; tile0 < ntile; tile0 += K::NW * STEPS) {
+      float x[STEPS][K::CG];
+      BTK_UNROLL
+      for (int s = 0; s < STEPS; s++) {
+        const int tile = tile0 + s * K::NW;
+        const int res = (tile % RT) * 16 + sub, blk = 2 * (tile / RT) + hb;
+        const long long t = t_lo + (long long)blk * D + res;
+        BTK_UNROLL
+        for (int c = 0; c < K::CG; c++) x[s][c] = 0.f;
+        if (tile < ntile && res < D && blk < L.NB && t >= 0 && t < T) {
+          const float* src = pcm + t * C + cg0;
+          if (vec4 && cg0 + K::CG <= C) {
+            const float4 q = *reinterpret_cast<const float4*>(src);
+            x[s][0] = q.x; x[s][1] = q.y; x[s][2] = q.z; x[s][3] = q.w;
+          } else {
+            BTK_UNROLL
+            for (int c = 0; c < K::CG; c++) if (cg0 + c < C) x[s][c] = src[c];
+          }
         }
       }
       BTK_UNROLL
-      for (int c = 0; c < K::CG; c++) s_xs[c * L.CS + res * L.SB + blk] = x[c];
+      for (int s = 0; s < STEPS; s++) {
+        const int tile = tile0 + s * K::NW;
+        const int res = (tile % RT) * 16 + sub, blk = 2 * (tile / RT) + hb;
+        if (tile < ntile && res < D && blk < L.NB) {
+          BTK_UNROLL
+          for (int c = 0; c < K::CG; c++) s_xs[c * L.CS + res * L.SB + blk] = x[s][c];
+        }
+      }
     }
+    if (wts) {
+      BTK_UNROLL
+      for (int i = 0; i < WPT; i++) {
+        const int idx = tid + i * K::NT;
+        if (idx < K::CG * K::M / 2) s_wts[idx] = wv[i];
+      }
+    }
+  });
+}
+
+// Ask L2 for the samples the NEXT iteration will stage that this one has not touched: W*D new time steps of
+// all C channels.  Issued before the compute rounds so that the next staging pass finds them in L2.
+template <class K, class Ctx>
+BTK_HD void prefetch_next_window(Ctx& ctx, const float* pcm, int C, int T, long long t_first) {
+  typedef ChainThreadState<K::M> TS;
+  ctx.par([&](int tid, TS&) {
+    long long lo = t_first < 0 ? 0 : t_first, hi = t_first + (long long)K::W * K::D;
+    if (hi > T) hi = T;
+    const long long b0 = lo * C, b1 = hi * C;      // float index range
+    for (long long i = b0 + (long long)tid * 32; i < b1; i += (long long)K::NT * 32) BTK_PREFETCH_L2(pcm + i);
   });
 }
 
@@ -465,12 +507,9 @@ BTK_HD void chain_tile(Ctx& ctx, const ChainParams& p, unsigned char* smem, int 
     });
 
     for (int cg0 = 0; cg0 < p.Cpad; cg0 += K::CG) {
-      stage_window<K>(ctx, L, s_xs, pcm, C, rec.T, t_lo, cg0, vec4);
-      // the weights of these CG channels, already in register order: [c][V/2][L] float4 = 2 complex
-      ctx.par([&](int tid, TS&) {
-        const float4* src = reinterpret_cast<const float4*>(p.wts + (long long)cg0 * M_);
-        for (int i = tid; i < K::CG * M_ / 2; i += K::NT) s_wts[i] = src[i];
-      });
+      // samples + the weights of these CG channels (register order: [c][V/2][L] float4 = 2 complex)
+      stage_window<K>(ctx, L, s_xs, pcm, C, rec.T, t_lo, cg0, vec4, s_wts, p.wts);
+      if (cg0 == 0 && it + 1 < n_it) prefetch_next_window<K>(ctx, pcm, C, rec.T, t_lo + (long long)L.NB * K::D);
       ctx.sync();
 
       // ---- per warp: frame pair (tau0, tau0+1); per lane group: one channel per round

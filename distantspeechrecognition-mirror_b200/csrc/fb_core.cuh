@@ -21,7 +21,13 @@
 #define BTK_UNROLL _Pragma("unroll")
 #define BTK_UNROLL_N(n) _Pragma(BTK_STR(unroll n))
 #define BTK_STR(x) #x
+#if defined(__CUDA_ARCH__)
+#define BTK_PREFETCH_L2(ptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr))
 #else
+#define BTK_PREFETCH_L2(ptr) ((void)(ptr))
+#endif
+#else
+#define BTK_PREFETCH_L2(ptr) ((void)(ptr))
 #define BTK_HD inline
 #define BTK_UNROLL
 #define BTK_UNROLL_N(n)

@@ -53,7 +53,7 @@ BTK_HD void analysis_tile(Ctx& ctx, const AnalysisParams& p, unsigned char* smem
     const int f_base = wk.j0 + it * K::W;          // emitted frame index t; internal frame i = t + laN
     const long long t_lo = (long long)(f_base + p.laN + 1) * K::D - N;
     for (int cg0 = 0; cg0 < p.Cpad; cg0 += K::CG) {
-      stage_window<K>(ctx, L, s_xs, pcm, C, rec.T, t_lo, cg0, vec4);
+      stage_window<K>(ctx, L, s_xs, pcm, C, rec.T, t_lo, cg0, vec4, (float4*)0, (const cf*)0);
       ctx.sync();
       for (int round = 0; round < K::CG / K::NG; round++) {
         analysis_round<K>(ctx, L, s_xs, s_taps, s_xbuf, s_twa, s_twb, m, round);
