@@ -180,18 +180,24 @@ BTK_HD void polyphase_pair(cf* z, int gl, const float* xrow, const float* taps, 
       const int rho = gl + G::L * rep + G::JA * e0;
       const float* xp = xrow + (K::D - 1 - rho) * L.SB;   // xp[b]: block b of this warp's span; s_t = xp[mR - t]
       const float* hp = taps + rho * L.TS;
-      float u0[R_], u1[R_];
+      cf u[R_];          // (u_{i0}, u_{i1})[rho + D a]
       BTK_UNROLL
-      for (int a = 0; a < R_; a++) { u0[a] = 0.f; u1[a] = 0.f; }
+      for (int a = 0; a < R_; a++) u[a] = mk(0.f, 0.f);
       if (K::MT > 0) {
         constexpr int mR = (K::MT > 0 ? K::MT : 1) * R_;
-        float xb[mR + 1], h[mR];
+        float xb[mR + 2], h[mR];
         load_floats<mR + 1, 2>(xb, xp);
         load_floats<mR, tap_vec(mR)>(h, hp);
+        // (u_{i0}, u_{i1}) += h_t (s_{t+1}, s_t) = h_t (xb[mR-t-1], xb[mR-t]): where that is an aligned pair of the
+        // float2 loads (mR-t-1 even) it is one packed FFMA2, otherwise two scalar ones
         BTK_UNROLL
         for (int t = 0; t < mR; t++) {
-          u1[t % R_] = fmaf(h[t], xb[mR - t], u1[t % R_]);
-          u0[t % R_] = fmaf(h[t], xb[mR - t - 1], u0[t % R_]);
+          if (((mR - t - 1) & 1) == 0) {
+            u[t % R_] = cfma_real(mk(xb[mR - t - 1], xb[mR - t]), h[t], u[t % R_]);
+          } else {
+            u[t % R_].y = fmaf(h[t], xb[mR - t], u[t % R_].y);
+            u[t % R_].x = fmaf(h[t], xb[mR - t - 1], u[t % R_].x);
+          }
         }
       } else {
         const int mR = m * R_;
@@ -200,13 +206,13 @@ BTK_HD void polyphase_pair(cf* z, int gl, const float* xrow, const float* taps, 
           for (int a = 0; a < R_; a++) {
             const int t = a + R_ * k;
             const float h = hp[t];
-            u1[a] = fmaf(h, xp[mR - t], u1[a]);
-            u0[a] = fmaf(h, xp[mR - t - 1], u0[a]);
+            u[a].y = fmaf(h, xp[mR - t], u[a].y);
+            u[a].x = fmaf(h, xp[mR - t - 1], u[a].x);
           }
         }
       }
       BTK_UNROLL
-      for (int a = 0; a < R_; a++) z[rep * G::Ra + e0 + K::E * a] = mk(u0[a], u1[a]);
+      for (int a = 0; a < R_; a++) z[rep * G::Ra + e0 + K::E * a] = u[a];
     }
   }
 }
@@ -375,10 +381,14 @@ BTK_HD void stage_window(Ctx& ctx, const ChainSmem& L, float* s_xs, const float*
   constexpr int D = K::D;
   constexpr int RT = (D + 15) / 16;
   constexpr int WPT = (K::CG * K::M / 2 + K::NT - 1) / K::NT;   // weight float4 per thread
-  constexpr int STEPS = 6;                                      // tiles in flight per thread
+  constexpr int STEPS = 6;                                      // loads in flight per thread
+  // warp -> (residue tile, first block pair); both strides are compile-time constants
+  constexpr int RSTEP = K::NW >= RT ? RT : K::NW;               // residue-tile stride of the outer loop
+  constexpr int BSTEP = K::NW >= RT ? K::NW / RT : 1;           // block-pair stride of the inner loop
+  static_assert((K::NW >= RT) ? (K::NW % RT == 0) : (RT % K::NW == 0), "warps and residue tiles must nest");
   ctx.par([&](int tid, TS&) {
     const int warp = tid >> 5, lane = tid & 31, sub = lane & 15, hb = lane >> 4;
-    const int ntile = ((L.NB + 1) / 2) * RT;
+    const int nbp = (L.NB + 1) / 2;
     float4 wv[WPT];
     if (wts) {
       const float4* src = reinterpret_cast<const float4*>(wts + (long long)cg0 * K::M);
@@ -388,33 +398,37 @@ BTK_HD void stage_window(Ctx& ctx, const ChainSmem& L, float* s_xs, const float*
         if (idx < K::CG * K::M / 2) wv[i] = src[idx];
       }
     }
-    for (int tile0 = warp; tile0 < ntile; tile0 += K::NW * STEPS) {
-      float x[STEPS][K::CG];
-      BTK_UNROLL
-      for (int s = 0; s < STEPS; s++) {
-        const int tile = tile0 + s * K::NW;
-        const int res = (tile % RT) * 16 + sub, blk = 2 * (tile / RT) + hb;
-        const long long t = t_lo + (long long)blk * D + res;
+    for (int rt = warp % RSTEP; rt < RT; rt += RSTEP) {
+      const int res = rt * 16 + sub;
+      if (res >= D) continue;
+      float* dst = s_xs + res * L.SB + hb;
+      const long long t_res = t_lo + res + (long long)hb * D;
+      for (int bp0 = (K::NW >= RT ? warp / RT : 0); bp0 < nbp; bp0 += BSTEP * STEPS) {
+        float x[STEPS][K::CG];
         BTK_UNROLL
-        for (int c = 0; c < K::CG; c++) x[s][c] = 0.f;
-        if (tile < ntile && res < D && blk < L.NB && t >= 0 && t < T) {
-          const float* src = pcm + t * C + cg0;
-          if (vec4 && cg0 + K::CG <= C) {
-            const float4 q = *reinterpret_cast<const float4*>(src);
-            x[s][0] = q.x; x[s][1] = q.y; x[s][2] = q.z; x[s][3] = q.w;
-          } else {
-            BTK_UNROLL
-            for (int c = 0; c < K::CG; c++) if (cg0 + c < C) x[s][c] = src[c];
+        for (int s = 0; s < STEPS; s++) {
+          const int bp = bp0 + s * BSTEP;
+          const long long t = t_res + (long long)bp * (2 * D);
+          BTK_UNROLL
+          for (int c = 0; c < K::CG; c++) x[s][c] = 0.f;
+          if (2 * bp + hb < L.NB && t >= 0 && t < T) {
+            const float* src = pcm + t * C + cg0;
+            if (vec4 && cg0 + K::CG <= C) {
+              const float4 q = *reinterpret_cast<const float4*>(src);
+              x[s][0] = q.x; x[s][1] = q.y; x[s][2] = q.z; x[s][3] = q.w;
+            } else {
+              BTK_UNROLL
+              for (int c = 0; c < K::CG; c++) if (cg0 + c < C) x[s][c] = src[c];
+            }
           }
         }
-      }
-      BTK_UNROLL
-      for (int s = 0; s < STEPS; s++) {
-        const int tile = tile0 + s * K::NW;
-        const int res = (tile % RT) * 16 + sub, blk = 2 * (tile / RT) + hb;
-        if (tile < ntile && res < D && blk < L.NB) {
-          BTK_UNROLL
-          for (int c = 0; c < K::CG; c++) s_xs[c * L.CS + res * L.SB + blk] = x[s][c];
+        BTK_UNROLL
+        for (int s = 0; s < STEPS; s++) {
+          const int bp = bp0 + s * BSTEP;
+          if (2 * bp + hb < L.NB) {
+            BTK_UNROLL
+            for (int c = 0; c < K::CG; c++) dst[c * L.CS + 2 * bp] = x[s][c];
+          }
         }
       }
     }
