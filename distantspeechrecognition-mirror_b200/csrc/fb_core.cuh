@@ -219,13 +219,24 @@ template <int M_, int S> struct GroupFFT {
       cf* p = v + rep * G::Ra;
       Dft<G::Ra, S>::run(p);
       const int j = gl + G::L * rep;
-      const float4* t4 = reinterpret_cast<const float4*>(twa + j * FT::TA);
       cf w[G::Ra + 1];
-      BTK_UNROLL
-      for (int i = 0; i < G::Ra / 2; i++) {
-        const float4 t = t4[i];
-        w[2 * i + 1] = mk(t.x, t.y);
-        w[2 * i + 2] = mk(t.z, t.w);
+      if (G::Rb == 1) {
+        // two-pass transforms: W_M^{j ka} from W_M^j by a product tree of depth <= 4.  The packed multiplies are
+        // cheaper than the shared-memory bandwidth a table read would take (the kernel is LDS-bound).
+        w[1] = twa[j * FT::TA];
+        BTK_UNROLL
+        for (int ka = 2; ka < G::Ra; ka++) {
+          const int hi = ka >= 8 ? 8 : (ka >= 4 ? 4 : 2);        // largest power of two <= ka
+          w[ka] = (ka == hi) ? cmul(w[ka / 2], w[ka / 2]) : cmul(w[hi], w[ka - hi]);
+        }
+      } else {
+        const float4* t4 = reinterpret_cast<const float4*>(twa + j * FT::TA);
+        BTK_UNROLL
+        for (int i = 0; i < G::Ra / 2; i++) {
+          const float4 t = t4[i];
+          w[2 * i + 1] = mk(t.x, t.y);
+          w[2 * i + 2] = mk(t.z, t.w);
+        }
       }
       BTK_UNROLL
       for (int ka = 1; ka < G::Ra; ka++) p[ka] = multw<S>(p[ka], w[ka]);
