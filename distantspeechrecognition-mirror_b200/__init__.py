@@ -5,7 +5,10 @@ reference's stream API.
 The directory name carries a hyphen (it mirrors the upstream repository name); import it through the
 ``btk_b200`` shim at the repository root:  ``import btk_b200``.
 """
-from . import _capi, workloads  # noqa: F401
+from . import _capi, streams, workloads  # noqa: F401
 from ._capi import BtkError, Plan, device_count, lib  # noqa: F401
+from .streams import (OverSampledDFTAnalysisBankPtr, OverSampledDFTSynthesisBankPtr, SampleFeaturePtr,  # noqa: F401
+                      SubbandDSPtr, SubbandMVDRPtr)
 
-__all__ = ["Plan", "BtkError", "device_count", "lib", "workloads"]
+__all__ = ["Plan", "BtkError", "device_count", "lib", "workloads", "streams", "SampleFeaturePtr",
+           "OverSampledDFTAnalysisBankPtr", "OverSampledDFTSynthesisBankPtr", "SubbandDSPtr", "SubbandMVDRPtr"]

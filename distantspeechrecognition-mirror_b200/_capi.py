@@ -155,6 +155,12 @@ class Plan:
         return int(self._L.btkb200_synthesis_frames(self._h, F))
 
     # -- weights
+    def has_weights(self) -> int:
+        """0 none, 1 delay-and-sum, 2 user / MVDR (re-queried: the flag changes after construction)."""
+        inf = Info()
+        self._L.btkb200_plan_info(self._h, ctypes.byref(inf))
+        return int(inf.has_weights)
+
     def set_ds_weights(self, fs: float, delays):
         d = np.ascontiguousarray(delays, dtype=np.float64)
         self._ck(self._L.btkb200_set_ds_weights(self._h, fs, _p(d), d.size))

@@ -1,0 +1,507 @@
+"""Drop-in feature-stream nodes: the reference's Python-visible ``*Ptr`` surface for the hot path, computed by the
+sm_100a kernels behind the C ABI (include/btkb200.h).
+
+Mirrors (paths relative to /root/reference/btk):
+  FeatureStream protocol  next(frameX=-5) / reset() / size() / isEnd() / current()      stream/stream.h:35-75
+  iterator glue           __iter__ = reset() + self, jiterator_error -> StopIteration    modulated/modulated.i:117-173,
+                                                                                        include/jexception.i:57-82
+  SampleFeature           block source, blockLen/shiftLen/padZeros                       feature/feature.cc:610-659
+  OverSampledDFTAnalysisBankPtr(samp, prototype, M, m, r, delayCompensationType)         modulated/modulated.i:117-132
+  OverSampledDFTSynthesisBankPtr(samp, prototype, M, m, r, delayCompensationType, gainFactor)   modulated.i:157-173
+  SubbandDSPtr(fftLen, halfBandShift) / SubbandMVDRPtr(fftLen, halfBandShift)           beamformer/beamformer.i:171-184, 319-332
+
+The reference pulls one frame per ``next()`` through the whole chain on one CPU thread.  These nodes keep that
+pull API but evaluate lazily per UTTERANCE: the first ``next()`` of a node drains its upstream (which may be a plain
+Python iterator, like PyVectorComplexFeatureStream allows, btk/stream/pyStream.h:89-130), runs the device kernels
+once, and then serves frames from the result.  When a synthesis bank sits on a SubbandDS/SubbandMVDR whose channels
+are all analysis banks of this module, the three stages run as ONE fused kernel (btkb200_chain) and no subband data
+ever reaches the host.  ``next()`` returns a view of the node's own buffer that the following ``next()`` overwrites
+(the reference's non-owning numpy view, include/vector.i:196-211 -- copy it if you keep it).
+
+There is no CPU path here: every number comes from libbtkb200.so; without a GPU the nodes raise BtkError.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _capi
+from ._capi import BtkError, Plan
+
+FrameResetX = -1
+
+
+class j_error(Exception):
+    """btk/common/jexception.h:41-173 (code JERROR)."""
+
+
+class jdimension_error(j_error):
+    pass
+
+
+class jconsistency_error(j_error):
+    pass
+
+
+class jiterator_error(StopIteration):
+    """End of stream.  The SWIG layer maps it to StopIteration (include/jexception.i:63-65)."""
+
+
+def _raise(e: BtkError):
+    """C-ABI status -> the exception type the reference throws at that point (include/btkb200.h)."""
+    if e.code == _capi.EINVAL:
+        raise jdimension_error(e.msg) from None
+    if e.code == _capi.ESTATE:
+        raise j_error(e.msg) from None
+    raise e
+
+
+class FeatureStream:
+    """stream/stream.h:35-75."""
+
+    def __init__(self, size: int, name: str):
+        self._size, self._name = int(size), name
+        self._frameX, self._endOfSamples = FrameResetX, False
+        self._vector = None
+
+    def name(self):
+        return self._name
+
+    def size(self):
+        return self._size
+
+    def frameX(self):
+        return self._frameX
+
+    def isEnd(self):
+        return self._endOfSamples
+
+    def current(self):
+        if self._frameX < 0:
+            raise jconsistency_error(f"Frame index ({self._frameX}) < 0.")
+        return self.next(self._frameX)
+
+    def reset(self):
+        self._frameX, self._endOfSamples = FrameResetX, False
+
+    def next(self, frameX: int = -5):  # pragma: no cover - interface
+        raise NotImplementedError
+
+    # Python iterator glue of the SWIG shadow classes (modulated.i:126-128)
+    def __iter__(self):
+        self.reset()
+        return self
+
+    def __next__(self):
+        return self.next()
+
+
+class SampleFeaturePtr(FeatureStream):
+    """In-memory block source with SampleFeature::next's rule (feature/feature.cc:610-659): blocks of ``blockLen``
+    samples every ``shiftLen``; with ``padZeros`` the last partial block is zero padded, then jiterator_error.
+    ``samples`` is one channel (1-D) of un-normalised float samples (feature.cc:273)."""
+
+    def __init__(self, samples=None, blockLen: int = 320, shiftLen: int = 160, padZeros: bool = False,
+                 nm: str = "Sample"):
+        super().__init__(blockLen, nm)
+        self._shift, self._pad = int(shiftLen), bool(padZeros)
+        self._samples = np.zeros(0, np.float32) if samples is None else np.ascontiguousarray(samples, np.float32).ravel()
+        self._cur = 0
+        self._vector = np.zeros(blockLen, np.float32)
+
+    def setSamples(self, samples, sampleRate: float = 16000.0):
+        self._samples = np.ascontiguousarray(samples, np.float32).ravel()
+        self.reset()
+
+    def samples(self):
+        return self._samples
+
+    def reset(self):
+        super().reset()
+        self._cur = 0
+
+    def next(self, frameX: int = -5):
+        if frameX == self._frameX:
+            return self._vector
+        if frameX >= 0 and frameX - 1 != self._frameX:      # feature.cc:622-625
+            raise jconsistency_error(f"Problem in Feature {self._name}: {frameX - 1} != {self._frameX}")
+        T, n = self._samples.size, self._size
+        if self._cur >= T or (not self._pad and self._cur + n > T):
+            self._endOfSamples = True
+            raise jiterator_error("end of samples!")
+        blk = self._samples[self._cur:self._cur + n]
+        self._vector[:blk.size] = blk
+        self._vector[blk.size:] = 0.0
+        self._cur += self._shift
+        self._frameX += 1
+        return self._vector
+
+
+def _drain(stream) -> list:
+    """Pull every remaining frame of an upstream node or plain iterator (copies: upstream reuses its buffer)."""
+    frames = []
+    if isinstance(stream, FeatureStream):
+        while True:
+            try:
+                frames.append(np.array(stream.next(), copy=True))
+            except StopIteration:
+                break
+    else:
+        for f in stream:
+            frames.append(np.array(f, copy=True))
+    return frames
+
+
+class _FilterBank:
+    def _geometry(self, prototype, M, m, r, dct):
+        self._M, self._m, self._r, self._dct = int(M), int(m), int(r), int(dct)
+        self._R = 1 << self._r
+        self._D = self._M // self._R
+        proto = np.ascontiguousarray(prototype, np.float64).ravel()
+        if proto.size != self._M * self._m:      # modulated.cc:269-271
+            raise jconsistency_error(f"Prototype sizes do not match ({proto.size} vs. {self._M * self._m}).")
+        self._prototype = proto.copy()           # copied at construction (modulated.cc:275-276)
+
+    def fftLen(self):
+        return self._M
+
+    def polyphase(self, m, n):
+        return float(self._prototype[m + self._M * n])     # modulated.h:233-236
+
+
+class OverSampledDFTAnalysisBankPtr(FeatureStream, _FilterBank):
+    """modulated/modulated.cc:359-516.  ``next()`` yields complex128[M] full Hermitian spectra."""
+
+    def __init__(self, samp, prototype, M: int = 256, m: int = 3, r: int = 0, delayCompensationType: int = 0,
+                 nm: str = "OverSampledDFTAnalysisBank"):
+        FeatureStream.__init__(self, M, nm)
+        self._geometry(prototype, M, m, r, delayCompensationType)
+        self._samp = samp
+        self._frames = None
+        self._plan = None
+        self._vector = np.zeros(M, np.complex128)
+
+    def nBlocks(self):
+        return 4
+
+    def subSampRate(self):
+        return 2
+
+    # -- hooks for the fused path
+    def _source_samples(self):
+        """All samples of this bank's source as one float32 array, or None when the source is not a block source
+        with blockLen == shiftLen == D (then frames have to be pulled one by one)."""
+        s = self._samp
+        if isinstance(s, SampleFeaturePtr) and s.size() == self._D and s._shift == self._D and s._pad:
+            return s.samples()
+        return None
+
+    def _pull_source(self) -> np.ndarray:
+        direct = self._source_samples()
+        if direct is not None:
+            return direct
+        blocks = _drain(self._samp)          # any exception from the source ends the input (modulated.cc:493-501)
+        for b in blocks:
+            if b.size != self._D:
+                raise jdimension_error(f"Input block length ({b.size}) != D ({self._D})")
+        return np.concatenate(blocks).astype(np.float32) if blocks else np.zeros(0, np.float32)
+
+    def _evaluate(self):
+        x = self._pull_source()
+        try:
+            if self._plan is None:
+                self._plan = Plan(self._M, self._m, self._r, 1, h=self._prototype, dct=self._dct)
+            snap = self._plan.analysis(x[:, None])[:, :, 0]           # [F][B]
+        except BtkError as e:
+            _raise(e)
+        self._frames = snap
+
+    def next(self, frameX: int = -5):
+        if frameX == self._frameX and self._frameX >= 0:
+            return self._vector
+        if self._frames is None:
+            self._evaluate()
+        t = self._frameX + 1
+        if t >= self._frames.shape[0]:
+            self._endOfSamples = True
+            raise jiterator_error("end of samples!")
+        half = self._frames[t]
+        B = self._M // 2 + 1
+        self._vector[:B] = half
+        self._vector[B:] = np.conj(half[1:self._M // 2][::-1])       # X[M-s] = conj X[s]
+        self._frameX = t
+        return self._vector
+
+    def reset(self):
+        FeatureStream.reset(self)
+        if isinstance(self._samp, FeatureStream):
+            self._samp.reset()
+        self._frames = None
+
+
+class _SubbandBeamformer(FeatureStream):
+    """SubbandBeamformer: ordered channel list, snapshot array, weight apply (beamformer.cc:1017-1048, 1137-1200)."""
+
+    def __init__(self, fftLen: int, halfBandShift: bool, nm: str):
+        super().__init__(fftLen, nm)
+        if halfBandShift:
+            raise j_error("halfBandShift is not supported by the B200 engine")
+        self._fftLen = int(fftLen)
+        self._channels = []
+        self._plan = None
+        self._Y = None
+        self._snap = None
+        self._vector = np.zeros(fftLen, np.complex128)
+
+    def setChannel(self, chan):
+        self._channels.append(chan)
+
+    def clearChannel(self):
+        self._channels = []
+        self._drop_plan()
+
+    def chanN(self):
+        return len(self._channels)
+
+    def fftLen(self):
+        return self._fftLen
+
+    def dim(self):
+        return self._fftLen
+
+    def _drop_plan(self):
+        if self._plan is not None:
+            self._plan.close()
+        self._plan = None
+
+    def _need_plan(self) -> Plan:
+        C = self.chanN()
+        if C == 0:
+            raise j_error("No channel is set")
+        if self._plan is None or self._plan.C != C:
+            self._drop_plan()
+            # geometry of the analysis side when the channels are our banks (needed for the staged analysis call)
+            a = self._channels[0]
+            if isinstance(a, OverSampledDFTAnalysisBankPtr):
+                self._plan = Plan(self._fftLen, a._m, a._r, C, h=a._prototype, dct=a._dct)
+            else:
+                self._plan = Plan(self._fftLen, 1, 0, C)
+        return self._plan
+
+    def calcArrayManifoldVectors(self, sampleRate: float, delays):
+        """beamformer.cc:1087-1091 -> beamformerWeights::calcMainlobe (:531-594)."""
+        d = np.ascontiguousarray(delays, np.float64).ravel()
+        if d.size != self.chanN():
+            raise jdimension_error(f"Number of delays does not match number of channels ({d.size} vs. {self.chanN()}).")
+        try:
+            self._need_plan().set_ds_weights(sampleRate, d)
+        except BtkError as e:
+            _raise(e)
+        self._weights_changed()
+
+    def _weights_changed(self):
+        self._Y = None
+
+    def getWeights(self, fbinX: int):
+        try:
+            return self._need_plan().get_weights()[fbinX]
+        except BtkError as e:
+            _raise(e)
+
+    def _all_own_banks(self) -> bool:
+        chans = self._channels
+        return bool(chans) and all(isinstance(c, OverSampledDFTAnalysisBankPtr) and c._frameX == FrameResetX and
+                                   (c._M, c._m, c._r, c._dct) == (chans[0]._M, chans[0]._m, chans[0]._r, chans[0]._dct)
+                                   and c._M == self._fftLen for c in chans)
+
+    def _interleaved_pcm(self):
+        """[T][C] float32 from the channels' sources when every channel is one of our analysis banks."""
+        xs = [c._pull_source() for c in self._channels]
+        T = max(x.size for x in xs)
+        pcm = np.zeros((T, len(xs)), np.float32)
+        for c, x in enumerate(xs):
+            pcm[:x.size, c] = x
+        return pcm
+
+    def _check_weights(self):
+        if not self._need_plan().has_weights():
+            raise j_error("call calcArrayManifoldVectorsX() once")   # beamformer.cc:1140-1143
+
+    def _evaluate(self):
+        self._check_weights()
+        p = self._plan
+        try:
+            if self._all_own_banks():
+                snap = p.analysis(self._interleaved_pcm())                     # one multichannel launch
+            else:
+                per = [_drain(c) for c in self._channels]
+                F = min(len(f) for f in per)
+                B = self._fftLen // 2 + 1
+                snap = np.empty((F, B, len(per)), np.complex64)
+                for c, fr in enumerate(per):
+                    snap[:, :, c] = np.asarray(fr[:F])[:, :B]
+            self._snap = snap
+            self._Y = p.beamform(snap)
+        except BtkError as e:
+            _raise(e)
+
+    def snapShotArray_f(self, fbinX: int):
+        if self._snap is None or self._frameX < 0:
+            raise j_error("no snapshot yet")
+        return self._snap[self._frameX, fbinX].astype(np.complex128)
+
+    def next(self, frameX: int = -5):
+        if frameX == self._frameX and self._frameX >= 0:
+            return self._vector
+        if self._Y is None:
+            self._evaluate()
+        t = self._frameX + 1
+        if t >= self._Y.shape[0]:
+            self._endOfSamples = True
+            raise jiterator_error("end of samples!")
+        half = self._Y[t]
+        B, M = self._fftLen // 2 + 1, self._fftLen
+        self._vector[:B] = half
+        self._vector[B:] = np.conj(half[1:M // 2][::-1])       # beamformer.cc:1189-1194
+        self._frameX = t
+        return self._vector
+
+    def reset(self):
+        super().reset()
+        for c in self._channels:
+            if isinstance(c, FeatureStream):
+                c.reset()
+        self._Y = None
+        self._snap = None
+
+
+class SubbandDSPtr(_SubbandBeamformer):
+    """beamformer/beamformer.h:159-182."""
+
+    def __init__(self, fftLen: int = 512, halfBandShift: bool = False, nm: str = "SubbandDS"):
+        super().__init__(fftLen, halfBandShift, nm)
+
+
+class SubbandMVDRPtr(_SubbandBeamformer):
+    """beamformer/beamformer.h:333-388, beamformer.cc:2321-2635."""
+
+    def __init__(self, fftLen: int = 512, halfBandShift: bool = False, nm: str = "SubbandMVDR"):
+        super().__init__(fftLen, halfBandShift, nm)
+
+    def setNoiseSpatialSpectralMatrix(self, fbinX: int, Rnn) -> bool:
+        R = np.asarray(Rnn)
+        if R.shape != (self.chanN(), self.chanN()):     # the reference prints and returns false (:2457-2464)
+            return False
+        self._need_plan().set_covariance(fbinX, R)
+        return True
+
+    def getNoiseSpatialSpectralMatrix(self, fbinX: int):
+        try:
+            return self._need_plan().get_covariance(fbinX)
+        except BtkError as e:
+            _raise(e)
+
+    def setDiffuseNoiseModel(self, micPositions, sampleRate: float, sspeed: float = 343740.0) -> bool:
+        mp = np.asarray(micPositions, np.float64)
+        if mp.ndim != 2 or mp.shape[0] != self.chanN() or mp.shape[1] < 3:
+            return False
+        self._need_plan().set_diffuse_noise_model(mp, sampleRate, sspeed)
+        return True
+
+    def setAllLevelsOfDiagonalLoading(self, diagonalWeight: float):
+        try:
+            self._need_plan().diag_load(float(diagonalWeight))
+        except BtkError as e:
+            _raise(e)
+
+    def setLevelOfDiagonalLoading(self, fbinX: int, diagonalWeight: float):
+        try:
+            self._need_plan().diag_load(float(diagonalWeight), fbinX)
+        except BtkError as e:
+            _raise(e)
+
+    def divideAllNonDiagonalElements(self, myu: float):
+        try:
+            self._need_plan().divide_nondiagonal(float(myu))
+        except BtkError as e:
+            _raise(e)
+
+    def calcMVDRWeights(self, sampleRate: float, dThreshold: float = 1.0e-8, calcInverseMatrix: bool = True) -> bool:
+        try:
+            self._need_plan().solve_mvdr(sampleRate, dThreshold)
+        except BtkError as e:
+            _raise(e)
+        self._weights_changed()
+        return True
+
+    def getMVDRWeights(self, fbinX: int):
+        return self.getWeights(fbinX)
+
+
+class OverSampledDFTSynthesisBankPtr(FeatureStream, _FilterBank):
+    """modulated/modulated.cc:521-674.  ``next()`` yields float32[D] blocks (scaled 1/D like the reference)."""
+
+    def __init__(self, samp, prototype, M: int = 256, m: int = 3, r: int = 0, delayCompensationType: int = 0,
+                 gainFactor: int = 1, nm: str = "OverSampledDFTSynthesisBank"):
+        D = int(M) >> int(r)
+        FeatureStream.__init__(self, D, nm)
+        self._geometry(prototype, M, m, r, delayCompensationType)
+        self._samp, self._gain = samp, int(gainFactor)
+        self._out = None
+        self._plan = None
+        self._fused = False
+        self._vector = np.zeros(D, np.float32)
+
+    def fused(self) -> bool:
+        """True when the last evaluation ran analysis -> beamformer -> synthesis as one kernel."""
+        return self._fused
+
+    def _can_fuse(self) -> bool:
+        bf = self._samp
+        return (isinstance(bf, _SubbandBeamformer) and bf._frameX == FrameResetX and bf._all_own_banks()
+                and bf._fftLen == self._M and bf._channels[0]._m == self._m and bf._channels[0]._r == self._r
+                and bf._channels[0]._dct == self._dct)
+
+    def _evaluate(self):
+        try:
+            if self._can_fuse():
+                bf = self._samp
+                bf._check_weights()
+                C = bf.chanN()
+                if self._plan is None or self._plan.C != C:
+                    if self._plan is not None:
+                        self._plan.close()
+                    self._plan = Plan(self._M, self._m, self._r, C, h=bf._channels[0]._prototype, g=self._prototype,
+                                      dct=self._dct, gain=self._gain)
+                self._plan.set_weights(bf._plan.get_weights())
+                out = self._plan.chain(bf._interleaved_pcm())
+                self._fused = True
+            else:
+                frames = _drain(self._samp)
+                B = self._M // 2 + 1
+                Y = np.asarray(frames, np.complex64)[:, :B] if frames else np.zeros((0, B), np.complex64)
+                if self._plan is None or self._plan.C != 1:
+                    self._plan = Plan(self._M, self._m, self._r, 1, g=self._prototype, dct=self._dct, gain=self._gain)
+                out = self._plan.synthesis(Y)
+                self._fused = False
+        except BtkError as e:
+            _raise(e)
+        self._out = out.reshape(-1, self._D)
+
+    def next(self, frameX: int = -5):
+        if frameX == self._frameX and self._frameX >= 0:
+            return self._vector
+        if self._out is None:
+            self._evaluate()
+        t = self._frameX + 1
+        if t >= self._out.shape[0]:
+            self._endOfSamples = True
+            raise jiterator_error("end of samples!")
+        self._vector[:] = self._out[t]
+        self._frameX = t
+        return self._vector
+
+    def reset(self):
+        FeatureStream.reset(self)
+        if isinstance(self._samp, FeatureStream):
+            self._samp.reset()
+        self._out = None
