@@ -9,7 +9,7 @@ never does and has no CPU fallback.
 Pinning: the reference ships no golden vectors, so this
 restatement is pinned against the reference ITSELF -- its own .cc files compiled
 in place by ``oracle/Makefile`` into ``oracle/_ref/libbtk_ref.so`` -- in
-``tests/test_oracle_vs_ref.py`` and through the committed fixtures under
+``tests/test_oracle_golden.py`` (test_oracle_matches_compiled_reference) and through the committed fixtures under
 ``tests/golden/`` (made by ``tests/golden/make_golden.py`` from that library).
 
 Every function cites the reference lines it restates (paths relative to
