@@ -398,21 +398,24 @@ BTK_HD void stage_window(Ctx& ctx, const ChainSmem& L, float* s_xs, const float*
         if (idx < K::CG * K::M / 2) wv[i] = src[idx];
       }
     }
+    // 32-bit sample indices inside the loops (T < 2^31; t may be negative at the stream start)
+    const int t0 = (int)t_lo;
+    const float* pcm_cg = pcm + cg0;
     for (int rt = warp % RSTEP; rt < RT; rt += RSTEP) {
       const int res = rt * 16 + sub;
       if (res >= D) continue;
       float* dst = s_xs + res * L.SB + hb;
-      const long long t_res = t_lo + res + (long long)hb * D;
+      const int t_res = t0 + res + hb * D;
       for (int bp0 = (K::NW >= RT ? warp / RT : 0); bp0 < nbp; bp0 += BSTEP * STEPS) {
         float x[STEPS][K::CG];
         BTK_UNROLL
         for (int s = 0; s < STEPS; s++) {
           const int bp = bp0 + s * BSTEP;
-          const long long t = t_res + (long long)bp * (2 * D);
+          const int t = t_res + bp * (2 * D);
           BTK_UNROLL
           for (int c = 0; c < K::CG; c++) x[s][c] = 0.f;
           if (2 * bp + hb < L.NB && t >= 0 && t < T) {
-            const float* src = pcm + t * C + cg0;
+            const float* src = pcm_cg + (size_t)((unsigned)t) * (unsigned)C;
             if (vec4 && cg0 + K::CG <= C) {
               const float4 q = *reinterpret_cast<const float4*>(src);
               x[s][0] = q.x; x[s][1] = q.y; x[s][2] = q.z; x[s][3] = q.w;
