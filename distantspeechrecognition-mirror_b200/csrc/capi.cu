@@ -423,7 +423,7 @@ int btkb200_chain_batch_dev(btkb200_plan* p, const float* d_pcm, const long long
       total += recs[i].nblk;
     }
     std::vector<WorkItem> work;
-    const int W = fb_frames_per_iter(p->geo.M, p->geo.R), H = p->geo.m * p->geo.R - 1;
+    const int W = chain_frames_per_iter(p->geo.M, p->geo.R, p->geo.m), H = p->geo.m * p->geo.R - 1;
     build_work(recs, choose_chunk(total, H, W), work);
     int rc = upload_desc(p, recs, work, st);
     if (rc) return rc;

@@ -61,15 +61,20 @@ struct ChainParams {
   int gain;              // synthesis gainFactor
 };
 
-template <int M_, int R_, int MT_ = 0>
+template <int M_, int R_, int MT_ = 0, int PP_ = 1>
 struct ChainCfg {
   typedef FFTGeom<M_> G;
   static constexpr int M = M_, R = R_, D = M_ / R_;
   static constexpr int MT = MT_;               // compile-time prototype length factor, 0 = runtime
-  static constexpr int NW = (M_ >= 1024) ? 4 : 8;   // warps per CTA, one frame PAIR per warp per iteration
-                                                    // (M = 1024 would not fit 227 KB of shared memory with 8)
+  static constexpr int PP = PP_;               // frame PAIRS per warp per iteration: with 2, a lane windows four
+                                               // consecutive frames from one set of tap / sample / weight loads
+  // warps per CTA: 8, or 4 where 8 would not leave room for a second CTA on the SM (two frame pairs per warp) or
+  // would not fit 227 KB of shared memory at all (M = 1024).  Two independent CTAs per SM matter more than a
+  // longer window: one CTA's staging (global-load latency) overlaps the other's transforms.
+  static constexpr int NW = (M_ >= 1024 || PP_ == 2) ? 4 : 8;
   static constexpr int NT = NW * 32;
-  static constexpr int W = 2 * NW;             // analysis frames per iteration
+  static constexpr int FW = 2 * PP_;           // frames per warp per iteration
+  static constexpr int W = FW * NW;            // analysis frames per iteration
   static constexpr int CG = 4;                 // channels staged per pass (one float4 per time step)
   static constexpr int NG = G::NG;             // lane groups per warp = channels processed concurrently
   static constexpr int E = G::Ra / R_;         // registers between members of one residue class
@@ -79,6 +84,7 @@ struct ChainCfg {
   static_assert(G::Ra % R_ == 0, "decimation factor must divide the first radix");
   static_assert(CG % NG == 0, "channel group must be a multiple of the lane groups per warp");
   static_assert(W % FPT == 0, "frames per thread must divide the iteration");
+  static_assert(PP_ == 1 || PP_ == 2, "one or two frame pairs per warp");
 };
 
 struct ChainSmem {
@@ -100,9 +106,9 @@ BTK_HD constexpr int tap_stride(int mR) {
   return ts;
 }
 
-template <int M_, int R_>
+template <int M_, int R_, int PP_ = 1>
 BTK_HD constexpr ChainSmem chain_smem_layout(int m) {
-  typedef ChainCfg<M_, R_, 0> K;
+  typedef ChainCfg<M_, R_, 0, PP_> K;
   typedef FFTTables<M_> FT;
   ChainSmem s = ChainSmem();
   const int mR = m * R_;
@@ -125,15 +131,15 @@ BTK_HD constexpr ChainSmem chain_smem_layout(int m) {
   if (xs_bytes < K::W * M_ * 4) xs_bytes = K::W * M_ * 4;
   s.xs = off;   off += xs_bytes;                 off = (off + 15) & ~15;
   s.wts = off;  off += K::CG * M_ * 8;
-  s.xbuf = off; off += K::NW * K::NG * K::G::XBUF * 8;
+  s.xbuf = off; off += K::NW * K::NG * PP_ * K::G::XBUF * 8;
   s.vhist = off; off += (s.H > 0 ? s.H : 1) * M_ * 4;
   s.total = off;
   return s;
 }
 
-template <int M_> struct ChainThreadState {
-  cf z[FFTGeom<M_>::V];
-  cf g[FFTGeom<M_>::V];
+template <int M_, int PP_ = 1> struct ChainThreadState {
+  cf z[PP_ * FFTGeom<M_>::V];    // [pp][V]
+  cf g[PP_ * FFTGeom<M_>::V];
 };
 
 // N consecutive floats, the first one aligned to VEC*4 bytes
@@ -161,42 +167,50 @@ BTK_HD void load_floats(float* dst, const float* src) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Polyphase windowing of one frame pair of one staged channel (modulated.cc:419-434), using the
-// overlap between the two frames: for the residue class rho (mod D)
+// Polyphase windowing of PP consecutive frame pairs of one staged channel (modulated.cc:419-434), using the
+// overlap between the frames: for the residue class rho (mod D) and pair pp (frames i0 = 2 pp, i1 = i0 + 1)
 //     s_t = x[(i1+1) D - 1 - rho - D t],  h_t = h[rho + D t],  t = a + R k
 //     u_{i1}[rho + D a] = sum_k h_t s_t ,   u_{i0}[rho + D a] = sum_k h_t s_{t+1}
-// i.e. m R + 1 sample loads and m R tap loads feed 2 m R multiply-adds.  In the staged window the
+// i.e. m R + 2 PP - 1 sample loads and m R tap loads feed 2 PP m R multiply-adds.  In the staged window the
 // samples of one residue are consecutive (xrow[(D-1-rho) SB + b], b = block index) and so are the taps.
-// z[r].x <- u_{i0}, z[r].y <- u_{i1} in the canonical register layout.
+// z[pp][r].x <- u_{i0}, z[pp][r].y <- u_{i1} in the canonical register layout.
 // ---------------------------------------------------------------------------------------------
 template <class K>
-BTK_HD void polyphase_pair(cf* z, int gl, const float* xrow, const float* taps, const ChainSmem& L, int m) {
+BTK_HD void polyphase_pairs(cf* z, int gl, const float* xrow, const float* taps, const ChainSmem& L, int m) {
   typedef typename K::G G;
-  constexpr int R_ = K::R;
+  constexpr int R_ = K::R, PP = K::PP;
   BTK_UNROLL
   for (int rep = 0; rep < G::RepA; rep++) {
     BTK_UNROLL
     for (int e0 = 0; e0 < K::E; e0++) {
       const int rho = gl + G::L * rep + G::JA * e0;
-      const float* xp = xrow + (K::D - 1 - rho) * L.SB;   // xp[b]: block b of this warp's span; s_t = xp[mR - t]
+      const float* xp = xrow + (K::D - 1 - rho) * L.SB;   // xp[b]: block b of this warp's span; s_t(pp) = xp[2 pp + mR - t]
       const float* hp = taps + rho * L.TS;
-      cf u[R_];          // (u_{i0}, u_{i1})[rho + D a]
+      cf u[PP][R_];          // (u_{i0}, u_{i1})[rho + D a] of pair pp
       BTK_UNROLL
-      for (int a = 0; a < R_; a++) u[a] = mk(0.f, 0.f);
+      for (int pp = 0; pp < PP; pp++) {
+        BTK_UNROLL
+        for (int a = 0; a < R_; a++) u[pp][a] = mk(0.f, 0.f);
+      }
       if (K::MT > 0) {
         constexpr int mR = (K::MT > 0 ? K::MT : 1) * R_;
-        float xb[mR + 2], h[mR];
-        load_floats<mR + 1, 2>(xb, xp);
+        constexpr int NX = mR + 1 + 2 * (PP - 1);          // samples needed; read as float2 (the row is padded to even)
+        float xb[NX + 2], h[mR];
+        load_floats<(NX + 1) & ~1, 2>(xb, xp);
         load_floats<mR, tap_vec(mR)>(h, hp);
-        // (u_{i0}, u_{i1}) += h_t (s_{t+1}, s_t) = h_t (xb[mR-t-1], xb[mR-t]): where that is an aligned pair of the
+        // (u_{i0}, u_{i1}) += h_t (s_{t+1}, s_t) = h_t (xb[2pp+mR-t-1], xb[2pp+mR-t]): where that is an aligned pair of the
         // float2 loads (mR-t-1 even) it is one packed FFMA2, otherwise two scalar ones
         BTK_UNROLL
         for (int t = 0; t < mR; t++) {
-          if (((mR - t - 1) & 1) == 0) {
-            u[t % R_] = cfma_real(mk(xb[mR - t - 1], xb[mR - t]), h[t], u[t % R_]);
-          } else {
-            u[t % R_].y = fmaf(h[t], xb[mR - t], u[t % R_].y);
-            u[t % R_].x = fmaf(h[t], xb[mR - t - 1], u[t % R_].x);
+          BTK_UNROLL
+          for (int pp = 0; pp < PP; pp++) {
+            const int i0 = 2 * pp + mR - t - 1;
+            if ((i0 & 1) == 0) {
+              u[pp][t % R_] = cfma_real(mk(xb[i0], xb[i0 + 1]), h[t], u[pp][t % R_]);
+            } else {
+              u[pp][t % R_].y = fmaf(h[t], xb[i0 + 1], u[pp][t % R_].y);
+              u[pp][t % R_].x = fmaf(h[t], xb[i0], u[pp][t % R_].x);
+            }
           }
         }
       } else {
@@ -206,60 +220,124 @@ BTK_HD void polyphase_pair(cf* z, int gl, const float* xrow, const float* taps, 
           for (int a = 0; a < R_; a++) {
             const int t = a + R_ * k;
             const float h = hp[t];
-            u[a].y = fmaf(h, xp[mR - t], u[a].y);
-            u[a].x = fmaf(h, xp[mR - t - 1], u[a].x);
+            BTK_UNROLL
+            for (int pp = 0; pp < PP; pp++) {
+              u[pp][a].y = fmaf(h, xp[2 * pp + mR - t], u[pp][a].y);
+              u[pp][a].x = fmaf(h, xp[2 * pp + mR - t - 1], u[pp][a].x);
+            }
           }
         }
       }
       BTK_UNROLL
-      for (int a = 0; a < R_; a++) z[rep * G::Ra + e0 + K::E * a] = u[a];
+      for (int pp = 0; pp < PP; pp++) {
+        BTK_UNROLL
+        for (int a = 0; a < R_; a++) z[pp * G::V + rep * G::Ra + e0 + K::E * a] = u[pp][a];
+      }
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Forward transform of the packed pair held in ts.g by lane group 0 of every warp, real parts into
-// the current-v area:  v_{tau0} + j v_{tau0+1} = FFT_fwd(G)   (modulated.cc:603-607, Re taken implicitly
-// because G is the sum of two Hermitian spectra).
+// Forward transforms of the packed pairs of every warp, real parts into the current-v area:
+//   v_{tau0} + j v_{tau0+1} = FFT_fwd(G)   (modulated.cc:603-607, Re taken implicitly because G is the sum of
+// two Hermitian spectra).  With one lane group per warp (NG == 1) group 0 transforms its PP pairs one after the
+// other; otherwise group pp (< PP) transforms pair pp, which synth_gather_pairs left in its ts.g[0..V).
 // ---------------------------------------------------------------------------------------------
 template <class K, class Ctx>
 BTK_HD void synth_transform_store(Ctx& ctx, cf* s_xbuf, const cf* s_twa, const cf* s_twb, float* s_vcur, int tau_base) {
   typedef typename K::G G;
   constexpr int M_ = K::M;
-  typedef ChainThreadState<M_> TS;
+  constexpr int NP = K::NG == 1 ? K::PP : 1;                 // transforms per owning lane
+  typedef ChainThreadState<M_, K::PP> TS;
+  auto owns = [](int grp) { return K::NG == 1 ? grp == 0 : grp < K::PP; };
+  auto slot = [&](int warp, int grp) { return s_xbuf + ((warp * K::NG + grp) * K::PP) * G::XBUF; };
   ctx.par([&](int tid, TS& ts) {
     const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
-    if (grp == 0) GroupFFT<M_, -1>::step1(ts.g, gl, s_xbuf + (warp * K::NG) * G::XBUF, s_twa);
+    if (owns(grp)) GroupFFT<M_, -1>::template step1_multi<NP>(ts.g, gl, slot(warp, grp), s_twa);
   });
   ctx.syncwarp();
   if (G::Rb > 1) {
     ctx.par([&](int tid, TS& ts) {
       const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
-      if (grp == 0) GroupFFT<M_, -1>::step2_load(ts.g, gl, s_xbuf + (warp * K::NG) * G::XBUF, s_twb);
+      if (owns(grp)) {
+        BTK_UNROLL
+        for (int pp = 0; pp < NP; pp++) GroupFFT<M_, -1>::step2_load(ts.g + pp * G::V, gl, slot(warp, grp) + pp * G::XBUF, s_twb);
+      }
     });
     ctx.syncwarp();
     ctx.par([&](int tid, TS& ts) {
       const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
-      if (grp == 0) GroupFFT<M_, -1>::step2_store(ts.g, gl, s_xbuf + (warp * K::NG) * G::XBUF);
+      if (owns(grp)) {
+        BTK_UNROLL
+        for (int pp = 0; pp < NP; pp++) GroupFFT<M_, -1>::step2_store(ts.g + pp * G::V, gl, slot(warp, grp) + pp * G::XBUF);
+      }
     });
     ctx.syncwarp();
   }
   ctx.par([&](int tid, TS& ts) {
     const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
-    if (grp == 0) {
-      GroupFFT<M_, -1>::step3(ts.g, gl, s_xbuf + (warp * K::NG) * G::XBUF);
-      const int tau0 = tau_base + 2 * warp;
-      // v of frames before the stream start is zero (the synthesis buffer starts zeroed, modulated.cc:666-674)
-      const float k0 = tau0 >= 0 ? 1.f : 0.f, k1 = tau0 + 1 >= 0 ? 1.f : 0.f;
-      float* v0 = s_vcur + (2 * warp) * M_;
+    if (owns(grp)) {
       BTK_UNROLL
-      for (int r = 0; r < G::V; r++) {
-        const int q = G::index_of(gl, r);
-        v0[q] = ts.g[r].x * k0;
-        v0[M_ + q] = ts.g[r].y * k1;
+      for (int pp = 0; pp < NP; pp++) {
+        GroupFFT<M_, -1>::step3(ts.g + pp * G::V, gl, slot(warp, grp) + pp * G::XBUF);
+        const int f = K::FW * warp + 2 * (K::NG == 1 ? pp : grp);        // frame of the iteration
+        const int tau0 = tau_base + f;
+        // v of frames before the stream start is zero (the synthesis buffer starts zeroed, modulated.cc:666-674)
+        const float k0 = tau0 >= 0 ? 1.f : 0.f, k1 = tau0 + 1 >= 0 ? 1.f : 0.f;
+        float* v0 = s_vcur + f * M_;
+        BTK_UNROLL
+        for (int r = 0; r < G::V; r++) {
+          const int q = G::index_of(gl, r);
+          v0[q] = ts.g[pp * G::V + r].x * k0;
+          v0[M_ + q] = ts.g[pp * G::V + r].y * k1;
+        }
       }
     }
   });
+}
+
+// Sum the partial G of the lane groups of each warp (channels were split across groups) and hand pair pp to
+// group pp: afterwards group pp (< PP) holds the complete G of pair pp in ts.g[0..V).  Only for NG > 1.
+template <class K, class Ctx>
+BTK_HD void synth_gather_pairs(Ctx& ctx, cf* s_xbuf) {
+  typedef typename K::G G;
+  typedef ChainThreadState<K::M, K::PP> TS;
+  static_assert(K::NG == 1 || K::NG >= K::PP, "a lane group per frame pair");
+  if (K::NG == 1) return;
+  auto slot = [&](int warp, int grp, int pp) { return s_xbuf + ((warp * K::NG + grp) * K::PP + pp) * G::XBUF; };
+  ctx.par([&](int tid, TS& ts) {
+    const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+    BTK_UNROLL
+    for (int pp = 0; pp < K::PP; pp++) {
+      if (grp != pp) {
+        cf* xb = slot(warp, grp, pp);
+        BTK_UNROLL
+        for (int r = 0; r < G::V; r++) xb[r * G::L + gl] = ts.g[pp * G::V + r];
+      }
+    }
+  });
+  ctx.syncwarp();
+  ctx.par([&](int tid, TS& ts) {
+    const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+    if (grp < K::PP) {
+      cf acc[G::V];
+      BTK_UNROLL
+      for (int r = 0; r < G::V; r++) {
+        acc[r] = ts.g[r];
+        BTK_UNROLL
+        for (int pp = 1; pp < K::PP; pp++) if (grp == pp) acc[r] = ts.g[pp * G::V + r];
+      }
+      for (int o = 0; o < K::NG; o++) {
+        if (o == grp) continue;
+        const cf* xb = slot(warp, o, grp);
+        BTK_UNROLL
+        for (int r = 0; r < G::V; r++) acc[r] = cadd(acc[r], xb[r * G::L + gl]);
+      }
+      BTK_UNROLL
+      for (int r = 0; r < G::V; r++) ts.g[r] = acc[r];
+    }
+  });
+  ctx.syncwarp();
 }
 
 // v frame f of the iteration (f in [-H, W)): history frames live in s_vhist, current ones in s_vcur
@@ -278,7 +356,7 @@ template <class K, class Ctx>
 BTK_HD void synth_emit(Ctx& ctx, const ChainSmem& L, const float* taps_g, const float* s_vhist, const float* s_vcur,
                        float* out, int m, int pd_s, int gain, int tau_base, int j0, int nj) {
   constexpr int M_ = K::M, R_ = K::R, D = K::D, FPT = K::FPT;
-  typedef ChainThreadState<M_> TS;
+  typedef ChainThreadState<M_, K::PP> TS;
   const float gf = gain > 0 ? (float)gain : 1.f;
   ctx.par([&](int tid, TS&) {
     for (int u = tid; u < D * (K::W / FPT); u += K::NT) {
@@ -330,42 +408,47 @@ BTK_HD void synth_emit(Ctx& ctx, const ChainSmem& L, const float* taps_g, const 
 // the last H current v frames become the history of the next iteration
 template <class K, class Ctx>
 BTK_HD void synth_roll_history(Ctx& ctx, const ChainSmem& L, float* s_vhist, const float* s_vcur) {
-  typedef ChainThreadState<K::M> TS;
+  typedef ChainThreadState<K::M, K::PP> TS;
   ctx.par([&](int tid, TS&) {
     for (int i = tid; i < L.H * K::M; i += K::NT) s_vhist[i] = s_vcur[(K::W - L.H) * K::M + i];
   });
 }
 
-// One analysis round of a warp: polyphase of the staged channel + backward transform, leaving
-// Z = X_{tau0} + j X_{tau0+1} of channel (round*NG + grp) in ts.z (canonical layout).
+// One analysis round of a warp: polyphase of the staged channel + backward transforms, leaving
+// Z = X_{tau0} + j X_{tau0+1} of channel (round*NG + grp), for each of the warp's PP frame pairs, in ts.z[pp][V]
+// (canonical layout).
 template <class K, class Ctx>
 BTK_HD void analysis_round(Ctx& ctx, const ChainSmem& L, const float* s_xs, const float* s_taps, cf* s_xbuf,
                            const cf* s_twa, const cf* s_twb, int m, int round) {
   typedef typename K::G G;
   constexpr int M_ = K::M;
-  typedef ChainThreadState<M_> TS;
+  typedef ChainThreadState<M_, K::PP> TS;
+  auto slot = [&](int warp, int grp) { return s_xbuf + ((warp * K::NG + grp) * K::PP) * G::XBUF; };
   ctx.par([&](int tid, TS& ts) {
     const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
     const int c_local = round * K::NG + grp;
-    polyphase_pair<K>(ts.z, gl, s_xs + c_local * L.CS + 2 * warp, s_taps, L, m);
-    GroupFFT<M_, +1>::step1(ts.z, gl, s_xbuf + (warp * K::NG + grp) * G::XBUF, s_twa);
+    polyphase_pairs<K>(ts.z, gl, s_xs + c_local * L.CS + K::FW * warp, s_taps, L, m);
+    GroupFFT<M_, +1>::template step1_multi<K::PP>(ts.z, gl, slot(warp, grp), s_twa);
   });
   ctx.syncwarp();
   if (G::Rb > 1) {
     ctx.par([&](int tid, TS& ts) {
       const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
-      GroupFFT<M_, +1>::step2_load(ts.z, gl, s_xbuf + (warp * K::NG + grp) * G::XBUF, s_twb);
+      BTK_UNROLL
+      for (int pp = 0; pp < K::PP; pp++) GroupFFT<M_, +1>::step2_load(ts.z + pp * G::V, gl, slot(warp, grp) + pp * G::XBUF, s_twb);
     });
     ctx.syncwarp();
     ctx.par([&](int tid, TS& ts) {
       const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
-      GroupFFT<M_, +1>::step2_store(ts.z, gl, s_xbuf + (warp * K::NG + grp) * G::XBUF);
+      BTK_UNROLL
+      for (int pp = 0; pp < K::PP; pp++) GroupFFT<M_, +1>::step2_store(ts.z + pp * G::V, gl, slot(warp, grp) + pp * G::XBUF);
     });
     ctx.syncwarp();
   }
   ctx.par([&](int tid, TS& ts) {
     const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
-    GroupFFT<M_, +1>::step3(ts.z, gl, s_xbuf + (warp * K::NG + grp) * G::XBUF);
+    BTK_UNROLL
+    for (int pp = 0; pp < K::PP; pp++) GroupFFT<M_, +1>::step3(ts.z + pp * G::V, gl, slot(warp, grp) + pp * G::XBUF);
   });
 }
 
@@ -377,7 +460,7 @@ BTK_HD void analysis_round(Ctx& ctx, const ChainSmem& L, const float* s_xs, cons
 template <class K, class Ctx>
 BTK_HD void stage_window(Ctx& ctx, const ChainSmem& L, float* s_xs, const float* pcm, int C, int T, long long t_lo,
                          int cg0, bool vec4, float4* s_wts, const cf* wts) {
-  typedef ChainThreadState<K::M> TS;
+  typedef ChainThreadState<K::M, K::PP> TS;
   constexpr int D = K::D;
   constexpr int RT = (D + 15) / 16;
   constexpr int WPT = (K::CG * K::M / 2 + K::NT - 1) / K::NT;   // weight float4 per thread
@@ -449,7 +532,7 @@ BTK_HD void stage_window(Ctx& ctx, const ChainSmem& L, float* s_xs, const float*
 // all C channels.  Issued before the compute rounds so that the next staging pass finds them in L2.
 template <class K, class Ctx>
 BTK_HD void prefetch_next_window(Ctx& ctx, const float* pcm, int C, int T, long long t_first) {
-  typedef ChainThreadState<K::M> TS;
+  typedef ChainThreadState<K::M, K::PP> TS;
   ctx.par([&](int tid, TS&) {
     long long lo = t_first < 0 ? 0 : t_first, hi = t_first + (long long)K::W * K::D;
     if (hi > T) hi = T;
@@ -462,7 +545,7 @@ BTK_HD void prefetch_next_window(Ctx& ctx, const float* pcm, int C, int T, long 
 template <class K, class Ctx>
 BTK_HD void load_tables(Ctx& ctx, const ChainSmem& L, unsigned char* smem, const float* taps_h, const cf* twa,
                         const cf* twb) {
-  typedef ChainThreadState<K::M> TS;
+  typedef ChainThreadState<K::M, K::PP> TS;
   typedef FFTTables<K::M> FT;
   float* s_taps = reinterpret_cast<float*>(smem + L.taps);
   cf* s_twa = reinterpret_cast<cf*>(smem + L.twa);
@@ -480,14 +563,14 @@ BTK_HD void load_tables(Ctx& ctx, const ChainSmem& L, unsigned char* smem, const
 //   void sync()                       CTA barrier;   void syncwarp()   warp barrier
 // Every cross-thread shared-memory dependency crosses a par() boundary followed by a barrier.
 // ---------------------------------------------------------------------------------------------
-template <int M_, int R_, int MT_, class Ctx>
+template <int M_, int R_, int MT_, int PP_, class Ctx>
 BTK_HD void chain_tile(Ctx& ctx, const ChainParams& p, unsigned char* smem, int work_id) {
-  typedef ChainCfg<M_, R_, MT_> K;
+  typedef ChainCfg<M_, R_, MT_, PP_> K;
   typedef typename K::G G;
-  typedef ChainThreadState<M_> TS;
+  typedef ChainThreadState<M_, PP_> TS;
   const int m = MT_ > 0 ? MT_ : p.m;
   const int N = M_ * m;
-  const ChainSmem L = chain_smem_layout<M_, R_>(m);
+  const ChainSmem L = chain_smem_layout<M_, R_, PP_>(m);
   const int H = L.H;                                        // v history needed before a frame
   float* s_taps = reinterpret_cast<float*>(smem + L.taps);
   cf* s_twa = reinterpret_cast<cf*>(smem + L.twa);
@@ -520,7 +603,7 @@ BTK_HD void chain_tile(Ctx& ctx, const ChainParams& p, unsigned char* smem, int 
 
     ctx.par([&](int, TS& ts) {
       BTK_UNROLL
-      for (int r = 0; r < G::V; r++) ts.g[r] = mk(0.f, 0.f);
+      for (int r = 0; r < PP_ * G::V; r++) ts.g[r] = mk(0.f, 0.f);
     });
 
     for (int cg0 = 0; cg0 < p.Cpad; cg0 += K::CG) {
@@ -529,7 +612,7 @@ BTK_HD void chain_tile(Ctx& ctx, const ChainParams& p, unsigned char* smem, int 
       if (cg0 == 0 && it + 1 < n_it) prefetch_next_window<K>(ctx, pcm, C, rec.T, t_lo + (long long)L.NB * K::D);
       ctx.sync();
 
-      // ---- per warp: frame pair (tau0, tau0+1); per lane group: one channel per round
+      // ---- per warp: PP frame pairs (tau0, tau0+1); per lane group: one channel per round
       for (int round = 0; round < K::CG / K::NG; round++) {
         analysis_round<K>(ctx, L, s_xs, s_taps, s_xbuf, s_twa, s_twb, m, round);
         ctx.par([&](int tid, TS& ts) {
@@ -538,8 +621,11 @@ BTK_HD void chain_tile(Ctx& ctx, const ChainParams& p, unsigned char* smem, int 
           BTK_UNROLL
           for (int r2 = 0; r2 < G::V / 2; r2++) {
             const float4 w = w4[r2 * G::L];
-            cfma(ts.g[2 * r2], ts.z[2 * r2], mk(w.x, w.y));
-            cfma(ts.g[2 * r2 + 1], ts.z[2 * r2 + 1], mk(w.z, w.w));
+            BTK_UNROLL
+            for (int pp = 0; pp < PP_; pp++) {
+              cfma(ts.g[pp * G::V + 2 * r2], ts.z[pp * G::V + 2 * r2], mk(w.x, w.y));
+              cfma(ts.g[pp * G::V + 2 * r2 + 1], ts.z[pp * G::V + 2 * r2 + 1], mk(w.z, w.w));
+            }
           }
         });
         ctx.syncwarp();
@@ -547,30 +633,7 @@ BTK_HD void chain_tile(Ctx& ctx, const ChainParams& p, unsigned char* smem, int 
       ctx.sync();
     }
 
-    // ---- sum the partial G of the lane groups of each warp (channels were split across groups)
-    if (K::NG > 1) {
-      ctx.par([&](int tid, TS& ts) {
-        const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
-        if (grp > 0) {
-          cf* xb = s_xbuf + (warp * K::NG + grp) * G::XBUF;
-          BTK_UNROLL
-          for (int r = 0; r < G::V; r++) xb[r * G::L + gl] = ts.g[r];
-        }
-      });
-      ctx.syncwarp();
-      ctx.par([&](int tid, TS& ts) {
-        const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
-        if (grp == 0) {
-          for (int o = 1; o < K::NG; o++) {
-            const cf* xb = s_xbuf + (warp * K::NG + o) * G::XBUF;
-            BTK_UNROLL
-            for (int r = 0; r < G::V; r++) ts.g[r] = cadd(ts.g[r], xb[r * G::L + gl]);
-          }
-        }
-      });
-      ctx.syncwarp();
-    }
-
+    synth_gather_pairs<K>(ctx, s_xbuf);
     synth_transform_store<K>(ctx, s_xbuf, s_twa, s_twb, s_vcur, tau_base);
     ctx.sync();
     synth_emit<K>(ctx, L, p.taps_g, s_vhist, s_vcur, out, m, p.pd_s, p.gain, tau_base, wk.j0, wk.nj);

@@ -212,12 +212,14 @@ template <int M_, int S> struct GroupFFT {
   typedef FFTGeom<M_> G;
   typedef FFTTables<M_> FT;
 
-  // step 1: pass A (+ twiddle) and scatter into the exchange buffer.
-  static BTK_HD void step1(cf* v, int gl, cf* xb, const cf* twa) {
+  // step 1: pass A (+ twiddle) and scatter into the exchange buffer, for PP independent transforms of the same
+  // lane (registers v + pp*V, exchange buffers xb + pp*XBUF) that share one set of twiddles.
+  template <int PP>
+  static BTK_HD void step1_multi(cf* v, int gl, cf* xb, const cf* twa) {
     BTK_UNROLL
     for (int rep = 0; rep < G::RepA; rep++) {
-      cf* p = v + rep * G::Ra;
-      Dft<G::Ra, S>::run(p);
+      BTK_UNROLL
+      for (int pp = 0; pp < PP; pp++) Dft<G::Ra, S>::run(v + pp * G::V + rep * G::Ra);
       const int j = gl + G::L * rep;
       cf w[G::Ra + 1];
       if (G::Rb == 1) {
@@ -239,11 +241,17 @@ template <int M_, int S> struct GroupFFT {
         }
       }
       BTK_UNROLL
-      for (int ka = 1; ka < G::Ra; ka++) p[ka] = multw<S>(p[ka], w[ka]);
-      BTK_UNROLL
-      for (int ka = 0; ka < G::Ra; ka++) xb[ka * (G::Rb > 1 ? G::S1 : G::S2) + j] = p[ka];
+      for (int pp = 0; pp < PP; pp++) {
+        cf* p = v + pp * G::V + rep * G::Ra;
+        cf* x = xb + pp * G::XBUF;
+        BTK_UNROLL
+        for (int ka = 1; ka < G::Ra; ka++) p[ka] = multw<S>(p[ka], w[ka]);
+        BTK_UNROLL
+        for (int ka = 0; ka < G::Ra; ka++) x[ka * (G::Rb > 1 ? G::S1 : G::S2) + j] = p[ka];
+      }
     }
   }
+  static BTK_HD void step1(cf* v, int gl, cf* xb, const cf* twa) { step1_multi<1>(v, gl, xb, twa); }
 
   // step 2 (only when Rb > 1): gather for pass B, radix-Rb, twiddle, scatter into exchange 2.
   // Reads complete before the caller's barrier; writes must come after it (same buffer is reused),

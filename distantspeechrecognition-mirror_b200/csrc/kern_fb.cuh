@@ -11,69 +11,84 @@
 
 namespace btk {
 
-template <int M> struct DevCtx {
-  ChainThreadState<M> ts;
+template <int M, int PP> struct DevCtx {
+  ChainThreadState<M, PP> ts;
   template <class F> __device__ __forceinline__ void par(F f) { f((int)threadIdx.x, ts); }
   __device__ __forceinline__ void sync() { __syncthreads(); }
   __device__ __forceinline__ void syncwarp() { __syncwarp(); }
 };
 
+#define BTK_MAX_SMEM (227 * 1024)
+
 // two CTAs per SM whenever two of them fit the 227 KB of shared memory
-template <int M, int R, int MT> struct KernCfg {
-  static constexpr int smem = chain_smem_layout<M, R>(MT > 0 ? MT : 4).total;
+template <int M, int R, int MT, int PP> struct KernCfg {
+  static constexpr int smem = chain_smem_layout<M, R, PP>(MT > 0 ? MT : 4).total;
   static constexpr int MINB = (M <= 256 && smem <= 113 * 1024) ? 2 : 1;
 };
 
-template <int M, int R, int MT>
-__global__ void __launch_bounds__(ChainCfg<M, R, MT>::NT, KernCfg<M, R, MT>::MINB) btk_chain_kernel(const ChainParams p) {
+// Frame pairs per warp of the fused chain: two (one 8-warp CTA per SM, up to 255 registers per thread, taps /
+// samples / weights / twiddles loaded once for four frames) whenever the larger window fits shared memory.
+template <int M, int R> static int chain_pp(int m) {
+  return (M <= 256 && chain_smem_layout<M, R, 2>(m).total <= BTK_MAX_SMEM) ? 2 : 1;
+}
+
+template <int M, int R, int MT, int PP>
+__global__ void __launch_bounds__(ChainCfg<M, R, MT, PP>::NT, KernCfg<M, R, MT, PP>::MINB) btk_chain_kernel(const ChainParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  DevCtx<M> ctx;
-  chain_tile<M, R, MT>(ctx, p, smem, (int)blockIdx.x);
+  DevCtx<M, PP> ctx;
+  chain_tile<M, R, MT, PP>(ctx, p, smem, (int)blockIdx.x);
 }
 
 template <int M, int R, int MT>
-__global__ void __launch_bounds__(ChainCfg<M, R, MT>::NT, KernCfg<M, R, MT>::MINB) btk_analysis_kernel(const AnalysisParams p) {
+__global__ void __launch_bounds__(ChainCfg<M, R, MT>::NT, KernCfg<M, R, MT, 1>::MINB) btk_analysis_kernel(const AnalysisParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  DevCtx<M> ctx;
+  DevCtx<M, 1> ctx;
   analysis_tile<M, R, MT>(ctx, p, smem, (int)blockIdx.x);
 }
 
 template <int M, int R, int MT>
-__global__ void __launch_bounds__(ChainCfg<M, R, MT>::NT, KernCfg<M, R, MT>::MINB) btk_synthesis_kernel(const SynthesisParams p) {
+__global__ void __launch_bounds__(ChainCfg<M, R, MT>::NT, KernCfg<M, R, MT, 1>::MINB) btk_synthesis_kernel(const SynthesisParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  DevCtx<M> ctx;
+  DevCtx<M, 1> ctx;
   synthesis_tile<M, R, MT>(ctx, p, smem, (int)blockIdx.x);
 }
 
-template <int M, int R, class Params, class Kern>
+template <int M, int R, int PP, class Params, class Kern>
 static cudaError_t launch_one(Kern kern, const Params& p, int m, int n_work, cudaStream_t st) {
-  const ChainSmem L = chain_smem_layout<M, R>(m);
+  const ChainSmem L = chain_smem_layout<M, R, PP>(m);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
   if (e != cudaSuccess) return e;
-  kern<<<n_work, ChainCfg<M, R, 0>::NT, L.total, st>>>(p);
+  kern<<<n_work, ChainCfg<M, R, 0, PP>::NT, L.total, st>>>(p);
   return cudaGetLastError();
 }
 
 // compile-time m where the unrolled polyphase stays within the register budget
 template <int M, int R, int MT> struct FastOk { static constexpr bool value = MT * R <= 16; };
+#define BTK_MT(MTV) (FastOk<M, R, MTV>::value ? MTV : 0)
 
 template <int M, int R>
 static cudaError_t launch_chain_r(const ChainParams& p, int n_work, cudaStream_t st) {
-  if (p.m == 2 && FastOk<M, R, 2>::value) return launch_one<M, R>(btk_chain_kernel<M, R, FastOk<M, R, 2>::value ? 2 : 0>, p, p.m, n_work, st);
-  if (p.m == 4 && FastOk<M, R, 4>::value) return launch_one<M, R>(btk_chain_kernel<M, R, FastOk<M, R, 4>::value ? 4 : 0>, p, p.m, n_work, st);
-  return launch_one<M, R>(btk_chain_kernel<M, R, 0>, p, p.m, n_work, st);
+  if (M <= 256 && chain_pp<M, R>(p.m) == 2) {
+    constexpr int PP = M <= 256 ? 2 : 1;     // (never instantiated with 2 for the large transforms)
+    if (p.m == 2 && FastOk<M, R, 2>::value) return launch_one<M, R, PP>(btk_chain_kernel<M, R, BTK_MT(2), PP>, p, p.m, n_work, st);
+    if (p.m == 4 && FastOk<M, R, 4>::value) return launch_one<M, R, PP>(btk_chain_kernel<M, R, BTK_MT(4), PP>, p, p.m, n_work, st);
+    return launch_one<M, R, PP>(btk_chain_kernel<M, R, 0, PP>, p, p.m, n_work, st);
+  }
+  if (p.m == 2 && FastOk<M, R, 2>::value) return launch_one<M, R, 1>(btk_chain_kernel<M, R, BTK_MT(2), 1>, p, p.m, n_work, st);
+  if (p.m == 4 && FastOk<M, R, 4>::value) return launch_one<M, R, 1>(btk_chain_kernel<M, R, BTK_MT(4), 1>, p, p.m, n_work, st);
+  return launch_one<M, R, 1>(btk_chain_kernel<M, R, 0, 1>, p, p.m, n_work, st);
 }
 template <int M, int R>
 static cudaError_t launch_analysis_r(const AnalysisParams& p, int n_work, cudaStream_t st) {
-  if (p.m == 2 && FastOk<M, R, 2>::value) return launch_one<M, R>(btk_analysis_kernel<M, R, FastOk<M, R, 2>::value ? 2 : 0>, p, p.m, n_work, st);
-  if (p.m == 4 && FastOk<M, R, 4>::value) return launch_one<M, R>(btk_analysis_kernel<M, R, FastOk<M, R, 4>::value ? 4 : 0>, p, p.m, n_work, st);
-  return launch_one<M, R>(btk_analysis_kernel<M, R, 0>, p, p.m, n_work, st);
+  if (p.m == 2 && FastOk<M, R, 2>::value) return launch_one<M, R, 1>(btk_analysis_kernel<M, R, BTK_MT(2)>, p, p.m, n_work, st);
+  if (p.m == 4 && FastOk<M, R, 4>::value) return launch_one<M, R, 1>(btk_analysis_kernel<M, R, BTK_MT(4)>, p, p.m, n_work, st);
+  return launch_one<M, R, 1>(btk_analysis_kernel<M, R, 0>, p, p.m, n_work, st);
 }
 template <int M, int R>
 static cudaError_t launch_synthesis_r(const SynthesisParams& p, int n_work, cudaStream_t st) {
-  if (p.m == 2 && FastOk<M, R, 2>::value) return launch_one<M, R>(btk_synthesis_kernel<M, R, FastOk<M, R, 2>::value ? 2 : 0>, p, p.m, n_work, st);
-  if (p.m == 4 && FastOk<M, R, 4>::value) return launch_one<M, R>(btk_synthesis_kernel<M, R, FastOk<M, R, 4>::value ? 4 : 0>, p, p.m, n_work, st);
-  return launch_one<M, R>(btk_synthesis_kernel<M, R, 0>, p, p.m, n_work, st);
+  if (p.m == 2 && FastOk<M, R, 2>::value) return launch_one<M, R, 1>(btk_synthesis_kernel<M, R, BTK_MT(2)>, p, p.m, n_work, st);
+  if (p.m == 4 && FastOk<M, R, 4>::value) return launch_one<M, R, 1>(btk_synthesis_kernel<M, R, BTK_MT(4)>, p, p.m, n_work, st);
+  return launch_one<M, R, 1>(btk_synthesis_kernel<M, R, 0>, p, p.m, n_work, st);
 }
 
 }  // namespace btk
@@ -107,6 +122,15 @@ static cudaError_t launch_synthesis_r(const SynthesisParams& p, int n_work, cuda
       case 8: return launch_synthesis_r<MM, 8>(p, n_work, st);                                                     \
     }                                                                                                              \
     return cudaErrorInvalidValue;                                                                                  \
+  }                                                                                                                \
+  int chain_frames_per_iter_m##MM(int R, int m) {                                                                  \
+    switch (R) {                                                                                                   \
+      case 1: return chain_pp<MM, 1>(m) == 2 ? ChainCfg<MM, 1, 0, 2>::W : ChainCfg<MM, 1, 0, 1>::W;                \
+      case 2: return chain_pp<MM, 2>(m) == 2 ? ChainCfg<MM, 2, 0, 2>::W : ChainCfg<MM, 2, 0, 1>::W;                \
+      case 4: return chain_pp<MM, 4>(m) == 2 ? ChainCfg<MM, 4, 0, 2>::W : ChainCfg<MM, 4, 0, 1>::W;                \
+      case 8: return chain_pp<MM, 8>(m) == 2 ? ChainCfg<MM, 8, 0, 2>::W : ChainCfg<MM, 8, 0, 1>::W;                \
+    }                                                                                                              \
+    return -1;                                                                                                     \
   }                                                                                                                \
   int fb_smem_bytes_m##MM(int R, int m) {                                                                          \
     switch (R) {                                                                                                   \

@@ -8,7 +8,8 @@ namespace btk {
   cudaError_t launch_chain_m##MM(int R, const ChainParams& p, int n_work, cudaStream_t st);           \
   cudaError_t launch_analysis_m##MM(int R, const AnalysisParams& p, int n_work, cudaStream_t st);     \
   cudaError_t launch_synthesis_m##MM(int R, const SynthesisParams& p, int n_work, cudaStream_t st);   \
-  int fb_smem_bytes_m##MM(int R, int m);
+  int fb_smem_bytes_m##MM(int R, int m);                                                              \
+  int chain_frames_per_iter_m##MM(int R, int m);
 BTK_DECL_M(64) BTK_DECL_M(128) BTK_DECL_M(256) BTK_DECL_M(512) BTK_DECL_M(1024)
 #undef BTK_DECL_M
 
@@ -50,7 +51,12 @@ int fb_smem_bytes(int M, int R, int m) {
   BTK_DISPATCH(fb_smem_bytes, R, m)
   return -1;
 }
-int fb_frames_per_iter(int M, int) { return M >= 1024 ? 8 : 16; }  // ChainCfg::W = 2 * NW
+int fb_frames_per_iter(int M, int) { return M >= 1024 ? 8 : 16; }  // ChainCfg::W = 2 * NW (staged kernels)
+int chain_frames_per_iter(int M, int R, int m) {                   // the fused chain may window two pairs per warp
+  if (!fb_supported(M, R)) return -1;
+  BTK_DISPATCH(chain_frames_per_iter, R, m)
+  return -1;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Weight apply on stored snapshots: one thread per (frame, bin), channels innermost and contiguous.

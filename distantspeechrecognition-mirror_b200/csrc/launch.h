@@ -15,6 +15,7 @@ bool fb_supported(int M, int R);
 // dynamic shared memory the filter-bank kernels need for (M, R, m); <0 when unsupported
 int fb_smem_bytes(int M, int R, int m);
 int fb_frames_per_iter(int M, int R);
+int chain_frames_per_iter(int M, int R, int m);
 
 // Y[f][s] = sum_c conj(w[s][c]) X[f][s][c]        (beamformer.cc:1181-1194)
 cudaError_t launch_beamform(const cf* snap, const cf* w, cf* Y, long long F, int B, int C, cudaStream_t st);

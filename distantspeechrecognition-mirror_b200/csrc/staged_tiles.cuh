@@ -26,7 +26,7 @@ struct AnalysisParams {
 
 template <int M_, int R_, int MT_, class Ctx>
 BTK_HD void analysis_tile(Ctx& ctx, const AnalysisParams& p, unsigned char* smem, int work_id) {
-  typedef ChainCfg<M_, R_, MT_> K;
+  typedef ChainCfg<M_, R_, MT_, 1> K;
   typedef typename K::G G;
   typedef ChainThreadState<M_> TS;
   const int m = MT_ > 0 ? MT_ : p.m;
@@ -103,7 +103,7 @@ struct SynthesisParams {
 
 template <int M_, int R_, int MT_, class Ctx>
 BTK_HD void synthesis_tile(Ctx& ctx, const SynthesisParams& p, unsigned char* smem, int work_id) {
-  typedef ChainCfg<M_, R_, MT_> K;
+  typedef ChainCfg<M_, R_, MT_, 1> K;
   typedef typename K::G G;
   typedef ChainThreadState<M_> TS;
   const int m = MT_ > 0 ? MT_ : p.m;

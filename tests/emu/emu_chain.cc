@@ -13,8 +13,8 @@ using namespace btk;
 
 #define BTK_EMU_CASES(X) X(64, 2) X(128, 2) X(128, 4) X(256, 1) X(256, 2) X(256, 4) X(512, 2) X(512, 4) X(512, 8) X(1024, 2) X(1024, 4)
 
-template <int M> struct HostCtx {
-  std::vector<ChainThreadState<M> > ts;
+template <int M, int PP = 1> struct HostCtx {
+  std::vector<ChainThreadState<M, PP> > ts;
   int nt;
   explicit HostCtx(int n) : ts(n), nt(n) {}
   template <class F> void par(F f) { for (int t = 0; t < nt; t++) f(t, ts[t]); }
@@ -22,11 +22,11 @@ template <int M> struct HostCtx {
   void syncwarp() {}
 };
 
-template <int M, int R, int MT>
+template <int M, int R, int MT, int PP>
 static int run_chain(int m, int dct, int C, int n_rec, const long long* Ts, const float* pcm, const long long* pcm_off,
                      float* out, const long long* out_off, const double* h, const double* g, const double* w_re_im,
                      int gain, int chunk) {
-  typedef ChainCfg<M, R, MT> K;
+  typedef ChainCfg<M, R, MT, PP> K;
   BankGeom geo(M, m, /*r=*/0, dct);
   geo.r = 0; for (int x = R; x > 1; x >>= 1) geo.r++;
   geo = BankGeom(M, m, geo.r, dct);
@@ -49,12 +49,12 @@ static int run_chain(int m, int dct, int C, int n_rec, const long long* Ts, cons
   p.pcm = pcm; p.out = out; p.recs = recs.data(); p.work = work.data();
   p.taps_h = hf.data(); p.taps_g = gp.data(); p.wts = gam.data(); p.twa = twa.data(); p.twb = twb.data();
   p.C = C; p.Cpad = Cpad; p.m = m; p.pd_s = geo.pd_s; p.laN = geo.laN; p.gain = gain;
-  const ChainSmem L = chain_smem_layout<M, R>(m);
+  const ChainSmem L = chain_smem_layout<M, R, PP>(m);
   std::vector<unsigned char> smem(L.total + 64, 0xA5);   // poison: every read must have been written
   for (size_t wi = 0; wi < work.size(); wi++) {
-    HostCtx<M> ctx(K::NT);
+    HostCtx<M, PP> ctx(K::NT);
     memset(smem.data(), 0xA5, smem.size());
-    chain_tile<M, R, MT>(ctx, p, smem.data(), (int)wi);
+    chain_tile<M, R, MT, PP>(ctx, p, smem.data(), (int)wi);
   }
   return (int)work.size();
 }
@@ -62,12 +62,19 @@ static int run_chain(int m, int dct, int C, int n_rec, const long long* Ts, cons
 extern "C" int emu_chain(int M, int m, int r, int dct, int C, int n_rec, const long long* Ts, const float* pcm,
                          const long long* pcm_off, float* out, const long long* out_off, const double* h,
                          const double* g, const double* w_re_im, int gain, int chunk, int fast) {
-  // fast != 0: the compile-time-m instantiation (MT = m) where one exists, like the library's dispatch
+  // fast & 1: the compile-time-m instantiation (MT = m) where one exists, like the library's dispatch;
+  // fast & 2: two frame pairs per warp (PP = 2)
+#define ARGS m, dct, C, n_rec, Ts, pcm, pcm_off, out, out_off, h, g, w_re_im, gain, chunk
 #define CASE(MM, RR) \
   if (M == MM && (1 << r) == RR) { \
-    if (fast && m == 2) return run_chain<MM, RR, 2>(m, dct, C, n_rec, Ts, pcm, pcm_off, out, out_off, h, g, w_re_im, gain, chunk); \
-    if (fast && m == 4) return run_chain<MM, RR, 4>(m, dct, C, n_rec, Ts, pcm, pcm_off, out, out_off, h, g, w_re_im, gain, chunk); \
-    return run_chain<MM, RR, 0>(m, dct, C, n_rec, Ts, pcm, pcm_off, out, out_off, h, g, w_re_im, gain, chunk); \
+    if (fast & 2) { \
+      if ((fast & 1) && m == 2) return run_chain<MM, RR, 2, 2>(ARGS); \
+      if ((fast & 1) && m == 4) return run_chain<MM, RR, 4, 2>(ARGS); \
+      return run_chain<MM, RR, 0, 2>(ARGS); \
+    } \
+    if ((fast & 1) && m == 2) return run_chain<MM, RR, 2, 1>(ARGS); \
+    if ((fast & 1) && m == 4) return run_chain<MM, RR, 4, 1>(ARGS); \
+    return run_chain<MM, RR, 0, 1>(ARGS); \
   }
   BTK_EMU_CASES(CASE)
 #undef CASE

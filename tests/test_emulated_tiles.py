@@ -42,7 +42,7 @@ CASES = [  # M, m, r, dct, C, T, chunk
 ]
 
 
-@pytest.mark.parametrize("fast", [1, 0])
+@pytest.mark.parametrize("fast", [3, 1, 0])   # bit 0: compile-time m, bit 1: two frame pairs per warp
 @pytest.mark.parametrize("case", CASES)
 def test_emulated_chain_matches_oracle(case, fast, emu, prototypes):
     M, m, r, dct, C, T, chunk = case
