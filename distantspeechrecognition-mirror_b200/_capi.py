@@ -12,7 +12,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_long, c_longlo
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbtkb200.so")
+LIB_PATH = os.environ.get("BTKB200_LIB") or os.path.join(_HERE, "libbtkb200.so")   # override: A/B builds while tuning
 
 OK, EINVAL, ESTATE, ECUDA, ENOMEM, EUNSUPPORTED = 0, 1, 2, 3, 4, 5
 

@@ -471,7 +471,6 @@ BTK_HD void stage_window(Ctx& ctx, const ChainSmem& L, float* s_xs, const float*
   static_assert((K::NW >= RT) ? (K::NW % RT == 0) : (RT % K::NW == 0), "warps and residue tiles must nest");
   ctx.par([&](int tid, TS&) {
     const int warp = tid >> 5, lane = tid & 31, sub = lane & 15, hb = lane >> 4;
-    const int nbp = (L.NB + 1) / 2;
     float4 wv[WPT];
     if (wts) {
       const float4* src = reinterpret_cast<const float4*>(wts + (long long)cg0 * K::M);
@@ -481,37 +480,41 @@ BTK_HD void stage_window(Ctx& ctx, const ChainSmem& L, float* s_xs, const float*
         if (idx < K::CG * K::M / 2) wv[i] = src[idx];
       }
     }
-    // 32-bit sample indices inside the loops (T < 2^31; t may be negative at the stream start)
+    // 32-bit sample indices inside the loops (T < 2^31; t may be negative at the stream start).
+    // (An unguarded fast path for windows entirely inside [0, T) measured 2.7 % SLOWER on B200: tools/ab_run.sh.)
     const int t0 = (int)t_lo;
     const float* pcm_cg = pcm + cg0;
+    const int nb_h = (L.NB - hb + 1) / 2;                   // block pairs this half-warp stages: 2 bp + hb < NB
     for (int rt = warp % RSTEP; rt < RT; rt += RSTEP) {
       const int res = rt * 16 + sub;
       if (res >= D) continue;
       float* dst = s_xs + res * L.SB + hb;
       const int t_res = t0 + res + hb * D;
-      for (int bp0 = (K::NW >= RT ? warp / RT : 0); bp0 < nbp; bp0 += BSTEP * STEPS) {
+      for (int bp0 = (K::NW >= RT ? warp / RT : 0); bp0 < nb_h; bp0 += BSTEP * STEPS) {
         float x[STEPS][K::CG];
-        BTK_UNROLL
-        for (int s = 0; s < STEPS; s++) {
-          const int bp = bp0 + s * BSTEP;
-          const int t = t_res + bp * (2 * D);
+        {
           BTK_UNROLL
-          for (int c = 0; c < K::CG; c++) x[s][c] = 0.f;
-          if (2 * bp + hb < L.NB && t >= 0 && t < T) {
-            const float* src = pcm_cg + (size_t)((unsigned)t) * (unsigned)C;
-            if (vec4 && cg0 + K::CG <= C) {
-              const float4 q = *reinterpret_cast<const float4*>(src);
-              x[s][0] = q.x; x[s][1] = q.y; x[s][2] = q.z; x[s][3] = q.w;
-            } else {
-              BTK_UNROLL
-              for (int c = 0; c < K::CG; c++) if (cg0 + c < C) x[s][c] = src[c];
+          for (int s = 0; s < STEPS; s++) {
+            const int bp = bp0 + s * BSTEP;
+            const int t = t_res + bp * (2 * D);
+            BTK_UNROLL
+            for (int c = 0; c < K::CG; c++) x[s][c] = 0.f;
+            if (bp < nb_h && t >= 0 && t < T) {
+              const float* src = pcm_cg + (size_t)((unsigned)t) * (unsigned)C;
+              if (vec4 && cg0 + K::CG <= C) {
+                const float4 q = *reinterpret_cast<const float4*>(src);
+                x[s][0] = q.x; x[s][1] = q.y; x[s][2] = q.z; x[s][3] = q.w;
+              } else {
+                BTK_UNROLL
+                for (int c = 0; c < K::CG; c++) if (cg0 + c < C) x[s][c] = src[c];
+              }
             }
           }
         }
         BTK_UNROLL
         for (int s = 0; s < STEPS; s++) {
           const int bp = bp0 + s * BSTEP;
-          if (2 * bp + hb < L.NB) {
+          if (bp < nb_h) {
             BTK_UNROLL
             for (int c = 0; c < K::CG; c++) dst[c * L.CS + 2 * bp] = x[s][c];
           }
