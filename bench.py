@@ -220,7 +220,19 @@ def run_ours(args, wl_cfg, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        # NCCL may print its version banner on stdout when the communicator is created; the contract is ONE JSON
+        # line on stdout, so fd 1 points at stderr until the first collective has run.
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     M, m, r, C, nb = wl_cfg["M"], wl_cfg["m"], wl_cfg["r"], wl_cfg["C"], wl_cfg["batch"]
     T = int(round(wl_cfg["seconds"] * FS))

@@ -63,7 +63,10 @@ struct btkb200_plan {
   PinBuf h_desc;
   std::vector<long long> sig;  // signature of the cached chain work list
   int cached_n_work = 0;
+  std::vector<int> rec_work_begin;   // first work item of every recording (+ total at the end)
   cudaStream_t stream = nullptr;
+  cudaStream_t s_in = nullptr, s_out = nullptr;   // copy engines of the pipelined host-buffer path
+  std::vector<cudaEvent_t> ev_in, ev_k;
   long launches = 0;
   std::string err;
 };
@@ -188,6 +191,10 @@ void btkb200_plan_destroy(btkb200_plan* p) {
   p->d_recs.release(); p->d_work.release(); p->d_in.release(); p->d_out.release(); p->d_aux.release(); p->d_aux2.release();
   p->h_desc.release();
   if (p->stream) cudaStreamDestroy(p->stream);
+  if (p->s_in) cudaStreamDestroy(p->s_in);
+  if (p->s_out) cudaStreamDestroy(p->s_out);
+  for (cudaEvent_t e : p->ev_in) cudaEventDestroy(e);
+  for (cudaEvent_t e : p->ev_k) cudaEventDestroy(e);
   delete p;
 }
 
@@ -402,6 +409,46 @@ int btkb200_synthesis_dev(btkb200_plan* p, const float* d_Y, long F, float* d_ou
 }
 
 // ------------------------------------------------------------------------------------------- fused (device)
+// Build (or reuse) the work list of a batch: every recording is cut into chunks of output frames, one CTA each.
+static int chain_prepare(btkb200_plan* p, const long long* pcm_off, const long long* T, const long long* out_off, int n,
+                         cudaStream_t st) {
+  std::vector<long long> sig;
+  sig.reserve(3 * (size_t)n + 1);
+  sig.push_back(n);
+  for (int i = 0; i < n; i++) { sig.push_back(pcm_off[i]); sig.push_back(T[i]); sig.push_back(out_off[i]); }
+  if (sig == p->sig) return BTKB200_OK;
+  std::vector<RecDesc> recs(n);
+  long long total = 0;
+  for (int i = 0; i < n; i++) {
+    if (T[i] < 0 || T[i] > 0x7ffffff0LL) return fail(p, BTKB200_EINVAL, "recording %d: bad length %lld", i, T[i]);
+    recs[i].pcm_off = pcm_off[i]; recs[i].out_off = out_off[i]; recs[i].T = (int)T[i]; recs[i].nblk = p->geo.nblk(T[i]);
+    total += recs[i].nblk;
+  }
+  std::vector<WorkItem> work;
+  const int W = chain_frames_per_iter(p->geo.M, p->geo.R, p->geo.m), H = p->geo.m * p->geo.R - 1;
+  build_work(recs, choose_chunk(total, H, W), work);
+  p->rec_work_begin.assign(n + 1, 0);
+  for (size_t w = 0; w < work.size(); w++) p->rec_work_begin[work[w].rec + 1]++;
+  for (int i = 0; i < n; i++) p->rec_work_begin[i + 1] += p->rec_work_begin[i];
+  int rc = upload_desc(p, recs, work, st);
+  if (rc) return rc;
+  p->sig = sig;
+  p->cached_n_work = (int)work.size();
+  return BTKB200_OK;
+}
+
+// Launch the work items [w0, w1) of the prepared batch.
+static int chain_launch(btkb200_plan* p, const float* d_pcm, float* d_out, int w0, int w1, cudaStream_t st) {
+  if (w1 <= w0) return BTKB200_OK;
+  ChainParams c;
+  c.pcm = d_pcm; c.out = d_out; c.recs = (const RecDesc*)p->d_recs.p; c.work = (const WorkItem*)p->d_work.p + w0;
+  c.taps_h = p->d_taps_h; c.taps_g = p->d_taps_g; c.wts = p->d_wts_chain; c.twa = p->d_twa; c.twb = p->d_twb;
+  c.C = p->C; c.Cpad = p->Cpad; c.m = p->geo.m; c.pd_s = p->geo.pd_s; c.laN = p->geo.laN; c.gain = p->gain;
+  CK(p, launch_chain(p->geo.M, p->geo.R, c, w1 - w0, st));
+  p->launches++;
+  return BTKB200_OK;
+}
+
 int btkb200_chain_batch_dev(btkb200_plan* p, const float* d_pcm, const long long* pcm_off, const long long* T,
                             const long long* out_off, int n, float* d_out, void* stream) {
   if (!p || !d_pcm || !d_out || !pcm_off || !T || !out_off || n < 0) return BTKB200_EINVAL;
@@ -410,34 +457,9 @@ int btkb200_chain_batch_dev(btkb200_plan* p, const float* d_pcm, const long long
   if (n == 0) return BTKB200_OK;
   CK(p, cudaSetDevice(p->device));
   cudaStream_t st = (cudaStream_t)stream;
-  std::vector<long long> sig;
-  sig.reserve(3 * (size_t)n + 1);
-  sig.push_back(n);
-  for (int i = 0; i < n; i++) { sig.push_back(pcm_off[i]); sig.push_back(T[i]); sig.push_back(out_off[i]); }
-  if (sig != p->sig) {
-    std::vector<RecDesc> recs(n);
-    long long total = 0;
-    for (int i = 0; i < n; i++) {
-      if (T[i] < 0 || T[i] > 0x7fffffffLL) return fail(p, BTKB200_EINVAL, "recording %d: bad length %lld", i, T[i]);
-      recs[i].pcm_off = pcm_off[i]; recs[i].out_off = out_off[i]; recs[i].T = (int)T[i]; recs[i].nblk = p->geo.nblk(T[i]);
-      total += recs[i].nblk;
-    }
-    std::vector<WorkItem> work;
-    const int W = chain_frames_per_iter(p->geo.M, p->geo.R, p->geo.m), H = p->geo.m * p->geo.R - 1;
-    build_work(recs, choose_chunk(total, H, W), work);
-    int rc = upload_desc(p, recs, work, st);
-    if (rc) return rc;
-    p->sig = sig;
-    p->cached_n_work = (int)work.size();
-  }
-  if (p->cached_n_work == 0) return BTKB200_OK;
-  ChainParams c;
-  c.pcm = d_pcm; c.out = d_out; c.recs = (const RecDesc*)p->d_recs.p; c.work = (const WorkItem*)p->d_work.p;
-  c.taps_h = p->d_taps_h; c.taps_g = p->d_taps_g; c.wts = p->d_wts_chain; c.twa = p->d_twa; c.twb = p->d_twb;
-  c.C = p->C; c.Cpad = p->Cpad; c.m = p->geo.m; c.pd_s = p->geo.pd_s; c.laN = p->geo.laN; c.gain = p->gain;
-  CK(p, launch_chain(p->geo.M, p->geo.R, c, p->cached_n_work, st));
-  p->launches++;
-  return BTKB200_OK;
+  int rc = chain_prepare(p, pcm_off, T, out_off, n, st);
+  if (rc) return rc;
+  return chain_launch(p, d_pcm, d_out, 0, p->cached_n_work, st);
 }
 
 long btkb200_launch_count(const btkb200_plan* p) { return p ? p->launches : -1; }
@@ -524,6 +546,7 @@ int btkb200_covariance(btkb200_plan* p, const float* snap, long F, const double*
 int btkb200_chain_batch(btkb200_plan* p, const float* const* pcm, const long* T, int n, float* const* out) {
   if (!p || !pcm || !T || !out || n < 0) return BTKB200_EINVAL;
   if (!p->has_weights) return fail(p, BTKB200_ESTATE, "call calcArrayManifoldVectorsX() once");
+  if (!p->has_h || !p->has_g) return fail(p, BTKB200_ESTATE, "the fused chain needs both prototypes");
   if (n == 0) return BTKB200_OK;
   CK(p, cudaSetDevice(p->device));
   std::vector<long long> poff(n), ooff(n), Tl(n);
@@ -536,15 +559,39 @@ int btkb200_chain_batch(btkb200_plan* p, const float* const* pcm, const long* T,
   }
   CK(p, p->d_in.reserve((size_t)(pin ? pin : 4) * sizeof(float)));
   CK(p, p->d_out.reserve((size_t)(pout ? pout : 4) * sizeof(float)));
-  for (int i = 0; i < n; i++)
-    if (T[i] > 0)
-      CK(p, cudaMemcpyAsync((float*)p->d_in.p + poff[i], pcm[i], (size_t)T[i] * p->C * sizeof(float), cudaMemcpyHostToDevice, p->stream));
-  int rc = btkb200_chain_batch_dev(p, (const float*)p->d_in.p, poff.data(), Tl.data(), ooff.data(), n, (float*)p->d_out.p, p->stream);
+  if (!p->s_in) CK(p, cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
+  if (!p->s_out) CK(p, cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
+  int rc = chain_prepare(p, poff.data(), Tl.data(), ooff.data(), n, p->stream);
   if (rc) return rc;
-  for (int i = 0; i < n; i++) {
-    const size_t b = (size_t)p->geo.nblk(T[i]) * p->geo.D * sizeof(float);
-    if (b) CK(p, cudaMemcpyAsync(out[i], (float*)p->d_out.p + ooff[i], b, cudaMemcpyDeviceToHost, p->stream));
+  // Three-stage pipeline over groups of recordings: H2D on s_in, kernel on the plan's stream, D2H on s_out, so the
+  // upload of group k+1, the transform of group k and the download of group k-1 overlap (PCIe is full duplex).
+  // Group boundaries balance input bytes; a group's launch covers exactly the work items of its recordings.
+  const int G = n < 8 ? n : 8;
+  while ((int)p->ev_in.size() < G) { cudaEvent_t e; CK(p, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); p->ev_in.push_back(e); }
+  while ((int)p->ev_k.size() < G) { cudaEvent_t e; CK(p, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); p->ev_k.push_back(e); }
+  int r0 = 0;
+  for (int g = 0; g < G; g++) {
+    const long long want = pin * (g + 1) / G;
+    int r1 = r0;
+    while (r1 < n && (r1 == r0 || poff[r1] < want)) r1++;
+    if (g == G - 1) r1 = n;
+    for (int i = r0; i < r1; i++)
+      if (T[i] > 0)
+        CK(p, cudaMemcpyAsync((float*)p->d_in.p + poff[i], pcm[i], (size_t)T[i] * p->C * sizeof(float), cudaMemcpyHostToDevice, p->s_in));
+    CK(p, cudaEventRecord(p->ev_in[g], p->s_in));
+    CK(p, cudaStreamWaitEvent(p->stream, p->ev_in[g], 0));
+    rc = chain_launch(p, (const float*)p->d_in.p, (float*)p->d_out.p, p->rec_work_begin[r0], p->rec_work_begin[r1], p->stream);
+    if (rc) return rc;
+    CK(p, cudaEventRecord(p->ev_k[g], p->stream));
+    CK(p, cudaStreamWaitEvent(p->s_out, p->ev_k[g], 0));
+    for (int i = r0; i < r1; i++) {
+      const size_t b = (size_t)p->geo.nblk(T[i]) * p->geo.D * sizeof(float);
+      if (b) CK(p, cudaMemcpyAsync(out[i], (float*)p->d_out.p + ooff[i], b, cudaMemcpyDeviceToHost, p->s_out));
+    }
+    r0 = r1;
+    if (r0 >= n) break;
   }
+  CK(p, cudaStreamSynchronize(p->s_out));
   CK(p, cudaStreamSynchronize(p->stream));
   return BTKB200_OK;
 }
