@@ -105,7 +105,10 @@ static int upload_weights(btkb200_plan* p) {
 // chunk of output frames per CTA: enough CTAs to fill 148 SMs several times over, but long enough
 // that the (m R - 1)-frame warm-up of the synthesis history stays a small fraction.
 static int choose_chunk(long long total_frames, int H, int W) {
-  const long long target_ctas = 148LL * 2 * 4;
+#ifndef BTK_CHUNK_WAVES
+#define BTK_CHUNK_WAVES 2
+#endif
+  const long long target_ctas = 148LL * 2 * BTK_CHUNK_WAVES;
   long long chunk = (total_frames + target_ctas - 1) / target_ctas;
   if (chunk < 3LL * W) chunk = 3LL * W;
   if (chunk > 64LL * W) chunk = 64LL * W;

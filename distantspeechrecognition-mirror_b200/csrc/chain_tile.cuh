@@ -74,6 +74,8 @@ struct ChainCfg {
   static constexpr int NW = (M_ >= 1024 || PP_ == 2) ? 4 : 8;
   static constexpr int NT = NW * 32;
   static constexpr int FW = 2 * PP_;           // frames per warp per iteration
+  static constexpr int LV = (FW % 4 == 0) ? 4 : 2;   // floats per shared-memory access of the staged window (a warp's
+                                                     // span starts at block FW*warp: 16- or 8-byte aligned)
   static constexpr int W = FW * NW;            // analysis frames per iteration
   static constexpr int CG = 4;                 // channels staged per pass (one float4 per time step)
   static constexpr int NG = G::NG;             // lane groups per warp = channels processed concurrently
@@ -93,7 +95,8 @@ struct ChainSmem {
   int TS;      // floats per residue row of the tap table (m R padded: conflict-free vector loads)
   int TV;      // vector width (floats) of the tap loads
   int NB;      // D-blocks in the staged window
-  int SB;      // floats per residue row of the staged window (NB padded, SB/2 odd)
+  int SB;      // floats per residue row of the staged window: LV = 2: NB padded so that SB/2 is odd (conflict-free
+               // 8-byte accesses); LV = 4: NB rounded up to a multiple of 4, 16-byte quads XOR-swizzled by row (xs_off)
   int CS;      // floats per staged channel
   int H;       // v history frames kept between iterations (m R - 1)
 };
@@ -115,8 +118,14 @@ BTK_HD constexpr ChainSmem chain_smem_layout(int m) {
   s.TV = tap_vec(mR);
   s.TS = tap_stride(mR);
   s.NB = K::W - 1 + mR;
-  int sb = (s.NB + 1) & ~1;
-  if (((sb / 2) & 1) == 0) sb += 2;
+  int sb = 0;
+  if (K::LV == 4) {
+    sb = (s.NB + 3) & ~3;
+    if (((sb / 4) & 1) != 0) sb += 4;      // an even number of quads per row: rows r and r+4 share a bank group, the swizzle splits them
+  } else {
+    sb = (s.NB + 1) & ~1;
+    if (((sb / 2) & 1) == 0) sb += 2;
+  }
   s.SB = sb;
   int cs = K::D * sb;
   if (K::G::L < 16) cs += (16 - (cs & 31) + 32) & 31;   // two lane groups per LDS.64 phase land in disjoint banks
@@ -166,6 +175,14 @@ BTK_HD void load_floats(float* dst, const float* src) {
   }
 }
 
+// Float offset of block group bg (LV consecutive D-blocks) of residue row res inside one staged channel.
+// LV = 4: rows are 24 B * k apart, so rows r and r+4 would hit the same bank group; quad index ^ ((res >> 2) & 1)
+// makes any 8 consecutive rows conflict-free for 16-byte accesses without padding the rows.
+template <int LV>
+BTK_HD int xs_off(int res, int bg, int SB) {
+  return LV == 4 ? res * SB + ((bg ^ ((res >> 2) & 1)) << 2) : res * SB + 2 * bg;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Polyphase windowing of PP consecutive frame pairs of one staged channel (modulated.cc:419-434), using the
 // overlap between the frames: for the residue class rho (mod D) and pair pp (frames i0 = 2 pp, i1 = i0 + 1)
@@ -176,7 +193,7 @@ BTK_HD void load_floats(float* dst, const float* src) {
 // z[pp][r].x <- u_{i0}, z[pp][r].y <- u_{i1} in the canonical register layout.
 // ---------------------------------------------------------------------------------------------
 template <class K>
-BTK_HD void polyphase_pairs(cf* z, int gl, const float* xrow, const float* taps, const ChainSmem& L, int m) {
+BTK_HD void polyphase_pairs(cf* z, int gl, const float* xch, int warp, const float* taps, const ChainSmem& L, int m) {
   typedef typename K::G G;
   constexpr int R_ = K::R, PP = K::PP;
   BTK_UNROLL
@@ -184,7 +201,8 @@ BTK_HD void polyphase_pairs(cf* z, int gl, const float* xrow, const float* taps,
     BTK_UNROLL
     for (int e0 = 0; e0 < K::E; e0++) {
       const int rho = gl + G::L * rep + G::JA * e0;
-      const float* xp = xrow + (K::D - 1 - rho) * L.SB;   // xp[b]: block b of this warp's span; s_t(pp) = xp[2 pp + mR - t]
+      const int res = K::D - 1 - rho;
+      // block b of this warp's span is block FW*warp + b of the window; s_t(pp) = that row[2 pp + mR - t]
       const float* hp = taps + rho * L.TS;
       cf u[PP][R_];          // (u_{i0}, u_{i1})[rho + D a] of pair pp
       BTK_UNROLL
@@ -195,8 +213,11 @@ BTK_HD void polyphase_pairs(cf* z, int gl, const float* xrow, const float* taps,
       if (K::MT > 0) {
         constexpr int mR = (K::MT > 0 ? K::MT : 1) * R_;
         constexpr int NX = mR + 1 + 2 * (PP - 1);          // samples needed; read as float2 (the row is padded to even)
-        float xb[NX + 2], h[mR];
-        load_floats<(NX + 1) & ~1, 2>(xb, xp);
+        constexpr int NV = (NX + K::LV - 1) / K::LV;       // vector loads
+        float xb[NV * K::LV], h[mR];
+        BTK_UNROLL
+        for (int i = 0; i < NV; i++)
+          load_floats<K::LV, K::LV>(xb + i * K::LV, xch + xs_off<K::LV>(res, (K::FW / K::LV) * warp + i, L.SB));
         load_floats<mR, tap_vec(mR)>(h, hp);
         // (u_{i0}, u_{i1}) += h_t (s_{t+1}, s_t) = h_t (xb[2pp+mR-t-1], xb[2pp+mR-t]): where that is an aligned pair of the
         // float2 loads (mR-t-1 even) it is one packed FFMA2, otherwise two scalar ones
@@ -215,6 +236,10 @@ BTK_HD void polyphase_pairs(cf* z, int gl, const float* xrow, const float* taps,
         }
       } else {
         const int mR = m * R_;
+        auto xs_at = [&](int b) {        // block b of this warp's span
+          const int blk = K::FW * warp + b;
+          return xch[xs_off<K::LV>(res, blk / K::LV, L.SB) + blk % K::LV];
+        };
         for (int k = 0; k < m; k++) {
           BTK_UNROLL
           for (int a = 0; a < R_; a++) {
@@ -222,8 +247,8 @@ BTK_HD void polyphase_pairs(cf* z, int gl, const float* xrow, const float* taps,
             const float h = hp[t];
             BTK_UNROLL
             for (int pp = 0; pp < PP; pp++) {
-              u[pp][a].y = fmaf(h, xp[2 * pp + mR - t], u[pp][a].y);
-              u[pp][a].x = fmaf(h, xp[2 * pp + mR - t - 1], u[pp][a].x);
+              u[pp][a].y = fmaf(h, xs_at(2 * pp + mR - t), u[pp][a].y);
+              u[pp][a].x = fmaf(h, xs_at(2 * pp + mR - t - 1), u[pp][a].x);
             }
           }
         }
@@ -427,7 +452,7 @@ BTK_HD void analysis_round(Ctx& ctx, const ChainSmem& L, const float* s_xs, cons
   ctx.par([&](int tid, TS& ts) {
     const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
     const int c_local = round * K::NG + grp;
-    polyphase_pairs<K>(ts.z, gl, s_xs + c_local * L.CS + K::FW * warp, s_taps, L, m);
+    polyphase_pairs<K>(ts.z, gl, s_xs + c_local * L.CS, warp, s_taps, L, m);
     GroupFFT<M_, +1>::template step1_multi<K::PP>(ts.z, gl, slot(warp, grp), s_twa);
   });
   ctx.syncwarp();
@@ -452,25 +477,23 @@ BTK_HD void analysis_round(Ctx& ctx, const ChainSmem& L, const float* s_xs, cons
   });
 }
 
-// Stage CG channels [cg0, cg0+CG) of the window starting at sample t_lo: pcm [t][C] -> s_xs[c][t mod D][t div D],
-// and (when wts != 0) the weights of those channels, already in register order, into s_wts.
-// A warp covers 16 consecutive residues of two consecutive D-blocks per step: the global reads are two
-// coalesced runs and the residue-major stores hit 32 distinct banks (SB/2 is odd).  All global loads of a
-// thread are issued before its first shared-memory store (one DRAM/L2 round trip per stage, not one per step).
+// Stage CG channels [cg0, cg0+CG) of the window starting at sample t_lo: pcm [t][C] -> s_xs[c][t mod D][t div D]
+// (residue-major), and (when wts != 0) the weights of those channels, already in register order, into s_wts.
+// One task = one residue x LV consecutive D-blocks: LV coalesced float4 loads (4 channels of one time step each;
+// consecutive lanes take consecutive time steps) are transposed in registers into ONE 16- or 8-byte store per
+// channel.  All loads of a batch of tasks are issued before its first store (12 in flight per thread).
 template <class K, class Ctx>
 BTK_HD void stage_window(Ctx& ctx, const ChainSmem& L, float* s_xs, const float* pcm, int C, int T, long long t_lo,
                          int cg0, bool vec4, float4* s_wts, const cf* wts) {
   typedef ChainThreadState<K::M, K::PP> TS;
-  constexpr int D = K::D;
-  constexpr int RT = (D + 15) / 16;
+  constexpr int D = K::D, LV = K::LV;
+  static_assert(K::CG == 4, "one float4 per time step");
   constexpr int WPT = (K::CG * K::M / 2 + K::NT - 1) / K::NT;   // weight float4 per thread
-  constexpr int STEPS = 6;                                      // loads in flight per thread
-  // warp -> (residue tile, first block pair); both strides are compile-time constants
-  constexpr int RSTEP = K::NW >= RT ? RT : K::NW;               // residue-tile stride of the outer loop
-  constexpr int BSTEP = K::NW >= RT ? K::NW / RT : 1;           // block-pair stride of the inner loop
-  static_assert((K::NW >= RT) ? (K::NW % RT == 0) : (RT % K::NW == 0), "warps and residue tiles must nest");
+#ifndef BTK_STAGE_LOADS
+#define BTK_STAGE_LOADS 12
+#endif
+  constexpr int TB = BTK_STAGE_LOADS / LV;                       // tasks per batch
   ctx.par([&](int tid, TS&) {
-    const int warp = tid >> 5, lane = tid & 31, sub = lane & 15, hb = lane >> 4;
     float4 wv[WPT];
     if (wts) {
       const float4* src = reinterpret_cast<const float4*>(wts + (long long)cg0 * K::M);
@@ -481,42 +504,49 @@ BTK_HD void stage_window(Ctx& ctx, const ChainSmem& L, float* s_xs, const float*
       }
     }
     // 32-bit sample indices inside the loops (T < 2^31; t may be negative at the stream start).
-    // (An unguarded fast path for windows entirely inside [0, T) measured 2.7 % SLOWER on B200: tools/ab_run.sh.)
     const int t0 = (int)t_lo;
     const float* pcm_cg = pcm + cg0;
-    const int nb_h = (L.NB - hb + 1) / 2;                   // block pairs this half-warp stages: 2 bp + hb < NB
-    for (int rt = warp % RSTEP; rt < RT; rt += RSTEP) {
-      const int res = rt * 16 + sub;
-      if (res >= D) continue;
-      float* dst = s_xs + res * L.SB + hb;
-      const int t_res = t0 + res + hb * D;
-      for (int bp0 = (K::NW >= RT ? warp / RT : 0); bp0 < nb_h; bp0 += BSTEP * STEPS) {
-        float x[STEPS][K::CG];
-        {
+    const bool v4 = vec4 && cg0 + K::CG <= C;
+    const int ntask = D * ((L.NB + LV - 1) / LV);
+    for (int task0 = tid; task0 < ntask; task0 += K::NT * TB) {
+      float x[TB][LV][K::CG];
+      BTK_UNROLL
+      for (int k = 0; k < TB; k++) {
+        const int task = task0 + k * K::NT;
+        const int res = task % D, bg = task / D;
+        BTK_UNROLL
+        for (int i = 0; i < LV; i++) {
+          const int blk = bg * LV + i;
+          const int t = t0 + blk * D + res;
           BTK_UNROLL
-          for (int s = 0; s < STEPS; s++) {
-            const int bp = bp0 + s * BSTEP;
-            const int t = t_res + bp * (2 * D);
-            BTK_UNROLL
-            for (int c = 0; c < K::CG; c++) x[s][c] = 0.f;
-            if (bp < nb_h && t >= 0 && t < T) {
-              const float* src = pcm_cg + (size_t)((unsigned)t) * (unsigned)C;
-              if (vec4 && cg0 + K::CG <= C) {
-                const float4 q = *reinterpret_cast<const float4*>(src);
-                x[s][0] = q.x; x[s][1] = q.y; x[s][2] = q.z; x[s][3] = q.w;
-              } else {
-                BTK_UNROLL
-                for (int c = 0; c < K::CG; c++) if (cg0 + c < C) x[s][c] = src[c];
-              }
+          for (int c = 0; c < K::CG; c++) x[k][i][c] = 0.f;
+          if (task < ntask && blk < L.NB && (unsigned)t < (unsigned)T) {
+            const float* src = pcm_cg + (size_t)((unsigned)t) * (unsigned)C;
+            if (v4) {
+              const float4 q = *reinterpret_cast<const float4*>(src);
+              x[k][i][0] = q.x; x[k][i][1] = q.y; x[k][i][2] = q.z; x[k][i][3] = q.w;
+            } else {
+              BTK_UNROLL
+              for (int c = 0; c < K::CG; c++) if (cg0 + c < C) x[k][i][c] = src[c];
             }
           }
         }
-        BTK_UNROLL
-        for (int s = 0; s < STEPS; s++) {
-          const int bp = bp0 + s * BSTEP;
-          if (bp < nb_h) {
-            BTK_UNROLL
-            for (int c = 0; c < K::CG; c++) dst[c * L.CS + 2 * bp] = x[s][c];
+      }
+      BTK_UNROLL
+      for (int k = 0; k < TB; k++) {
+        const int task = task0 + k * K::NT;
+        if (task < ntask) {
+          const int res = task % D, bg = task / D;
+          float* dst = s_xs + xs_off<LV>(res, bg, L.SB);
+          BTK_UNROLL
+          for (int c = 0; c < K::CG; c++) {
+            if (LV == 4) {
+              float4 v; v.x = x[k][0][c]; v.y = x[k][1][c]; v.z = x[k][LV > 2 ? 2 : 0][c]; v.w = x[k][LV - 1][c];
+              *reinterpret_cast<float4*>(dst + c * L.CS) = v;
+            } else {
+              float2 v; v.x = x[k][0][c]; v.y = x[k][1][c];
+              *reinterpret_cast<float2*>(dst + c * L.CS) = v;
+            }
           }
         }
       }

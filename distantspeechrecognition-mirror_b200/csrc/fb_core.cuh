@@ -198,7 +198,8 @@ template <int M_> struct FFTGeom {
 // loads of 8 consecutive lanes fall into distinct bank groups.
 template <int M_> struct FFTTables {
   typedef FFTGeom<M_> G;
-  static constexpr int ta_() { int t = (G::Ra - 1 + 1) & ~1; if (((t / 2) & 1) == 0) t += 2; return t; }
+  // two-pass transforms read only W_M^j (the powers are formed in registers): one word per owner
+  static constexpr int ta_() { if (G::Rb == 1) return 1; int t = (G::Ra - 1 + 1) & ~1; if (((t / 2) & 1) == 0) t += 2; return t; }
   static constexpr int TA = ta_();
   static constexpr int TWA_WORDS = G::JA * TA;
   static constexpr int TB = G::Rb > 1 ? (G::Rb == 2 ? 2 : 6) : 0;

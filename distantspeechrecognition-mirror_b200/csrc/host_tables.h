@@ -44,9 +44,10 @@ inline void build_fft_tables_m(std::vector<cf>& twa, std::vector<cf>& twb) {
     return mk((float)cos(a), (float)sin(a));
   };
   twa.assign(FT::TWA_WORDS > 0 ? FT::TWA_WORDS : 1, mk(1.f, 0.f));
-  for (int j = 0; j < G::JA; j++)
-    for (int ka = 1; ka < G::Ra; ka++)
-      twa[(size_t)j * FT::TA + (ka - 1)] = G::Rb > 1 ? W((long long)(j / G::Rc) * ka * G::Rc) : W((long long)j * ka);
+  for (int j = 0; j < G::JA; j++) {
+    if (G::Rb == 1) { twa[(size_t)j * FT::TA] = W((long long)j); continue; }      // powers are formed in registers
+    for (int ka = 1; ka < G::Ra; ka++) twa[(size_t)j * FT::TA + (ka - 1)] = W((long long)(j / G::Rc) * ka * G::Rc);
+  }
   twb.assign(FT::TWB_WORDS > 0 ? FT::TWB_WORDS : 1, mk(1.f, 0.f));
   if (G::Rb > 1)
     for (int iB = 0; iB < M_ / G::Rb; iB++) {

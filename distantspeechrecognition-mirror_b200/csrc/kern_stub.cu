@@ -1,0 +1,12 @@
+// kern_stub.cu -- tuning builds only (tools/ab_multi.sh): stands in for the transform sizes that are not being
+// compared, so that an A/B library compiles in seconds.  Never part of libbtkb200.so.
+#include "launch.h"
+namespace btk {
+#define STUB(MM)                                                                                                   \
+  cudaError_t launch_chain_m##MM(int, const ChainParams&, int, cudaStream_t) { return cudaErrorInvalidValue; }       \
+  cudaError_t launch_analysis_m##MM(int, const AnalysisParams&, int, cudaStream_t) { return cudaErrorInvalidValue; } \
+  cudaError_t launch_synthesis_m##MM(int, const SynthesisParams&, int, cudaStream_t) { return cudaErrorInvalidValue; } \
+  int fb_smem_bytes_m##MM(int, int) { return -1; }                                                                 \
+  int chain_frames_per_iter_m##MM(int, int) { return -1; }
+STUB(64) STUB(128) STUB(512) STUB(1024)
+}  // namespace btk
