@@ -23,7 +23,8 @@ SYMBOLS = [
     "btkb200_set_ds_weights", "btkb200_set_weights", "btkb200_get_weights", "btkb200_get_manifold",
     "btkb200_set_covariance", "btkb200_get_covariance", "btkb200_set_diffuse_noise_model", "btkb200_diag_load",
     "btkb200_diag_load_bin", "btkb200_divide_nondiagonal", "btkb200_solve_mvdr", "btkb200_analysis",
-    "btkb200_beamform", "btkb200_synthesis", "btkb200_covariance", "btkb200_chain", "btkb200_chain_batch",
+    "btkb200_beamform", "btkb200_synthesis", "btkb200_covariance", "btkb200_estimate_covariance", "btkb200_chain",
+    "btkb200_chain_batch",
     "btkb200_chain_batch_multi", "btkb200_chain_batch_dev", "btkb200_analysis_dev", "btkb200_beamform_dev",
     "btkb200_synthesis_dev", "btkb200_launch_count", "btkb200_sync", "btkb200_host_alloc", "btkb200_host_free",
 ]
@@ -83,6 +84,7 @@ def lib() -> ctypes.CDLL:
     L.btkb200_beamform.argtypes = [vp, vp, c_long, vp]
     L.btkb200_synthesis.argtypes = [vp, vp, c_long, vp, POINTER(c_long)]
     L.btkb200_covariance.argtypes = [vp, vp, c_long, vp, c_int, vp]
+    L.btkb200_estimate_covariance.argtypes = [vp, vp, c_long, c_double, c_long, c_int]
     L.btkb200_chain.argtypes = [vp, vp, c_long, vp]
     L.btkb200_chain_batch.argtypes = [vp, POINTER(vp), POINTER(c_long), c_int, POINTER(vp)]
     L.btkb200_chain_batch_multi.argtypes = [POINTER(vp), c_int, POINTER(vp), POINTER(c_long), c_int, POINTER(vp)]
@@ -254,6 +256,13 @@ class Plan:
         R = np.zeros((self.B, self.C, self.C), dtype=np.complex128)
         self._ck(self._L.btkb200_covariance(self._h, _p(s), F, _p(w), 1 if conjugate else 0, _p(R)))
         return R
+
+    def estimate_covariance(self, pcm, forget: float = 0.99, last_frame: int = -1, conjugate: bool = True):
+        """pcm [T][C] -> the plan's per-bin noise matrices (analysis + covariance on the device)."""
+        x = np.ascontiguousarray(pcm, dtype=np.float32)
+        if x.ndim != 2 or x.shape[1] != self.C:
+            raise BtkError(EINVAL, f"pcm must be [T][{self.C}]")
+        self._ck(self._L.btkb200_estimate_covariance(self._h, _p(x), x.shape[0], forget, last_frame, 1 if conjugate else 0))
 
     # -- fused path (host numpy buffers)
     def chain(self, pcm) -> np.ndarray:

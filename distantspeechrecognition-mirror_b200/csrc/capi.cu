@@ -546,6 +546,42 @@ int btkb200_covariance(btkb200_plan* p, const float* snap, long F, const double*
   return BTKB200_OK;
 }
 
+int btkb200_estimate_covariance(btkb200_plan* p, const float* pcm, long T, double forget, long last_frame, int conjugate) {
+  if (!p || !pcm || T < 0 || !(forget >= 0.0 && forget <= 1.0)) return BTKB200_EINVAL;
+  if (!p->has_h) return fail(p, BTKB200_ESTATE, "plan was created without an analysis prototype");
+  if (p->C > 64) return fail(p, BTKB200_EUNSUPPORTED, "covariance supports at most 64 channels (got %d)", p->C);
+  CK(p, cudaSetDevice(p->device));
+  const int B = p->geo.B, C = p->C;
+  const long F = p->geo.analysis_frames(T);
+  long Fu = (last_frame >= 0 && last_frame + 1 < F) ? last_frame + 1 : F;      // frames that adapt
+  // frame weights of the recursion unrolled: frame f contributes (1-ff) ff^(Fu-1-f); the Python flavour starts from
+  // S = x0 x0^H (weight ff^(Fu-1) for frame 0), the C++ flavour from R = 0
+  std::vector<double> wt((size_t)(Fu > 0 ? Fu : 1), 0.0);
+  double acc = 1.0;
+  for (long f = Fu - 1; f >= 0; f--) { wt[f] = (1.0 - forget) * acc; acc *= forget; }
+  if (conjugate && Fu > 0) wt[0] = pow(forget, (double)(Fu - 1));   // pow(0, 0) == 1: a single frame keeps S = x0 x0^H
+  const size_t bin = (size_t)T * C * sizeof(float), bsnap = (size_t)F * B * C * sizeof(cf);
+  const size_t bw = (size_t)wt.size() * sizeof(double), bR = (size_t)B * C * C * sizeof(double2);
+  CK(p, p->d_in.reserve(bin ? bin : 16));
+  CK(p, p->d_out.reserve(bsnap ? bsnap : 16));
+  CK(p, p->d_aux2.reserve(bw + 16 + bR));
+  double* dwt = (double*)p->d_aux2.p;
+  double2* dR = (double2*)((char*)p->d_aux2.p + ((bw + 15) / 16) * 16);
+  if (bin) CK(p, cudaMemcpyAsync(p->d_in.p, pcm, bin, cudaMemcpyHostToDevice, p->stream));
+  CK(p, cudaMemsetAsync(dR, 0, bR, p->stream));
+  int rc = btkb200_analysis_dev(p, (const float*)p->d_in.p, T, (float*)p->d_out.p, p->stream);
+  if (rc) return rc;
+  if (Fu > 0) {
+    CK(p, cudaMemcpyAsync(dwt, wt.data(), bw, cudaMemcpyHostToDevice, p->stream));
+    CK(p, launch_covariance((const cf*)p->d_out.p, dwt, dR, Fu, B, C, conjugate ? 1 : 0, p->stream));
+    p->launches++;
+  }
+  CK(p, cudaMemcpyAsync(p->Rn.data(), dR, bR, cudaMemcpyDeviceToHost, p->stream));
+  CK(p, cudaStreamSynchronize(p->stream));
+  std::fill(p->Rn_set.begin(), p->Rn_set.end(), 1);
+  return BTKB200_OK;
+}
+
 int btkb200_chain_batch(btkb200_plan* p, const float* const* pcm, const long* T, int n, float* const* out) {
   if (!p || !pcm || !T || !out || n < 0) return BTKB200_EINVAL;
   if (!p->has_weights) return fail(p, BTKB200_ESTATE, "call calcArrayManifoldVectorsX() once");

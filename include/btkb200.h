@@ -110,6 +110,15 @@ int btkb200_synthesis(btkb200_plan* plan, const float* Y, long F, float* out, lo
 int btkb200_covariance(btkb200_plan* plan, const float* snap, long F, const double* frame_weights, int conjugate,
                        double* R);
 
+/* Adaptive (sample-covariance) MVDR in one call, entirely on the device: analysis of pcm [T][C] -> per-bin
+ * spatial covariance with exponential forgetting -> the plan's noise matrices (as if setNoiseSpatialSpectralMatrix had
+ * been called for every bin).  Follows SubbandBeamformerMVDR.updateSx (lib/subbandBeamforming.py:1138, 1170-1175):
+ * S = x x^H at frame 0, then S <- ff S + (1-ff) x x^H while frame <= last_frame (last_frame < 0: all frames);
+ * conjugate == 0 gives the C++ SpectralMatrixArray::update flavour x x^T with R <- mu R + (1-mu) x x^T from R = 0
+ * (beamformer.cc:142-163).  Follow with btkb200_diag_load and btkb200_solve_mvdr; no subband data touches the host. */
+int btkb200_estimate_covariance(btkb200_plan* plan, const float* pcm, long T, double forget, long last_frame,
+                                int conjugate);
+
 /* ---- fused path ---------------------------------------------------------------------------------------- */
 /* pcm -> out through analysis -> weight apply -> synthesis in ONE kernel; out holds nblk(T)*D floats.
  * ESTATE if no weights are installed (j_error, beamformer.cc:1140-1143). */

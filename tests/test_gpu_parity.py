@@ -155,6 +155,42 @@ def test_sample_covariance_and_adaptive_mvdr(prototypes):
     plan.close()
 
 
+def test_adaptive_mvdr_on_device_end_to_end(prototypes):
+    """cfg3 geometry (16-mic linear array, M=512 m=2 r=2): covariance estimated from a noise-only lead-in ON THE DEVICE
+    (btkb200_estimate_covariance), loading 1e-2 trace/C, per-bin solve, then the fused chain on the recording."""
+    M, m, r, C, T = 512, 2, 2, 16, 32000
+    h, g = proto(prototypes, M, m, r)
+    geo = bo.BankGeometry(M, m, r, 0)
+    mp = wl.linear_array(C, 41.0)
+    tau = wl.farfield_delays(mp, np.deg2rad(30), np.deg2rad(90))
+    noise = wl.noise_recording(16000, C, seed=41, sigma=300.0)
+    pcm = wl.array_recording(T, tau, seed=42, noise_sigma=300.0)
+    plan = btk_b200.Plan(M, m, r, C, h, g)
+    plan.set_ds_weights(FS, tau)
+    for ff, last, conj in [(0.99, -1, True), (0.9, 20, True), (0.95, -1, False)]:
+        plan.estimate_covariance(noise, forget=ff, last_frame=last, conjugate=conj)
+        X = np.stack([bo.analysis(noise[:, c], h, geo) for c in range(C)], axis=1)
+        if conj:
+            S = bo.spectral_matrix_py(X[: (last + 1) if last >= 0 else None], ff)
+        else:
+            S = bo.spectral_matrix_cpp(X, ff)[: geo.B]
+        Sd = np.stack([plan.get_covariance(s) for s in range(geo.B)])
+        assert bo.rel_l2(Sd, S) <= TOL_REL
+    plan.estimate_covariance(noise, forget=0.99)
+    Sd = np.stack([plan.get_covariance(s) for s in range(geo.B)])
+    load = 1e-2 * float(np.real(np.trace(Sd[40]))) / C
+    plan.diag_load(load)
+    assert plan.solve_mvdr() == 0
+    W = bo.mvdr_weights(bo.diagonal_load(Sd, load), bo.ds_weights(tau, FS, M))
+    assert bo.rel_l2(plan.get_weights(), W) <= 1e-6
+    _, Y, ref = bo.chain(pcm, h, g, geo, W)
+    assert bo.snr_db(plan.chain(pcm), ref) >= TOL_SNR
+    # distortionless towards the look direction: w^H d = 1/C * C ... the reference normalisation gives w^H v = 1
+    d = bo.ds_weights(tau, FS, M) * C
+    assert np.allclose(np.sum(np.conj(W[1:]) * d[1:], axis=1), 1.0, atol=1e-6)
+    plan.close()
+
+
 def test_batch_ragged_and_edge_lengths(prototypes):
     M, m, r, C = 256, 4, 1, 4
     h, g = proto(prototypes, M, m, r)
