@@ -23,7 +23,7 @@ template <int M, int PP> struct DevCtx {
 // two CTAs per SM whenever two of them fit the 227 KB of shared memory
 template <int M, int R, int MT, int PP> struct KernCfg {
   static constexpr int smem = chain_smem_layout<M, R, PP>(MT > 0 ? MT : 4).total;
-  static constexpr int MINB = (M <= 256 && smem <= 113 * 1024) ? 2 : 1;
+  static constexpr int MINB = (smem <= 112 * 1024) ? 2 : 1;
 };
 
 // Frame pairs per warp of the fused chain: two (one 8-warp CTA per SM, up to 255 registers per thread, taps /
