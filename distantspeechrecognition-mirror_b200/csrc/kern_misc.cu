@@ -88,72 +88,116 @@ cudaError_t launch_beamform(const cf* snap, const cf* w, cf* Y, long long F, int
 }
 
 // ---------------------------------------------------------------------------------------------
-// Weighted Gram matrices.  grid = (B bins, SPLIT frame slices); each CTA stages FB frames of its bin in
-// shared memory and every thread owns a strided set of (i, j) pairs with double accumulators; slices are
-// merged with double atomics into Rout (zeroed by the caller).
+// Weighted Gram matrices R[s] = sum_f wt[f] x_f x_f^H (conj) or x_f x_f^T, register-tiled outer products.
+// grid = (B bins, SPLIT frame slices).  A CTA stages 32 frames of its bin in shared memory twice -- x and
+// wt*conj(x) -- and every thread owns one TILE x TILE block of the upper triangle (both flavours are symmetric
+// up to conjugation): per frame 2*TILE complex loads feed TILE^2 packed complex multiply-adds.  fp32 partial sums
+// over <= 32 frames are promoted to fp64 accumulators; slices are merged with fp64 atomics into Rout (zeroed by the
+// caller), the lower triangle is written as the mirror.
 // ---------------------------------------------------------------------------------------------
 #define BTK_COV_FB 32
-#define BTK_COV_MAXPAIRS 16
+template <int TILE>
 __global__ void __launch_bounds__(256) btk_covariance_kernel(const cf* __restrict__ snap, const double* __restrict__ wt,
                                                             double2* __restrict__ Rout, long long F, int B, int C,
                                                             int conj) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  cf* sx = reinterpret_cast<cf*>(smem_raw);              // [FB][C]
-  float* sw = reinterpret_cast<float*>(sx + BTK_COV_FB * C);
+  const int Cp = (C + TILE - 1) / TILE * TILE, nt = Cp / TILE, ntile = nt * (nt + 1) / 2;
+  cf* sx = reinterpret_cast<cf*>(smem_raw);              // [FB][Cp]  x
+  cf* sy = sx + BTK_COV_FB * Cp;                          // [FB][Cp]  wt * (conj ? conj(x) : x)
   const int s = blockIdx.x;
   const long long per = (F + gridDim.y - 1) / gridDim.y;
   const long long f_lo = per * blockIdx.y, f_hi = (f_lo + per < F) ? f_lo + per : F;
-  const int npair = C * C;
-  double ar[BTK_COV_MAXPAIRS], ai[BTK_COV_MAXPAIRS];
+  // upper-triangular tile (ti <= tj) of this thread
+  int ti = 0, tj = 0;
+  const bool active = (int)threadIdx.x < ntile;
+  {
+    int kk = threadIdx.x;
+    for (ti = 0; ti < nt; ti++) {
+      const int len = nt - ti;
+      if (kk < len) { tj = ti + kk; break; }
+      kk -= len;
+    }
+    if (!active) { ti = 0; tj = 0; }
+  }
+  double2 acc[TILE][TILE];
 #pragma unroll
-  for (int k = 0; k < BTK_COV_MAXPAIRS; k++) { ar[k] = 0.0; ai[k] = 0.0; }
+  for (int p = 0; p < TILE; p++)
+#pragma unroll
+    for (int q = 0; q < TILE; q++) acc[p][q] = make_double2(0.0, 0.0);
   for (long long f0 = f_lo; f0 < f_hi; f0 += BTK_COV_FB) {
     const int nf = (int)((f_hi - f0 < BTK_COV_FB) ? f_hi - f0 : BTK_COV_FB);
     __syncthreads();
-    for (int i = threadIdx.x; i < nf * C; i += blockDim.x) {
-      const int ff = i / C, c = i % C;
-      sx[i] = snap[((f0 + ff) * B + s) * C + c];
+    for (int i = threadIdx.x; i < nf * Cp; i += blockDim.x) {
+      const int ff = i / Cp, c = i % Cp;
+      cf v = mk(0.f, 0.f);
+      if (c < C) v = snap[((f0 + ff) * B + s) * C + c];
+      const float w = (float)wt[f0 + ff];
+      sx[i] = v;
+      sy[i] = mk(w * v.x, conj ? -w * v.y : w * v.y);
     }
-    for (int i = threadIdx.x; i < nf; i += blockDim.x) sw[i] = (float)wt[f0 + i];
     __syncthreads();
+    if (active) {
+      cf part[TILE][TILE];
 #pragma unroll
-    for (int k = 0; k < BTK_COV_MAXPAIRS; k++) {
-      const int pr = threadIdx.x + k * 256;
-      if (pr < npair) {
-        const int i = pr / C, j = pr % C;
-        float pre = 0.f, pim = 0.f;   // fp32 partial over <= 32 frames, promoted to double per batch
-        for (int ff = 0; ff < nf; ff++) {
-          const cf a = sx[ff * C + i];
-          cf b = sx[ff * C + j];
-          if (conj) b.y = -b.y;
-          const float wgt = sw[ff];
-          pre = fmaf(wgt, fmaf(a.x, b.x, -a.y * b.y), pre);
-          pim = fmaf(wgt, fmaf(a.x, b.y, a.y * b.x), pim);
+      for (int p = 0; p < TILE; p++)
+#pragma unroll
+        for (int q = 0; q < TILE; q++) part[p][q] = mk(0.f, 0.f);
+      const cf* pa = sx + ti * TILE;
+      const cf* pb = sy + tj * TILE;
+      for (int ff = 0; ff < nf; ff++) {
+        cf a[TILE], b[TILE];
+#pragma unroll
+        for (int p = 0; p < TILE; p += 2) {
+          const float4 va = *reinterpret_cast<const float4*>(pa + ff * Cp + p);
+          const float4 vb = *reinterpret_cast<const float4*>(pb + ff * Cp + p);
+          a[p] = mk(va.x, va.y); a[p + 1] = mk(va.z, va.w);
+          b[p] = mk(vb.x, vb.y); b[p + 1] = mk(vb.z, vb.w);
         }
-        ar[k] += (double)pre; ai[k] += (double)pim;
+#pragma unroll
+        for (int p = 0; p < TILE; p++)
+#pragma unroll
+          for (int q = 0; q < TILE; q++) cfma(part[p][q], a[p], b[q]);
       }
+#pragma unroll
+      for (int p = 0; p < TILE; p++)
+#pragma unroll
+        for (int q = 0; q < TILE; q++) { acc[p][q].x += (double)part[p][q].x; acc[p][q].y += (double)part[p][q].y; }
     }
   }
+  if (active) {
+    double2* Rs = Rout + (long long)s * C * C;
 #pragma unroll
-  for (int k = 0; k < BTK_COV_MAXPAIRS; k++) {
-    const int pr = threadIdx.x + k * 256;
-    if (pr < npair) {
-      double2* dst = Rout + (long long)s * npair + pr;
-      atomicAdd(&dst->x, ar[k]);
-      atomicAdd(&dst->y, ai[k]);
-    }
+    for (int p = 0; p < TILE; p++)
+#pragma unroll
+      for (int q = 0; q < TILE; q++) {
+        const int i = ti * TILE + p, j = tj * TILE + q;
+        if (i >= C || j >= C) continue;
+        atomicAdd(&Rs[i * C + j].x, acc[p][q].x);
+        atomicAdd(&Rs[i * C + j].y, acc[p][q].y);
+        if (ti != tj) {      // mirror: R_ji = conj(R_ij) (Hermitian flavour) or R_ij (x x^T flavour)
+          atomicAdd(&Rs[j * C + i].x, acc[p][q].x);
+          atomicAdd(&Rs[j * C + i].y, conj ? -acc[p][q].y : acc[p][q].y);
+        }
+      }
   }
 }
 
 cudaError_t launch_covariance(const cf* snap, const double* wt, double2* Rout, long long F, int B, int C, int conj,
                               cudaStream_t st) {
-  if (C * C > 256 * BTK_COV_MAXPAIRS) return cudaErrorInvalidValue;   // C <= 64
+  if (C > 64) return cudaErrorInvalidValue;
   if (F == 0) return cudaSuccess;
   int split = (int)((F + 511) / 512);
   if (split < 1) split = 1;
   if (split > 64) split = 64;
-  const size_t smem = (size_t)BTK_COV_FB * C * sizeof(cf) + BTK_COV_FB * sizeof(float);
-  btk_covariance_kernel<<<dim3(B, split), 256, smem, st>>>(snap, wt, Rout, F, B, C, conj);
+  if (C >= 32) {
+    const int Cp = (C + 3) / 4 * 4;
+    const size_t smem = (size_t)2 * BTK_COV_FB * Cp * sizeof(cf);
+    btk_covariance_kernel<4><<<dim3(B, split), 160, smem, st>>>(snap, wt, Rout, F, B, C, conj);
+  } else {
+    const int Cp = (C + 1) / 2 * 2;
+    const size_t smem = (size_t)2 * BTK_COV_FB * Cp * sizeof(cf);
+    btk_covariance_kernel<2><<<dim3(B, split), 160, smem, st>>>(snap, wt, Rout, F, B, C, conj);
+  }
   return cudaGetLastError();
 }
 
