@@ -110,7 +110,9 @@ static int choose_chunk(long long total_frames, int H, int W) {
 #endif
   const long long target_ctas = 148LL * 2 * BTK_CHUNK_WAVES;
   long long chunk = (total_frames + target_ctas - 1) / target_ctas;
-  if (chunk < 3LL * W) chunk = 3LL * W;
+  // small jobs (one short recording): prefer filling the SMs over amortising the warm-up, down to chunks whose
+  // warm-up is half of their work (a 10-s recording is 139 CTAs instead of 22)
+  if (chunk < H) chunk = H;
   if (chunk > 64LL * W) chunk = 64LL * W;
   // make chunk + H a multiple of W so no iteration is partly wasted
   long long its = (chunk + H + W - 1) / W;
@@ -376,7 +378,14 @@ int btkb200_analysis_dev(btkb200_plan* p, const float* d_pcm, long T, float* d_s
   AnalysisParams a;
   a.pcm = d_pcm; a.snap = (cf*)d_snap; a.recs = (const RecDesc*)p->d_recs.p; a.work = (const WorkItem*)p->d_work.p;
   a.taps_h = p->d_taps_h; a.twa = p->d_twa; a.twb = p->d_twb; a.C = p->C; a.Cpad = p->Cpad; a.m = p->geo.m; a.laN = p->geo.laN;
-  if (!work.empty()) { CK(p, launch_analysis(p->geo.M, p->geo.R, a, (int)work.size(), st)); p->launches++; }
+  // channels are independent in the analysis bank: when the frame chunks alone do not fill the SMs, the channel
+  // groups of a chunk are spread over several CTAs
+  const int n_cg = p->Cpad / 4;
+  int slices = work.empty() ? 1 : (int)(2 * 148 / work.size());
+  if (slices < 1) slices = 1;
+  if (slices > n_cg) slices = n_cg;
+  a.cg_slices = slices;
+  if (!work.empty()) { CK(p, launch_analysis(p->geo.M, p->geo.R, a, (int)work.size() * slices, st)); p->launches++; }
   return BTKB200_OK;
 }
 

@@ -211,6 +211,12 @@ __device__ __forceinline__ double2 zdiv(double2 a, double2 b) {
   return make_double2((a.x * b.x + a.y * b.y) / d, (a.y * b.x - a.x * b.y) / d);
 }
 
+__device__ __forceinline__ double shfl_d(double v, int src) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_sync(0xffffffffu, lo, src); hi = __shfl_sync(0xffffffffu, hi, src);
+  return __hiloint2double(hi, lo);
+}
+
 __global__ void __launch_bounds__(128) btk_mvdr_solve_kernel(const double2* __restrict__ Rn, const double2* __restrict__ dvec,
                                                             double2* __restrict__ w, int* __restrict__ fallback, int C,
                                                             double dThreshold) {
@@ -218,7 +224,9 @@ __global__ void __launch_bounds__(128) btk_mvdr_solve_kernel(const double2* __re
   double2* A = reinterpret_cast<double2*>(smem_raw);       // [C][C+1]
   __shared__ int s_piv;
   __shared__ int s_bad;
-  const int s = blockIdx.x, ld = C + 1, tid = threadIdx.x, nt = blockDim.x;
+  __shared__ double s_best[4];
+  __shared__ int s_bidx[4];
+  const int s = blockIdx.x, ld = C + 1, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const double2* d = dvec + (long long)s * C;
   double2* ws = w + (long long)s * C;
   if (s == 0) {   // w[0] = (1, ..., 1), beamformer.cc:2410-2415
@@ -236,15 +244,22 @@ __global__ void __launch_bounds__(128) btk_mvdr_solve_kernel(const double2* __re
   if (tid == 0) s_bad = 0;
   __syncthreads();
   for (int k = 0; k < C; k++) {
+    // partial pivoting: arg max |A[r][k]|^2 over r >= k, one row per thread (C <= 128)
+    double best = -1.0; int bidx = k;
+    if (tid >= k && tid < C) { const double2 v = A[tid * ld + k]; best = v.x * v.x + v.y * v.y; bidx = tid; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = shfl_d(best, lane ^ o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+    }
+    if (lane == 0) { s_best[warp] = best; s_bidx[warp] = bidx; }
+    __syncthreads();
     if (tid == 0) {
-      int piv = k; double best = -1.0;
-      for (int r = k; r < C; r++) {
-        const double2 v = A[r * ld + k];
-        const double a = v.x * v.x + v.y * v.y;
-        if (a > best) { best = a; piv = r; }
-      }
-      s_piv = piv;
-      if (!(best > dThreshold * dThreshold) || !isfinite(best)) s_bad = 1;
+      double bb = s_best[0]; int bi = s_bidx[0];
+      for (int q = 1; q < (nt >> 5); q++) if (s_best[q] > bb || (s_best[q] == bb && s_bidx[q] < bi)) { bb = s_best[q]; bi = s_bidx[q]; }
+      s_piv = bi;
+      if (!(bb > dThreshold * dThreshold) || !isfinite(bb)) s_bad = 1;
     }
     __syncthreads();
     if (s_bad) break;
@@ -255,13 +270,14 @@ __global__ void __launch_bounds__(128) btk_mvdr_solve_kernel(const double2* __re
       }
     }
     __syncthreads();
-    const double2 pv = A[k * ld + k];
+    // row factors f_r = A[r][k] / pivot, once per row (stored in place in column k), then the rank-1 update
+    const double2 inv = zdiv(make_double2(1.0, 0.0), A[k * ld + k]);
+    for (int r = k + 1 + tid; r < C; r += nt) A[r * ld + k] = zmul(A[r * ld + k], inv);
+    __syncthreads();
     const int rows = C - 1 - k, cols = C - k;      // eliminate rows k+1.., columns k+1..C (incl. rhs)
-    // factors are read from column k, which this step does not overwrite
     for (int i = tid; i < rows * cols; i += nt) {
       const int r = k + 1 + i / cols, c = k + 1 + i % cols;
-      const double2 f = zdiv(A[r * ld + k], pv);
-      const double2 t = zmul(f, A[k * ld + c]);
+      const double2 t = zmul(A[r * ld + k], A[k * ld + c]);
       A[r * ld + c].x -= t.x; A[r * ld + c].y -= t.y;
     }
     __syncthreads();
@@ -277,21 +293,36 @@ __global__ void __launch_bounds__(128) btk_mvdr_solve_kernel(const double2* __re
     }
     return;
   }
-  if (tid == 0) {
+  if (warp == 0) {
+    // back substitution, column oriented, inside one warp: lane owns rows lane, lane+32, ... (right-hand sides in
+    // registers); t_r is broadcast with shuffles, no block barrier
+    double2 rhs[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) { const int r = lane + 32 * q; rhs[q] = r < C ? A[r * ld + C] : make_double2(0.0, 0.0); }
     for (int r = C - 1; r >= 0; r--) {
-      double2 acc = A[r * ld + C];
-      for (int c = r + 1; c < C; c++) { const double2 t = zmul(A[r * ld + c], A[c * ld + C]); acc.x -= t.x; acc.y -= t.y; }
-      A[r * ld + C] = zdiv(acc, A[r * ld + r]);           // t_r overwrites the rhs
+      double2 tr = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int q = 0; q < 4; q++) if ((r >> 5) == q && lane == (r & 31)) tr = zdiv(rhs[q], A[r * ld + r]);
+      tr.x = shfl_d(tr.x, r & 31); tr.y = shfl_d(tr.y, r & 31);
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int i = lane + 32 * q;
+        if (i < r) { const double2 t = zmul(A[i * ld + r], tr); rhs[q].x -= t.x; rhs[q].y -= t.y; }
+        if (i == r) rhs[q] = tr;                      // t_r overwrites the rhs
+      }
     }
     double2 lam = make_double2(0.0, 0.0);                  // lam = t^H d  (gsl_blas_zdotc(tmpH, d))
-    for (int c = 0; c < C; c++) {
-      const double2 t = A[c * ld + C];
-      lam.x += t.x * d[c].x + t.y * d[c].y;
-      lam.y += t.x * d[c].y - t.y * d[c].x;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int c = lane + 32 * q;
+      if (c < C) { lam.x += rhs[q].x * d[c].x + rhs[q].y * d[c].y; lam.y += rhs[q].x * d[c].y - rhs[q].y * d[c].x; }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { lam.x += shfl_d(lam.x, lane ^ o); lam.y += shfl_d(lam.y, lane ^ o); }
     const double2 nrm = make_double2(lam.x * C, lam.y * C);
-    for (int c = 0; c < C; c++) ws[c] = zdiv(A[c * ld + C], nrm);
-    fallback[s] = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) { const int c = lane + 32 * q; if (c < C) ws[c] = zdiv(rhs[q], nrm); }
+    if (lane == 0) fallback[s] = 0;
   }
 }
 

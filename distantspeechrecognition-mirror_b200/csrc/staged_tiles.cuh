@@ -22,6 +22,7 @@ struct AnalysisParams {
   const cf* twa;
   const cf* twb;
   int C, Cpad, m, laN;
+  int cg_slices;          // CTAs per work item: slice s takes channel groups s, s + cg_slices, ...
 };
 
 template <int M_, int R_, int MT_, class Ctx>
@@ -38,7 +39,9 @@ BTK_HD void analysis_tile(Ctx& ctx, const AnalysisParams& p, unsigned char* smem
   float* s_xs = reinterpret_cast<float*>(smem + L.xs);
   cf* s_xbuf = reinterpret_cast<cf*>(smem + L.xbuf);
 
-  const WorkItem wk = p.work[work_id];
+  const int slices = p.cg_slices > 0 ? p.cg_slices : 1;
+  const WorkItem wk = p.work[work_id / slices];
+  const int slice = work_id % slices;
   const RecDesc rec = p.recs[wk.rec];
   const float* pcm = p.pcm + rec.pcm_off;
   cf* snap = p.snap + rec.out_off;
@@ -52,7 +55,7 @@ BTK_HD void analysis_tile(Ctx& ctx, const AnalysisParams& p, unsigned char* smem
   for (int it = 0; it < n_it; it++) {
     const int f_base = wk.j0 + it * K::W;          // emitted frame index t; internal frame i = t + laN
     const long long t_lo = (long long)(f_base + p.laN + 1) * K::D - N;
-    for (int cg0 = 0; cg0 < p.Cpad; cg0 += K::CG) {
+    for (int cg0 = slice * K::CG; cg0 < p.Cpad; cg0 += slices * K::CG) {
       stage_window<K>(ctx, L, s_xs, pcm, C, rec.T, t_lo, cg0, vec4, (float4*)0, (const cf*)0);
       ctx.sync();
       for (int round = 0; round < K::CG / K::NG; round++) {

@@ -97,9 +97,10 @@ static int run_analysis(int m, int dct, int C, long long T, const float* pcm, fl
   AnalysisParams p;
   p.pcm = pcm; p.snap = reinterpret_cast<cf*>(snap); p.recs = recs.data(); p.work = work.data();
   p.taps_h = hf.data(); p.twa = twa.data(); p.twb = twb.data(); p.C = C; p.Cpad = Cpad; p.m = m; p.laN = geo.laN;
+  p.cg_slices = Cpad / K::CG > 1 ? 2 : 1;
   const ChainSmem L = chain_smem_layout<M, R>(m);
   std::vector<unsigned char> smem(L.total + 64);
-  for (size_t wi = 0; wi < work.size(); wi++) {
+  for (size_t wi = 0; wi < work.size() * p.cg_slices; wi++) {
     HostCtx<M> ctx(K::NT);
     memset(smem.data(), 0xA5, smem.size());
     analysis_tile<M, R, MT>(ctx, p, smem.data(), (int)wi);
