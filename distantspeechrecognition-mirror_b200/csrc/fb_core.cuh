@@ -188,23 +188,24 @@ template <int M_> struct FFTGeom {
   static BTK_HD int index_of(int gl, int r) { return (gl + L * (r / Ra)) + JA * (r % Ra); }
 };
 
-// Lane-contiguous twiddle tables (built on the host by host_tables.h::build_fft_tables, copied to shared
-// memory by every tile program): a lane reads its pass-A / pass-B twiddles as float4 pairs at immediate
-// offsets instead of indexing a natural-order table.
-//   pass A, owner j = gl + L rep in [0, JA):  twa[j*TA + (ka-1)] = W_M^{j ka}            (two-pass transforms)
-//                                                                  W_M^{(j / Rc) ka Rc}   (three-pass transforms)
-//   pass B, owner iB = gl + L rep in [0, M/Rb): twb[iB*TB + kb]  = W_M^{nc (ka + Ra kb)},  ka = iB / Rc, nc = iB % Rc
-// with W_M = e^{+j 2 pi / M}.  TA (TB) complex words per owner, even with an odd half so that the 16-byte
-// loads of 8 consecutive lanes fall into distinct bank groups.
+// Twiddle seeds (built on the host by host_tables.h::build_fft_tables, copied to shared memory by every tile
+// program).  A lane needs Ra-1 pass-A twiddles and, for the three-pass sizes, V pass-B twiddles per transform; all
+// of them are powers of a few lane constants, so only those seeds are read and the powers are formed in registers
+// with packed complex multiplies (the kernels are bound by shared-memory bandwidth, not by FP32 issue):
+//   pass A, owner j = gl + L rep in [0, JA):   twa[j] = W_M^j (two-pass) or W_M^{(j / Rc) Rc} (three-pass);
+//                                              twiddle of output ka = twa[j]^ka
+//   pass B, lane gl (nc = gl % Rc):            twb[4 gl + 0] = W_M^{nc (gl / Rc)},  [1] = W_M^{nc L / Rc},  [2] = W_M^{nc Ra}
+//                                              twiddle of (rep, kb) = [0] * [1]^rep * [2]^kb  =  W_M^{nc (ka + Ra kb)},
+//                                              ka = (gl + L rep) / Rc
+// with W_M = e^{+j 2 pi / M}.
 template <int M_> struct FFTTables {
   typedef FFTGeom<M_> G;
-  // two-pass transforms read only W_M^j (the powers are formed in registers): one word per owner
-  static constexpr int ta_() { if (G::Rb == 1) return 1; int t = (G::Ra - 1 + 1) & ~1; if (((t / 2) & 1) == 0) t += 2; return t; }
-  static constexpr int TA = ta_();
+  static constexpr int TA = 1;
   static constexpr int TWA_WORDS = G::JA * TA;
-  static constexpr int TB = G::Rb > 1 ? (G::Rb == 2 ? 2 : 6) : 0;
-  static constexpr int TWB_WORDS = G::Rb > 1 ? (G::M / G::Rb) * TB : 0;
+  static constexpr int TB = 4;
+  static constexpr int TWB_WORDS = G::Rb > 1 ? G::L * TB : 0;
   static_assert(G::Rb == 1 || G::Rb == 2 || G::Rb == 4, "pass B radix");
+  static_assert(G::Rb == 1 || G::L % G::Rc == 0, "pass-B owners must keep nc per lane");
 };
 
 // One lane's share of the pass structure.
@@ -222,24 +223,14 @@ template <int M_, int S> struct GroupFFT {
       BTK_UNROLL
       for (int pp = 0; pp < PP; pp++) Dft<G::Ra, S>::run(v + pp * G::V + rep * G::Ra);
       const int j = gl + G::L * rep;
+      // W^{ka} from the seed W = twa[j] by a product tree of depth <= 4.  The packed multiplies are cheaper than the
+      // shared-memory bandwidth a table read would take.
       cf w[G::Ra + 1];
-      if (G::Rb == 1) {
-        // two-pass transforms: W_M^{j ka} from W_M^j by a product tree of depth <= 4.  The packed multiplies are
-        // cheaper than the shared-memory bandwidth a table read would take (the kernel is LDS-bound).
-        w[1] = twa[j * FT::TA];
-        BTK_UNROLL
-        for (int ka = 2; ka < G::Ra; ka++) {
-          const int hi = ka >= 8 ? 8 : (ka >= 4 ? 4 : 2);        // largest power of two <= ka
-          w[ka] = (ka == hi) ? cmul(w[ka / 2], w[ka / 2]) : cmul(w[hi], w[ka - hi]);
-        }
-      } else {
-        const float4* t4 = reinterpret_cast<const float4*>(twa + j * FT::TA);
-        BTK_UNROLL
-        for (int i = 0; i < G::Ra / 2; i++) {
-          const float4 t = t4[i];
-          w[2 * i + 1] = mk(t.x, t.y);
-          w[2 * i + 2] = mk(t.z, t.w);
-        }
+      w[1] = twa[j * FT::TA];
+      BTK_UNROLL
+      for (int ka = 2; ka < G::Ra; ka++) {
+        const int hi = ka >= 8 ? 8 : (ka >= 4 ? 4 : 2);        // largest power of two <= ka
+        w[ka] = (ka == hi) ? cmul(w[ka / 2], w[ka / 2]) : cmul(w[hi], w[ka - hi]);
       }
       BTK_UNROLL
       for (int pp = 0; pp < PP; pp++) {
@@ -259,6 +250,10 @@ template <int M_, int S> struct GroupFFT {
   // hence the split into step2_load / step2_store.
   static BTK_HD void step2_load(cf* v, int gl, const cf* xb, const cf* twb) {
     if (G::Rb > 1) {
+      const float4 s01 = *reinterpret_cast<const float4*>(twb + gl * FT::TB);
+      const cf q = twb[gl * FT::TB + 2];
+      cf a = mk(s01.x, s01.y);                 // W^{nc ka} of the current rep
+      const cf step = mk(s01.z, s01.w);
       BTK_UNROLL
       for (int rep = 0; rep < G::RepB; rep++) {
         const int iB = gl + G::L * rep;
@@ -267,13 +262,13 @@ template <int M_, int S> struct GroupFFT {
         BTK_UNROLL
         for (int nb = 0; nb < G::Rb; nb++) p[nb] = xb[ka * G::S1 + nb * G::Rc + nc];
         Dft<G::Rb, S>::run(p);
-        const float4* t4 = reinterpret_cast<const float4*>(twb + iB * FT::TB);
+        cf t = a;
         BTK_UNROLL
-        for (int i = 0; i < G::Rb / 2; i++) {
-          const float4 t = t4[i];
-          p[2 * i] = multw<S>(p[2 * i], mk(t.x, t.y));
-          p[2 * i + 1] = multw<S>(p[2 * i + 1], mk(t.z, t.w));
+        for (int kb = 0; kb < G::Rb; kb++) {
+          p[kb] = multw<S>(p[kb], t);
+          if (kb + 1 < G::Rb) t = cmul(t, q);
         }
+        if (rep + 1 < G::RepB) a = cmul(a, step);
       }
     }
   }

@@ -44,15 +44,14 @@ inline void build_fft_tables_m(std::vector<cf>& twa, std::vector<cf>& twb) {
     return mk((float)cos(a), (float)sin(a));
   };
   twa.assign(FT::TWA_WORDS > 0 ? FT::TWA_WORDS : 1, mk(1.f, 0.f));
-  for (int j = 0; j < G::JA; j++) {
-    if (G::Rb == 1) { twa[(size_t)j * FT::TA] = W((long long)j); continue; }      // powers are formed in registers
-    for (int ka = 1; ka < G::Ra; ka++) twa[(size_t)j * FT::TA + (ka - 1)] = W((long long)(j / G::Rc) * ka * G::Rc);
-  }
+  for (int j = 0; j < G::JA; j++) twa[(size_t)j * FT::TA] = G::Rb > 1 ? W((long long)(j / G::Rc) * G::Rc) : W((long long)j);
   twb.assign(FT::TWB_WORDS > 0 ? FT::TWB_WORDS : 1, mk(1.f, 0.f));
   if (G::Rb > 1)
-    for (int iB = 0; iB < M_ / G::Rb; iB++) {
-      const int ka = iB / G::Rc, nc = iB % G::Rc;
-      for (int kb = 0; kb < G::Rb; kb++) twb[(size_t)iB * FT::TB + kb] = W((long long)nc * (ka + G::Ra * kb));
+    for (int gl = 0; gl < G::L; gl++) {
+      const int nc = gl % G::Rc;
+      twb[(size_t)gl * FT::TB + 0] = W((long long)nc * (gl / G::Rc));
+      twb[(size_t)gl * FT::TB + 1] = W((long long)nc * (G::L / G::Rc));
+      twb[(size_t)gl * FT::TB + 2] = W((long long)nc * G::Ra);
     }
 }
 inline bool build_fft_tables(int M, std::vector<cf>& twa, std::vector<cf>& twb) {
