@@ -72,7 +72,7 @@ struct ChainCfg {
   // would not fit 227 KB of shared memory at all (M = 1024).  Two independent CTAs per SM matter more than a
   // longer window: one CTA's staging (global-load latency) overlaps the other's transforms.  (M = 512 with 4 warps
   // and two CTAs measured 11-38 % slower than 8 warps and one CTA: the window halo doubles; tools/ab_run2.sh.)
-  static constexpr int NW = (M_ >= 1024 || PP_ == 2) ? 4 : 8;
+  static constexpr int NW = (M_ >= 1024 || (PP_ == 2 && M_ <= 256)) ? 4 : 8;
   static constexpr int NT = NW * 32;
   static constexpr int FW = 2 * PP_;           // frames per warp per iteration
   static constexpr int LV = (FW % 4 == 0) ? 4 : 2;   // floats per shared-memory access of the staged window (a warp's

@@ -28,8 +28,11 @@ template <int M, int R, int MT, int PP> struct KernCfg {
 
 // Frame pairs per warp of the fused chain: two (one 8-warp CTA per SM, up to 255 registers per thread, taps /
 // samples / weights / twiddles loaded once for four frames) whenever the larger window fits shared memory.
+#ifndef BTK_PP_MAX_M
+#define BTK_PP_MAX_M 256   // M = 512 with two pairs per warp measured equal (16 ch) or 44 % slower (64 ch): tools/ab_run2.sh
+#endif
 template <int M, int R> static int chain_pp(int m) {
-  return (M <= 256 && chain_smem_layout<M, R, 2>(m).total <= BTK_MAX_SMEM) ? 2 : 1;
+  return (M <= BTK_PP_MAX_M && chain_smem_layout<M, R, 2>(m).total <= BTK_MAX_SMEM) ? 2 : 1;
 }
 
 template <int M, int R, int MT, int PP>
@@ -68,8 +71,8 @@ template <int M, int R, int MT> struct FastOk { static constexpr bool value = MT
 
 template <int M, int R>
 static cudaError_t launch_chain_r(const ChainParams& p, int n_work, cudaStream_t st) {
-  if (M <= 256 && chain_pp<M, R>(p.m) == 2) {
-    constexpr int PP = M <= 256 ? 2 : 1;     // (never instantiated with 2 for the large transforms)
+  if (M <= BTK_PP_MAX_M && chain_pp<M, R>(p.m) == 2) {
+    constexpr int PP = M <= BTK_PP_MAX_M ? 2 : 1;     // (never instantiated with 2 for the largest transforms)
     if (p.m == 2 && FastOk<M, R, 2>::value) return launch_one<M, R, PP>(btk_chain_kernel<M, R, BTK_MT(2), PP>, p, p.m, n_work, st);
     if (p.m == 4 && FastOk<M, R, 4>::value) return launch_one<M, R, PP>(btk_chain_kernel<M, R, BTK_MT(4), PP>, p, p.m, n_work, st);
     return launch_one<M, R, PP>(btk_chain_kernel<M, R, 0, PP>, p, p.m, n_work, st);
