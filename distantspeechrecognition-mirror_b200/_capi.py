@@ -19,7 +19,7 @@ OK, EINVAL, ESTATE, ECUDA, ENOMEM, EUNSUPPORTED = 0, 1, 2, 3, 4, 5
 # every symbol include/btkb200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
     "btkb200_device_count", "btkb200_version", "btkb200_last_error", "btkb200_plan_create", "btkb200_plan_destroy",
-    "btkb200_plan_info", "btkb200_nblk", "btkb200_analysis_frames", "btkb200_synthesis_frames",
+    "btkb200_plan_info", "btkb200_nblk", "btkb200_analysis_frames", "btkb200_synthesis_frames", "btkb200_chain_frames",
     "btkb200_set_ds_weights", "btkb200_set_weights", "btkb200_get_weights", "btkb200_get_manifold",
     "btkb200_set_covariance", "btkb200_get_covariance", "btkb200_set_diffuse_noise_model", "btkb200_diag_load",
     "btkb200_diag_load_bin", "btkb200_divide_nondiagonal", "btkb200_solve_mvdr", "btkb200_analysis",
@@ -66,7 +66,7 @@ def lib() -> ctypes.CDLL:
     L.btkb200_plan_destroy.restype = None
     L.btkb200_plan_destroy.argtypes = [vp]
     L.btkb200_plan_info.argtypes = [vp, POINTER(Info)]
-    for f in ("btkb200_nblk", "btkb200_analysis_frames", "btkb200_synthesis_frames"):
+    for f in ("btkb200_nblk", "btkb200_analysis_frames", "btkb200_synthesis_frames", "btkb200_chain_frames"):
         getattr(L, f).restype = c_long
         getattr(L, f).argtypes = [vp, c_long]
     L.btkb200_set_ds_weights.argtypes = [vp, c_double, vp, c_uint]
@@ -149,6 +149,9 @@ class Plan:
     # -- geometry
     def nblk(self, T: int) -> int:
         return int(self._L.btkb200_nblk(self._h, T))
+
+    def chain_frames(self, T: int) -> int:
+        return int(self._L.btkb200_chain_frames(self._h, T))
 
     def analysis_frames(self, T: int) -> int:
         return int(self._L.btkb200_analysis_frames(self._h, T))
@@ -271,13 +274,13 @@ class Plan:
             x = x[:, None]
         if x.shape[1] != self.C:
             raise BtkError(EINVAL, f"pcm has {x.shape[1]} channels, plan has {self.C}")
-        out = np.empty(self.nblk(x.shape[0]) * self.D, dtype=np.float32)
+        out = np.empty(self.chain_frames(x.shape[0]) * self.D, dtype=np.float32)
         self._ck(self._L.btkb200_chain(self._h, _p(x), x.shape[0], _p(out)))
         return out
 
     def chain_batch(self, pcms) -> list:
         xs = [np.ascontiguousarray(x, dtype=np.float32) for x in pcms]
-        outs = [np.empty(self.nblk(x.shape[0]) * self.D, dtype=np.float32) for x in xs]
+        outs = [np.empty(self.chain_frames(x.shape[0]) * self.D, dtype=np.float32) for x in xs]
         self.chain_batch_into(xs, outs)
         return outs
 

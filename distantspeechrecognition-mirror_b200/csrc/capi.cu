@@ -215,6 +215,7 @@ int btkb200_plan_info(const btkb200_plan* p, btkb200_info* info) {
 long btkb200_nblk(const btkb200_plan* p, long T) { return p ? p->geo.nblk(T) : -1; }
 long btkb200_analysis_frames(const btkb200_plan* p, long T) { return p ? p->geo.analysis_frames(T) : -1; }
 long btkb200_synthesis_frames(const btkb200_plan* p, long F) { return p ? p->geo.synthesis_frames((int)F) : -1; }
+long btkb200_chain_frames(const btkb200_plan* p, long T) { return p ? p->geo.chain_frames(T) : -1; }
 
 // ------------------------------------------------------------------------------------------- weights
 int btkb200_set_ds_weights(btkb200_plan* p, double fs, const double* delays, unsigned n) {
@@ -433,7 +434,7 @@ static int chain_prepare(btkb200_plan* p, const long long* pcm_off, const long l
   long long total = 0;
   for (int i = 0; i < n; i++) {
     if (T[i] < 0 || T[i] > 0x7ffffff0LL) return fail(p, BTKB200_EINVAL, "recording %d: bad length %lld", i, T[i]);
-    recs[i].pcm_off = pcm_off[i]; recs[i].out_off = out_off[i]; recs[i].T = (int)T[i]; recs[i].nblk = p->geo.nblk(T[i]);
+    recs[i].pcm_off = pcm_off[i]; recs[i].out_off = out_off[i]; recs[i].T = (int)T[i]; recs[i].nblk = p->geo.chain_frames(T[i]);
     total += recs[i].nblk;
   }
   std::vector<WorkItem> work;
@@ -603,7 +604,7 @@ int btkb200_chain_batch(btkb200_plan* p, const float* const* pcm, const long* T,
     if (T[i] < 0 || !pcm[i] || !out[i]) return fail(p, BTKB200_EINVAL, "recording %d: bad buffer or length", i);
     poff[i] = pin; ooff[i] = pout; Tl[i] = T[i];
     pin += ((long long)T[i] * p->C + 3) / 4 * 4;            // keep every recording 16-byte aligned for float4 loads
-    pout += ((long long)p->geo.nblk(T[i]) * p->geo.D + 3) / 4 * 4;
+    pout += ((long long)p->geo.chain_frames(T[i]) * p->geo.D + 3) / 4 * 4;
   }
   CK(p, p->d_in.reserve((size_t)(pin ? pin : 4) * sizeof(float)));
   CK(p, p->d_out.reserve((size_t)(pout ? pout : 4) * sizeof(float)));
@@ -633,7 +634,7 @@ int btkb200_chain_batch(btkb200_plan* p, const float* const* pcm, const long* T,
     CK(p, cudaEventRecord(p->ev_k[g], p->stream));
     CK(p, cudaStreamWaitEvent(p->s_out, p->ev_k[g], 0));
     for (int i = r0; i < r1; i++) {
-      const size_t b = (size_t)p->geo.nblk(T[i]) * p->geo.D * sizeof(float);
+      const size_t b = (size_t)p->geo.chain_frames(T[i]) * p->geo.D * sizeof(float);
       if (b) CK(p, cudaMemcpyAsync(out[i], (float*)p->d_out.p + ooff[i], b, cudaMemcpyDeviceToHost, p->s_out));
     }
     r0 = r1;

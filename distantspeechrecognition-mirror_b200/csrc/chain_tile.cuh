@@ -435,9 +435,18 @@ BTK_HD void synth_emit(Ctx& ctx, const ChainSmem& L, const float* taps_g, const 
 template <class K, class Ctx>
 BTK_HD void synth_roll_history(Ctx& ctx, const ChainSmem& L, float* s_vhist, const float* s_vcur) {
   typedef ChainThreadState<K::M, K::PP> TS;
-  ctx.par([&](int tid, TS&) {
-    for (int i = tid; i < L.H * K::M; i += K::NT) s_vhist[i] = s_vcur[(K::W - L.H) * K::M + i];
-  });
+  // History frame f (f in [-H, 0)) of the next iteration is frame f + W of this one.  With H <= W that is always a
+  // current frame (one pass).  With H > W (long prototypes at high decimation: m R - 1 > W) the older part comes
+  // from the history itself, shifted down by W frames: copied in ascending slices of W frames with a barrier
+  // between slices, so that a slice never reads what the same pass writes.
+  const int HM = L.H * K::M, WM = K::W * K::M;
+  for (int base = 0; base < HM; base += WM) {
+    ctx.par([&](int tid, TS&) {
+      const int hi = base + WM < HM ? base + WM : HM;
+      for (int i = base + tid; i < hi; i += K::NT) s_vhist[i] = i + WM < HM ? s_vhist[i + WM] : s_vcur[i + WM - HM];
+    });
+    if (base + WM < HM) ctx.sync();
+  }
 }
 
 // One analysis round of a warp: polyphase of the staged channel + backward transforms, leaving

@@ -32,6 +32,9 @@ struct BankGeom {
   int analysis_frames(long long T) const { return nblk(T) + pd_a - laN; }
   // modulated.cc:626-642: pd_s frames consumed by priming, then one output per input frame
   int synthesis_frames(int F) const { return F > pd_s ? F - pd_s : 0; }
+  // output frames of analysis -> beamformer -> synthesis: nblk, except for delayCompensationType 2 with an odd
+  // m R, where pd_a - laN - pd_s = 1 and the reference chain emits one more (all-padding) frame
+  int chain_frames(long long T) const { return synthesis_frames(analysis_frames(T)); }
 };
 
 // Lane-contiguous twiddle tables of the M-point transform (layout: fb_core.cuh, FFTTables).

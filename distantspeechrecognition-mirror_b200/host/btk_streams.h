@@ -511,7 +511,7 @@ class OverSampledDFTSynthesisBank : public OverSampledDFTFilterBank, public Vect
       check(btkb200_set_weights(_plan.get(), &w[0]), _plan.get());
       std::vector<float> pcm; long T;
       bf->interleaved_pcm(pcm, T);
-      const long nblk = btkb200_nblk(_plan.get(), T);
+      const long nblk = btkb200_chain_frames(_plan.get(), T);
       _out.assign((size_t)nblk * _D + 1, 0.f);
       float dummy = 0.f;
       check(btkb200_chain(_plan.get(), pcm.empty() ? &dummy : &pcm[0], T, &_out[0]), _plan.get());

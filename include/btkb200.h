@@ -63,6 +63,9 @@ long btkb200_nblk(const btkb200_plan* plan, long T);
 long btkb200_analysis_frames(const btkb200_plan* plan, long T);
 /* F - pd_s (modulated.cc:626-642). */
 long btkb200_synthesis_frames(const btkb200_plan* plan, long F);
+/* Output frames of the whole chain = synthesis_frames(analysis_frames(T)): nblk(T), or nblk(T)+1 for
+ * delayCompensationType 2 with an odd m*R (modulated.cc:278-296: pd - laN - pd_synthesis = 1 there). */
+long btkb200_chain_frames(const btkb200_plan* plan, long T);
 
 /* ---- weights ------------------------------------------------------------------------------------------ */
 /* SubbandDS::calcArrayManifoldVectors -> beamformerWeights::calcMainlobe, halfBandShift=false
@@ -120,7 +123,7 @@ int btkb200_estimate_covariance(btkb200_plan* plan, const float* pcm, long T, do
                                 int conjugate);
 
 /* ---- fused path ---------------------------------------------------------------------------------------- */
-/* pcm -> out through analysis -> weight apply -> synthesis in ONE kernel; out holds nblk(T)*D floats.
+/* pcm -> out through analysis -> weight apply -> synthesis in ONE kernel; out holds chain_frames(T)*D floats.
  * ESTATE if no weights are installed (j_error, beamformer.cc:1140-1143). */
 int btkb200_chain(btkb200_plan* plan, const float* pcm, long T, float* out);
 /* n independent recordings (ragged lengths allowed), host buffers. */

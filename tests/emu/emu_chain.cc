@@ -11,7 +11,9 @@
 
 using namespace btk;
 
+#ifndef BTK_EMU_CASES
 #define BTK_EMU_CASES(X) X(64, 1) X(64, 8) X(64, 2) X(128, 2) X(128, 4) X(256, 1) X(256, 2) X(256, 4) X(512, 2) X(512, 4) X(512, 8) X(1024, 2) X(1024, 4)
+#endif
 
 template <int M, int PP = 1> struct HostCtx {
   std::vector<ChainThreadState<M, PP> > ts;
@@ -41,7 +43,7 @@ static int run_chain(int m, int dct, int C, int n_rec, const long long* Ts, cons
   build_chain_weight_table(w.data(), M, C, Cpad, gam);
   std::vector<RecDesc> recs(n_rec);
   for (int r = 0; r < n_rec; r++) {
-    recs[r].pcm_off = pcm_off[r]; recs[r].out_off = out_off[r]; recs[r].T = (int)Ts[r]; recs[r].nblk = geo.nblk(Ts[r]);
+    recs[r].pcm_off = pcm_off[r]; recs[r].out_off = out_off[r]; recs[r].T = (int)Ts[r]; recs[r].nblk = geo.chain_frames(Ts[r]);
   }
   std::vector<WorkItem> work;
   build_work(recs, chunk, work);
