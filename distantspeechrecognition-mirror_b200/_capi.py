@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BTKB200_LIB") or os.path.join(_HERE, "libbtkb200.so")   # override: A/B builds while tuning
 
 OK, EINVAL, ESTATE, ECUDA, ENOMEM, EUNSUPPORTED = 0, 1, 2, 3, 4, 5
+PCM_F32, PCM_S16, PCM_S24BE = 0, 1, 2      # raw PCM formats of chain_batch_pcm / convert_pcm (include/btkb200.h)
 
 # every symbol include/btkb200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
@@ -24,7 +25,7 @@ SYMBOLS = [
     "btkb200_set_covariance", "btkb200_get_covariance", "btkb200_set_diffuse_noise_model", "btkb200_diag_load",
     "btkb200_diag_load_bin", "btkb200_divide_nondiagonal", "btkb200_solve_mvdr", "btkb200_analysis",
     "btkb200_beamform", "btkb200_synthesis", "btkb200_covariance", "btkb200_estimate_covariance", "btkb200_chain",
-    "btkb200_chain_batch",
+    "btkb200_chain_batch", "btkb200_chain_batch_pcm", "btkb200_convert_pcm",
     "btkb200_chain_batch_multi", "btkb200_chain_batch_dev", "btkb200_analysis_dev", "btkb200_beamform_dev",
     "btkb200_synthesis_dev", "btkb200_launch_count", "btkb200_sync", "btkb200_host_alloc", "btkb200_host_free",
 ]
@@ -87,6 +88,8 @@ def lib() -> ctypes.CDLL:
     L.btkb200_estimate_covariance.argtypes = [vp, vp, c_long, c_double, c_long, c_int]
     L.btkb200_chain.argtypes = [vp, vp, c_long, vp]
     L.btkb200_chain_batch.argtypes = [vp, POINTER(vp), POINTER(c_long), c_int, POINTER(vp)]
+    L.btkb200_chain_batch_pcm.argtypes = [vp, POINTER(vp), c_int, POINTER(c_long), c_int, POINTER(vp)]
+    L.btkb200_convert_pcm.argtypes = [vp, vp, c_int, c_long, vp]
     L.btkb200_chain_batch_multi.argtypes = [POINTER(vp), c_int, POINTER(vp), POINTER(c_long), c_int, POINTER(vp)]
     L.btkb200_chain_batch_dev.argtypes = [vp, vp, POINTER(c_longlong), POINTER(c_longlong), POINTER(c_longlong), c_int,
                                           vp, vp]
@@ -291,6 +294,34 @@ class Plan:
         oo = (c_void_p * n)(*[o.ctypes.data for o in outs])
         TT = (c_long * n)(*[x.shape[0] for x in xs])
         self._ck(self._L.btkb200_chain_batch(self._h, pp, TT, n, oo))
+
+    def chain_batch_pcm_into(self, raws, fmt: int, Ts, outs):
+        """raws: C-contiguous arrays of raw interleaved PCM -- float32 [T][C] (PCM_F32), int16 [T][C] (PCM_S16) or
+        uint8 [T][C][3] big-endian 24-bit (PCM_S24BE); Ts: samples per channel; outs preallocated float32."""
+        n = len(raws)
+        pp = (c_void_p * n)(*[x.ctypes.data for x in raws])
+        oo = (c_void_p * n)(*[o.ctypes.data for o in outs])
+        TT = (c_long * n)(*[int(t) for t in Ts])
+        self._ck(self._L.btkb200_chain_batch_pcm(self._h, pp, fmt, TT, n, oo))
+
+    def chain_batch_pcm(self, raws, fmt: int) -> list:
+        want = {PCM_F32: np.float32, PCM_S16: np.int16, PCM_S24BE: np.uint8}[fmt]
+        xs = [np.ascontiguousarray(x, dtype=want) for x in raws]
+        for x in xs:
+            if x.ndim < 2 or x.shape[1] != self.C or (fmt == PCM_S24BE and (x.ndim != 3 or x.shape[2] != 3)):
+                raise BtkError(EINVAL, f"raw pcm of shape {x.shape} does not match {self.C} channels / format {fmt}")
+        outs = [np.empty(self.chain_frames(x.shape[0]) * self.D, dtype=np.float32) for x in xs]
+        self.chain_batch_pcm_into(xs, fmt, [x.shape[0] for x in xs], outs)
+        return outs
+
+    def convert_pcm(self, raw, fmt: int) -> np.ndarray:
+        """The ingest conversion alone (through the device): raw samples -> float32, same order."""
+        want = {PCM_F32: np.float32, PCM_S16: np.int16, PCM_S24BE: np.uint8}[fmt]
+        x = np.ascontiguousarray(raw, dtype=want)
+        n = x.size // 3 if fmt == PCM_S24BE else x.size
+        out = np.empty(n, dtype=np.float32)
+        self._ck(self._L.btkb200_convert_pcm(self._h, _p(x), fmt, n, _p(out)))
+        return out.reshape(x.shape[:-1] if fmt == PCM_S24BE else x.shape)
 
     # -- device-resident variants (raw device pointers as ints, e.g. torch.Tensor.data_ptr())
     def chain_batch_dev(self, d_pcm: int, pcm_off, T, out_off, d_out: int, stream: int = 0):

@@ -59,7 +59,7 @@ struct btkb200_plan {
   cf* d_wts_chain = nullptr;   // [Cpad][M]
   cf* d_w = nullptr;           // [B][C]
   // scratch
-  DevBuf d_recs, d_work, d_in, d_out, d_aux, d_aux2;
+  DevBuf d_recs, d_work, d_in, d_out, d_aux, d_aux2, d_raw;
   PinBuf h_desc;
   std::vector<long long> sig;  // signature of the cached chain work list
   int cached_n_work = 0;
@@ -193,7 +193,7 @@ void btkb200_plan_destroy(btkb200_plan* p) {
   cudaSetDevice(p->device);
   if (p->stream) cudaStreamSynchronize(p->stream);
   cudaFree(p->d_taps_h); cudaFree(p->d_taps_g); cudaFree(p->d_twa); cudaFree(p->d_twb); cudaFree(p->d_wts_chain); cudaFree(p->d_w);
-  p->d_recs.release(); p->d_work.release(); p->d_in.release(); p->d_out.release(); p->d_aux.release(); p->d_aux2.release();
+  p->d_recs.release(); p->d_work.release(); p->d_in.release(); p->d_out.release(); p->d_aux.release(); p->d_aux2.release(); p->d_raw.release();
   p->h_desc.release();
   if (p->stream) cudaStreamDestroy(p->stream);
   if (p->s_in) cudaStreamDestroy(p->s_in);
@@ -592,8 +592,38 @@ int btkb200_estimate_covariance(btkb200_plan* p, const float* pcm, long T, doubl
   return BTKB200_OK;
 }
 
+static int pcm_bytes_per_sample(int format) {
+  return format == BTKB200_PCM_F32 ? 4 : format == BTKB200_PCM_S16 ? 2 : format == BTKB200_PCM_S24BE ? 3 : 0;
+}
+
+int btkb200_convert_pcm(btkb200_plan* p, const void* src, int format, long n, float* dst) {
+  if (!p || !src || !dst || n < 0) return BTKB200_EINVAL;
+  const int bpe = pcm_bytes_per_sample(format);
+  if (!bpe) return fail(p, BTKB200_EINVAL, "unknown PCM format %d", format);
+  if (n == 0) return BTKB200_OK;
+  CK(p, cudaSetDevice(p->device));
+  CK(p, p->d_in.reserve((size_t)n * sizeof(float)));
+  if (format == BTKB200_PCM_F32) {
+    CK(p, cudaMemcpyAsync(p->d_in.p, src, (size_t)n * 4, cudaMemcpyHostToDevice, p->stream));
+  } else {
+    CK(p, p->d_raw.reserve((size_t)n * bpe + 16));
+    CK(p, cudaMemcpyAsync(p->d_raw.p, src, (size_t)n * bpe, cudaMemcpyHostToDevice, p->stream));
+    CK(p, launch_ingest(format, p->d_raw.p, (float*)p->d_in.p, n, p->stream));
+    p->launches++;
+  }
+  CK(p, cudaMemcpyAsync(dst, p->d_in.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+  CK(p, cudaStreamSynchronize(p->stream));
+  return BTKB200_OK;
+}
+
 int btkb200_chain_batch(btkb200_plan* p, const float* const* pcm, const long* T, int n, float* const* out) {
+  return btkb200_chain_batch_pcm(p, (const void* const*)pcm, BTKB200_PCM_F32, T, n, out);
+}
+
+int btkb200_chain_batch_pcm(btkb200_plan* p, const void* const* pcm, int format, const long* T, int n, float* const* out) {
   if (!p || !pcm || !T || !out || n < 0) return BTKB200_EINVAL;
+  const int bpe = pcm_bytes_per_sample(format);
+  if (!bpe) return fail(p, BTKB200_EINVAL, "unknown PCM format %d", format);
   if (!p->has_weights) return fail(p, BTKB200_ESTATE, "call calcArrayManifoldVectorsX() once");
   if (!p->has_h || !p->has_g) return fail(p, BTKB200_ESTATE, "the fused chain needs both prototypes");
   if (n == 0) return BTKB200_OK;
@@ -608,6 +638,7 @@ int btkb200_chain_batch(btkb200_plan* p, const float* const* pcm, const long* T,
   }
   CK(p, p->d_in.reserve((size_t)(pin ? pin : 4) * sizeof(float)));
   CK(p, p->d_out.reserve((size_t)(pout ? pout : 4) * sizeof(float)));
+  if (format != BTKB200_PCM_F32) CK(p, p->d_raw.reserve((size_t)(pin ? pin : 4) * bpe + 16));
   if (!p->s_in) CK(p, cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
   if (!p->s_out) CK(p, cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
   int rc = chain_prepare(p, poff.data(), Tl.data(), ooff.data(), n, p->stream);
@@ -624,11 +655,19 @@ int btkb200_chain_batch(btkb200_plan* p, const float* const* pcm, const long* T,
     int r1 = r0;
     while (r1 < n && (r1 == r0 || poff[r1] < want)) r1++;
     if (g == G - 1) r1 = n;
+    // raw formats land in d_raw at the same ELEMENT offsets (multiples of 4 elements: 8- / 12-byte aligned) and are
+    // converted to float32 in d_in by one element-wise kernel per group, ahead of the group's chain launch
+    char* dst_base = format == BTKB200_PCM_F32 ? (char*)p->d_in.p : (char*)p->d_raw.p;
     for (int i = r0; i < r1; i++)
       if (T[i] > 0)
-        CK(p, cudaMemcpyAsync((float*)p->d_in.p + poff[i], pcm[i], (size_t)T[i] * p->C * sizeof(float), cudaMemcpyHostToDevice, p->s_in));
+        CK(p, cudaMemcpyAsync(dst_base + (size_t)poff[i] * bpe, pcm[i], (size_t)T[i] * p->C * bpe, cudaMemcpyHostToDevice, p->s_in));
     CK(p, cudaEventRecord(p->ev_in[g], p->s_in));
     CK(p, cudaStreamWaitEvent(p->stream, p->ev_in[g], 0));
+    if (format != BTKB200_PCM_F32) {
+      const long long e0 = poff[r0], e1 = r1 < n ? poff[r1] : pin;
+      CK(p, launch_ingest(format, (const char*)p->d_raw.p + (size_t)e0 * bpe, (float*)p->d_in.p + e0, e1 - e0, p->stream));
+      p->launches++;
+    }
     rc = chain_launch(p, (const float*)p->d_in.p, (float*)p->d_out.p, p->rec_work_begin[r0], p->rec_work_begin[r1], p->stream);
     if (rc) return rc;
     CK(p, cudaEventRecord(p->ev_k[g], p->stream));

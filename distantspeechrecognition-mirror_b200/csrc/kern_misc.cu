@@ -88,6 +88,53 @@ cudaError_t launch_beamform(const cf* snap, const cf* w, cf* Y, long long F, int
 }
 
 // ---------------------------------------------------------------------------------------------
+// Ingest: raw interleaved PCM -> float32 (same [T][C] order).  HBM-bound element-wise converts; four samples per
+// thread per step (8- or 12-byte loads, one 16-byte store).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) btk_ingest_s16_kernel(const short* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long n4 = n >> 2, stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const short4 v = reinterpret_cast<const short4*>(src)[i];
+    reinterpret_cast<float4*>(dst)[i] = make_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) dst[(n4 << 2) + threadIdx.x] = (float)src[(n4 << 2) + threadIdx.x];
+}
+
+__device__ __forceinline__ float s24be(unsigned b0, unsigned b1, unsigned b2) {   // b0 = most significant byte
+  return (float)((int)((b0 << 24) | (b1 << 16) | (b2 << 8)) >> 8);
+}
+
+__global__ void __launch_bounds__(256) btk_ingest_s24be_kernel(const unsigned char* __restrict__ src, float* __restrict__ dst,
+                                                              long long n) {
+  const long long n4 = n >> 2, stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const unsigned* p = reinterpret_cast<const unsigned*>(src) + 3 * i;      // 12 bytes = 4 samples
+    const unsigned w0 = p[0], w1 = p[1], w2 = p[2];                          // little-endian words of the byte stream
+    float4 o;
+    o.x = s24be(w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u);
+    o.y = s24be(w0 >> 24, w1 & 255u, (w1 >> 8) & 255u);
+    o.z = s24be((w1 >> 16) & 255u, w1 >> 24, w2 & 255u);
+    o.w = s24be((w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24);
+    reinterpret_cast<float4*>(dst)[i] = o;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const unsigned char* q = src + 3 * ((n4 << 2) + threadIdx.x);
+    dst[(n4 << 2) + threadIdx.x] = s24be(q[0], q[1], q[2]);
+  }
+}
+
+cudaError_t launch_ingest(int fmt, const void* src, float* dst, long long n, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  long long blocks = ((n >> 2) + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (fmt == 1) btk_ingest_s16_kernel<<<(int)blocks, 256, 0, st>>>((const short*)src, dst, n);
+  else if (fmt == 2) btk_ingest_s24be_kernel<<<(int)blocks, 256, 0, st>>>((const unsigned char*)src, dst, n);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // Weighted Gram matrices R[s] = sum_f wt[f] x_f x_f^H (conj) or x_f x_f^T, register-tiled outer products.
 // grid = (B bins, SPLIT frame slices).  A CTA stages 32 frames of its bin in shared memory twice -- x and
 // wt*conj(x) -- and every thread owns one TILE x TILE block of the upper triangle (both flavours are symmetric

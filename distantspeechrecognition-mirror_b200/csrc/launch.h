@@ -26,4 +26,11 @@ cudaError_t launch_covariance(const cf* snap, const double* wt, double2* Rout, l
 cudaError_t launch_mvdr_solve(const double2* Rn, const double2* d, double2* w, int* fallback, int B, int C,
                               double dThreshold, cudaStream_t st);
 
+// Raw PCM -> float32, element for element (bit-exact integer -> float):
+//   fmt 1: int16 little endian (what sf_readf_float returns with SFC_SET_NORM_FLOAT off, feature/feature.cc:273, 868-896)
+//   fmt 2: packed 24-bit big endian, sign extended (Conversion24bit2Float::next, feature/feature.cc:190-217;
+//          the Mark-III / Mark-IV frame payload, driver/mk4_common.h:50-54)
+// src must be 8-byte (fmt 1) / 4-byte (fmt 2) aligned, dst 16-byte aligned.
+cudaError_t launch_ingest(int fmt, const void* src, float* dst, long long n, cudaStream_t st);
+
 }  // namespace btk

@@ -128,6 +128,20 @@ int btkb200_estimate_covariance(btkb200_plan* plan, const float* pcm, long T, do
 int btkb200_chain(btkb200_plan* plan, const float* pcm, long T, float* out);
 /* n independent recordings (ragged lengths allowed), host buffers. */
 int btkb200_chain_batch(btkb200_plan* plan, const float* const* pcm, const long* T, int n, float* const* out);
+/* Same with raw interleaved PCM in host memory, converted on the device (element order unchanged, exact):
+ *   BTKB200_PCM_F32   float32                           (IterativeSampleFeature buffer, feature/feature.cc:868-896)
+ *   BTKB200_PCM_S16   int16 little endian               (16-bit WAV payload: what sf_readf_float delivers with
+ *                                                        SFC_SET_NORM_FLOAT off, feature/feature.cc:273)
+ *   BTKB200_PCM_S24BE packed 24-bit big endian, signed  (Conversion24bit2Float::next, feature/feature.cc:190-217;
+ *                                                        Mark-III/IV data frames: 64 ch x 3 bytes, driver/mk4_common.h:50-54)
+ * Halves (or cuts by a quarter) the host->device bytes of the end-to-end path, which is PCIe-bound. */
+#define BTKB200_PCM_F32 0
+#define BTKB200_PCM_S16 1
+#define BTKB200_PCM_S24BE 2
+int btkb200_chain_batch_pcm(btkb200_plan* plan, const void* const* pcm, int format, const long* T, int n,
+                            float* const* out);
+/* The conversion alone: n raw samples (host) -> n floats (host), through the device kernels. */
+int btkb200_convert_pcm(btkb200_plan* plan, const void* src, int format, long n, float* dst);
 /* Same, recordings spread round-robin over n_plans plans living on different devices (no inter-GPU traffic). */
 int btkb200_chain_batch_multi(btkb200_plan* const* plans, int n_plans, const float* const* pcm, const long* T, int n,
                               float* const* out);

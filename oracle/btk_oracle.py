@@ -378,6 +378,22 @@ class CompiledReference:
 
 
 # --------------------------------------------------------------------------- metrics
+def ingest_s16(raw: np.ndarray) -> np.ndarray:
+    """16-bit PCM -> float32 without normalisation: what sf_readf_float hands IterativeSampleFeature when
+    SFC_SET_NORM_FLOAT is off (feature/feature.cc:273, 849, 868-896).  Same element order."""
+    return np.asarray(raw, dtype=np.int16).astype(np.float32)
+
+
+def ingest_s24be(raw: np.ndarray) -> np.ndarray:
+    """Packed big-endian 24-bit -> float32, a loop restatement of Conversion24bit2Float::next
+    (feature/feature.cc:190-217): byte 0 is the most significant one and carries the sign; Mark-III/IV data
+    frames are 64 channels x 3 bytes (driver/mk4_common.h:50-54).  raw: uint8 [..., 3]."""
+    b = np.asarray(raw, dtype=np.uint8).astype(np.int64)
+    v = (b[..., 0] << 16) | (b[..., 1] << 8) | b[..., 2]
+    v = np.where(b[..., 0] & 128, v - (1 << 24), v)
+    return v.astype(np.float32)
+
+
 def rel_l2(a: np.ndarray, b: np.ndarray) -> float:
     """||a - b||_2 / ||b||_2 (b is the reference)."""
     a = np.asarray(a)
