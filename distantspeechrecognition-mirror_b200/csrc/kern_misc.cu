@@ -1,5 +1,7 @@
 // kern_misc.cu -- per-M dispatch glue + the subband-domain kernels that are not filter banks:
 // weight apply on stored snapshots, weighted spatial covariance accumulation, per-bin MVDR solve.
+#include <stdlib.h>
+
 #include "launch.h"
 
 namespace btk {
@@ -233,6 +235,11 @@ cudaError_t launch_covariance(const cf* snap, const double* wt, double2* Rout, l
                               cudaStream_t st) {
   if (C > 64) return cudaErrorInvalidValue;
   if (F == 0) return cudaSuccess;
+  // The per-bin contraction (2C x 2C x F over the reals) runs on the tensor cores (kern_cov_tc.cu; bins are packed
+  // side by side into the 128 x 128 tcgen05 tile when C < 64).  BTK_COV_SIMT=1 selects the register-tiled SIMT kernel
+  // below instead (A/B measurements, tests of both paths).
+  static const bool force_simt = getenv("BTK_COV_SIMT") && getenv("BTK_COV_SIMT")[0] == '1';
+  if (!force_simt) return launch_covariance_tc(snap, wt, Rout, F, B, C, conj, st);
   int split = (int)((F + 511) / 512);
   if (split < 1) split = 1;
   if (split > 64) split = 64;

@@ -22,6 +22,9 @@ cudaError_t launch_beamform(const cf* snap, const cf* w, cf* Y, long long F, int
 // R[s] += sum_f wt[f] x x^H (conj) or x x^T     (beamformer.cc:142-163 / subbandBeamforming.py:1170-1175)
 cudaError_t launch_covariance(const cf* snap, const double* wt, double2* Rout, long long F, int B, int C, int conj,
                               cudaStream_t st);
+// the same contraction on tcgen05 tensor cores (TF32 hi/lo split inputs, FP32 accumulation in TMEM): kern_cov_tc.cu
+cudaError_t launch_covariance_tc(const cf* snap, const double* wt, double2* Rout, long long F, int B, int C, int conj,
+                                 cudaStream_t st);
 // per-bin MVDR solve (beamformer.cc:2392-2446); Rn [B][C][C], d [B][C] -> w [B][C]; fallback[B] flags
 cudaError_t launch_mvdr_solve(const double2* Rn, const double2* d, double2* w, int* fallback, int B, int C,
                               double dThreshold, cudaStream_t st);
