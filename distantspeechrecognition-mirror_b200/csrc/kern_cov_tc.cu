@@ -139,13 +139,15 @@ __global__ void __launch_bounds__(COV_TC_THREADS) btk_covariance_tc_kernel(const
     }
     return x;
   };
+  // frame weights travel as raw doubles with the prefetched rows; the square root is taken when the chunk is consumed,
+  // so that no instruction waits on a global load inside the prefetch
   float4 xn[4];
-  float wn[4];
+  double wn[4];
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     const long long f = f_lo + 4 * warp + i;
     xn[i] = load4(f);
-    wn[i] = f < f_hi ? sqrtf((float)wt[f]) : 0.f;
+    wn[i] = f < f_hi ? __ldg(wt + f) : 0.0;
   }
 
   for (int ch = 0; ch < n_chunks; ch++) {
@@ -153,13 +155,13 @@ __global__ void __launch_bounds__(COV_TC_THREADS) btk_covariance_tc_kernel(const
     float4 x[4];
     float w[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) { x[i] = xn[i]; w[i] = wn[i]; }
+    for (int i = 0; i < 4; i++) { x[i] = xn[i]; w[i] = sqrtf((float)wn[i]); }
     if (ch + 1 < n_chunks) {               // next chunk's rows are in flight while this one is split and multiplied
 #pragma unroll
       for (int i = 0; i < 4; i++) {
         const long long f = f_lo + (long long)(ch + 1) * COV_TC_KC + 4 * warp + i;
         xn[i] = load4(f);
-        wn[i] = f < f_hi ? sqrtf((float)wt[f]) : 0.f;
+        wn[i] = f < f_hi ? __ldg(wt + f) : 0.0;
       }
     }
     if (ch >= 2) mbar_wait(smem_u32(&s_bar[st]), (uint32_t)(((ch >> 1) - 1) & 1));   // MMAs of chunk ch-2 have read this stage
