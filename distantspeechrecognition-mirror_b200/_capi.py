@@ -25,7 +25,8 @@ SYMBOLS = [
     "btkb200_set_covariance", "btkb200_get_covariance", "btkb200_set_diffuse_noise_model", "btkb200_diag_load",
     "btkb200_diag_load_bin", "btkb200_divide_nondiagonal", "btkb200_solve_mvdr", "btkb200_analysis",
     "btkb200_beamform", "btkb200_synthesis", "btkb200_covariance", "btkb200_estimate_covariance", "btkb200_chain",
-    "btkb200_chain_batch", "btkb200_chain_batch_pcm", "btkb200_convert_pcm",
+    "btkb200_chain_batch", "btkb200_chain_batch_pcm", "btkb200_convert_pcm", "btkb200_beamform_zelinski",
+    "btkb200_chain_zelinski", "btkb200_beamform_zelinski_dev",
     "btkb200_chain_batch_multi", "btkb200_chain_batch_dev", "btkb200_analysis_dev", "btkb200_beamform_dev",
     "btkb200_synthesis_dev", "btkb200_launch_count", "btkb200_sync", "btkb200_host_alloc", "btkb200_host_free",
 ]
@@ -90,6 +91,9 @@ def lib() -> ctypes.CDLL:
     L.btkb200_chain_batch.argtypes = [vp, POINTER(vp), POINTER(c_long), c_int, POINTER(vp)]
     L.btkb200_chain_batch_pcm.argtypes = [vp, POINTER(vp), c_int, POINTER(c_long), c_int, POINTER(vp)]
     L.btkb200_convert_pcm.argtypes = [vp, vp, c_int, c_long, vp]
+    L.btkb200_beamform_zelinski.argtypes = [vp, vp, c_long, c_double, c_int, c_int, vp, vp]
+    L.btkb200_chain_zelinski.argtypes = [vp, vp, c_long, c_double, c_int, c_int, vp]
+    L.btkb200_beamform_zelinski_dev.argtypes = [vp, vp, c_long, c_double, c_int, c_int, vp, vp, vp]
     L.btkb200_chain_batch_multi.argtypes = [POINTER(vp), c_int, POINTER(vp), POINTER(c_long), c_int, POINTER(vp)]
     L.btkb200_chain_batch_dev.argtypes = [vp, vp, POINTER(c_longlong), POINTER(c_longlong), POINTER(c_longlong), c_int,
                                           vp, vp]
@@ -269,6 +273,27 @@ class Plan:
         if x.ndim != 2 or x.shape[1] != self.C:
             raise BtkError(EINVAL, f"pcm must be [T][{self.C}]")
         self._ck(self._L.btkb200_estimate_covariance(self._h, _p(x), x.shape[0], forget, last_frame, 1 if conjugate else 0))
+
+    # -- Zelinski post-filter (postfilter/postfilter.cc:30-222, 428-500)
+    def beamform_zelinski(self, snap, alpha: float = 0.6, pf_type: int = 2, min_frames: int = 0):
+        """snapshots [F][B][C] -> (post-filtered beamformer output [F][B] complex64, gains [F][B] float32)."""
+        s = np.ascontiguousarray(snap, dtype=np.complex64)
+        F = s.shape[0]
+        if s.shape[1:] != (self.B, self.C):
+            raise BtkError(EINVAL, f"snapshots must be [F][{self.B}][{self.C}]")
+        Y = np.empty((F, self.B), dtype=np.complex64)
+        W = np.empty((F, self.B), dtype=np.float32)
+        self._ck(self._L.btkb200_beamform_zelinski(self._h, _p(s), F, alpha, pf_type, min_frames, _p(Y), _p(W)))
+        return Y, W
+
+    def chain_zelinski(self, pcm, alpha: float = 0.6, pf_type: int = 2, min_frames: int = 0) -> np.ndarray:
+        """pcm [T][C] -> analysis -> beamformer -> Zelinski post-filter -> synthesis, all on the device."""
+        x = np.ascontiguousarray(pcm, dtype=np.float32)
+        if x.ndim != 2 or x.shape[1] != self.C:
+            raise BtkError(EINVAL, f"pcm must be [T][{self.C}]")
+        out = np.empty(self.chain_frames(x.shape[0]) * self.D, dtype=np.float32)
+        self._ck(self._L.btkb200_chain_zelinski(self._h, _p(x), x.shape[0], alpha, pf_type, min_frames, _p(out)))
+        return out
 
     # -- fused path (host numpy buffers)
     def chain(self, pcm) -> np.ndarray:

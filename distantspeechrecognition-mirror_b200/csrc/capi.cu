@@ -58,6 +58,7 @@ struct btkb200_plan {
   cf* d_twb = nullptr;
   cf* d_wts_chain = nullptr;   // [Cpad][M]
   cf* d_w = nullptr;           // [B][C]
+  cf* d_ta = nullptr;          // [B][C] array manifold (time alignment of the post-filter)
   // scratch
   DevBuf d_recs, d_work, d_in, d_out, d_aux, d_aux2, d_raw;
   PinBuf h_desc;
@@ -167,6 +168,7 @@ int btkb200_plan_create(btkb200_plan** out, unsigned M, unsigned m, unsigned r, 
   if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_twb, twb.size() * sizeof(cf));
   if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_wts_chain, (size_t)p->Cpad * M * sizeof(cf));
   if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_w, (size_t)B * C * sizeof(cf));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_ta, (size_t)B * C * sizeof(cf));
   if (e == cudaSuccess) {
     if (h) p->has_h = true;
     if (g) { build_synthesis_taps(g, (int)M, (int)m, gp); p->has_g = true; }
@@ -192,7 +194,7 @@ void btkb200_plan_destroy(btkb200_plan* p) {
   if (!p) return;
   cudaSetDevice(p->device);
   if (p->stream) cudaStreamSynchronize(p->stream);
-  cudaFree(p->d_taps_h); cudaFree(p->d_taps_g); cudaFree(p->d_twa); cudaFree(p->d_twb); cudaFree(p->d_wts_chain); cudaFree(p->d_w);
+  cudaFree(p->d_taps_h); cudaFree(p->d_taps_g); cudaFree(p->d_twa); cudaFree(p->d_twb); cudaFree(p->d_wts_chain); cudaFree(p->d_w); cudaFree(p->d_ta);
   p->d_recs.release(); p->d_work.release(); p->d_in.release(); p->d_out.release(); p->d_aux.release(); p->d_aux2.release(); p->d_raw.release();
   p->h_desc.release();
   if (p->stream) cudaStreamDestroy(p->stream);
@@ -226,6 +228,13 @@ int btkb200_set_ds_weights(btkb200_plan* p, double fs, const double* delays, uns
   p->has_manifold = true;
   p->w = p->wq;
   p->has_weights = 1;
+  {
+    std::vector<cf> ta(p->wq.size());
+    for (size_t i = 0; i < ta.size(); i++) ta[i] = mk((float)p->wq[i].real(), (float)p->wq[i].imag());
+    CK(p, cudaSetDevice(p->device));
+    CK(p, cudaStreamSynchronize(p->stream));
+    CK(p, cudaMemcpy(p->d_ta, ta.data(), ta.size() * sizeof(cf), cudaMemcpyHostToDevice));
+  }
   return upload_weights(p);
 }
 
@@ -398,6 +407,21 @@ int btkb200_beamform_dev(btkb200_plan* p, const float* d_snap, long F, float* d_
   return BTKB200_OK;
 }
 
+int btkb200_beamform_zelinski_dev(btkb200_plan* p, const float* d_snap, long F, double alpha, int type, int min_frames,
+                                  float* d_Y, float* d_W, void* stream) {
+  if (!p || !d_snap || !d_Y || F < 0) return BTKB200_EINVAL;
+  if (!p->has_weights) return fail(p, BTKB200_ESTATE, "call calcArrayManifoldVectorsX() once");
+  if (!p->has_manifold) return fail(p, BTKB200_ESTATE, "set beamformer's weights");
+  if (p->C <= 1) return fail(p, BTKB200_EINVAL, "The number of channels %d is <= 1", p->C);   // postfilter.cc:62-65
+  CK(p, cudaSetDevice(p->device));
+  if (F == 0) return BTKB200_OK;
+  CK(p, p->d_aux.reserve((size_t)F * p->geo.B * sizeof(float4)));
+  CK(p, launch_beamform_zelinski((const cf*)d_snap, p->d_w, p->d_ta, (cf*)d_Y, (float4*)p->d_aux.p, d_W, F, p->geo.B, p->C,
+                                 alpha, type, min_frames, (cudaStream_t)stream));
+  p->launches += 2;
+  return BTKB200_OK;
+}
+
 int btkb200_synthesis_dev(btkb200_plan* p, const float* d_Y, long F, float* d_out, void* stream) {
   if (!p || !d_Y || !d_out || F < 0) return BTKB200_EINVAL;
   if (!p->has_g) return fail(p, BTKB200_ESTATE, "plan was created without a synthesis prototype");
@@ -513,6 +537,49 @@ int btkb200_beamform(btkb200_plan* p, const float* snap, long F, float* Y) {
   int rc = btkb200_beamform_dev(p, (const float*)p->d_in.p, F, (float*)p->d_out.p, p->stream);
   if (rc) return rc;
   CK(p, cudaMemcpyAsync(Y, p->d_out.p, bout, cudaMemcpyDeviceToHost, p->stream));
+  CK(p, cudaStreamSynchronize(p->stream));
+  return BTKB200_OK;
+}
+
+int btkb200_beamform_zelinski(btkb200_plan* p, const float* snap, long F, double alpha, int type, int min_frames, float* Y,
+                              float* W) {
+  if (!p || !snap || !Y || F < 0) return BTKB200_EINVAL;
+  CK(p, cudaSetDevice(p->device));
+  const size_t bin = (size_t)F * p->geo.B * p->C * sizeof(cf), bY = (size_t)F * p->geo.B * sizeof(cf);
+  const size_t bW = (size_t)F * p->geo.B * sizeof(float);
+  if (F == 0) return BTKB200_OK;
+  CK(p, p->d_in.reserve(bin));
+  CK(p, p->d_out.reserve(bY + bW + 16));
+  float* dW = (float*)((char*)p->d_out.p + ((bY + 15) / 16) * 16);
+  CK(p, cudaMemcpyAsync(p->d_in.p, snap, bin, cudaMemcpyHostToDevice, p->stream));
+  int rc = btkb200_beamform_zelinski_dev(p, (const float*)p->d_in.p, F, alpha, type, min_frames, (float*)p->d_out.p, dW, p->stream);
+  if (rc) return rc;
+  CK(p, cudaMemcpyAsync(Y, p->d_out.p, bY, cudaMemcpyDeviceToHost, p->stream));
+  if (W) CK(p, cudaMemcpyAsync(W, dW, bW, cudaMemcpyDeviceToHost, p->stream));
+  CK(p, cudaStreamSynchronize(p->stream));
+  return BTKB200_OK;
+}
+
+int btkb200_chain_zelinski(btkb200_plan* p, const float* pcm, long T, double alpha, int type, int min_frames, float* out) {
+  if (!p || !pcm || !out || T < 0) return BTKB200_EINVAL;
+  if (!p->has_h || !p->has_g) return fail(p, BTKB200_ESTATE, "the chain needs both prototypes");
+  CK(p, cudaSetDevice(p->device));
+  const long F = p->geo.analysis_frames(T), nout = p->geo.synthesis_frames((int)F);
+  const size_t bin = (size_t)T * p->C * sizeof(float), bsnap = (size_t)F * p->geo.B * p->C * sizeof(cf);
+  const size_t bY = (size_t)F * p->geo.B * sizeof(cf), bout = (size_t)nout * p->geo.D * sizeof(float);
+  CK(p, p->d_in.reserve(bin ? bin : 16));
+  CK(p, p->d_out.reserve(bsnap ? bsnap : 16));
+  CK(p, p->d_aux2.reserve(bY + bout + 32));
+  float* dY = (float*)p->d_aux2.p;
+  float* dout = (float*)((char*)p->d_aux2.p + ((bY + 15) / 16) * 16);
+  if (bin) CK(p, cudaMemcpyAsync(p->d_in.p, pcm, bin, cudaMemcpyHostToDevice, p->stream));
+  int rc = btkb200_analysis_dev(p, (const float*)p->d_in.p, T, (float*)p->d_out.p, p->stream);
+  if (rc) return rc;
+  rc = btkb200_beamform_zelinski_dev(p, (const float*)p->d_out.p, F, alpha, type, min_frames, dY, nullptr, p->stream);
+  if (rc) return rc;
+  rc = btkb200_synthesis_dev(p, dY, F, dout, p->stream);
+  if (rc) return rc;
+  if (bout) CK(p, cudaMemcpyAsync(out, dout, bout, cudaMemcpyDeviceToHost, p->stream));
   CK(p, cudaStreamSynchronize(p->stream));
   return BTKB200_OK;
 }

@@ -1,0 +1,122 @@
+// kern_postfilter.cu -- Zelinski post-filter between the beamformer and the synthesis bank
+// (postfilter/postfilter.cc:30-222 ZelinskiFilter_f / ZelinskiFilter, :428-500 ZelinskiPostFilter::next; used by both
+// shipped drivers, src/superdirectiveBeamformer.cc:164,200 and src/beamformerDS.cc:154,183).
+//
+// Reference, per frame n and bin s (0..M/2):  y_i = conj(ta_i) x_i  (time alignment with the array manifold),
+//     Phi_ij(n) = a_n Phi_ij(n-1) + (1 - a_n) y_i conj(y_j)   for every pair i < j,      (calcCSD, :8-21)
+//     Psi_i(n)  = a_n Psi_i(n-1)  + (1 - a_n) |y_i|^2,
+//     W = clamp( num / sum_i Psi_i * 2 / (C - 1), 1e-4, 1 ),  num = |sum_{i<j} Phi_ij| (ABS) or max(Re sum, 0) (REAL),
+// with a_n = alpha for n >= 2 and 0 for the first two frames (alpha is applied only once _frameX > 0, :466-469), and
+// the beamformer output is multiplied by W from frame minFrames + 1 on (:474-479).
+//
+// The recursions are linear and share a_n, so the sum over pairs obeys the same recursion: only
+//     S(n) = a_n S(n-1) + (1 - a_n) s(n),  s(n) = sum_{i<j} y_i conj(y_j)   and   P(n), p(n) = sum_i |y_i|^2
+// are carried -- O(C) per (frame, bin) with a running prefix sum instead of O(C^2) state per bin.
+//   kernel 1 (frame- and bin-parallel): beamformer output Y, s, p from the stored snapshots (one pass over them);
+//   kernel 2: the first-order recursion over frames as a segmented scan (affine maps compose), then W and Y *= W.
+#include "launch.h"
+
+namespace btk {
+
+__global__ void __launch_bounds__(256) btk_beamform_zelinski_kernel(const cf* __restrict__ snap, const cf* __restrict__ w,
+                                                                   const cf* __restrict__ ta, cf* __restrict__ Y,
+                                                                   float4* __restrict__ stat, long long FB, int B, int C) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < FB;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int s = (int)(idx % B);
+    const cf* x = snap + idx * C;
+    const cf* ws = w + (long long)s * C;
+    const cf* ts = ta + (long long)s * C;
+    float yr = 0.f, yi = 0.f;            // beamformer output  sum_c conj(w_c) x_c   (beamformer.cc:1181-1188)
+    float pr = 0.f, pi = 0.f;            // prefix sum of the aligned channels
+    float sr = 0.f, si = 0.f, p = 0.f;
+    for (int c = 0; c < C; c++) {
+      const cf a = ws[c], t = ts[c], b = x[c];
+      yr = fmaf(a.x, b.x, yr); yr = fmaf(a.y, b.y, yr);
+      yi = fmaf(a.x, b.y, yi); yi = fmaf(-a.y, b.x, yi);
+      const float ar = t.x * b.x + t.y * b.y, ai = t.x * b.y - t.y * b.x;      // y_c = conj(ta_c) x_c
+      // s += (sum_{i<c} y_i) conj(y_c)
+      sr += pr * ar + pi * ai;
+      si += pi * ar - pr * ai;
+      p = fmaf(ar, ar, fmaf(ai, ai, p));
+      pr += ar; pi += ai;
+    }
+    Y[idx] = mk(yr, yi);
+    stat[idx] = make_float4(sr, si, p, 0.f);
+  }
+}
+
+#define ZEL_SEG 16          // frame segments (warps) per CTA
+// CTA = 32 consecutive bins (lanes, coalesced) x ZEL_SEG contiguous frame segments (warps).
+__global__ void __launch_bounds__(32 * ZEL_SEG) btk_zelinski_scan_kernel(const float4* __restrict__ stat, cf* __restrict__ Y,
+                                                                        float* __restrict__ Wout, long long F, int B, int C,
+                                                                        double alpha, int type, int min_frames) {
+  __shared__ double s_end[ZEL_SEG][32][3];
+  __shared__ double s_A[ZEL_SEG][32];
+  const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
+  const int s = blockIdx.x * 32 + lane;
+  const long long per = (F + ZEL_SEG - 1) / ZEL_SEG;
+  const long long n0 = per * seg, n1 = (n0 + per < F) ? n0 + per : F;
+  const bool live = s < B;
+  // pass 1: the segment from a zero state: end state and the product of its coefficients
+  double Sr = 0.0, Si = 0.0, P = 0.0, A = 1.0;
+  if (live) {
+    for (long long n = n0; n < n1; n++) {
+      const double a = n >= 2 ? alpha : 0.0;
+      const float4 v = stat[n * B + s];
+      Sr = a * Sr + (1.0 - a) * (double)v.x;
+      Si = a * Si + (1.0 - a) * (double)v.y;
+      P = a * P + (1.0 - a) * (double)v.z;
+      A *= a;
+    }
+  }
+  s_end[seg][lane][0] = Sr; s_end[seg][lane][1] = Si; s_end[seg][lane][2] = P; s_A[seg][lane] = A;
+  __syncthreads();
+  // state entering this segment: fold the earlier segments in order
+  Sr = 0.0; Si = 0.0; P = 0.0;
+  for (int q = 0; q < seg; q++) {
+    const double a = s_A[q][lane];
+    Sr = a * Sr + s_end[q][lane][0];
+    Si = a * Si + s_end[q][lane][1];
+    P = a * P + s_end[q][lane][2];
+  }
+  if (!live) return;
+  const double scale = 2.0 / ((double)C - 1.0);             // 2 / (nChan - 1), postfilter.cc:121
+  for (long long n = n0; n < n1; n++) {
+    const double a = n >= 2 ? alpha : 0.0;
+    const float4 v = stat[n * B + s];
+    Sr = a * Sr + (1.0 - a) * (double)v.x;
+    Si = a * Si + (1.0 - a) * (double)v.y;
+    P = a * P + (1.0 - a) * (double)v.z;
+    const bool applied = n > min_frames && type != 0;       // frames 0 .. minFrames only update the densities, and
+                                                            // their (unused) gain follows the |.| branch (pfType = 0)
+    double num;
+    if (applied && (type & 1)) num = Sr < 0.0 ? 0.0 : Sr;   // TYPE_ZELINSKI1_REAL
+    else num = sqrt(Sr * Sr + Si * Si);
+    double W = (num / P) * scale;
+    if (W >= 1.0) W = 1.0;
+    if (W < 1.0e-4) W = 1.0e-4;                              // SPECTRAL_FLOOR
+    if (Wout) Wout[n * B + s] = (float)W;
+    if (applied) {
+      cf y = Y[n * B + s];
+      y.x *= (float)W; y.y *= (float)W;
+      Y[n * B + s] = y;
+    }
+  }
+}
+
+cudaError_t launch_beamform_zelinski(const cf* snap, const cf* w, const cf* ta, cf* Y, float4* stat, float* Wout, long long F,
+                                     int B, int C, double alpha, int type, int min_frames, cudaStream_t st) {
+  const long long FB = F * B;
+  if (FB == 0) return cudaSuccess;
+  if (C < 2) return cudaErrorInvalidValue;                  // jdimension_error in the reference (postfilter.cc:62-65)
+  long long blocks = (FB + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  btk_beamform_zelinski_kernel<<<(int)blocks, 256, 0, st>>>(snap, w, ta, Y, stat, FB, B, C);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  btk_zelinski_scan_kernel<<<(B + 31) / 32, 32 * ZEL_SEG, 0, st>>>(stat, Y, Wout, F, B, C, alpha, type, min_frames);
+  return cudaGetLastError();
+}
+
+}  // namespace btk

@@ -29,6 +29,11 @@ cudaError_t launch_covariance_tc(const cf* snap, const double* wt, double2* Rout
 cudaError_t launch_mvdr_solve(const double2* Rn, const double2* d, double2* w, int* fallback, int B, int C,
                               double dThreshold, cudaStream_t st);
 
+// Beamformer output + Zelinski post-filter on stored snapshots (postfilter/postfilter.cc:30-222, 428-500): Y [F][B]
+// post-filtered in place semantics (Y is written, then scaled), stat = scratch [F][B] float4, Wout [F][B] or NULL.
+cudaError_t launch_beamform_zelinski(const cf* snap, const cf* w, const cf* ta, cf* Y, float4* stat, float* Wout, long long F,
+                                     int B, int C, double alpha, int type, int min_frames, cudaStream_t st);
+
 // Raw PCM -> float32, element for element (bit-exact integer -> float):
 //   fmt 1: int16 little endian (what sf_readf_float returns with SFC_SET_NORM_FLOAT off, feature/feature.cc:273, 868-896)
 //   fmt 2: packed 24-bit big endian, sign extended (Conversion24bit2Float::next, feature/feature.cc:190-217;

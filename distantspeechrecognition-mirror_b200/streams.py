@@ -437,6 +437,75 @@ class SubbandMVDRPtr(_SubbandBeamformer):
         return self.getWeights(fbinX)
 
 
+TYPE_ZELINSKI1_REAL, TYPE_ZELINSKI1_ABS, TYPE_APAB, TYPE_ZELINSKI2, NO_USE_POST_FILTER = 0x01, 0x02, 0x04, 0x08, 0x00
+
+
+class ZelinskiPostFilterPtr(FeatureStream):
+    """postfilter/postfilter.h:95-126, postfilter.cc:340-500: the node both shipped drivers put between the beamformer and
+    the synthesis bank (src/beamformerDS.cc:154,183).  ``output`` must be the SubbandDS/SubbandMVDR node that is also
+    given to setBeamformer(); its snapshots and array manifold feed the filter (setSnapShotArray / setArrayManifoldVector
+    with foreign sources are not supported by the B200 engine)."""
+
+    def __init__(self, output, fftLen: int, alpha: float = 0.6, type: int = 2, minFrames: int = 0,
+                 nm: str = "ZelinskPostFilter"):
+        super().__init__(fftLen, nm)
+        if output.size() != fftLen:          # postfilter.cc:355-358
+            raise jdimension_error(f"Input block length ({output.size()}) != fftLen ({fftLen})")
+        self._samp, self._alpha, self._type, self._minFrames = output, float(alpha), int(type), int(minFrames)
+        self._bf = None
+        self._Y = None
+        self._W = None
+        self._vector = np.zeros(fftLen, np.complex128)
+
+    def setBeamformer(self, beamformer):
+        self._bf = beamformer
+
+    def getPostFilterWeights(self):
+        """wp1 of the frame last returned (full M bins, conjugate-mirrored like postfilter.cc:185-186)."""
+        if self._W is None or self._frameX < 0:
+            return None
+        M = self._size
+        half = self._W[self._frameX].astype(np.complex128)
+        return np.concatenate([half, np.conj(half[1:M // 2][::-1])])
+
+    def _evaluate(self):
+        bf = self._bf
+        if bf is None or not isinstance(bf, _SubbandBeamformer):
+            raise j_error("set beamformer's weights \n")            # postfilter.cc:449-452
+        if bf is not self._samp:
+            raise j_error("the B200 post-filter expects its input stream to be the beamformer given to setBeamformer()")
+        if bf._snap is None:
+            bf._evaluate()
+        try:
+            self._Y, self._W = bf._plan.beamform_zelinski(bf._snap, self._alpha, self._type, self._minFrames)
+        except BtkError as e:
+            _raise(e)
+
+    def next(self, frameX: int = -5):
+        if frameX == self._frameX and self._frameX >= 0:
+            return self._vector
+        if self._Y is None:
+            self._evaluate()
+        t = self._frameX + 1
+        if t >= self._Y.shape[0]:
+            self._endOfSamples = True
+            raise jiterator_error("end of samples!")
+        half = self._Y[t]
+        M = self._size
+        B = M // 2 + 1
+        self._vector[:B] = half
+        self._vector[B:] = np.conj(half[1:M // 2][::-1])       # postfilter.cc:213-216
+        self._frameX = t
+        return self._vector
+
+    def reset(self):
+        super().reset()
+        if isinstance(self._samp, FeatureStream):
+            self._samp.reset()
+        self._Y = None
+        self._W = None
+
+
 class OverSampledDFTSynthesisBankPtr(FeatureStream, _FilterBank):
     """modulated/modulated.cc:521-674.  ``next()`` yields float32[D] blocks (scaled 1/D like the reference)."""
 

@@ -122,6 +122,21 @@ int btkb200_covariance(btkb200_plan* plan, const float* snap, long F, const doub
 int btkb200_estimate_covariance(btkb200_plan* plan, const float* pcm, long T, double forget, long last_frame,
                                 int conjugate);
 
+/* ---- Zelinski post-filter ------------------------------------------------------------------- */
+/* ZelinskiPostFilter::next over a whole recording (postfilter/postfilter.cc:428-500 -> ZelinskiFilter :153-222 ->
+ * ZelinskiFilter_f :56-140), with the beamformer as set by setBeamformer(): snapshots [F][B][C] -> beamformer output
+ * (current weights) multiplied by the post-filter gain, Y [F][B] complex64; W [F][B] float32 receives the gains
+ * (getPostFilterWeights() of every frame) when not NULL.  alpha = forgetting factor (default 0.6), type =
+ * PostfilterType (1 = TYPE_ZELINSKI1_REAL, 2 = TYPE_ZELINSKI1_ABS, 0 = NO_USE_POST_FILTER: gains only), min_frames as
+ * in the constructor.  The time alignment uses the array manifold of set_ds_weights (beamformerWeights::arrayManifold).
+ * EINVAL for fewer than two channels (jdimension_error, :62-65). */
+int btkb200_beamform_zelinski(btkb200_plan* plan, const float* snap, long F, double alpha, int type, int min_frames,
+                              float* Y, float* W);
+/* analysis -> beamformer -> Zelinski post-filter -> synthesis on the device, host pcm in, host PCM out
+ * (the chain of src/superdirectiveBeamformer.cc:150-205 and src/beamformerDS.cc); out holds chain_frames(T)*D floats. */
+int btkb200_chain_zelinski(btkb200_plan* plan, const float* pcm, long T, double alpha, int type, int min_frames,
+                           float* out);
+
 /* ---- fused path ---------------------------------------------------------------------------------------- */
 /* pcm -> out through analysis -> weight apply -> synthesis in ONE kernel; out holds chain_frames(T)*D floats.
  * ESTATE if no weights are installed (j_error, beamformer.cc:1140-1143). */
@@ -152,6 +167,8 @@ int btkb200_chain_batch_dev(btkb200_plan* plan, const float* d_pcm, const long l
                             const long long* out_off, int n, float* d_out, void* stream);
 int btkb200_analysis_dev(btkb200_plan* plan, const float* d_pcm, long T, float* d_snap, void* stream);
 int btkb200_beamform_dev(btkb200_plan* plan, const float* d_snap, long F, float* d_Y, void* stream);
+int btkb200_beamform_zelinski_dev(btkb200_plan* plan, const float* d_snap, long F, double alpha, int type, int min_frames,
+                                  float* d_Y, float* d_W, void* stream);
 int btkb200_synthesis_dev(btkb200_plan* plan, const float* d_Y, long F, float* d_out, void* stream);
 /* Kernels enqueued by this plan so far (for launch accounting in bench.py). */
 long btkb200_launch_count(const btkb200_plan* plan);

@@ -267,6 +267,73 @@ def chain(pcm: np.ndarray, h: np.ndarray, g: np.ndarray, geo: BankGeometry, W: n
     return X, Y, out.reshape(-1)
 
 
+# --------------------------------------------------------------------------- Zelinski post-filter
+TYPE_ZELINSKI1_REAL, TYPE_ZELINSKI1_ABS, NO_USE_POST_FILTER = 1, 2, 0      # postfilter/postfilter.h:66-72
+SPECTRAL_FLOOR = 1.0e-4                                                     # postfilter/postfilter.cc:56
+
+
+def zelinski_postfilter(X: np.ndarray, Y: np.ndarray, ta: np.ndarray, alpha: float = 0.6,
+                        pf_type: int = TYPE_ZELINSKI1_ABS, min_frames: int = 0):
+    """ZelinskiPostFilter::next over a stream (postfilter/postfilter.cc:428-500), restated with the reference's own
+    per-pair state:  X [F][C][M] snapshots, Y [F][M] beamformer output, ta [B][C] array manifold
+    (beamformerWeights::arrayManifold = the delay-and-sum weights, beamformer.cc:583, 992-997).
+    Per frame n (the node's _frameX is n - 1 when the frame is processed):
+      alpha_n = alpha if n - 1 > 0 else 0                                        (:466-469)
+      y_i = conj(ta_i) x_i                                                        (TimeAlignment, :30-43)
+      Phi_ij <- alpha_n Phi_ij + (1 - alpha_n) y_i conj(y_j), i < j  (or y_i conj(y_j) when alpha_n == 0)   (calcCSD, :8-21)
+      Psi_i  <- alpha_n Psi_i  + (1 - alpha_n) |y_i|^2                            (:96-110)
+      W = clamp(num / sum Psi * 2 / (C - 1), 1e-4, 1), num = max(Re sum Phi, 0) (REAL) or |sum Phi| (otherwise)  (:84-124)
+      bins 0..M/2, mirrored; the signal is multiplied only when n - 1 >= min_frames and type != 0   (:474-479, 197-199)
+    Returns (Ypf [F][M] complex128, W [F][B] float64)."""
+    X = np.asarray(X, dtype=np.complex128)
+    Y = np.asarray(Y, dtype=np.complex128)
+    F, C, M = X.shape
+    B = M // 2 + 1
+    if C <= 1:
+        raise ValueError(f"The number of channels {C} is <= 1")
+    iu = np.triu_indices(C, 1)
+    Phi = np.zeros((B, iu[0].size), dtype=np.complex128)
+    Psi = np.zeros((B, C), dtype=np.float64)
+    Ypf = Y.copy()
+    Wall = np.zeros((F, B), dtype=np.float64)
+    for n in range(F):
+        a = alpha if (n - 1) > 0 else 0.0
+        y = np.conj(ta[:B]) * X[n, :, :B].T                     # [B][C]
+        cross = y[:, iu[0]] * np.conj(y[:, iu[1]])
+        if a > 0.0:
+            Phi = a * Phi + (1.0 - a) * cross
+            Psi = a * Psi + (1.0 - a) * np.abs(y) ** 2
+        else:
+            Phi = cross
+            Psi = np.abs(y) ** 2
+        tot = Phi.sum(axis=1)
+        # frames that only update the densities are processed with pfType = NO_USE_POST_FILTER (:474-476), whose
+        # gain (stored in wp1, not applied) follows the |.| branch
+        applied = (n - 1) >= min_frames and pf_type != NO_USE_POST_FILTER
+        num = np.maximum(tot.real, 0.0) if (applied and (pf_type & TYPE_ZELINSKI1_REAL)) else np.abs(tot)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            W = (num / Psi.sum(axis=1)) * (2.0 / (C - 1.0))
+        W = np.where(W >= 1.0, 1.0, W)
+        W = np.where(W < SPECTRAL_FLOOR, SPECTRAL_FLOOR, W)
+        Wall[n] = W
+        if applied:
+            Ypf[n, :B] = W * Y[n, :B]
+            Ypf[n, B:] = np.conj(Ypf[n, 1:M // 2][::-1])
+    return Ypf, Wall
+
+
+def chain_zelinski(pcm, h, g, geo: BankGeometry, W, ta, alpha=0.6, pf_type=TYPE_ZELINSKI1_ABS, min_frames=0, gain=1):
+    """analysis -> beamform (weights W) -> Zelinski post-filter (manifold ta) -> synthesis.
+    Returns (X, Y, Ypf, Wpf, out)."""
+    pcm = np.asarray(pcm)
+    C = pcm.shape[1]
+    X = np.stack([analysis(pcm[:, c], h, geo) for c in range(C)], axis=1)
+    Y = beamform(X, W)
+    Ypf, Wpf = zelinski_postfilter(X, Y, ta, alpha, pf_type, min_frames)
+    out = synthesis(Ypf, g, geo, gain)
+    return X, Y, Ypf, Wpf, out.reshape(-1)
+
+
 # --------------------------------------------------------------------------- compiled reference (oracle/_ref)
 class _ChainCfg(ctypes.Structure):
     _fields_ = [
@@ -299,6 +366,10 @@ class CompiledReference:
         L.btkref_chain.restype = cl
         L.btkref_chain.argtypes = [ctypes.POINTER(_ChainCfg), vp, cl, vp, vp, vp, vp, vp, vp, vp, cl, vp, cl,
                                    ctypes.POINTER(cl), vp]
+        if hasattr(L, "btkref_chain_zelinski"):
+            L.btkref_chain_zelinski.restype = cl
+            L.btkref_chain_zelinski.argtypes = [ctypes.POINTER(_ChainCfg), vp, cl, vp, vp, vp, cd, ci, ci, vp, vp, cl, vp,
+                                                cl, ctypes.POINTER(cl)]
         L.btkref_spectral_matrix.restype = cl
         L.btkref_spectral_matrix.argtypes = [vp, cl, ci, vp, ci, ci, ci, ci, cd, vp]
         L.btkref_error_probe.restype = ci
@@ -359,6 +430,29 @@ class CompiledReference:
             res["X"] = np.ascontiguousarray(snap[:n].view(np.complex128)[..., 0].transpose(0, 2, 1))  # [F][C][M]
         if want_Y:
             res["Y"] = Y[:n].view(np.complex128)[..., 0]
+        if g is not None:
+            res["out"] = out[: nout.value].reshape(-1)
+        return res
+
+    def chain_zelinski(self, pcm, h, g, geo: BankGeometry, delays, alpha=0.6, pf_type=2, min_frames=0, fs=16000.0, gain=1):
+        """The reference's SubbandDS -> ZelinskiPostFilter -> synthesis chain.  Returns dict(Ypf [F][M], Wpf [F][M], out)."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.float32)
+        T, C = pcm.shape
+        h = np.ascontiguousarray(h, dtype=np.float64)
+        g = None if g is None else np.ascontiguousarray(g, dtype=np.float64)
+        delays = np.ascontiguousarray(delays, dtype=np.float64)
+        cfg = _ChainCfg(geo.M, geo.m, geo.r, geo.dct, C, fs, 0, 1, 0, 1e-8, 0.0, -1.0, SSPEED, gain)
+        cap = geo.analysis_frames(T) + 4
+        Ypf = np.zeros((cap, geo.M, 2), dtype=np.float64)
+        Wpf = np.zeros((cap, geo.M), dtype=np.float64)
+        cap_out = geo.nblk(T) + 4
+        out = np.zeros((cap_out, geo.D), dtype=np.float32) if g is not None else None
+        nout = ctypes.c_long(0)
+        n = self.lib.btkref_chain_zelinski(ctypes.byref(cfg), _dp(pcm), T, _dp(h), _dp(g), _dp(delays), alpha, pf_type,
+                                           min_frames, _dp(Ypf), _dp(Wpf), cap, _dp(out), cap_out, ctypes.byref(nout))
+        if n < 0 or n > cap:
+            raise RuntimeError(f"btkref_chain_zelinski returned {n}")
+        res = {"frames": int(n), "Ypf": Ypf[:n].view(np.complex128)[..., 0], "Wpf": Wpf[:n]}
         if g is not None:
             res["out"] = out[: nout.value].reshape(-1)
         return res

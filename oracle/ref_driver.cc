@@ -11,6 +11,7 @@
 //   SubbandDS                    btk/beamformer/beamformer.cc:1057-1212
 //   SubbandMVDR                  btk/beamformer/beamformer.cc:2321-2635
 //   SpectralMatrixArray          btk/beamformer/beamformer.cc:119-163
+//   ZelinskiPostFilter           btk/postfilter/postfilter.cc:340-500
 // This file only feeds them from memory and copies their per-frame outputs out.
 // The in-memory source reproduces SampleFeature::next's block/pad rule
 // (btk/feature/feature.cc:610-659) because feature.cc itself needs libsndfile.
@@ -24,19 +25,8 @@
 #include "modulated/modulated.h"
 #include "beamformer/beamformer.h"
 
-// ---------------------------------------------------------------------------
-// Symbols the reference's beamformer.cc references from postfilter.cc (only via
-// SubbandMMI, which is never instantiated here).  Defining them keeps the .so
-// free of undefined symbols without building postfilter.cc.
-// ---------------------------------------------------------------------------
+// postfilter/postfilter.cc is part of the build (ZelinskiPostFilter: btk/postfilter/postfilter.cc:30-222, 340-500).
 #include "postfilter/postfilter.h"
-void ZelinskiFilter(gsl_vector_complex**, SnapShotArrayPtr, bool, gsl_vector_complex*, gsl_vector_complex**,
-                    gsl_vector_complex*, double, int) {
-  throw j_error("ZelinskiFilter is not part of the oracle build");
-}
-void ApabFilter(gsl_vector_complex**, SnapShotArrayPtr, int, int, bool, gsl_vector_complex*, int) {
-  throw j_error("ApabFilter is not part of the oracle build");
-}
 
 namespace {
 
@@ -342,6 +332,76 @@ long btkref_chain(const btkref_chain_cfg* cfg, const float* pcm, long T, const d
     delete bf;
     return nf;
   } catch (std::exception& e) { fprintf(stderr, "btkref_chain: %s\n", e.what()); return -1; }
+}
+
+// analysis banks -> SubbandDS -> ZelinskiPostFilter -> (optional) synthesis, wired like the shipped drivers
+// (src/beamformerDS.cc:150-190, src/superdirectiveBeamformer.cc:150-205).
+//   Ypf : [cap][M][2] post-filtered beamformer output or NULL;  Wpf: [cap][M] post-filter gains (real part of wp1) or NULL
+// Returns post-filter frames emitted; *n_out = synthesis frames emitted.
+long btkref_chain_zelinski(const btkref_chain_cfg* cfg, const float* pcm, long T, const double* h, const double* g,
+                           const double* delays, double alpha, int type, int min_frames, double* Ypf, double* Wpf,
+                           long cap, float* out, long cap_out, long* n_out) {
+  try {
+    const int M = cfg->M, m = cfg->m, r = cfg->r, C = cfg->C;
+    const unsigned D = M >> r;
+    gsl_vector* hp = make_vector(h, (size_t)M * m);
+    SubbandDSPtr bf(new SubbandDS(M, false));
+    for (int c = 0; c < C; c++) {
+      VectorFloatFeatureStreamPtr src(new MemorySampleFeature(pcm + c, T, C, D));
+      VectorComplexFeatureStreamPtr bank(new OverSampledDFTAnalysisBank(src, hp, M, m, r, cfg->dct));
+      bf->setChannel(bank);
+    }
+    gsl_vector_free(hp);
+    gsl_vector* dv = make_vector(delays, C);
+    bf->calcArrayManifoldVectors(cfg->fs, dv);
+    gsl_vector_free(dv);
+    ZelinskiPostFilterPtr pf(new ZelinskiPostFilter((VectorComplexFeatureStreamPtr&)bf, M, alpha, type, min_frames));
+    pf->setBeamformer(bf);
+    long nsyn = 0, nf = 0;
+    // a tee is not needed: the post-filter's own buffer is read after every pull
+    struct Rec : public VectorComplexFeatureStream {
+      ZelinskiPostFilterPtr pf; double* Ypf; double* Wpf; long cap; long n;
+      Rec(ZelinskiPostFilterPtr& p, unsigned M, double* y, double* w, long c)
+          : VectorComplexFeatureStream(M, "Rec"), pf(p), Ypf(y), Wpf(w), cap(c), n(0) {}
+      virtual const gsl_vector_complex* next(int frameX = -5) {
+        if (frameX == _frameX) return _vector;
+        const gsl_vector_complex* y = pf->next(frameX);
+        const unsigned M = size();
+        gsl_vector_complex_memcpy(_vector, y);
+        if (n < cap) {
+          if (Ypf) for (unsigned s = 0; s < M; s++) {
+            gsl_complex z = gsl_vector_complex_get(y, s);
+            Ypf[2 * (n * M + s)] = GSL_REAL(z); Ypf[2 * (n * M + s) + 1] = GSL_IMAG(z);
+          }
+          const gsl_vector_complex* w = pf->getPostFilterWeights();
+          if (Wpf && w) for (unsigned s = 0; s < M; s++) Wpf[n * M + s] = GSL_REAL(gsl_vector_complex_get(w, s));
+        }
+        n++;
+        _increment();
+        return _vector;
+      }
+      virtual void reset() { pf->reset(); VectorComplexFeatureStream::reset(); }
+    };
+    Rec* rec = new Rec(pf, M, Ypf, Wpf, cap);
+    VectorComplexFeatureStreamPtr recp(rec);
+    if (g) {
+      gsl_vector* gp = make_vector(g, (size_t)M * m);
+      OverSampledDFTSynthesisBankPtr syn(new OverSampledDFTSynthesisBank(recp, gp, M, m, r, cfg->dct, cfg->gain));
+      gsl_vector_free(gp);
+      try {
+        for (;;) {
+          const gsl_vector_float* f = syn->next();
+          if (out && nsyn < cap_out) for (unsigned d = 0; d < D; d++) out[nsyn * D + d] = gsl_vector_float_get(f, d);
+          nsyn++;
+        }
+      } catch (jiterator_error&) {}
+    } else {
+      try { for (;;) recp->next(); } catch (jiterator_error&) {}
+    }
+    if (n_out) *n_out = nsyn;
+    nf = rec->n;
+    return nf;
+  } catch (std::exception& e) { fprintf(stderr, "btkref_chain_zelinski: %s\n", e.what()); return -1; }
 }
 
 // SpectralMatrixArray recursion (beamformer.cc:142-163) over all frames of a recording.

@@ -1,0 +1,133 @@
+"""Zelinski post-filter (postfilter/postfilter.cc:30-222, 428-500).
+CPU tier: the numpy restatement against outputs of the compiled reference (tests/golden/zelinski_*.npz, made by
+tests/golden/make_golden_zelinski.py) and against the compiled reference itself where oracle/_ref exists.
+GPU tier: the device kernels (segmented scan of the pair-summed recursion) against the same fixtures and the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import btk_b200
+import btk_oracle as bo
+from conftest import GOLDEN, proto
+
+wl = btk_b200.workloads
+FS = 16000.0
+CASES = sorted(f[len("zelinski_"):-4] for f in os.listdir(GOLDEN) if f.startswith("zelinski_") and f.endswith(".npz"))
+
+
+def _load(name):
+    Z = np.load(os.path.join(GOLDEN, f"zelinski_{name}.npz"))
+    return {k: Z[k] for k in Z.files}
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_outputs(name, prototypes):
+    G = _load(name)
+    M, m, r, dct, C, T = [int(v) for v in G["geo"]]
+    h, g = proto(prototypes, M, m, r)
+    geo = bo.BankGeometry(M, m, r, dct)
+    Wd = bo.ds_weights(G["delays"], FS, M)
+    _, _, Ypf, Wpf, out = bo.chain_zelinski(G["pcm"], h, g, geo, Wd, Wd, float(G["alpha"]), int(G["pf_type"]),
+                                            int(G["min_frames"]))
+    assert Ypf.shape == G["Ypf"].shape
+    assert bo.rel_l2(Ypf, G["Ypf"]) <= 1e-12
+    assert np.abs(Wpf - G["Wpf"]).max() <= 1e-10
+    assert bo.snr_db(out, G["out"]) >= 120.0
+
+
+def test_oracle_matches_compiled_reference_live(prototypes):
+    if not bo.CompiledReference.available():
+        pytest.skip("oracle/_ref not built here")
+    ref = bo.CompiledReference()
+    if not hasattr(ref.lib, "btkref_chain_zelinski"):
+        pytest.skip("oracle/_ref predates the post-filter harness")
+    M, m, r, C, T = 256, 4, 1, 5, 3000
+    h, g = proto(prototypes, M, m, r)
+    geo = bo.BankGeometry(M, m, r, 1)
+    tau = wl.farfield_delays(wl.circular_array(C), 0.8, 1.3)
+    pcm = wl.array_recording(T, tau, seed=77, noise_sigma=900.0)
+    Wd = bo.ds_weights(tau, FS, M)
+    for typ, mf, al in [(2, 0, 0.6), (1, 2, 0.8)]:
+        R = ref.chain_zelinski(pcm, h, g, geo, tau, al, typ, mf)
+        _, _, Ypf, Wpf, out = bo.chain_zelinski(pcm, h, g, geo, Wd, Wd, al, typ, mf)
+        assert bo.rel_l2(Ypf, R["Ypf"]) <= 1e-12
+        assert np.abs(Wpf - R["Wpf"][:, : geo.B]).max() <= 1e-10
+        assert bo.snr_db(out, R["out"]) >= 120.0
+
+
+def test_oracle_rejects_single_channel():
+    with pytest.raises(ValueError):         # jdimension_error, postfilter.cc:62-65
+        bo.zelinski_postfilter(np.zeros((3, 1, 8), complex), np.zeros((3, 8), complex), np.ones((5, 1), complex))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_device_postfilter_matches_reference_outputs(name, prototypes):
+    G = _load(name)
+    M, m, r, dct, C, T = [int(v) for v in G["geo"]]
+    h, g = proto(prototypes, M, m, r)
+    alpha, typ, mf = float(G["alpha"]), int(G["pf_type"]), int(G["min_frames"])
+    plan = btk_b200.Plan(M, m, r, C, h, g, dct=dct)
+    plan.set_ds_weights(FS, G["delays"])
+    snap = plan.analysis(G["pcm"])
+    Y, W = plan.beamform_zelinski(snap, alpha, typ, mf)
+    B = plan.B
+    assert bo.rel_l2(Y, G["Ypf"][:, :B]) <= 1e-4
+    # gains: clamped to [1e-4, 1]; compare absolutely (a gain near the floor has no relative meaning)
+    assert np.abs(W - G["Wpf"]).max() <= 2e-4
+    out = plan.chain_zelinski(G["pcm"], alpha, typ, mf)
+    assert out.shape == G["out"].shape
+    assert bo.snr_db(out, G["out"]) >= 70.0
+    plan.close()
+
+
+@pytest.mark.gpu
+def test_device_postfilter_long_recording_and_mvdr_weights(prototypes):
+    """60 s x 8 channels (BASELINE config 2 geometry): 7507 frames through the 16-segment scan, MVDR weights applied
+    while the time alignment keeps using the array manifold (getBeamformerWeightObject(0)->arrayManifold())."""
+    M, m, r, C, T = 256, 4, 1, 8, 120000
+    h, g = proto(prototypes, M, m, r)
+    geo = bo.BankGeometry(M, m, r, 0)
+    mp = wl.circular_array(C)
+    tau = wl.farfield_delays(mp, np.deg2rad(60), np.deg2rad(90))
+    pcm = wl.array_recording(T, tau, seed=9, noise_sigma=500.0)
+    plan = btk_b200.Plan(M, m, r, C, h, g)
+    plan.set_ds_weights(FS, tau)
+    plan.set_diffuse_noise_model(mp, FS)
+    plan.diag_load(0.1)
+    assert plan.solve_mvdr() == 0
+    Wm = plan.get_weights()
+    ta = bo.ds_weights(tau, FS, M)
+    X, Y, Ypf, Wpf, ref = bo.chain_zelinski(pcm, h, g, geo, Wm, ta, 0.6, 2, 0)
+    Yd, Wd = plan.beamform_zelinski(plan.analysis(pcm), 0.6, 2, 0)
+    assert bo.rel_l2(Yd, Ypf[:, : geo.B]) <= 1e-4
+    assert np.abs(Wd - Wpf).max() <= 2e-4
+    assert bo.snr_db(plan.chain_zelinski(pcm, 0.6, 2, 0), ref) >= 70.0
+    plan.close()
+
+
+@pytest.mark.gpu
+def test_stream_node_mirrors_driver_wiring(prototypes):
+    """src/beamformerDS.cc:150-190 in the drop-in Python nodes: banks -> SubbandDS -> ZelinskiPostFilter -> synthesis."""
+    M, m, r, C, T = 256, 4, 1, 4, 5000
+    h, g = proto(prototypes, M, m, r)
+    geo = bo.BankGeometry(M, m, r, 0)
+    tau = wl.farfield_delays(wl.circular_array(C), 0.9, 1.2)
+    pcm = wl.array_recording(T, tau, seed=31, noise_sigma=700.0)
+    bf = btk_b200.SubbandDSPtr(M, False)
+    for c in range(C):
+        src = btk_b200.SampleFeaturePtr(pcm[:, c], blockLen=geo.D, shiftLen=geo.D, padZeros=True)
+        bf.setChannel(btk_b200.OverSampledDFTAnalysisBankPtr(src, h, M, m, r))
+    bf.calcArrayManifoldVectors(FS, tau)
+    pf = btk_b200.ZelinskiPostFilterPtr(bf, M, 0.6, 2)
+    pf.setBeamformer(bf)
+    syn = btk_b200.OverSampledDFTSynthesisBankPtr(pf, g, M, m, r)
+    out = np.concatenate([np.array(f, copy=True) for f in syn])
+    Wd = bo.ds_weights(tau, FS, M)
+    _, _, Ypf, Wpf, ref = bo.chain_zelinski(pcm, h, g, geo, Wd, Wd, 0.6, 2, 0)
+    assert out.shape == ref.shape and bo.snr_db(out, ref) >= 70.0
+    w_last = pf.getPostFilterWeights()
+    assert w_last is not None and w_last.shape == (M,)
+    with pytest.raises(btk_b200.streams.jdimension_error):      # postfilter.cc:355-358
+        btk_b200.ZelinskiPostFilterPtr(bf, M // 2)
