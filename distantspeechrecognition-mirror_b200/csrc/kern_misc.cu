@@ -3,6 +3,7 @@
 #include <stdlib.h>
 
 #include "launch.h"
+#include "snap_tile.cuh"
 
 namespace btk {
 
@@ -61,31 +62,55 @@ int chain_frames_per_iter(int M, int R, int m) {                   // the fused 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Weight apply on stored snapshots: one thread per (frame, bin), channels innermost and contiguous.
+// Weight apply on stored snapshots (SubbandDS::next / SubbandMVDR::next zdotc loop, beamformer.cc:1181-1194, 2616-2630):
+// a lane group per (frame, bin) item, channels across the lanes (snap_tile.cuh); HBM-bound: 8 C F B + 8 F B bytes.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) btk_beamform_kernel(const cf* __restrict__ snap, const cf* __restrict__ w,
-                                                          cf* __restrict__ Y, long long FB, int B, int C) {
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < FB;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int s = (int)(idx % B);
-    const cf* x = snap + idx * C;
-    const cf* ws = w + (long long)s * C;
-    float re = 0.f, im = 0.f;
-    for (int c = 0; c < C; c++) {
-      const cf a = ws[c], b = x[c];     // conj(a) * b
-      re = fmaf(a.x, b.x, re); re = fmaf(a.y, b.y, re);
-      im = fmaf(a.x, b.y, im); im = fmaf(-a.y, b.x, im);
+template <int GS>
+__global__ void __launch_bounds__(SNAP_THREADS) btk_beamform_kernel(const cf* __restrict__ snap, const cf* __restrict__ w,
+                                                                   cf* __restrict__ Y, long long FB, int B, int C) {
+  const int lg = threadIdx.x % GS;
+  const long long g0 = ((long long)blockIdx.x * SNAP_THREADS + threadIdx.x) / GS;
+  const long long gstride = (long long)gridDim.x * (SNAP_THREADS / GS);
+  const long long n_it = (FB + gstride - 1) / gstride;        // the same trip count for every lane of a warp
+  constexpr int U = 4;                                        // items in flight per group (independent loads)
+  for (long long it = 0; it < n_it; it += U) {
+    float re[U], im[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const long long idx = g0 + (it + u) * gstride;
+      re[u] = 0.f; im[u] = 0.f;
+      if (it + u < n_it && idx < FB) {
+        const int s = (int)(idx % B);
+        const cf* x = snap + idx * C;
+        const cf* ws = w + (long long)s * C;
+        for (int c = lg; c < C; c += GS) {
+          const cf a = __ldg(ws + c), b = x[c];     // conj(a) * b
+          re[u] = fmaf(a.x, b.x, re[u]); re[u] = fmaf(a.y, b.y, re[u]);
+          im[u] = fmaf(a.x, b.y, im[u]); im[u] = fmaf(-a.y, b.x, im[u]);
+        }
+      }
     }
-    Y[idx] = mk(re, im);
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const long long idx = g0 + (it + u) * gstride;
+      const float r = group_sum<GS>(re[u]), i = group_sum<GS>(im[u]);
+      if (it + u < n_it && idx < FB && lg == 0) Y[idx] = mk(r, i);
+    }
   }
 }
 
 cudaError_t launch_beamform(const cf* snap, const cf* w, cf* Y, long long F, int B, int C, cudaStream_t st) {
   const long long FB = F * B;
   if (FB == 0) return cudaSuccess;
-  long long blocks = (FB + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  btk_beamform_kernel<<<(int)blocks, 256, 0, st>>>(snap, w, Y, FB, B, C);
+  const int grid = snap_grid(FB, C);
+  switch (snap_group_size(C)) {
+    case 1: btk_beamform_kernel<1><<<grid, SNAP_THREADS, 0, st>>>(snap, w, Y, FB, B, C); break;
+    case 2: btk_beamform_kernel<2><<<grid, SNAP_THREADS, 0, st>>>(snap, w, Y, FB, B, C); break;
+    case 4: btk_beamform_kernel<4><<<grid, SNAP_THREADS, 0, st>>>(snap, w, Y, FB, B, C); break;
+    case 8: btk_beamform_kernel<8><<<grid, SNAP_THREADS, 0, st>>>(snap, w, Y, FB, B, C); break;
+    case 16: btk_beamform_kernel<16><<<grid, SNAP_THREADS, 0, st>>>(snap, w, Y, FB, B, C); break;
+    default: btk_beamform_kernel<32><<<grid, SNAP_THREADS, 0, st>>>(snap, w, Y, FB, B, C); break;
+  }
   return cudaGetLastError();
 }
 

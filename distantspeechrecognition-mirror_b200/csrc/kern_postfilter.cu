@@ -12,37 +12,58 @@
 // The recursions are linear and share a_n, so the sum over pairs obeys the same recursion: only
 //     S(n) = a_n S(n-1) + (1 - a_n) s(n),  s(n) = sum_{i<j} y_i conj(y_j)   and   P(n), p(n) = sum_i |y_i|^2
 // are carried -- O(C) per (frame, bin) with a running prefix sum instead of O(C^2) state per bin.
-//   kernel 1 (frame- and bin-parallel): beamformer output Y, s, p from the stored snapshots (one pass over them);
+//   kernel 1 (frame- and bin-parallel): beamformer output Y, s, p from the stored snapshots (one coalesced pass);
 //   kernel 2: the first-order recursion over frames as a segmented scan (affine maps compose), then W and Y *= W.
 #include "launch.h"
+#include "snap_tile.cuh"
 
 namespace btk {
 
-__global__ void __launch_bounds__(256) btk_beamform_zelinski_kernel(const cf* __restrict__ snap, const cf* __restrict__ w,
-                                                                   const cf* __restrict__ ta, cf* __restrict__ Y,
-                                                                   float4* __restrict__ stat, long long FB, int B, int C) {
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < FB;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int s = (int)(idx % B);
-    const cf* x = snap + idx * C;
+// A lane group per (frame, bin) item, channels across the lanes in rows of GS (snap_tile.cuh).  The ordered pair sum
+//   s = sum_j (sum_{i<j} y_i) conj(y_j)
+// needs the prefix over the channel index: within a row of GS channels an exclusive group scan, across rows the
+// running total of the earlier rows.
+template <int GS>
+__global__ void __launch_bounds__(SNAP_THREADS) btk_beamform_zelinski_kernel(const cf* __restrict__ snap, const cf* __restrict__ w,
+                                                                            const cf* __restrict__ ta, cf* __restrict__ Y,
+                                                                            float4* __restrict__ stat, long long FB, int B, int C) {
+  const int lg = threadIdx.x % GS;
+  const long long g0 = ((long long)blockIdx.x * SNAP_THREADS + threadIdx.x) / GS;
+  const long long gstride = (long long)gridDim.x * (SNAP_THREADS / GS);
+  const long long n_it = (FB + gstride - 1) / gstride;
+  const int rows = (C + GS - 1) / GS;
+  for (long long it = 0; it < n_it; it++) {
+    const long long idx = g0 + it * gstride;
+    const bool live = idx < FB;
+    const int s = live ? (int)(idx % B) : 0;
+    const cf* x = snap + (live ? idx : 0) * C;
     const cf* ws = w + (long long)s * C;
     const cf* ts = ta + (long long)s * C;
     float yr = 0.f, yi = 0.f;            // beamformer output  sum_c conj(w_c) x_c   (beamformer.cc:1181-1188)
-    float pr = 0.f, pi = 0.f;            // prefix sum of the aligned channels
+    float tr = 0.f, ti = 0.f;            // sum of the aligned channels of the earlier rows
     float sr = 0.f, si = 0.f, p = 0.f;
-    for (int c = 0; c < C; c++) {
-      const cf a = ws[c], t = ts[c], b = x[c];
-      yr = fmaf(a.x, b.x, yr); yr = fmaf(a.y, b.y, yr);
-      yi = fmaf(a.x, b.y, yi); yi = fmaf(-a.y, b.x, yi);
-      const float ar = t.x * b.x + t.y * b.y, ai = t.x * b.y - t.y * b.x;      // y_c = conj(ta_c) x_c
-      // s += (sum_{i<c} y_i) conj(y_c)
-      sr += pr * ar + pi * ai;
+    for (int row = 0; row < rows; row++) {
+      const int c = row * GS + lg;
+      float ar = 0.f, ai = 0.f;
+      if (live && c < C) {
+        const cf a = __ldg(ws + c), t = __ldg(ts + c), b = x[c];
+        yr = fmaf(a.x, b.x, yr); yr = fmaf(a.y, b.y, yr);
+        yi = fmaf(a.x, b.y, yi); yi = fmaf(-a.y, b.x, yi);
+        ar = t.x * b.x + t.y * b.y; ai = t.x * b.y - t.y * b.x;      // y_c = conj(ta_c) x_c
+      }
+      const float pr = tr + group_exscan<GS>(ar, lg), pi = ti + group_exscan<GS>(ai, lg);   // sum_{i<c} y_i
+      sr += pr * ar + pi * ai;           // (sum_{i<c} y_i) conj(y_c)
       si += pi * ar - pr * ai;
       p = fmaf(ar, ar, fmaf(ai, ai, p));
-      pr += ar; pi += ai;
+      tr += group_sum<GS>(ar);
+      ti += group_sum<GS>(ai);
     }
-    Y[idx] = mk(yr, yi);
-    stat[idx] = make_float4(sr, si, p, 0.f);
+    yr = group_sum<GS>(yr); yi = group_sum<GS>(yi);
+    sr = group_sum<GS>(sr); si = group_sum<GS>(si); p = group_sum<GS>(p);
+    if (live && lg == 0) {
+      Y[idx] = mk(yr, yi);
+      stat[idx] = make_float4(sr, si, p, 0.f);
+    }
   }
 }
 
@@ -110,9 +131,14 @@ cudaError_t launch_beamform_zelinski(const cf* snap, const cf* w, const cf* ta, 
   const long long FB = F * B;
   if (FB == 0) return cudaSuccess;
   if (C < 2) return cudaErrorInvalidValue;                  // jdimension_error in the reference (postfilter.cc:62-65)
-  long long blocks = (FB + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  btk_beamform_zelinski_kernel<<<(int)blocks, 256, 0, st>>>(snap, w, ta, Y, stat, FB, B, C);
+  const int grid = snap_grid(FB, C);
+  switch (snap_group_size(C)) {
+    case 2: btk_beamform_zelinski_kernel<2><<<grid, SNAP_THREADS, 0, st>>>(snap, w, ta, Y, stat, FB, B, C); break;
+    case 4: btk_beamform_zelinski_kernel<4><<<grid, SNAP_THREADS, 0, st>>>(snap, w, ta, Y, stat, FB, B, C); break;
+    case 8: btk_beamform_zelinski_kernel<8><<<grid, SNAP_THREADS, 0, st>>>(snap, w, ta, Y, stat, FB, B, C); break;
+    case 16: btk_beamform_zelinski_kernel<16><<<grid, SNAP_THREADS, 0, st>>>(snap, w, ta, Y, stat, FB, B, C); break;
+    default: btk_beamform_zelinski_kernel<32><<<grid, SNAP_THREADS, 0, st>>>(snap, w, ta, Y, stat, FB, B, C); break;
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   btk_zelinski_scan_kernel<<<(B + 31) / 32, 32 * ZEL_SEG, 0, st>>>(stat, Y, Wout, F, B, C, alpha, type, min_frames);
