@@ -8,7 +8,7 @@ The directory name carries a hyphen (it mirrors the upstream repository name); i
 from . import _capi, streams, workloads  # noqa: F401
 from ._capi import BtkError, Plan, device_count, lib  # noqa: F401
 from .streams import (OverSampledDFTAnalysisBankPtr, OverSampledDFTSynthesisBankPtr, SampleFeaturePtr,  # noqa: F401
-                      SubbandDSPtr, SubbandMVDRPtr, ZelinskiPostFilterPtr)
+                      SubbandDSPtr, SubbandGSCPtr, SubbandMVDRPtr, ZelinskiPostFilterPtr)
 
 __all__ = ["Plan", "BtkError", "device_count", "lib", "workloads", "streams", "SampleFeaturePtr",
-           "OverSampledDFTAnalysisBankPtr", "OverSampledDFTSynthesisBankPtr", "SubbandDSPtr", "SubbandMVDRPtr", "ZelinskiPostFilterPtr"]
+           "OverSampledDFTAnalysisBankPtr", "OverSampledDFTSynthesisBankPtr", "SubbandDSPtr", "SubbandGSCPtr", "SubbandMVDRPtr", "ZelinskiPostFilterPtr"]

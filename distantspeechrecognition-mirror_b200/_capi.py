@@ -26,7 +26,8 @@ SYMBOLS = [
     "btkb200_diag_load_bin", "btkb200_divide_nondiagonal", "btkb200_solve_mvdr", "btkb200_analysis",
     "btkb200_beamform", "btkb200_synthesis", "btkb200_covariance", "btkb200_estimate_covariance", "btkb200_chain",
     "btkb200_chain_batch", "btkb200_chain_batch_pcm", "btkb200_convert_pcm", "btkb200_beamform_zelinski",
-    "btkb200_chain_zelinski", "btkb200_beamform_zelinski_dev",
+    "btkb200_chain_zelinski", "btkb200_beamform_zelinski_dev", "btkb200_gsc_calc_weights",
+    "btkb200_gsc_set_active_weights", "btkb200_gsc_zero_active_weights", "btkb200_gsc_get_blocking_matrix", "btkb200_gsc_apply",
     "btkb200_chain_batch_multi", "btkb200_chain_batch_dev", "btkb200_analysis_dev", "btkb200_beamform_dev",
     "btkb200_synthesis_dev", "btkb200_launch_count", "btkb200_sync", "btkb200_host_alloc", "btkb200_host_free",
 ]
@@ -94,6 +95,11 @@ def lib() -> ctypes.CDLL:
     L.btkb200_beamform_zelinski.argtypes = [vp, vp, c_long, c_double, c_int, c_int, vp, vp]
     L.btkb200_chain_zelinski.argtypes = [vp, vp, c_long, c_double, c_int, c_int, vp]
     L.btkb200_beamform_zelinski_dev.argtypes = [vp, vp, c_long, c_double, c_int, c_int, vp, vp, vp]
+    L.btkb200_gsc_calc_weights.argtypes = [vp, c_double, vp, c_uint]
+    L.btkb200_gsc_set_active_weights.argtypes = [vp, c_uint, vp, c_uint]
+    L.btkb200_gsc_zero_active_weights.argtypes = [vp]
+    L.btkb200_gsc_get_blocking_matrix.argtypes = [vp, c_uint, vp]
+    L.btkb200_gsc_apply.argtypes = [vp, c_int]
     L.btkb200_chain_batch_multi.argtypes = [POINTER(vp), c_int, POINTER(vp), POINTER(c_long), c_int, POINTER(vp)]
     L.btkb200_chain_batch_dev.argtypes = [vp, vp, POINTER(c_longlong), POINTER(c_longlong), POINTER(c_longlong), c_int,
                                           vp, vp]
@@ -273,6 +279,26 @@ class Plan:
         if x.ndim != 2 or x.shape[1] != self.C:
             raise BtkError(EINVAL, f"pcm must be [T][{self.C}]")
         self._ck(self._L.btkb200_estimate_covariance(self._h, _p(x), x.shape[0], forget, last_frame, 1 if conjugate else 0))
+
+    # -- SubbandGSC with fixed active weights (beamformer.cc:1296-1447)
+    def gsc_calc_weights(self, fs: float, delays):
+        d = np.ascontiguousarray(delays, dtype=np.float64)
+        self._ck(self._L.btkb200_gsc_calc_weights(self._h, fs, _p(d), d.size))
+
+    def gsc_set_active_weights(self, fbin: int, packed):
+        w = np.ascontiguousarray(packed, dtype=np.float64).ravel()
+        self._ck(self._L.btkb200_gsc_set_active_weights(self._h, fbin, _p(w), w.size))
+
+    def gsc_zero_active_weights(self):
+        self._ck(self._L.btkb200_gsc_zero_active_weights(self._h))
+
+    def gsc_blocking_matrix(self, fbin: int) -> np.ndarray:
+        Bm = np.zeros((self.C, self.C - 1), dtype=np.complex128)
+        self._ck(self._L.btkb200_gsc_get_blocking_matrix(self._h, fbin, _p(Bm)))
+        return Bm
+
+    def gsc_apply(self, normalize: bool = False):
+        self._ck(self._L.btkb200_gsc_apply(self._h, 1 if normalize else 0))
 
     # -- Zelinski post-filter (postfilter/postfilter.cc:30-222, 428-500)
     def beamform_zelinski(self, snap, alpha: float = 0.6, pf_type: int = 2, min_frames: int = 0):

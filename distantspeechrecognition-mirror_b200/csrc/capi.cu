@@ -50,6 +50,8 @@ struct btkb200_plan {
   int has_weights = 0;      // 0 none, 1 DS, 2 user/MVDR
   bool has_manifold = false;
   std::vector<zd> w, wq, Rn;
+  std::vector<zd> gsc_B, gsc_wa;   // SubbandGSC: blocking matrices [B][C][C-1], active weights [B][C-1]
+  bool has_gsc = false;
   std::vector<char> Rn_set;
   // device constants
   float* d_taps_h = nullptr;   // residue-major [D][TS]
@@ -257,6 +259,73 @@ int btkb200_get_manifold(const btkb200_plan* p, double* w) {
   if (!p->has_manifold) return fail(const_cast<btkb200_plan*>(p), BTKB200_ESTATE, "call calcArrayManifoldVectorsX() once");
   for (size_t i = 0; i < p->wq.size(); i++) { w[2 * i] = p->wq[i].real(); w[2 * i + 1] = p->wq[i].imag(); }
   return BTKB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------- GSC (fixed active weights)
+int btkb200_gsc_calc_weights(btkb200_plan* p, double fs, const double* delays, unsigned n) {
+  if (!p || !delays) return BTKB200_EINVAL;
+  if (p->C <= 1) return fail(p, BTKB200_EINVAL, "The number of channels must be > 1 but it is %d", p->C);   // beamformer.cc:536-539
+  int rc = btkb200_set_ds_weights(p, fs, delays, n);
+  if (rc) return rc;
+  const int B = p->geo.B, C = p->C, bs = C - 1;
+  p->gsc_B.assign((size_t)B * C * bs, zd(0, 0));
+  p->gsc_wa.assign((size_t)B * bs, zd(0, 0));
+  std::vector<zd> Bm;
+  for (int s = 0; s < B; s++) {
+    if (!blocking_matrix(&p->wq[(size_t)s * C], C, 1, Bm)) return fail(p, BTKB200_EINVAL, "_calcBlockingMatrix() failed");
+    std::copy(Bm.begin(), Bm.end(), p->gsc_B.begin() + (size_t)s * C * bs);
+  }
+  p->has_gsc = true;
+  return BTKB200_OK;
+}
+
+int btkb200_gsc_set_active_weights(btkb200_plan* p, unsigned bin, const double* packed, unsigned n) {
+  if (!p || !packed) return BTKB200_EINVAL;
+  if (!p->has_gsc) return fail(p, BTKB200_ESTATE, "call calcGSCWeightsX() once");          // beamformer.cc:1427-1430
+  const unsigned bs = (unsigned)p->C - 1;
+  if (n != 2 * bs)
+    return fail(p, BTKB200_EINVAL, "the size of an active weight vector must be %u but it is %u", 2 * bs, n);   // :764-766
+  if ((int)bin >= p->geo.B) return fail(p, BTKB200_EINVAL, "Must be a frequency bin %u < %d", bin, p->geo.B);
+  for (unsigned k = 0; k < bs; k++) p->gsc_wa[(size_t)bin * bs + k] = zd(packed[2 * k], packed[2 * k + 1]);
+  return BTKB200_OK;
+}
+
+int btkb200_gsc_zero_active_weights(btkb200_plan* p) {
+  if (!p) return BTKB200_EINVAL;
+  if (!p->has_gsc) return fail(p, BTKB200_ESTATE, "call calcGSCWeightsX() once");
+  std::fill(p->gsc_wa.begin(), p->gsc_wa.end(), zd(0, 0));
+  return BTKB200_OK;
+}
+
+int btkb200_gsc_get_blocking_matrix(const btkb200_plan* p, unsigned bin, double* Bout) {
+  if (!p || !Bout || (int)bin >= p->geo.B) return BTKB200_EINVAL;
+  if (!p->has_gsc) return fail(const_cast<btkb200_plan*>(p), BTKB200_ESTATE, "call calcGSCWeightsX() once");
+  const size_t n = (size_t)p->C * (p->C - 1);
+  for (size_t i = 0; i < n; i++) { Bout[2 * i] = p->gsc_B[bin * n + i].real(); Bout[2 * i + 1] = p->gsc_B[bin * n + i].imag(); }
+  return BTKB200_OK;
+}
+
+int btkb200_gsc_apply(btkb200_plan* p, int normalize) {
+  if (!p) return BTKB200_EINVAL;
+  if (!p->has_gsc) return fail(p, BTKB200_ESTATE, "call calcGSCWeightsX() once");
+  const int B = p->geo.B, C = p->C, bs = C - 1;
+  p->w = p->wq;                       // bin 0: the quiescent vector alone (beamformer.cc:1320-1324)
+  for (int s = 1; s < B; s++) {
+    double nn = 0;
+    for (int c = 0; c < C; c++) {
+      zd wl(0, 0);                    // (B wa)_c   (zgemv, beamformer.cc:782)
+      for (int k = 0; k < bs; k++) wl += p->gsc_B[((size_t)s * C + c) * bs + k] * p->gsc_wa[(size_t)s * bs + k];
+      const zd v = p->wq[(size_t)s * C + c] - wl;
+      p->w[(size_t)s * C + c] = v;
+      nn += std::norm(v);
+    }
+    if (normalize) {                  // w <- w / (||w|| C)   (calcOutputOfGSC, beamformer.cc:1273-1282)
+      const double d = sqrt(nn) * C;
+      for (int c = 0; c < C; c++) p->w[(size_t)s * C + c] /= d;
+    }
+  }
+  p->has_weights = 2;
+  return upload_weights(p);
 }
 
 // ------------------------------------------------------------------------------------------- MVDR setup

@@ -68,6 +68,32 @@ inline bool build_fft_tables(int M, std::vector<cf>& twa, std::vector<cf>& twb) 
   return false;
 }
 
+// Blocking matrix of a distortionless beamformer (beamformer/beamformer.cc:398-479 _calcBlockingMatrix, NC = 1):
+// Gram-Schmidt on the first C - NC columns of  P = I - conj(v) v^T / ||v||^2  (zgeru, unconjugated rank-1 update), each
+// column projected against the earlier block columns with zdotc (first argument conjugated) and normalised.
+// Bm: [C][C - NC] row major.  false when C <= NC (the reference prints and fails).
+inline bool blocking_matrix(const zd* v, int C, int NC, std::vector<zd>& Bm) {
+  const int bs = C - NC;
+  if (bs <= 0) return false;
+  Bm.assign((size_t)C * bs, zd(0, 0));
+  double nv = 0;
+  for (int i = 0; i < C; i++) nv += std::norm(v[i]);
+  std::vector<zd> vec(C);
+  for (int id = 0; id < bs; id++) {
+    for (int i = 0; i < C; i++) vec[i] = (i == id ? zd(1, 0) : zd(0, 0)) - std::conj(v[i]) * v[id] / nv;
+    for (int jd = 0; jd < id; jd++) {
+      zd ip(0, 0);
+      for (int i = 0; i < C; i++) ip += std::conj(Bm[(size_t)i * bs + jd]) * vec[i];
+      for (int i = 0; i < C; i++) vec[i] -= ip * Bm[(size_t)i * bs + jd];
+    }
+    double nn = 0;
+    for (int i = 0; i < C; i++) nn += std::norm(vec[i]);
+    nn = sqrt(nn);
+    for (int i = 0; i < C; i++) Bm[(size_t)i * bs + id] = vec[i] / nn;
+  }
+  return true;
+}
+
 // Residue-major analysis taps: th[rho*TS + t] = h[rho + D t], t in [0, m R)  (chain_tile.cuh, polyphase_pair).
 inline void build_analysis_taps(const double* h, int M, int m, int R, std::vector<float>& th) {
   const int D = M / R, mR = m * R, TS = tap_stride(mR);

@@ -381,6 +381,68 @@ class SubbandDSPtr(_SubbandBeamformer):
         super().__init__(fftLen, halfBandShift, nm)
 
 
+class SubbandGSCPtr(_SubbandBeamformer):
+    """beamformer/beamformer.h:186-210, beamformer.cc:1296-1447 with FIXED active weights (the adaptive subclasses are out of
+    scope): calcGSCWeights -> setActiveWeights_f per bin -> next().  The effective weights wq - B wa are installed when
+    the utterance is evaluated."""
+
+    def __init__(self, fftLen: int = 512, halfBandShift: bool = False, nm: str = "SubbandGSC"):
+        super().__init__(fftLen, halfBandShift, nm)
+        self._normalize = False
+        self._gsc_dirty = False
+
+    def normalizeWeight(self, flag: bool):
+        self._normalize = bool(flag)
+        self._gsc_dirty = True
+        self._weights_changed()
+
+    def calcGSCWeights(self, sampleRate: float, delaysT):
+        d = np.ascontiguousarray(delaysT, np.float64).ravel()
+        if d.size != self.chanN():
+            raise jdimension_error(f"Number of delays does not match number of channels ({d.size} vs. {self.chanN()}).")
+        try:
+            self._need_plan().gsc_calc_weights(sampleRate, d)
+        except BtkError as e:
+            _raise(e)
+        self._gsc_dirty = True
+        self._weights_changed()
+
+    def setActiveWeights_f(self, fbinX: int, packedWeight):
+        try:
+            if fbinX <= self._fftLen // 2:          # the upper bins are the conjugate mirror and never read (:1326-1352)
+                self._need_plan().gsc_set_active_weights(fbinX, packedWeight)
+        except BtkError as e:
+            _raise(e)
+        self._gsc_dirty = True
+        self._weights_changed()
+
+    def zeroActiveWeights(self):
+        try:
+            self._need_plan().gsc_zero_active_weights()
+        except BtkError as e:
+            _raise(e)
+        self._gsc_dirty = True
+        self._weights_changed()
+
+    def getBlockingMatrix(self, srcX: int, fbinX: int):
+        try:
+            return self._need_plan().gsc_blocking_matrix(fbinX)
+        except BtkError as e:
+            _raise(e)
+
+    def _check_weights(self):
+        if self._gsc_dirty:
+            try:
+                self._need_plan().gsc_apply(self._normalize)
+            except BtkError as e:
+                if e.code == _capi.ESTATE:
+                    raise j_error("call calcGSCWeightsX() once") from None      # beamformer.cc:1307-1310
+                _raise(e)
+            self._gsc_dirty = False
+        if not self._need_plan().has_weights():
+            raise j_error("call calcGSCWeightsX() once")
+
+
 class SubbandMVDRPtr(_SubbandBeamformer):
     """beamformer/beamformer.h:333-388, beamformer.cc:2321-2635."""
 

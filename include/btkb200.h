@@ -122,6 +122,22 @@ int btkb200_covariance(btkb200_plan* plan, const float* snap, long F, const doub
 int btkb200_estimate_covariance(btkb200_plan* plan, const float* pcm, long T, double forget, long last_frame,
                                 int conjugate);
 
+/* ---- SubbandGSC with fixed active weights ------------------------------------------------------- */
+/* SubbandGSC::calcGSCWeights (beamformer.cc:1373-1377): delay-and-sum quiescent vectors + one blocking matrix per bin
+ * (_calcBlockingMatrix, :398-479, NC = 1); the active weights start at zero.  EINVAL for a single channel (:536-539). */
+int btkb200_gsc_calc_weights(btkb200_plan* plan, double sample_rate, const double* delays, unsigned n_delays);
+/* SubbandGSC::setActiveWeights_f (:1425-1433 -> calcSidelobeCancellerP_f :761-783): packed = (re, im) x (C-1).
+ * ESTATE before gsc_calc_weights (j_error), EINVAL for a wrong length (jdimension_error). */
+int btkb200_gsc_set_active_weights(btkb200_plan* plan, unsigned bin, const double* packed, unsigned n);
+/* SubbandGSC::zeroActiveWeights (:1435-1447). */
+int btkb200_gsc_zero_active_weights(btkb200_plan* plan);
+/* SubbandGSC::getBlockingMatrix(0, bin): [C][C-1] complex128, row major. */
+int btkb200_gsc_get_blocking_matrix(const btkb200_plan* plan, unsigned bin, double* B);
+/* Installs the weights SubbandGSC::next applies (:1296-1356, calcOutputOfGSC :1251-1289): w = wq - B wa for bins
+ * 1..M/2 (divided by ||w|| C when normalize != 0, normalizeWeight(true)), wq alone for bin 0.  Afterwards every
+ * beamform / chain entry point computes the GSC output. */
+int btkb200_gsc_apply(btkb200_plan* plan, int normalize);
+
 /* ---- Zelinski post-filter ------------------------------------------------------------------- */
 /* ZelinskiPostFilter::next over a whole recording (postfilter/postfilter.cc:428-500 -> ZelinskiFilter :153-222 ->
  * ZelinskiFilter_f :56-140), with the beamformer as set by setBeamformer(): snapshots [F][B][C] -> beamformer output

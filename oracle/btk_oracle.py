@@ -267,6 +267,41 @@ def chain(pcm: np.ndarray, h: np.ndarray, g: np.ndarray, geo: BankGeometry, W: n
     return X, Y, out.reshape(-1)
 
 
+# --------------------------------------------------------------------------- SubbandGSC (fixed active weights)
+def blocking_matrix(v: np.ndarray, NC: int = 1) -> np.ndarray:
+    """_calcBlockingMatrix (beamformer/beamformer.cc:398-479), loop for loop: P = I - conj(v) v^T / ||v||^2 (zgeru), then
+    Gram-Schmidt of its first C-NC columns with zdotc (first argument conjugated) and unit normalisation.  [C][C-NC]."""
+    v = np.asarray(v, dtype=np.complex128)
+    C = v.size
+    bs = C - NC
+    if bs <= 0:
+        raise ValueError(f"The number of sensors {C} > the number of constraints {NC}")
+    P = np.eye(C, dtype=np.complex128) - np.outer(np.conj(v), v) / (np.linalg.norm(v) ** 2)
+    Bm = np.zeros((C, bs), dtype=np.complex128)
+    for idim in range(bs):
+        vec = P[:, idim].copy()
+        for jdim in range(idim):
+            rvec = Bm[:, jdim]
+            vec = vec - np.vdot(rvec, vec) * rvec
+        Bm[:, idim] = vec / np.linalg.norm(vec)
+    return Bm
+
+
+def gsc_weights(wq: np.ndarray, wa: np.ndarray, normalize: bool = False) -> np.ndarray:
+    """The weights SubbandGSC::next applies (beamformer.cc:1296-1356 with calcOutputOfGSC :1251-1289):
+    bin 0: wq alone; bins 1..M/2: w = wq - B wa, divided by ||w|| C when normalizeWeight is set.
+    wq [B][C] quiescent (delay-and-sum) vectors, wa [B][C-1] active weights."""
+    wq = np.asarray(wq, dtype=np.complex128)
+    W = wq.copy()
+    C = wq.shape[1]
+    for s in range(1, wq.shape[0]):
+        w = wq[s] - blocking_matrix(wq[s]) @ np.asarray(wa[s], dtype=np.complex128)
+        if normalize:
+            w = w / (np.linalg.norm(w) * C)
+        W[s] = w
+    return W
+
+
 # --------------------------------------------------------------------------- Zelinski post-filter
 TYPE_ZELINSKI1_REAL, TYPE_ZELINSKI1_ABS, NO_USE_POST_FILTER = 1, 2, 0      # postfilter/postfilter.h:66-72
 SPECTRAL_FLOOR = 1.0e-4                                                     # postfilter/postfilter.cc:56
@@ -370,6 +405,10 @@ class CompiledReference:
             L.btkref_chain_zelinski.restype = cl
             L.btkref_chain_zelinski.argtypes = [ctypes.POINTER(_ChainCfg), vp, cl, vp, vp, vp, cd, ci, ci, vp, vp, cl, vp,
                                                 cl, ctypes.POINTER(cl)]
+        if hasattr(L, "btkref_chain_gsc"):
+            L.btkref_chain_gsc.restype = cl
+            L.btkref_chain_gsc.argtypes = [ctypes.POINTER(_ChainCfg), vp, cl, vp, vp, vp, vp, ci, vp, cl, vp, cl,
+                                           ctypes.POINTER(cl), vp, vp]
         L.btkref_spectral_matrix.restype = cl
         L.btkref_spectral_matrix.argtypes = [vp, cl, ci, vp, ci, ci, ci, ci, cd, vp]
         L.btkref_error_probe.restype = ci
@@ -453,6 +492,34 @@ class CompiledReference:
         if n < 0 or n > cap:
             raise RuntimeError(f"btkref_chain_zelinski returned {n}")
         res = {"frames": int(n), "Ypf": Ypf[:n].view(np.complex128)[..., 0], "Wpf": Wpf[:n]}
+        if g is not None:
+            res["out"] = out[: nout.value].reshape(-1)
+        return res
+
+    def chain_gsc(self, pcm, h, g, geo: BankGeometry, delays, wa, normalize=False, fs=16000.0, gain=1):
+        """The reference's SubbandGSC (calcGSCWeights + setActiveWeights_f per bin) -> synthesis.
+        wa [B][C-1] complex.  Returns dict(Y [F][M], out, Bm [B][C][C-1], wq [B][C])."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.float32)
+        T, C = pcm.shape
+        h = np.ascontiguousarray(h, dtype=np.float64)
+        g = None if g is None else np.ascontiguousarray(g, dtype=np.float64)
+        delays = np.ascontiguousarray(delays, dtype=np.float64)
+        wa = np.ascontiguousarray(wa, dtype=np.complex128)
+        cfg = _ChainCfg(geo.M, geo.m, geo.r, geo.dct, C, fs, 2, 1, 0, 1e-8, 0.0, -1.0, SSPEED, gain)
+        cap = geo.analysis_frames(T) + 4
+        Y = np.zeros((cap, geo.M, 2), dtype=np.float64)
+        cap_out = geo.nblk(T) + 4
+        out = np.zeros((cap_out, geo.D), dtype=np.float32) if g is not None else None
+        Bm = np.zeros((geo.B, C, C - 1, 2), dtype=np.float64)
+        wq = np.zeros((geo.B, C, 2), dtype=np.float64)
+        nout = ctypes.c_long(0)
+        n = self.lib.btkref_chain_gsc(ctypes.byref(cfg), _dp(pcm), T, _dp(h), _dp(g), _dp(delays), _dp(wa),
+                                      1 if normalize else 0, _dp(Y), cap, _dp(out), cap_out, ctypes.byref(nout), _dp(Bm),
+                                      _dp(wq))
+        if n < 0 or n > cap:
+            raise RuntimeError(f"btkref_chain_gsc returned {n}")
+        res = {"frames": int(n), "Y": Y[:n].view(np.complex128)[..., 0], "Bm": Bm.view(np.complex128)[..., 0],
+               "wq": wq.view(np.complex128)[..., 0]}
         if g is not None:
             res["out"] = out[: nout.value].reshape(-1)
         return res

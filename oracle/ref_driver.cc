@@ -404,6 +404,72 @@ long btkref_chain_zelinski(const btkref_chain_cfg* cfg, const float* pcm, long T
   } catch (std::exception& e) { fprintf(stderr, "btkref_chain_zelinski: %s\n", e.what()); return -1; }
 }
 
+// analysis banks -> SubbandGSC (calcGSCWeights, then setActiveWeights_f for every bin 0..M/2) -> (optional) synthesis.
+//   wa : [B][C-1][2] active weights;  Bout: [B][C][C-1][2] blocking matrices or NULL;  wq: [B][C][2] or NULL
+long btkref_chain_gsc(const btkref_chain_cfg* cfg, const float* pcm, long T, const double* h, const double* g,
+                      const double* delays, const double* wa, int normalize, double* Y, long cap, float* out, long cap_out,
+                      long* n_out, double* Bout, double* wq) {
+  try {
+    const int M = cfg->M, m = cfg->m, r = cfg->r, C = cfg->C;
+    const unsigned D = M >> r, B = M / 2 + 1;
+    gsl_vector* hp = make_vector(h, (size_t)M * m);
+    SubbandGSC* bf = new SubbandGSC(M, false);
+    for (int c = 0; c < C; c++) {
+      VectorFloatFeatureStreamPtr src(new MemorySampleFeature(pcm + c, T, C, D));
+      VectorComplexFeatureStreamPtr bank(new OverSampledDFTAnalysisBank(src, hp, M, m, r, cfg->dct));
+      bf->setChannel(bank);
+    }
+    gsl_vector_free(hp);
+    gsl_vector* dv = make_vector(delays, C);
+    bf->calcGSCWeights(cfg->fs, dv);
+    gsl_vector_free(dv);
+    bf->normalizeWeight(normalize != 0);
+    gsl_vector* pw = gsl_vector_alloc(2 * (C - 1));
+    for (unsigned s = 0; s < B; s++) {
+      for (int k = 0; k < 2 * (C - 1); k++) gsl_vector_set(pw, k, wa[(size_t)s * 2 * (C - 1) + k]);
+      bf->setActiveWeights_f(s, pw);
+      if (Bout) {
+        const gsl_matrix_complex* Bm = bf->getBlockingMatrix(0, s);
+        for (int i = 0; i < C; i++) for (int k = 0; k < C - 1; k++) {
+          gsl_complex z = gsl_matrix_complex_get(Bm, i, k);
+          double* p = Bout + 2 * (((size_t)s * C + i) * (C - 1) + k);
+          p[0] = GSL_REAL(z); p[1] = GSL_IMAG(z);
+        }
+      }
+      if (wq) {
+        const gsl_vector_complex* w = bf->getWeights(s);
+        for (int c = 0; c < C; c++) {
+          gsl_complex z = gsl_vector_complex_get(w, c);
+          wq[2 * (s * C + c)] = GSL_REAL(z); wq[2 * (s * C + c) + 1] = GSL_IMAG(z);
+        }
+      }
+    }
+    gsl_vector_free(pw);
+    RecordingTee* tee = new RecordingTee(bf, M, C, Y, NULL, cap);
+    VectorComplexFeatureStreamPtr teep(tee);
+    long nsyn = 0;
+    if (g) {
+      gsl_vector* gp = make_vector(g, (size_t)M * m);
+      OverSampledDFTSynthesisBankPtr syn(new OverSampledDFTSynthesisBank(teep, gp, M, m, r, cfg->dct, cfg->gain));
+      gsl_vector_free(gp);
+      try {
+        for (;;) {
+          const gsl_vector_float* f = syn->next();
+          if (out && nsyn < cap_out) for (unsigned d = 0; d < D; d++) out[nsyn * D + d] = gsl_vector_float_get(f, d);
+          nsyn++;
+        }
+      } catch (jiterator_error&) {}
+    } else {
+      try { for (;;) teep->next(); } catch (jiterator_error&) {}
+    }
+    if (n_out) *n_out = nsyn;
+    long nf = tee->frames();
+    bf->clearChannel();
+    delete bf;
+    return nf;
+  } catch (std::exception& e) { fprintf(stderr, "btkref_chain_gsc: %s\n", e.what()); return -1; }
+}
+
 // SpectralMatrixArray recursion (beamformer.cc:142-163) over all frames of a recording.
 // Rout: [M][C][C][2].  Returns frames consumed.
 long btkref_spectral_matrix(const float* pcm, long T, int C, const double* h, int M, int m, int r, int dct,
