@@ -332,6 +332,15 @@ class SubbandBeamformer : public VectorComplexFeatureStream {
     for (c = 0; c < C; c++) for (size_t t = 0; t < xs[c].size(); t++) pcm[t * C + c] = xs[c][t];
   }
   btkb200_plan* plan() { return need_plan(); }
+  // beamformer output multiplied by the Zelinski gain for every frame of the utterance (ZelinskiPostFilter::next)
+  void post_filter(double alpha, int type, int minFrames, std::vector<float>& Y, std::vector<float>& W, int& F) {
+    if (_F < 0) evaluate();
+    const unsigned B = _fftLen / 2 + 1;
+    Y.assign((size_t)_F * B * 2 + 2, 0.f);
+    W.assign((size_t)_F * B + 1, 0.f);
+    if (_F > 0) check(btkb200_beamform_zelinski(_plan.get(), &_snapshots[0], _F, alpha, type, minFrames, &Y[0], &W[0]), _plan.get());
+    F = _F;
+  }
   void require_weights() {
     if (!need_plan() || !_plan.has_weights()) throw j_error("call calcArrayManifoldVectorsX() once\n");   // :1140-1143
   }
@@ -456,6 +465,102 @@ class SubbandMVDR : public SubbandDS {
 typedef std::shared_ptr<SubbandDS> SubbandDSPtr;
 typedef std::shared_ptr<SubbandMVDR> SubbandMVDRPtr;
 
+// SubbandGSC with FIXED active weights (beamformer/beamformer.h:186-210, beamformer.cc:1296-1447); the adaptive
+// subclasses (SubbandGSCRLS, ...) are out of scope.  The effective weights wq - B wa are installed before evaluation.
+class SubbandGSC : public SubbandDS {
+ public:
+  SubbandGSC(unsigned fftLen = 512, bool halfBandShift = false, const String& nm = "SubbandGSC")
+      : SubbandDS(fftLen, halfBandShift, nm), _normalizeWeight(false), _dirty(false) {
+    _bm = new btk_matrix_complex(); _bm->size1 = _bm->size2 = _bm->tda = 0; _bm->data = 0; _bm->block = 0; _bm->owner = 0;
+  }
+  ~SubbandGSC() { delete[] _bm->data; delete _bm; }
+  void normalizeWeight(bool flag) { _normalizeWeight = flag; _dirty = true; _F = -1; }
+  void calcGSCWeights(double sampleRate, const btk_vector* delaysT) {          // :1373-1377
+    if (delaysT->size != chanN())
+      throw jdimension_error("Number of delays does not match number of channels (%d vs. %d).\n", (int)delaysT->size, (int)chanN());
+    std::vector<double> d(delaysT->size);
+    for (size_t i = 0; i < d.size(); i++) d[i] = delaysT->data[i * delaysT->stride];
+    check(btkb200_gsc_calc_weights(need_plan(), sampleRate, &d[0], (unsigned)d.size()), _plan.get());
+    _dirty = true; _F = -1;
+  }
+  void setActiveWeights_f(unsigned fbinX, const btk_vector* packedWeight) {   // :1425-1433
+    std::vector<double> w(packedWeight->size);
+    for (size_t i = 0; i < w.size(); i++) w[i] = packedWeight->data[i * packedWeight->stride];
+    if (fbinX <= _fftLen2) check(btkb200_gsc_set_active_weights(need_plan(), fbinX, &w[0], (unsigned)w.size()), _plan.get());
+    _dirty = true; _F = -1;
+  }
+  void zeroActiveWeights() { check(btkb200_gsc_zero_active_weights(need_plan()), _plan.get()); _dirty = true; _F = -1; }   // :1435-1447
+  btk_matrix_complex* getBlockingMatrix(unsigned /*srcX*/, unsigned fbinX) {
+    const unsigned C = chanN();
+    if (_bm->size1 != C) { delete[] _bm->data; _bm->data = new double[2 * (size_t)C * (C - 1)](); _bm->size1 = C; _bm->size2 = _bm->tda = C - 1; }
+    check(btkb200_gsc_get_blocking_matrix(need_plan(), fbinX, _bm->data), _plan.get());
+    return _bm;
+  }
+  virtual const btk_vector_complex* next(int frameX = -5) {
+    if (_dirty) { check(btkb200_gsc_apply(need_plan(), _normalizeWeight ? 1 : 0), _plan.get()); _dirty = false; _F = -1; }
+    return SubbandDS::next(frameX);
+  }
+  // the fused synthesis path asks for the weights through plan(): make sure they are current
+  void commit() { if (_dirty) { check(btkb200_gsc_apply(need_plan(), _normalizeWeight ? 1 : 0), _plan.get()); _dirty = false; } }
+
+ protected:
+  bool _normalizeWeight, _dirty;
+  btk_matrix_complex* _bm;
+};
+typedef std::shared_ptr<SubbandGSC> SubbandGSCPtr;
+
+// ZelinskiPostFilter (postfilter/postfilter.h:95-126, postfilter.cc:340-500): the node both shipped drivers put between the
+// beamformer and the synthesis bank.  `output` must be the SubbandDS / SubbandMVDR also passed to setBeamformer().
+enum PostfilterType { TYPE_ZELINSKI1_REAL = 0x01, TYPE_ZELINSKI1_ABS = 0x02, TYPE_APAB = 0x04, TYPE_ZELINSKI2 = 0x08, NO_USE_POST_FILTER = 0x00 };
+class ZelinskiPostFilter : public VectorComplexFeatureStream {
+ public:
+  ZelinskiPostFilter(VectorComplexFeatureStreamPtr& output, unsigned fftLen, double alpha = 0.6, int type = 2, int minFrames = 0,
+                     const String& nm = "ZelinskPostFilter")
+      : VectorComplexFeatureStream(fftLen, nm), _samp(output), _alpha(alpha), _type(type), _minFrames(minFrames), _F(-1) {
+    if (output->size() != fftLen)      // postfilter.cc:355-358
+      throw jdimension_error("Input block length (%d) != fftLen (%d)\n", (int)output->size(), (int)fftLen);
+    _wp1 = new btk_vector_complex(); _wp1->size = fftLen; _wp1->stride = 1; _wp1->data = new double[2 * (size_t)fftLen](); _wp1->block = 0; _wp1->owner = 1;
+  }
+  ~ZelinskiPostFilter() { delete[] _wp1->data; delete _wp1; }
+  void setBeamformer(SubbandDSPtr& beamformer) { _bf = beamformer; }
+  const btk_vector_complex* getPostFilterWeights() { return (_F < 0 || _frameX < 0) ? 0 : _wp1; }
+  virtual const btk_vector_complex* next(int frameX = -5) {
+    if (frameX == _frameX && _frameX >= 0) return _vector;
+    if (_F < 0) evaluate();
+    const int t = _frameX + 1;
+    if (t >= _F) { _endOfSamples = true; throw jiterator_error("end of samples!"); }
+    const unsigned M = size(), B = M / 2 + 1;
+    const float* half = &_Y[(size_t)t * B * 2];
+    const float* wh = &_W[(size_t)t * B];
+    for (unsigned s = 0; s < B; s++) {
+      _vector->data[2 * s] = half[2 * s]; _vector->data[2 * s + 1] = half[2 * s + 1];
+      _wp1->data[2 * s] = wh[s]; _wp1->data[2 * s + 1] = 0.0;
+    }
+    for (unsigned s = 1; s < M / 2; s++) {                     // postfilter.cc:185-186, 213-216
+      _vector->data[2 * (M - s)] = half[2 * s]; _vector->data[2 * (M - s) + 1] = -half[2 * s + 1];
+      _wp1->data[2 * (M - s)] = wh[s]; _wp1->data[2 * (M - s) + 1] = 0.0;
+    }
+    _increment();
+    return _vector;
+  }
+  virtual void reset() { _samp->reset(); VectorComplexFeatureStream::reset(); _F = -1; }
+
+ private:
+  void evaluate() {
+    if (!_bf) throw j_error("set beamformer's weights \n");   // postfilter.cc:449-452
+    if (static_cast<VectorComplexFeatureStream*>(_bf.get()) != _samp.get())
+      throw j_error("the B200 post-filter expects its input stream to be the beamformer given to setBeamformer()");
+    _bf->post_filter(_alpha, _type, _minFrames, _Y, _W, _F);
+  }
+  VectorComplexFeatureStreamPtr _samp;
+  SubbandDSPtr _bf;
+  double _alpha;
+  int _type, _minFrames, _F;
+  std::vector<float> _Y, _W;
+  btk_vector_complex* _wp1;
+};
+typedef std::shared_ptr<ZelinskiPostFilter> ZelinskiPostFilterPtr;
+
 // ---- OverSampledDFTSynthesisBank ---------------------------------------------------------------------------------
 class OverSampledDFTSynthesisBank : public OverSampledDFTFilterBank, public VectorFloatFeatureStream {
  public:
@@ -503,6 +608,7 @@ class OverSampledDFTSynthesisBank : public OverSampledDFTFilterBank, public Vect
     unsigned m, r, dct;
     if (bf && bf->frameX() < 0 && bf->fftLen() == _M && bf->all_own_banks(m, r, dct) && m == _m && r == _r && dct == _dct) {
       // ---- analysis -> weights -> synthesis as ONE kernel
+      if (SubbandGSC* gsc = dynamic_cast<SubbandGSC*>(bf)) gsc->commit();   // install wq - B wa before the weights are read
       bf->require_weights();
       const unsigned C = bf->chanN(), B = _M / 2 + 1;
       need_plan(C, &bf->analysis_prototype()[0]);

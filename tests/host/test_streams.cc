@@ -3,7 +3,10 @@
 // jiterator_error, write what came out.  The Python tests compare the files with the oracle.
 //
 //   test_streams errors                      host-only checks (no GPU needed): exception types and codes
-//   test_streams chain <in.bin> <out.bin>    DS (mode 0) or MVDR (mode 1) chain through the stream nodes
+//   test_streams chain <in.bin> <out.bin>    DS (mode 0) or MVDR (mode 1) chain through the stream nodes;
+//                                            mode 2: DS -> ZelinskiPostFilter -> synthesis (src/beamformerDS.cc:150-190);
+//                                            mode 3: SubbandGSC with fixed active weights wa[s][k] = 0.05 (cos(s+k) + j sin(2s-k))
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -60,7 +63,7 @@ int main(int argc, char** argv) {
   fclose(f);
   try {
     btk_vector hv = make_vec(h), gv = make_vec(g), tv = make_vec(tau);
-    std::shared_ptr<SubbandDS> bf(mode == 1 ? new SubbandMVDR(M) : new SubbandDS(M));
+    std::shared_ptr<SubbandDS> bf(mode == 1 ? new SubbandMVDR(M) : mode == 3 ? new SubbandGSC(M) : new SubbandDS(M));
     for (int c = 0; c < C; c++) {
       std::vector<float> x(T);
       for (int t = 0; t < T; t++) x[t] = pcm[(size_t)t * C + c];
@@ -68,7 +71,44 @@ int main(int argc, char** argv) {
       VectorComplexFeatureStreamPtr analysis(new OverSampledDFTAnalysisBank(sample, &hv, M, m, r, dct));
       bf->setChannel(analysis);
     }
-    bf->calcArrayManifoldVectors(fs, &tv);
+    if (mode == 3) {
+      SubbandGSC* gsc = static_cast<SubbandGSC*>(bf.get());
+      gsc->calcGSCWeights(fs, &tv);
+      std::vector<double> pw(2 * (C - 1));
+      btk_vector pv = make_vec(pw);
+      for (int s = 0; s <= M / 2; s++) {
+        for (int k = 0; k < C - 1; k++) { pw[2 * k] = 0.05 * cos((double)(s + k)); pw[2 * k + 1] = 0.05 * sin((double)(2 * s - k)); }
+        gsc->setActiveWeights_f(s, &pv);
+      }
+      if (gsc->getBlockingMatrix(0, 1)->size2 != (size_t)C - 1) return 3;
+    } else {
+      bf->calcArrayManifoldVectors(fs, &tv);
+    }
+    if (mode == 2 || mode == 3) {
+      VectorComplexFeatureStreamPtr bfs = bf;
+      VectorComplexFeatureStreamPtr last = bfs;
+      ZelinskiPostFilterPtr pf;
+      if (mode == 2) {
+        pf.reset(new ZelinskiPostFilter(bfs, M, 0.6, TYPE_ZELINSKI1_ABS));
+        pf->setBeamformer(bf);
+        last = pf;
+      }
+      OverSampledDFTSynthesisBank synth(last, &gv, M, m, r, dct);
+      std::vector<float> out;
+      for (;;) {
+        const btk_vector_float* b;
+        try { b = synth.next(); } catch (jiterator_error&) { break; }
+        out.insert(out.end(), b->data, b->data + b->size);
+      }
+      if (mode == 2 && (!pf->getPostFilterWeights() || pf->getPostFilterWeights()->size != (size_t)M)) return 3;
+      FILE* o = fopen(argv[3], "wb");
+      int oh[4] = {(int)out.size(), synth.fused() ? 1 : 0, 0, 0};
+      fwrite(oh, sizeof(int), 4, o);
+      fwrite(out.data(), 4, out.size(), o);
+      fclose(o);
+      printf("chain ok: %zu samples, mode=%d\n", out.size(), mode);
+      return 0;
+    }
     if (mode == 1) {
       SubbandMVDR* mv = static_cast<SubbandMVDR*>(bf.get());
       btk_matrix mp; mp.size1 = C; mp.size2 = 3; mp.tda = 3; mp.data = mic.data(); mp.block = 0; mp.owner = 0;

@@ -49,7 +49,7 @@ def run_chain(exe, tmp_path, M, m, r, dct, C, T, mode, h, g, tau, mic, load, pcm
     n_out, fused, n_y, n_push = struct.unpack("4i", raw[:16])
     off = 16
     out = np.frombuffer(raw, np.float32, n_out, off); off += 4 * n_out
-    Y = np.frombuffer(raw, np.float64, n_y, off).view(np.complex128).reshape(4, M); off += 8 * n_y
+    Y = np.frombuffer(raw, np.float64, n_y, off).view(np.complex128).reshape(-1, M); off += 8 * n_y
     pushed = np.frombuffer(raw, np.float32, n_push, off)
     return out, fused, Y, pushed
 
@@ -73,3 +73,35 @@ def test_cpp_stream_chain_matches_oracle(cfg, exe, tmp_path, prototypes):
     assert bo.rel_l2(Y4, Y[:4]) <= 1e-4                 # the beamformer node alone: full-M Hermitian spectra
     # push-style synthesis (inputSourceVector + next): the same first frames, priming quirk included
     assert pushed.size == 6 * geo.D and bo.snr_db(pushed, ref[: 6 * geo.D]) >= 70.0
+
+
+@pytest.mark.gpu
+def test_cpp_driver_with_zelinski_postfilter(exe, tmp_path, prototypes):
+    """src/beamformerDS.cc:150-190 through the C++ drop-in nodes: banks -> SubbandDS -> ZelinskiPostFilter -> synthesis."""
+    M, m, r, dct, C, T = 256, 4, 1, 0, 4, 8000
+    h, g = proto(prototypes, M, m, r)
+    mp = wl.linear_array(C, 41.0)
+    tau = wl.farfield_delays(mp, np.deg2rad(30), np.deg2rad(90))
+    pcm = wl.array_recording(T, tau, seed=5, noise_sigma=700.0)
+    out, fused, _, _ = run_chain(exe, tmp_path, M, m, r, dct, C, T, 2, h, g, tau, mp, 0.0, pcm)
+    geo = bo.BankGeometry(M, m, r, dct)
+    wq = bo.ds_weights(tau, FS, M)
+    ref = bo.chain_zelinski(pcm, h, g, geo, wq, wq, 0.6, 2, 0)[4]
+    assert fused == 0 and out.shape == ref.shape and bo.snr_db(out, ref) >= 70.0
+
+
+@pytest.mark.gpu
+def test_cpp_gsc_chain(exe, tmp_path, prototypes):
+    """SubbandGSC (calcGSCWeights + setActiveWeights_f per bin) -> synthesis through the C++ nodes, fused kernel."""
+    M, m, r, dct, C, T = 512, 2, 2, 0, 5, 6000
+    h, g = proto(prototypes, M, m, r)
+    mp = wl.linear_array(C, 41.0)
+    tau = wl.farfield_delays(mp, np.deg2rad(30), np.deg2rad(90))
+    pcm = wl.array_recording(T, tau, seed=6, noise_sigma=700.0)
+    out, fused, _, _ = run_chain(exe, tmp_path, M, m, r, dct, C, T, 3, h, g, tau, mp, 0.0, pcm)
+    geo = bo.BankGeometry(M, m, r, dct)
+    s_, k_ = np.meshgrid(np.arange(geo.B), np.arange(C - 1), indexing="ij")
+    wa = 0.05 * (np.cos(s_ + k_) + 1j * np.sin(2 * s_ - k_))
+    W = bo.gsc_weights(bo.ds_weights(tau, FS, M), wa, False)
+    ref = bo.chain(pcm, h, g, geo, W)[2]
+    assert fused == 1 and out.shape == ref.shape and bo.snr_db(out, ref) >= 70.0
