@@ -9,25 +9,34 @@
 // so a 64-channel bin is a 128 x 128 x F GEMM whose A and B operands are the SAME shared-memory tile.
 //
 // tcgen05.mma kind::tf32 keeps 10 mantissa bits of its inputs; to stay inside the 1e-4 parity gate with margin the
-// inputs are split  z = hi + lo  (both rounded to TF32 by cvt.rna), and  P += hi hi^T + hi lo^T + lo hi^T  (the
-// dropped lo lo^T term is 2^-22 relative): three MMAs per 8 frames, FP32 accumulation in TMEM.
+// inputs are split  z = hi + lo  (both exactly representable in TF32), and  P = hi hi^T + hi lo^T + lo hi^T  (the
+// dropped lo lo^T term is 2^-22 relative).  The last two terms are transposes of each other, so the B operand is the
+// stacked tile [hi; lo] (N = 256) and ONE MMA per 8 frames yields  D = [ HH | S ],  HH = hi hi^T,  S = hi lo^T  in 256
+// TMEM columns; the epilogue forms  P = HH + S + S^T  (S^T through shared memory).  Against three 128 x 128 MMAs this
+// is 2/3 of the tensor time and half of the operand bytes fetched from shared memory, which is what bounds an
+// M = N = 128 tile (8 KB of operands per 64 cycles of math = the full 128 B/clk of the shared-memory pipe).
 //
 // CTA = (bin, frame slice), 256 threads.  Per chunk of 32 frames every thread reads four consecutive frames of four
 // real columns (16-byte loads, one 512-byte snapshot row per warp), scales, splits, transposes in registers and writes
 // 16-byte words into the two tiles, which are laid out directly in the canonical K-major no-swizzle UMMA layout
 // (8 x 16-byte core matrices):
-//     tile[k4][rho]  (16-byte units),  k4 = frame / 4,  rho = row  ->  LBO (K direction) = 2048 B, SBO (8-row
-// groups) = 128 B.  The next chunk's rows are requested before the current one is processed.  Two stages: the MMAs of
+//     tile[k4][row]  (16-byte units),  k4 = frame / 4,  row = rho (hi) or 128 + rho (lo)  ->  LBO (K direction) =
+// 4096 B, SBO (8-row groups) = 128 B; A reads rows 0..127, B rows 0..255 of the same slab.  The next chunk's rows are requested before the current one is processed.  Two stages: the MMAs of
 // chunk i (issued by one thread, completion signalled through tcgen05.commit on an mbarrier) overlap the staging of
-// chunk i+1.  Fewer than 64 channels: several consecutive bins share one tile (see G below).  Epilogue: tcgen05.ld of the 128 x 128 accumulator (thread = row),
-// pairing of rows (2a, 2a+1) with one shuffle per column pair, fp64 atomics into R (slices of frames are summed there).
+// chunk i+1.  Fewer than 64 channels: several consecutive bins share one tile (see G below).  Epilogue: tcgen05.ld of
+// the accumulator (thread = row), S^T through shared memory, pairing of the (Re, Im) rows with one shuffle per column
+// pair; one frame slice per tile writes R directly, several slices are merged with fp64 atomics.
+#include <stdlib.h>
+
 #include "launch.h"
 
 namespace btk {
 
 #define COV_TC_KC 32                      // frames per stage
-#define COV_TC_TILE_BYTES (128 * COV_TC_KC * 4)
-#define COV_TC_STAGE_BYTES (2 * COV_TC_TILE_BYTES)
+#define COV_TC_STAGE_BYTES (256 * COV_TC_KC * 4)   // [KC/4][256 rows] 16-byte words: hi rows 0..127, lo rows 128..255
+#define COV_TC_LBO ((256 * 16))                     // bytes between the two 16-byte K groups of one MMA
+#define COV_TC_ST_STRIDE 129                       // floats per row of the S^T exchange (conflict-free both ways)
+#define COV_TC_SMEM (128 * COV_TC_ST_STRIDE * 4 > 2 * COV_TC_STAGE_BYTES ? 128 * COV_TC_ST_STRIDE * 4 : 2 * COV_TC_STAGE_BYTES)
 #define COV_TC_THREADS 256
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -59,7 +68,7 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr, uint32_t lb
   return d;
 }
 
-// D[tmem] (+)= A[smem] * B[smem]^T, 128 x 128 x 8, TF32 inputs, FP32 accumulate
+// D[tmem] (+)= A[smem] * B[smem]^T, M x N x 8 as the instruction descriptor says, TF32 inputs, FP32 accumulate
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -69,11 +78,11 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       : "memory");
 }
 
-__device__ __forceinline__ float to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
+// TF32 split with integer arithmetic (cvt.rna.tf32.f32 issues on a slow conversion pipe: 32 of them per thread and
+// chunk cost as much as the chunk's MMAs): hi = z rounded to nearest at bit 13 (add half an ulp, clear 13 bits), so
+// |z - hi| <= 2^-11 |z|; lo = (z - hi) truncated to TF32 (error <= 2^-11 |lo| <= 2^-22 |z|).
+__device__ __forceinline__ float tf32_round(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
 __global__ void __launch_bounds__(COV_TC_THREADS) btk_covariance_tc_kernel(const cf* __restrict__ snap, const double* __restrict__ wt,
                                                                           double2* __restrict__ Rout, long long F, int B, int C,
@@ -98,7 +107,7 @@ __global__ void __launch_bounds__(COV_TC_THREADS) btk_covariance_tc_kernel(const
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(&s_tmem)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&s_tmem)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -106,9 +115,9 @@ __global__ void __launch_bounds__(COV_TC_THREADS) btk_covariance_tc_kernel(const
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = s_tmem;
 
-  // instruction descriptor: D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2), both K-major, N = 128 (>>3 at
+  // instruction descriptor: D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2), both K-major, N = 256 (>>3 at
   // bit 17), M = 128 (>>4 at bit 24)
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
   const uint32_t smem_base = smem_u32(smem);
 
   // Staging map: warp w owns frames 4w .. 4w+3 of the chunk (one 16-byte K group), lane l the real columns 4l .. 4l+3:
@@ -165,8 +174,8 @@ __global__ void __launch_bounds__(COV_TC_THREADS) btk_covariance_tc_kernel(const
       }
     }
     if (ch >= 2) mbar_wait(smem_u32(&s_bar[st]), (uint32_t)(((ch >> 1) - 1) & 1));   // MMAs of chunk ch-2 have read this stage
-    float4* hi = reinterpret_cast<float4*>(smem + st * COV_TC_STAGE_BYTES) + warp * 128;
-    float4* lo = reinterpret_cast<float4*>(smem + st * COV_TC_STAGE_BYTES + COV_TC_TILE_BYTES) + warp * 128;
+    float4* hi = reinterpret_cast<float4*>(smem + st * COV_TC_STAGE_BYTES) + warp * 256;
+    float4* lo = hi + 128;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       float z[4], h4[4], l4[4];
@@ -175,7 +184,7 @@ __global__ void __launch_bounds__(COV_TC_THREADS) btk_covariance_tc_kernel(const
       z[2] = (j == 0 ? x[2].x : j == 1 ? x[2].y : j == 2 ? x[2].z : x[2].w) * w[2];
       z[3] = (j == 0 ? x[3].x : j == 1 ? x[3].y : j == 2 ? x[3].z : x[3].w) * w[3];
 #pragma unroll
-      for (int i = 0; i < 4; i++) { h4[i] = to_tf32(z[i]); l4[i] = to_tf32(z[i] - h4[i]); }
+      for (int i = 0; i < 4; i++) { h4[i] = tf32_round(z[i]); l4[i] = tf32_trunc(z[i] - h4[i]); }
       hi[rho0 + 8 * j] = make_float4(h4[0], h4[1], h4[2], h4[3]);
       lo[rho0 + 8 * j] = make_float4(l4[0], l4[1], l4[2], l4[3]);
     }
@@ -185,14 +194,12 @@ __global__ void __launch_bounds__(COV_TC_THREADS) btk_covariance_tc_kernel(const
     __syncthreads();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_hi = smem_base + st * COV_TC_STAGE_BYTES, a_lo = a_hi + COV_TC_TILE_BYTES;
+      const uint32_t slab = smem_base + st * COV_TC_STAGE_BYTES;
 #pragma unroll
       for (int k8 = 0; k8 < COV_TC_KC / 8; k8++) {
-        const uint64_t dh = umma_desc_kmajor(a_hi + k8 * 2 * 2048, 2048, 128);
-        const uint64_t dl = umma_desc_kmajor(a_lo + k8 * 2 * 2048, 2048, 128);
-        umma_tf32(tmem, dh, dh, idesc, (ch | k8) != 0);
-        umma_tf32(tmem, dh, dl, idesc, 1);
-        umma_tf32(tmem, dl, dh, idesc, 1);
+        // A = rows 0..127 (hi), B = rows 0..255 ([hi; lo]) of the same K slab: D = [hi hi^T | hi lo^T]
+        const uint64_t d = umma_desc_kmajor(slab + k8 * 2 * COV_TC_LBO, COV_TC_LBO, 128);
+        umma_tf32(tmem, d, d, idesc, (ch | k8) != 0);
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_bar[st]))
                    : "memory");
@@ -205,8 +212,35 @@ __global__ void __launch_bounds__(COV_TC_THREADS) btk_covariance_tc_kernel(const
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
 
+#define COV_TC_LD32(u, taddr)                                                                                      \
+  asm volatile(                                                                                                    \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                    \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                    \
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                    \
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), \
+        "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),      \
+        "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),     \
+        "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])                   \
+      : "r"(taddr)                                                                                                 \
+      : "memory");                                                                                                 \
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory")
+
+  // ---- epilogue.  TMEM lane = UMMA row rho = 32 warp + t (warps 0..3); columns 0..127 hold HH[rho][.], 128..255 S[rho][.].
+  // Pass 1: S goes to shared memory (the stage buffers are free: every MMA has completed) so that pass 2 can read S^T.
+  float* sT = reinterpret_cast<float*>(smem);
+  const int row = 32 * warp + lane;
   if (warp < 4) {
-    // TMEM lane = UMMA row rho = 32 warp + t:  real column = 4 ((t & 7) + 8 warp) + (t >> 3)   (inverse of the staging map)
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      uint32_t u[32];
+      COV_TC_LD32(u, tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(128 + c0));
+#pragma unroll
+      for (int tt = 0; tt < 32; tt++) sT[row * COV_TC_ST_STRIDE + c0 + tt] = __uint_as_float(u[tt]);
+    }
+  }
+  __syncthreads();
+  if (warp < 4) {
+    // real column of this row = 4 ((t & 7) + 8 warp) + (t >> 3)   (inverse of the staging map)
     const int t = lane;
     const int col = 4 * ((t & 7) + 8 * warp) + (t >> 3);
     const int ga = col / (2 * Cp), a = (col % (2 * Cp)) >> 1, comp = col & 1;   // bin of the tile, channel; even columns
@@ -214,37 +248,36 @@ __global__ void __launch_bounds__(COV_TC_THREADS) btk_covariance_tc_kernel(const
     const float sgn = (conj != 0) == (comp == 0) ? 1.f : -1.f;
     double* Rs = reinterpret_cast<double*>(Rout + (long long)(s + ga) * C * C);
     const bool row_live = a < C && s + ga < B;
+    const bool single = gridDim.y == 1;      // the only slice of this tile: R is written, not merged
 #pragma unroll 1
     for (int c0 = 0; c0 < 128; c0 += 32) {
-      uint32_t u[32];
-      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
-            "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
-            "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
-            "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
-          : "r"(taddr)
-          : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      uint32_t u[32], v[32];
+      COV_TC_LD32(u, tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0);
+      COV_TC_LD32(v, tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(128 + c0));
+      float P[32];
+#pragma unroll
+      for (int tt = 0; tt < 32; tt++)
+        P[tt] = __uint_as_float(u[tt]) + (__uint_as_float(v[tt]) + sT[(c0 + tt) * COV_TC_ST_STRIDE + row]);
       // accumulator column n' = c0 + tt holds real column 4 ((tt & 7) + 8 (c0 >> 5)) + (tt >> 3); the (2b, 2b+1) pair
       // of channel b sits at tt and tt + 8 with (tt >> 3) even
 #pragma unroll
       for (int tt = 0; tt < 32; tt++) {
         if ((tt >> 3) & 1) continue;
-        const float v0 = __uint_as_float(u[tt]), v1 = __uint_as_float(u[tt + 8]);
+        const float v0 = P[tt], v1 = P[tt + 8];
         const float pv1 = __shfl_xor_sync(0xffffffffu, v1, 8);
         const int colb = 4 * ((tt & 7) + 8 * (c0 >> 5)) + (tt >> 3);      // even real column of the pair
         const int gb = colb / (2 * Cp), b = (colb % (2 * Cp)) >> 1;
-        if (row_live && gb == ga && b < C) atomicAdd(Rs + 2 * ((long long)a * C + b) + comp, (double)(v0 + sgn * pv1));
+        if (row_live && gb == ga && b < C) {
+          double* dst = Rs + 2 * ((long long)a * C + b) + comp;
+          const double val = (double)(v0 + sgn * pv1);
+          if (single) *dst = val; else atomicAdd(dst, val);   // (the caller zeroes R: a single slice simply writes it)
+        }
       }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
 }
 
 cudaError_t launch_covariance_tc(const cf* snap, const double* wt, double2* Rout, long long F, int B, int C, int conj,
@@ -254,16 +287,18 @@ cudaError_t launch_covariance_tc(const cf* snap, const double* wt, double2* Rout
   int Cp = 4;
   while (Cp < C) Cp *= 2;
   const int tiles = (B + 64 / Cp - 1) / (64 / Cp);
-  // frame slices: at most 512 frames each (FP32 accumulation span), and enough CTAs for two waves where slices of
-  // at least 64 frames allow it
-  int split = (int)((F + 511) / 512);
-  const int want = (2 * 148 + tiles - 1) / tiles;
+  // frame slices: at most 2048 frames each (FP32 accumulation span in TMEM).  With at least one tile per SM a single
+  // slice per tile is best (R is then written without atomics); fewer tiles are cut into slices of at least 64 frames
+  // until there are about 1.5 CTAs per SM (measured: more slices only add atomics).
+  int split = (int)((F + 2047) / 2048);
+  const int want = tiles >= 148 ? 1 : (3 * 148 / 2 + tiles - 1) / tiles;   // measured: C = 64 best unsplit, C = 16 best at 4 slices
   if (split < want) split = want;
   const int cap = (int)((F + 63) / 64);
   if (split > cap) split = cap;
   if (split < 1) split = 1;
   if (split > 64) split = 64;
-  const int smem = 2 * COV_TC_STAGE_BYTES;
+  if (const char* e = getenv("BTK_COV_SPLIT")) { const int v = atoi(e); if (v >= 1 && v <= 64) split = v; }   // tuning knob (A/B runs)
+  const int smem = COV_TC_SMEM;
   cudaError_t e = cudaFuncSetAttribute(btk_covariance_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   btk_covariance_tc_kernel<<<dim3(tiles, split), COV_TC_THREADS, smem, st>>>(snap, wt, Rout, F, B, C, conj, Cp);
