@@ -27,7 +27,7 @@ SYMBOLS = [
     "btkb200_beamform", "btkb200_synthesis", "btkb200_covariance", "btkb200_estimate_covariance", "btkb200_chain",
     "btkb200_chain_batch", "btkb200_chain_batch_pcm", "btkb200_convert_pcm", "btkb200_beamform_zelinski",
     "btkb200_chain_zelinski", "btkb200_beamform_zelinski_dev", "btkb200_gsc_calc_weights",
-    "btkb200_gsc_set_active_weights", "btkb200_gsc_zero_active_weights", "btkb200_gsc_get_blocking_matrix", "btkb200_gsc_apply",
+    "btkb200_design_analysis_prototype", "btkb200_design_synthesis_prototype", "btkb200_gsc_set_active_weights", "btkb200_gsc_zero_active_weights", "btkb200_gsc_get_blocking_matrix", "btkb200_gsc_apply",
     "btkb200_chain_batch_multi", "btkb200_chain_batch_dev", "btkb200_analysis_dev", "btkb200_beamform_dev",
     "btkb200_synthesis_dev", "btkb200_launch_count", "btkb200_sync", "btkb200_host_alloc", "btkb200_host_free",
 ]
@@ -95,6 +95,8 @@ def lib() -> ctypes.CDLL:
     L.btkb200_beamform_zelinski.argtypes = [vp, vp, c_long, c_double, c_int, c_int, vp, vp]
     L.btkb200_chain_zelinski.argtypes = [vp, vp, c_long, c_double, c_int, c_int, vp]
     L.btkb200_beamform_zelinski_dev.argtypes = [vp, vp, c_long, c_double, c_int, c_int, vp, vp, vp]
+    L.btkb200_design_analysis_prototype.argtypes = [c_uint, c_uint, c_uint, c_double, c_int, c_double, c_int, vp, vp]
+    L.btkb200_design_synthesis_prototype.argtypes = [vp, c_uint, c_uint, c_uint, c_double, c_double, c_int, c_double, c_int, vp, vp]
     L.btkb200_gsc_calc_weights.argtypes = [vp, c_double, vp, c_uint]
     L.btkb200_gsc_set_active_weights.argtypes = [vp, c_uint, vp, c_uint]
     L.btkb200_gsc_zero_active_weights.argtypes = [vp]
@@ -397,6 +399,33 @@ class Plan:
 
     def sync(self):
         self._ck(self._L.btkb200_sync(self._h))
+
+
+def design_analysis_prototype(M: int, m: int, r: int, wp_factor: float = 1.0, tau: int = -1, tolerance: float = 1e-7,
+                              device: int = 0):
+    """AnalysisOversampledDFTDesign(M, m, r, wpFactor, tau).design(tolerance) on the device.  Returns (h, err[3])."""
+    L = lib()
+    h = np.zeros(M * m, dtype=np.float64)
+    err = np.zeros(3, dtype=np.float64)
+    rc = L.btkb200_design_analysis_prototype(M, m, r, wp_factor, tau, tolerance, device, _p(h), _p(err))
+    if rc != OK:
+        raise BtkError(rc, (L.btkb200_last_error(None) or b"").decode())
+    return h, err
+
+
+def design_synthesis_prototype(h, M: int, m: int, r: int, v: float = 1.0, wp_factor: float = 1.0, tau: int = -1,
+                               tolerance: float = 1e-7, device: int = 0):
+    """SynthesisOversampledDFTDesign(h, M, m, r, v, wpFactor, tau).design(tolerance) on the device.  Returns (g, err[3])."""
+    L = lib()
+    hh = np.ascontiguousarray(h, dtype=np.float64)
+    if hh.size != M * m:
+        raise BtkError(EINVAL, f"Prototype sizes do not match ({hh.size} vs. {M * m}).")
+    g = np.zeros(M * m, dtype=np.float64)
+    err = np.zeros(3, dtype=np.float64)
+    rc = L.btkb200_design_synthesis_prototype(_p(hh), M, m, r, v, wp_factor, tau, tolerance, device, _p(g), _p(err))
+    if rc != OK:
+        raise BtkError(rc, (L.btkb200_last_error(None) or b"").decode())
+    return g, err
 
 
 def device_count() -> int:

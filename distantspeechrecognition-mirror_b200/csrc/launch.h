@@ -34,6 +34,11 @@ cudaError_t launch_mvdr_solve(const double2* Rn, const double2* d, double2* w, i
 cudaError_t launch_beamform_zelinski(const cf* snap, const cf* w, const cf* ta, cf* Y, float4* stat, float* Wout, long long F,
                                      int B, int C, double alpha, int type, int min_frames, cudaStream_t st);
 
+// de Haan prototype design in fp64 on the device (kern_design.cu): kind 0 = analysis h = pinv(A + C) b, kind 1 = synthesis
+// g = pinv(E + v P) f from h_in (modulated/prototypeDesign.cc:223-272, 640-712, 836-901).  Host pointers.
+cudaError_t design_prototype(int kind, const double* h_in, int M, int m, int r, double v, double wp_factor, int tau, double tolerance,
+                             double* proto_out, double* err, int* sweeps_out);
+
 // Raw PCM -> float32, element for element (bit-exact integer -> float):
 //   fmt 1: int16 little endian (what sf_readf_float returns with SFC_SET_NORM_FLOAT off, feature/feature.cc:273, 868-896)
 //   fmt 2: packed 24-bit big endian, sign extended (Conversion24bit2Float::next, feature/feature.cc:190-217;

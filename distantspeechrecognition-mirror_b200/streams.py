@@ -499,6 +499,57 @@ class SubbandMVDRPtr(_SubbandBeamformer):
         return self.getWeights(fbinX)
 
 
+class AnalysisOversampledDFTDesignPtr:
+    """modulated/modulated.i shadow of AnalysisOversampledDFTDesign (prototypeDesign.h:148-166): design() / calcError() / save()."""
+
+    def __init__(self, M: int = 512, m: int = 2, r: int = 1, wpFactor: float = 1.0, tau_h: int = -1):
+        self._M, self._m, self._r, self._wp, self._tau = int(M), int(m), int(r), float(wpFactor), int(tau_h)
+        self._proto = None
+        self._err = None
+
+    def design(self, tolerance: float = 1.0e-07):
+        try:
+            self._proto, self._err = _capi.design_analysis_prototype(self._M, self._m, self._r, self._wp, self._tau, tolerance)
+        except BtkError as e:
+            _raise(e)
+        return self._proto
+
+    def calcError(self, doPrint: bool = True):
+        if self._err is None:
+            raise j_error("call design() first")
+        if doPrint:
+            print("eps_p = %f\neps_i = %f" % (self._err[0], self._err[1]))
+        return self._err
+
+    def save(self, fileName: str):                    # one "%24.21e" per line (prototypeDesign.cc:214-220)
+        with open(fileName, "w") as fp:
+            for x in self._proto:
+                fp.write("%24.21e\n" % x)
+
+
+class SynthesisOversampledDFTDesignPtr(AnalysisOversampledDFTDesignPtr):
+    """prototypeDesign.h:177-218: SynthesisOversampledDFTDesign(h, M, m, r, v, wpFactor, tau_g)."""
+
+    def __init__(self, h, M: int = 512, m: int = 2, r: int = 1, v: float = 1.0, wpFactor: float = 1.0, tau_g: int = -1):
+        super().__init__(M, m, r, wpFactor, tau_g)
+        self._h, self._v = np.ascontiguousarray(h, np.float64).ravel().copy(), float(v)
+
+    def design(self, tolerance: float = 1.0e-07):
+        try:
+            self._proto, self._err = _capi.design_synthesis_prototype(self._h, self._M, self._m, self._r, self._v, self._wp,
+                                                                      self._tau, tolerance)
+        except BtkError as e:
+            _raise(e)
+        return self._proto
+
+    def calcError(self, doPrint: bool = True):
+        if self._err is None:
+            raise j_error("call design() first")
+        if doPrint:
+            print("eps_t = %f\neps_r = %f" % (self._err[0], self._err[1]))
+        return self._err
+
+
 TYPE_ZELINSKI1_REAL, TYPE_ZELINSKI1_ABS, TYPE_APAB, TYPE_ZELINSKI2, NO_USE_POST_FILTER = 0x01, 0x02, 0x04, 0x08, 0x00
 
 

@@ -122,6 +122,17 @@ int btkb200_covariance(btkb200_plan* plan, const float* snap, long F, const doub
 int btkb200_estimate_covariance(btkb200_plan* plan, const float* pcm, long T, double forget, long last_frame,
                                 int conjugate);
 
+/* ---- prototype design ------------------------------------------------------------------------------ */
+/* AnalysisOversampledDFTDesign(M, m, r, wpFactor, tau_h).design(tolerance) (modulated/prototypeDesign.cc:223-272, 611-712):
+ * h = pinv(A + C) b, singular values below tolerance * s_max dropped; tau < 0 = M m / 2.  h: M*m doubles; err (or NULL)
+ * receives calcError(): passband response error, in-band aliasing distortion, their sum (dB).  fp64 on the device. */
+int btkb200_design_analysis_prototype(unsigned M, unsigned m, unsigned r, double wp_factor, int tau, double tolerance,
+                                      int device, double* h, double* err);
+/* SynthesisOversampledDFTDesign(h, M, m, r, v, wpFactor, tau_g).design(tolerance) (prototypeDesign.cc:768-901):
+ * g = pinv(E + v P) f.  err: total response error, residual aliasing distortion, eps_t + v eps_r (dB). */
+int btkb200_design_synthesis_prototype(const double* h, unsigned M, unsigned m, unsigned r, double v, double wp_factor,
+                                       int tau, double tolerance, int device, double* g, double* err);
+
 /* ---- SubbandGSC with fixed active weights ------------------------------------------------------- */
 /* SubbandGSC::calcGSCWeights (beamformer.cc:1373-1377): delay-and-sum quiescent vectors + one blocking matrix per bin
  * (_calcBlockingMatrix, :398-479, NC = 1); the active weights start at zero.  EINVAL for a single channel (:536-539). */

@@ -267,6 +267,60 @@ def chain(pcm: np.ndarray, h: np.ndarray, g: np.ndarray, geo: BankGeometry, W: n
     return X, Y, out.reshape(-1)
 
 
+# --------------------------------------------------------------------------- prototype design (de Haan)
+def _pinv_solve(K: np.ndarray, b: np.ndarray, tol: float) -> np.ndarray:
+    """x = V diag(1/s_n or 0) U^T b with singular values below tol * s_0 dropped (prototypeDesign.cc:691-712, 885-901)."""
+    U, s, Vt = np.linalg.svd(K)
+    c = U.T @ b
+    keep = (s / s[0]) >= tol
+    c = np.where(keep, c / np.where(keep, s, 1.0), 0.0)
+    return Vt.T @ c
+
+
+def design_analysis_dehaan(M: int, m: int, r: int, wp_factor: float = 1.0, tau: int = -1, tol: float = 1e-7) -> np.ndarray:
+    """AnalysisOversampledDFTDesign::design (prototypeDesign.cc:223-272, 640-712):  h = pinv(A + C) b with
+    A(m,n) = sinc(wp (n-m)), b(m) = sinc(wp (tau - m)), wp = pi / (wpFactor M), tau = L/2 by default,
+    C(m,n) = f/D (n == m) or f sin(pi (n-m)/D) / (pi D (n-m)), f = D-1 where D divides n-m, else -1."""
+    L, D = M * m, M >> r
+    wp = np.pi / (wp_factor * M)
+    tau = L // 2 if tau < 0 else tau
+    idx = np.arange(L)
+    d = idx[None, :] - idx[:, None]                       # n - m
+    with np.errstate(divide="ignore", invalid="ignore"):
+        A = np.where(d == 0, 1.0, np.sin(wp * d) / (wp * d))
+        t = tau - idx
+        b = np.where(t == 0, 1.0, np.sin(wp * t) / (wp * t))
+        f = np.where(d % D == 0, D - 1.0, -1.0)
+        C = np.where(d == 0, f / D, f * np.sin(np.pi * d / D) / (np.pi * D * d))
+    return _pinv_solve(A + C, b, tol)
+
+
+def design_synthesis_dehaan(h: np.ndarray, M: int, m: int, r: int, v: float = 1.0, tau: int = -1,
+                            tol: float = 1e-7) -> np.ndarray:
+    """SynthesisOversampledDFTDesign::design (prototypeDesign.cc:836-901):  g = pinv(E + v P) f with
+    E(m,n) = (M/D)^2 sum_{k=0..2m} h[kM-m] h[kM-n],  P(m,n) = M/D^2 f(m-n) sum_k h[k+n] h[k+m]  (f as above),
+    f(m) = M/(pi D) h[2 tau - m]; out-of-range taps are skipped."""
+    h = np.asarray(h, dtype=np.float64)
+    L, D = M * m, M >> r
+    tau = L // 2 if tau < 0 else tau
+    idx = np.arange(L)
+    E = np.zeros((L, L))
+    for k in range(2 * m + 1):
+        j = k * M - idx
+        ok = (j >= 0) & (j <= L - 1)
+        col = np.where(ok, h[np.clip(j, 0, L - 1)], 0.0)
+        E += np.outer(col, col)
+    E *= float((M // D) * (M // D))
+    rr = np.correlate(h, h, mode="full")                   # rr[L-1+d] = sum_j h[j] h[j+d]
+    d = idx[:, None] - idx[None, :]                        # m - n
+    fac = np.where(d % D == 0, D - 1.0, -1.0)
+    P = fac * rr[L - 1 + np.abs(d)] * (M / (float(D) * float(D)))
+    j = 2 * tau - idx
+    ok = (j >= 0) & (j <= L - 1)
+    f = np.where(ok, h[np.clip(j, 0, L - 1)], 0.0) * (M / (np.pi * D))
+    return _pinv_solve(E + v * P, f, tol)
+
+
 # --------------------------------------------------------------------------- SubbandGSC (fixed active weights)
 def blocking_matrix(v: np.ndarray, NC: int = 1) -> np.ndarray:
     """_calcBlockingMatrix (beamformer/beamformer.cc:398-479), loop for loop: P = I - conj(v) v^T / ||v||^2 (zgeru), then
@@ -409,6 +463,9 @@ class CompiledReference:
             L.btkref_chain_gsc.restype = cl
             L.btkref_chain_gsc.argtypes = [ctypes.POINTER(_ChainCfg), vp, cl, vp, vp, vp, vp, ci, vp, cl, vp, cl,
                                            ctypes.POINTER(cl), vp, vp]
+        if hasattr(L, "btkref_design_dehaan"):
+            L.btkref_design_dehaan.restype = ci
+            L.btkref_design_dehaan.argtypes = [ci, ci, ci, cd, cd, cd, vp, vp, vp, vp]
         L.btkref_spectral_matrix.restype = cl
         L.btkref_spectral_matrix.argtypes = [vp, cl, ci, vp, ci, ci, ci, ci, cd, vp]
         L.btkref_error_probe.restype = ci
@@ -523,6 +580,15 @@ class CompiledReference:
         if g is not None:
             res["out"] = out[: nout.value].reshape(-1)
         return res
+
+    def design_dehaan(self, M, m, r, wp_factor=1.0, v=1.0, tol=1e-7):
+        """The reference's AnalysisOversampledDFTDesign + SynthesisOversampledDFTDesign.  Returns (h, g, err_h, err_g)."""
+        L = M * m
+        h, g, eh, eg = np.zeros(L), np.zeros(L), np.zeros(3), np.zeros(3)
+        rc = self.lib.btkref_design_dehaan(M, m, r, wp_factor, v, tol, _dp(h), _dp(g), _dp(eh), _dp(eg))
+        if rc != 0:
+            raise RuntimeError(f"btkref_design_dehaan returned {rc}")
+        return h, g, eh, eg
 
     def spectral_matrix(self, pcm, h, geo: BankGeometry, mu=0.95) -> np.ndarray:
         pcm = np.ascontiguousarray(pcm, dtype=np.float32)

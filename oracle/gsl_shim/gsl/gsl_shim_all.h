@@ -292,6 +292,76 @@ static inline int gsl_blas_zaxpy(const gsl_complex a, const gsl_vector_complex* 
   return GSL_SUCCESS;
 }
 static inline int gsl_blas_daxpy(double a, const gsl_vector* x, gsl_vector* y) { for (size_t i = 0; i < x->size; i++) y->data[i * y->stride] += a * x->data[i * x->stride]; return GSL_SUCCESS; }
+
+/* ---------------------------------------------------------------- real dense algebra used by modulated/prototypeDesign.cc
+ * (views :283-323, dgemv/dgemm :346-548, SVD :276-300).  Textbook operations; the SVD is a one-sided Jacobi (Hestenes)
+ * iteration in double with the singular values sorted in decreasing order like gsl_linalg_SV_decomp delivers them. */
+#ifndef HUGE
+#define HUGE HUGE_VAL
+#endif
+static inline gsl_matrix_view gsl_matrix_submatrix(gsl_matrix* m, size_t k1, size_t k2, size_t n1, size_t n2) {
+  gsl_matrix_view v; v.matrix.size1 = n1; v.matrix.size2 = n2; v.matrix.tda = m->tda; v.matrix.data = m->data + k1 * m->tda + k2;
+  v.matrix.block = m->block; v.matrix.owner = 0; return v; }
+static inline gsl_vector_view gsl_vector_subvector(gsl_vector* x, size_t k, size_t n) {
+  gsl_vector_view v; v.vector.size = n; v.vector.stride = x->stride; v.vector.data = x->data + k * x->stride;
+  v.vector.block = x->block; v.vector.owner = 0; return v; }
+static inline int gsl_blas_dgemv(CBLAS_TRANSPOSE_t t, double alpha, const gsl_matrix* A, const gsl_vector* x, double beta, gsl_vector* y) {
+  const size_t rows = (t == CblasNoTrans) ? A->size1 : A->size2, cols = (t == CblasNoTrans) ? A->size2 : A->size1;
+  double* tmp = (double*)malloc(sizeof(double) * (rows ? rows : 1));
+  for (size_t i = 0; i < rows; i++) {
+    double acc = 0;
+    for (size_t j = 0; j < cols; j++) acc += ((t == CblasNoTrans) ? A->data[i * A->tda + j] : A->data[j * A->tda + i]) * x->data[j * x->stride];
+    tmp[i] = alpha * acc + (beta != 0.0 ? beta * y->data[i * y->stride] : 0.0);
+  }
+  for (size_t i = 0; i < rows; i++) y->data[i * y->stride] = tmp[i];
+  free(tmp); return GSL_SUCCESS; }
+static inline int gsl_blas_dgemm(CBLAS_TRANSPOSE_t ta, CBLAS_TRANSPOSE_t tb, double alpha, const gsl_matrix* A, const gsl_matrix* B, double beta, gsl_matrix* C) {
+  const size_t n1 = C->size1, n2 = C->size2, kk = (ta == CblasNoTrans) ? A->size2 : A->size1;
+  double* tmp = (double*)malloc(sizeof(double) * (n1 * n2 ? n1 * n2 : 1));
+  for (size_t i = 0; i < n1; i++) for (size_t j = 0; j < n2; j++) {
+    double acc = 0;
+    for (size_t k = 0; k < kk; k++)
+      acc += ((ta == CblasNoTrans) ? A->data[i * A->tda + k] : A->data[k * A->tda + i]) * ((tb == CblasNoTrans) ? B->data[k * B->tda + j] : B->data[j * B->tda + k]);
+    tmp[i * n2 + j] = alpha * acc + (beta != 0.0 ? beta * C->data[i * C->tda + j] : 0.0);
+  }
+  for (size_t i = 0; i < n1; i++) for (size_t j = 0; j < n2; j++) C->data[i * C->tda + j] = tmp[i * n2 + j];
+  free(tmp); return GSL_SUCCESS; }
+/* A (M x N, M >= N) = U S V^T : A is overwritten by U, V is N x N, S holds the singular values in decreasing order. */
+static inline int gsl_linalg_SV_decomp(gsl_matrix* A, gsl_matrix* V, gsl_vector* S, gsl_vector* work) {
+  (void)work;
+  const size_t M = A->size1, N = A->size2;
+  for (size_t i = 0; i < N; i++) for (size_t j = 0; j < N; j++) V->data[i * V->tda + j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 60; sweep++) {
+    double off = 0;
+    for (size_t p = 0; p + 1 < N; p++) for (size_t q = p + 1; q < N; q++) {
+      double a = 0, b = 0, g = 0;
+      for (size_t i = 0; i < M; i++) { const double x = A->data[i * A->tda + p], y = A->data[i * A->tda + q]; a += x * x; b += y * y; g += x * y; }
+      if (g == 0.0 || a == 0.0 || b == 0.0) continue;
+      const double rel = fabs(g) / sqrt(a * b);
+      if (rel > off) off = rel;
+      if (rel < 1e-15) continue;
+      const double zeta = (b - a) / (2.0 * g), tt = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+      const double c = 1.0 / sqrt(1.0 + tt * tt), sn = c * tt;
+      for (size_t i = 0; i < M; i++) { const double x = A->data[i * A->tda + p], y = A->data[i * A->tda + q]; A->data[i * A->tda + p] = c * x - sn * y; A->data[i * A->tda + q] = sn * x + c * y; }
+      for (size_t i = 0; i < N; i++) { const double x = V->data[i * V->tda + p], y = V->data[i * V->tda + q]; V->data[i * V->tda + p] = c * x - sn * y; V->data[i * V->tda + q] = sn * x + c * y; }
+    }
+    if (off < 1e-15) break;
+  }
+  for (size_t j = 0; j < N; j++) {
+    double n2 = 0; for (size_t i = 0; i < M; i++) n2 += A->data[i * A->tda + j] * A->data[i * A->tda + j];
+    const double sv = sqrt(n2); S->data[j * S->stride] = sv;
+    if (sv > 0) for (size_t i = 0; i < M; i++) A->data[i * A->tda + j] /= sv;
+  }
+  for (size_t j = 0; j + 1 < N; j++) {          /* selection sort, decreasing */
+    size_t best = j;
+    for (size_t k = j + 1; k < N; k++) if (S->data[k * S->stride] > S->data[best * S->stride]) best = k;
+    if (best != j) {
+      const double t = S->data[j * S->stride]; S->data[j * S->stride] = S->data[best * S->stride]; S->data[best * S->stride] = t;
+      for (size_t i = 0; i < M; i++) { const double x = A->data[i * A->tda + j]; A->data[i * A->tda + j] = A->data[i * A->tda + best]; A->data[i * A->tda + best] = x; }
+      for (size_t i = 0; i < N; i++) { const double x = V->data[i * V->tda + j]; V->data[i * V->tda + j] = V->data[i * V->tda + best]; V->data[i * V->tda + best] = x; }
+    }
+  }
+  return GSL_SUCCESS; }
 static inline gsl_complex btkshim_op(const gsl_matrix_complex* A, CBLAS_TRANSPOSE_t t, size_t i, size_t j) {
   if (t == CblasNoTrans) return gsl_matrix_complex_get(A, i, j);
   gsl_complex z = gsl_matrix_complex_get(A, j, i);

@@ -12,6 +12,7 @@
 //   SubbandMVDR                  btk/beamformer/beamformer.cc:2321-2635
 //   SpectralMatrixArray          btk/beamformer/beamformer.cc:119-163
 //   ZelinskiPostFilter           btk/postfilter/postfilter.cc:340-500
+//   Analysis/SynthesisOversampledDFTDesign   btk/modulated/prototypeDesign.cc:223-272, 611-951
 // This file only feeds them from memory and copies their per-frame outputs out.
 // The in-memory source reproduces SampleFeature::next's block/pad rule
 // (btk/feature/feature.cc:610-659) because feature.cc itself needs libsndfile.
@@ -24,6 +25,7 @@
 #include "stream/stream.h"
 #include "modulated/modulated.h"
 #include "beamformer/beamformer.h"
+#include "modulated/prototypeDesign.h"
 
 // postfilter/postfilter.cc is part of the build (ZelinskiPostFilter: btk/postfilter/postfilter.cc:30-222, 340-500).
 #include "postfilter/postfilter.h"
@@ -182,6 +184,21 @@ class MVDRDoubleInverse : public SubbandMVDR {
       gsl_matrix_complex_set(inv, i, j, gsl_complex_rect((double)ar[i * 2 * n + n + j], (double)ai[i * 2 * n + n + j]));
     return true;
   }
+};
+
+// SynthesisOversampledDFTDesign re-declares _singularVals / _scratch / _workSpace (prototypeDesign.h:199-202), hiding the
+// base-class vectors, and its constructor never allocates them (prototypeDesign.cc:768-779): _solve() then hands
+// uninitialised pointers to the SVD (:886-899).  The members are protected, so a subclass can allocate them; nothing
+// else of the reference's design code is touched.
+class SynthesisDesignWithWorkspace : public SynthesisOversampledDFTDesign {
+ public:
+  SynthesisDesignWithWorkspace(const gsl_vector* h, int M, int m, int r, double v, double wp, int tau)
+      : SynthesisOversampledDFTDesign(h, M, m, r, v, wp, tau) {
+    _singularVals = gsl_vector_calloc(M * m);
+    _scratch = gsl_vector_calloc(M * m);
+    _workSpace = gsl_vector_calloc(M * m);
+  }
+  ~SynthesisDesignWithWorkspace() { gsl_vector_free(_singularVals); gsl_vector_free(_scratch); gsl_vector_free(_workSpace); }
 };
 
 gsl_vector* make_vector(const double* src, size_t n) {
@@ -468,6 +485,30 @@ long btkref_chain_gsc(const btkref_chain_cfg* cfg, const float* pcm, long T, con
     delete bf;
     return nf;
   } catch (std::exception& e) { fprintf(stderr, "btkref_chain_gsc: %s\n", e.what()); return -1; }
+}
+
+// de Haan prototype design (prototypeDesign.cc:611-951): h = pinv(A + C) b, then g = pinv(E + v P) f from that h.
+//   h, g: [M*m] outputs;  err_h[3] / err_g[3]: calcError() of the two designs (dB).  Returns 0, <0 on error.
+int btkref_design_dehaan(int M, int m, int r, double wpFactor, double v, double tolerance, double* h, double* g,
+                         double* err_h, double* err_g) {
+  try {
+    const int L = M * m;
+    AnalysisOversampledDFTDesign ana(M, m, r, wpFactor, -1);
+    const gsl_vector* hv = ana.design(tolerance);
+    for (int n = 0; n < L; n++) h[n] = gsl_vector_get(hv, n);
+    const gsl_vector* eh = ana.calcError(false);
+    if (err_h) for (int k = 0; k < 3; k++) err_h[k] = gsl_vector_get(eh, k);
+    if (g) {
+      gsl_vector* hc = make_vector(h, L);
+      SynthesisDesignWithWorkspace syn(hc, M, m, r, v, wpFactor, -1);
+      const gsl_vector* gv = syn.design(tolerance);
+      for (int n = 0; n < L; n++) g[n] = gsl_vector_get(gv, n);
+      const gsl_vector* eg = syn.calcError(false);
+      if (err_g) for (int k = 0; k < 3; k++) err_g[k] = gsl_vector_get(eg, k);
+      gsl_vector_free(hc);
+    }
+    return 0;
+  } catch (std::exception& e) { fprintf(stderr, "btkref_design_dehaan: %s\n", e.what()); return -1; }
 }
 
 // SpectralMatrixArray recursion (beamformer.cc:142-163) over all frames of a recording.
