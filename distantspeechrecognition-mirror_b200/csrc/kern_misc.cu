@@ -296,15 +296,15 @@ __device__ __forceinline__ double shfl_d(double v, int src) {
   return __hiloint2double(hi, lo);
 }
 
-__global__ void __launch_bounds__(128) btk_mvdr_solve_kernel(const double2* __restrict__ Rn, const double2* __restrict__ dvec,
+__global__ void __launch_bounds__(256) btk_mvdr_solve_kernel(const double2* __restrict__ Rn, const double2* __restrict__ dvec,
                                                             double2* __restrict__ w, int* __restrict__ fallback, int C,
                                                             double dThreshold) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* A = reinterpret_cast<double2*>(smem_raw);       // [C][C+1]
   __shared__ int s_piv;
   __shared__ int s_bad;
-  __shared__ double s_best[4];
-  __shared__ int s_bidx[4];
+  __shared__ double s_best[8];
+  __shared__ int s_bidx[8];
   const int s = blockIdx.x, ld = C + 1, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const double2* d = dvec + (long long)s * C;
   double2* ws = w + (long long)s * C;
@@ -349,15 +349,28 @@ __global__ void __launch_bounds__(128) btk_mvdr_solve_kernel(const double2* __re
       }
     }
     __syncthreads();
-    // row factors f_r = A[r][k] / pivot, once per row (stored in place in column k), then the rank-1 update
-    const double2 inv = zdiv(make_double2(1.0, 0.0), A[k * ld + k]);
-    for (int r = k + 1 + tid; r < C; r += nt) A[r * ld + k] = zmul(A[r * ld + k], inv);
-    __syncthreads();
-    const int rows = C - 1 - k, cols = C - k;      // eliminate rows k+1.., columns k+1..C (incl. rhs)
-    for (int i = tid; i < rows * cols; i += nt) {
-      const int r = k + 1 + i / cols, c = k + 1 + i % cols;
-      const double2 t = zmul(A[r * ld + k], A[k * ld + c]);
-      A[r * ld + c].x -= t.x; A[r * ld + c].y -= t.y;
+    // rank-1 update of rows k+1.., columns k+1..C (incl. the rhs): a warp per row, lanes across the columns
+    // (consecutive 16-byte words: conflict-free; the pivot-row elements of a lane's columns stay in registers, the row
+    // factor f_r = A[r][k] / pivot is a broadcast load + one multiply per lane -- no separate scaling pass, no
+    // index division)
+    {
+      const double2 inv = zdiv(make_double2(1.0, 0.0), A[k * ld + k]);
+      double2 pk[3];                                  // columns k+1+lane, +32, +64  (C <= 64 -> at most 65 columns)
+#pragma unroll
+      for (int q = 0; q < 3; q++) { const int c = k + 1 + lane + 32 * q; pk[q] = c <= C ? A[k * ld + c] : make_double2(0.0, 0.0); }
+      for (int r = k + 1 + warp; r < C; r += (nt >> 5)) {
+        const double2 f = zmul(A[r * ld + k], inv);
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+          const int c = k + 1 + lane + 32 * q;
+          if (c <= C) {
+            const double2 t = zmul(f, pk[q]);
+            double2 a = A[r * ld + c];
+            a.x -= t.x; a.y -= t.y;
+            A[r * ld + c] = a;
+          }
+        }
+      }
     }
     __syncthreads();
   }
@@ -410,7 +423,7 @@ cudaError_t launch_mvdr_solve(const double2* Rn, const double2* d, double2* w, i
   const size_t smem = (size_t)C * (C + 1) * sizeof(double2);
   cudaError_t e = cudaFuncSetAttribute(btk_mvdr_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  btk_mvdr_solve_kernel<<<B, 128, smem, st>>>(Rn, d, w, fallback, C, dThreshold);
+  btk_mvdr_solve_kernel<<<B, C > 32 ? 256 : 128, smem, st>>>(Rn, d, w, fallback, C, dThreshold);
   return cudaGetLastError();
 }
 
