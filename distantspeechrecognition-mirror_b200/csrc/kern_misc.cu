@@ -301,8 +301,6 @@ __global__ void __launch_bounds__(256) btk_mvdr_solve_kernel(const double2* __re
                                                             double dThreshold) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* A = reinterpret_cast<double2*>(smem_raw);       // [C][C+1]
-  __shared__ int s_piv;
-  __shared__ int s_bad;
   __shared__ double s_best[8];
   __shared__ int s_bidx[8];
   const int s = blockIdx.x, ld = C + 1, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
@@ -320,7 +318,7 @@ __global__ void __launch_bounds__(256) btk_mvdr_solve_kernel(const double2* __re
     A[r * ld + c] = make_double2(v.x, -v.y);
   }
   for (int r = tid; r < C; r += nt) A[r * ld + C] = d[r];
-  if (tid == 0) s_bad = 0;
+  bool bad = false;
   __syncthreads();
   for (int k = 0; k < C; k++) {
     // partial pivoting: arg max |A[r][k]|^2 over r >= k, one row per thread (C <= 128)
@@ -334,15 +332,11 @@ __global__ void __launch_bounds__(256) btk_mvdr_solve_kernel(const double2* __re
     }
     if (lane == 0) { s_best[warp] = best; s_bidx[warp] = bidx; }
     __syncthreads();
-    if (tid == 0) {
-      double bb = s_best[0]; int bi = s_bidx[0];
-      for (int q = 1; q < (nt >> 5); q++) if (s_best[q] > bb || (s_best[q] == bb && s_bidx[q] < bi)) { bb = s_best[q]; bi = s_bidx[q]; }
-      s_piv = bi;
-      if (!(bb > dThreshold * dThreshold) || !isfinite(bb)) s_bad = 1;
-    }
-    __syncthreads();
-    if (s_bad) break;
-    const int piv = s_piv;
+    // every thread folds the per-warp candidates itself (broadcast loads, same result everywhere): no serial section
+    // and no second barrier; the slots are rewritten two barriers later
+    double bb = s_best[0]; int piv = s_bidx[0];
+    for (int q = 1; q < (nt >> 5); q++) { const double b2 = s_best[q]; const int i2 = s_bidx[q]; if (b2 > bb || (b2 == bb && i2 < piv)) { bb = b2; piv = i2; } }
+    if (!(bb > dThreshold * dThreshold) || !isfinite(bb)) { bad = true; break; }
     if (piv != k) {
       for (int c = k + tid; c <= C; c += nt) {
         const double2 t = A[k * ld + c]; A[k * ld + c] = A[piv * ld + c]; A[piv * ld + c] = t;
@@ -354,7 +348,10 @@ __global__ void __launch_bounds__(256) btk_mvdr_solve_kernel(const double2* __re
     // factor f_r = A[r][k] / pivot is a broadcast load + one multiply per lane -- no separate scaling pass, no
     // index division)
     {
-      const double2 inv = zdiv(make_double2(1.0, 0.0), A[k * ld + k]);
+      // 1 / pivot = conj(pivot) / |pivot|^2 with one reciprocal (a full complex division costs two fp64 divisions)
+      const double2 pv = A[k * ld + k];
+      const double rd = __drcp_rn(pv.x * pv.x + pv.y * pv.y);
+      const double2 inv = make_double2(pv.x * rd, -pv.y * rd);
       double2 pk[3];                                  // columns k+1+lane, +32, +64  (C <= 64 -> at most 65 columns)
 #pragma unroll
       for (int q = 0; q < 3; q++) { const int c = k + 1 + lane + 32 * q; pk[q] = c <= C ? A[k * ld + c] : make_double2(0.0, 0.0); }
@@ -374,7 +371,7 @@ __global__ void __launch_bounds__(256) btk_mvdr_solve_kernel(const double2* __re
     }
     __syncthreads();
   }
-  if (s_bad) {
+  if (bad) {
     // identity fallback (beamformer.cc:2425-2427): t = d
     __syncthreads();
     if (tid == 0) {
