@@ -147,12 +147,35 @@ template <int S> BTK_HD void dft16(cf* v) {
   }
 }
 
+// 32-point DFT: even / odd 16-point DFTs, then W32^{S k}
+template <int S> BTK_HD void dft32(cf* v) {
+  cf e[16], o[16];
+  BTK_UNROLL
+  for (int i = 0; i < 16; i++) { e[i] = v[2 * i]; o[i] = v[2 * i + 1]; }
+  dft16<S>(e);
+  dft16<S>(o);
+  // cos / sin of 2 pi k / 32, k = 0..15
+  const float c32[16] = {1.f, 0.98078528040323044913f, BTK_COS_PI_8, 0.83146961230254523708f, BTK_SQRT1_2, 0.55557023301960222474f,
+                         BTK_SIN_PI_8, 0.19509032201612826785f, 0.f, -0.19509032201612826785f, -BTK_SIN_PI_8,
+                         -0.55557023301960222474f, -BTK_SQRT1_2, -0.83146961230254523708f, -BTK_COS_PI_8, -0.98078528040323044913f};
+  const float s32[16] = {0.f, 0.19509032201612826785f, BTK_SIN_PI_8, 0.55557023301960222474f, BTK_SQRT1_2, 0.83146961230254523708f,
+                         BTK_COS_PI_8, 0.98078528040323044913f, 1.f, 0.98078528040323044913f, BTK_COS_PI_8,
+                         0.83146961230254523708f, BTK_SQRT1_2, 0.55557023301960222474f, BTK_SIN_PI_8, 0.19509032201612826785f};
+  BTK_UNROLL
+  for (int k = 0; k < 16; k++) {
+    const cf t = k == 0 ? o[0] : (k == 8 ? mulj<S>(o[8]) : mulw<S>(o[k], c32[k], s32[k]));
+    v[k] = cadd(e[k], t);
+    v[k + 16] = csub(e[k], t);
+  }
+}
+
 template <int R, int S> struct Dft;
 template <int S> struct Dft<1, S> { static BTK_HD void run(cf*) {} };
 template <int S> struct Dft<2, S> { static BTK_HD void run(cf* v) { dft2<S>(v[0], v[1]); } };
 template <int S> struct Dft<4, S> { static BTK_HD void run(cf* v) { dft4<S>(v[0], v[1], v[2], v[3]); } };
 template <int S> struct Dft<8, S> { static BTK_HD void run(cf* v) { dft8<S>(v); } };
 template <int S> struct Dft<16, S> { static BTK_HD void run(cf* v) { dft16<S>(v); } };
+template <int S> struct Dft<32, S> { static BTK_HD void run(cf* v) { dft32<S>(v); } };
 
 // ---------------------------------------------------------------------------------------------
 // M-point transform shared by the L lanes of a group, V = M/L values per lane.
@@ -169,7 +192,11 @@ template <> struct FFTPlan<64>   { static constexpr int M = 64,   Ra = 8,  Rb = 
 template <> struct FFTPlan<128>  { static constexpr int M = 128,  Ra = 8,  Rb = 2, Rc = 8,  V = 8,  L = 16; };
 template <> struct FFTPlan<256>  { static constexpr int M = 256,  Ra = 16, Rb = 1, Rc = 16, V = 16, L = 16; };
 template <> struct FFTPlan<512>  { static constexpr int M = 512,  Ra = 16, Rb = 2, Rc = 16, V = 16, L = 32; };
+#ifdef BTK_FFT1024_3PASS   // A/B: the three-pass plan of the first sessions (two exchanges)
 template <> struct FFTPlan<1024> { static constexpr int M = 1024, Ra = 16, Rb = 4, Rc = 16, V = 32, L = 32; };
+#else
+template <> struct FFTPlan<1024> { static constexpr int M = 1024, Ra = 32, Rb = 1, Rc = 32, V = 32, L = 32; };   // one exchange
+#endif
 
 template <int M_> struct FFTGeom {
   typedef FFTPlan<M_> P;
@@ -225,19 +252,38 @@ template <int M_, int S> struct GroupFFT {
       const int j = gl + G::L * rep;
       // W^{ka} from the seed W = twa[j] by a product tree of depth <= 4.  The packed multiplies are cheaper than the
       // shared-memory bandwidth a table read would take.
-      cf w[G::Ra + 1];
+      // (radix 32: only W^1..W^3 and W^4, W^8, .., W^28 are kept -- 11 values instead of 31 -- and W^ka = W^{ka & 3} W^{ka & ~3}
+      // is formed when it is applied)
+      constexpr int NLO = G::Ra > 16 ? 4 : G::Ra;               // w[1 .. NLO-1] directly
+      cf w[NLO + 1];
       w[1] = twa[j * FT::TA];
       BTK_UNROLL
-      for (int ka = 2; ka < G::Ra; ka++) {
+      for (int ka = 2; ka < NLO; ka++) {
         const int hi = ka >= 8 ? 8 : (ka >= 4 ? 4 : 2);        // largest power of two <= ka
         w[ka] = (ka == hi) ? cmul(w[ka / 2], w[ka / 2]) : cmul(w[hi], w[ka - hi]);
+      }
+      cf wh[G::Ra > 16 ? G::Ra / 4 : 1];                        // wh[i] = W^{4 i}
+      if (G::Ra > 16) {
+        wh[1] = cmul(w[2], w[2]);
+        BTK_UNROLL
+        for (int i = 2; i < G::Ra / 4; i++) {
+          const int hi = i >= 4 ? 4 : 2;
+          wh[i] = (i == hi) ? cmul(wh[i / 2], wh[i / 2]) : cmul(wh[hi], wh[i - hi]);
+        }
       }
       BTK_UNROLL
       for (int pp = 0; pp < PP; pp++) {
         cf* p = v + pp * G::V + rep * G::Ra;
         cf* x = xb + pp * G::XBUF;
         BTK_UNROLL
-        for (int ka = 1; ka < G::Ra; ka++) p[ka] = multw<S>(p[ka], w[ka]);
+        for (int ka = 1; ka < G::Ra; ka++) {
+          if (G::Ra > 16) {
+            const cf wk = (ka & 3) == 0 ? wh[ka >> 2] : ((ka >> 2) == 0 ? w[ka & 3] : cmul(w[ka & 3], wh[ka >> 2]));
+            p[ka] = multw<S>(p[ka], wk);
+          } else {
+            p[ka] = multw<S>(p[ka], w[ka]);
+          }
+        }
         BTK_UNROLL
         for (int ka = 0; ka < G::Ra; ka++) x[ka * (G::Rb > 1 ? G::S1 : G::S2) + j] = p[ka];
       }
