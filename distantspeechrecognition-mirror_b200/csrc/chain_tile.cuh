@@ -72,7 +72,8 @@ struct ChainCfg {
   // would not fit 227 KB of shared memory at all (M = 1024).  Two independent CTAs per SM matter more than a
   // longer window: one CTA's staging (global-load latency) overlaps the other's transforms.  (M = 512 with 4 warps
   // and two CTAs measured 11-38 % slower than 8 warps and one CTA: the window halo doubles; tools/ab_run2.sh.)
-  static constexpr int NW = (M_ >= 1024 || (PP_ == 2 && M_ <= 256)) ? 4 : 8;
+  // (M = 512 without oversampling, D = 512: the window of 8 warps does not fit next to the exchange buffers either)
+  static constexpr int NW = (M_ >= 1024 || (M_ == 512 && R_ == 1) || (PP_ == 2 && M_ <= 256)) ? 4 : 8;
   static constexpr int NT = NW * 32;
   static constexpr int FW = 2 * PP_;           // frames per warp per iteration
   static constexpr int LV = (FW % 4 == 0) ? 4 : 2;   // floats per shared-memory access of the staged window (a warp's
@@ -279,7 +280,10 @@ BTK_HD void synth_transform_store(Ctx& ctx, cf* s_xbuf, const cf* s_twa, const c
   auto slot = [&](int warp, int grp) { return s_xbuf + ((warp * K::NG + grp) * K::PP) * G::XBUF; };
   ctx.par([&](int tid, TS& ts) {
     const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
-    if (owns(grp)) GroupFFT<M_, -1>::template step1_multi<NP>(ts.g, gl, slot(warp, grp), s_twa);
+    if (owns(grp)) {
+      if (G::ASYM) GroupFFT<M_, -1>::template inv_step1_multi<NP>(ts.g, gl, slot(warp, grp), s_twa);
+      else GroupFFT<M_, -1>::template step1_multi<NP>(ts.g, gl, slot(warp, grp), s_twa);
+    }
   });
   ctx.syncwarp();
   if (G::Rb > 1) {
@@ -305,7 +309,8 @@ BTK_HD void synth_transform_store(Ctx& ctx, cf* s_xbuf, const cf* s_twa, const c
     if (owns(grp)) {
       BTK_UNROLL
       for (int pp = 0; pp < NP; pp++) {
-        GroupFFT<M_, -1>::step3(ts.g + pp * G::V, gl, slot(warp, grp) + pp * G::XBUF);
+        if (G::ASYM) GroupFFT<M_, -1>::inv_step3(ts.g + pp * G::V, gl, slot(warp, grp) + pp * G::XBUF);
+        else GroupFFT<M_, -1>::step3(ts.g + pp * G::V, gl, slot(warp, grp) + pp * G::XBUF);
         const int f = K::FW * warp + 2 * (K::NG == 1 ? pp : grp);        // frame of the iteration
         const int tau0 = tau_base + f;
         // v of frames before the stream start is zero (the synthesis buffer starts zeroed, modulated.cc:666-674)

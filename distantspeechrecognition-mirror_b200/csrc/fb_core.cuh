@@ -93,6 +93,8 @@ template <int S> BTK_HD cf multw(cf a, cf w) { return S > 0 ? cmul(a, w) : cmulc
 #define BTK_SQRT1_2 0.70710678118654752440f
 #define BTK_COS_PI_8 0.92387953251128675613f
 #define BTK_SIN_PI_8 0.38268343236508977173f
+#define BTK_COS_PI_16 0.98078528040323044913f
+#define BTK_SIN_PI_16 0.19509032201612826785f
 
 // ---------------------------------------------------------------------------------------------
 // Small in-register DFTs, natural-order in and out:  X[k] = sum_n x[n] e^{S j 2 pi n k / R}.
@@ -191,7 +193,14 @@ template <int M_> struct FFTPlan;
 template <> struct FFTPlan<64>   { static constexpr int M = 64,   Ra = 8,  Rb = 1, Rc = 8,  V = 8,  L = 8;  };
 template <> struct FFTPlan<128>  { static constexpr int M = 128,  Ra = 8,  Rb = 2, Rc = 8,  V = 8,  L = 16; };
 template <> struct FFTPlan<256>  { static constexpr int M = 256,  Ra = 16, Rb = 1, Rc = 16, V = 16, L = 16; };
+#ifdef BTK_FFT512_3PASS    // A/B: the three-pass plan of the first sessions (two exchanges, 32 lanes per transform)
 template <> struct FFTPlan<512>  { static constexpr int M = 512,  Ra = 16, Rb = 2, Rc = 16, V = 16, L = 32; };
+#else
+// 512 = 32 x 16 with ONE exchange: radix-32 in registers, then radix-16; 16 lanes per transform (two channels per warp).
+// Ra != Rc: the spectrum comes out in a register order different from the time-domain one (see FFTGeom::index_of_spec),
+// and the synthesis direction runs the transposed flow (radix-16 first, GroupFFT::inv_*).
+template <> struct FFTPlan<512>  { static constexpr int M = 512,  Ra = 32, Rb = 1, Rc = 16, V = 32, L = 16; };
+#endif
 #ifdef BTK_FFT1024_3PASS   // A/B: the three-pass plan of the first sessions (two exchanges)
 template <> struct FFTPlan<1024> { static constexpr int M = 1024, Ra = 16, Rb = 4, Rc = 16, V = 32, L = 32; };
 #else
@@ -204,7 +213,9 @@ template <int M_> struct FFTGeom {
   static constexpr int NG = 32 / L;            // groups per warp
   static constexpr int JA = M / Ra;            // owners of pass A per transform (= Rb*Rc)
   static constexpr int RepA = V / Ra;          // radix-Ra DFTs per lane in pass A (and C)
+  static constexpr int RepC = V / Rc;          // radix-Rc DFTs per lane in pass C
   static constexpr int RepB = (Rb > 1) ? V / Rb : 0;
+  static constexpr bool ASYM = (Rb == 1) && (Ra != Rc);   // time-domain and spectrum register orders differ
   static constexpr int PadA = (Rc % 32 == 0) ? 0 : Rc;  // S1 == Rc (mod 32) keeps pass-B reads conflict free
   static constexpr int S1 = JA + PadA;         // row stride (complex words) of exchange 1: idx = ka*S1 + j
   static constexpr int S2 = Rc + 1;            // row stride of exchange 2: idx = iC*S2 + nc
@@ -212,7 +223,11 @@ template <int M_> struct FFTGeom {
   static constexpr int X2 = (M / Rc) * S2;
   static constexpr int XBUF = X1 > X2 ? X1 : X2;   // complex words per group
   // register <-> transform index
+  // time-domain order (input of the analysis transform, output of the synthesis transform)
   static BTK_HD int index_of(int gl, int r) { return (gl + L * (r / Ra)) + JA * (r % Ra); }
+  // spectrum order (output of the analysis transform, input of the synthesis transform): value r = rep*Rc + kc of a
+  // lane is bin (gl + L rep) + Ra kc.  Identical to index_of unless ASYM.
+  static BTK_HD int index_of_spec(int gl, int r) { return ASYM ? (gl + L * (r / Rc)) + Ra * (r % Rc) : index_of(gl, r); }
 };
 
 // Twiddle seeds (built on the host by host_tables.h::build_fft_tables, copied to shared memory by every tile
@@ -330,10 +345,50 @@ template <int M_, int S> struct GroupFFT {
     }
   }
 
+  // ---- transposed flow for ASYM plans (spectrum order in, time-domain order out):
+  //   n = nc + Rc na, k = ka + Ra kc:  x[n] = sum_ka W_Ra^{S na ka} W_M^{S nc ka} sum_kc X[ka + Ra kc] W_Rc^{S nc kc}
+  // inv_step1: radix-Rc over kc (lane holds ka = gl + L rep), twiddle W_M^{S nc ka}, scatter to xb[ka * S2 + nc];
+  // inv_step3: lane nc = gl gathers all ka and runs radix-Ra: value na is sample gl + Rc na = index_of(gl, na).
+  // The twiddle seed W_M^{ka} is twa[gl] (ka < L) times the constant W_M^{L rep}.
+  template <int PP>
+  static BTK_HD void inv_step1_multi(cf* v, int gl, cf* xb, const cf* twa) {
+    static_assert(!G::ASYM || G::Rc <= 16, "product tree of the pass twiddles");
+    static_assert(!G::ASYM || (G::RepC <= 2 && 32 * G::L == M_), "W_M^L is hard-wired as e^{j pi / 16}");
+    BTK_UNROLL
+    for (int rep = 0; rep < G::RepC; rep++) {
+      BTK_UNROLL
+      for (int pp = 0; pp < PP; pp++) Dft<G::Rc, S>::run(v + pp * G::V + rep * G::Rc);
+      const int ka = gl + G::L * rep;
+      cf w[G::Rc + 1];
+      w[1] = twa[gl * FT::TA];
+      if (rep > 0) w[1] = cmul(w[1], mk(BTK_COS_PI_16, BTK_SIN_PI_16));     // W_M^{L}: 2 pi L / M = pi / 16 (static_assert below)
+      BTK_UNROLL
+      for (int nc = 2; nc < G::Rc; nc++) {
+        const int hi = nc >= 8 ? 8 : (nc >= 4 ? 4 : 2);
+        w[nc] = (nc == hi) ? cmul(w[nc / 2], w[nc / 2]) : cmul(w[hi], w[nc - hi]);
+      }
+      BTK_UNROLL
+      for (int pp = 0; pp < PP; pp++) {
+        cf* p = v + pp * G::V + rep * G::Rc;
+        cf* x = xb + pp * G::XBUF;
+        BTK_UNROLL
+        for (int nc = 1; nc < G::Rc; nc++) p[nc] = multw<S>(p[nc], w[nc]);
+        BTK_UNROLL
+        for (int nc = 0; nc < G::Rc; nc++) x[ka * G::S2 + nc] = p[nc];
+      }
+    }
+  }
+  static BTK_HD void inv_step3(cf* v, int gl, const cf* xb) {
+    static_assert(!G::ASYM || G::RepA == 1, "one radix-Ra transform per lane");
+    BTK_UNROLL
+    for (int ka = 0; ka < G::Ra; ka++) v[ka] = xb[ka * G::S2 + gl];
+    Dft<G::Ra, S>::run(v);
+  }
+
   // step 3: gather for pass C and radix-Rc; result in the canonical register layout.
   static BTK_HD void step3(cf* v, int gl, const cf* xb) {
     BTK_UNROLL
-    for (int rep = 0; rep < G::RepA; rep++) {
+    for (int rep = 0; rep < G::RepC; rep++) {
       const int iC = gl + G::L * rep;
       cf* p = v + rep * G::Rc;
       BTK_UNROLL

@@ -130,7 +130,7 @@ inline void ds_weights(const double* delays, double fs, int M, int C, std::vecto
 // Hermitian-extended conjugate weight table for the fused chain (see chain_tile.cuh header):
 //   gam[c][k] = conj(w[k][c]) for 0 < k < M/2 ; gam[c][M-k] = w[k][c] ; real part only at k = 0, M/2,
 // stored in the register order of the transform: element ((c*(V/2) + r2)*L + gl)*2 + i holds bin
-// index_of(gl, 2 r2 + i), so that a lane's two consecutive registers are one 16-byte load and the lanes of a
+// index_of_spec(gl, 2 r2 + i), so that a lane's two consecutive registers are one 16-byte load and the lanes of a
 // group read consecutive 16-byte words.
 template <int M_>
 inline void build_chain_weight_table_m(const zd* w, int C, int Cpad, std::vector<cf>& gam) {
@@ -148,7 +148,7 @@ inline void build_chain_weight_table_m(const zd* w, int C, int Cpad, std::vector
     }
     for (int gl = 0; gl < G::L; gl++)
       for (int r = 0; r < G::V; r++)
-        gam[(((size_t)c * (G::V / 2) + r / 2) * G::L + gl) * 2 + (r & 1)] = row[G::index_of(gl, r)];
+        gam[(((size_t)c * (G::V / 2) + r / 2) * G::L + gl) * 2 + (r & 1)] = row[G::index_of_spec(gl, r)];
   }
 }
 inline bool build_chain_weight_table(const zd* w, int M, int C, int Cpad, std::vector<cf>& gam) {

@@ -54,7 +54,7 @@ int fb_smem_bytes(int M, int R, int m) {
   BTK_DISPATCH(fb_smem_bytes, R, m)
   return -1;
 }
-int fb_frames_per_iter(int M, int) { return M >= 1024 ? 8 : 16; }  // ChainCfg::W = 2 * NW (staged kernels)
+int fb_frames_per_iter(int M, int R) { return (M >= 1024 || (M == 512 && R == 1)) ? 8 : 16; }  // ChainCfg::W = 2 * NW (staged kernels)
 int chain_frames_per_iter(int M, int R, int m) {                   // the fused chain may window two pairs per warp
   if (!fb_supported(M, R)) return -1;
   BTK_DISPATCH(chain_frames_per_iter, R, m)

@@ -66,7 +66,7 @@ BTK_HD void analysis_tile(Ctx& ctx, const AnalysisParams& p, unsigned char* smem
           const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
           cf* xb = s_xbuf + (warp * K::NG + grp) * G::XBUF;
           BTK_UNROLL
-          for (int r = 0; r < G::V; r++) xb[G::index_of(gl, r)] = ts.z[r];
+          for (int r = 0; r < G::V; r++) xb[G::index_of_spec(gl, r)] = ts.z[r];
         });
         ctx.syncwarp();
         ctx.par([&](int tid, TS& ts) {
@@ -77,7 +77,7 @@ BTK_HD void analysis_tile(Ctx& ctx, const AnalysisParams& p, unsigned char* smem
           const bool ok0 = c < C && f0 < wk.j0 + wk.nj && f0 < F, ok1 = c < C && f1 < wk.j0 + wk.nj && f1 < F;
           BTK_UNROLL
           for (int r = 0; r < G::V; r++) {
-            const int k = G::index_of(gl, r);
+            const int k = G::index_of_spec(gl, r);
             if (k > M_ / 2) continue;
             const cf zk = ts.z[r];
             const cf zm = xb[(M_ - k) & (M_ - 1)];
@@ -143,7 +143,7 @@ BTK_HD void synthesis_tile(Ctx& ctx, const SynthesisParams& p, unsigned char* sm
       const bool ok0 = tau0 >= 0 && tau0 < F, ok1 = tau1 >= 0 && tau1 < F;
       BTK_UNROLL
       for (int r = 0; r < G::V; r++) {
-        const int k = G::index_of(gl, r);
+        const int k = G::index_of_spec(gl, r);
         const int kk = k <= M_ / 2 ? k : M_ - k;
         cf a = ok0 ? Y[(long long)tau0 * B + kk] : mk(0.f, 0.f);
         cf b = ok1 ? Y[(long long)tau1 * B + kk] : mk(0.f, 0.f);

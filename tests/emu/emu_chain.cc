@@ -12,7 +12,7 @@
 using namespace btk;
 
 #ifndef BTK_EMU_CASES
-#define BTK_EMU_CASES(X) X(64, 1) X(64, 8) X(64, 2) X(128, 2) X(128, 4) X(256, 1) X(256, 2) X(256, 4) X(512, 2) X(512, 4) X(512, 8) X(1024, 2) X(1024, 4)
+#define BTK_EMU_CASES(X) X(64, 1) X(64, 8) X(64, 2) X(128, 2) X(128, 4) X(256, 1) X(256, 2) X(256, 4) X(512, 1) X(512, 2) X(512, 4) X(512, 8) X(1024, 2) X(1024, 4)
 #endif
 
 template <int M, int PP = 1> struct HostCtx {

@@ -39,6 +39,7 @@ CASES = [  # M, m, r, dct, C, T, chunk
     (128, 2, 1, 0, 5, 900, 25),
     (64, 2, 1, 0, 6, 500, 25),
     (1024, 2, 2, 0, 2, 4000, 32),
+    (512, 2, 0, 0, 3, 5000, 24),
 ]
 
 
