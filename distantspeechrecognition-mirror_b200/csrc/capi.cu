@@ -142,6 +142,9 @@ int btkb200_plan_create(btkb200_plan** out, unsigned M, unsigned m, unsigned r, 
   *out = nullptr;
   if (M == 0 || m == 0 || C == 0 || r > 8) return fail(nullptr, BTKB200_EINVAL, "bad geometry M=%u m=%u r=%u C=%u", M, m, r, C);
   const int R = 1 << r;
+  // delayCompensationType 2 looks m R / 2 - 1 frames ahead (modulated.cc:285-290, an unsigned in the reference): with
+  // m R = 1 that underflows and the reference's behaviour is undefined -- refused here
+  if (dct == 2 && m * R < 2) return fail(nullptr, BTKB200_EINVAL, "delayCompensationType 2 needs m*R >= 2 (got %u)", m * R);
   if (!fb_supported((int)M, R) || (M % R) != 0)
     return fail(nullptr, BTKB200_EUNSUPPORTED, "no kernel for M=%u, R=%d (supported: M in {64,128,256,512,1024}, r in 0..3)", M, R);
   const int smem = fb_smem_bytes((int)M, R, (int)m);

@@ -269,3 +269,11 @@ def test_linearity_property_full_size(prototypes):
     # steering at the true direction of arrival passes the source: output power ~ source power / D^2
     assert np.std(y1) * 128 > 0.5 * 8000 / np.sqrt(2)
     plan.close()
+
+
+def test_dct2_with_unit_prototype_span_is_refused(prototypes):
+    """delayCompensationType 2 with m*R = 1: the reference's look-ahead m R / 2 - 1 underflows (modulated.cc:285-290)."""
+    h, g = wl.kaiser_prototype(256, 1, 0)
+    with pytest.raises(btk_b200.BtkError) as e:
+        btk_b200.Plan(256, 1, 0, 2, h, g, dct=2)
+    assert e.value.code == btk_b200._capi.EINVAL
