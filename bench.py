@@ -354,11 +354,26 @@ def run_ours(args, wl_cfg, rank, world, local_rank):
     if not np.isfinite(float(h_out[0, : 4 * D].double().abs().sum())):
         raise SystemExit("bench.py: 16-bit end-to-end output is not finite")
 
+    # ---- optional: per-utterance adaptive MVDR, end to end (covariance on a 1-s lead-in -> loading -> solve -> chain)
+    mvdr_s = 0.0
+    if args.mvdr:
+        lead = int(FS // D)          # frames of the first second
+        kw = dict(forget=0.99, last_frame=lead, conjugate=True, load_abs=0.0, load_rel=1e-2)
+        plan.mvdr_chain_batch_into(xs, outs, **kw)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            nfb = plan.mvdr_chain_batch_into(xs, outs, **kw)
+        torch.cuda.synchronize()
+        mvdr_s = (time.perf_counter() - t0) / e2e_steps
+        if int(nfb.sum()) != 0 or not np.isfinite(float(h_out[0, : 4 * D].double().abs().sum())):
+            raise SystemExit("bench.py: adaptive MVDR produced fallback bins or non-finite output")
+
     # ---- max over ranks
-    tt = torch.tensor([total_ms, kern_ms, e2e_s, e2e16_s], dtype=torch.float64, device=dev)
+    tt = torch.tensor([total_ms, kern_ms, e2e_s, e2e16_s, mvdr_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    total_ms, kern_ms, e2e_s, e2e16_s = [float(v) for v in tt.tolist()]
+    total_ms, kern_ms, e2e_s, e2e16_s, mvdr_s = [float(v) for v in tt.tolist()]
     if old_affinity:
         os.sched_setaffinity(0, old_affinity)
 
@@ -396,6 +411,12 @@ def run_ours(args, wl_cfg, rank, world, local_rank):
                                "note": "same call with 16-bit PCM host buffers (btkb200_chain_batch_pcm), converted on the device"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        if args.mvdr:
+            line["e2e_adaptive_mvdr"] = {
+                "value": world * units_per_step / mvdr_s, "unit": UNIT, "ms_per_step": mvdr_s * 1e3,
+                "h2d_bytes_per_step": int(nb * n_in * 4), "d2h_bytes_per_step": int(nb * n_out * 4),
+                "note": "btkb200_mvdr_chain_batch: per utterance covariance (x x^H, ff 0.99) on the first second -> load 1e-2 "
+                        "trace/C -> per-bin MVDR solve -> fused chain with that utterance's weights; host buffers in and out"}
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             ctx = mp.get_context("spawn")
@@ -421,6 +442,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="utterances per GPU (default: per workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mvdr", action="store_true", help="also time the per-utterance adaptive MVDR path end to end")
     args = ap.parse_args()
     wl_cfg = dict(WORKLOADS[args.workload])
     if args.batch > 0:

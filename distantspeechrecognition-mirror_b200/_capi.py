@@ -25,12 +25,17 @@ SYMBOLS = [
     "btkb200_set_covariance", "btkb200_get_covariance", "btkb200_set_diffuse_noise_model", "btkb200_diag_load",
     "btkb200_diag_load_bin", "btkb200_divide_nondiagonal", "btkb200_solve_mvdr", "btkb200_analysis",
     "btkb200_beamform", "btkb200_synthesis", "btkb200_covariance", "btkb200_estimate_covariance", "btkb200_chain",
-    "btkb200_chain_batch", "btkb200_chain_batch_pcm", "btkb200_convert_pcm", "btkb200_beamform_zelinski",
+    "btkb200_chain_batch", "btkb200_mvdr_chain_batch", "btkb200_chain_batch_pcm", "btkb200_convert_pcm", "btkb200_beamform_zelinski",
     "btkb200_chain_zelinski", "btkb200_beamform_zelinski_dev", "btkb200_gsc_calc_weights",
     "btkb200_design_analysis_prototype", "btkb200_design_synthesis_prototype", "btkb200_gsc_set_active_weights", "btkb200_gsc_zero_active_weights", "btkb200_gsc_get_blocking_matrix", "btkb200_gsc_apply",
     "btkb200_chain_batch_multi", "btkb200_chain_batch_dev", "btkb200_analysis_dev", "btkb200_beamform_dev",
     "btkb200_synthesis_dev", "btkb200_launch_count", "btkb200_sync", "btkb200_host_alloc", "btkb200_host_free",
 ]
+
+
+class MvdrAdapt(ctypes.Structure):
+    _fields_ = [("forget", c_double), ("last_frame", c_long), ("conjugate", c_int), ("load_abs", c_double),
+                ("load_rel", c_double), ("dThreshold", c_double)]
 
 
 class Info(ctypes.Structure):
@@ -90,6 +95,7 @@ def lib() -> ctypes.CDLL:
     L.btkb200_estimate_covariance.argtypes = [vp, vp, c_long, c_double, c_long, c_int]
     L.btkb200_chain.argtypes = [vp, vp, c_long, vp]
     L.btkb200_chain_batch.argtypes = [vp, POINTER(vp), POINTER(c_long), c_int, POINTER(vp)]
+    L.btkb200_mvdr_chain_batch.argtypes = [vp, POINTER(vp), POINTER(c_long), c_int, POINTER(MvdrAdapt), POINTER(vp), vp]
     L.btkb200_chain_batch_pcm.argtypes = [vp, POINTER(vp), c_int, POINTER(c_long), c_int, POINTER(vp)]
     L.btkb200_convert_pcm.argtypes = [vp, vp, c_int, c_long, vp]
     L.btkb200_beamform_zelinski.argtypes = [vp, vp, c_long, c_double, c_int, c_int, vp, vp]
@@ -347,6 +353,25 @@ class Plan:
         oo = (c_void_p * n)(*[o.ctypes.data for o in outs])
         TT = (c_long * n)(*[x.shape[0] for x in xs])
         self._ck(self._L.btkb200_chain_batch(self._h, pp, TT, n, oo))
+
+    def mvdr_chain_batch_into(self, xs, outs, forget=0.99, last_frame=-1, conjugate=True, load_abs=0.0, load_rel=0.0,
+                              dThreshold=1e-8):
+        """Per-recording covariance -> loading -> MVDR solve -> fused chain, all on the device.  Returns the number of
+        identity-fallback bins per recording."""
+        n = len(xs)
+        pp = (c_void_p * n)(*[x.ctypes.data for x in xs])
+        oo = (c_void_p * n)(*[o.ctypes.data for o in outs])
+        TT = (c_long * n)(*[x.shape[0] for x in xs])
+        cfg = MvdrAdapt(forget, last_frame, 1 if conjugate else 0, load_abs, load_rel, dThreshold)
+        nfb = np.zeros(n, dtype=np.int32)
+        self._ck(self._L.btkb200_mvdr_chain_batch(self._h, pp, TT, n, ctypes.byref(cfg), oo, _p(nfb)))
+        return nfb
+
+    def mvdr_chain_batch(self, pcms, **kw):
+        xs = [np.ascontiguousarray(x, dtype=np.float32) for x in pcms]
+        outs = [np.empty(self.chain_frames(x.shape[0]) * self.D, dtype=np.float32) for x in xs]
+        nfb = self.mvdr_chain_batch_into(xs, outs, **kw)
+        return outs, nfb
 
     def chain_batch_pcm_into(self, raws, fmt: int, Ts, outs):
         """raws: C-contiguous arrays of raw interleaved PCM -- float32 [T][C] (PCM_F32), int16 [T][C] (PCM_S16) or

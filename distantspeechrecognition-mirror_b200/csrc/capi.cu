@@ -62,7 +62,7 @@ struct btkb200_plan {
   cf* d_w = nullptr;           // [B][C]
   cf* d_ta = nullptr;          // [B][C] array manifold (time alignment of the post-filter)
   // scratch
-  DevBuf d_recs, d_work, d_in, d_out, d_aux, d_aux2, d_raw;
+  DevBuf d_recs, d_work, d_in, d_out, d_aux, d_aux2, d_raw, d_adapt;
   PinBuf h_desc;
   std::vector<long long> sig;  // signature of the cached chain work list
   int cached_n_work = 0;
@@ -200,7 +200,7 @@ void btkb200_plan_destroy(btkb200_plan* p) {
   cudaSetDevice(p->device);
   if (p->stream) cudaStreamSynchronize(p->stream);
   cudaFree(p->d_taps_h); cudaFree(p->d_taps_g); cudaFree(p->d_twa); cudaFree(p->d_twb); cudaFree(p->d_wts_chain); cudaFree(p->d_w); cudaFree(p->d_ta);
-  p->d_recs.release(); p->d_work.release(); p->d_in.release(); p->d_out.release(); p->d_aux.release(); p->d_aux2.release(); p->d_raw.release();
+  p->d_recs.release(); p->d_work.release(); p->d_in.release(); p->d_out.release(); p->d_aux.release(); p->d_aux2.release(); p->d_raw.release(); p->d_adapt.release();
   p->h_desc.release();
   if (p->stream) cudaStreamDestroy(p->stream);
   if (p->s_in) cudaStreamDestroy(p->s_in);
@@ -576,11 +576,13 @@ static int chain_prepare(btkb200_plan* p, const long long* pcm_off, const long l
 }
 
 // Launch the work items [w0, w1) of the prepared batch.
-static int chain_launch(btkb200_plan* p, const float* d_pcm, float* d_out, int w0, int w1, cudaStream_t st) {
+static int chain_launch(btkb200_plan* p, const float* d_pcm, float* d_out, int w0, int w1, cudaStream_t st,
+                        const cf* wts = nullptr, long long wts_stride = 0) {
   if (w1 <= w0) return BTKB200_OK;
   ChainParams c;
   c.pcm = d_pcm; c.out = d_out; c.recs = (const RecDesc*)p->d_recs.p; c.work = (const WorkItem*)p->d_work.p + w0;
-  c.taps_h = p->d_taps_h; c.taps_g = p->d_taps_g; c.wts = p->d_wts_chain; c.twa = p->d_twa; c.twb = p->d_twb;
+  c.taps_h = p->d_taps_h; c.taps_g = p->d_taps_g; c.wts = wts ? wts : p->d_wts_chain; c.wts_stride = wts_stride;
+  c.twa = p->d_twa; c.twb = p->d_twb;
   c.C = p->C; c.Cpad = p->Cpad; c.m = p->geo.m; c.pd_s = p->geo.pd_s; c.laN = p->geo.laN; c.gain = p->gain;
   CK(p, launch_chain(p->geo.M, p->geo.R, c, w1 - w0, st));
   p->launches++;
@@ -849,6 +851,144 @@ int btkb200_chain_batch_pcm(btkb200_plan* p, const void* const* pcm, int format,
   }
   CK(p, cudaStreamSynchronize(p->s_out));
   CK(p, cudaStreamSynchronize(p->stream));
+  return BTKB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------- adaptive MVDR, batched
+static void recursion_weights(std::vector<double>& wt, long Fu, double forget, int conjugate) {
+  // frame f of the unrolled recursion contributes (1-ff) ff^(Fu-1-f); the Python flavour starts from S = x0 x0^H
+  wt.assign((size_t)(Fu > 0 ? Fu : 1), 0.0);
+  double acc = 1.0;
+  for (long f = Fu - 1; f >= 0; f--) { wt[f] = (1.0 - forget) * acc; acc *= forget; }
+  if (conjugate && Fu > 0) wt[0] = pow(forget, (double)(Fu - 1));
+}
+
+int btkb200_mvdr_chain_batch(btkb200_plan* p, const float* const* pcm, const long* T, int n, const btkb200_mvdr_adapt* cfg,
+                             float* const* out, int* n_fallback) {
+  if (!p || !pcm || !T || !out || !cfg || n < 0) return BTKB200_EINVAL;
+  if (!(cfg->forget >= 0.0 && cfg->forget <= 1.0)) return fail(p, BTKB200_EINVAL, "forgetting factor %g outside [0, 1]", cfg->forget);
+  if (!p->has_h || !p->has_g) return fail(p, BTKB200_ESTATE, "the fused chain needs both prototypes");
+  if (!p->has_manifold) return fail(p, BTKB200_ESTATE, "call calcArrayManifoldVectorsX() once");
+  if (p->C > 64) return fail(p, BTKB200_EUNSUPPORTED, "MVDR adaptation supports at most 64 channels (got %d)", p->C);
+  if (n == 0) return BTKB200_OK;
+  CK(p, cudaSetDevice(p->device));
+  const int B = p->geo.B, C = p->C, M = p->geo.M, D = p->geo.D, Cpad = p->Cpad;
+  // ---- batch layout (like btkb200_chain_batch)
+  std::vector<long long> poff(n), ooff(n), Tl(n);
+  long long pin = 0, pout = 0;
+  for (int i = 0; i < n; i++) {
+    if (T[i] < 0 || !pcm[i] || !out[i]) return fail(p, BTKB200_EINVAL, "recording %d: bad buffer or length", i);
+    poff[i] = pin; ooff[i] = pout; Tl[i] = T[i];
+    pin += ((long long)T[i] * C + 3) / 4 * 4;
+    pout += ((long long)p->geo.chain_frames(T[i]) * D + 3) / 4 * 4;
+  }
+  CK(p, p->d_in.reserve((size_t)(pin ? pin : 4) * sizeof(float)));
+  CK(p, p->d_out.reserve((size_t)(pout ? pout : 4) * sizeof(float)));
+  if (!p->s_in) CK(p, cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
+  int rc = chain_prepare(p, poff.data(), Tl.data(), ooff.data(), n, p->stream);
+  if (rc) return rc;
+  // ---- per-recording adaptation descriptors: analysis of the adapting lead-in only, recursion weights
+  std::vector<RecDesc> arecs(n);
+  std::vector<WorkItem> awork;
+  std::vector<int> awb(n + 1, 0), aslices(n, 1);
+  std::vector<long> Fu(n);
+  std::vector<double> fw_all, wt;
+  std::vector<long long> fwoff(n);
+  const int Wa = fb_frames_per_iter(M, p->geo.R), n_cg = Cpad / 4;
+  size_t max_snap = 16;
+  for (int i = 0; i < n; i++) {
+    const long F = p->geo.analysis_frames(T[i]);
+    Fu[i] = (cfg->last_frame >= 0 && cfg->last_frame + 1 < F) ? cfg->last_frame + 1 : F;
+    // frames 0 .. Fu-1 only look at samples below (Fu + laN) D: analyse just that lead-in
+    long Ta = (long)((long long)(Fu[i] + p->geo.laN) * D);
+    if (Ta > T[i]) Ta = T[i];
+    const long Fa = Fu[i];
+    arecs[i].pcm_off = poff[i]; arecs[i].out_off = 0; arecs[i].T = (int)Ta; arecs[i].nblk = (int)Fa;
+    std::vector<RecDesc> one(1, arecs[i]);
+    std::vector<WorkItem> w1;
+    long long chunk = ((long long)Fa + 148 * 4 - 1) / (148 * 4);
+    chunk = (chunk + Wa - 1) / Wa * Wa;
+    if (chunk < Wa) chunk = Wa;
+    build_work(one, (int)chunk, w1);
+    for (size_t k = 0; k < w1.size(); k++) { w1[k].rec = i; awork.push_back(w1[k]); }
+    awb[i + 1] = (int)awork.size();
+    int slices = w1.empty() ? 1 : (int)(2 * 148 / w1.size());
+    if (slices < 1) slices = 1;
+    if (slices > n_cg) slices = n_cg;
+    aslices[i] = slices;
+    recursion_weights(wt, Fu[i], cfg->forget, cfg->conjugate);
+    fwoff[i] = (long long)fw_all.size();
+    fw_all.insert(fw_all.end(), wt.begin(), wt.end());
+    const size_t bs = (size_t)Fa * B * C * sizeof(cf);
+    if (bs > max_snap) max_snap = bs;
+  }
+  std::vector<int> binmap;
+  if (!build_weight_binmap(M, binmap)) return fail(p, BTKB200_EUNSUPPORTED, "no weight layout for M=%d", M);
+  // ---- one scratch allocation: descriptors | recursion weights | bin map | manifold | R | w | fallback flags | tables | snapshots
+  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+  const size_t o_arecs = 0, o_awork = o_arecs + al(arecs.size() * sizeof(RecDesc));
+  const size_t o_fw = o_awork + al((awork.size() ? awork.size() : 1) * sizeof(WorkItem));
+  const size_t o_map = o_fw + al(fw_all.size() * sizeof(double));
+  const size_t o_d = o_map + al(binmap.size() * sizeof(int));
+  const size_t o_R = o_d + al((size_t)B * C * sizeof(double2));
+  const size_t o_w = o_R + al((size_t)B * C * C * sizeof(double2));
+  const size_t o_fb = o_w + al((size_t)B * C * sizeof(double2));
+  const size_t o_tab = o_fb + al((size_t)n * B * sizeof(int));
+  const size_t o_snap = o_tab + al((size_t)n * Cpad * M * sizeof(cf));
+  CK(p, p->d_adapt.reserve(o_snap + al(max_snap)));
+  char* base = (char*)p->d_adapt.p;
+  CK(p, cudaStreamSynchronize(p->stream));
+  CK(p, cudaMemcpy(base + o_arecs, arecs.data(), arecs.size() * sizeof(RecDesc), cudaMemcpyHostToDevice));
+  if (!awork.empty()) CK(p, cudaMemcpy(base + o_awork, awork.data(), awork.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
+  CK(p, cudaMemcpy(base + o_fw, fw_all.data(), fw_all.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CK(p, cudaMemcpy(base + o_map, binmap.data(), binmap.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CK(p, cudaMemcpy(base + o_d, p->wq.data(), (size_t)B * C * sizeof(double2), cudaMemcpyHostToDevice));
+  double2* dR = (double2*)(base + o_R);
+  double2* dw = (double2*)(base + o_w);
+  int* dfb = (int*)(base + o_fb);
+  cf* dtab = (cf*)(base + o_tab);
+  cf* dsnap = (cf*)(base + o_snap);
+  // ---- adaptation, recording by recording on the plan's stream; the uploads run ahead on the copy stream
+  while ((int)p->ev_in.size() < n) { cudaEvent_t e; CK(p, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); p->ev_in.push_back(e); }
+  for (int i = 0; i < n; i++) {
+    if (T[i] > 0)
+      CK(p, cudaMemcpyAsync((float*)p->d_in.p + poff[i], pcm[i], (size_t)T[i] * C * sizeof(float), cudaMemcpyHostToDevice, p->s_in));
+    CK(p, cudaEventRecord(p->ev_in[i], p->s_in));
+  }
+  for (int i = 0; i < n; i++) {
+    CK(p, cudaStreamWaitEvent(p->stream, p->ev_in[i], 0));
+    CK(p, cudaMemsetAsync(dR, 0, (size_t)B * C * C * sizeof(double2), p->stream));
+    const int nw = awb[i + 1] - awb[i];
+    if (nw > 0 && Fu[i] > 0) {
+      AnalysisParams a;
+      a.pcm = (const float*)p->d_in.p; a.snap = dsnap; a.recs = (const RecDesc*)(base + o_arecs);
+      a.work = (const WorkItem*)(base + o_awork) + awb[i];
+      a.taps_h = p->d_taps_h; a.twa = p->d_twa; a.twb = p->d_twb; a.C = C; a.Cpad = Cpad; a.m = p->geo.m; a.laN = p->geo.laN;
+      a.cg_slices = aslices[i];
+      CK(p, launch_analysis(M, p->geo.R, a, nw * aslices[i], p->stream));
+      CK(p, launch_covariance(dsnap, (const double*)(base + o_fw) + fwoff[i], dR, Fu[i], B, C, cfg->conjugate ? 1 : 0, p->stream));
+      p->launches += 2;
+    }
+    if (cfg->load_abs != 0.0 || cfg->load_rel != 0.0) {
+      CK(p, launch_diag_load(dR, B, C, (float)cfg->load_abs, cfg->load_rel, p->stream));
+      p->launches++;
+    }
+    CK(p, launch_mvdr_solve(dR, (const double2*)(base + o_d), dw, dfb + (size_t)i * B, B, C, cfg->dThreshold, p->stream));
+    CK(p, launch_weight_table(dw, (const int*)(base + o_map), dtab + (size_t)i * Cpad * M, M, C, Cpad, p->stream));
+    p->launches += 2;
+  }
+  // ---- one fused-chain launch over the whole batch, every recording with its own weight table
+  rc = chain_launch(p, (const float*)p->d_in.p, (float*)p->d_out.p, 0, p->cached_n_work, p->stream, dtab, (long long)Cpad * M);
+  if (rc) return rc;
+  for (int i = 0; i < n; i++) {
+    const size_t b = (size_t)p->geo.chain_frames(T[i]) * D * sizeof(float);
+    if (b) CK(p, cudaMemcpyAsync(out[i], (float*)p->d_out.p + ooff[i], b, cudaMemcpyDeviceToHost, p->stream));
+  }
+  std::vector<int> fb;
+  if (n_fallback) { fb.resize((size_t)n * B); CK(p, cudaMemcpyAsync(fb.data(), dfb, fb.size() * sizeof(int), cudaMemcpyDeviceToHost, p->stream)); }
+  CK(p, cudaStreamSynchronize(p->stream));
+  if (n_fallback)
+    for (int i = 0; i < n; i++) { int s = 0; for (int b = 0; b < B; b++) s += fb[(size_t)i * B + b]; n_fallback[i] = s; }
   return BTKB200_OK;
 }
 

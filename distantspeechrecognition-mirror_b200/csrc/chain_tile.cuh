@@ -52,6 +52,7 @@ struct ChainParams {
   const float* taps_h;   // [D][TS]   taps_h[rho*TS + t] = h[rho + D t]            (host_tables.h)
   const float* taps_g;   // [m][M]    gp[k][q] = g[M-1-q + M k]
   const cf* wts;         // [Cpad][V/2][L][2] Hermitian-extended conj weights in register order
+  long long wts_stride;  // elements between the tables of consecutive recordings (0: one table for the whole batch)
   const cf* twa;         // pass-A twiddles, lane-contiguous (FFTTables)
   const cf* twb;         // pass-B twiddles (three-pass transforms only)
   int C, Cpad;
@@ -656,7 +657,7 @@ BTK_HD void chain_tile(Ctx& ctx, const ChainParams& p, unsigned char* smem, int 
 
     for (int cg0 = 0; cg0 < p.Cpad; cg0 += K::CG) {
       // samples + the weights of these CG channels (register order: [c][V/2][L] float4 = 2 complex)
-      stage_window<K>(ctx, L, s_xs, pcm, C, rec.T, t_lo, cg0, vec4, s_wts, p.wts);
+      stage_window<K>(ctx, L, s_xs, pcm, C, rec.T, t_lo, cg0, vec4, s_wts, p.wts + (long long)wk.rec * p.wts_stride);
       if (cg0 == 0 && it + 1 < n_it) prefetch_next_window<K>(ctx, pcm, C, rec.T, t_lo + (long long)L.NB * K::D);
       ctx.sync();
 

@@ -151,6 +151,24 @@ inline void build_chain_weight_table_m(const zd* w, int C, int Cpad, std::vector
         gam[(((size_t)c * (G::V / 2) + r / 2) * G::L + gl) * 2 + (r & 1)] = row[G::index_of_spec(gl, r)];
   }
 }
+// bin index of every slot of one channel's row of the chain weight table (for the device-side table builder)
+template <int M_>
+inline void build_weight_binmap_m(std::vector<int>& map) {
+  typedef FFTGeom<M_> G;
+  map.assign(M_, 0);
+  for (int gl = 0; gl < G::L; gl++)
+    for (int r = 0; r < G::V; r++) map[((size_t)(r / 2) * G::L + gl) * 2 + (r & 1)] = G::index_of_spec(gl, r);
+}
+inline bool build_weight_binmap(int M, std::vector<int>& map) {
+  switch (M) {
+    case 64: build_weight_binmap_m<64>(map); return true;
+    case 128: build_weight_binmap_m<128>(map); return true;
+    case 256: build_weight_binmap_m<256>(map); return true;
+    case 512: build_weight_binmap_m<512>(map); return true;
+    case 1024: build_weight_binmap_m<1024>(map); return true;
+  }
+  return false;
+}
 inline bool build_chain_weight_table(const zd* w, int M, int C, int Cpad, std::vector<cf>& gam) {
   switch (M) {
     case 64: build_chain_weight_table_m<64>(w, C, Cpad, gam); return true;

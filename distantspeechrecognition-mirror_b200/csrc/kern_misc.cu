@@ -114,6 +114,52 @@ cudaError_t launch_beamform(const cf* snap, const cf* w, cf* Y, long long F, int
   return cudaGetLastError();
 }
 
+__device__ __forceinline__ double shfl_d(double v, int src);
+
+// ---------------------------------------------------------------------------------------------
+// Pieces of the device-resident MVDR adaptation (btkb200_mvdr_chain_batch): diagonal loading of the estimated
+// matrices and the chain weight table, both without a trip to the host.
+// ---------------------------------------------------------------------------------------------
+// R[s][c][c] += (double)(float)load_abs + load_rel * trace(R[s]) / C   (setAllLevelsOfDiagonalLoading keeps the weight as a
+// float, beamformer.cc:2342, 2562-2565; the relative term is the "1e-2 trace(R)/C" loading of SURVEY 8d).  One warp per bin.
+__global__ void btk_diag_load_kernel(double2* __restrict__ Rn, int B, int C, float load_abs, double load_rel) {
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (s >= B) return;
+  double2* Rs = Rn + (long long)s * C * C;
+  double tr = 0.0;
+  for (int c = lane; c < C; c += 32) tr += Rs[c * C + c].x;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tr += shfl_d(tr, lane ^ o);
+  const double add = (double)load_abs + load_rel * tr / (double)C;
+  for (int c = lane; c < C; c += 32) Rs[c * C + c].x += add;
+}
+
+// Hermitian-extended conjugate weight table of the fused chain from double weights on the device (the device twin of
+// host_tables.h::build_chain_weight_table; binmap[slot] = bin of table slot ((r/2) L + gl) 2 + (r & 1)).
+__global__ void btk_weight_table_kernel(const double2* __restrict__ w, const int* __restrict__ binmap, cf* __restrict__ gam, int M, int C,
+                                        int Cpad) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Cpad * M) return;
+  const int c = idx / M, slot = idx - c * M;
+  cf v = mk(0.f, 0.f);
+  if (c < C) {
+    const int k = binmap[slot];
+    if (k == 0 || k == M / 2) v = mk((float)w[(long long)k * C + c].x, 0.f);
+    else if (k < M / 2) { const double2 z = w[(long long)k * C + c]; v = mk((float)z.x, (float)-z.y); }
+    else { const double2 z = w[(long long)(M - k) * C + c]; v = mk((float)z.x, (float)z.y); }
+  }
+  gam[idx] = v;
+}
+
+cudaError_t launch_diag_load(double2* Rn, int B, int C, float load_abs, double load_rel, cudaStream_t st) {
+  btk_diag_load_kernel<<<(B + 3) / 4, 128, 0, st>>>(Rn, B, C, load_abs, load_rel);
+  return cudaGetLastError();
+}
+cudaError_t launch_weight_table(const double2* w, const int* binmap, cf* gam, int M, int C, int Cpad, cudaStream_t st) {
+  btk_weight_table_kernel<<<(Cpad * M + 255) / 256, 256, 0, st>>>(w, binmap, gam, M, C, Cpad);
+  return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------
 // Ingest: raw interleaved PCM -> float32 (same [T][C] order).  HBM-bound element-wise converts; four samples per
 // thread per step (8- or 12-byte loads, one 16-byte store).

@@ -39,6 +39,10 @@ cudaError_t launch_beamform_zelinski(const cf* snap, const cf* w, const cf* ta, 
 cudaError_t design_prototype(int kind, const double* h_in, int M, int m, int r, double v, double wp_factor, int tau, double tolerance,
                              double* proto_out, double* err, int* sweeps_out);
 
+// device-resident MVDR adaptation helpers (kern_misc.cu): diagonal loading, chain weight table from device weights
+cudaError_t launch_diag_load(double2* Rn, int B, int C, float load_abs, double load_rel, cudaStream_t st);
+cudaError_t launch_weight_table(const double2* w, const int* binmap, cf* gam, int M, int C, int Cpad, cudaStream_t st);
+
 // Raw PCM -> float32, element for element (bit-exact integer -> float):
 //   fmt 1: int16 little endian (what sf_readf_float returns with SFC_SET_NORM_FLOAT off, feature/feature.cc:273, 868-896)
 //   fmt 2: packed 24-bit big endian, sign extended (Conversion24bit2Float::next, feature/feature.cc:190-217;

@@ -170,6 +170,27 @@ int btkb200_chain_zelinski(btkb200_plan* plan, const float* pcm, long T, double 
 int btkb200_chain(btkb200_plan* plan, const float* pcm, long T, float* out);
 /* n independent recordings (ragged lengths allowed), host buffers. */
 int btkb200_chain_batch(btkb200_plan* plan, const float* const* pcm, const long* T, int n, float* const* out);
+/* Adaptive MVDR over a batch, entirely on the device (BASELINE configs 2-3: "SubbandMVDR with per-subband spatial covariance
+ * + diagonal loading", many utterances).  Per recording, in the reference's own call order:
+ *   SpectralMatrixArray::update over frames 0..last_frame (conjugate = 0, beamformer.cc:142-163) or updateSx (conjugate = 1,
+ *   lib/subbandBeamforming.py:1170-1175)  ->  setNoiseSpatialSpectralMatrix for every bin (beamformer.cc:2454-2477)
+ *   ->  setAllLevelsOfDiagonalLoading(load_abs) (:2555-2568; the weight is kept as a float like there) plus, when
+ *   load_rel != 0, load_rel * trace(R_s) / C per bin  ->  calcMVDRWeights(dThreshold) (:2392-2446)  ->  the fused
+ *   analysis -> weight apply -> synthesis chain with THAT recording's weights.
+ * The analysis of the adapting lead-in, the tensor-core covariance, the loading, the per-bin solve and the chain weight
+ * table run per recording on the device; one fused-chain launch then covers the whole batch with a weight table per
+ * recording.  No subband data, matrices or weights cross PCIe.  n_fallback[i] (or NULL) receives the number of bins of
+ * recording i whose inverse failed (identity fallback, :2425-2427).  The array manifold comes from set_ds_weights. */
+typedef struct btkb200_mvdr_adapt {
+  double forget;     /* forgetting factor of the covariance recursion (mu / ff) */
+  long last_frame;   /* frames 0..last_frame adapt; < 0: every frame */
+  int conjugate;     /* 1: x x^H (updateSx), 0: x x^T (SpectralMatrixArray::update) */
+  double load_abs;   /* setAllLevelsOfDiagonalLoading */
+  double load_rel;   /* additional load_rel * trace(R_s) / C */
+  double dThreshold; /* calcMVDRWeights */
+} btkb200_mvdr_adapt;
+int btkb200_mvdr_chain_batch(btkb200_plan* plan, const float* const* pcm, const long* T, int n,
+                             const btkb200_mvdr_adapt* cfg, float* const* out, int* n_fallback);
 /* Same with raw interleaved PCM in host memory, converted on the device (element order unchanged, exact):
  *   BTKB200_PCM_F32   float32                           (IterativeSampleFeature buffer, feature/feature.cc:868-896)
  *   BTKB200_PCM_S16   int16 little endian               (16-bit WAV payload: what sf_readf_float delivers with
