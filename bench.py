@@ -46,6 +46,8 @@ WORKLOADS = {
                  desc="BASELINE configs[2] geometry: 16-mic linear array, fixed-weight MVDR/DS apply, M=512 m=2 r=2, 16 kHz, 10 s"),
     "m1024": dict(M=1024, m=2, r=1, C=8, seconds=10.0, batch=64, geom="circular",
                   desc="BASELINE configs[4] sweep point: 8 channels, M=1024 m=2 r=1 (Kaiser prototype), 16 kHz, 10 s utterances"),
+    "m128": dict(M=128, m=2, r=1, C=8, seconds=10.0, batch=64, geom="circular",
+                 desc="BASELINE configs[4] sweep point: 8 channels, M=128 m=2 r=1 (Kaiser prototype), 16 kHz, 10 s utterances"),
     "cfg4": dict(M=512, m=2, r=2, C=64, seconds=10.0, batch=32, geom="linear20",
                  desc="BASELINE configs[3] geometry: 64-ch Mark-III-style array, M=512 m=2 r=2, 16 kHz, 10 s utterances"),
 }

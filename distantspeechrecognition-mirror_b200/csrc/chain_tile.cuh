@@ -74,7 +74,10 @@ struct ChainCfg {
   // longer window: one CTA's staging (global-load latency) overlaps the other's transforms.  (M = 512 with 4 warps
   // and two CTAs measured 11-38 % slower than 8 warps and one CTA: the window halo doubles; tools/ab_run2.sh.)
   // (M = 512 without oversampling, D = 512: the window of 8 warps does not fit next to the exchange buffers either)
-  static constexpr int NW = (M_ >= 1024 || (M_ == 512 && R_ == 1) || (PP_ == 2 && M_ <= 256)) ? 4 : 8;
+#ifndef BTK_NW512_4
+#define BTK_NW512_4 0      // tuning: 1 = four-warp CTAs (two per SM) for every M = 512 geometry
+#endif
+  static constexpr int NW = (M_ >= 1024 || (M_ == 512 && (R_ == 1 || BTK_NW512_4)) || (PP_ == 2 && M_ <= 256)) ? 4 : 8;
   static constexpr int NT = NW * 32;
   static constexpr int FW = 2 * PP_;           // frames per warp per iteration
   static constexpr int LV = (FW % 4 == 0) ? 4 : 2;   // floats per shared-memory access of the staged window (a warp's

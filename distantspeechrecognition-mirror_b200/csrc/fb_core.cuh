@@ -191,7 +191,11 @@ template <int S> struct Dft<32, S> { static BTK_HD void run(cf* v) { dft32<S>(v)
 // ---------------------------------------------------------------------------------------------
 template <int M_> struct FFTPlan;
 template <> struct FFTPlan<64>   { static constexpr int M = 64,   Ra = 8,  Rb = 1, Rc = 8,  V = 8,  L = 8;  };
+#ifdef BTK_FFT128_1EXCH    // A/B: 16 x 8 with one exchange measured 5 % SLOWER than the three-pass plan at M = 128 (0.293 vs 0.278 ms)
+template <> struct FFTPlan<128>  { static constexpr int M = 128,  Ra = 16, Rb = 1, Rc = 8,  V = 16, L = 8;  };
+#else
 template <> struct FFTPlan<128>  { static constexpr int M = 128,  Ra = 8,  Rb = 2, Rc = 8,  V = 8,  L = 16; };
+#endif
 template <> struct FFTPlan<256>  { static constexpr int M = 256,  Ra = 16, Rb = 1, Rc = 16, V = 16, L = 16; };
 #ifdef BTK_FFT512_3PASS    // A/B: the three-pass plan of the first sessions (two exchanges, 32 lanes per transform)
 template <> struct FFTPlan<512>  { static constexpr int M = 512,  Ra = 16, Rb = 2, Rc = 16, V = 16, L = 32; };
@@ -353,7 +357,7 @@ template <int M_, int S> struct GroupFFT {
   template <int PP>
   static BTK_HD void inv_step1_multi(cf* v, int gl, cf* xb, const cf* twa) {
     static_assert(!G::ASYM || G::Rc <= 16, "product tree of the pass twiddles");
-    static_assert(!G::ASYM || (G::RepC <= 2 && 32 * G::L == M_), "W_M^L is hard-wired as e^{j pi / 16}");
+    static_assert(!G::ASYM || (G::RepC <= 2 && (32 * G::L == M_ || 16 * G::L == M_)), "W_M^L is hard-wired");
     BTK_UNROLL
     for (int rep = 0; rep < G::RepC; rep++) {
       BTK_UNROLL
@@ -361,7 +365,8 @@ template <int M_, int S> struct GroupFFT {
       const int ka = gl + G::L * rep;
       cf w[G::Rc + 1];
       w[1] = twa[gl * FT::TA];
-      if (rep > 0) w[1] = cmul(w[1], mk(BTK_COS_PI_16, BTK_SIN_PI_16));     // W_M^{L}: 2 pi L / M = pi / 16 (static_assert below)
+      // W_M^{L} with 2 pi L / M = pi / 16 (M = 32 L) or pi / 8 (M = 16 L), see the static_assert below
+      if (rep > 0) w[1] = cmul(w[1], M_ == 32 * G::L ? mk(BTK_COS_PI_16, BTK_SIN_PI_16) : mk(BTK_COS_PI_8, BTK_SIN_PI_8));
       BTK_UNROLL
       for (int nc = 2; nc < G::Rc; nc++) {
         const int hi = nc >= 8 ? 8 : (nc >= 4 ? 4 : 2);
