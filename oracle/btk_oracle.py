@@ -10,7 +10,12 @@ Pinning: the reference ships no golden vectors, so this
 restatement is pinned against the reference ITSELF -- its own .cc files compiled
 in place by ``oracle/Makefile`` into ``oracle/_ref/libbtk_ref.so`` -- in
 ``tests/test_oracle_golden.py`` (test_oracle_matches_compiled_reference) and through the committed fixtures under
-``tests/golden/`` (made by ``tests/golden/make_golden.py`` from that library).
+``tests/golden/`` (made by ``tests/golden/make_golden.py`` from that library).  The same holds for the later rows:
+Zelinski post-filter (``make_golden_zelinski.py``, reference postfilter.cc compiled in), SubbandGSC with fixed active
+weights (``make_golden_gsc.py``), de Haan prototype design (``make_golden_design.py``, reference prototypeDesign.cc compiled
+in).  ONE row is a restatement without running reference code behind it -- PARITY UNPINNED for it: the raw-PCM ingest
+(``ingest_s16`` / ``ingest_s24be``), because feature/feature.cc needs libsndfile and does not build here; it is checked on
+hand-computed known answers only.
 
 Every function cites the reference lines it restates (paths relative to
 /root/reference/btk).
