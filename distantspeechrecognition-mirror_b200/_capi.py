@@ -26,7 +26,7 @@ SYMBOLS = [
     "btkb200_diag_load_bin", "btkb200_divide_nondiagonal", "btkb200_solve_mvdr", "btkb200_analysis",
     "btkb200_beamform", "btkb200_synthesis", "btkb200_covariance", "btkb200_estimate_covariance", "btkb200_chain",
     "btkb200_chain_batch", "btkb200_mvdr_chain_batch", "btkb200_chain_batch_pcm", "btkb200_convert_pcm", "btkb200_beamform_zelinski",
-    "btkb200_chain_zelinski", "btkb200_beamform_zelinski_dev", "btkb200_gsc_calc_weights",
+    "btkb200_chain_zelinski", "btkb200_chain_zelinski_batch", "btkb200_beamform_zelinski_dev", "btkb200_gsc_calc_weights",
     "btkb200_design_analysis_prototype", "btkb200_design_synthesis_prototype", "btkb200_gsc_set_active_weights", "btkb200_gsc_zero_active_weights", "btkb200_gsc_get_blocking_matrix", "btkb200_gsc_apply",
     "btkb200_chain_batch_multi", "btkb200_chain_batch_dev", "btkb200_analysis_dev", "btkb200_beamform_dev",
     "btkb200_synthesis_dev", "btkb200_launch_count", "btkb200_sync", "btkb200_host_alloc", "btkb200_host_free",
@@ -100,6 +100,7 @@ def lib() -> ctypes.CDLL:
     L.btkb200_convert_pcm.argtypes = [vp, vp, c_int, c_long, vp]
     L.btkb200_beamform_zelinski.argtypes = [vp, vp, c_long, c_double, c_int, c_int, vp, vp]
     L.btkb200_chain_zelinski.argtypes = [vp, vp, c_long, c_double, c_int, c_int, vp]
+    L.btkb200_chain_zelinski_batch.argtypes = [vp, POINTER(vp), POINTER(c_long), c_int, c_double, c_int, c_int, POINTER(vp)]
     L.btkb200_beamform_zelinski_dev.argtypes = [vp, vp, c_long, c_double, c_int, c_int, vp, vp, vp]
     L.btkb200_design_analysis_prototype.argtypes = [c_uint, c_uint, c_uint, c_double, c_int, c_double, c_int, vp, vp]
     L.btkb200_design_synthesis_prototype.argtypes = [vp, c_uint, c_uint, c_uint, c_double, c_double, c_int, c_double, c_int, vp, vp]
@@ -328,6 +329,16 @@ class Plan:
         out = np.empty(self.chain_frames(x.shape[0]) * self.D, dtype=np.float32)
         self._ck(self._L.btkb200_chain_zelinski(self._h, _p(x), x.shape[0], alpha, pf_type, min_frames, _p(out)))
         return out
+
+    def chain_zelinski_batch(self, pcms, alpha: float = 0.6, pf_type: int = 2, min_frames: int = 0) -> list:
+        xs = [np.ascontiguousarray(x, dtype=np.float32) for x in pcms]
+        outs = [np.empty(self.chain_frames(x.shape[0]) * self.D, dtype=np.float32) for x in xs]
+        n = len(xs)
+        pp = (c_void_p * n)(*[x.ctypes.data for x in xs])
+        oo = (c_void_p * n)(*[o.ctypes.data for o in outs])
+        TT = (c_long * n)(*[x.shape[0] for x in xs])
+        self._ck(self._L.btkb200_chain_zelinski_batch(self._h, pp, TT, n, alpha, pf_type, min_frames, oo))
+        return outs
 
     # -- fused path (host numpy buffers)
     def chain(self, pcm) -> np.ndarray:

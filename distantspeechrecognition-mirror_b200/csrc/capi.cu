@@ -687,6 +687,116 @@ int btkb200_chain_zelinski(btkb200_plan* p, const float* pcm, long T, double alp
   return BTKB200_OK;
 }
 
+// Many recordings through analysis -> beamformer -> Zelinski post-filter -> synthesis: all descriptors are uploaded once,
+// the uploads run ahead on the copy stream, the four kernels of a recording follow each other on the plan's stream and
+// the downloads trail on a third stream.
+int btkb200_chain_zelinski_batch(btkb200_plan* p, const float* const* pcm, const long* T, int n, double alpha, int type,
+                                 int min_frames, float* const* out) {
+  if (!p || !pcm || !T || !out || n < 0) return BTKB200_EINVAL;
+  if (!p->has_h || !p->has_g) return fail(p, BTKB200_ESTATE, "the chain needs both prototypes");
+  if (!p->has_weights) return fail(p, BTKB200_ESTATE, "call calcArrayManifoldVectorsX() once");
+  if (!p->has_manifold) return fail(p, BTKB200_ESTATE, "set beamformer's weights");
+  if (p->C <= 1) return fail(p, BTKB200_EINVAL, "The number of channels %d is <= 1", p->C);
+  if (n == 0) return BTKB200_OK;
+  CK(p, cudaSetDevice(p->device));
+  const int B = p->geo.B, C = p->C, M = p->geo.M, D = p->geo.D, Cpad = p->Cpad;
+  std::vector<long long> poff(n), ooff(n);
+  long long pin = 0, pout = 0;
+  for (int i = 0; i < n; i++) {
+    if (T[i] < 0 || !pcm[i] || !out[i]) return fail(p, BTKB200_EINVAL, "recording %d: bad buffer or length", i);
+    poff[i] = pin; ooff[i] = pout;
+    pin += ((long long)T[i] * C + 3) / 4 * 4;
+    pout += ((long long)p->geo.chain_frames(T[i]) * D + 3) / 4 * 4;
+  }
+  // descriptors of the analysis and synthesis launches of every recording
+  std::vector<RecDesc> arecs(n), srecs(n);
+  std::vector<WorkItem> awork, swork;
+  std::vector<int> awb(n + 1, 0), swb(n + 1, 0), aslices(n, 1);
+  const int Wa = fb_frames_per_iter(M, p->geo.R), H = p->geo.m * p->geo.R - 1, n_cg = Cpad / 4;
+  size_t max_snap = 16, max_Y = 16;
+  for (int i = 0; i < n; i++) {
+    const long F = p->geo.analysis_frames(T[i]);
+    const int nout = p->geo.synthesis_frames((int)F);
+    arecs[i].pcm_off = poff[i]; arecs[i].out_off = 0; arecs[i].T = (int)T[i]; arecs[i].nblk = (int)F;
+    srecs[i].pcm_off = 0; srecs[i].out_off = ooff[i]; srecs[i].T = (int)F; srecs[i].nblk = nout;
+    std::vector<RecDesc> one(1, arecs[i]);
+    std::vector<WorkItem> w1;
+    long long chunk = ((long long)F + 148 * 4 - 1) / (148 * 4);
+    chunk = (chunk + Wa - 1) / Wa * Wa;
+    if (chunk < Wa) chunk = Wa;
+    build_work(one, (int)chunk, w1);
+    for (size_t k = 0; k < w1.size(); k++) { w1[k].rec = i; awork.push_back(w1[k]); }
+    awb[i + 1] = (int)awork.size();
+    int slices = w1.empty() ? 1 : (int)(2 * 148 / w1.size());
+    if (slices < 1) slices = 1;
+    if (slices > n_cg) slices = n_cg;
+    aslices[i] = slices;
+    one[0] = srecs[i];
+    w1.clear();
+    if (nout > 0) build_work(one, choose_chunk(nout, H, Wa), w1);
+    for (size_t k = 0; k < w1.size(); k++) { w1[k].rec = i; swork.push_back(w1[k]); }
+    swb[i + 1] = (int)swork.size();
+    if ((size_t)F * B * C * sizeof(cf) > max_snap) max_snap = (size_t)F * B * C * sizeof(cf);
+    if ((size_t)F * B * sizeof(cf) > max_Y) max_Y = (size_t)F * B * sizeof(cf);
+  }
+  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+  const size_t o_arecs = 0, o_srecs = o_arecs + al(n * sizeof(RecDesc));
+  const size_t o_awork = o_srecs + al(n * sizeof(RecDesc));
+  const size_t o_swork = o_awork + al((awork.size() ? awork.size() : 1) * sizeof(WorkItem));
+  const size_t o_Y = o_swork + al((swork.size() ? swork.size() : 1) * sizeof(WorkItem));
+  const size_t o_stat = o_Y + al(max_Y);
+  const size_t o_snap = o_stat + al(max_Y * 2);            // float4 per (frame, bin)
+  CK(p, p->d_adapt.reserve(o_snap + al(max_snap)));
+  CK(p, p->d_in.reserve((size_t)(pin ? pin : 4) * sizeof(float)));
+  CK(p, p->d_out.reserve((size_t)(pout ? pout : 4) * sizeof(float)));
+  if (!p->s_in) CK(p, cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
+  if (!p->s_out) CK(p, cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
+  char* base = (char*)p->d_adapt.p;
+  CK(p, cudaStreamSynchronize(p->stream));
+  CK(p, cudaMemcpy(base + o_arecs, arecs.data(), n * sizeof(RecDesc), cudaMemcpyHostToDevice));
+  CK(p, cudaMemcpy(base + o_srecs, srecs.data(), n * sizeof(RecDesc), cudaMemcpyHostToDevice));
+  if (!awork.empty()) CK(p, cudaMemcpy(base + o_awork, awork.data(), awork.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
+  if (!swork.empty()) CK(p, cudaMemcpy(base + o_swork, swork.data(), swork.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
+  cf* dY = (cf*)(base + o_Y);
+  float4* dstat = (float4*)(base + o_stat);
+  cf* dsnap = (cf*)(base + o_snap);
+  while ((int)p->ev_in.size() < n) { cudaEvent_t e; CK(p, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); p->ev_in.push_back(e); }
+  while ((int)p->ev_k.size() < n) { cudaEvent_t e; CK(p, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); p->ev_k.push_back(e); }
+  for (int i = 0; i < n; i++) {
+    if (T[i] > 0)
+      CK(p, cudaMemcpyAsync((float*)p->d_in.p + poff[i], pcm[i], (size_t)T[i] * C * sizeof(float), cudaMemcpyHostToDevice, p->s_in));
+    CK(p, cudaEventRecord(p->ev_in[i], p->s_in));
+  }
+  for (int i = 0; i < n; i++) {
+    CK(p, cudaStreamWaitEvent(p->stream, p->ev_in[i], 0));
+    const long F = arecs[i].nblk;
+    if (awb[i + 1] > awb[i]) {
+      AnalysisParams a;
+      a.pcm = (const float*)p->d_in.p; a.snap = dsnap; a.recs = (const RecDesc*)(base + o_arecs);
+      a.work = (const WorkItem*)(base + o_awork) + awb[i];
+      a.taps_h = p->d_taps_h; a.twa = p->d_twa; a.twb = p->d_twb; a.C = C; a.Cpad = Cpad; a.m = p->geo.m; a.laN = p->geo.laN;
+      a.cg_slices = aslices[i];
+      CK(p, launch_analysis(M, p->geo.R, a, (awb[i + 1] - awb[i]) * aslices[i], p->stream));
+      CK(p, launch_beamform_zelinski(dsnap, p->d_w, p->d_ta, dY, dstat, nullptr, F, B, C, alpha, type, min_frames, p->stream));
+      p->launches += 3;
+    }
+    if (swb[i + 1] > swb[i]) {
+      SynthesisParams s;
+      s.Y = dY; s.out = (float*)p->d_out.p; s.recs = (const RecDesc*)(base + o_srecs); s.work = (const WorkItem*)(base + o_swork) + swb[i];
+      s.taps_g = p->d_taps_g; s.twa = p->d_twa; s.twb = p->d_twb; s.m = p->geo.m; s.pd_s = p->geo.pd_s; s.gain = p->gain;
+      CK(p, launch_synthesis(M, p->geo.R, s, swb[i + 1] - swb[i], p->stream));
+      p->launches++;
+    }
+    CK(p, cudaEventRecord(p->ev_k[i], p->stream));
+    CK(p, cudaStreamWaitEvent(p->s_out, p->ev_k[i], 0));
+    const size_t b = (size_t)p->geo.chain_frames(T[i]) * D * sizeof(float);
+    if (b) CK(p, cudaMemcpyAsync(out[i], (float*)p->d_out.p + ooff[i], b, cudaMemcpyDeviceToHost, p->s_out));
+  }
+  CK(p, cudaStreamSynchronize(p->s_out));
+  CK(p, cudaStreamSynchronize(p->stream));
+  return BTKB200_OK;
+}
+
 int btkb200_synthesis(btkb200_plan* p, const float* Y, long F, float* out, long* n_out_frames) {
   if (!p || !Y || !out || F < 0) return BTKB200_EINVAL;
   CK(p, cudaSetDevice(p->device));

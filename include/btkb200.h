@@ -164,6 +164,10 @@ int btkb200_beamform_zelinski(btkb200_plan* plan, const float* snap, long F, dou
 int btkb200_chain_zelinski(btkb200_plan* plan, const float* pcm, long T, double alpha, int type, int min_frames,
                            float* out);
 
+/* Same for n independent recordings, pipelined (uploads ahead on a copy stream, downloads behind on another). */
+int btkb200_chain_zelinski_batch(btkb200_plan* plan, const float* const* pcm, const long* T, int n, double alpha, int type,
+                                 int min_frames, float* const* out);
+
 /* ---- fused path ---------------------------------------------------------------------------------------- */
 /* pcm -> out through analysis -> weight apply -> synthesis in ONE kernel; out holds chain_frames(T)*D floats.
  * ESTATE if no weights are installed (j_error, beamformer.cc:1140-1143). */

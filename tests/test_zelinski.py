@@ -131,3 +131,19 @@ def test_stream_node_mirrors_driver_wiring(prototypes):
     assert w_last is not None and w_last.shape == (M,)
     with pytest.raises(btk_b200.streams.jdimension_error):      # postfilter.cc:355-358
         btk_b200.ZelinskiPostFilterPtr(bf, M // 2)
+
+
+@pytest.mark.gpu
+def test_batch_equals_single_recording_calls(prototypes):
+    """btkb200_chain_zelinski_batch (pipelined, ragged batch) gives exactly what btkb200_chain_zelinski gives per recording."""
+    M, m, r, C = 256, 4, 1, 4
+    h, g = proto(prototypes, M, m, r)
+    tau = wl.farfield_delays(wl.circular_array(C), 0.9, 1.2)
+    plan = btk_b200.Plan(M, m, r, C, h, g)
+    plan.set_ds_weights(FS, tau)
+    pcms = [wl.array_recording(T, tau, seed=70 + i, noise_sigma=600.0) for i, T in enumerate([5000, 1, 12800, 777])]
+    outs = plan.chain_zelinski_batch(pcms, 0.6, 2, 0)
+    for pcm, out in zip(pcms, outs):
+        assert np.array_equal(out, plan.chain_zelinski(pcm, 0.6, 2, 0))
+    assert plan.chain_zelinski_batch([]) == []
+    plan.close()
