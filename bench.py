@@ -371,11 +371,24 @@ def run_ours(args, wl_cfg, rank, world, local_rank):
         if int(nfb.sum()) != 0 or not np.isfinite(float(h_out[0, : 4 * D].double().abs().sum())):
             raise SystemExit("bench.py: adaptive MVDR produced fallback bins or non-finite output")
 
+    # ---- optional: the shipped drivers' chain with the Zelinski post-filter, end to end
+    pf_s = 0.0
+    if args.postfilter:
+        plan.chain_zelinski_batch_into(xs, outs, 0.6, 2, 0)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            plan.chain_zelinski_batch_into(xs, outs, 0.6, 2, 0)
+        torch.cuda.synchronize()
+        pf_s = (time.perf_counter() - t0) / e2e_steps
+        if not np.isfinite(float(h_out[0, : 4 * D].double().abs().sum())):
+            raise SystemExit("bench.py: post-filter chain output is not finite")
+
     # ---- max over ranks
-    tt = torch.tensor([total_ms, kern_ms, e2e_s, e2e16_s, mvdr_s], dtype=torch.float64, device=dev)
+    tt = torch.tensor([total_ms, kern_ms, e2e_s, e2e16_s, mvdr_s, pf_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    total_ms, kern_ms, e2e_s, e2e16_s, mvdr_s = [float(v) for v in tt.tolist()]
+    total_ms, kern_ms, e2e_s, e2e16_s, mvdr_s, pf_s = [float(v) for v in tt.tolist()]
     if old_affinity:
         os.sched_setaffinity(0, old_affinity)
 
@@ -419,6 +432,11 @@ def run_ours(args, wl_cfg, rank, world, local_rank):
                 "h2d_bytes_per_step": int(nb * n_in * 4), "d2h_bytes_per_step": int(nb * n_out * 4),
                 "note": "btkb200_mvdr_chain_batch: per utterance covariance (x x^H, ff 0.99) on the first second -> load 1e-2 "
                         "trace/C -> per-bin MVDR solve -> fused chain with that utterance's weights; host buffers in and out"}
+        if args.postfilter:
+            line["e2e_zelinski_postfilter"] = {
+                "value": world * units_per_step / pf_s, "unit": UNIT, "ms_per_step": pf_s * 1e3,
+                "note": "btkb200_chain_zelinski_batch (analysis -> SubbandDS -> ZelinskiPostFilter alpha 0.6 |.| -> synthesis, "
+                        "staged kernels, pipelined over the batch); pinned host buffers in and out"}
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             ctx = mp.get_context("spawn")
@@ -444,6 +462,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="utterances per GPU (default: per workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--postfilter", action="store_true", help="also time the chain with the Zelinski post-filter end to end")
     ap.add_argument("--mvdr", action="store_true", help="also time the per-utterance adaptive MVDR path end to end")
     args = ap.parse_args()
     wl_cfg = dict(WORKLOADS[args.workload])

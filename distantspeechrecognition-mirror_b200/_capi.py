@@ -333,12 +333,16 @@ class Plan:
     def chain_zelinski_batch(self, pcms, alpha: float = 0.6, pf_type: int = 2, min_frames: int = 0) -> list:
         xs = [np.ascontiguousarray(x, dtype=np.float32) for x in pcms]
         outs = [np.empty(self.chain_frames(x.shape[0]) * self.D, dtype=np.float32) for x in xs]
+        self.chain_zelinski_batch_into(xs, outs, alpha, pf_type, min_frames)
+        return outs
+
+    def chain_zelinski_batch_into(self, xs, outs, alpha: float = 0.6, pf_type: int = 2, min_frames: int = 0):
+        """xs / outs: lists of C-contiguous float32 arrays (outs preallocated, ideally pinned); no allocation here."""
         n = len(xs)
         pp = (c_void_p * n)(*[x.ctypes.data for x in xs])
         oo = (c_void_p * n)(*[o.ctypes.data for o in outs])
         TT = (c_long * n)(*[x.shape[0] for x in xs])
         self._ck(self._L.btkb200_chain_zelinski_batch(self._h, pp, TT, n, alpha, pf_type, min_frames, oo))
-        return outs
 
     # -- fused path (host numpy buffers)
     def chain(self, pcm) -> np.ndarray:

@@ -516,10 +516,10 @@ int btkb200_beamform_zelinski_dev(btkb200_plan* p, const float* d_snap, long F, 
   if (p->C <= 1) return fail(p, BTKB200_EINVAL, "The number of channels %d is <= 1", p->C);   // postfilter.cc:62-65
   CK(p, cudaSetDevice(p->device));
   if (F == 0) return BTKB200_OK;
-  CK(p, p->d_aux.reserve((size_t)F * p->geo.B * sizeof(float4)));
+  CK(p, p->d_aux.reserve(zelinski_scratch_bytes(F, p->geo.B)));
   CK(p, launch_beamform_zelinski((const cf*)d_snap, p->d_w, p->d_ta, (cf*)d_Y, (float4*)p->d_aux.p, d_W, F, p->geo.B, p->C,
                                  alpha, type, min_frames, (cudaStream_t)stream));
-  p->launches += 2;
+  p->launches += 4;
   return BTKB200_OK;
 }
 
@@ -745,7 +745,7 @@ int btkb200_chain_zelinski_batch(btkb200_plan* p, const float* const* pcm, const
   const size_t o_swork = o_awork + al((awork.size() ? awork.size() : 1) * sizeof(WorkItem));
   const size_t o_Y = o_swork + al((swork.size() ? swork.size() : 1) * sizeof(WorkItem));
   const size_t o_stat = o_Y + al(max_Y);
-  const size_t o_snap = o_stat + al(max_Y * 2);            // float4 per (frame, bin)
+  const size_t o_snap = o_stat + al(max_Y * 2 + (max_Y / 8 / 32 + B + 64) * 32);   // float4 per (frame, bin) + scan segments
   CK(p, p->d_adapt.reserve(o_snap + al(max_snap)));
   CK(p, p->d_in.reserve((size_t)(pin ? pin : 4) * sizeof(float)));
   CK(p, p->d_out.reserve((size_t)(pout ? pout : 4) * sizeof(float)));
@@ -778,7 +778,7 @@ int btkb200_chain_zelinski_batch(btkb200_plan* p, const float* const* pcm, const
       a.cg_slices = aslices[i];
       CK(p, launch_analysis(M, p->geo.R, a, (awb[i + 1] - awb[i]) * aslices[i], p->stream));
       CK(p, launch_beamform_zelinski(dsnap, p->d_w, p->d_ta, dY, dstat, nullptr, F, B, C, alpha, type, min_frames, p->stream));
-      p->launches += 3;
+      p->launches += 5;
     }
     if (swb[i + 1] > swb[i]) {
       SynthesisParams s;

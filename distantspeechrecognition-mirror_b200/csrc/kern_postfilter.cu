@@ -13,7 +13,7 @@
 //     S(n) = a_n S(n-1) + (1 - a_n) s(n),  s(n) = sum_{i<j} y_i conj(y_j)   and   P(n), p(n) = sum_i |y_i|^2
 // are carried -- O(C) per (frame, bin) with a running prefix sum instead of O(C^2) state per bin.
 //   kernel 1 (frame- and bin-parallel): beamformer output Y, s, p from the stored snapshots (one coalesced pass);
-//   kernel 2: the first-order recursion over frames as a segmented scan (affine maps compose), then W and Y *= W.
+//   kernels 2-4: the first-order recursion over frames as a three-phase segmented scan (affine maps compose), W, Y *= W.
 #include "launch.h"
 #include "snap_tile.cuh"
 
@@ -67,61 +67,94 @@ __global__ void __launch_bounds__(SNAP_THREADS) btk_beamform_zelinski_kernel(con
   }
 }
 
-#define ZEL_SEG 16          // frame segments (warps) per CTA
-// CTA = 32 consecutive bins (lanes, coalesced) x ZEL_SEG contiguous frame segments (warps).
-__global__ void __launch_bounds__(32 * ZEL_SEG) btk_zelinski_scan_kernel(const float4* __restrict__ stat, cf* __restrict__ Y,
-                                                                        float* __restrict__ Wout, long long F, int B, int C,
-                                                                        double alpha, int type, int min_frames) {
-  __shared__ double s_end[ZEL_SEG][32][3];
-  __shared__ double s_A[ZEL_SEG][32];
-  const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
-  const int s = blockIdx.x * 32 + lane;
-  const long long per = (F + ZEL_SEG - 1) / ZEL_SEG;
-  const long long n0 = per * seg, n1 = (n0 + per < F) ? n0 + per : F;
-  const bool live = s < B;
-  // pass 1: the segment from a zero state: end state and the product of its coefficients
+// ---- the recursion over frames as a three-phase segmented scan (affine maps compose) ---------------------------------
+// segments of ZEL_LEN frames; thread = (bin, segment), lanes across 32 consecutive bins (coalesced).
+//   phase 1: every segment from a zero state -> its end state and the product of its coefficients
+//   phase 2: per bin, fold the segments in order -> the state entering every segment   (F / ZEL_LEN dependent steps)
+//   phase 3: every segment again from its entering state -> gains W, Y *= W
+#define ZEL_LEN 64
+#define ZEL_WARPS 8
+
+__device__ __forceinline__ double zel_alpha(long long n, double alpha) { return n >= 2 ? alpha : 0.0; }   // postfilter.cc:466-469
+
+__global__ void __launch_bounds__(32 * ZEL_WARPS) btk_zelinski_seg_kernel(const float4* __restrict__ stat, double4* __restrict__ seg,
+                                                                         long long F, int B, int nseg, double alpha) {
+  const int s = blockIdx.x * 32 + (threadIdx.x & 31), g = blockIdx.y * ZEL_WARPS + (threadIdx.x >> 5);
+  if (s >= B || g >= nseg) return;
+  const long long n0 = (long long)g * ZEL_LEN, n1 = n0 + ZEL_LEN < F ? n0 + ZEL_LEN : F;
   double Sr = 0.0, Si = 0.0, P = 0.0, A = 1.0;
-  if (live) {
-    for (long long n = n0; n < n1; n++) {
-      const double a = n >= 2 ? alpha : 0.0;
-      const float4 v = stat[n * B + s];
-      Sr = a * Sr + (1.0 - a) * (double)v.x;
-      Si = a * Si + (1.0 - a) * (double)v.y;
-      P = a * P + (1.0 - a) * (double)v.z;
+  for (long long nb = n0; nb < n1; nb += 4) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) v[u] = nb + u < n1 ? stat[(nb + u) * B + s] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (nb + u >= n1) break;
+      const double a = zel_alpha(nb + u, alpha);
+      Sr = a * Sr + (1.0 - a) * (double)v[u].x;
+      Si = a * Si + (1.0 - a) * (double)v[u].y;
+      P = a * P + (1.0 - a) * (double)v[u].z;
       A *= a;
     }
   }
-  s_end[seg][lane][0] = Sr; s_end[seg][lane][1] = Si; s_end[seg][lane][2] = P; s_A[seg][lane] = A;
-  __syncthreads();
-  // state entering this segment: fold the earlier segments in order
-  Sr = 0.0; Si = 0.0; P = 0.0;
-  for (int q = 0; q < seg; q++) {
-    const double a = s_A[q][lane];
-    Sr = a * Sr + s_end[q][lane][0];
-    Si = a * Si + s_end[q][lane][1];
-    P = a * P + s_end[q][lane][2];
+  seg[(long long)g * B + s] = make_double4(Sr, Si, P, A);
+}
+
+// in place: seg[g] <- state ENTERING segment g
+__global__ void btk_zelinski_fold_kernel(double4* __restrict__ seg, int B, int nseg) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= B) return;
+  double Sr = 0.0, Si = 0.0, P = 0.0;
+  for (int g0 = 0; g0 < nseg; g0 += 8) {           // the loads do not depend on the state: eight in flight
+    double4 e[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) e[u] = g0 + u < nseg ? seg[(long long)(g0 + u) * B + s] : make_double4(0.0, 0.0, 0.0, 1.0);
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      if (g0 + u >= nseg) break;
+      seg[(long long)(g0 + u) * B + s] = make_double4(Sr, Si, P, 0.0);
+      Sr = e[u].w * Sr + e[u].x; Si = e[u].w * Si + e[u].y; P = e[u].w * P + e[u].z;
+    }
   }
-  if (!live) return;
+}
+
+__global__ void __launch_bounds__(32 * ZEL_WARPS) btk_zelinski_apply_kernel(const float4* __restrict__ stat, const double4* __restrict__ seg,
+                                                                           cf* __restrict__ Y, float* __restrict__ Wout, long long F,
+                                                                           int B, int C, int nseg, double alpha, int type,
+                                                                           int min_frames) {
+  const int s = blockIdx.x * 32 + (threadIdx.x & 31), g = blockIdx.y * ZEL_WARPS + (threadIdx.x >> 5);
+  if (s >= B || g >= nseg) return;
+  const long long n0 = (long long)g * ZEL_LEN, n1 = n0 + ZEL_LEN < F ? n0 + ZEL_LEN : F;
+  const double4 e = seg[(long long)g * B + s];
+  double Sr = e.x, Si = e.y, P = e.z;
   const double scale = 2.0 / ((double)C - 1.0);             // 2 / (nChan - 1), postfilter.cc:121
-  for (long long n = n0; n < n1; n++) {
-    const double a = n >= 2 ? alpha : 0.0;
-    const float4 v = stat[n * B + s];
-    Sr = a * Sr + (1.0 - a) * (double)v.x;
-    Si = a * Si + (1.0 - a) * (double)v.y;
-    P = a * P + (1.0 - a) * (double)v.z;
-    const bool applied = n > min_frames && type != 0;       // frames 0 .. minFrames only update the densities, and
+  for (long long nb = n0; nb < n1; nb += 4) {
+    float4 v[4];
+    cf y[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const bool ok = nb + u < n1;
+      v[u] = ok ? stat[(nb + u) * B + s] : make_float4(0.f, 0.f, 0.f, 0.f);
+      y[u] = ok ? Y[(nb + u) * B + s] : mk(0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const long long n = nb + u;
+      if (n >= n1) break;
+      const double a = zel_alpha(n, alpha);
+      Sr = a * Sr + (1.0 - a) * (double)v[u].x;
+      Si = a * Si + (1.0 - a) * (double)v[u].y;
+      P = a * P + (1.0 - a) * (double)v[u].z;
+      const bool applied = n > min_frames && type != 0;     // frames 0 .. minFrames only update the densities, and
                                                             // their (unused) gain follows the |.| branch (pfType = 0)
-    double num;
-    if (applied && (type & 1)) num = Sr < 0.0 ? 0.0 : Sr;   // TYPE_ZELINSKI1_REAL
-    else num = sqrt(Sr * Sr + Si * Si);
-    double W = (num / P) * scale;
-    if (W >= 1.0) W = 1.0;
-    if (W < 1.0e-4) W = 1.0e-4;                              // SPECTRAL_FLOOR
-    if (Wout) Wout[n * B + s] = (float)W;
-    if (applied) {
-      cf y = Y[n * B + s];
-      y.x *= (float)W; y.y *= (float)W;
-      Y[n * B + s] = y;
+      double num;
+      if (applied && (type & 1)) num = Sr < 0.0 ? 0.0 : Sr; // TYPE_ZELINSKI1_REAL
+      else num = sqrt(Sr * Sr + Si * Si);
+      double W = (num / P) * scale;
+      if (W >= 1.0) W = 1.0;
+      if (W < 1.0e-4) W = 1.0e-4;                            // SPECTRAL_FLOOR
+      if (Wout) Wout[n * B + s] = (float)W;
+      if (applied) Y[n * B + s] = mk(y[u].x * (float)W, y[u].y * (float)W);
     }
   }
 }
@@ -141,7 +174,13 @@ cudaError_t launch_beamform_zelinski(const cf* snap, const cf* w, const cf* ta, 
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  btk_zelinski_scan_kernel<<<(B + 31) / 32, 32 * ZEL_SEG, 0, st>>>(stat, Y, Wout, F, B, C, alpha, type, min_frames);
+  // the scan scratch (one double4 per bin and segment) follows the statistics in the caller's buffer
+  const int nseg = (int)((F + ZEL_LEN - 1) / ZEL_LEN);
+  double4* seg = reinterpret_cast<double4*>(stat + ((FB + 1) & ~1LL));
+  const dim3 sgrid((B + 31) / 32, (nseg + ZEL_WARPS - 1) / ZEL_WARPS);
+  btk_zelinski_seg_kernel<<<sgrid, 32 * ZEL_WARPS, 0, st>>>(stat, seg, F, B, nseg, alpha);
+  btk_zelinski_fold_kernel<<<(B + 127) / 128, 128, 0, st>>>(seg, B, nseg);
+  btk_zelinski_apply_kernel<<<sgrid, 32 * ZEL_WARPS, 0, st>>>(stat, seg, Y, Wout, F, B, C, nseg, alpha, type, min_frames);
   return cudaGetLastError();
 }
 

@@ -30,7 +30,9 @@ cudaError_t launch_mvdr_solve(const double2* Rn, const double2* d, double2* w, i
                               double dThreshold, cudaStream_t st);
 
 // Beamformer output + Zelinski post-filter on stored snapshots (postfilter/postfilter.cc:30-222, 428-500): Y [F][B]
-// post-filtered in place semantics (Y is written, then scaled), stat = scratch [F][B] float4, Wout [F][B] or NULL.
+// post-filtered in place semantics (Y is written, then scaled), Wout [F][B] or NULL; stat = scratch of
+// zelinski_scratch_bytes(F, B) bytes ([F][B] float4 statistics + one double4 per bin and segment of at least 32 frames).
+inline size_t zelinski_scratch_bytes(long long F, int B) { return (size_t)(F * B + 2) * 16 + (size_t)((F + 31) / 32 + 1) * B * 32; }
 cudaError_t launch_beamform_zelinski(const cf* snap, const cf* w, const cf* ta, cf* Y, float4* stat, float* Wout, long long F,
                                      int B, int C, double alpha, int type, int min_frames, cudaStream_t st);
 
