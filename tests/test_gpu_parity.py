@@ -46,6 +46,11 @@ def test_against_reference_golden(name, prototypes):
         assert bo.rel_l2(plan.get_weights(), G["W"]) <= 1e-12
     Y = plan.beamform(snap)
     assert bo.rel_l2(Y, G["Y"][:, : plan.B]) <= TOL_REL
+    if "Y_floatsvd" in G:
+        # the STOCK reference path (single-precision LINPACK SVD pseudoinverse, beamformer.cc:253-305): weights and
+        # beamformer outputs stay inside the north_star tolerance of it as well
+        assert bo.rel_l2(plan.get_weights(), G["W_floatsvd"]) <= TOL_REL
+        assert bo.rel_l2(Y, G["Y_floatsvd"][:, : plan.B]) <= TOL_REL
     out = plan.synthesis(Y)
     assert out.shape == G["out"].shape
     assert bo.snr_db(out, G["out"]) >= TOL_SNR
