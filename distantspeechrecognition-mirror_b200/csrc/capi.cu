@@ -3,6 +3,7 @@
 // analysis / beamform / synthesis / chain / covariance / solve call runs the sm_100a kernels or fails.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -107,11 +108,12 @@ static int upload_weights(btkb200_plan* p) {
 
 // chunk of output frames per CTA: enough CTAs to fill 148 SMs several times over, but long enough
 // that the (m R - 1)-frame warm-up of the synthesis history stays a small fraction.
-static int choose_chunk(long long total_frames, int H, int W) {
+static int choose_chunk(long long total_frames, int H, int W, int waves = 0) {
 #ifndef BTK_CHUNK_WAVES
 #define BTK_CHUNK_WAVES 2
 #endif
-  const long long target_ctas = 148LL * 2 * BTK_CHUNK_WAVES;
+  static const int waves_env = getenv("BTK_CHUNK_WAVES") ? atoi(getenv("BTK_CHUNK_WAVES")) : 0;   // tuning knob (A/B runs)
+  const long long target_ctas = 148LL * 2 * (waves_env > 0 ? waves_env : (waves > 0 ? waves : BTK_CHUNK_WAVES));
   long long chunk = (total_frames + target_ctas - 1) / target_ctas;
   // small jobs (one short recording): prefer filling the SMs over amortising the warm-up, down to chunks whose
   // warm-up is half of their work (a 10-s recording is 139 CTAs instead of 22)
@@ -564,7 +566,9 @@ static int chain_prepare(btkb200_plan* p, const long long* pcm_off, const long l
   }
   std::vector<WorkItem> work;
   const int W = chain_frames_per_iter(p->geo.M, p->geo.R, p->geo.m), H = p->geo.m * p->geo.R - 1;
-  build_work(recs, choose_chunk(total, H, W), work);
+  // measured (BTK_CHUNK_WAVES sweep on cfg2 / cfg3 / cfg4 / M = 1024): the kernels that run two CTAs per SM (M <= 256) like
+  // three waves' worth of chunks (+3 % on cfg2), the one-CTA-per-SM kernels two
+  build_work(recs, choose_chunk(total, H, W, p->geo.M <= 256 ? 3 : 2), work);
   p->rec_work_begin.assign(n + 1, 0);
   for (size_t w = 0; w < work.size(); w++) p->rec_work_begin[work[w].rec + 1]++;
   for (int i = 0; i < n; i++) p->rec_work_begin[i + 1] += p->rec_work_begin[i];
