@@ -126,6 +126,49 @@ static int choose_chunk(long long total_frames, int H, int W, int waves = 0) {
   return (int)chunk;
 }
 
+// Chunk size of a fused-chain batch from a list-scheduling model of the launch: CTAs are handed to the first free slot in
+// launch order, a chunk of `its` iterations costs its + 0.3 (table loads, cold first window), the last chunk of a
+// recording is shorter and fills gaps.  The candidate with the smallest makespan wins among those that keep at least
+// two waves of CTAs in flight (a single wave runs the co-resident CTAs in lockstep: staging no longer overlaps the
+// transforms, measured 16 % slower).  The model orders the measured BTK_CHUNK_WAVES sweeps of cfg2 / cfg3 / cfg4 correctly
+// (DESIGN.md); small jobs fall back to choose_chunk (fill the SMs first).
+static int choose_chunk_model(const std::vector<RecDesc>& recs, int H, int W, int slots) {
+  long long total = 0;
+  for (size_t r = 0; r < recs.size(); r++) total += recs[r].nblk;
+  int best_its = 0;
+  double best = 1e300;
+  std::vector<double> heap;
+  for (int its = 2; its <= 64; its++) {
+    const long long chunk = (long long)its * W - H;
+    if (chunk < 1) continue;
+    long long n_cta = 0;
+    for (size_t r = 0; r < recs.size(); r++) n_cta += (recs[r].nblk + chunk - 1) / chunk;
+    if (n_cta < 2LL * slots) break;            // longer chunks only make fewer CTAs
+    heap.assign(slots, 0.0);                   // min-heap of slot finish times (all equal at the start)
+    auto push_down = [&](size_t i) {
+      for (;;) {
+        size_t l = 2 * i + 1, rr = l + 1, m = i;
+        if (l < heap.size() && heap[l] < heap[m]) m = l;
+        if (rr < heap.size() && heap[rr] < heap[m]) m = rr;
+        if (m == i) break;
+        std::swap(heap[i], heap[m]); i = m;
+      }
+    };
+    double makespan = 0.0;
+    for (size_t r = 0; r < recs.size(); r++)
+      for (long long j = 0; j < recs[r].nblk; j += chunk) {
+        const long long nj = recs[r].nblk - j < chunk ? recs[r].nblk - j : chunk;
+        const double d = (double)((nj + H + W - 1) / W) + 0.3;
+        heap[0] += d;
+        if (heap[0] > makespan) makespan = heap[0];
+        push_down(0);
+      }
+    if (makespan < best) { best = makespan; best_its = its; }
+  }
+  if (best_its == 0) return choose_chunk(total, H, W);
+  return best_its * W - H;
+}
+
 extern "C" {
 
 int btkb200_device_count(void) {
@@ -566,9 +609,9 @@ static int chain_prepare(btkb200_plan* p, const long long* pcm_off, const long l
   }
   std::vector<WorkItem> work;
   const int W = chain_frames_per_iter(p->geo.M, p->geo.R, p->geo.m), H = p->geo.m * p->geo.R - 1;
-  // measured (BTK_CHUNK_WAVES sweep on cfg2 / cfg3 / cfg4 / M = 1024): the kernels that run two CTAs per SM (M <= 256) like
-  // three waves' worth of chunks (+3 % on cfg2), the one-CTA-per-SM kernels two
-  build_work(recs, choose_chunk(total, H, W, p->geo.M <= 256 ? 3 : 2), work);
+  // two CTAs per SM for M <= 256 (kern_fb.cuh KernCfg::MINB), one otherwise; BTK_CHUNK_WAVES overrides the model (A/B runs)
+  if (getenv("BTK_CHUNK_WAVES")) build_work(recs, choose_chunk(total, H, W), work);
+  else build_work(recs, choose_chunk_model(recs, H, W, 148 * (p->geo.M <= 256 ? 2 : 1)), work);
   p->rec_work_begin.assign(n + 1, 0);
   for (size_t w = 0; w < work.size(); w++) p->rec_work_begin[work[w].rec + 1]++;
   for (int i = 0; i < n; i++) p->rec_work_begin[i + 1] += p->rec_work_begin[i];
