@@ -129,8 +129,9 @@ static int choose_chunk(long long total_frames, int H, int W, int waves = 0) {
 // Chunk size of a fused-chain batch from a list-scheduling model of the launch: CTAs are handed to the first free slot in
 // launch order, a chunk of `its` iterations costs its + 0.3 (table loads, cold first window), the last chunk of a
 // recording is shorter and fills gaps.  The candidate with the smallest makespan wins among those that keep at least
-// two waves of CTAs in flight (a single wave runs the co-resident CTAs in lockstep: staging no longer overlaps the
-// transforms, measured 16 % slower).  The model orders the measured BTK_CHUNK_WAVES sweeps of cfg2 / cfg3 / cfg4 correctly
+// two waves of CTAs in flight (a single wave measured 16 % slower than three: nothing fills the gaps behind the slowest
+// CTAs; a deliberate start offset between the co-resident CTAs of the first wave made no difference, so it is not a
+// lockstep effect).  The model orders the measured BTK_CHUNK_WAVES sweeps of cfg2 / cfg3 / cfg4 correctly
 // (DESIGN.md); small jobs fall back to choose_chunk (fill the SMs first).
 static int choose_chunk_model(const std::vector<RecDesc>& recs, int H, int W, int slots) {
   long long total = 0;
