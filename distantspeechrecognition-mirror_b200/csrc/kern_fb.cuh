@@ -26,8 +26,9 @@ template <int M, int R, int MT, int PP> struct KernCfg {
   static constexpr int MINB = (smem <= 112 * 1024) ? 2 : 1;
 };
 
-// Frame pairs per warp of the fused chain: two (one 8-warp CTA per SM, up to 255 registers per thread, taps /
-// samples / weights / twiddles loaded once for four frames) whenever the larger window fits shared memory.
+// Frame pairs per warp of the fused chain: two for M <= 256 (four-warp CTAs, two per SM, ~230 registers per thread; taps /
+// samples / weights / twiddles loaded once for four frames) whenever the larger window fits shared memory; one for the
+// 32-values-per-lane transforms of M = 512 / 1024.
 #ifndef BTK_PP_MAX_M
 #define BTK_PP_MAX_M 256   // M = 512 with two pairs per warp measured equal (16 ch) or 44 % slower (64 ch): tools/ab_run2.sh
 #endif
