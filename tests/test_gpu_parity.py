@@ -282,3 +282,24 @@ def test_dct2_with_unit_prototype_span_is_refused(prototypes):
     with pytest.raises(btk_b200.BtkError) as e:
         btk_b200.Plan(256, 1, 0, 2, h, g, dct=2)
     assert e.value.code == btk_b200._capi.EINVAL
+
+
+def test_large_batch_chunk_model_matches_single_recording_calls(prototypes):
+    """A batch big enough for choose_chunk_model (more than two waves of CTAs) against the same recordings one by one
+    (small-job chunking, itself checked against the oracle above): the chunk size must not change the result beyond
+    float32 rounding (a frame can be packed with a different partner frame)."""
+    M, m, r, C = 256, 4, 1, 2
+    h, g = proto(prototypes, M, m, r)
+    geo = bo.BankGeometry(M, m, r, 0)
+    tau = wl.farfield_delays(wl.circular_array(C), 0.4, 1.3)
+    plan = btk_b200.Plan(M, m, r, C, h, g)
+    plan.set_ds_weights(FS, tau)
+    rng = np.random.default_rng(11)
+    pcms = [wl.noise_recording(int(rng.integers(50000, 70000)), C, seed=500 + i, sigma=900.0) for i in range(64)]
+    outs = plan.chain_batch(pcms)
+    for i in (0, 1, 17, 40, 63):
+        single = plan.chain(pcms[i])
+        assert outs[i].shape == single.shape and bo.snr_db(outs[i], single) >= 100.0
+    W = bo.ds_weights(tau, FS, M)
+    assert bo.snr_db(outs[5], bo.chain(pcms[5], h, g, geo, W)[2]) >= TOL_SNR
+    plan.close()
