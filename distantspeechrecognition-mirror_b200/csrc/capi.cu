@@ -67,6 +67,7 @@ struct btkb200_plan {
   PinBuf h_desc;
   std::vector<long long> sig;  // signature of the cached chain work list
   int cached_n_work = 0;
+  int one_cta = 0;             // fused chain: keep one CTA per SM (chain_prepare decides from the L2 footprint)
   std::vector<int> rec_work_begin;   // first work item of every recording (+ total at the end)
   cudaStream_t stream = nullptr;
   cudaStream_t s_in = nullptr, s_out = nullptr;   // copy engines of the pipelined host-buffer path
@@ -610,9 +611,23 @@ static int chain_prepare(btkb200_plan* p, const long long* pcm_off, const long l
   }
   std::vector<WorkItem> work;
   const int W = chain_frames_per_iter(p->geo.M, p->geo.R, p->geo.m), H = p->geo.m * p->geo.R - 1;
-  // two CTAs per SM for M <= 256 (kern_fb.cuh KernCfg::MINB), one otherwise; BTK_CHUNK_WAVES overrides the model (A/B runs)
+  // two CTAs per SM for M <= 256 (kern_fb.cuh KernCfg::MINB), one otherwise.  Every resident CTA walks its window of
+  // (W - 1 + mR) blocks of D time steps once per group of four channels, and the rows of interleaved PCM it touches hold
+  // ALL channels: when the windows of all resident CTAs together no longer fit L2, each of the Cpad/4 passes goes back to
+  // HBM (measured: M=256, 32 channels 2.43 ms with two CTAs per SM, 1.50 ms with one; 64 channels 5.23 -> 2.94 ms; below
+  // ~100 MB two CTAs stay ahead).  Then keep one CTA per SM.
+  int cps = p->geo.M <= 256 ? 2 : 1;
+  if (cps == 2) {
+    int l2 = 0;
+    CK(p, cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, p->device));
+    const double window_bytes = (double)(W - 1 + p->geo.m * p->geo.R) * p->geo.D * p->Cpad * sizeof(float);
+    static const int one_cta_env = getenv("BTK_ONE_CTA") ? atoi(getenv("BTK_ONE_CTA")) : -1;   // A/B runs
+    p->one_cta = one_cta_env >= 0 ? one_cta_env : (148.0 * cps * window_bytes > 0.8 * l2);
+    if (p->one_cta) cps = 1;
+  }
+  // BTK_CHUNK_WAVES overrides the chunk model (A/B runs)
   if (getenv("BTK_CHUNK_WAVES")) build_work(recs, choose_chunk(total, H, W), work);
-  else build_work(recs, choose_chunk_model(recs, H, W, 148 * (p->geo.M <= 256 ? 2 : 1)), work);
+  else build_work(recs, choose_chunk_model(recs, H, W, 148 * cps), work);
   p->rec_work_begin.assign(n + 1, 0);
   for (size_t w = 0; w < work.size(); w++) p->rec_work_begin[work[w].rec + 1]++;
   for (int i = 0; i < n; i++) p->rec_work_begin[i + 1] += p->rec_work_begin[i];
@@ -631,6 +646,7 @@ static int chain_launch(btkb200_plan* p, const float* d_pcm, float* d_out, int w
   c.pcm = d_pcm; c.out = d_out; c.recs = (const RecDesc*)p->d_recs.p; c.work = (const WorkItem*)p->d_work.p + w0;
   c.taps_h = p->d_taps_h; c.taps_g = p->d_taps_g; c.wts = wts ? wts : p->d_wts_chain; c.wts_stride = wts_stride;
   c.twa = p->d_twa; c.twb = p->d_twb;
+  c.one_cta = p->one_cta;
   c.C = p->C; c.Cpad = p->Cpad; c.m = p->geo.m; c.pd_s = p->geo.pd_s; c.laN = p->geo.laN; c.gain = p->gain;
   CK(p, launch_chain(p->geo.M, p->geo.R, c, w1 - w0, st));
   p->launches++;

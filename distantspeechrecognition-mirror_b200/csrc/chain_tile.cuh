@@ -53,6 +53,7 @@ struct ChainParams {
   const float* taps_g;   // [m][M]    gp[k][q] = g[M-1-q + M k]
   const cf* wts;         // [Cpad][V/2][L][2] Hermitian-extended conj weights in register order
   long long wts_stride;  // elements between the tables of consecutive recordings (0: one table for the whole batch)
+  int one_cta;           // launch hint: keep one CTA per SM (host side only, see kern_fb.cuh / capi.cu)
   const cf* twa;         // pass-A twiddles, lane-contiguous (FFTTables)
   const cf* twb;         // pass-B twiddles (three-pass transforms only)
   int C, Cpad;
@@ -527,7 +528,13 @@ BTK_HD void stage_window(Ctx& ctx, const ChainSmem& L, float* s_xs, const float*
     const float* pcm_cg = pcm + cg0;
     const bool v4 = vec4 && cg0 + K::CG <= C;
     const int ntask = D * ((L.NB + LV - 1) / LV);
-    for (int task0 = tid; task0 < ntask; task0 += K::NT * TB) {
+    // Every channel group walks the same rows of interleaved PCM (a row holds all channels).  Odd groups walk the window
+    // backwards: a cyclic walk over a footprint larger than the L2 share of this CTA would miss on every pass, the
+    // back-and-forth walk re-reads the most recently touched rows first (many-channel inputs).
+    const int nbatch = (ntask + K::NT * TB - 1) / (K::NT * TB);
+    const bool backwards = ((cg0 / K::CG) & 1) != 0;
+    for (int b = 0; b < nbatch; b++) {
+      const int task0 = tid + (backwards ? nbatch - 1 - b : b) * (K::NT * TB);
       float x[TB][LV][K::CG];
       BTK_UNROLL
       for (int k = 0; k < TB; k++) {

@@ -57,12 +57,21 @@ __global__ void __launch_bounds__(ChainCfg<M, R, MT>::NT, KernCfg<M, R, MT, 1>::
   synthesis_tile<M, R, MT>(ctx, p, smem, (int)blockIdx.x);
 }
 
+// only the fused chain carries the hint; the staged kernels keep their natural occupancy
+inline bool one_cta_per_sm(const ChainParams& p) { return p.one_cta != 0; }
+inline bool one_cta_per_sm(const AnalysisParams&) { return false; }
+inline bool one_cta_per_sm(const SynthesisParams&) { return false; }
+
 template <int M, int R, int PP, class Params, class Kern>
 static cudaError_t launch_one(Kern kern, const Params& p, int m, int n_work, cudaStream_t st) {
   const ChainSmem L = chain_smem_layout<M, R, PP>(m);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+  // one_cta_per_sm(p): the launch asks for more than half of the SM's shared memory, so that only one CTA is resident
+  // (see chain_one_cta_per_sm below: many-channel inputs whose concurrent windows would not fit L2 otherwise)
+  int smem = L.total;
+  if (one_cta_per_sm(p) && smem < 116 * 1024) smem = 116 * 1024;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  kern<<<n_work, ChainCfg<M, R, 0, PP>::NT, L.total, st>>>(p);
+  kern<<<n_work, ChainCfg<M, R, 0, PP>::NT, smem, st>>>(p);
   return cudaGetLastError();
 }
 

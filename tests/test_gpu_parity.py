@@ -78,6 +78,8 @@ CASES = [  # M, m, r, dct, C, T
     (1024, 2, 2, 0, 4, 30000),
     (256, 2, 2, 0, 4, 8000),
     (512, 2, 1, 0, 4, 8000),
+    (256, 4, 1, 0, 32, 6000),     # many channels: the launch keeps one CTA per SM (L2 footprint, capi.cu chain_prepare)
+    (128, 2, 1, 0, 64, 4000),     # many channels, two CTAs per SM
 ]
 
 
