@@ -67,6 +67,7 @@ struct btkb200_plan {
   PinBuf h_desc;
   std::vector<long long> sig;  // signature of the cached chain work list
   int cached_n_work = 0;
+  int no_prefetch = 0;         // fused chain: no L2 prefetch of the next window (chain_prepare, same footprint estimate)
   int one_cta = 0;             // fused chain: keep one CTA per SM (chain_prepare decides from the L2 footprint)
   std::vector<int> rec_work_begin;   // first work item of every recording (+ total at the end)
   cudaStream_t stream = nullptr;
@@ -617,13 +618,19 @@ static int chain_prepare(btkb200_plan* p, const long long* pcm_off, const long l
   // HBM (measured: M=256, 32 channels 2.43 ms with two CTAs per SM, 1.50 ms with one; 64 channels 5.23 -> 2.94 ms; below
   // ~100 MB two CTAs stay ahead).  Then keep one CTA per SM.
   int cps = p->geo.M <= 256 ? 2 : 1;
+  int l2 = 0;
+  CK(p, cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, p->device));
+  const double window_bytes = (double)(W - 1 + p->geo.m * p->geo.R) * p->geo.D * p->Cpad * sizeof(float);
   if (cps == 2) {
-    int l2 = 0;
-    CK(p, cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, p->device));
-    const double window_bytes = (double)(W - 1 + p->geo.m * p->geo.R) * p->geo.D * p->Cpad * sizeof(float);
     static const int one_cta_env = getenv("BTK_ONE_CTA") ? atoi(getenv("BTK_ONE_CTA")) : -1;   // A/B runs
     p->one_cta = one_cta_env >= 0 ? one_cta_env : (148.0 * cps * window_bytes > 0.8 * l2);
     if (p->one_cta) cps = 1;
+  }
+  {
+    static const int npf_env = getenv("BTK_NO_PREFETCH") ? atoi(getenv("BTK_NO_PREFETCH")) : -1;   // A/B runs
+    // the L2 prefetch of the next window's new rows (all channels) evicts rows still in use once the windows fill half
+    // of L2: measured -2 % (M=512, 64 ch) to -5 % (M=1024, 32/64 ch) without it there, +1-2 % without it at 16 channels
+    p->no_prefetch = npf_env >= 0 ? npf_env : (148.0 * cps * window_bytes > 0.5 * l2);
   }
   // BTK_CHUNK_WAVES overrides the chunk model (A/B runs)
   if (getenv("BTK_CHUNK_WAVES")) build_work(recs, choose_chunk(total, H, W), work);
@@ -647,6 +654,7 @@ static int chain_launch(btkb200_plan* p, const float* d_pcm, float* d_out, int w
   c.taps_h = p->d_taps_h; c.taps_g = p->d_taps_g; c.wts = wts ? wts : p->d_wts_chain; c.wts_stride = wts_stride;
   c.twa = p->d_twa; c.twb = p->d_twb;
   c.one_cta = p->one_cta;
+  c.no_prefetch = p->no_prefetch;
   c.C = p->C; c.Cpad = p->Cpad; c.m = p->geo.m; c.pd_s = p->geo.pd_s; c.laN = p->geo.laN; c.gain = p->gain;
   CK(p, launch_chain(p->geo.M, p->geo.R, c, w1 - w0, st));
   p->launches++;

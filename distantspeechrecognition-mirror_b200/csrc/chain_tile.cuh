@@ -53,6 +53,7 @@ struct ChainParams {
   const float* taps_g;   // [m][M]    gp[k][q] = g[M-1-q + M k]
   const cf* wts;         // [Cpad][V/2][L][2] Hermitian-extended conj weights in register order
   long long wts_stride;  // elements between the tables of consecutive recordings (0: one table for the whole batch)
+  int no_prefetch;       // skip the L2 prefetch of the next window (many channels: it would evict the rows in use)
   int one_cta;           // launch hint: keep one CTA per SM (host side only, see kern_fb.cuh / capi.cu)
   const cf* twa;         // pass-A twiddles, lane-contiguous (FFTTables)
   const cf* twb;         // pass-B twiddles (three-pass transforms only)
@@ -688,7 +689,7 @@ BTK_HD void chain_tile(Ctx& ctx, const ChainParams& p, unsigned char* smem, int 
     for (int cg0 = 0; cg0 < p.Cpad; cg0 += K::CG) {
       // samples + the weights of these CG channels (register order: [c][V/2][L] float4 = 2 complex)
       stage_window<K>(ctx, L, s_xs, pcm, C, rec.T, t_lo, cg0, vec4, s_wts, p.wts + (long long)wk.rec * p.wts_stride);
-      if (cg0 == 0 && it + 1 < n_it) prefetch_next_window<K>(ctx, pcm, C, rec.T, t_lo + (long long)L.NB * K::D);
+      if (cg0 == 0 && it + 1 < n_it && !p.no_prefetch) prefetch_next_window<K>(ctx, pcm, C, rec.T, t_lo + (long long)L.NB * K::D);
       ctx.sync();
 
       // ---- per warp: PP frame pairs (tau0, tau0+1); per lane group: one channel per round

@@ -49,7 +49,7 @@ static int run_chain(int m, int dct, int C, int n_rec, const long long* Ts, cons
   build_work(recs, chunk, work);
   ChainParams p;
   p.pcm = pcm; p.out = out; p.recs = recs.data(); p.work = work.data();
-  p.taps_h = hf.data(); p.taps_g = gp.data(); p.wts = gam.data(); p.wts_stride = 0; p.one_cta = 0; p.twa = twa.data(); p.twb = twb.data();
+  p.taps_h = hf.data(); p.taps_g = gp.data(); p.wts = gam.data(); p.wts_stride = 0; p.one_cta = 0; p.no_prefetch = 0; p.twa = twa.data(); p.twb = twb.data();
   p.C = C; p.Cpad = Cpad; p.m = m; p.pd_s = geo.pd_s; p.laN = geo.laN; p.gain = gain;
   const ChainSmem L = chain_smem_layout<M, R, PP>(m);
   std::vector<unsigned char> smem(L.total + 64, 0xA5);   // poison: every read must have been written
