@@ -628,9 +628,10 @@ static int chain_prepare(btkb200_plan* p, const long long* pcm_off, const long l
   }
   {
     static const int npf_env = getenv("BTK_NO_PREFETCH") ? atoi(getenv("BTK_NO_PREFETCH")) : -1;   // A/B runs
-    // the L2 prefetch of the next window's new rows (all channels) evicts rows still in use once the windows fill half
-    // of L2: measured -2 % (M=512, 64 ch) to -5 % (M=1024, 32/64 ch) without it there, +1-2 % without it at 16 channels
-    p->no_prefetch = npf_env >= 0 ? npf_env : (148.0 * cps * window_bytes > 0.5 * l2);
+    // the L2 prefetch of the next window's new rows (all channels) evicts rows still in use once a row of PCM is a full
+    // 128-byte line or more: without it -1..-2 % at 32 channels (M = 128 .. 512), -2 % (M=512) to -5 % (M=1024) at 64,
+    // but +0.4..2.4 % at 16 channels, whatever the footprint -- the channel count decides, not the bytes in flight
+    p->no_prefetch = npf_env >= 0 ? npf_env : (p->Cpad >= 32);
   }
   // BTK_CHUNK_WAVES overrides the chunk model (A/B runs)
   if (getenv("BTK_CHUNK_WAVES")) build_work(recs, choose_chunk(total, H, W), work);
