@@ -56,7 +56,11 @@ namespace btkb200 {
 typedef std::string String;
 
 // ---- exceptions (common/jexception.h:41-173: code + formatted message) ---------------------------------------
-enum { JERROR = 0, JCONSISTENCY = 3, JDIMENSION = 4, JITERATOR = 9 };   // values of common/jexception.h:41-57
+// error_type of common/jexception.h:41-57, every value in the reference's order (0-based): the SWIG wrappers switch on
+// getCode() (include/jexception.i:63-69: JITERATOR -> StopIteration, JIO -> IOError), so the numbers are part of the ABI
+enum error_type { JERROR = 0, JALLOCATION, JARITHMETIC, JCONSISTENCY, JDIMENSION, JINDEX, JINITIALIZATION, JIO, JITERATOR,
+                  JPYTHON, JKEY, JNUMERIC, JPARAMETER, JPARSE, JTYPE };
+static_assert(JCONSISTENCY == 3 && JDIMENSION == 4 && JIO == 7 && JITERATOR == 8 && JPYTHON == 9, "common/jexception.h:41-57");
 class j_error : public std::exception {
  public:
   j_error() : _code(JERROR) {}

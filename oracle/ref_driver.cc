@@ -570,6 +570,14 @@ int btkref_error_probe(int which) {
     } else if (which == 2) {
       SubbandDS bf(8, false);
       bf.next();
+    } else if (which == 3) {
+      // end of stream: the reference's own analysis bank throws jiterator_error once its pd padded frames are out
+      // (modulated.cc:503-515)
+      gsl_vector* p = gsl_vector_calloc(16);
+      float x[8] = {0};
+      VectorFloatFeatureStreamPtr src(new MemorySampleFeature(x, 8, 1, 4));
+      OverSampledDFTAnalysisBankPtr bank(new OverSampledDFTAnalysisBank(src, p, 8, 2, 1, 0));
+      for (int i = 0; i < 64; i++) bank->next();
     }
   } catch (j_error& e) { return (int)e.getCode(); }
   catch (std::exception&) { return -2; }

@@ -60,5 +60,6 @@ def test_oracle_matches_compiled_reference(cfg, prototypes):
     assert bo.rel_l2(X, res["X"]) < 1e-13
     assert bo.rel_l2(Y, res["Y"]) < 1e-13
     assert bo.snr_db(out, res["out"]) > 140.0
-    # error behaviour the drop-in classes must reproduce: JCONSISTENCY=3, JDIMENSION=4, JERROR=0
-    assert [ref.error_probe(i) for i in range(3)] == [3, 4, 0]
+    # error behaviour the drop-in classes must reproduce: JCONSISTENCY=3, JDIMENSION=4, JERROR=0, JITERATOR=8
+    # (common/jexception.h:41-57; the SWIG layer maps code 8 to StopIteration, include/jexception.i:63-69)
+    assert [ref.error_probe(i) for i in range(4)] == [3, 4, 0, 8]
