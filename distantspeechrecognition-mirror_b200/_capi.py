@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("BTKB200_LIB") or os.path.join(_HERE, "libbtkb200.so")
 
 OK, EINVAL, ESTATE, ECUDA, ENOMEM, EUNSUPPORTED = 0, 1, 2, 3, 4, 5
 PCM_F32, PCM_S16, PCM_S24BE = 0, 1, 2      # raw PCM formats of chain_batch_pcm / convert_pcm (include/btkb200.h)
+TUNE_CHAIN_WS, TUNE_CLUSTER = 1, 2         # btkb200_plan_tune knobs (include/btkb200.h)
 
 # every symbol include/btkb200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
@@ -30,6 +31,7 @@ SYMBOLS = [
     "btkb200_design_analysis_prototype", "btkb200_design_synthesis_prototype", "btkb200_gsc_set_active_weights", "btkb200_gsc_zero_active_weights", "btkb200_gsc_get_blocking_matrix", "btkb200_gsc_apply",
     "btkb200_chain_batch_multi", "btkb200_chain_batch_dev", "btkb200_analysis_dev", "btkb200_beamform_dev",
     "btkb200_synthesis_dev", "btkb200_launch_count", "btkb200_sync", "btkb200_host_alloc", "btkb200_host_free",
+    "btkb200_plan_tune", "btkb200_plan_tuning",
 ]
 
 
@@ -115,6 +117,8 @@ def lib() -> ctypes.CDLL:
     L.btkb200_analysis_dev.argtypes = [vp, vp, c_long, vp, vp]
     L.btkb200_beamform_dev.argtypes = [vp, vp, c_long, vp, vp]
     L.btkb200_synthesis_dev.argtypes = [vp, vp, c_long, vp, vp]
+    L.btkb200_plan_tune.argtypes = [vp, c_int, c_int]
+    L.btkb200_plan_tuning.argtypes = [vp, c_int]
     L.btkb200_launch_count.restype = c_long
     L.btkb200_launch_count.argtypes = [vp]
     L.btkb200_sync.argtypes = [vp]
@@ -436,6 +440,18 @@ class Plan:
 
     def launch_count(self) -> int:
         return int(self._L.btkb200_launch_count(self._h))
+
+    def tune(self, chain_ws: int | None = None, cluster: int | None = None):
+        """Launch-geometry knobs of the fused chain (btkb200_plan_tune): A/B runs and tests only."""
+        if chain_ws is not None:
+            self._ck(self._L.btkb200_plan_tune(self._h, TUNE_CHAIN_WS, int(chain_ws)))
+        if cluster is not None:
+            self._ck(self._L.btkb200_plan_tune(self._h, TUNE_CLUSTER, int(cluster)))
+
+    def tuning(self) -> dict:
+        """What the last fused-chain launch used: {'chain_ws': 0|1, 'cluster': n} (-1 before any launch)."""
+        return {"chain_ws": int(self._L.btkb200_plan_tuning(self._h, TUNE_CHAIN_WS)),
+                "cluster": int(self._L.btkb200_plan_tuning(self._h, TUNE_CLUSTER))}
 
     def sync(self):
         self._ck(self._L.btkb200_sync(self._h))

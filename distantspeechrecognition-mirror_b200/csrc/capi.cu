@@ -69,6 +69,10 @@ struct btkb200_plan {
   int cached_n_work = 0;
   int no_prefetch = 0;         // fused chain: no L2 prefetch of the next window (chain_prepare, same footprint estimate)
   int one_cta = 0;             // fused chain: keep one CTA per SM (chain_prepare decides from the L2 footprint)
+  int use_ws = 0;              // fused chain: the warp-specialised producer / consumer kernel (chain_ws.cuh) runs this shape
+  int cluster = 1;             // ... with this many CTAs of a thread-block cluster sharing a work item (channel split)
+  int tune_ws = -1, tune_cluster = 0;   // btkb200_plan_tune overrides (-1 / 0 = automatic)
+  bool launched_chain = false;
   std::vector<int> rec_work_begin;   // first work item of every recording (+ total at the end)
   cudaStream_t stream = nullptr;
   cudaStream_t s_in = nullptr, s_out = nullptr;   // copy engines of the pipelined host-buffer path
@@ -611,15 +615,50 @@ static int chain_prepare(btkb200_plan* p, const long long* pcm_off, const long l
     total += recs[i].nblk;
   }
   std::vector<WorkItem> work;
-  const int W = chain_frames_per_iter(p->geo.M, p->geo.R, p->geo.m), H = p->geo.m * p->geo.R - 1;
+  const int H = p->geo.m * p->geo.R - 1;
+  int l2 = 0;
+  CK(p, cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, p->device));
+  // The warp-specialised kernel (one CTA per SM: eight transform warps fed by a producer warpgroup through two
+  // mbarrier-guarded stages) runs every shape whose stages fit shared memory; BTK_CHAIN_WS=0 keeps the first
+  // sessions' kernel for A/B runs.
+  {
+    static const int ws_env = getenv("BTK_CHAIN_WS") ? atoi(getenv("BTK_CHAIN_WS")) : -1;
+    const int Wws = chain_ws_frames_per_iter(p->geo.M, p->geo.R, p->geo.m);
+    p->use_ws = (Wws > 0 && (p->tune_ws >= 0 ? p->tune_ws != 0 : ws_env != 0)) ? 1 : 0;
+    p->cluster = 1;
+    if (p->use_ws) {
+      // Channel split over a thread-block cluster: S CTAs share a work item, each stages only its own channel groups and
+      // the partial beamformer outputs are summed through distributed shared memory.  Without it one CTA walks the rows
+      // of interleaved PCM (all channels per row) Cpad/4 times out of L2, and the windows of 148 CTAs have to survive
+      // there: 111 MB at 64 channels (M = 512), 7 x the input bytes re-read from HBM at M = 1024.
+      // The smallest power of two that brings the windows in flight under a third of L2 and leaves at most four
+      // channel groups per CTA is used.
+      static const int cl_env = getenv("BTK_CLUSTER") ? atoi(getenv("BTK_CLUSTER")) : 0;
+      const int n_groups = p->Cpad / 4;
+      const double window_all = (double)(Wws - 1 + p->geo.m * p->geo.R) * p->geo.D * p->Cpad * sizeof(float);
+      int S = 1;
+      while (S < 8 && n_groups % (2 * S) == 0 && chain_ws_cluster_ok(p->geo.M, p->geo.R, p->geo.m, 2 * S) &&
+             (148.0 * window_all / S > l2 / 3.0 || n_groups / S > 4))
+        S *= 2;
+      if (cl_env > 0 && n_groups % cl_env == 0 && chain_ws_cluster_ok(p->geo.M, p->geo.R, p->geo.m, cl_env)) S = cl_env;
+      if (p->tune_cluster > 0) S = p->tune_cluster;     // validated by btkb200_plan_tune
+      p->cluster = S;
+    }
+    if (p->use_ws) {
+      int slots = 148 / p->cluster;
+      if (getenv("BTK_CHUNK_WAVES")) build_work(recs, choose_chunk(total, H, Wws), work);
+      else build_work(recs, choose_chunk_model(recs, H, Wws, slots), work);
+      p->one_cta = 1; p->no_prefetch = 1;
+    }
+  }
+  const int W = chain_frames_per_iter(p->geo.M, p->geo.R, p->geo.m);
+  if (!p->use_ws) {
   // two CTAs per SM for M <= 256 (kern_fb.cuh KernCfg::MINB), one otherwise.  Every resident CTA walks its window of
   // (W - 1 + mR) blocks of D time steps once per group of four channels, and the rows of interleaved PCM it touches hold
   // ALL channels: when the windows of all resident CTAs together no longer fit L2, each of the Cpad/4 passes goes back to
   // HBM (measured: M=256, 32 channels 2.43 ms with two CTAs per SM, 1.50 ms with one; 64 channels 5.23 -> 2.94 ms; below
   // ~100 MB two CTAs stay ahead).  Then keep one CTA per SM.
   int cps = p->geo.M <= 256 ? 2 : 1;
-  int l2 = 0;
-  CK(p, cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, p->device));
   const double window_bytes = (double)(W - 1 + p->geo.m * p->geo.R) * p->geo.D * p->Cpad * sizeof(float);
   if (cps == 2) {
     static const int one_cta_env = getenv("BTK_ONE_CTA") ? atoi(getenv("BTK_ONE_CTA")) : -1;   // A/B runs
@@ -636,6 +675,7 @@ static int chain_prepare(btkb200_plan* p, const long long* pcm_off, const long l
   // BTK_CHUNK_WAVES overrides the chunk model (A/B runs)
   if (getenv("BTK_CHUNK_WAVES")) build_work(recs, choose_chunk(total, H, W), work);
   else build_work(recs, choose_chunk_model(recs, H, W, 148 * cps), work);
+  }
   p->rec_work_begin.assign(n + 1, 0);
   for (size_t w = 0; w < work.size(); w++) p->rec_work_begin[work[w].rec + 1]++;
   for (int i = 0; i < n; i++) p->rec_work_begin[i + 1] += p->rec_work_begin[i];
@@ -657,7 +697,10 @@ static int chain_launch(btkb200_plan* p, const float* d_pcm, float* d_out, int w
   c.one_cta = p->one_cta;
   c.no_prefetch = p->no_prefetch;
   c.C = p->C; c.Cpad = p->Cpad; c.m = p->geo.m; c.pd_s = p->geo.pd_s; c.laN = p->geo.laN; c.gain = p->gain;
-  CK(p, launch_chain(p->geo.M, p->geo.R, c, w1 - w0, st));
+  c.cluster = p->use_ws ? p->cluster : 1;
+  if (p->use_ws) CK(p, launch_chain_ws(p->geo.M, p->geo.R, c, w1 - w0, st));
+  else CK(p, launch_chain(p->geo.M, p->geo.R, c, w1 - w0, st));
+  p->launched_chain = true;
   p->launches++;
   return BTKB200_OK;
 }
@@ -676,6 +719,32 @@ int btkb200_chain_batch_dev(btkb200_plan* p, const float* d_pcm, const long long
 }
 
 long btkb200_launch_count(const btkb200_plan* p) { return p ? p->launches : -1; }
+
+int btkb200_plan_tune(btkb200_plan* p, int knob, int value) {
+  if (!p) return BTKB200_EINVAL;
+  const bool has_ws = chain_ws_frames_per_iter(p->geo.M, p->geo.R, p->geo.m) > 0;
+  if (knob == BTKB200_TUNE_CHAIN_WS) {
+    if (value > 0 && !has_ws)
+      return fail(p, BTKB200_EUNSUPPORTED, "no warp-specialised chain kernel for M=%d r=%d m=%d", p->geo.M, p->geo.r, p->geo.m);
+    p->tune_ws = value < 0 ? -1 : (value ? 1 : 0);
+  } else if (knob == BTKB200_TUNE_CLUSTER) {
+    if (value < 0 || value > 8) return fail(p, BTKB200_EUNSUPPORTED, "cluster size %d outside 0..8", value);
+    if (value > 0 && (!has_ws || (p->Cpad / 4) % value != 0 || !chain_ws_cluster_ok(p->geo.M, p->geo.R, p->geo.m, value)))
+      return fail(p, BTKB200_EUNSUPPORTED, "cluster of %d CTAs impossible for %d channels, M=%d", value, p->C, p->geo.M);
+    p->tune_cluster = value;
+  } else {
+    return fail(p, BTKB200_EINVAL, "unknown tuning knob %d", knob);
+  }
+  p->sig.clear();      // the next launch rebuilds its work list
+  return BTKB200_OK;
+}
+
+int btkb200_plan_tuning(const btkb200_plan* p, int knob) {
+  if (!p || !p->launched_chain) return -1;
+  if (knob == BTKB200_TUNE_CHAIN_WS) return p->use_ws;
+  if (knob == BTKB200_TUNE_CLUSTER) return p->use_ws ? p->cluster : 1;
+  return -1;
+}
 
 int btkb200_sync(btkb200_plan* p) {
   if (!p) return BTKB200_EINVAL;

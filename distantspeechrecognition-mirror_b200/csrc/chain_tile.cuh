@@ -62,6 +62,8 @@ struct ChainParams {
   int pd_s;              // synthesis processing delay (frames)
   int laN;               // analysis look-ahead (frames skipped)
   int gain;              // synthesis gainFactor
+  int cluster;           // warp-specialised chain only (chain_ws.cuh): CTAs per work item, the channel groups are split
+                         // across the CTAs of a thread-block cluster (0 / 1 = no cluster)
 };
 
 template <int M_, int R_, int MT_ = 0, int PP_ = 1>
@@ -87,6 +89,7 @@ struct ChainCfg {
   static constexpr int W = FW * NW;            // analysis frames per iteration
   static constexpr int CG = 4;                 // channels staged per pass (one float4 per time step)
   static constexpr int NG = G::NG;             // lane groups per warp = channels processed concurrently
+  static constexpr int XS = PP_;               // exchange buffers per lane group (one per frame pair)
   static constexpr int E = G::Ra / R_;         // registers between members of one residue class
   // emit: frames per thread (register blocking of the synthesis polyphase)
   static constexpr int FPT_RAW = (W * D) / NT;
@@ -276,17 +279,25 @@ BTK_HD void polyphase_pairs(cf* z, int gl, const float* xch, int warp, const flo
 // two Hermitian spectra).  With one lane group per warp (NG == 1) group 0 transforms its PP pairs one after the
 // other; otherwise group pp (< PP) transforms pair pp, which synth_gather_pairs left in its ts.g[0..V).
 // ---------------------------------------------------------------------------------------------
+// (pair_mod, pair_rem): only the frame pairs P = warp * PP + pp with P % pair_mod == pair_rem are transformed and stored
+// (cluster mode of chain_ws.cuh: the other pairs' sums live in other CTAs); every pair by default.  A lane that owns
+// several pairs (NG == 1 with PP > 1) is selected by its first pair; no configuration combines that with a cluster.
 template <class K, class Ctx>
-BTK_HD void synth_transform_store(Ctx& ctx, cf* s_xbuf, const cf* s_twa, const cf* s_twb, float* s_vcur, int tau_base) {
+BTK_HD void synth_transform_store(Ctx& ctx, cf* s_xbuf, const cf* s_twa, const cf* s_twb, float* s_vcur, int tau_base,
+                                  int pair_mod = 1, int pair_rem = 0) {
   typedef typename K::G G;
   constexpr int M_ = K::M;
   constexpr int NP = K::NG == 1 ? K::PP : 1;                 // transforms per owning lane
   typedef ChainThreadState<M_, K::PP> TS;
-  auto owns = [](int grp) { return K::NG == 1 ? grp == 0 : grp < K::PP; };
-  auto slot = [&](int warp, int grp) { return s_xbuf + ((warp * K::NG + grp) * K::PP) * G::XBUF; };
+  auto owns = [&](int warp, int grp) {
+    if (!(K::NG == 1 ? grp == 0 : grp < K::PP)) return false;
+    return pair_mod <= 1 || (warp * K::PP + (K::NG == 1 ? 0 : grp)) % pair_mod == pair_rem;
+  };
+  static_assert(K::NG > 1 || K::XS == K::PP, "a lane owning PP transforms needs PP exchange buffers");
+  auto slot = [&](int warp, int grp) { return s_xbuf + ((warp * K::NG + grp) * K::XS) * G::XBUF; };
   ctx.par([&](int tid, TS& ts) {
     const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
-    if (owns(grp)) {
+    if (owns(warp, grp)) {
       if (G::ASYM) GroupFFT<M_, -1>::template inv_step1_multi<NP>(ts.g, gl, slot(warp, grp), s_twa);
       else GroupFFT<M_, -1>::template step1_multi<NP>(ts.g, gl, slot(warp, grp), s_twa);
     }
@@ -295,7 +306,7 @@ BTK_HD void synth_transform_store(Ctx& ctx, cf* s_xbuf, const cf* s_twa, const c
   if (G::Rb > 1) {
     ctx.par([&](int tid, TS& ts) {
       const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
-      if (owns(grp)) {
+      if (owns(warp, grp)) {
         BTK_UNROLL
         for (int pp = 0; pp < NP; pp++) GroupFFT<M_, -1>::step2_load(ts.g + pp * G::V, gl, slot(warp, grp) + pp * G::XBUF, s_twb);
       }
@@ -303,7 +314,7 @@ BTK_HD void synth_transform_store(Ctx& ctx, cf* s_xbuf, const cf* s_twa, const c
     ctx.syncwarp();
     ctx.par([&](int tid, TS& ts) {
       const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
-      if (owns(grp)) {
+      if (owns(warp, grp)) {
         BTK_UNROLL
         for (int pp = 0; pp < NP; pp++) GroupFFT<M_, -1>::step2_store(ts.g + pp * G::V, gl, slot(warp, grp) + pp * G::XBUF);
       }
@@ -312,7 +323,7 @@ BTK_HD void synth_transform_store(Ctx& ctx, cf* s_xbuf, const cf* s_twa, const c
   }
   ctx.par([&](int tid, TS& ts) {
     const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
-    if (owns(grp)) {
+    if (owns(warp, grp)) {
       BTK_UNROLL
       for (int pp = 0; pp < NP; pp++) {
         if (G::ASYM) GroupFFT<M_, -1>::inv_step3(ts.g + pp * G::V, gl, slot(warp, grp) + pp * G::XBUF);
@@ -341,7 +352,9 @@ BTK_HD void synth_gather_pairs(Ctx& ctx, cf* s_xbuf) {
   typedef ChainThreadState<K::M, K::PP> TS;
   static_assert(K::NG == 1 || K::NG >= K::PP, "a lane group per frame pair");
   if (K::NG == 1) return;
-  auto slot = [&](int warp, int grp, int pp) { return s_xbuf + ((warp * K::NG + grp) * K::PP + pp) * G::XBUF; };
+  // with one exchange buffer per lane group (XS == 1 < PP) every group parks exactly one partial: needs NG == PP == 2
+  static_assert(K::XS == K::PP || (K::XS == 1 && K::NG == 2 && K::PP == 2), "exchange buffers per lane group");
+  auto slot = [&](int warp, int grp, int pp) { return s_xbuf + ((warp * K::NG + grp) * K::XS + (K::XS == K::PP ? pp : 0)) * G::XBUF; };
   ctx.par([&](int tid, TS& ts) {
     const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
     BTK_UNROLL
@@ -391,13 +404,14 @@ BTK_HD const float* v_frame(const float* s_vhist, const float* s_vcur, int H, in
 // ---------------------------------------------------------------------------------------------
 template <class K, class Ctx>
 BTK_HD void synth_emit(Ctx& ctx, const ChainSmem& L, const float* taps_g, const float* s_vhist, const float* s_vcur,
-                       float* out, int m, int pd_s, int gain, int tau_base, int j0, int nj) {
+                       float* out, int m, int pd_s, int gain, int tau_base, int j0, int nj, int d_lo = 0, int d_n = K::D) {
   constexpr int M_ = K::M, R_ = K::R, D = K::D, FPT = K::FPT;
   typedef ChainThreadState<M_, K::PP> TS;
   const float gf = gain > 0 ? (float)gain : 1.f;
   ctx.par([&](int tid, TS&) {
-    for (int u = tid; u < D * (K::W / FPT); u += K::NT) {
-      const int d = u % D, f0 = (u / D) * FPT;        // frames f0 .. f0+FPT-1 of this iteration
+    // (d_lo, d_n): the slice of every output frame this CTA writes (the whole frame unless a cluster shares the item)
+    for (int u = tid; u < d_n * (K::W / FPT); u += K::NT) {
+      const int d = d_lo + u % d_n, f0 = (u / d_n) * FPT;        // frames f0 .. f0+FPT-1 of this iteration
       const int jb = tau_base + f0 - pd_s;            // output frame index of f0
       if (jb + FPT <= j0 || jb >= j0 + nj) continue;
       float acc[FPT];
@@ -469,7 +483,38 @@ BTK_HD void analysis_round(Ctx& ctx, const ChainSmem& L, const float* s_xs, cons
   typedef typename K::G G;
   constexpr int M_ = K::M;
   typedef ChainThreadState<M_, K::PP> TS;
-  auto slot = [&](int warp, int grp) { return s_xbuf + ((warp * K::NG + grp) * K::PP) * G::XBUF; };
+  auto slot = [&](int warp, int grp) { return s_xbuf + ((warp * K::NG + grp) * K::XS) * G::XBUF; };
+  if constexpr (K::XS < K::PP) {
+    // the frame pairs of a lane take turns on one exchange buffer: pass A of all pairs (one set of twiddles), then
+    // scatter / gather pair by pair, then the final radix passes
+    ctx.par([&](int tid, TS& ts) {
+      const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+      const int c_local = round * K::NG + grp;
+      polyphase_pairs<K>(ts.z, gl, s_xs + c_local * L.CS, warp, s_taps, L, m);
+      GroupFFT<M_, +1>::template step1_twiddle<K::PP>(ts.z, gl, s_twa);
+      GroupFFT<M_, +1>::step1_scatter(ts.z, gl, slot(warp, grp));
+    });
+    ctx.syncwarp();
+    for (int pp = 0; pp < K::PP; pp++) {
+      ctx.par([&](int tid, TS& ts) {
+        const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+        GroupFFT<M_, +1>::step3_gather(ts.z + pp * G::V, gl, slot(warp, grp));
+      });
+      ctx.syncwarp();
+      if (pp + 1 < K::PP) {
+        ctx.par([&](int tid, TS& ts) {
+          const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+          GroupFFT<M_, +1>::step1_scatter(ts.z + (pp + 1) * G::V, gl, slot(warp, grp));
+        });
+        ctx.syncwarp();
+      }
+    }
+    ctx.par([&](int, TS& ts) {
+      BTK_UNROLL
+      for (int pp = 0; pp < K::PP; pp++) GroupFFT<M_, +1>::step3_dft(ts.z + pp * G::V);
+    });
+    return;
+  }
   ctx.par([&](int tid, TS& ts) {
     const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
     const int c_local = round * K::NG + grp;

@@ -1,0 +1,365 @@
+// chain_ws.cuh -- the fused hot path (chain_tile.cuh) as a warp-specialised producer / consumer pipeline.
+//
+// Same arithmetic, same framing, same register programs as chain_tile.cuh (reference: modulated/modulated.cc:412-516,
+// 595-664; beamformer/beamformer.cc:1137-1200, 2583-2635).  What changes is WHO moves the samples:
+//
+//   * NW compute warps never touch global PCM.  They wait on an mbarrier for a staged window of CG = 4 channels, run
+//     polyphase -> backward transform -> weight accumulate on it, and hand the stage back.  Between channel groups there
+//     is no CTA barrier any more: warps drift against each other by up to one stage.
+//   * one producer warpgroup (4 warps, its registers given to the compute warps with setmaxnreg) walks the same
+//     sequence of (iteration, channel group) windows one stage AHEAD: coalesced 16-byte loads of interleaved PCM,
+//     register transpose, 16-byte shared stores into the residue-major window (stage_window's scheme), and ONE
+//     cp.async.bulk per stage for the 4 channels' weight rows, completing on the stage's "full" mbarrier.
+//   * NS = 2 stages.  The window of the next channel group (or of the next iteration's first group) lands while the
+//     transforms of the current one run, so global-load latency never sits on a transform warp.
+//   * the synthesis side's current-v frames alias the window of the LAST stage of an iteration where they fit; that
+//     stage is handed back after the overlap-add instead of after the last transform.
+//
+// Thread-block clusters (channel split): with p.cluster = S > 1 the S CTAs of a cluster share one work item and CTA
+// `rank` takes channel groups [rank * ncg, (rank + 1) * ncg).  A row of interleaved PCM is then read by S CTAs, each
+// touching only its own 16-byte granules, instead of being walked C/4 times by one CTA out of L2 -- the L2 footprint of
+// all windows in flight drops by S and every PCM byte is fetched from HBM once.  The partial
+// beamformer outputs G of the ranks are summed through distributed shared memory: every rank writes the partial of
+// frame pair P into the receive buffer of rank P mod S, that rank adds them up, runs the forward transform and
+// broadcasts the two real v frames to all ranks; every rank keeps the complete v history and emits its D/S slice of
+// each output frame.  Cluster-scope synchronisation is done with mbarriers arrived on remotely by the compute warps
+// only, so the producer warps keep running ahead.
+//
+// The tile program is written against a context like chain_tile.cuh, so the CPU-only tests run the very same code
+// sequentially (tests/emu): ctx.acquire(stage, parity, fill) waits for the producer on the device and runs `fill`
+// (the producer's per-thread routine for that stage, for every producer thread) inline on the host.
+#pragma once
+
+#include "chain_tile.cuh"
+
+namespace btk {
+
+template <int M_, int R_, int MT_ = 0, int PP_ = 1>
+struct WsCfg {
+  typedef FFTGeom<M_> G;
+  static constexpr int M = M_, R = R_, D = M_ / R_;
+  static constexpr int MT = MT_;
+  static constexpr int PP = PP_;
+  // eight compute warps (two per scheduler) wherever the exchange buffers allow; the 32-lane transforms of M = 1024
+  // keep four
+  static constexpr int NW = M_ >= 1024 ? 4 : 8;
+  static constexpr int NT = NW * 32;
+  static constexpr int NPW = 4;                // producer warps: one warpgroup (setmaxnreg works on warpgroups)
+  static constexpr int NPT = NPW * 32;
+  static constexpr int FW = 2 * PP_;
+  static constexpr int LV = (FW % 4 == 0) ? 4 : 2;
+  static constexpr int W = FW * NW;
+  static constexpr int CG = 4;
+  static constexpr int NG = G::NG;
+  // exchange buffers per lane group: the two frame pairs of M = 256 take turns on one (analysis_round), which is what
+  // lets two 4-channel stages of the 32-frame window fit next to the buffers of eight warps
+  static constexpr int XS = (PP_ == 2 && G::Rb == 1 && G::Ra <= 16 && G::NG == 2) ? 1 : PP_;
+  static constexpr int E = G::Ra / R_;
+  static constexpr int FPT_RAW = (W * D) / NT;
+  static constexpr int FPT = FPT_RAW >= 8 ? 8 : (FPT_RAW >= 4 ? 4 : (FPT_RAW >= 2 ? 2 : 1));
+  static constexpr int NS = 2;                 // stages
+  static_assert(G::Ra % R_ == 0, "decimation factor must divide the first radix");
+  static_assert(CG % NG == 0, "channel group must be a multiple of the lane groups per warp");
+  static_assert(W % FPT == 0, "frames per thread must divide the iteration");
+};
+
+struct WsSmem {
+  ChainSmem L;          // TS, TV, NB, SB, CS, H + taps / twa / twb offsets (the fields the shared tile pieces read)
+  int bars;             // mbarriers: full[NS], empty[NS], tables, cluster barriers
+  int stage0;           // first stage; a stage = window of CG channels, then their weight rows
+  int stage_bytes;
+  int wts_off;          // offset of the weight rows inside a stage
+  int xbuf, vhist, vcur;
+  int rbuf;             // cluster receive buffer (aliases the exchange buffers: they are idle during the reduction)
+  int valias;           // current-v frames alias the window of a stage
+  int total;
+};
+
+enum { WS_BAR_FULL = 0, WS_BAR_EMPTY = 2, WS_BAR_TABLES = 4, WS_BAR_CL0 = 5, WS_BAR_CL1 = 6, WS_BAR_CL2 = 7, WS_NBARS = 8 };
+
+template <int M_, int R_, int PP_>
+BTK_HD constexpr WsSmem ws_smem_layout(int m) {
+  typedef WsCfg<M_, R_, 0, PP_> K;
+  typedef FFTTables<M_> FT;
+  WsSmem s = WsSmem();
+  const int mR = m * R_;
+  s.L.TV = tap_vec(mR);
+  s.L.TS = tap_stride(mR);
+  s.L.NB = K::W - 1 + mR;
+  int sb = 0;
+  if (K::LV == 4) {
+    sb = (s.L.NB + 3) & ~3;
+    if (((sb / 4) & 1) != 0) sb += 4;
+  } else {
+    sb = (s.L.NB + 1) & ~1;
+    if (((sb / 2) & 1) == 0) sb += 2;
+  }
+  s.L.SB = sb;
+  int cs = K::D * sb;
+  if (K::G::L < 16) cs += (16 - (cs & 31) + 32) & 31;
+  s.L.CS = cs;
+  s.L.H = mR - 1;
+  int off = 0;
+  s.bars = off;   off += WS_NBARS * 8;                  off = (off + 127) & ~127;
+  s.L.taps = off; off += K::D * s.L.TS * 4;             off = (off + 15) & ~15;
+  s.L.twa = off;  off += FT::TWA_WORDS * 8;             off = (off + 15) & ~15;
+  s.L.twb = off;  off += FT::TWB_WORDS * 8;             off = (off + 127) & ~127;
+  const int win = K::CG * cs * 4;
+  s.wts_off = (win + 127) & ~127;
+  s.stage_bytes = (s.wts_off + K::CG * M_ * 8 + 127) & ~127;
+  s.stage0 = off; off += K::NS * s.stage_bytes;
+  s.xbuf = off;   off += K::NW * K::NG * K::XS * K::G::XBUF * 8;   off = (off + 15) & ~15;
+  s.vhist = off;  off += (s.L.H > 0 ? s.L.H : 1) * M_ * 4;          off = (off + 15) & ~15;
+  s.valias = (K::W * M_ * 4 <= win) ? 1 : 0;
+  s.vcur = off;
+  if (!s.valias) off += K::W * M_ * 4;
+  s.rbuf = s.xbuf;
+  s.L.xs = s.stage0; s.L.wts = s.stage0 + s.wts_off; s.L.xbuf = s.xbuf; s.L.vhist = s.vhist;
+  s.total = off;
+  s.L.total = off;
+  return s;
+}
+
+// cluster receive buffer: NW * PP pairs in total, [src rank][owned pair] blocks of V * L complex words
+template <class K>
+BTK_HD constexpr bool ws_cluster_ok(int S) {
+  return S >= 1 && (K::NW * K::PP) % S == 0 && K::D % S == 0 &&
+         K::NW * K::PP * K::M * 8 <= K::NW * K::NG * K::XS * K::G::XBUF * 8 && K::NG <= 2;
+}
+
+// The window one producer pass stages: iteration `it`, channel group `cgi` of this CTA.
+struct WsWalk {
+  int a_start, n_it, ncg, cg_base;
+  BTK_HD int groups() const { return n_it * ncg; }
+};
+
+// One producer thread's share of a stage: CG channels [cg0, cg0 + CG) of the window starting at sample t_lo,
+// pcm [t][C] -> s_xs[c][t mod D][t div D] (residue-major, see chain_tile.cuh::stage_window for the layout and the
+// register transpose).  TB tasks (= TB * LV 16-byte loads) are in flight per thread.
+template <class K, int TB>
+BTK_HD void ws_fill_thread(int ptid, const ChainSmem& L, float* s_xs, const float* pcm, int C, int T, long long t_lo,
+                           int cg0, bool vec4) {
+  constexpr int D = K::D, LV = K::LV;
+  static_assert(K::CG == 4, "one float4 per time step");
+  const int t0 = (int)t_lo;
+  const float* pcm_cg = pcm + cg0;
+  const bool v4 = vec4 && cg0 + K::CG <= C;
+  const int ntask = D * ((L.NB + LV - 1) / LV);
+  const int nbatch = (ntask + K::NPT * TB - 1) / (K::NPT * TB);
+  for (int b = 0; b < nbatch; b++) {
+    const int task0 = ptid + b * (K::NPT * TB);
+    float x[TB][LV][K::CG];
+    BTK_UNROLL
+    for (int k = 0; k < TB; k++) {
+      const int task = task0 + k * K::NPT;
+      const int res = task % D, bg = task / D;
+      BTK_UNROLL
+      for (int i = 0; i < LV; i++) {
+        const int blk = bg * LV + i;
+        const int t = t0 + blk * D + res;
+        BTK_UNROLL
+        for (int c = 0; c < K::CG; c++) x[k][i][c] = 0.f;
+        if (task < ntask && blk < L.NB && (unsigned)t < (unsigned)T) {
+          const float* src = pcm_cg + (size_t)((unsigned)t) * (unsigned)C;
+          if (v4) {
+            const float4 q = *reinterpret_cast<const float4*>(src);
+            x[k][i][0] = q.x; x[k][i][1] = q.y; x[k][i][2] = q.z; x[k][i][3] = q.w;
+          } else {
+            BTK_UNROLL
+            for (int c = 0; c < K::CG; c++) if (cg0 + c < C) x[k][i][c] = src[c];
+          }
+        }
+      }
+    }
+    BTK_UNROLL
+    for (int k = 0; k < TB; k++) {
+      const int task = task0 + k * K::NPT;
+      if (task < ntask) {
+        const int res = task % D, bg = task / D;
+        float* dst = s_xs + xs_off<LV>(res, bg, L.SB);
+        BTK_UNROLL
+        for (int c = 0; c < K::CG; c++) {
+          if (LV == 4) {
+            float4 v; v.x = x[k][0][c]; v.y = x[k][1][c]; v.z = x[k][LV > 2 ? 2 : 0][c]; v.w = x[k][LV - 1][c];
+            *reinterpret_cast<float4*>(dst + c * L.CS) = v;
+          } else {
+            float2 v; v.x = x[k][0][c]; v.y = x[k][1][c];
+            *reinterpret_cast<float2*>(dst + c * L.CS) = v;
+          }
+        }
+      }
+    }
+  }
+}
+
+// oldest sample of the window of iteration `it`: frame i = tau_base + laN needs x[(i+1) D - N .. (i+1) D - 1]
+template <class K>
+BTK_HD long long ws_window_start(const WsWalk& w, int it, int laN, int N) {
+  const int tau_base = w.a_start + it * K::W;
+  return (long long)(tau_base + laN + 1) * K::D - N;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The compute side of the tile program.  Ctx provides, besides par / sync / syncwarp of chain_tile.cuh (sync = barrier
+// of the COMPUTE threads only):
+//   acquire(stage, parity, fill)    wait until the producer has filled `stage`; the host context runs fill() instead
+//   release(stage)                  this warp (device) / the CTA (host) is done with `stage`
+//   wait_tables()                   taps and twiddles have landed
+//   cluster hooks (only used when p.cluster > 1):
+//     cl_rank() / cl_size(), cl_sync(k): cluster-wide barrier k of the compute warps,
+//     cl_map(ptr, rank): the same shared-memory address in CTA `rank`
+// ---------------------------------------------------------------------------------------------
+template <int M_, int R_, int MT_, int PP_, class Ctx>
+BTK_HD void chain_ws_compute(Ctx& ctx, const ChainParams& p, unsigned char* smem, const WorkItem wk, const RecDesc rec) {
+  typedef WsCfg<M_, R_, MT_, PP_> K;
+  typedef typename K::G G;
+  typedef ChainThreadState<M_, PP_> TS;
+  const int m = MT_ > 0 ? MT_ : p.m;
+  const int N = M_ * m;
+  const WsSmem S = ws_smem_layout<M_, R_, PP_>(m);
+  const ChainSmem& L = S.L;
+  const int H = L.H;
+  float* s_taps = reinterpret_cast<float*>(smem + L.taps);
+  cf* s_twa = reinterpret_cast<cf*>(smem + L.twa);
+  cf* s_twb = reinterpret_cast<cf*>(smem + L.twb);
+  cf* s_xbuf = reinterpret_cast<cf*>(smem + S.xbuf);
+  float* s_vhist = reinterpret_cast<float*>(smem + S.vhist);
+
+  const float* pcm = p.pcm + rec.pcm_off;
+  float* out = p.out + rec.out_off;
+  const int C = p.C;
+  const int csz = p.cluster > 1 ? p.cluster : 1;
+  const int rank = csz > 1 ? ctx.cl_rank() : 0;
+  WsWalk walk;
+  walk.a_start = wk.j0 + p.pd_s - H;
+  walk.n_it = (wk.nj + H + K::W - 1) / K::W;
+  walk.ncg = (p.Cpad / K::CG) / csz;
+  walk.cg_base = rank * walk.ncg;
+  const bool vec4 = (C % 4 == 0) && (rec.pcm_off % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.pcm) & 15) == 0);
+  const cf* wts = p.wts + (long long)wk.rec * p.wts_stride;
+
+  ctx.par([&](int tid, TS&) {
+    for (int i = tid; i < H * M_; i += K::NT) s_vhist[i] = 0.f;
+  });
+  ctx.wait_tables();
+  ctx.sync();
+
+  int g = 0;                                                  // stages consumed so far
+  for (int it = 0; it < walk.n_it; it++) {
+    const int tau_base = walk.a_start + it * K::W;
+    const long long t_lo = ws_window_start<K>(walk, it, p.laN, N);
+    ctx.par([&](int, TS& ts) {
+      BTK_UNROLL
+      for (int r = 0; r < PP_ * G::V; r++) ts.g[r] = mk(0.f, 0.f);
+    });
+    int s_last = 0;
+    for (int cgi = 0; cgi < walk.ncg; cgi++, g++) {
+      const int st = g % K::NS;
+      unsigned char* stage = smem + S.stage0 + st * S.stage_bytes;
+      float* s_xs = reinterpret_cast<float*>(stage);
+      const float4* s_wts = reinterpret_cast<const float4*>(stage + S.wts_off);
+      const int cg0 = (walk.cg_base + cgi) * K::CG;
+      ctx.acquire(st, (g / K::NS) & 1, [&]() {
+        for (int ptid = 0; ptid < K::NPT; ptid++) ws_fill_thread<K, 1>(ptid, L, s_xs, pcm, C, rec.T, t_lo, cg0, vec4);
+        const float4* src = reinterpret_cast<const float4*>(wts + (long long)cg0 * M_);
+        float4* dst = reinterpret_cast<float4*>(stage + S.wts_off);
+        for (int i = 0; i < K::CG * M_ / 2; i++) dst[i] = src[i];
+      });
+      for (int round = 0; round < K::CG / K::NG; round++) {
+        analysis_round<K>(ctx, L, s_xs, s_taps, s_xbuf, s_twa, s_twb, m, round);
+        ctx.par([&](int tid, TS& ts) {
+          const int lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+          const float4* w4 = s_wts + (round * K::NG + grp) * (G::V / 2) * G::L + gl;
+          BTK_UNROLL
+          for (int r2 = 0; r2 < G::V / 2; r2++) {
+            const float4 w = w4[r2 * G::L];
+            BTK_UNROLL
+            for (int pp = 0; pp < PP_; pp++) {
+              cfma(ts.g[pp * G::V + 2 * r2], ts.z[pp * G::V + 2 * r2], mk(w.x, w.y));
+              cfma(ts.g[pp * G::V + 2 * r2 + 1], ts.z[pp * G::V + 2 * r2 + 1], mk(w.z, w.w));
+            }
+          }
+        });
+        ctx.syncwarp();
+      }
+      s_last = st;
+      // the stage whose window the v frames alias stays with the compute warps until the overlap-add is done
+      if (!(S.valias && cgi + 1 == walk.ncg)) ctx.release(st);
+    }
+    float* s_vcur = S.valias ? reinterpret_cast<float*>(smem + S.stage0 + s_last * S.stage_bytes)
+                             : reinterpret_cast<float*>(smem + S.vcur);
+
+    synth_gather_pairs<K>(ctx, s_xbuf);
+    if (csz > 1) {
+      // ---- sum the partial G of the ranks: pair P = warp * PP + pp goes to rank P % S, slot [src][P / S]
+      constexpr int PW = G::V * G::L;                      // complex words per pair
+      const int own = (K::NW * K::PP) / csz;               // pairs this rank owns
+      cf* rbuf = reinterpret_cast<cf*>(smem + S.rbuf);
+      ctx.cl_sync(0);                                       // every rank is past its last transform: exchange buffers idle
+      ctx.par([&](int tid, TS& ts) {
+        const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+        const bool has = K::NG == 1 ? grp == 0 : grp < K::PP;
+        if (!has) return;
+        BTK_UNROLL
+        for (int q = 0; q < (K::NG == 1 ? K::PP : 1); q++) {
+          const int pp = K::NG == 1 ? q : grp;
+          const int P = warp * K::PP + pp, dst_rank = P % csz;
+          if (dst_rank == rank) continue;
+          cf* dst = ctx.cl_map(rbuf + ((long long)rank * own + P / csz) * PW, dst_rank);
+          BTK_UNROLL
+          for (int r = 0; r < G::V; r++) dst[r * G::L + gl] = ts.g[q * G::V + r];
+        }
+      });
+      ctx.cl_sync(1);                                       // partials have landed
+      ctx.par([&](int tid, TS& ts) {
+        const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+        const bool has = K::NG == 1 ? grp == 0 : grp < K::PP;
+        if (!has) return;
+        BTK_UNROLL
+        for (int q = 0; q < (K::NG == 1 ? K::PP : 1); q++) {
+          const int pp = K::NG == 1 ? q : grp;
+          const int P = warp * K::PP + pp;
+          if (P % csz != rank) continue;
+          for (int src = 0; src < csz; src++) {
+            if (src == rank) continue;
+            const cf* sp = rbuf + ((long long)src * own + P / csz) * PW;
+            BTK_UNROLL
+            for (int r = 0; r < G::V; r++) ts.g[q * G::V + r] = cadd(ts.g[q * G::V + r], sp[r * G::L + gl]);
+          }
+        }
+      });
+      ctx.sync();                                           // the receive buffer is the exchange buffer of the transforms below
+    } else if (S.valias) {
+      ctx.sync();                                           // every warp is past its last read of the aliased window
+    }
+    synth_transform_store<K>(ctx, s_xbuf, s_twa, s_twb, s_vcur, tau_base, csz, rank);
+    if (csz > 1) {
+      // ---- only the pairs this rank owns (complete sums) were transformed; their v frames go to every other rank (the
+      // local copy is already in place)
+      ctx.sync();
+      ctx.par([&](int tid, TS&) {
+        for (int P = rank; P < K::NW * K::PP; P += csz) {
+          const float4* src = reinterpret_cast<const float4*>(s_vcur + (long long)(2 * P) * M_);
+          for (int o = 1; o < csz; o++) {
+            const int dr = (rank + o) % csz;
+            float4* dst = reinterpret_cast<float4*>(ctx.cl_map(s_vcur + (long long)(2 * P) * M_, dr));
+            for (int i = tid; i < 2 * M_ / 4; i += K::NT) dst[i] = src[i];
+          }
+        }
+      });
+      ctx.cl_sync(2);                                       // all v frames of the iteration are in every rank
+    } else {
+      ctx.sync();
+    }
+    {
+      const int dn = K::D / csz;
+      synth_emit<K>(ctx, L, p.taps_g, s_vhist, s_vcur, out, m, p.pd_s, p.gain, tau_base, wk.j0, wk.nj, rank * dn, dn);
+    }
+    ctx.sync();
+    synth_roll_history<K>(ctx, L, s_vhist, s_vcur);
+    ctx.sync();
+    if (S.valias) ctx.release(s_last);
+  }
+}
+
+}  // namespace btk

@@ -310,6 +310,54 @@ template <int M_, int S> struct GroupFFT {
   }
   static BTK_HD void step1(cf* v, int gl, cf* xb, const cf* twa) { step1_multi<1>(v, gl, xb, twa); }
 
+  // The same pass A split in two for transforms that take turns on ONE exchange buffer (the warp-specialised chain,
+  // chain_ws.cuh): step1_twiddle leaves the twiddled pass-A outputs of PP transforms in registers, step1_scatter writes
+  // one of them to the buffer, step3_gather reads one back and step3_dft runs the final radix-Rc transforms.
+  // Two-pass plans with the symmetric layout only (Rb == 1, Ra <= 16).
+  template <int PP>
+  static BTK_HD void step1_twiddle(cf* v, int gl, const cf* twa) {
+    static_assert(G::Rb == 1 && G::Ra <= 16, "two-pass plans with a full product tree");
+    BTK_UNROLL
+    for (int rep = 0; rep < G::RepA; rep++) {
+      BTK_UNROLL
+      for (int pp = 0; pp < PP; pp++) Dft<G::Ra, S>::run(v + pp * G::V + rep * G::Ra);
+      const int j = gl + G::L * rep;
+      cf w[G::Ra + 1];
+      w[1] = twa[j * FT::TA];
+      BTK_UNROLL
+      for (int ka = 2; ka < G::Ra; ka++) {
+        const int hi = ka >= 8 ? 8 : (ka >= 4 ? 4 : 2);
+        w[ka] = (ka == hi) ? cmul(w[ka / 2], w[ka / 2]) : cmul(w[hi], w[ka - hi]);
+      }
+      BTK_UNROLL
+      for (int pp = 0; pp < PP; pp++) {
+        cf* p = v + pp * G::V + rep * G::Ra;
+        BTK_UNROLL
+        for (int ka = 1; ka < G::Ra; ka++) p[ka] = multw<S>(p[ka], w[ka]);
+      }
+    }
+  }
+  static BTK_HD void step1_scatter(const cf* v, int gl, cf* xb) {
+    BTK_UNROLL
+    for (int rep = 0; rep < G::RepA; rep++) {
+      const int j = gl + G::L * rep;
+      BTK_UNROLL
+      for (int ka = 0; ka < G::Ra; ka++) xb[ka * G::S2 + j] = v[rep * G::Ra + ka];
+    }
+  }
+  static BTK_HD void step3_gather(cf* v, int gl, const cf* xb) {
+    BTK_UNROLL
+    for (int rep = 0; rep < G::RepC; rep++) {
+      const int iC = gl + G::L * rep;
+      BTK_UNROLL
+      for (int nc = 0; nc < G::Rc; nc++) v[rep * G::Rc + nc] = xb[iC * G::S2 + nc];
+    }
+  }
+  static BTK_HD void step3_dft(cf* v) {
+    BTK_UNROLL
+    for (int rep = 0; rep < G::RepC; rep++) Dft<G::Rc, S>::run(v + rep * G::Rc);
+  }
+
   // step 2 (only when Rb > 1): gather for pass B, radix-Rb, twiddle, scatter into exchange 2.
   // Reads complete before the caller's barrier; writes must come after it (same buffer is reused),
   // hence the split into step2_load / step2_store.

@@ -16,6 +16,14 @@ namespace btk {
 BTK_DECL_M(64) BTK_DECL_M(128) BTK_DECL_M(256) BTK_DECL_M(512) BTK_DECL_M(1024)
 #undef BTK_DECL_M
 
+// warp-specialised fused chain (kern_ws.cuh), one translation unit per transform size
+#define BTK_DECL_WS(MM)                                                                               \
+  cudaError_t launch_chain_ws_m##MM(int R, const ChainParams& p, int n_work, cudaStream_t st);        \
+  int chain_ws_frames_per_iter_m##MM(int R, int m);                                                   \
+  bool chain_ws_cluster_ok_m##MM(int R, int m, int S);
+BTK_DECL_WS(64) BTK_DECL_WS(128) BTK_DECL_WS(256) BTK_DECL_WS(512) BTK_DECL_WS(1024)
+#undef BTK_DECL_WS
+
 bool fb_supported(int M, int R) {
   if (R != 1 && R != 2 && R != 4 && R != 8) return false;
   switch (M) {
@@ -53,6 +61,21 @@ int fb_smem_bytes(int M, int R, int m) {
   if (!fb_supported(M, R)) return -1;
   BTK_DISPATCH(fb_smem_bytes, R, m)
   return -1;
+}
+cudaError_t launch_chain_ws(int M, int R, const ChainParams& p, int n_work, cudaStream_t st) {
+  if (!fb_supported(M, R)) return cudaErrorInvalidValue;
+  BTK_DISPATCH(launch_chain_ws, R, p, n_work, st)
+  return cudaErrorInvalidValue;
+}
+int chain_ws_frames_per_iter(int M, int R, int m) {
+  if (!fb_supported(M, R)) return -1;
+  BTK_DISPATCH(chain_ws_frames_per_iter, R, m)
+  return -1;
+}
+bool chain_ws_cluster_ok(int M, int R, int m, int S) {
+  if (!fb_supported(M, R)) return false;
+  BTK_DISPATCH(chain_ws_cluster_ok, R, m, S)
+  return false;
 }
 int fb_frames_per_iter(int M, int R) { return (M >= 1024 || (M == 512 && R == 1)) ? 8 : 16; }  // ChainCfg::W = 2 * NW (staged kernels)
 int chain_frames_per_iter(int M, int R, int m) {                   // the fused chain may window two pairs per warp

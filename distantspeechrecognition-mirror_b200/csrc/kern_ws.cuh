@@ -1,0 +1,285 @@
+// kern_ws.cuh -- __global__ wrapper, device context and launch dispatch of the warp-specialised fused chain
+// (chain_ws.cuh).  Included by kern_ws_m<M>.cu with one transform size per translation unit.
+//
+// Roles inside a CTA of NT + 128 threads:
+//   threads [0, NT)        compute warps   (setmaxnreg.inc: the transform register program needs 230-240 registers)
+//   threads [NT, NT + 128) producer warps  (setmaxnreg.dec: 16-byte loads, register transpose, shared stores)
+// Synchronisation: mbarriers in shared memory (full / empty per stage, one for the tables), a named barrier for the
+// compute warps, cluster-scope mbarriers for the channel-split reduction.  Bulk asynchronous copies (cp.async.bulk,
+// SASS UBLKCP) bring the tap / twiddle tables at CTA start and the weight rows of every stage.
+#pragma once
+
+#include <cooperative_groups.h>
+
+#include "chain_ws.cuh"
+#include "launch.h"
+
+namespace btk {
+
+namespace cg = cooperative_groups;
+
+#define BTK_MAX_SMEM_WS (227 * 1024)
+
+__device__ __forceinline__ uint32_t ws_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ws_smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ws_smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(ws_smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ws_smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WS_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WS_DONE;\n"
+      "bra WS_WAIT;\n"
+      "WS_DONE:\n"
+      "}\n" ::"r"(ws_smem_u32(b)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WS_CWAIT:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WS_CDONE;\n"
+      "bra WS_CWAIT;\n"
+      "WS_CDONE:\n"
+      "}\n" ::"r"(ws_smem_u32(b)), "r"(parity)
+      : "memory");
+}
+// arrive on the same barrier of CTA `rank` of the cluster (release at cluster scope: the DSMEM stores before it are
+// visible to whoever acquires the completed phase)
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* b, int rank) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(ws_smem_u32(b)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+// contiguous global -> shared copy by the bulk-copy engine; completes `bytes` on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ws_smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(ws_smem_u32(bar))
+               : "memory");
+}
+
+template <int M, int PP, int NT> struct DevCtxWS {
+  ChainThreadState<M, PP> ts;
+  uint64_t* bars;
+  int csz, crank;
+  unsigned cl_phase;
+  template <class F> __device__ __forceinline__ void par(F f) { f((int)threadIdx.x, ts); }
+  __device__ __forceinline__ void sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
+  __device__ __forceinline__ void syncwarp() { __syncwarp(); }
+  template <class F> __device__ __forceinline__ void acquire(int stage, int parity, F) { mbar_wait(bars + WS_BAR_FULL + stage, parity); }
+  __device__ __forceinline__ void release(int stage) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bars + WS_BAR_EMPTY + stage);
+  }
+  __device__ __forceinline__ void wait_tables() { mbar_wait(bars + WS_BAR_TABLES, 0); }
+  __device__ __forceinline__ int cl_rank() const { return crank; }
+  // barrier k of the compute warps of the whole cluster: every warp arrives on barrier k of every rank, waits on its own.
+  // Each barrier is used once per iteration, so its phase parity is the use count's low bit.
+  __device__ __forceinline__ void cl_sync(int k) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+      asm volatile("fence.acq_rel.cluster;" ::: "memory");
+      for (int r = 0; r < csz; r++) mbar_arrive_remote(bars + WS_BAR_CL0 + k, r);
+    }
+    mbar_wait_cluster(bars + WS_BAR_CL0 + k, (cl_phase >> k) & 1u);
+    cl_phase ^= 1u << k;
+  }
+  template <class T> __device__ __forceinline__ T* cl_map(T* p, int rank) { return cg::this_cluster().map_shared_rank(p, rank); }
+};
+
+// Registers per thread of the two roles.  The CTA is launched with LR registers per thread (what __launch_bounds__ of
+// NT + 128 threads, one CTA per SM, allows); setmaxnreg.inc of the compute warpgroups can only take what setmaxnreg.dec of
+// the producer warpgroup has returned to the CTA's pool, so 128 (LR - RP) >= NT (RC - LR) must hold or the compute warps
+// spin in the allocation for ever.  RC covers the largest register program of each size (cuobjdump: 187 registers for
+// M <= 256 with two frame pairs per warp, 209 for M = 512); the producers keep the rest for loads in flight.
+template <int M, int NT> struct WsRegs {
+  static constexpr bool split = NT + 128 > 256;
+  static constexpr int LR = 65536 / (NT + 128) / 8 * 8;
+  static constexpr int RC = M >= 512 ? 216 : 192;
+  static constexpr int RP = LR - ((NT * (RC - LR) + 127) / 128 + 7) / 8 * 8;
+  static_assert(!split || (RC > LR && RP >= 24 && 128 * (LR - RP) >= NT * (RC - LR)), "register pool balance");
+};
+// loads in flight per producer thread follow its register budget (a task is LV 16-byte loads)
+template <int M, int NT, int LV> struct WsProd {
+  static constexpr int RP = WsRegs<M, NT>::split ? WsRegs<M, NT>::RP : 255;
+  static constexpr int LOADS = RP >= 112 ? 12 : (RP >= 64 ? 8 : 4);
+  static constexpr int TB = LOADS / LV;
+};
+
+template <int M, int R, int MT, int PP>
+__global__ void __launch_bounds__(WsCfg<M, R, MT, PP>::NT + WsCfg<M, R, MT, PP>::NPT, 1) btk_chain_ws_kernel(const ChainParams p) {
+  typedef WsCfg<M, R, MT, PP> K;
+  typedef WsRegs<M, K::NT> RG;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int m = MT > 0 ? MT : p.m;
+  const WsSmem S = ws_smem_layout<M, R, PP>(m);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S.bars);
+  const int csz = p.cluster > 1 ? p.cluster : 1;
+  const int crank = csz > 1 ? (int)cg::this_cluster().block_rank() : 0;
+  const WorkItem wk = p.work[blockIdx.x / csz];
+  const RecDesc rec = p.recs[wk.rec];
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < K::NS; s++) {
+      mbar_init(bars + WS_BAR_FULL + s, K::NPT);
+      mbar_init(bars + WS_BAR_EMPTY + s, K::NW);
+    }
+    mbar_init(bars + WS_BAR_TABLES, 1);
+    for (int k = 0; k < 3; k++) mbar_init(bars + WS_BAR_CL0 + k, csz * K::NW);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (csz > 1) cg::this_cluster().sync();      // nobody arrives on a remote barrier before it is initialised
+
+  if (threadIdx.x >= K::NT) {
+    // ------------------------------------------------------------------ producer warpgroup
+    if (RG::split) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RG::RP));
+    const int ptid = (int)threadIdx.x - K::NT;
+    const ChainSmem& L = S.L;
+    if (ptid == 0) {
+      typedef FFTTables<M> FT;
+      const uint32_t b_taps = K::D * L.TS * 4, b_twa = FT::TWA_WORDS * 8, b_twb = FT::TWB_WORDS * 8;
+      mbar_arrive_expect_tx(bars + WS_BAR_TABLES, b_taps + b_twa + b_twb);
+      bulk_g2s(smem + L.taps, p.taps_h, b_taps, bars + WS_BAR_TABLES);
+      bulk_g2s(smem + L.twa, p.twa, b_twa, bars + WS_BAR_TABLES);
+      if (b_twb) bulk_g2s(smem + L.twb, p.twb, b_twb, bars + WS_BAR_TABLES);
+    }
+    const int N = M * m;
+    WsWalk walk;
+    walk.a_start = wk.j0 + p.pd_s - L.H;
+    walk.n_it = (wk.nj + L.H + K::W - 1) / K::W;
+    walk.ncg = (p.Cpad / K::CG) / csz;
+    walk.cg_base = crank * walk.ncg;
+    const float* pcm = p.pcm + rec.pcm_off;
+    const cf* wts = p.wts + (long long)wk.rec * p.wts_stride;
+    const bool vec4 = (p.C % 4 == 0) && (rec.pcm_off % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.pcm) & 15) == 0);
+    int g = 0;
+    for (int it = 0; it < walk.n_it; it++) {
+      const long long t_lo = ws_window_start<K>(walk, it, p.laN, N);
+      for (int cgi = 0; cgi < walk.ncg; cgi++, g++) {
+        const int st = g % K::NS;
+        unsigned char* stage = smem + S.stage0 + st * S.stage_bytes;
+        const int cg0 = (walk.cg_base + cgi) * K::CG;
+        mbar_wait(bars + WS_BAR_EMPTY + st, ((g / K::NS) & 1) ^ 1);
+        if (ptid == 0) {
+          mbar_expect_tx(bars + WS_BAR_FULL + st, K::CG * M * 8);
+          bulk_g2s(stage + S.wts_off, wts + (long long)cg0 * M, K::CG * M * 8, bars + WS_BAR_FULL + st);
+        }
+        ws_fill_thread<K, WsProd<M, K::NT, K::LV>::TB>(ptid, L, reinterpret_cast<float*>(stage), pcm, p.C, rec.T, t_lo, cg0, vec4);
+        mbar_arrive(bars + WS_BAR_FULL + st);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ compute warps
+    if (RG::split) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(RG::RC));
+    DevCtxWS<M, PP, K::NT> ctx;
+    ctx.bars = bars; ctx.csz = csz; ctx.crank = crank; ctx.cl_phase = 0;
+    chain_ws_compute<M, R, MT, PP>(ctx, p, smem, wk, rec);
+  }
+  // no CTA of a cluster leaves while a peer may still write into its shared memory
+  if (csz > 1) cg::this_cluster().sync();
+}
+
+// two frame pairs per warp for M <= 256 where the layout fits, else one; 0 = the shape does not fit at all
+template <int M, int R> static int chain_ws_pp(int m) {
+  if (M <= 256 && ws_smem_layout<M, R, 2>(m).total <= BTK_MAX_SMEM_WS) return 2;
+  if (ws_smem_layout<M, R, 1>(m).total <= BTK_MAX_SMEM_WS) return 1;
+  return 0;
+}
+
+template <int M, int R, int MT, int PP>
+static cudaError_t launch_ws_one(const ChainParams& p, int n_work, cudaStream_t st) {
+  typedef WsCfg<M, R, MT, PP> K;
+  auto kern = btk_chain_ws_kernel<M, R, MT, PP>;
+  const int smem = ws_smem_layout<M, R, PP>(p.m).total;
+  const int csz = p.cluster > 1 ? p.cluster : 1;
+  if (csz > 1 && !ws_cluster_ok<K>(csz)) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(n_work * csz), 1, 1);
+  cfg.blockDim = dim3(K::NT + K::NPT, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csz; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
+template <int M, int R, int MT> struct WsFastOk { static constexpr bool value = MT * R <= 16; };
+#define BTK_WS_MT(MTV) (WsFastOk<M, R, MTV>::value ? MTV : 0)
+
+template <int M, int R>
+static cudaError_t launch_chain_ws_r(const ChainParams& p, int n_work, cudaStream_t st) {
+  const int pp = chain_ws_pp<M, R>(p.m);
+  if (pp == 0) return cudaErrorInvalidValue;
+  if (M <= 256 && pp == 2) {
+    constexpr int PP = M <= 256 ? 2 : 1;
+    if (p.m == 2 && WsFastOk<M, R, 2>::value) return launch_ws_one<M, R, BTK_WS_MT(2), PP>(p, n_work, st);
+    if (p.m == 4 && WsFastOk<M, R, 4>::value) return launch_ws_one<M, R, BTK_WS_MT(4), PP>(p, n_work, st);
+    return launch_ws_one<M, R, 0, PP>(p, n_work, st);
+  }
+  if (p.m == 2 && WsFastOk<M, R, 2>::value) return launch_ws_one<M, R, BTK_WS_MT(2), 1>(p, n_work, st);
+  if (p.m == 4 && WsFastOk<M, R, 4>::value) return launch_ws_one<M, R, BTK_WS_MT(4), 1>(p, n_work, st);
+  return launch_ws_one<M, R, 0, 1>(p, n_work, st);
+}
+
+template <int M, int R> static int chain_ws_w(int m) {
+  const int pp = chain_ws_pp<M, R>(m);
+  if (pp == 0) return -1;
+  return pp == 2 ? WsCfg<M, R, 0, 2>::W : WsCfg<M, R, 0, 1>::W;
+}
+template <int M, int R> static bool chain_ws_cluster_ok(int m, int S) {
+  const int pp = chain_ws_pp<M, R>(m);
+  if (pp == 0) return false;
+  return pp == 2 ? ws_cluster_ok<WsCfg<M, R, 0, 2> >(S) : ws_cluster_ok<WsCfg<M, R, 0, 1> >(S);
+}
+
+}  // namespace btk
+
+#define BTK_DEFINE_WS_LAUNCHERS(MM)                                                                                \
+  namespace btk {                                                                                                  \
+  cudaError_t launch_chain_ws_m##MM(int R, const ChainParams& p, int n_work, cudaStream_t st) {                    \
+    switch (R) {                                                                                                   \
+      case 1: return launch_chain_ws_r<MM, 1>(p, n_work, st);                                                      \
+      case 2: return launch_chain_ws_r<MM, 2>(p, n_work, st);                                                      \
+      case 4: return launch_chain_ws_r<MM, 4>(p, n_work, st);                                                      \
+      case 8: return launch_chain_ws_r<MM, 8>(p, n_work, st);                                                      \
+    }                                                                                                              \
+    return cudaErrorInvalidValue;                                                                                  \
+  }                                                                                                                \
+  int chain_ws_frames_per_iter_m##MM(int R, int m) {                                                               \
+    switch (R) {                                                                                                   \
+      case 1: return chain_ws_w<MM, 1>(m);                                                                         \
+      case 2: return chain_ws_w<MM, 2>(m);                                                                         \
+      case 4: return chain_ws_w<MM, 4>(m);                                                                         \
+      case 8: return chain_ws_w<MM, 8>(m);                                                                         \
+    }                                                                                                              \
+    return -1;                                                                                                     \
+  }                                                                                                                \
+  bool chain_ws_cluster_ok_m##MM(int R, int m, int S) {                                                            \
+    switch (R) {                                                                                                   \
+      case 1: return chain_ws_cluster_ok<MM, 1>(m, S);                                                             \
+      case 2: return chain_ws_cluster_ok<MM, 2>(m, S);                                                             \
+      case 4: return chain_ws_cluster_ok<MM, 4>(m, S);                                                             \
+      case 8: return chain_ws_cluster_ok<MM, 8>(m, S);                                                             \
+    }                                                                                                              \
+    return false;                                                                                                  \
+  }                                                                                                                \
+  }

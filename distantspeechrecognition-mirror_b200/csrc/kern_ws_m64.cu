@@ -1,0 +1,3 @@
+// kern_ws_m64.cu -- warp-specialised fused chain for M = 64 (all decimation factors R = 1, 2, 4, 8).
+#include "kern_ws.cuh"
+BTK_DEFINE_WS_LAUNCHERS(64)

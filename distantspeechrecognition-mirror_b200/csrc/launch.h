@@ -11,6 +11,12 @@ namespace btk {
 cudaError_t launch_chain(int M, int R, const ChainParams& p, int n_work, cudaStream_t st);
 cudaError_t launch_analysis(int M, int R, const AnalysisParams& p, int n_work, cudaStream_t st);
 cudaError_t launch_synthesis(int M, int R, const SynthesisParams& p, int n_work, cudaStream_t st);
+// The warp-specialised producer / consumer form of the fused chain (chain_ws.cuh).  cudaErrorInvalidValue when the shape
+// has no such kernel (its stages do not fit shared memory): the caller then uses launch_chain.  p.cluster CTAs share a
+// work item (channel split); n_work counts work items, not CTAs.
+cudaError_t launch_chain_ws(int M, int R, const ChainParams& p, int n_work, cudaStream_t st);
+int chain_ws_frames_per_iter(int M, int R, int m);       // <0: no warp-specialised kernel for this shape
+bool chain_ws_cluster_ok(int M, int R, int m, int S);    // may S CTAs share a work item?
 bool fb_supported(int M, int R);
 // dynamic shared memory the filter-bank kernels need for (M, R, m); <0 when unsupported
 int fb_smem_bytes(int M, int R, int m);

@@ -222,6 +222,16 @@ int btkb200_beamform_dev(btkb200_plan* plan, const float* d_snap, long F, float*
 int btkb200_beamform_zelinski_dev(btkb200_plan* plan, const float* d_snap, long F, double alpha, int type, int min_frames,
                                   float* d_Y, float* d_W, void* stream);
 int btkb200_synthesis_dev(btkb200_plan* plan, const float* d_Y, long F, float* d_out, void* stream);
+/* Launch-geometry knobs of the fused chain (measurement aid: A/B runs and tests; results do not depend on them).
+ *   BTKB200_TUNE_CHAIN_WS  1 / 0: use / do not use the warp-specialised producer-consumer kernel (chain_ws.cuh); -1 = automatic
+ *   BTKB200_TUNE_CLUSTER   n > 0: n CTAs of a thread-block cluster share a work item (channel split); 0 = automatic
+ * An impossible value (shape without such a kernel, n not dividing the channel groups) returns BTKB200_EUNSUPPORTED and
+ * leaves the knob unchanged.  No reference counterpart: the reference has no launch geometry. */
+#define BTKB200_TUNE_CHAIN_WS 1
+#define BTKB200_TUNE_CLUSTER 2
+int btkb200_plan_tune(btkb200_plan* plan, int knob, int value);
+/* what the last fused-chain launch of this plan used: value of the knob after the automatic choice (-1 before any launch) */
+int btkb200_plan_tuning(const btkb200_plan* plan, int knob);
 /* Kernels enqueued by this plan so far (for launch accounting in bench.py). */
 long btkb200_launch_count(const btkb200_plan* plan);
 /* Block until all work enqueued by this plan has finished. */

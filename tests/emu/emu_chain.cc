@@ -8,6 +8,7 @@
 
 #include "host_tables.h"
 #include "staged_tiles.cuh"
+#include "chain_ws.cuh"
 
 using namespace btk;
 
@@ -154,5 +155,89 @@ extern "C" int emu_synthesis(int M, int m, int r, int dct, int F, const float* Y
     return run_synthesis<MM, RR, 0>(m, dct, F, Y, out, g, gain, chunk); }
   BTK_EMU_CASES(CASE)
 #undef CASE
+  return -1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-specialised chain (csrc/chain_ws.cuh): the compute side runs as above; acquire() runs the producer's fill routine
+// for that stage inline (every producer thread in turn), so the staged windows, the stage rotation, the aliasing of the
+// v frames with the last stage and the shared exchange buffers are all exercised.  Cluster mode needs concurrently
+// running CTAs and is covered by the GPU tests only.
+template <int M, int PP> struct HostCtxWS {
+  std::vector<ChainThreadState<M, PP> > ts;
+  int nt;
+  explicit HostCtxWS(int n) : ts(n), nt(n) {}
+  template <class F> void par(F f) { for (int t = 0; t < nt; t++) f(t, ts[t]); }
+  void sync() {}
+  void syncwarp() {}
+  template <class F> void acquire(int, int, F fill) { fill(); }
+  void release(int) {}
+  void wait_tables() {}
+  int cl_rank() const { return 0; }
+  void cl_sync(int) {}
+  template <class T> T* cl_map(T* p, int) { return p; }
+};
+
+template <int M, int R, int MT, int PP>
+static int run_chain_ws(int m, int dct, int C, int n_rec, const long long* Ts, const float* pcm, const long long* pcm_off,
+                        float* out, const long long* out_off, const double* h, const double* g, const double* w_re_im,
+                        int gain, int chunk) {
+  typedef WsCfg<M, R, MT, PP> K;
+  typedef FFTTables<M> FT;
+  int r = 0; for (int x = R; x > 1; x >>= 1) r++;
+  BankGeom geo(M, m, r, dct);
+  const int Cpad = (C + K::CG - 1) / K::CG * K::CG;
+  std::vector<cf> twa, twb, gam;
+  std::vector<float> gp, hf;
+  build_fft_tables(M, twa, twb);
+  build_synthesis_taps(g, M, m, gp);
+  build_analysis_taps(h, M, m, R, hf);
+  std::vector<zd> w((size_t)geo.B * C);
+  for (size_t i = 0; i < w.size(); i++) w[i] = zd(w_re_im[2 * i], w_re_im[2 * i + 1]);
+  build_chain_weight_table(w.data(), M, C, Cpad, gam);
+  std::vector<RecDesc> recs(n_rec);
+  for (int i = 0; i < n_rec; i++) {
+    recs[i].pcm_off = pcm_off[i]; recs[i].out_off = out_off[i]; recs[i].T = (int)Ts[i]; recs[i].nblk = geo.chain_frames(Ts[i]);
+  }
+  std::vector<WorkItem> work;
+  build_work(recs, chunk, work);
+  ChainParams p;
+  p.pcm = pcm; p.out = out; p.recs = recs.data(); p.work = work.data();
+  p.taps_h = hf.data(); p.taps_g = gp.data(); p.wts = gam.data(); p.wts_stride = 0; p.one_cta = 0; p.no_prefetch = 0; p.twa = twa.data(); p.twb = twb.data();
+  p.C = C; p.Cpad = Cpad; p.m = m; p.pd_s = geo.pd_s; p.laN = geo.laN; p.gain = gain; p.cluster = 1;
+  const WsSmem S = ws_smem_layout<M, R, PP>(m);
+  if (S.total > 227 * 1024) return -2;
+  std::vector<unsigned char> smem(S.total + 64, 0xA5);
+  for (size_t wi = 0; wi < work.size(); wi++) {
+    HostCtxWS<M, PP> ctx(K::NT);
+    memset(smem.data(), 0xA5, smem.size());   // poison: every read must have been written
+    // what the bulk copies of the producer bring at CTA start
+    memcpy(smem.data() + S.L.taps, hf.data(), (size_t)K::D * S.L.TS * 4);
+    memcpy(smem.data() + S.L.twa, twa.data(), (size_t)FT::TWA_WORDS * 8);
+    if (FT::TWB_WORDS) memcpy(smem.data() + S.L.twb, twb.data(), (size_t)FT::TWB_WORDS * 8);
+    chain_ws_compute<M, R, MT, PP>(ctx, p, smem.data(), work[wi], recs[work[wi].rec]);
+  }
+  return (int)work.size();
+}
+
+extern "C" int emu_chain_ws(int M, int m, int r, int dct, int C, int n_rec, const long long* Ts, const float* pcm,
+                            const long long* pcm_off, float* out, const long long* out_off, const double* h,
+                            const double* g, const double* w_re_im, int gain, int chunk, int fast) {
+#define ARGS m, dct, C, n_rec, Ts, pcm, pcm_off, out, out_off, h, g, w_re_im, gain, chunk
+#define CASE(MM, RR) \
+  if (M == MM && (1 << r) == RR) { \
+    if ((fast & 2) && MM <= 256) { \
+      constexpr int PP = MM <= 256 ? 2 : 1; \
+      if ((fast & 1) && m == 2) return run_chain_ws<MM, RR, 2, PP>(ARGS); \
+      if ((fast & 1) && m == 4) return run_chain_ws<MM, RR, 4, PP>(ARGS); \
+      return run_chain_ws<MM, RR, 0, PP>(ARGS); \
+    } \
+    if ((fast & 1) && m == 2) return run_chain_ws<MM, RR, 2, 1>(ARGS); \
+    if ((fast & 1) && m == 4) return run_chain_ws<MM, RR, 4, 1>(ARGS); \
+    return run_chain_ws<MM, RR, 0, 1>(ARGS); \
+  }
+  BTK_EMU_CASES(CASE)
+#undef CASE
+#undef ARGS
   return -1;
 }

@@ -61,6 +61,27 @@ def test_emulated_chain_matches_oracle(case, fast, emu, prototypes):
     assert bo.snr_db(out, ref) > 100.0   # north_star gate is 70 dB
 
 
+@pytest.mark.parametrize("fast", [3, 1, 0])
+@pytest.mark.parametrize("case", CASES)
+def test_emulated_ws_chain_matches_oracle(case, fast, emu, prototypes):
+    """The warp-specialised tile program (csrc/chain_ws.cuh): producer fill + stage rotation + compute side."""
+    M, m, r, dct, C, T, chunk = case
+    h, g = proto(prototypes, M, m, r)
+    geo = bo.BankGeometry(M, m, r, dct)
+    pcm = wl.noise_recording(T, C, seed=9)
+    mp = wl.circular_array(C) if C > 1 else np.zeros((1, 3))
+    W = bo.ds_weights(wl.farfield_delays(mp, 1.0, 1.4), 16000.0, M)
+    _, _, ref = bo.chain(pcm, h, g, geo, W)
+    out = np.zeros(geo.nblk(T) * geo.D, np.float32)
+    Ts, z = np.array([T], np.int64), np.array([0], np.int64)
+    Wc = np.ascontiguousarray(W, dtype=np.complex128)
+    n = emu.emu_chain_ws(M, m, r, dct, C, 1, vp(Ts), vp(pcm), vp(z), vp(out), vp(z), vp(h), vp(g), vp(Wc), 1, chunk, fast)
+    if n == -2:
+        pytest.skip("no warp-specialised layout for this shape (stages exceed 227 KB): the library uses chain_tile")
+    assert n > 0
+    assert bo.snr_db(out, ref) > 100.0   # north_star gate is 70 dB
+
+
 @pytest.mark.parametrize("fast", [1, 0])
 @pytest.mark.parametrize("case", CASES[:6])
 def test_emulated_staged_tiles_match_oracle(case, fast, emu, prototypes):
