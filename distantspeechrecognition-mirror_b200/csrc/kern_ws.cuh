@@ -45,6 +45,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
       "}\n" ::"r"(ws_smem_u32(b)), "r"(parity)
       : "memory");
 }
+// the producer's wait: it is a stage ahead most of the time, so it backs off between polls instead of taking issue slots
+// from the transform warps
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WS_BWAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WS_BDONE;\n"
+      "nanosleep.u32 200;\n"
+      "bra WS_BWAIT;\n"
+      "WS_BDONE:\n"
+      "}\n" ::"r"(ws_smem_u32(b)), "r"(parity)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* b, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -90,10 +105,10 @@ template <int M, int PP, int NT> struct DevCtxWS {
   // Each barrier is used once per iteration, so its phase parity is the use count's low bit.
   __device__ __forceinline__ void cl_sync(int k) {
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) {
-      asm volatile("fence.acq_rel.cluster;" ::: "memory");
+    // lane 0's release.cluster arrive orders the whole warp's earlier shared / DSMEM stores (they happen before the
+    // __syncwarp it has passed); a separate fence.acq_rel.cluster here compiled to MEMBAR.ALL.GPU and cost ~1.5 us per use
+    if ((threadIdx.x & 31) == 0)
       for (int r = 0; r < csz; r++) mbar_arrive_remote(bars + WS_BAR_CL0 + k, r);
-    }
     mbar_wait_cluster(bars + WS_BAR_CL0 + k, (cl_phase >> k) & 1u);
     cl_phase ^= 1u << k;
   }
@@ -173,7 +188,11 @@ __global__ void __launch_bounds__(WsCfg<M, R, MT, PP>::NT + WsCfg<M, R, MT, PP>:
         const int st = g % K::NS;
         unsigned char* stage = smem + S.stage0 + st * S.stage_bytes;
         const int cg0 = (walk.cg_base + cgi) * K::CG;
+#ifdef BTK_WS_NO_BACKOFF
         mbar_wait(bars + WS_BAR_EMPTY + st, ((g / K::NS) & 1) ^ 1);
+#else
+        mbar_wait_backoff(bars + WS_BAR_EMPTY + st, ((g / K::NS) & 1) ^ 1);
+#endif
         if (ptid == 0) {
           mbar_expect_tx(bars + WS_BAR_FULL + st, K::CG * M * 8);
           bulk_g2s(stage + S.wts_off, wts + (long long)cg0 * M, K::CG * M * 8, bars + WS_BAR_FULL + st);
