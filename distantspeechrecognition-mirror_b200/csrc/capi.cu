@@ -624,21 +624,23 @@ static int chain_prepare(btkb200_plan* p, const long long* pcm_off, const long l
   {
     static const int ws_env = getenv("BTK_CHAIN_WS") ? atoi(getenv("BTK_CHAIN_WS")) : -1;
     const int Wws = chain_ws_frames_per_iter(p->geo.M, p->geo.R, p->geo.m);
-    p->use_ws = (Wws > 0 && (p->tune_ws >= 0 ? p->tune_ws != 0 : ws_env != 0)) ? 1 : 0;
+    // automatic choice: from M = 256 up (M = 128 measured 4 % slower than the first sessions' kernel with two CTAs per SM)
+    p->use_ws = (Wws > 0 && (p->tune_ws >= 0 ? p->tune_ws != 0 : (ws_env >= 0 ? ws_env != 0 : p->geo.M >= 256))) ? 1 : 0;
     p->cluster = 1;
     if (p->use_ws) {
       // Channel split over a thread-block cluster: S CTAs share a work item, each stages only its own channel groups and
       // the partial beamformer outputs are summed through distributed shared memory.  Without it one CTA walks the rows
       // of interleaved PCM (all channels per row) Cpad/4 times out of L2, and the windows of 148 CTAs have to survive
-      // there: 111 MB at 64 channels (M = 512), 7 x the input bytes re-read from HBM at M = 1024.
-      // The smallest power of two that brings the windows in flight under a third of L2 and leaves at most four
-      // channel groups per CTA is used.
+      // there: 111 MB at 64 channels (M = 512), 189 MB for M = 256.  The split costs a rendezvous and two
+      // exchanges per iteration while the transforms per CTA shrink by S, so the smallest power of two that brings the
+      // windows in flight under 0.45 x L2 is used (measured: M = 256, 64 channels 0.90 -> 0.81 ms at S = 4 and 1.12 ms at
+      // S = 8; M = 512, 64 channels 1.88 ms at S = 1 and 2, 2.48 at 4, 3.27 at 8; 16 channels always best unsplit).
       static const int cl_env = getenv("BTK_CLUSTER") ? atoi(getenv("BTK_CLUSTER")) : 0;
       const int n_groups = p->Cpad / 4;
       const double window_all = (double)(Wws - 1 + p->geo.m * p->geo.R) * p->geo.D * p->Cpad * sizeof(float);
       int S = 1;
       while (S < 8 && n_groups % (2 * S) == 0 && chain_ws_cluster_ok(p->geo.M, p->geo.R, p->geo.m, 2 * S) &&
-             (148.0 * window_all / S > l2 / 3.0 || n_groups / S > 4))
+             148.0 * window_all / S > 0.45 * l2)
         S *= 2;
       if (cl_env > 0 && n_groups % cl_env == 0 && chain_ws_cluster_ok(p->geo.M, p->geo.R, p->geo.m, cl_env)) S = cl_env;
       if (p->tune_cluster > 0) S = p->tune_cluster;     // validated by btkb200_plan_tune

@@ -60,24 +60,11 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* b, uint32_t parity) 
       "}\n" ::"r"(ws_smem_u32(b)), "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* b, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WS_CWAIT:\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WS_CDONE;\n"
-      "bra WS_CWAIT;\n"
-      "WS_CDONE:\n"
-      "}\n" ::"r"(ws_smem_u32(b)), "r"(parity)
-      : "memory");
-}
-// arrive on the same barrier of CTA `rank` of the cluster (release at cluster scope: the DSMEM stores before it are
-// visible to whoever acquires the completed phase)
+// arrive on the same barrier of CTA `rank` of the cluster (default semantics: release at CTA scope, no GPU-wide fence)
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* b, int rank) {
   uint32_t raddr;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(ws_smem_u32(b)), "r"(rank));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
 // contiguous global -> shared copy by the bulk-copy engine; completes `bytes` on the mbarrier
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -101,18 +88,31 @@ template <int M, int PP, int NT> struct DevCtxWS {
   }
   __device__ __forceinline__ void wait_tables() { mbar_wait(bars + WS_BAR_TABLES, 0); }
   __device__ __forceinline__ int cl_rank() const { return crank; }
-  // barrier k of the compute warps of the whole cluster: every warp arrives on barrier k of every rank, waits on its own.
-  // Each barrier is used once per iteration, so its phase parity is the use count's low bit.
-  __device__ __forceinline__ void cl_sync(int k) {
+  // Rendezvous of the compute warps of the whole cluster: every warp arrives on the READY barrier of every rank and waits
+  // on its own.  Plain (CTA-scope release) remote arrives: the rendezvous only orders this CTA's earlier shared-memory
+  // READS against the peers' later writes, the data itself is synchronised by the transaction counts below.
+  __device__ __forceinline__ void cl_ready() {
     __syncwarp();
-    // lane 0's release.cluster arrive orders the whole warp's earlier shared / DSMEM stores (they happen before the
-    // __syncwarp it has passed); a separate fence.acq_rel.cluster here compiled to MEMBAR.ALL.GPU and cost ~1.5 us per use
     if ((threadIdx.x & 31) == 0)
-      for (int r = 0; r < csz; r++) mbar_arrive_remote(bars + WS_BAR_CL0 + k, r);
-    mbar_wait_cluster(bars + WS_BAR_CL0 + k, (cl_phase >> k) & 1u);
-    cl_phase ^= 1u << k;
+      for (int r = 0; r < csz; r++) mbar_arrive_remote(bars + WS_BAR_READY, r);
+    mbar_wait(bars + WS_BAR_READY, cl_phase & 1u);
+    cl_phase ^= 1u;
   }
-  template <class T> __device__ __forceinline__ T* cl_map(T* p, int rank) { return cg::this_cluster().map_shared_rank(p, rank); }
+  __device__ __forceinline__ void cl_expect(int k, unsigned bytes) {
+    if (threadIdx.x == 0) mbar_arrive_expect_tx(bars + WS_BAR_RX0 + k, bytes);
+  }
+  __device__ __forceinline__ void cl_send16(void* local_dst, int rank, float4 v, int k) {
+    uint32_t daddr, baddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(daddr) : "r"(ws_smem_u32(local_dst)), "r"(rank));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(baddr) : "r"(ws_smem_u32(bars + WS_BAR_RX0 + k)), "r"(rank));
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(daddr),
+                 "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(baddr)
+                 : "memory");
+  }
+  __device__ __forceinline__ void cl_wait(int k) {
+    mbar_wait(bars + WS_BAR_RX0 + k, (cl_phase >> (1 + k)) & 1u);
+    cl_phase ^= 2u << k;
+  }
 };
 
 // Registers per thread of the two roles.  The CTA is launched with LR registers per thread (what __launch_bounds__ of
@@ -153,7 +153,9 @@ __global__ void __launch_bounds__(WsCfg<M, R, MT, PP>::NT + WsCfg<M, R, MT, PP>:
       mbar_init(bars + WS_BAR_EMPTY + s, K::NW);
     }
     mbar_init(bars + WS_BAR_TABLES, 1);
-    for (int k = 0; k < 3; k++) mbar_init(bars + WS_BAR_CL0 + k, csz * K::NW);
+    mbar_init(bars + WS_BAR_READY, csz * K::NW);
+    mbar_init(bars + WS_BAR_RX0, 1);
+    mbar_init(bars + WS_BAR_RX1, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();

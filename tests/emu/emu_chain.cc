@@ -174,8 +174,10 @@ template <int M, int PP> struct HostCtxWS {
   void release(int) {}
   void wait_tables() {}
   int cl_rank() const { return 0; }
-  void cl_sync(int) {}
-  template <class T> T* cl_map(T* p, int) { return p; }
+  void cl_ready() {}
+  void cl_expect(int, unsigned) {}
+  void cl_send16(void*, int, float4, int) {}
+  void cl_wait(int) {}
 };
 
 template <int M, int R, int MT, int PP>
