@@ -233,11 +233,258 @@ def bind_to_gpu_numa_node(index):
 
 
 # --------------------------------------------------------------------------------------------- our arm
-def run_ours(args, wl_cfg, rank, world, local_rank):
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # 148 SMs x 128 FP32 lanes x FMA at the 1965 MHz boost clock
+
+
+def chain_flops_per_channel_sample(M, m, r, C):
+    """analysis 2mR + 2.5 R log2 M, weight apply 4R, synthesis (2mR + 2.5 R log2 M) / C."""
+    R = 1 << r
+    bank = 2.0 * m * R + 2.5 * R * np.log2(M)
+    return bank + 4.0 * R + bank / C
+
+
+# the extra configurations the default run also measures (BASELINE.json configs[2], configs[3]); batch = utterances in total,
+# split over the ranks (strong scaling) -- the primary line keeps its fixed batch per GPU (weak scaling)
+EXTRA = [
+    ("cfg3_mvdr", "cfg3", "mvdr", 64),
+    ("cfg4_ds", "cfg4", "ds", 1024),
+    ("cfg4_mvdr", "cfg4", "mvdr", 1024),
+]
+MVDR_LOAD = {16: 0.1, 64: 1.0}     # absolute diagonal loading of the diffuse-noise model (SURVEY 7: keeps the reference's
+                                   # float-SVD inverse and the exact solve within 1e-6 of each other)
+
+
+def _reference_output_worker(job):
+    """One recording through the compiled reference chain (the parity check of the timed output)."""
+    wl_cfg, mode, index, config_id = job
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull, 1)
+    os.dup2(devnull, 2)
+    import btk_oracle as bo
+
+    M, m, r, C = wl_cfg["M"], wl_cfg["m"], wl_cfg["r"], wl_cfg["C"]
+    h, g = prototypes(M, m, r)
+    geo = bo.BankGeometry(M, m, r, 0)
+    mp_, tau = geometry(wl_cfg)
+    pcm = make_recording(wl_cfg, tau, index, config_id)
+    if bo.CompiledReference.available():
+        ref = bo.CompiledReference()
+        if mode == "mvdr":
+            res = ref.chain(pcm, h, g, geo, tau, mode="mvdr", micpos=mp_, diag_load=MVDR_LOAD.get(C, 0.1), inverse="double",
+                            want_snap=False, want_Y=False)
+        else:
+            res = ref.chain(pcm, h, g, geo, tau, want_snap=False, want_Y=False)
+        return res["out"], "reference"
+    W = bo.ds_weights(tau, FS, M)
+    if mode == "mvdr":
+        W = bo.mvdr_weights(bo.diagonal_load(bo.diffuse_coherence(mp_, FS, M), MVDR_LOAD.get(C, 0.1)), W)
+    return bo.chain(pcm, h, g, geo, W)[2], "port"
+
+
+def snr_db(x, ref):
+    x = np.asarray(x, np.float64); ref = np.asarray(ref, np.float64)
+    n = min(x.size, ref.size)
+    err = float(np.sum((x[:n] - ref[:n]) ** 2)) + 1e-300
+    return 10.0 * np.log10(float(np.sum(ref[:n] ** 2)) / err)
+
+
+def measure(wl_cfg, mode, nb, args, rank, world, local_rank, dev, config_id, steps, full_host_inputs, with_s16, adaptive,
+            sampler=None):
+    """Time one configuration on this rank.  Returns a dict of this rank's raw numbers (times in seconds / ms)."""
     import torch
     import torch.distributed as dist
 
     import btk_b200
+
+    M, m, r, C = wl_cfg["M"], wl_cfg["m"], wl_cfg["r"], wl_cfg["C"]
+    T = int(round(wl_cfg["seconds"] * FS))
+    h, g = prototypes(M, m, r)
+    mp_, tau = geometry(wl_cfg)
+    plan = btk_b200.Plan(M, m, r, C, h, g, device=local_rank)
+    plan.set_ds_weights(FS, tau)
+    if mode == "mvdr":
+        # SubbandMVDR: diffuse-noise coherence + diagonal loading -> per-bin solve -> weights (beamformer.cc:2392-2581)
+        plan.set_diffuse_noise_model(mp_, FS)
+        plan.diag_load(MVDR_LOAD.get(C, 0.1))
+        if plan.solve_mvdr(FS, 1e-8) != 0:
+            raise SystemExit("bench.py: MVDR solve fell back to identity weights")
+    nblk, D = plan.nblk(T), plan.D
+    n_in, n_out = T * C, nblk * D
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # this rank's shard: a few distinct signals, reused round-robin
+    distinct = min(nb, 4)
+    first = rank * nb
+    base = [make_recording(wl_cfg, tau, first + i, config_id) for i in range(distinct)]
+    n_host = nb if full_host_inputs else distinct
+    h_in = torch.empty((n_host, n_in), dtype=torch.float32, pin_memory=True)
+    for i in range(n_host):
+        h_in[i].copy_(torch.from_numpy(base[i % distinct].reshape(-1)))
+    h_out = torch.empty((nb, n_out), dtype=torch.float32, pin_memory=True)
+    d_in = torch.empty((nb, n_in), dtype=torch.float32, device=dev)
+    for i in range(nb):
+        d_in[i].copy_(h_in[i % n_host], non_blocking=True)
+    d_out = torch.zeros((nb, n_out), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    pcm_off = np.arange(nb, dtype=np.int64) * n_in
+    out_off = np.arange(nb, dtype=np.int64) * n_out
+    Ts = np.full(nb, T, dtype=np.int64)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_dev():
+        plan.chain_batch_dev(d_in.data_ptr(), pcm_off, Ts, out_off, d_out.data_ptr(), stream)
+
+    # ---- device-resident timing.  The clock sampler (primary configuration only) runs from before the warm-up to after
+    # the timed steps; the untimed warm-up is stretched to ~0.8 s of the same launches so that the samples show the clocks
+    # this workload sustains going into the timed steps.
+    if sampler is not None:
+        sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    torch.cuda.synchronize()
+    if sampler is not None:
+        t_load = time.perf_counter()
+        while time.perf_counter() - t_load < 0.8:
+            for _ in range(50):
+                step_dev()
+            torch.cuda.synchronize()
+    barrier()
+    l0 = plan.launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_begin.record()
+    for a, b in evs:
+        a.record()
+        step_dev()
+        b.record()
+    t_end.record()
+    barrier()
+    res = {"launches": plan.launch_count() - l0, "total_ms": t_begin.elapsed_time(t_end),
+           "kern_ms": float(np.mean([a.elapsed_time(b) for a, b in evs])), "tuning": plan.tuning()}
+    if sampler is not None:
+        res["clocks"] = sampler.stop()
+
+    # ---- end to end through the host-buffer C-ABI call (H2D + kernels + D2H inside)
+    xs = [h_in[i % n_host].numpy().reshape(T, C) for i in range(nb)]
+    outs = [h_out[i].numpy() for i in range(nb)]
+    e2e_steps = max(2, min(steps, 5))
+    plan.chain_batch_into(xs, outs)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        plan.chain_batch_into(xs, outs)
+    torch.cuda.synchronize()
+    res["e2e_s"] = (time.perf_counter() - t0) / e2e_steps
+    checksum = float(h_out[0, : 4 * D].double().abs().sum())
+    if not np.isfinite(checksum) or checksum == 0.0:
+        raise SystemExit("bench.py: end-to-end output is empty or not finite")
+    res["same"] = bool(torch.equal(d_out[0].cpu(), h_out[0]))
+    res["out0"] = h_out[0].numpy().copy()          # recording `first` of this shard: parity-checked against the reference
+
+    # ---- the same call fed with 16-bit PCM (what the recordings are on disk: the reference converts 16-bit WAV to
+    # float on the host, feature/feature.cc:273, 868-896); the conversion runs on the device, H2D bytes halve
+    res["e2e16_s"] = 0.0
+    if with_s16:
+        h_in16 = torch.empty((n_host, n_in), dtype=torch.int16, pin_memory=True)
+        for i in range(n_host):
+            h_in16[i].copy_(torch.from_numpy(np.round(base[i % distinct].reshape(-1)).clip(-32768, 32767).astype(np.int16)))
+        raws = [h_in16[i % n_host].numpy().reshape(T, C) for i in range(nb)]
+        plan.chain_batch_pcm_into(raws, btk_b200._capi.PCM_S16, [T] * nb, outs)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            plan.chain_batch_pcm_into(raws, btk_b200._capi.PCM_S16, [T] * nb, outs)
+        torch.cuda.synchronize()
+        res["e2e16_s"] = (time.perf_counter() - t0) / e2e_steps
+        if not np.isfinite(float(h_out[0, : 4 * D].double().abs().sum())):
+            raise SystemExit("bench.py: 16-bit end-to-end output is not finite")
+
+    # ---- per-utterance adaptive MVDR, end to end (covariance on a 1-s lead-in -> loading -> solve -> chain)
+    res["adaptive_s"] = 0.0
+    if adaptive:
+        lead = int(FS // D)          # frames of the first second
+        kw = dict(forget=0.99, last_frame=lead, conjugate=True, load_abs=0.0, load_rel=1e-2)
+        plan.mvdr_chain_batch_into(xs, outs, **kw)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            nfb = plan.mvdr_chain_batch_into(xs, outs, **kw)
+        torch.cuda.synchronize()
+        res["adaptive_s"] = (time.perf_counter() - t0) / e2e_steps
+        if int(nfb.sum()) != 0 or not np.isfinite(float(h_out[0, : 4 * D].double().abs().sum())):
+            raise SystemExit("bench.py: adaptive MVDR produced fallback bins or non-finite output")
+
+    # ---- optional: the shipped drivers' chain with the Zelinski post-filter, end to end
+    res["pf_s"] = 0.0
+    if args.postfilter and mode == "ds":
+        plan.chain_zelinski_batch_into(xs, outs, 0.6, 2, 0)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            plan.chain_zelinski_batch_into(xs, outs, 0.6, 2, 0)
+        torch.cuda.synchronize()
+        res["pf_s"] = (time.perf_counter() - t0) / e2e_steps
+    res.update(nblk=nblk, D=D, T=T, n_in=n_in, n_out=n_out, nb=nb, first=first)
+    plan.close()
+    del d_in, d_out, h_in, h_out
+    torch.cuda.empty_cache()
+    return res
+
+
+def summarise(wl_cfg, mode, res, world, steps, peak, peak_src, traffic):
+    """This configuration's numbers, after the max over ranks: whole-job throughput, both rooflines, end to end."""
+    M, m, r, C = wl_cfg["M"], wl_cfg["m"], wl_cfg["r"], wl_cfg["C"]
+    nb, T, nblk, D = res["nb"], res["T"], res["nblk"], res["D"]
+    units = nb * C * wl_cfg["seconds"]                        # channel-audio-seconds one rank processes per step
+    alg_bytes = nb * (4.0 * C * T + 4.0 * nblk * D)           # SURVEY 8d fused-chain bytes per launch
+    flops = nb * C * T * chain_flops_per_channel_sample(M, m, r, C)
+    achieved = alg_bytes / (res["kern_ms"] * 1e-3) / 1e9
+    tf = flops / (res["kern_ms"] * 1e-3) / 1e12
+    ms_per_step = res["total_ms"] / steps
+    out = {
+        "value": world * units / (ms_per_step * 1e-3), "unit": UNIT, "ms_per_step": ms_per_step,
+        "beamformer": "SubbandMVDR (diffuse-noise model + diagonal loading, per-bin solve on the device, then fixed weights)"
+                      if mode == "mvdr" else "SubbandDS (delay-and-sum at the true DOA)",
+        "utterances": world * nb, "channels": C, "M": M, "m": m, "r": r,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                     "kernel_ms": res["kern_ms"],
+                     "kernel": ("btk_chain_ws_kernel" if res["tuning"]["chain_ws"] else "btk_chain_kernel") + f"<{M},{1 << r}>",
+                     "cluster": res["tuning"]["cluster"]},
+        "roofline_fp32": {"bound": "fp32", "achieved": tf, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tf / FP32_PEAK_TFLOPS,
+                          "flop_per_channel_sample": chain_flops_per_channel_sample(M, m, r, C),
+                          "peak_source": "148 SMs x 128 lanes x 2 flop x 1.965 GHz (SURVEY 8d)"},
+        "e2e": {"value": world * units / res["e2e_s"], "unit": UNIT, "h2d_bytes_per_step": int(nb * res["n_in"] * 4),
+                "d2h_bytes_per_step": int(nb * res["n_out"] * 4), "ms_per_step": res["e2e_s"] * 1e3,
+                "per_gpu": units / res["e2e_s"], "matches_device_resident_output": res["same"]},
+        "gpu_launches": int(res["launches"]),
+    }
+    if res["e2e16_s"] > 0:
+        out["e2e_s16_ingest"] = {"value": world * units / res["e2e16_s"], "unit": UNIT, "h2d_bytes_per_step": int(nb * res["n_in"] * 2),
+                                 "d2h_bytes_per_step": int(nb * res["n_out"] * 4), "ms_per_step": res["e2e16_s"] * 1e3,
+                                 "note": "same call with 16-bit PCM host buffers (btkb200_chain_batch_pcm), converted on the device"}
+    if res["adaptive_s"] > 0:
+        out["e2e_adaptive_mvdr"] = {
+            "value": world * units / res["adaptive_s"], "unit": UNIT, "ms_per_step": res["adaptive_s"] * 1e3,
+            "h2d_bytes_per_step": int(nb * res["n_in"] * 4), "d2h_bytes_per_step": int(nb * res["n_out"] * 4),
+            "note": "btkb200_mvdr_chain_batch: per utterance covariance (x x^H, ff 0.99) on the first second -> load 1e-2 "
+                    "trace/C -> per-bin MVDR solve -> fused chain with that utterance's weights; host buffers in and out"}
+    if res["pf_s"] > 0:
+        out["e2e_zelinski_postfilter"] = {
+            "value": world * units / res["pf_s"], "unit": UNIT, "ms_per_step": res["pf_s"] * 1e3,
+            "note": "btkb200_chain_zelinski_batch (analysis -> SubbandDS -> ZelinskiPostFilter alpha 0.6 |.| -> synthesis, "
+                    "staged kernels, pipelined over the batch); pinned host buffers in and out"}
+    return out
+
+
+def run_ours(args, wl_cfg, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device visible; the hot path has no CPU fallback")
@@ -259,195 +506,85 @@ def run_ours(args, wl_cfg, rank, world, local_rank):
             os.dup2(saved, 1)
             os.close(saved)
 
-    M, m, r, C, nb = wl_cfg["M"], wl_cfg["m"], wl_cfg["r"], wl_cfg["C"], wl_cfg["batch"]
-    T = int(round(wl_cfg["seconds"] * FS))
-    h, g = prototypes(M, m, r)
-    _, tau = geometry(wl_cfg)
-    plan = btk_b200.Plan(M, m, r, C, h, g, device=local_rank)
-    plan.set_ds_weights(FS, tau)
-    nblk, D = plan.nblk(T), plan.D
-    n_in, n_out = T * C, nblk * D
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "of measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "of fallback (B200_PROFILING.md)"
+    traffic_all = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic_all = json.load(open(tpath))
+        except Exception:
+            traffic_all = {}
 
-    # this rank's shard of the job: recordings rank*nb .. rank*nb+nb-1 (weak scaling), a few distinct signals reused
-    distinct = min(nb, 4)
-    base = [make_recording(wl_cfg, tau, rank * nb + i) for i in range(distinct)]
-    h_in = torch.empty((nb, n_in), dtype=torch.float32, pin_memory=True)
-    h_out = torch.empty((nb, n_out), dtype=torch.float32, pin_memory=True)
-    for i in range(nb):
-        h_in[i].copy_(torch.from_numpy(base[i % distinct].reshape(-1)))
-    d_in = h_in.to(dev)
-    d_out = torch.zeros((nb, n_out), dtype=torch.float32, device=dev)
-    pcm_off = np.arange(nb, dtype=np.int64) * n_in
-    out_off = np.arange(nb, dtype=np.int64) * n_out
-    Ts = np.full(nb, T, dtype=np.int64)
-    stream = torch.cuda.current_stream().cuda_stream
-
-    def step_dev():
-        plan.chain_batch_dev(d_in.data_ptr(), pcm_off, Ts, out_off, d_out.data_ptr(), stream)
-
-    def barrier():
+    def max_over_ranks(res):
+        keys = ["total_ms", "kern_ms", "e2e_s", "e2e16_s", "adaptive_s", "pf_s"]
+        tt = torch.tensor([res[k] for k in keys], dtype=torch.float64, device=dev)
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        for k, v in zip(keys, tt.tolist()):
+            res[k] = float(v)
+        return res
 
-    units_per_step = nb * C * wl_cfg["seconds"]              # channel-audio-seconds this rank processes per step
-    alg_bytes = nb * (4.0 * C * T + 4.0 * nblk * D)           # SURVEY 8d fused-chain bytes per launch
+    # ---- primary configuration (weak scaling: fixed batch per GPU)
+    config_id = 2
+    prim = measure(wl_cfg, "ds", wl_cfg["batch"], args, rank, world, local_rank, dev, config_id, args.steps,
+                   full_host_inputs=True, with_s16=True, adaptive=args.mvdr, sampler=ClockSampler(local_rank))
+    prim = max_over_ranks(prim)
 
-    # ---- device-resident timing
-    # The clock sampler (nvidia-smi every 200 ms) runs from before the warm-up to after the timed steps.  The timed
-    # region itself is a few milliseconds, so the untimed warm-up is stretched to ~0.8 s of the SAME launches: the
-    # samples then show the clocks this workload actually sustains (and any throttle reason) going into the timed steps.
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        step_dev()
-    torch.cuda.synchronize()
-    t_load = time.perf_counter()
-    while time.perf_counter() - t_load < 0.8:
-        for _ in range(50):
-            step_dev()
-        torch.cuda.synchronize()
-    barrier()
-    l0 = plan.launch_count()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_begin.record()
-    for a, b in evs:
-        a.record()
-        step_dev()
-        b.record()
-    t_end.record()
-    barrier()
-    launches = plan.launch_count() - l0
-    total_ms = t_begin.elapsed_time(t_end)
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
-    clocks = sampler.stop()
-
-    # ---- end to end through the host-buffer C-ABI call (H2D + kernels + D2H inside)
-    xs = [h_in[i].numpy().reshape(T, C) for i in range(nb)]
-    outs = [h_out[i].numpy() for i in range(nb)]
-    e2e_steps = max(2, min(args.steps, 5))
-    plan.chain_batch_into(xs, outs)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        plan.chain_batch_into(xs, outs)
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    checksum = float(h_out[0, : 4 * D].double().abs().sum())
-    if not np.isfinite(checksum) or checksum == 0.0:
-        raise SystemExit("bench.py: end-to-end output is empty or not finite")
-    same = bool(torch.allclose(d_out[0].cpu(), h_out[0], rtol=0, atol=0))
-
-    # ---- the same call fed with 16-bit PCM (what the recordings are on disk: the reference converts 16-bit WAV to
-    # float on the host, feature/feature.cc:273, 868-896); the conversion runs on the device, H2D bytes halve
-    h_in16 = torch.empty((nb, n_in), dtype=torch.int16, pin_memory=True)
-    for i in range(nb):
-        h_in16[i].copy_(torch.from_numpy(np.round(base[i % distinct].reshape(-1)).clip(-32768, 32767).astype(np.int16)))
-    raws = [h_in16[i].numpy().reshape(T, C) for i in range(nb)]
-    plan.chain_batch_pcm_into(raws, btk_b200._capi.PCM_S16, [T] * nb, outs)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        plan.chain_batch_pcm_into(raws, btk_b200._capi.PCM_S16, [T] * nb, outs)
-    torch.cuda.synchronize()
-    e2e16_s = (time.perf_counter() - t0) / e2e_steps
-    if not np.isfinite(float(h_out[0, : 4 * D].double().abs().sum())):
-        raise SystemExit("bench.py: 16-bit end-to-end output is not finite")
-
-    # ---- optional: per-utterance adaptive MVDR, end to end (covariance on a 1-s lead-in -> loading -> solve -> chain)
-    mvdr_s = 0.0
-    if args.mvdr:
-        lead = int(FS // D)          # frames of the first second
-        kw = dict(forget=0.99, last_frame=lead, conjugate=True, load_abs=0.0, load_rel=1e-2)
-        plan.mvdr_chain_batch_into(xs, outs, **kw)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            nfb = plan.mvdr_chain_batch_into(xs, outs, **kw)
-        torch.cuda.synchronize()
-        mvdr_s = (time.perf_counter() - t0) / e2e_steps
-        if int(nfb.sum()) != 0 or not np.isfinite(float(h_out[0, : 4 * D].double().abs().sum())):
-            raise SystemExit("bench.py: adaptive MVDR produced fallback bins or non-finite output")
-
-    # ---- optional: the shipped drivers' chain with the Zelinski post-filter, end to end
-    pf_s = 0.0
-    if args.postfilter:
-        plan.chain_zelinski_batch_into(xs, outs, 0.6, 2, 0)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            plan.chain_zelinski_batch_into(xs, outs, 0.6, 2, 0)
-        torch.cuda.synchronize()
-        pf_s = (time.perf_counter() - t0) / e2e_steps
-        if not np.isfinite(float(h_out[0, : 4 * D].double().abs().sum())):
-            raise SystemExit("bench.py: post-filter chain output is not finite")
-
-    # ---- max over ranks
-    tt = torch.tensor([total_ms, kern_ms, e2e_s, e2e16_s, mvdr_s, pf_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    total_ms, kern_ms, e2e_s, e2e16_s, mvdr_s, pf_s = [float(v) for v in tt.tolist()]
+    # ---- the other BASELINE configurations (strong scaling: the utterances are split over the ranks)
+    extras = []
+    if not args.only_primary and args.workload == "cfg2":
+        for key, wl_name, mode, total in EXTRA:
+            cfg = dict(WORKLOADS[wl_name])
+            nb = max(1, total // world)
+            steps = 3 if total >= 512 else max(3, min(args.steps, 10))
+            res = measure(cfg, mode, nb, args, rank, world, local_rank, dev, 3 if wl_name == "cfg3" else 4, steps,
+                          full_host_inputs=False, with_s16=False, adaptive=(mode == "mvdr"))
+            extras.append((key, cfg, mode, steps, max_over_ranks(res)))
     if old_affinity:
         os.sched_setaffinity(0, old_affinity)
 
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "of measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak, peak_src = 6650.0, "of fallback (B200_PROFILING.md)"
-        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-        ms_per_step = total_ms / args.steps
-        value = world * units_per_step / (ms_per_step * 1e-3)
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            try:
-                traffic = json.load(open(tpath)).get(args.workload)
-            except Exception:
-                traffic = None
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(wl_cfg, args),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms,
-                         "kernel": f"btk_chain_kernel<{M},{1 << r}>",
-                         "fp32_note": "fused chain is FP32-issue bound before HBM for M>=256 (SURVEY 8d); see DESIGN.md"},
-            "e2e": {"value": world * units_per_step / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(nb * n_in * 4),
-                    "d2h_bytes_per_step": int(nb * n_out * 4), "ms_per_step": e2e_s * 1e3,
-                    "matches_device_resident_output": same},
-            "e2e_s16_ingest": {"value": world * units_per_step / e2e16_s, "unit": UNIT,
-                               "h2d_bytes_per_step": int(nb * n_in * 2), "d2h_bytes_per_step": int(nb * n_out * 4),
-                               "ms_per_step": e2e16_s * 1e3,
-                               "note": "same call with 16-bit PCM host buffers (btkb200_chain_batch_pcm), converted on the device"},
-            "gpu_launches": int(launches), "clocks": clocks,
-        }
-        if args.mvdr:
-            line["e2e_adaptive_mvdr"] = {
-                "value": world * units_per_step / mvdr_s, "unit": UNIT, "ms_per_step": mvdr_s * 1e3,
-                "h2d_bytes_per_step": int(nb * n_in * 4), "d2h_bytes_per_step": int(nb * n_out * 4),
-                "note": "btkb200_mvdr_chain_batch: per utterance covariance (x x^H, ff 0.99) on the first second -> load 1e-2 "
-                        "trace/C -> per-bin MVDR solve -> fused chain with that utterance's weights; host buffers in and out"}
-        if args.postfilter:
-            line["e2e_zelinski_postfilter"] = {
-                "value": world * units_per_step / pf_s, "unit": UNIT, "ms_per_step": pf_s * 1e3,
-                "note": "btkb200_chain_zelinski_batch (analysis -> SubbandDS -> ZelinskiPostFilter alpha 0.6 |.| -> synthesis, "
-                        "staged kernels, pipelined over the batch); pinned host buffers in and out"}
-        if world == 1 and not args.no_cpu_baseline:
+        line = {"metric": METRIC, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(wl_cfg, args)}
+        line.update(summarise(wl_cfg, "ds", prim, world, args.steps, peak, peak_src, traffic_all.get(args.workload)))
+        line["clocks"] = prim["clocks"]
+        jobs = [(wl_cfg, "ds", prim["first"], config_id)]
+        line["configs"] = {}
+        for key, cfg, mode, steps, res in extras:
+            sub = summarise(cfg, mode, res, world, steps, peak, peak_src, traffic_all.get(key))
+            sub["scaling"] = "strong"
+            sub["steps"] = steps
+            sub["workload"] = cfg["desc"]
+            line["configs"][key] = sub
+            jobs.append((cfg, mode, res["first"], 3 if cfg["C"] == 16 else 4))
+        if not args.no_cpu_baseline:
+            # parity of the timed outputs (first recording of every configuration) against the reference's CPU chain, and
+            # the CPU baseline itself (N = 1 only), on the host cores of this box
             cores = os.cpu_count() or 1
             ctx = mp.get_context("spawn")
-            with ctx.Pool(cores) as pool:
-                secs = wl_cfg["seconds"]
-                rate, kind, wall = cpu_chain_rate(wl_cfg, secs, 2, cores, pool)
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
-                                    "sample": f"{cores} single-threaded processes x 2 recordings of {C} ch x {secs:g} s "
-                                              f"(same chain, same prototype; {wall:.1f} s wall)"}
+            with ctx.Pool(min(cores, max(2, len(jobs)))) as pool:
+                refs = pool.map(_reference_output_worker, jobs)
+            outs0 = [prim["out0"]] + [e[4]["out0"] for e in extras]
+            names = ["primary"] + [e[0] for e in extras]
+            for name, out0, (ref, kind) in zip(names, outs0, refs):
+                par = {"snr_db": snr_db(out0, ref), "against": "oracle/_ref (compiled reference chain)" if kind == "reference"
+                       else "oracle port", "gate_db": 70.0, "recording": "first utterance of rank 0, whole length"}
+                if par["snr_db"] < 70.0:
+                    raise SystemExit(f"bench.py: {name}: timed output is {par['snr_db']:.1f} dB from the reference (< 70 dB)")
+                (line if name == "primary" else line["configs"][name])["parity"] = par
+            if world == 1:
+                with ctx.Pool(cores) as pool:
+                    secs = wl_cfg["seconds"]
+                    rate, kind, wall = cpu_chain_rate(wl_cfg, secs, 2, cores, pool)
+                line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+                                        "sample": f"{cores} single-threaded processes x 2 recordings of {wl_cfg['C']} ch x {secs:g} s "
+                                                  f"(same chain, same prototype; the FFT under the reference's gsl calls is "
+                                                  f"oracle/gsl_shim's radix-2; {wall:.1f} s wall)"}
         print(json.dumps(line), flush=True)
-    plan.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -463,7 +600,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="utterances per GPU (default: per workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--postfilter", action="store_true", help="also time the chain with the Zelinski post-filter end to end")
-    ap.add_argument("--mvdr", action="store_true", help="also time the per-utterance adaptive MVDR path end to end")
+    ap.add_argument("--mvdr", action="store_true", help="also time the per-utterance adaptive MVDR path end to end on the primary workload")
+    ap.add_argument("--only-primary", action="store_true", help="skip the cfg3 / cfg4 (MVDR, 64-channel) configurations")
     args = ap.parse_args()
     wl_cfg = dict(WORKLOADS[args.workload])
     if args.batch > 0:

@@ -262,6 +262,7 @@ class Plan:
 
     def beamform(self, snap) -> np.ndarray:
         s = np.ascontiguousarray(snap, dtype=np.complex64)
+        self._check_snap(s)
         F = s.shape[0]
         Y = np.empty((F, self.B), dtype=np.complex64)
         self._ck(self._L.btkb200_beamform(self._h, _p(s), F, _p(Y)))
@@ -269,6 +270,8 @@ class Plan:
 
     def synthesis(self, Y) -> np.ndarray:
         y = np.ascontiguousarray(Y, dtype=np.complex64)
+        if y.ndim != 2 or y.shape[1] != self.B:
+            raise BtkError(EINVAL, f"beamformer output must be [F][{self.B}], got {y.shape}")
         F = y.shape[0]
         nout = self.synthesis_frames(F)
         out = np.empty(nout * self.D, dtype=np.float32)
@@ -278,6 +281,7 @@ class Plan:
 
     def covariance(self, snap, frame_weights, conjugate: bool = True) -> np.ndarray:
         s = np.ascontiguousarray(snap, dtype=np.complex64)
+        self._check_snap(s)
         F = s.shape[0]
         w = np.ascontiguousarray(frame_weights, dtype=np.float64)
         if w.shape != (F,):
@@ -343,10 +347,35 @@ class Plan:
     def chain_zelinski_batch_into(self, xs, outs, alpha: float = 0.6, pf_type: int = 2, min_frames: int = 0):
         """xs / outs: lists of C-contiguous float32 arrays (outs preallocated, ideally pinned); no allocation here."""
         n = len(xs)
+        self._check_pcm_list(xs)
+        self._check_out_list([x.shape[0] for x in xs], outs)
         pp = (c_void_p * n)(*[x.ctypes.data for x in xs])
         oo = (c_void_p * n)(*[o.ctypes.data for o in outs])
         TT = (c_long * n)(*[x.shape[0] for x in xs])
         self._ck(self._L.btkb200_chain_zelinski_batch(self._h, pp, TT, n, alpha, pf_type, min_frames, oo))
+
+    # -- argument checks of the raw-pointer entry points: the C side trusts (pointer, T) pairs, so a wrong shape, dtype or
+    #    a non-contiguous view would make it read or write past the end of the numpy buffer
+    def _check_pcm_list(self, xs, dtype=np.float32, inner=None):
+        for i, x in enumerate(xs):
+            want_nd = 2 if inner is None else 3
+            if (not isinstance(x, np.ndarray) or x.dtype != dtype or x.ndim != want_nd or x.shape[1] != self.C
+                    or (inner is not None and x.shape[2] != inner) or not x.flags.c_contiguous):
+                raise BtkError(EINVAL, f"recording {i}: need a C-contiguous {np.dtype(dtype).name} array of shape [T][{self.C}]"
+                                       + (f"[{inner}]" if inner else "") + f", got {getattr(x, 'dtype', type(x))} {getattr(x, 'shape', '')}")
+
+    def _check_out_list(self, Ts, outs):
+        if len(outs) != len(Ts):
+            raise BtkError(EINVAL, f"{len(Ts)} recordings but {len(outs)} output buffers")
+        for i, (T, o) in enumerate(zip(Ts, outs)):
+            need = self.chain_frames(int(T)) * self.D
+            if (not isinstance(o, np.ndarray) or o.dtype != np.float32 or not o.flags.c_contiguous or o.size < need
+                    or not o.flags.writeable):
+                raise BtkError(EINVAL, f"output {i}: need a writable C-contiguous float32 array of at least {need} elements")
+
+    def _check_snap(self, s):
+        if s.ndim != 3 or s.shape[1:] != (self.B, self.C):
+            raise BtkError(EINVAL, f"snapshots must be [F][{self.B}][{self.C}], got {s.shape}")
 
     # -- fused path (host numpy buffers)
     def chain(self, pcm) -> np.ndarray:
@@ -368,6 +397,8 @@ class Plan:
     def chain_batch_into(self, xs, outs):
         """xs / outs: lists of C-contiguous float32 arrays (outs preallocated); no allocation here."""
         n = len(xs)
+        self._check_pcm_list(xs)
+        self._check_out_list([x.shape[0] for x in xs], outs)
         pp = (c_void_p * n)(*[x.ctypes.data for x in xs])
         oo = (c_void_p * n)(*[o.ctypes.data for o in outs])
         TT = (c_long * n)(*[x.shape[0] for x in xs])
@@ -378,6 +409,8 @@ class Plan:
         """Per-recording covariance -> loading -> MVDR solve -> fused chain, all on the device.  Returns the number of
         identity-fallback bins per recording."""
         n = len(xs)
+        self._check_pcm_list(xs)
+        self._check_out_list([x.shape[0] for x in xs], outs)
         pp = (c_void_p * n)(*[x.ctypes.data for x in xs])
         oo = (c_void_p * n)(*[o.ctypes.data for o in outs])
         TT = (c_long * n)(*[x.shape[0] for x in xs])
@@ -396,6 +429,12 @@ class Plan:
         """raws: C-contiguous arrays of raw interleaved PCM -- float32 [T][C] (PCM_F32), int16 [T][C] (PCM_S16) or
         uint8 [T][C][3] big-endian 24-bit (PCM_S24BE); Ts: samples per channel; outs preallocated float32."""
         n = len(raws)
+        if fmt not in (PCM_F32, PCM_S16, PCM_S24BE):
+            raise BtkError(EINVAL, f"unknown PCM format {fmt}")
+        self._check_pcm_list(raws, {PCM_F32: np.float32, PCM_S16: np.int16, PCM_S24BE: np.uint8}[fmt], 3 if fmt == PCM_S24BE else None)
+        if len(Ts) != n or any(int(t) != x.shape[0] for t, x in zip(Ts, raws)):
+            raise BtkError(EINVAL, "Ts must give the number of samples per channel of every raw buffer")
+        self._check_out_list(Ts, outs)
         pp = (c_void_p * n)(*[x.ctypes.data for x in raws])
         oo = (c_void_p * n)(*[o.ctypes.data for o in outs])
         TT = (c_long * n)(*[int(t) for t in Ts])

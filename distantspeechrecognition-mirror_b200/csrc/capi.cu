@@ -50,6 +50,8 @@ struct btkb200_plan {
   bool has_h = false, has_g = false;
   int has_weights = 0;      // 0 none, 1 DS, 2 user/MVDR
   bool has_manifold = false;
+  bool mvdr_solved = false;  // w holds solved MVDR weights: a later set_ds_weights refreshes the manifold only (the reference
+                             // keeps _wmvdr apart from the quiescent vectors, beamformer.h:380-388)
   std::vector<zd> w, wq, Rn;
   std::vector<zd> gsc_B, gsc_wa;   // SubbandGSC: blocking matrices [B][C][C-1], active weights [B][C-1]
   bool has_gsc = false;
@@ -283,8 +285,10 @@ int btkb200_set_ds_weights(btkb200_plan* p, double fs, const double* delays, uns
     return fail(p, BTKB200_EINVAL, "Number of delays does not match number of channels (%u vs. %d).", n, p->C);
   ds_weights(delays, fs, p->geo.M, p->C, p->wq);
   p->has_manifold = true;
-  p->w = p->wq;
-  p->has_weights = 1;
+  if (!p->mvdr_solved) {
+    p->w = p->wq;
+    p->has_weights = 1;
+  }
   {
     std::vector<cf> ta(p->wq.size());
     for (size_t i = 0; i < ta.size(); i++) ta[i] = mk((float)p->wq[i].real(), (float)p->wq[i].imag());
@@ -292,13 +296,14 @@ int btkb200_set_ds_weights(btkb200_plan* p, double fs, const double* delays, uns
     CK(p, cudaStreamSynchronize(p->stream));
     CK(p, cudaMemcpy(p->d_ta, ta.data(), ta.size() * sizeof(cf), cudaMemcpyHostToDevice));
   }
-  return upload_weights(p);
+  return p->mvdr_solved ? BTKB200_OK : upload_weights(p);
 }
 
 int btkb200_set_weights(btkb200_plan* p, const double* w) {
   if (!p || !w) return BTKB200_EINVAL;
   for (size_t i = 0; i < p->w.size(); i++) p->w[i] = zd(w[2 * i], w[2 * i + 1]);
   p->has_weights = 2;
+  p->mvdr_solved = false;
   return upload_weights(p);
 }
 
@@ -502,6 +507,7 @@ int btkb200_solve_mvdr(btkb200_plan* p, double /*sample_rate: unused by the refe
   if (n_fallback) *n_fallback = nfb;
   p->w = wnew;
   p->has_weights = 2;
+  p->mvdr_solved = true;
   return upload_weights(p);
 }
 

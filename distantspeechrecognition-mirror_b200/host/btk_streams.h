@@ -345,7 +345,7 @@ class SubbandBeamformer : public VectorComplexFeatureStream {
     if (_F > 0) check(btkb200_beamform_zelinski(_plan.get(), &_snapshots[0], _F, alpha, type, minFrames, &Y[0], &W[0]), _plan.get());
     F = _F;
   }
-  void require_weights() {
+  virtual void require_weights() {
     if (!need_plan() || !_plan.has_weights()) throw j_error("call calcArrayManifoldVectorsX() once\n");   // :1140-1143
   }
 
@@ -462,8 +462,20 @@ class SubbandMVDR : public SubbandDS {
     int nfb = 0;
     check(btkb200_solve_mvdr(need_plan(), sampleRate, dThreshold, &nfb), _plan.get());
     _F = -1;
+    _mvdr_ready = true;
     return true;
   }
+  // SubbandMVDR::next (beamformer.cc:2587-2594): the manifold first, then the MVDR weights; delay-and-sum output is never
+  // served in place of MVDR output
+  virtual void require_weights() {
+    SubbandBeamformer::require_weights();
+    if (!_mvdr_ready) throw j_error("call calcMVDRWeights() once\n");
+  }
+
+ private:
+  bool _mvdr_ready = false;
+
+ public:
   const btk_vector_complex* getMVDRWeights(unsigned fbinX) { return getWeights(fbinX); }
 };
 typedef std::shared_ptr<SubbandDS> SubbandDSPtr;

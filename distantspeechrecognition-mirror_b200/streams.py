@@ -492,8 +492,17 @@ class SubbandMVDRPtr(_SubbandBeamformer):
             self._need_plan().solve_mvdr(sampleRate, dThreshold)
         except BtkError as e:
             _raise(e)
+        self._mvdr_ready = True
         self._weights_changed()
         return True
+
+    def _check_weights(self):
+        # SubbandMVDR::next (beamformer.cc:2587-2594): the manifold first, then the MVDR weights -- delay-and-sum output is
+        # never served in place of MVDR output
+        if not self._need_plan().has_weights():
+            raise j_error("call calcArrayManifoldVectorsX() once")
+        if not getattr(self, "_mvdr_ready", False):
+            raise j_error("call calcMVDRWeights() once")
 
     def getMVDRWeights(self, fbinX: int):
         return self.getWeights(fbinX)

@@ -112,3 +112,32 @@ def test_ws_chain_unaligned_and_odd_channels(prototypes):
             if ref.size:
                 assert bo.snr_db(out, ref) >= 70.0
         plan.close()
+
+
+def test_raw_pointer_entry_points_validate_their_arrays(prototypes):
+    """The batch calls hand (pointer, T) pairs to the C side: wrong shapes, dtypes or strides are refused before that."""
+    M, m, r, C = 256, 4, 1, 4
+    h, g = proto(prototypes, M, m, r)
+    plan = btk_b200.Plan(M, m, r, C, h, g)
+    plan.set_ds_weights(FS, np.zeros(C))
+    T = 1000
+    good = wl.noise_recording(T, C, seed=1)
+    out = np.empty(plan.chain_frames(T) * plan.D, np.float32)
+    bad_inputs = [good[:, :3].copy(), good.reshape(-1), good.astype(np.float64), good[::2], good.T.copy().T]
+    for bad in bad_inputs:
+        for call in (plan.chain_batch_into, plan.mvdr_chain_batch_into, plan.chain_zelinski_batch_into):
+            with pytest.raises(btk_b200.BtkError) as e:
+                call([bad], [out])
+            assert e.value.code == btk_b200._capi.EINVAL
+    for bad_out in (out[:-1].copy(), out.astype(np.float64), np.empty(2 * out.size, np.float32)[::2]):
+        with pytest.raises(btk_b200.BtkError) as e:
+            plan.chain_batch_into([good], [bad_out])
+        assert e.value.code == btk_b200._capi.EINVAL
+    with pytest.raises(btk_b200.BtkError):
+        plan.chain_batch_pcm_into([good.astype(np.int16)], btk_b200._capi.PCM_S16, [T + 1], [out])
+    with pytest.raises(btk_b200.BtkError):
+        plan.beamform(np.zeros((5, plan.B, C + 1), np.complex64))
+    with pytest.raises(btk_b200.BtkError):
+        plan.synthesis(np.zeros((5, plan.B + 1), np.complex64))
+    plan.chain_batch_into([good], [out])          # the good arrays still pass
+    plan.close()

@@ -129,6 +129,34 @@ def test_superdirective_chain_like_reference_driver(prototypes):
     assert bo.snr_db(out, ref) >= 70.0
 
 
+def test_mvdr_node_refuses_to_serve_delay_and_sum_output(prototypes):
+    """SubbandMVDR::next throws 'call calcMVDRWeights() once' when only the manifold exists (beamformer.cc:2587-2594), and a
+    calcArrayManifoldVectors AFTER calcMVDRWeights leaves the MVDR weights in place (_wmvdr is separate from wq)."""
+    M, m, r, C, T = 256, 4, 1, 4, 4000
+    h, g = proto(prototypes, M, m, r)
+    mp = wl.linear_array(C, 41.0)
+    tau = wl.farfield_delays(mp, np.deg2rad(30), np.deg2rad(90))
+    pcm = wl.array_recording(T, tau, seed=3)
+    bf = SubbandMVDRPtr(fftLen=M)
+    synth = build_chain(bf, pcm, h, g, M, m, r)
+    with pytest.raises(j_error, match="calcArrayManifoldVectors"):
+        bf.next()
+    bf.calcArrayManifoldVectors(FS, tau)
+    with pytest.raises(j_error, match="calcMVDRWeights"):
+        bf.next()
+    with pytest.raises(j_error, match="calcMVDRWeights"):
+        next(iter(synth))
+    assert bf.setDiffuseNoiseModel(mp, FS)
+    bf.setAllLevelsOfDiagonalLoading(0.1)
+    assert bf.calcMVDRWeights(FS, 1.0e-8)
+    W = bo.mvdr_weights(bo.diagonal_load(bo.diffuse_coherence(mp, FS, M), 0.1), bo.ds_weights(tau, FS, M))
+    bf.calcArrayManifoldVectors(FS, tau)               # must not replace the solved weights
+    assert bo.rel_l2(np.stack([bf.getMVDRWeights(s) for s in range(M // 2 + 1)]), W) <= 1e-7
+    out = np.concatenate([b.copy() for b in synth])
+    _, _, ref = bo.chain(pcm, h, g, bo.BankGeometry(M, m, r, 0), W)
+    assert bo.snr_db(out, ref) >= 70.0
+
+
 def test_foreign_upstream_iterator_is_drained_frame_by_frame(prototypes):
     """A plain Python iterator in the middle of the chain (what PyVectorComplexFeatureStream allows,
     btk/stream/pyStream.h:89-130): the synthesis bank pulls its frames one by one."""
