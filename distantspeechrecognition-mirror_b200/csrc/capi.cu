@@ -1147,59 +1147,72 @@ int btkb200_mvdr_chain_batch(btkb200_plan* p, const float* const* pcm, const lon
   if (!p->s_in) CK(p, cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
   int rc = chain_prepare(p, poff.data(), Tl.data(), ooff.data(), n, p->stream);
   if (rc) return rc;
-  // ---- per-recording adaptation descriptors: analysis of the adapting lead-in only, recursion weights
-  std::vector<RecDesc> arecs(n);
-  std::vector<WorkItem> awork;
-  std::vector<int> awb(n + 1, 0), aslices(n, 1);
+  // ---- Adaptation runs group by group: ONE launch per stage over all recordings of a group (analysis of the adapting
+  // lead-ins, tensor-core covariance with the recording as grid.z, diagonal loading over n B bins, n B solve CTAs, n weight
+  // tables), then the fused-chain launch of that group with per-recording weight tables and the download of its outputs.
+  // The first sessions' version issued the five small launches recording by recording: at 64 channels the latency-bound
+  // solve alone (140 us, 257 CTAs) made 1 024 utterances cost more than their chain.
   std::vector<long> Fu(n);
-  std::vector<double> fw_all, wt;
   std::vector<long long> fwoff(n);
+  std::vector<double> fw_all, wt;
   const int Wa = fb_frames_per_iter(M, p->geo.R), n_cg = Cpad / 4;
-  size_t max_snap = 16;
+  long Fa_max = 0;
   for (int i = 0; i < n; i++) {
     const long F = p->geo.analysis_frames(T[i]);
     Fu[i] = (cfg->last_frame >= 0 && cfg->last_frame + 1 < F) ? cfg->last_frame + 1 : F;
+    if (Fu[i] > Fa_max) Fa_max = Fu[i];
+    recursion_weights(wt, Fu[i], cfg->forget, cfg->conjugate);
+    fwoff[i] = (long long)fw_all.size();
+    fw_all.insert(fw_all.end(), wt.begin(), wt.end());
+  }
+  const size_t snap_stride = (size_t)(Fa_max > 0 ? Fa_max : 1) * B * C;           // complex elements per recording
+  const size_t per_rec = snap_stride * sizeof(cf) + (size_t)B * C * C * sizeof(double2) + (size_t)B * C * sizeof(double2);
+  // recordings per group: at most 3 GB of snapshots + matrices in flight
+  const size_t budget = (size_t)3 << 30;
+  int Gn = per_rec > 0 && budget / per_rec < 4096 ? (int)(budget / per_rec) : 4096;
+  if (Gn < 1) Gn = 1;
+  if (Gn > n) Gn = n;
+  if (Gn > 4096) Gn = 4096;
+  std::vector<RecDesc> arecs(n);
+  std::vector<WorkItem> awork;
+  std::vector<int> awb(n + 1, 0);
+  std::vector<CovRec> crecs(n);
+  for (int i = 0; i < n; i++) {
     // frames 0 .. Fu-1 only look at samples below (Fu + laN) D: analyse just that lead-in
     long Ta = (long)((long long)(Fu[i] + p->geo.laN) * D);
     if (Ta > T[i]) Ta = T[i];
-    const long Fa = Fu[i];
-    arecs[i].pcm_off = poff[i]; arecs[i].out_off = 0; arecs[i].T = (int)Ta; arecs[i].nblk = (int)Fa;
+    arecs[i].pcm_off = poff[i]; arecs[i].out_off = (long long)(i % Gn) * (long long)snap_stride; arecs[i].T = (int)Ta; arecs[i].nblk = (int)Fu[i];
     std::vector<RecDesc> one(1, arecs[i]);
     std::vector<WorkItem> w1;
-    long long chunk = ((long long)Fa + 148 * 4 - 1) / (148 * 4);
+    long long chunk = ((long long)Fu[i] + 4 - 1) / 4;          // about four CTAs per lead-in: a group supplies the parallelism
     chunk = (chunk + Wa - 1) / Wa * Wa;
     if (chunk < Wa) chunk = Wa;
     build_work(one, (int)chunk, w1);
     for (size_t k = 0; k < w1.size(); k++) { w1[k].rec = i; awork.push_back(w1[k]); }
     awb[i + 1] = (int)awork.size();
-    int slices = w1.empty() ? 1 : (int)(2 * 148 / w1.size());
-    if (slices < 1) slices = 1;
-    if (slices > n_cg) slices = n_cg;
-    aslices[i] = slices;
-    recursion_weights(wt, Fu[i], cfg->forget, cfg->conjugate);
-    fwoff[i] = (long long)fw_all.size();
-    fw_all.insert(fw_all.end(), wt.begin(), wt.end());
-    const size_t bs = (size_t)Fa * B * C * sizeof(cf);
-    if (bs > max_snap) max_snap = bs;
+    crecs[i].snap_off = (long long)(i % Gn) * (long long)snap_stride; crecs[i].wt_off = fwoff[i]; crecs[i].F = Fu[i];
   }
   std::vector<int> binmap;
   if (!build_weight_binmap(M, binmap)) return fail(p, BTKB200_EUNSUPPORTED, "no weight layout for M=%d", M);
-  // ---- one scratch allocation: descriptors | recursion weights | bin map | manifold | R | w | fallback flags | tables | snapshots
+  // ---- one scratch allocation: descriptors | recursion weights | bin map | manifold | fallback flags | tables (all n) |
+  //      R, w, snapshots (one group)
   auto al = [](size_t x) { return (x + 255) / 256 * 256; };
   const size_t o_arecs = 0, o_awork = o_arecs + al(arecs.size() * sizeof(RecDesc));
-  const size_t o_fw = o_awork + al((awork.size() ? awork.size() : 1) * sizeof(WorkItem));
+  const size_t o_crecs = o_awork + al((awork.size() ? awork.size() : 1) * sizeof(WorkItem));
+  const size_t o_fw = o_crecs + al(crecs.size() * sizeof(CovRec));
   const size_t o_map = o_fw + al(fw_all.size() * sizeof(double));
   const size_t o_d = o_map + al(binmap.size() * sizeof(int));
-  const size_t o_R = o_d + al((size_t)B * C * sizeof(double2));
-  const size_t o_w = o_R + al((size_t)B * C * C * sizeof(double2));
-  const size_t o_fb = o_w + al((size_t)B * C * sizeof(double2));
+  const size_t o_fb = o_d + al((size_t)B * C * sizeof(double2));
   const size_t o_tab = o_fb + al((size_t)n * B * sizeof(int));
-  const size_t o_snap = o_tab + al((size_t)n * Cpad * M * sizeof(cf));
-  CK(p, p->d_adapt.reserve(o_snap + al(max_snap)));
+  const size_t o_R = o_tab + al((size_t)n * Cpad * M * sizeof(cf));
+  const size_t o_w = o_R + al((size_t)Gn * B * C * C * sizeof(double2));
+  const size_t o_snap = o_w + al((size_t)Gn * B * C * sizeof(double2));
+  CK(p, p->d_adapt.reserve(o_snap + al((size_t)Gn * snap_stride * sizeof(cf))));
   char* base = (char*)p->d_adapt.p;
   CK(p, cudaStreamSynchronize(p->stream));
   CK(p, cudaMemcpy(base + o_arecs, arecs.data(), arecs.size() * sizeof(RecDesc), cudaMemcpyHostToDevice));
   if (!awork.empty()) CK(p, cudaMemcpy(base + o_awork, awork.data(), awork.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
+  CK(p, cudaMemcpy(base + o_crecs, crecs.data(), crecs.size() * sizeof(CovRec), cudaMemcpyHostToDevice));
   CK(p, cudaMemcpy(base + o_fw, fw_all.data(), fw_all.size() * sizeof(double), cudaMemcpyHostToDevice));
   CK(p, cudaMemcpy(base + o_map, binmap.data(), binmap.size() * sizeof(int), cudaMemcpyHostToDevice));
   CK(p, cudaMemcpy(base + o_d, p->wq.data(), (size_t)B * C * sizeof(double2), cudaMemcpyHostToDevice));
@@ -1208,47 +1221,73 @@ int btkb200_mvdr_chain_batch(btkb200_plan* p, const float* const* pcm, const lon
   int* dfb = (int*)(base + o_fb);
   cf* dtab = (cf*)(base + o_tab);
   cf* dsnap = (cf*)(base + o_snap);
-  // ---- adaptation, recording by recording on the plan's stream; the uploads run ahead on the copy stream
-  while ((int)p->ev_in.size() < n) { cudaEvent_t e; CK(p, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); p->ev_in.push_back(e); }
-  for (int i = 0; i < n; i++) {
-    if (T[i] > 0)
-      CK(p, cudaMemcpyAsync((float*)p->d_in.p + poff[i], pcm[i], (size_t)T[i] * C * sizeof(float), cudaMemcpyHostToDevice, p->s_in));
-    CK(p, cudaEventRecord(p->ev_in[i], p->s_in));
+  if (!p->s_out) CK(p, cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
+  const int n_groups = (n + Gn - 1) / Gn;
+  while ((int)p->ev_in.size() < n_groups) { cudaEvent_t e; CK(p, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); p->ev_in.push_back(e); }
+  while ((int)p->ev_k.size() < n_groups) { cudaEvent_t e; CK(p, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); p->ev_k.push_back(e); }
+  // the uploads of all groups run ahead on the copy stream
+  for (int g = 0; g < n_groups; g++) {
+    const int r0 = g * Gn, r1 = r0 + Gn < n ? r0 + Gn : n;
+    for (int i = r0; i < r1; i++)
+      if (T[i] > 0)
+        CK(p, cudaMemcpyAsync((float*)p->d_in.p + poff[i], pcm[i], (size_t)T[i] * C * sizeof(float), cudaMemcpyHostToDevice, p->s_in));
+    CK(p, cudaEventRecord(p->ev_in[g], p->s_in));
   }
-  for (int i = 0; i < n; i++) {
-    CK(p, cudaStreamWaitEvent(p->stream, p->ev_in[i], 0));
-    CK(p, cudaMemsetAsync(dR, 0, (size_t)B * C * C * sizeof(double2), p->stream));
-    const int nw = awb[i + 1] - awb[i];
-    if (nw > 0 && Fu[i] > 0) {
+  static const bool cov_simt = getenv("BTK_COV_SIMT") && getenv("BTK_COV_SIMT")[0] == '1';
+  for (int g = 0; g < n_groups; g++) {
+    const int r0 = g * Gn, r1 = r0 + Gn < n ? r0 + Gn : n, ng = r1 - r0;
+    CK(p, cudaStreamWaitEvent(p->stream, p->ev_in[g], 0));
+    CK(p, cudaMemsetAsync(dR, 0, (size_t)ng * B * C * C * sizeof(double2), p->stream));
+    const int nw = awb[r1] - awb[r0];
+    long Fg = 0;
+    for (int i = r0; i < r1; i++) if (Fu[i] > Fg) Fg = Fu[i];
+    if (nw > 0 && Fg > 0) {
       AnalysisParams a;
       a.pcm = (const float*)p->d_in.p; a.snap = dsnap; a.recs = (const RecDesc*)(base + o_arecs);
-      a.work = (const WorkItem*)(base + o_awork) + awb[i];
+      a.work = (const WorkItem*)(base + o_awork) + awb[r0];
       a.taps_h = p->d_taps_h; a.twa = p->d_twa; a.twb = p->d_twb; a.C = C; a.Cpad = Cpad; a.m = p->geo.m; a.laN = p->geo.laN;
-      a.cg_slices = aslices[i];
-      CK(p, launch_analysis(M, p->geo.R, a, nw * aslices[i], p->stream));
-      CK(p, launch_covariance(dsnap, (const double*)(base + o_fw) + fwoff[i], dR, Fu[i], B, C, cfg->conjugate ? 1 : 0, p->stream));
-      p->launches += 2;
+      int slices = (int)(2 * 148 / nw);                 // few work items (a small batch): spread the channel groups over CTAs
+      if (slices < 1) slices = 1;
+      if (slices > n_cg) slices = n_cg;
+      a.cg_slices = slices;
+      CK(p, launch_analysis(M, p->geo.R, a, nw * slices, p->stream));
+      p->launches++;
+      if (cov_simt) {
+        for (int i = r0; i < r1; i++)
+          if (Fu[i] > 0)
+            CK(p, launch_covariance(dsnap + crecs[i].snap_off, (const double*)(base + o_fw) + fwoff[i], dR + (size_t)(i - r0) * B * C * C,
+                                    Fu[i], B, C, cfg->conjugate ? 1 : 0, p->stream));
+        p->launches += ng;
+      } else {
+        CK(p, launch_covariance_tc_batch(dsnap, (const double*)(base + o_fw), dR, (const CovRec*)(base + o_crecs) + r0, ng, Fg, B, C,
+                                         cfg->conjugate ? 1 : 0, p->stream));
+        p->launches++;
+      }
     }
     if (cfg->load_abs != 0.0 || cfg->load_rel != 0.0) {
-      CK(p, launch_diag_load(dR, B, C, (float)cfg->load_abs, cfg->load_rel, p->stream));
+      CK(p, launch_diag_load(dR, ng * B, C, (float)cfg->load_abs, cfg->load_rel, p->stream));
       p->launches++;
     }
-    CK(p, launch_mvdr_solve(dR, (const double2*)(base + o_d), dw, dfb + (size_t)i * B, B, C, cfg->dThreshold, p->stream));
-    CK(p, launch_weight_table(dw, (const int*)(base + o_map), dtab + (size_t)i * Cpad * M, M, C, Cpad, p->stream));
+    CK(p, launch_mvdr_solve(dR, (const double2*)(base + o_d), dw, dfb + (size_t)r0 * B, B, C, cfg->dThreshold, p->stream, ng));
+    CK(p, launch_weight_table(dw, (const int*)(base + o_map), dtab + (size_t)r0 * Cpad * M, M, C, Cpad, p->stream, ng));
     p->launches += 2;
-  }
-  // ---- one fused-chain launch over the whole batch, every recording with its own weight table
-  rc = chain_launch(p, (const float*)p->d_in.p, (float*)p->d_out.p, 0, p->cached_n_work, p->stream, dtab, (long long)Cpad * M);
-  if (rc) return rc;
-  for (int i = 0; i < n; i++) {
-    const size_t b = (size_t)p->geo.chain_frames(T[i]) * D * sizeof(float);
-    if (b) CK(p, cudaMemcpyAsync(out[i], (float*)p->d_out.p + ooff[i], b, cudaMemcpyDeviceToHost, p->stream));
+    // the fused chain of this group, every recording with its own weight table, then its outputs go home
+    rc = chain_launch(p, (const float*)p->d_in.p, (float*)p->d_out.p, p->rec_work_begin[r0], p->rec_work_begin[r1], p->stream, dtab,
+                      (long long)Cpad * M);
+    if (rc) return rc;
+    CK(p, cudaEventRecord(p->ev_k[g], p->stream));
+    CK(p, cudaStreamWaitEvent(p->s_out, p->ev_k[g], 0));
+    for (int i = r0; i < r1; i++) {
+      const size_t b = (size_t)p->geo.chain_frames(T[i]) * D * sizeof(float);
+      if (b) CK(p, cudaMemcpyAsync(out[i], (float*)p->d_out.p + ooff[i], b, cudaMemcpyDeviceToHost, p->s_out));
+    }
   }
   std::vector<int> fb;
   if (n_fallback) { fb.resize((size_t)n * B); CK(p, cudaMemcpyAsync(fb.data(), dfb, fb.size() * sizeof(int), cudaMemcpyDeviceToHost, p->stream)); }
+  CK(p, cudaStreamSynchronize(p->s_out));
   CK(p, cudaStreamSynchronize(p->stream));
   if (n_fallback)
-    for (int i = 0; i < n; i++) { int s = 0; for (int b = 0; b < B; b++) s += fb[(size_t)i * B + b]; n_fallback[i] = s; }
+    for (int i = 0; i < n; i++) { int sfb = 0; for (int b = 0; b < B; b++) sfb += fb[(size_t)i * B + b]; n_fallback[i] = sfb; }
   return BTKB200_OK;
 }
 

@@ -86,8 +86,13 @@ __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__
 
 __global__ void __launch_bounds__(COV_TC_THREADS) btk_covariance_tc_kernel(const cf* __restrict__ snap, const double* __restrict__ wt,
                                                                           double2* __restrict__ Rout, long long F, int B, int C,
-                                                                          int conj, int Cp) {
+                                                                          int conj, int Cp, const CovRec* __restrict__ recs) {
   extern __shared__ __align__(1024) unsigned char smem[];
+  if (recs) {        // batched launch: blockIdx.z is the recording (its snapshots, recursion weights, frame count, R block)
+    const CovRec rc = recs[blockIdx.z];
+    snap += rc.snap_off; wt += rc.wt_off; F = rc.F;
+    Rout += (long long)blockIdx.z * B * C * C;
+  }
   __shared__ __align__(8) unsigned long long s_bar[2];
   __shared__ uint32_t s_tmem;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -301,7 +306,31 @@ cudaError_t launch_covariance_tc(const cf* snap, const double* wt, double2* Rout
   const int smem = COV_TC_SMEM;
   cudaError_t e = cudaFuncSetAttribute(btk_covariance_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  btk_covariance_tc_kernel<<<dim3(tiles, split), COV_TC_THREADS, smem, st>>>(snap, wt, Rout, F, B, C, conj, Cp);
+  btk_covariance_tc_kernel<<<dim3(tiles, split), COV_TC_THREADS, smem, st>>>(snap, wt, Rout, F, B, C, conj, Cp, nullptr);
+  return cudaGetLastError();
+}
+
+// n recordings in one launch (grid.z): recs[i] = (snapshot offset, weight offset, frames), R block i = Rout + i B C C.
+// One frame slice per (tile, recording) as soon as the grid fills the SMs (R is then written without atomics and needs no
+// zeroing); Fmax = the largest frame count of the batch.
+cudaError_t launch_covariance_tc_batch(const cf* snap, const double* wt, double2* Rout, const CovRec* recs, int n, long long Fmax,
+                                       int B, int C, int conj, cudaStream_t st) {
+  if (C > 64 || C < 1 || n < 1 || n > 65535) return cudaErrorInvalidValue;
+  if (Fmax == 0) return cudaSuccess;
+  int Cp = 4;
+  while (Cp < C) Cp *= 2;
+  const int tiles = (B + 64 / Cp - 1) / (64 / Cp);
+  int split = (int)((Fmax + 2047) / 2048);
+  const long long ctas = (long long)tiles * n;
+  const int want = ctas >= 148 ? 1 : (int)((3 * 148 / 2 + ctas - 1) / ctas);
+  if (split < want) split = want;
+  const int cap = (int)((Fmax + 63) / 64);
+  if (split > cap) split = cap;
+  if (split < 1) split = 1;
+  if (split > 64) split = 64;
+  cudaError_t e = cudaFuncSetAttribute(btk_covariance_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, COV_TC_SMEM);
+  if (e != cudaSuccess) return e;
+  btk_covariance_tc_kernel<<<dim3(tiles, split, n), COV_TC_THREADS, COV_TC_SMEM, st>>>(snap, wt, Rout, 0, B, C, conj, Cp, recs);
   return cudaGetLastError();
 }
 

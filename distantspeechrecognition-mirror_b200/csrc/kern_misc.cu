@@ -163,6 +163,8 @@ __global__ void btk_weight_table_kernel(const double2* __restrict__ w, const int
                                         int Cpad) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Cpad * M) return;
+  w += (long long)blockIdx.y * (M / 2 + 1) * C;          // grid.y = recording of a batch
+  gam += (long long)blockIdx.y * Cpad * M;
   const int c = idx / M, slot = idx - c * M;
   cf v = mk(0.f, 0.f);
   if (c < C) {
@@ -178,8 +180,8 @@ cudaError_t launch_diag_load(double2* Rn, int B, int C, float load_abs, double l
   btk_diag_load_kernel<<<(B + 3) / 4, 128, 0, st>>>(Rn, B, C, load_abs, load_rel);
   return cudaGetLastError();
 }
-cudaError_t launch_weight_table(const double2* w, const int* binmap, cf* gam, int M, int C, int Cpad, cudaStream_t st) {
-  btk_weight_table_kernel<<<(Cpad * M + 255) / 256, 256, 0, st>>>(w, binmap, gam, M, C, Cpad);
+cudaError_t launch_weight_table(const double2* w, const int* binmap, cf* gam, int M, int C, int Cpad, cudaStream_t st, int n) {
+  btk_weight_table_kernel<<<dim3((Cpad * M + 255) / 256, n), 256, 0, st>>>(w, binmap, gam, M, C, Cpad);
   return cudaGetLastError();
 }
 
@@ -367,20 +369,22 @@ __device__ __forceinline__ double shfl_d(double v, int src) {
 
 __global__ void __launch_bounds__(256) btk_mvdr_solve_kernel(const double2* __restrict__ Rn, const double2* __restrict__ dvec,
                                                             double2* __restrict__ w, int* __restrict__ fallback, int C,
-                                                            double dThreshold) {
+                                                            double dThreshold, int B) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* A = reinterpret_cast<double2*>(smem_raw);       // [C][C+1]
   __shared__ double s_best[8];
   __shared__ int s_bidx[8];
-  const int s = blockIdx.x, ld = C + 1, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  // block = (recording, bin): the manifold is shared by the recordings of a batch, R / w / fallback are per recording
+  const int sb = blockIdx.x, s = sb % B, ld = C + 1, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const double2* d = dvec + (long long)s * C;
-  double2* ws = w + (long long)s * C;
+  double2* ws = w + (long long)sb * C;
+  fallback += sb - s;                          // this recording's flags
   if (s == 0) {   // w[0] = (1, ..., 1), beamformer.cc:2410-2415
     for (int c = tid; c < C; c += nt) ws[c] = make_double2(1.0, 0.0);
     if (tid == 0) fallback[0] = 0;
     return;
   }
-  const double2* Rs = Rn + (long long)s * C * C;
+  const double2* Rs = Rn + (long long)sb * C * C;
   for (int i = tid; i < C * C; i += nt) {
     const int r = i / C, c = i % C;
     const double2 v = Rs[c * C + r];                        // (R^H)[r][c] = conj(R[c][r])
@@ -485,11 +489,11 @@ __global__ void __launch_bounds__(256) btk_mvdr_solve_kernel(const double2* __re
 }
 
 cudaError_t launch_mvdr_solve(const double2* Rn, const double2* d, double2* w, int* fallback, int B, int C,
-                              double dThreshold, cudaStream_t st) {
+                              double dThreshold, cudaStream_t st, int n) {
   const size_t smem = (size_t)C * (C + 1) * sizeof(double2);
   cudaError_t e = cudaFuncSetAttribute(btk_mvdr_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  btk_mvdr_solve_kernel<<<B, C > 32 ? 256 : 128, smem, st>>>(Rn, d, w, fallback, C, dThreshold);
+  btk_mvdr_solve_kernel<<<B * n, C > 32 ? 256 : 128, smem, st>>>(Rn, d, w, fallback, C, dThreshold, B);
   return cudaGetLastError();
 }
 

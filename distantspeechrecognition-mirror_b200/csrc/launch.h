@@ -31,9 +31,15 @@ cudaError_t launch_covariance(const cf* snap, const double* wt, double2* Rout, l
 // the same contraction on tcgen05 tensor cores (TF32 hi/lo split inputs, FP32 accumulation in TMEM): kern_cov_tc.cu
 cudaError_t launch_covariance_tc(const cf* snap, const double* wt, double2* Rout, long long F, int B, int C, int conj,
                                  cudaStream_t st);
-// per-bin MVDR solve (beamformer.cc:2392-2446); Rn [B][C][C], d [B][C] -> w [B][C]; fallback[B] flags
+// batched form: recording i of n reads its snapshots at snap + recs[i].snap_off, its frame weights at wt + recs[i].wt_off,
+// recs[i].F frames, and writes Rout + i B C C (device array of descriptors; one launch, grid.z = recording)
+struct CovRec { long long snap_off, wt_off, F; };
+cudaError_t launch_covariance_tc_batch(const cf* snap, const double* wt, double2* Rout, const CovRec* recs, int n, long long Fmax,
+                                       int B, int C, int conj, cudaStream_t st);
+// per-bin MVDR solve (beamformer.cc:2392-2446); Rn [n][B][C][C], d [B][C] (one manifold for all n) -> w [n][B][C];
+// fallback[n][B] flags.  One CTA per (recording, bin): n = 1 is the single-recording call.
 cudaError_t launch_mvdr_solve(const double2* Rn, const double2* d, double2* w, int* fallback, int B, int C,
-                              double dThreshold, cudaStream_t st);
+                              double dThreshold, cudaStream_t st, int n = 1);
 
 // Beamformer output + Zelinski post-filter on stored snapshots (postfilter/postfilter.cc:30-222, 428-500): Y [F][B]
 // post-filtered in place semantics (Y is written, then scaled), Wout [F][B] or NULL; stat = scratch of
@@ -49,7 +55,7 @@ cudaError_t design_prototype(int kind, const double* h_in, int M, int m, int r, 
 
 // device-resident MVDR adaptation helpers (kern_misc.cu): diagonal loading, chain weight table from device weights
 cudaError_t launch_diag_load(double2* Rn, int B, int C, float load_abs, double load_rel, cudaStream_t st);
-cudaError_t launch_weight_table(const double2* w, const int* binmap, cf* gam, int M, int C, int Cpad, cudaStream_t st);
+cudaError_t launch_weight_table(const double2* w, const int* binmap, cf* gam, int M, int C, int Cpad, cudaStream_t st, int n = 1);
 
 // Raw PCM -> float32, element for element (bit-exact integer -> float):
 //   fmt 1: int16 little endian (what sf_readf_float returns with SFC_SET_NORM_FLOAT off, feature/feature.cc:273, 868-896)
