@@ -1170,6 +1170,9 @@ int btkb200_mvdr_chain_batch(btkb200_plan* p, const float* const* pcm, const lon
   // recordings per group: at most 3 GB of snapshots + matrices in flight
   const size_t budget = (size_t)3 << 30;
   int Gn = per_rec > 0 && budget / per_rec < 4096 ? (int)(budget / per_rec) : 4096;
+  // at least eight groups for a batch of 16 or more: the upload of group k+1 and the download of group k-1 overlap the
+  // kernels of group k (one group = upload everything, then compute, then download: cfg3 +17 % end to end)
+  if (n >= 16 && Gn > (n + 7) / 8) Gn = (n + 7) / 8;
   if (Gn < 1) Gn = 1;
   if (Gn > n) Gn = n;
   if (Gn > 4096) Gn = 4096;

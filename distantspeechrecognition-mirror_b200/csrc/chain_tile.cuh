@@ -429,12 +429,31 @@ BTK_HD void synth_emit(Ctx& ctx, const ChainSmem& L, const float* taps_g, const 
           for (int k = 0; k < mm; k++) g[k] = taps_g[k * M_ + q];
           BTK_UNROLL
           for (int i = 0; i < NV; i++) v[i] = v_frame(s_vhist, s_vcur, L.H, M_, f0 - back - R_ * (mm - 1) + i)[q];
-          BTK_UNROLL
-          for (int f = 0; f < FPT; f++) {
-            float w = 0.f;
+#ifndef BTK_EMIT_SCALAR
+          if (R_ % 2 == 0 && FPT % 2 == 0) {
+            // frames f, f+1 (f even) read v[f + R (mm-1-k)] and its neighbour: with R even that is an aligned register
+            // pair for every tap, so the two frames share one packed multiply-add per tap
             BTK_UNROLL
-            for (int k = 0; k < mm; k++) w = fmaf(g[k], v[f + R_ * (mm - 1) - R_ * k], w);
-            if (jb + f - back >= 0) acc[f] += w;
+            for (int f = 0; f < FPT; f += 2) {
+              cf w = mk(0.f, 0.f);
+              BTK_UNROLL
+              for (int k = 0; k < mm; k++) {
+                const int i0 = f + R_ * (mm - 1) - R_ * k;
+                w = cfma_real(mk(v[i0], v[i0 + 1]), g[k], w);
+              }
+              if (jb + f - back >= 0) acc[f] += w.x;
+              if (jb + f + 1 - back >= 0) acc[f + 1] += w.y;
+            }
+          } else
+#endif
+          {
+            BTK_UNROLL
+            for (int f = 0; f < FPT; f++) {
+              float w = 0.f;
+              BTK_UNROLL
+              for (int k = 0; k < mm; k++) w = fmaf(g[k], v[f + R_ * (mm - 1) - R_ * k], w);
+              if (jb + f - back >= 0) acc[f] += w;
+            }
           }
         } else {
           BTK_UNROLL

@@ -147,6 +147,57 @@ BTK_HD void ws_fill_thread(int ptid, const ChainSmem& L, float* s_xs, const floa
   const bool v4 = vec4 && cg0 + K::CG <= C;
   const int ntask = D * ((L.NB + LV - 1) / LV);
   const int nbatch = (ntask + K::NPT * TB - 1) / (K::NPT * TB);
+#ifdef BTK_WS_FASTFILL
+  // A/B, OFF by default: interior windows (every sample of the window lies inside the recording) skip the per-sample
+  // range tests -- the guarded loop below spends ~17 instructions per 16-byte load on them (ncu).  Measured on B200 the
+  // lean loop is SLOWER: cfg2 0.3614 -> 0.3657 ms, cfg3 0.8235 -> 0.8747 ms, cfg4 1.887 -> 2.003 ms.  Its loads leave
+  // back to back, and a burst of 32-sector requests in the LSU queue delays the shared-memory accesses of the transform
+  // warps, which are what bounds the kernel; the guarded loop happens to pace the loads.
+  if (v4 && t0 >= 0 && (long long)t0 + (long long)L.NB * D <= (long long)T) {
+    const size_t row = (size_t)D * (unsigned)C;                     // floats between consecutive D-blocks of one residue
+    for (int b = 0; b < nbatch; b++) {
+      const int task0 = ptid + b * (K::NPT * TB);
+      float4 q[TB][LV];
+      BTK_UNROLL
+      for (int k = 0; k < TB; k++) {
+        const int task = task0 + k * K::NPT;
+        const int res = task % D, bg = task / D;
+        const float* src = pcm_cg + (size_t)((unsigned)(t0 + res)) * (unsigned)C + (size_t)(bg * LV) * row;
+        BTK_UNROLL
+        for (int i = 0; i < LV; i++) {
+          q[k][i].x = 0.f; q[k][i].y = 0.f; q[k][i].z = 0.f; q[k][i].w = 0.f;
+          if (task < ntask && bg * LV + i < L.NB) q[k][i] = *reinterpret_cast<const float4*>(src + i * row);
+        }
+      }
+      BTK_UNROLL
+      for (int k = 0; k < TB; k++) {
+        const int task = task0 + k * K::NPT;
+        if (task < ntask) {
+          const int res = task % D, bg = task / D;
+          float* dst = s_xs + xs_off<LV>(res, bg, L.SB);
+          if (LV == 4) {
+            float4 v;
+            v.x = q[k][0].x; v.y = q[k][1].x; v.z = q[k][LV > 2 ? 2 : 0].x; v.w = q[k][LV - 1].x;
+            *reinterpret_cast<float4*>(dst) = v;
+            v.x = q[k][0].y; v.y = q[k][1].y; v.z = q[k][LV > 2 ? 2 : 0].y; v.w = q[k][LV - 1].y;
+            *reinterpret_cast<float4*>(dst + L.CS) = v;
+            v.x = q[k][0].z; v.y = q[k][1].z; v.z = q[k][LV > 2 ? 2 : 0].z; v.w = q[k][LV - 1].z;
+            *reinterpret_cast<float4*>(dst + 2 * L.CS) = v;
+            v.x = q[k][0].w; v.y = q[k][1].w; v.z = q[k][LV > 2 ? 2 : 0].w; v.w = q[k][LV - 1].w;
+            *reinterpret_cast<float4*>(dst + 3 * L.CS) = v;
+          } else {
+            float2 v;
+            v.x = q[k][0].x; v.y = q[k][1].x; *reinterpret_cast<float2*>(dst) = v;
+            v.x = q[k][0].y; v.y = q[k][1].y; *reinterpret_cast<float2*>(dst + L.CS) = v;
+            v.x = q[k][0].z; v.y = q[k][1].z; *reinterpret_cast<float2*>(dst + 2 * L.CS) = v;
+            v.x = q[k][0].w; v.y = q[k][1].w; *reinterpret_cast<float2*>(dst + 3 * L.CS) = v;
+          }
+        }
+      }
+    }
+    return;
+  }
+#endif
   for (int b = 0; b < nbatch; b++) {
     const int task0 = ptid + b * (K::NPT * TB);
     float x[TB][LV][K::CG];
