@@ -6,10 +6,12 @@ The directory name carries a hyphen (it mirrors the upstream repository name); i
 ``btk_b200`` shim at the repository root:  ``import btk_b200``.
 """
 from . import _capi, streams, workloads  # noqa: F401
-from ._capi import (BtkError, Plan, design_analysis_prototype, design_synthesis_prototype, device_count,  # noqa: F401
-                    lib)
+from ._capi import (BtkError, Plan, calc_all_delays, calc_delays_polar, design_analysis_prototype,  # noqa: F401
+                    design_synthesis_prototype, device_count, lib)
 from .streams import (OverSampledDFTAnalysisBankPtr, OverSampledDFTSynthesisBankPtr, SampleFeaturePtr,  # noqa: F401
-                      SubbandDSPtr, SubbandGSCPtr, SubbandMVDRPtr, ZelinskiPostFilterPtr)
+                      SnapShotArrayPtr, SpectralMatrixArrayPtr, SubbandDSPtr, SubbandGSCPtr, SubbandMVDRPtr,
+                      ZelinskiPostFilterPtr)
 
 __all__ = ["Plan", "BtkError", "device_count", "lib", "design_analysis_prototype", "design_synthesis_prototype", "workloads", "streams", "SampleFeaturePtr",
-           "OverSampledDFTAnalysisBankPtr", "OverSampledDFTSynthesisBankPtr", "SubbandDSPtr", "SubbandGSCPtr", "SubbandMVDRPtr", "ZelinskiPostFilterPtr"]
+           "OverSampledDFTAnalysisBankPtr", "OverSampledDFTSynthesisBankPtr", "SubbandDSPtr", "SubbandGSCPtr", "SubbandMVDRPtr", "ZelinskiPostFilterPtr",
+           "SnapShotArrayPtr", "SpectralMatrixArrayPtr", "calc_delays_polar", "calc_all_delays"]

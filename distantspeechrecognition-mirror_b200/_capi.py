@@ -31,7 +31,8 @@ SYMBOLS = [
     "btkb200_design_analysis_prototype", "btkb200_design_synthesis_prototype", "btkb200_gsc_set_active_weights", "btkb200_gsc_zero_active_weights", "btkb200_gsc_get_blocking_matrix", "btkb200_gsc_apply",
     "btkb200_chain_batch_multi", "btkb200_chain_batch_dev", "btkb200_analysis_dev", "btkb200_beamform_dev",
     "btkb200_synthesis_dev", "btkb200_launch_count", "btkb200_sync", "btkb200_host_alloc", "btkb200_host_free",
-    "btkb200_plan_tune", "btkb200_plan_tuning",
+    "btkb200_plan_tune", "btkb200_plan_tuning", "btkb200_set_null_weights", "btkb200_calc_delays_polar",
+    "btkb200_calc_all_delays", "btkb200_get_array_manifold",
 ]
 
 
@@ -80,6 +81,10 @@ def lib() -> ctypes.CDLL:
         getattr(L, f).restype = c_long
         getattr(L, f).argtypes = [vp, c_long]
     L.btkb200_set_ds_weights.argtypes = [vp, c_double, vp, c_uint]
+    L.btkb200_set_null_weights.argtypes = [vp, c_double, vp, c_uint, vp, c_uint]
+    L.btkb200_calc_delays_polar.argtypes = [c_float, c_float, vp, c_uint, vp]
+    L.btkb200_calc_all_delays.argtypes = [c_double, c_double, c_double, vp, c_uint, vp]
+    L.btkb200_get_array_manifold.argtypes = [vp, vp]
     L.btkb200_set_weights.argtypes = [vp, vp]
     L.btkb200_get_weights.argtypes = [vp, vp]
     L.btkb200_get_manifold.argtypes = [vp, vp]
@@ -195,6 +200,19 @@ class Plan:
     def set_ds_weights(self, fs: float, delays):
         d = np.ascontiguousarray(delays, dtype=np.float64)
         self._ck(self._L.btkb200_set_ds_weights(self._h, fs, _p(d), d.size))
+
+    def set_null_weights(self, fs: float, delaysT, delaysJ):
+        """SubbandDS::calcArrayManifoldVectors2 / N (beamformer.cc:1100-1121): delaysJ is [C] or [NC-1][C]."""
+        dT = np.ascontiguousarray(delaysT, dtype=np.float64)
+        dJ = np.ascontiguousarray(np.atleast_2d(np.asarray(delaysJ, dtype=np.float64)))
+        if dJ.ndim != 2 or dJ.shape[1] != self.C:
+            raise BtkError(EINVAL, f"interferer delays must be [NC-1][{self.C}], got {dJ.shape}")
+        self._ck(self._L.btkb200_set_null_weights(self._h, fs, _p(dT), dT.size, _p(dJ), dJ.shape[0] + 1))
+
+    def get_array_manifold(self) -> np.ndarray:
+        w = np.zeros((self.B, self.C), dtype=np.complex128)
+        self._ck(self._L.btkb200_get_array_manifold(self._h, _p(w)))
+        return w
 
     def set_weights(self, W):
         w = np.ascontiguousarray(W, dtype=np.complex128)
@@ -521,6 +539,30 @@ def design_synthesis_prototype(h, M: int, m: int, r: int, v: float = 1.0, wp_fac
     if rc != OK:
         raise BtkError(rc, (L.btkb200_last_error(None) or b"").decode())
     return g, err
+
+
+def calc_delays_polar(azimuth: float, elevation: float, micpos_mm) -> np.ndarray:
+    """calcDelaysPolar2 (src/superdirectiveBeamformer.cc:118-137): far-field delays in seconds, micpos [C][3] in mm."""
+    mp = np.ascontiguousarray(micpos_mm, dtype=np.float64)
+    if mp.ndim != 2 or mp.shape[1] != 3:
+        raise BtkError(EINVAL, f"micpos must be [C][3], got {mp.shape}")
+    d = np.zeros(mp.shape[0], dtype=np.float64)
+    rc = lib().btkb200_calc_delays_polar(azimuth, elevation, _p(mp), mp.shape[0], _p(d))
+    if rc:
+        raise BtkError(rc, "btkb200_calc_delays_polar")
+    return d
+
+
+def calc_all_delays(x: float, y: float, z: float, micpos_mm) -> np.ndarray:
+    """calcAllDelays (beamformer.cc:1214-1231); the source position is ignored, as in the reference."""
+    mp = np.ascontiguousarray(micpos_mm, dtype=np.float64)
+    if mp.ndim != 2 or mp.shape[1] != 3:
+        raise BtkError(EINVAL, f"micpos must be [C][3], got {mp.shape}")
+    d = np.zeros(mp.shape[0], dtype=np.float64)
+    rc = lib().btkb200_calc_all_delays(x, y, z, _p(mp), mp.shape[0], _p(d))
+    if rc:
+        raise BtkError(rc, "btkb200_calc_all_delays")
+    return d
 
 
 def device_count() -> int:

@@ -53,6 +53,7 @@ struct btkb200_plan {
   bool mvdr_solved = false;  // w holds solved MVDR weights: a later set_ds_weights refreshes the manifold only (the reference
                              // keeps _wmvdr apart from the quiescent vectors, beamformer.h:380-388)
   std::vector<zd> w, wq, Rn;
+  std::vector<zd> ta;          // array manifold (target delay-and-sum vector): equals wq unless null-steering weights are installed
   std::vector<zd> gsc_B, gsc_wa;   // SubbandGSC: blocking matrices [B][C][C-1], active weights [B][C-1]
   bool has_gsc = false;
   std::vector<char> Rn_set;
@@ -284,6 +285,7 @@ int btkb200_set_ds_weights(btkb200_plan* p, double fs, const double* delays, uns
   if ((int)n != p->C)
     return fail(p, BTKB200_EINVAL, "Number of delays does not match number of channels (%u vs. %d).", n, p->C);
   ds_weights(delays, fs, p->geo.M, p->C, p->wq);
+  p->ta = p->wq;
   p->has_manifold = true;
   if (!p->mvdr_solved) {
     p->w = p->wq;
@@ -297,6 +299,51 @@ int btkb200_set_ds_weights(btkb200_plan* p, double fs, const double* delays, uns
     CK(p, cudaMemcpy(p->d_ta, ta.data(), ta.size() * sizeof(cf), cudaMemcpyHostToDevice));
   }
   return p->mvdr_solved ? BTKB200_OK : upload_weights(p);
+}
+
+// SubbandDS::calcArrayManifoldVectors2 / calcArrayManifoldVectorsN (beamformer.cc:1100-1121 -> beamformerWeights::calcMainlobe2 /
+// calcMainlobeN, :603-735): distortionless towards the target, nulls towards NC - 1 interferers.  The array manifold (what
+// the post-filter time-aligns with) stays the target's delay-and-sum vector, as in the reference.
+int btkb200_set_null_weights(btkb200_plan* p, double fs, const double* delaysT, unsigned n, const double* delaysJ, unsigned NC) {
+  if (!p || !delaysT || !delaysJ) return BTKB200_EINVAL;
+  if ((int)n != p->C)
+    return fail(p, BTKB200_EINVAL, "Number of delays does not match number of channels (%u vs. %d).", n, p->C);
+  if (NC < 2 || (int)NC > p->C)
+    return fail(p, BTKB200_EINVAL, "1 < the number of constraints %u <= the number of sensors %d.", NC, p->C);
+  std::vector<zd>& ta = p->ta;
+  if (!null_weights(delaysT, delaysJ, fs, p->geo.M, p->C, (int)NC, ta, p->wq)) return fail(p, BTKB200_ESTATE, "calcNullBeamformer() failed");
+  p->has_manifold = true;
+  if (!p->mvdr_solved) {
+    p->w = p->wq;
+    p->has_weights = 1;
+  }
+  {
+    std::vector<cf> t32(ta.size());
+    for (size_t i = 0; i < ta.size(); i++) t32[i] = mk((float)ta[i].real(), (float)ta[i].imag());
+    CK(p, cudaSetDevice(p->device));
+    CK(p, cudaStreamSynchronize(p->stream));
+    CK(p, cudaMemcpy(p->d_ta, t32.data(), t32.size() * sizeof(cf), cudaMemcpyHostToDevice));
+  }
+  return p->mvdr_solved ? BTKB200_OK : upload_weights(p);
+}
+
+// G1: the delay helpers of the reference's drivers, host arithmetic in the reference's own precision.
+int btkb200_calc_delays_polar(float azimuth, float elevation, const double* micpos, unsigned n, double* delays) {
+  if (!micpos || !delays || n == 0) return BTKB200_EINVAL;
+  delays_polar2(azimuth, elevation, micpos, (int)n, delays);
+  return BTKB200_OK;
+}
+int btkb200_calc_all_delays(double x, double y, double z, const double* micpos, unsigned n, double* delays) {
+  if (!micpos || !delays || n == 0) return BTKB200_EINVAL;
+  all_delays(x, y, z, micpos, (int)n, delays);
+  return BTKB200_OK;
+}
+
+int btkb200_get_array_manifold(const btkb200_plan* p, double* w) {
+  if (!p || !w) return BTKB200_EINVAL;
+  if (!p->has_manifold || p->ta.empty()) return fail(const_cast<btkb200_plan*>(p), BTKB200_ESTATE, "call calcArrayManifoldVectorsX() once");
+  for (size_t i = 0; i < p->ta.size(); i++) { w[2 * i] = p->ta[i].real(); w[2 * i + 1] = p->ta[i].imag(); }
+  return BTKB200_OK;
 }
 
 int btkb200_set_weights(btkb200_plan* p, const double* w) {

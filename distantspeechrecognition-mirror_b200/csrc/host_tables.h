@@ -127,6 +127,120 @@ inline void ds_weights(const double* delays, double fs, int M, int C, std::vecto
   }
 }
 
+// calcNullBeamformer (beamformer/beamformer.cc:315-397): constraint matrix Cm = [wt | pWj_0 | ...] ([C][NC]),
+// wt <- Cm (Cm^H Cm)^{-1} e_0.  NC == 2 goes through putInverseMat22 (:202-242: plain 2 x 2 inverse, 0.01 added to the
+// diagonal when |det| < 1e-7); larger NC through pseudoinverse() (:253-305, single-precision SVD) in the reference --
+// here a double-precision Gauss-Jordan inverse, which agrees with it to the float SVD's own rounding.
+inline bool null_beamformer(zd* wt, const zd* pWj /*[NC-1][C]*/, int C, int NC) {
+  std::vector<zd> Cm((size_t)C * NC), A((size_t)NC * NC, zd(0, 0));
+  for (int i = 0; i < C; i++) {
+    Cm[(size_t)i * NC] = wt[i];
+    for (int j = 1; j < NC; j++) Cm[(size_t)i * NC + j] = pWj[(size_t)(j - 1) * C + i];
+  }
+  for (int a = 0; a < NC; a++)
+    for (int b = 0; b < NC; b++) {
+      zd s(0, 0);
+      for (int i = 0; i < C; i++) s += std::conj(Cm[(size_t)i * NC + a]) * Cm[(size_t)i * NC + b];
+      A[(size_t)a * NC + b] = s;
+    }
+  std::vector<zd> v(NC);                      // first column of A^{-1}
+  if (NC == 2) {
+    zd m00 = A[0], m01 = A[1], m10 = A[2], m11 = A[3];
+    zd det = m00 * m11 - m01 * m10;
+    if (std::abs(det) < 1.0e-7) { m00 += 0.01; m11 += 0.01; det = m00 * m11 - m01 * m10; }
+    v[0] = m11 / det;
+    v[1] = -(m10 / det);
+  } else {
+    std::vector<zd> aug((size_t)NC * (NC + 1));
+    for (int a = 0; a < NC; a++) {
+      for (int b = 0; b < NC; b++) aug[(size_t)a * (NC + 1) + b] = A[(size_t)a * NC + b];
+      aug[(size_t)a * (NC + 1) + NC] = a == 0 ? zd(1, 0) : zd(0, 0);
+    }
+    for (int col = 0; col < NC; col++) {
+      int piv = col;
+      for (int a = col + 1; a < NC; a++)
+        if (std::abs(aug[(size_t)a * (NC + 1) + col]) > std::abs(aug[(size_t)piv * (NC + 1) + col])) piv = a;
+      if (std::abs(aug[(size_t)piv * (NC + 1) + col]) == 0.0) return false;
+      if (piv != col)
+        for (int b = 0; b <= NC; b++) std::swap(aug[(size_t)piv * (NC + 1) + b], aug[(size_t)col * (NC + 1) + b]);
+      const zd ip = zd(1, 0) / aug[(size_t)col * (NC + 1) + col];
+      for (int b = 0; b <= NC; b++) aug[(size_t)col * (NC + 1) + b] *= ip;
+      for (int a = 0; a < NC; a++) {
+        if (a == col) continue;
+        const zd f = aug[(size_t)a * (NC + 1) + col];
+        for (int b = 0; b <= NC; b++) aug[(size_t)a * (NC + 1) + b] -= f * aug[(size_t)col * (NC + 1) + b];
+      }
+    }
+    for (int a = 0; a < NC; a++) v[a] = aug[(size_t)a * (NC + 1) + NC];
+  }
+  for (int i = 0; i < C; i++) {
+    zd s(0, 0);
+    for (int j = 0; j < NC; j++) s += Cm[(size_t)i * NC + j] * v[j];
+    wt[i] = s;
+  }
+  return true;
+}
+
+// beamformerWeights::calcMainlobeN, halfBandShift == false (beamformer/beamformer.cc:632-735; calcMainlobe2 :603-623 is
+// NC == 2): distortionless towards delaysT with nulls towards the NC - 1 interferers delaysJ [NC-1][C].
+// ta <- the delay-and-sum weights of the target (what the reference keeps as the array manifold _ta), w <- the
+// quiescent weights.  Restated statement for statement, including the reference's handling of bin M/2 (:722-734): inside
+// the channel loop element c is first rescaled, then overwritten with the LAST interferer's steering value / C, and the
+// null beamformer is re-run on the whole vector after every channel with the interferer vectors left over from bin
+// M/2 - 1.  Only bins 0..M/2 are produced (SubbandDS::next mirrors the rest, :1189-1194).
+inline bool null_weights(const double* delaysT, const double* delaysJ, double fs, int M, int C, int NC, std::vector<zd>& ta,
+                         std::vector<zd>& w) {
+  ds_weights(delaysT, fs, M, C, ta);
+  w = ta;
+  std::vector<zd> pWj((size_t)(NC - 1) * C, zd(0, 0));
+  for (int s = 1; s < M / 2; s++) {
+    zd* vec = &w[(size_t)s * C];
+    for (int c = 0; c < C; c++) {
+      vec[c] *= (double)C;
+      for (int n = 0; n < NC - 1; n++) {
+        const double valJ = -2.0 * M_PI * s * fs * delaysJ[(size_t)n * C + c] / M;
+        pWj[(size_t)n * C + c] = zd(cos(valJ), sin(valJ));
+      }
+    }
+    if (!null_beamformer(vec, pWj.data(), C, NC)) return false;
+  }
+  zd* vec = &w[(size_t)(M / 2) * C];
+  for (int c = 0; c < C; c++) {
+    vec[c] *= (double)C;
+    for (int n = 0; n < NC - 1; n++) {
+      const double val = -M_PI * fs * delaysJ[(size_t)n * C + c];
+      vec[c] = zd(cos(val), sin(val)) / (double)C;
+    }
+    if (!null_beamformer(vec, pWj.data(), C, NC)) return false;
+  }
+  return true;
+}
+
+// Far-field delays of the shipped C++ driver (src/superdirectiveBeamformer.cc:118-137 calcDelaysPolar2): direction
+// cosines, coordinates and the quotient are computed in SINGLE precision there (float locals, SOUNDSPEED 343740.0 mm/s),
+// then widened into the gsl_vector; restated with the same types so the delays agree bit for bit.
+inline void delays_polar2(float azimuth, float elevation, const double* micpos /*[n][3] mm*/, int n, double* delays) {
+  const float c_x = -sinf(elevation) * cosf(azimuth);
+  const float c_y = -sinf(elevation) * sinf(azimuth);
+  const float c_z = -cosf(elevation);
+  for (int i = 0; i < n; i++) {
+    const float x = (float)micpos[3 * i], y = (float)micpos[3 * i + 1], z = (float)micpos[3 * i + 2];
+    const float t = (float)((double)(c_x * x + c_y * y + c_z * z) / 343740.0);
+    delays[i] = t;
+  }
+}
+// calcAllDelays (beamformer/beamformer.cc:1214-1231): distance of every microphone from the ORIGIN over the speed of
+// sound, minus the value of the middle element -- the source position (x, y, z) is accepted and ignored, as in the
+// reference (:1219-1223 never read it).
+inline void all_delays(double /*x*/, double /*y*/, double /*z*/, const double* micpos, int n, double* delays) {
+  for (int c = 0; c < n; c++) {
+    const double xm = micpos[3 * c], ym = micpos[3 * c + 1], zm = micpos[3 * c + 2];
+    delays[c] = sqrt(xm * xm + ym * ym + zm * zm) / 343740.0;
+  }
+  const double mid = delays[n / 2];
+  for (int c = 0; c < n; c++) delays[c] -= mid;
+}
+
 // Hermitian-extended conjugate weight table for the fused chain (see chain_tile.cuh header):
 //   gam[c][k] = conj(w[k][c]) for 0 < k < M/2 ; gam[c][M-k] = w[k][c] ; real part only at k = 0, M/2,
 // stored in the register order of the transform: element ((c*(V/2) + r2)*L + gl)*2 + i holds bin

@@ -16,13 +16,22 @@
 // channels are all OverSampledDFTAnalysisBank nodes runs the whole chain as ONE fused kernel (btkb200_chain).
 // There is no CPU fallback: without a CUDA device the first next() throws j_error with the library's message.
 //
-// Types.  The reference's element containers are gsl_vector_float / gsl_vector_complex / gsl_vector /
-// gsl_matrix(_complex).  GSL is not part of this build, so this header defines containers with the SAME field
-// layout (size, stride, data, block, owner) under the names btk_vector_*; inside the reference tree define
-// BTKB200_WITH_GSL before including it and the gsl types are used directly.
+// Two build modes.
+//   * stand-alone (default): GSL and the reference tree are not needed.  The header defines containers with the SAME
+//     field layout as gsl_vector_float / gsl_vector_complex / gsl_vector / gsl_matrix(_complex) under the names
+//     btk_vector_*, and its own FeatureStream / j_error family / SnapShotArray with the reference's members.
+//   * BTKB200_WITH_BTK: compiled INSIDE the reference tree (include path = btk/ and GSL).  Nothing is re-declared: the
+//     nodes derive from the reference's own FeatureStream<> (stream/stream.h:35-107), are held by its refcountable_ptr
+//     (common/refcount.h:186-285), throw its j_error family (common/jexception.h:41-173), and the beamformer derives from the
+//     reference's ::SubbandDS (beamformer/beamformer.h:159-182), keeping its SnapShotArray and beamformerWeights objects
+//     current -- so a reference node (ZelinskiPostFilter(VectorComplexFeatureStreamPtr&, ...) + setBeamformer(SubbandDSPtr&),
+//     OverSampledDFTSynthesisBank, ...) takes a B200 node and the reverse.  The test tier builds this mode against the
+//     reference's headers and runs mixed chains (tests/host/test_mixed_chain.cc); INTEGRATION.md shows the build line
+//     inside the reference tree.
 #ifndef BTKB200_STREAMS_H
 #define BTKB200_STREAMS_H
 
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -35,9 +44,11 @@
 
 #include "../../include/btkb200.h"
 
-#ifdef BTKB200_WITH_GSL
+#if defined(BTKB200_WITH_BTK)
 #include <gsl/gsl_matrix.h>
 #include <gsl/gsl_vector.h>
+#include "stream/stream.h"
+#include "beamformer/beamformer.h"
 typedef gsl_vector_float btk_vector_float;
 typedef gsl_vector_complex btk_vector_complex;
 typedef gsl_vector btk_vector;
@@ -53,6 +64,24 @@ struct btk_matrix_complex { size_t size1, size2, tda; double* data; void* block;
 
 namespace btkb200 {
 
+#if defined(BTKB200_WITH_BTK)
+// ---- everything below comes from the reference's own headers ---------------------------------------------------
+typedef ::String String;
+using ::j_error;
+using ::jiterator_error;
+using ::jconsistency_error;
+using ::jdimension_error;
+using ::VectorFloatFeatureStream;
+using ::VectorComplexFeatureStream;
+using ::VectorFloatFeatureStreamPtr;
+using ::VectorComplexFeatureStreamPtr;
+using ::SnapShotArray;
+using ::SnapShotArrayPtr;
+using ::beamformerWeights;
+template <class T> struct node_ptr { typedef refcountable_ptr<T> type; };
+template <class T> inline T* pget(const refcountable_ptr<T>& p) { return p.isNull() ? 0 : p.operator->(); }
+template <class T> inline T* pget(const refcount_ptr<T>& p) { return p.isNull() ? 0 : p.operator->(); }
+#else
 typedef std::string String;
 
 // ---- exceptions (common/jexception.h:41-173: code + formatted message) ---------------------------------------
@@ -82,14 +111,6 @@ BTKB200_DEFINE_ERROR(jiterator_error, JITERATOR)       // doubles as end of stre
 BTKB200_DEFINE_ERROR(jconsistency_error, JCONSISTENCY)
 BTKB200_DEFINE_ERROR(jdimension_error, JDIMENSION)
 #undef BTKB200_DEFINE_ERROR
-
-// status of the C ABI -> the exception the reference throws at that point (include/btkb200.h)
-inline void check(int rc, const btkb200_plan* plan) {
-  if (rc == BTKB200_OK) return;
-  const char* msg = btkb200_last_error(plan);
-  if (rc == BTKB200_EINVAL) throw jdimension_error("%s", msg);
-  throw j_error("%s", msg);
-}
 
 // ---- FeatureStream (stream/stream.h:35-75) ------------------------------------------------------------------------
 template <typename Type, typename item_type>
@@ -133,8 +154,43 @@ class VectorComplexFeatureStream : public FeatureStream<btk_vector_complex, doub
  protected:
   VectorComplexFeatureStream(unsigned sz, const String& nm) : FeatureStream<btk_vector_complex, double>(sz, nm, 2) {}
 };
+template <class T> struct node_ptr { typedef std::shared_ptr<T> type; };
+template <class T> inline T* pget(const std::shared_ptr<T>& p) { return p.get(); }
 typedef std::shared_ptr<VectorFloatFeatureStream> VectorFloatFeatureStreamPtr;
 typedef std::shared_ptr<VectorComplexFeatureStream> VectorComplexFeatureStreamPtr;
+#endif
+
+// a vector of n complex values with the gsl_vector_complex field layout
+inline btk_vector_complex* new_cvec(size_t n) {
+  btk_vector_complex* v = new btk_vector_complex();
+  v->size = n; v->stride = 1; v->data = n ? new double[2 * n]() : 0; v->block = 0; v->owner = 0;
+  return v;
+}
+inline void free_cvec(btk_vector_complex* v) { if (v) { delete[] v->data; delete v; } }
+
+// status of the C ABI -> the exception the reference throws at that point (include/btkb200.h)
+inline void check(int rc, const btkb200_plan* plan) {
+  if (rc == BTKB200_OK) return;
+  const char* msg = btkb200_last_error(plan);
+  if (rc == BTKB200_EINVAL) throw jdimension_error("%s", msg);
+  throw j_error("%s", msg);
+}
+
+// ---- G1: delay helpers of the reference's drivers ----------------------------------------------------
+// calcDelaysPolar2 (src/superdirectiveBeamformer.cc:118-137): far-field delays in seconds, micPos [C][3] in mm
+inline void calcDelaysPolar2(float azimuth, float elevation, const btk_matrix* micPos, btk_vector* delays) {
+  std::vector<double> mp(micPos->size1 * 3), d(micPos->size1);
+  for (size_t c = 0; c < micPos->size1; c++) for (int k = 0; k < 3; k++) mp[c * 3 + k] = micPos->data[c * micPos->tda + k];
+  check(btkb200_calc_delays_polar(azimuth, elevation, &mp[0], (unsigned)micPos->size1, &d[0]), 0);
+  for (size_t c = 0; c < d.size(); c++) delays->data[c * delays->stride] = d[c];
+}
+// calcAllDelays (beamformer/beamformer.cc:1214-1231), the ignored source position included
+inline void calcAllDelays(double x, double y, double z, const btk_matrix* mpos, btk_vector* delays) {
+  std::vector<double> mp(mpos->size1 * 3), d(mpos->size1);
+  for (size_t c = 0; c < mpos->size1; c++) for (int k = 0; k < 3; k++) mp[c * 3 + k] = mpos->data[c * mpos->tda + k];
+  check(btkb200_calc_all_delays(x, y, z, &mp[0], (unsigned)mpos->size1, &d[0]), 0);
+  for (size_t c = 0; c < d.size(); c++) delays->data[c * delays->stride] = d[c];
+}
 
 // ---- block source with SampleFeature::next's rule (feature/feature.cc:610-659) ----------------------------------
 class MemorySampleFeature : public VectorFloatFeatureStream {
@@ -234,7 +290,7 @@ class OverSampledDFTAnalysisBank : public OverSampledDFTFilterBank, public Vecto
   // every sample of the source (the analysis bank swallows any exception from it and pads, modulated.cc:493-501)
   void pull_source(std::vector<float>& x) {
     x.clear();
-    MemorySampleFeature* ms = dynamic_cast<MemorySampleFeature*>(_samp.get());
+    MemorySampleFeature* ms = dynamic_cast<MemorySampleFeature*>(pget(_samp));
     if (ms && ms->shiftLen() == _D && ms->padZeros() && ms->frameX() < 0) { x = ms->samples(); return; }
     for (;;) {
       const btk_vector_float* b;
@@ -260,34 +316,218 @@ class OverSampledDFTAnalysisBank : public OverSampledDFTFilterBank, public Vecto
   std::vector<float> _frames;   // [F][B] complex64
   int _F;
 };
-typedef std::shared_ptr<OverSampledDFTAnalysisBank> OverSampledDFTAnalysisBankPtr;
+typedef node_ptr<OverSampledDFTAnalysisBank>::type OverSampledDFTAnalysisBankPtr;
 
 // ---- SubbandBeamformer / SubbandDS / SubbandMVDR ----------------------------------------------------------------
-class SubbandBeamformer : public VectorComplexFeatureStream {
+#if !defined(BTKB200_WITH_BTK)
+// SnapShotArray (beamformer/spectralinfoarray.h:6-31, beamformer.cc:35-113): the current frame of every channel
+// ([C][M], newSample) transposed into per-bin snapshots ([M][C], update / getSnapShot).
+class SnapShotArray {
  public:
-  SubbandBeamformer(unsigned fftLen = 512, bool halfBandShift = false, const String& nm = "SubbandBeamformer")
-      : VectorComplexFeatureStream(fftLen, nm), _fftLen(fftLen), _fftLen2(fftLen / 2), _F(-1) {
-    if (halfBandShift) throw j_error("halfBandShift is not supported by the B200 engine");
-    _snap = new btk_vector_complex(); _snap->size = 0; _snap->stride = 1; _snap->data = 0; _snap->block = 0; _snap->owner = 0;
-    _wvec = new btk_vector_complex(); *_wvec = *_snap;
+  SnapShotArray(unsigned fftLn, unsigned nChn) : _fftLen(fftLn), _nChan(nChn) {
+    _specSamples = new btk_vector_complex*[_nChan];
+    for (unsigned i = 0; i < _nChan; i++) _specSamples[i] = new_cvec(_fftLen);
+    _specSnapShots = new btk_vector_complex*[_fftLen];
+    for (unsigned i = 0; i < _fftLen; i++) _specSnapShots[i] = new_cvec(_nChan);
   }
-  ~SubbandBeamformer() { delete[] _snap->data; delete _snap; delete[] _wvec->data; delete _wvec; }
+  virtual ~SnapShotArray() {
+    for (unsigned i = 0; i < _nChan; i++) free_cvec(_specSamples[i]);
+    delete[] _specSamples;
+    for (unsigned i = 0; i < _fftLen; i++) free_cvec(_specSnapShots[i]);
+    delete[] _specSnapShots;
+  }
+  const btk_vector_complex* getSnapShot(unsigned fbinX) const { return _specSnapShots[fbinX]; }
+  void newSample(const btk_vector_complex* samp, unsigned chanX) const {                        // beamformer.cc:76-80
+    for (unsigned s = 0; s < _fftLen; s++) {
+      _specSamples[chanX]->data[2 * s] = samp->data[2 * s * samp->stride];
+      _specSamples[chanX]->data[2 * s + 1] = samp->data[2 * s * samp->stride + 1];
+    }
+  }
+  // beamformer.cc:99-113, its mirror index (fftLen2 - fbinX, not fftLen - fbinX) included
+  void newSnapShot(const btk_vector_complex* snapshots, unsigned fbinX) {
+    const unsigned fftLen2 = _fftLen / 2;
+    memcpy(_specSnapShots[fbinX]->data, snapshots->data, sizeof(double) * 2 * _nChan);
+    if (fbinX == 0 || fbinX == fftLen2) return;
+    for (unsigned c = 0; c < _nChan; c++) {
+      _specSnapShots[fftLen2 - fbinX]->data[2 * c] = snapshots->data[2 * c * snapshots->stride];
+      _specSnapShots[fftLen2 - fbinX]->data[2 * c + 1] = -snapshots->data[2 * c * snapshots->stride + 1];
+    }
+  }
+  unsigned fftLen() const { return _fftLen; }
+  unsigned nChan() const { return _nChan; }
+  virtual void update() {                                                                       // beamformer.cc:82-90
+    for (unsigned s = 0; s < _fftLen; s++)
+      for (unsigned c = 0; c < _nChan; c++) {
+        _specSnapShots[s]->data[2 * c] = _specSamples[c]->data[2 * s];
+        _specSnapShots[s]->data[2 * c + 1] = _specSamples[c]->data[2 * s + 1];
+      }
+  }
+  virtual void zero() {
+    for (unsigned i = 0; i < _nChan; i++) memset(_specSamples[i]->data, 0, sizeof(double) * 2 * _fftLen);
+    for (unsigned i = 0; i < _fftLen; i++) memset(_specSnapShots[i]->data, 0, sizeof(double) * 2 * _nChan);
+  }
+
+ protected:
+  const unsigned _fftLen, _nChan;
+  mutable btk_vector_complex** _specSamples;
+  mutable btk_vector_complex** _specSnapShots;
+};
+typedef std::shared_ptr<SnapShotArray> SnapShotArrayPtr;
+
+// The accessors of beamformerWeights (beamformer/beamformer.h:49-118) that other nodes read: quiescent weights per bin
+// (full M bins, upper half = conjugate mirror, beamformer.cc:566-574) and the array manifold.
+class beamformerWeights {
+ public:
+  beamformerWeights(unsigned fftLen, unsigned chanN, bool halfBandShift, unsigned NC = 1)
+      : _halfBandShift(halfBandShift), _fftLen(fftLen), _chanN(chanN), _NC(NC) {
+    _wq = new btk_vector_complex*[fftLen]; _ta = new btk_vector_complex*[fftLen];
+    for (unsigned s = 0; s < fftLen; s++) { _wq[s] = new_cvec(chanN); _ta[s] = new_cvec(chanN); }
+  }
+  ~beamformerWeights() {
+    for (unsigned s = 0; s < _fftLen; s++) { free_cvec(_wq[s]); free_cvec(_ta[s]); }
+    delete[] _wq; delete[] _ta;
+  }
+  unsigned NC() { return _NC; }
+  bool isHalfBandShift() { return _halfBandShift; }
+  unsigned fftLen() { return _fftLen; }
+  unsigned chanN() { return _chanN; }
+  btk_vector_complex* wq_f(unsigned fbinX) { return _wq[fbinX]; }
+  btk_vector_complex** wq() { return _wq; }
+  btk_vector_complex** arrayManifold() { return _ta; }
+  // half spectra [B][C] (re, im) -> all M bins
+  void fill(const double* wq_half, const double* ta_half) {
+    for (unsigned s = 0; s <= _fftLen / 2; s++)
+      for (unsigned c = 0; c < _chanN; c++)
+        for (int t = 0; t < 2; t++) {
+          const double* src = (t ? ta_half : wq_half) + ((size_t)s * _chanN + c) * 2;
+          btk_vector_complex** dst = t ? _ta : _wq;
+          dst[s]->data[2 * c] = src[0]; dst[s]->data[2 * c + 1] = src[1];
+          if (s > 0 && s < _fftLen / 2) { dst[_fftLen - s]->data[2 * c] = src[0]; dst[_fftLen - s]->data[2 * c + 1] = -src[1]; }
+        }
+  }
+
+ private:
+  bool _halfBandShift;
+  unsigned _fftLen, _chanN, _NC;
+  btk_vector_complex** _wq;
+  btk_vector_complex** _ta;
+};
+
+// The members of the reference's SubbandBeamformer + SubbandDS that the B200 node builds on
+// (beamformer/beamformer.h:126-182, beamformer.cc:1017-1134): channel list, snapshot array, weight objects.
+class BeamformerCore : public VectorComplexFeatureStream {
+ public:
+  BeamformerCore(unsigned fftLen, bool halfBandShift, const String& nm)
+      : VectorComplexFeatureStream(fftLen, nm), _fftLen(fftLen), _fftLen2(fftLen / 2), _halfBandShift(halfBandShift) {}
+  virtual ~BeamformerCore() { for (size_t i = 0; i < _bfWeightV.size(); i++) delete _bfWeightV[i]; }
   unsigned fftLen() const { return _fftLen; }
   unsigned fftLen2() const { return _fftLen2; }
   unsigned chanN() const { return (unsigned)_channelList.size(); }
   virtual unsigned dim() const { return chanN(); }
+  const btk_vector_complex* snapShotArray_f(unsigned fbinX) { return _snapShotArray->getSnapShot(fbinX); }
+  virtual SnapShotArrayPtr getSnapShotArray() { return _snapShotArray; }
   void setChannel(VectorComplexFeatureStreamPtr& chan) { _channelList.push_back(chan); }
-  virtual void clearChannel() { _channelList.clear(); _plan.reset(); _F = -1; }
-
-  // snapshot of the CURRENT frame at one bin, C complex values (SnapShotArray::getSnapShot)
-  const btk_vector_complex* snapShotArray_f(unsigned fbinX) {
-    if (_F < 0 || _frameX < 0) throw j_error("no snapshot yet");
-    const unsigned C = chanN(), B = _fftLen / 2 + 1;
-    fill(_snap, C);
-    const float* s = &_snapshots[(((size_t)_frameX * B) + fbinX) * C * 2];
-    for (unsigned i = 0; i < 2 * C; i++) _snap->data[i] = s[i];
-    return _snap;
+  virtual void clearChannel() {                                                                 // beamformer.cc:1076-1085
+    _channelList.clear();
+    for (size_t i = 0; i < _bfWeightV.size(); i++) delete _bfWeightV[i];
+    _bfWeightV.clear();
+    _snapShotArray.reset();
   }
+  virtual void reset() {                                                                        // beamformer.cc:1038-1048
+    for (_ChannelIterator it = _channelList.begin(); it != _channelList.end(); ++it) (*it)->reset();
+    if (_snapShotArray) _snapShotArray->zero();
+    VectorComplexFeatureStream::reset();
+  }
+  virtual beamformerWeights* getBeamformerWeightObject(unsigned srcX = 0) { return _bfWeightV[srcX]; }
+
+ protected:
+  typedef std::list<VectorComplexFeatureStreamPtr> _ChannelList;
+  typedef _ChannelList::iterator _ChannelIterator;
+  void _allocImage() { if (!_snapShotArray) _snapShotArray.reset(new SnapShotArray(_fftLen, chanN())); }   // :1123-1127
+  void _allocBFWeight(int nSource, int NC) {                                                              // :1129-1139
+    for (size_t i = 0; i < _bfWeightV.size(); i++) delete _bfWeightV[i];
+    _bfWeightV.resize(nSource);
+    for (size_t i = 0; i < _bfWeightV.size(); i++) _bfWeightV[i] = new beamformerWeights(_fftLen, chanN(), _halfBandShift, NC);
+    _allocImage();
+  }
+  SnapShotArrayPtr _snapShotArray;
+  unsigned _fftLen, _fftLen2;
+  _ChannelList _channelList;
+  bool _halfBandShift;
+  std::vector<beamformerWeights*> _bfWeightV;
+};
+#else
+// inside the reference tree the core IS the reference's SubbandDS: its channel list, its SnapShotArray, its
+// beamformerWeights -- reference nodes that take a SubbandDSPtr (ZelinskiPostFilter::setBeamformer, postfilter.h:95-126)
+// accept the B200 beamformer and read the snapshots / weights it publishes
+typedef ::SubbandDS BeamformerCore;
+#endif
+
+// ---- SpectralMatrixArray (beamformer/spectralinfoarray.h:38-54, beamformer.cc:119-163) -----------------------------
+// Per bin R <- mu R + (1 - mu) x x^T (NO conjugate, :151-159) on every update().  B200 evaluation: update() records the
+// frame, getSpecMatrix() folds everything recorded since the last read on the device in ONE weighted Gram launch
+// (btkb200_covariance, tensor cores; frame f of n pending frames gets the weight (1 - mu) mu^(n-1-f)) and adds mu^n times
+// the previous matrices.  The device works on the half spectrum: bins above M/2 come back as the element-wise conjugate
+// of their mirror bin, which is what Hermitian spectra (an analysis bank's output) give.
+class SpectralMatrixArray : public SnapShotArray {
+ public:
+  SpectralMatrixArray(unsigned fftLn, unsigned nChn, double forgetFact = 0.95)
+      : SnapShotArray(fftLn, nChn), _muB200(forgetFact), _R((size_t)(fftLn / 2 + 1) * nChn * nChn * 2, 0.0) {
+    _mat = new btk_matrix_complex();
+    _mat->size1 = _mat->size2 = _mat->tda = nChn; _mat->block = 0; _mat->owner = 0;
+    _mat->data = new double[2 * (size_t)nChn * nChn]();
+  }
+  virtual ~SpectralMatrixArray() { delete[] _mat->data; delete _mat; }
+  virtual void update() {
+    SnapShotArray::update();
+    const unsigned B = _fftLen / 2 + 1;
+    for (unsigned s = 0; s < B; s++)
+      for (unsigned c = 0; c < _nChan; c++) {
+        _pending.push_back((float)_specSnapShots[s]->data[2 * c * _specSnapShots[s]->stride]);
+        _pending.push_back((float)_specSnapShots[s]->data[2 * c * _specSnapShots[s]->stride + 1]);
+      }
+  }
+  virtual void zero() { SnapShotArray::zero(); _pending.clear(); _R.assign(_R.size(), 0.0); }
+  // valid until the next getSpecMatrix() / update()
+  btk_matrix_complex* getSpecMatrix(unsigned idx) {
+    flush();
+    const unsigned C = _nChan, h = _fftLen / 2;
+    const bool mirror = idx > h;
+    const double* src = &_R[(size_t)(mirror ? _fftLen - idx : idx) * C * C * 2];
+    for (size_t i = 0; i < (size_t)C * C; i++) { _mat->data[2 * i] = src[2 * i]; _mat->data[2 * i + 1] = mirror ? -src[2 * i + 1] : src[2 * i + 1]; }
+    return _mat;
+  }
+
+ private:
+  void flush() {
+    const unsigned B = _fftLen / 2 + 1, C = _nChan;
+    const long n = (long)(_pending.size() / ((size_t)2 * B * C));
+    if (n == 0) return;
+    if (!_plan) _plan.create(_fftLen, 1, 0, 0, C, 0, 0, 1);
+    std::vector<double> wt(n), G(_R.size());
+    for (long f = 0; f < n; f++) wt[f] = (1.0 - _muB200) * pow(_muB200, (double)(n - 1 - f));
+    check(btkb200_covariance(_plan.get(), &_pending[0], n, &wt[0], 0, &G[0]), _plan.get());
+    const double keep = pow(_muB200, (double)n);
+    for (size_t i = 0; i < _R.size(); i++) _R[i] = keep * _R[i] + G[i];
+    _pending.clear();
+  }
+  double _muB200;
+  std::vector<double> _R;          // [B][C][C] (re, im)
+  std::vector<float> _pending;     // [n][B][C] complex64
+  PlanHandle _plan;
+  btk_matrix_complex* _mat;
+};
+
+class SubbandBeamformer : public BeamformerCore {
+ public:
+  SubbandBeamformer(unsigned fftLen = 512, bool halfBandShift = false, const String& nm = "SubbandBeamformer")
+      : BeamformerCore(fftLen, halfBandShift, nm), _F(-1) {
+    if (halfBandShift) throw j_error("halfBandShift is not supported by the B200 engine");
+    _wvec = new_cvec(0);
+    _tmp = new_cvec(fftLen);
+  }
+  ~SubbandBeamformer() { free_cvec(_wvec); free_cvec(_tmp); }
+  virtual void clearChannel() { BeamformerCore::clearChannel(); _plan.reset(); _F = -1; }
 
   virtual const btk_vector_complex* next(int frameX = -5) {
     if (frameX == _frameX && _frameX >= 0) return _vector;
@@ -298,21 +538,18 @@ class SubbandBeamformer : public VectorComplexFeatureStream {
     const float* half = &_Y[(size_t)t * B * 2];
     for (unsigned s = 0; s < B; s++) { _vector->data[2 * s] = half[2 * s]; _vector->data[2 * s + 1] = half[2 * s + 1]; }
     for (unsigned s = 1; s < M / 2; s++) { _vector->data[2 * (M - s)] = half[2 * s]; _vector->data[2 * (M - s) + 1] = -half[2 * s + 1]; }   // :1189-1194
+    publish(t);
     _increment();
     return _vector;
   }
-  virtual void reset() {
-    for (_ChannelIterator it = _channelList.begin(); it != _channelList.end(); ++it) (*it)->reset();
-    VectorComplexFeatureStream::reset();
-    _F = -1;
-  }
+  virtual void reset() { BeamformerCore::reset(); _F = -1; }
 
   // ---- used by OverSampledDFTSynthesisBank for the fused path
-  bool all_own_banks(unsigned& m, unsigned& r, unsigned& dct) const {
+  bool all_own_banks(unsigned& m, unsigned& r, unsigned& dct) {
     if (_channelList.empty()) return false;
     const OverSampledDFTAnalysisBank* a0 = 0;
-    for (_ChannelList::const_iterator it = _channelList.begin(); it != _channelList.end(); ++it) {
-      const OverSampledDFTAnalysisBank* a = dynamic_cast<const OverSampledDFTAnalysisBank*>(it->get());
+    for (_ChannelIterator it = _channelList.begin(); it != _channelList.end(); ++it) {
+      const OverSampledDFTAnalysisBank* a = dynamic_cast<const OverSampledDFTAnalysisBank*>(pget(*it));
       if (!a || a->frameX() >= 0 || a->_M != _fftLen) return false;
       if (!a0) a0 = a;
       if (a->_m != a0->_m || a->_r != a0->_r || a->_dct != a0->_dct) return false;
@@ -320,8 +557,8 @@ class SubbandBeamformer : public VectorComplexFeatureStream {
     m = a0->_m; r = a0->_r; dct = a0->_dct;
     return true;
   }
-  const std::vector<double>& analysis_prototype() const {
-    return dynamic_cast<const OverSampledDFTAnalysisBank*>(_channelList.front().get())->_prototype;
+  const std::vector<double>& analysis_prototype() {
+    return dynamic_cast<const OverSampledDFTAnalysisBank*>(pget(_channelList.front()))->_prototype;
   }
   void interleaved_pcm(std::vector<float>& pcm, long& T) {
     const unsigned C = chanN();
@@ -329,7 +566,7 @@ class SubbandBeamformer : public VectorComplexFeatureStream {
     unsigned c = 0;
     T = 0;
     for (_ChannelIterator it = _channelList.begin(); it != _channelList.end(); ++it, ++c) {
-      dynamic_cast<OverSampledDFTAnalysisBank*>(it->get())->pull_source(xs[c]);
+      dynamic_cast<OverSampledDFTAnalysisBank*>(pget(*it))->pull_source(xs[c]);
       if ((long)xs[c].size() > T) T = (long)xs[c].size();
     }
     pcm.assign((size_t)T * C, 0.f);
@@ -350,11 +587,24 @@ class SubbandBeamformer : public VectorComplexFeatureStream {
   }
 
  protected:
-  typedef std::list<VectorComplexFeatureStreamPtr> _ChannelList;
-  typedef _ChannelList::iterator _ChannelIterator;
-
   static void fill(btk_vector_complex* v, unsigned n) {
     if (v->size != n) { delete[] v->data; v->data = new double[2 * (size_t)n](); v->size = n; }
+  }
+  // the snapshots of frame t go into the SnapShotArray other nodes read (SubbandDS::next: newSample per channel, update,
+  // beamformer.cc:1152-1161)
+  void publish(int t) {
+    SnapShotArray* sa = pget(_snapShotArray);
+    if (!sa || sa->nChan() != chanN()) return;
+    const unsigned C = chanN(), B = _fftLen / 2 + 1, M = _fftLen;
+    for (unsigned c = 0; c < C; c++) {
+      for (unsigned s = 0; s < B; s++) {
+        const float* x = &_snapshots[(((size_t)t * B + s) * C + c) * 2];
+        _tmp->data[2 * s] = x[0]; _tmp->data[2 * s + 1] = x[1];
+        if (s > 0 && s < M / 2) { _tmp->data[2 * (M - s)] = x[0]; _tmp->data[2 * (M - s) + 1] = -x[1]; }
+      }
+      sa->newSample(_tmp, c);
+    }
+    sa->update();
   }
   btkb200_plan* need_plan() {
     const unsigned C = chanN();
@@ -405,13 +655,11 @@ class SubbandBeamformer : public VectorComplexFeatureStream {
     _F = (int)F;
   }
 
-  unsigned _fftLen, _fftLen2;
-  _ChannelList _channelList;
   PlanHandle _plan;
   std::vector<float> _snapshots, _Y;
   int _F;
-  btk_vector_complex* _snap;
   btk_vector_complex* _wvec;
+  btk_vector_complex* _tmp;
 };
 
 class SubbandDS : public SubbandBeamformer {
@@ -425,7 +673,35 @@ class SubbandDS : public SubbandBeamformer {
     std::vector<double> d(delays->size);
     for (size_t i = 0; i < d.size(); i++) d[i] = delays->data[i * delays->stride];
     check(btkb200_set_ds_weights(need_plan(), sampleRate, &d[0], (unsigned)d.size()), _plan.get());
+#if defined(BTKB200_WITH_BTK)
+    BeamformerCore::calcArrayManifoldVectors(sampleRate, delays);     // the reference's own weight object, for its nodes
+#else
+    _allocBFWeight(1, 1);
+    sync_weight_object();
+#endif
     _F = -1;
+  }
+  // beamformer.cc:1100-1121 -> calcMainlobe2 / calcMainlobeN (:603-735): unit gain on the target, nulls on the interferers
+  virtual void calcArrayManifoldVectors2(double sampleRate, const btk_vector* delaysT, const btk_vector* delaysJ) {
+    if (delaysJ->size != chanN())
+      throw jdimension_error("The number of delays for an interference signal does not match number of channels (%d vs. %d).\n",
+                             (int)delaysJ->size, (int)chanN());
+    std::vector<double> dj(delaysJ->size);
+    for (size_t i = 0; i < dj.size(); i++) dj[i] = delaysJ->data[i * delaysJ->stride];
+    null_weights(sampleRate, delaysT, &dj[0], 2);
+#if defined(BTKB200_WITH_BTK)
+    BeamformerCore::calcArrayManifoldVectors2(sampleRate, delaysT, delaysJ);
+#endif
+  }
+  virtual void calcArrayManifoldVectorsN(double sampleRate, const btk_vector* delaysT, const btk_matrix* delaysJ, unsigned NC = 2) {
+    if (NC < 2 || NC > chanN() || delaysJ->size1 + 1 < NC || delaysJ->size2 != chanN())
+      throw jdimension_error("1 < the number of constraints %d <= the number of sensors %d.\n", (int)NC, (int)chanN());
+    std::vector<double> dj((size_t)(NC - 1) * chanN());
+    for (unsigned n = 0; n + 1 < NC; n++) for (unsigned c = 0; c < chanN(); c++) dj[(size_t)n * chanN() + c] = delaysJ->data[n * delaysJ->tda + c];
+    null_weights(sampleRate, delaysT, &dj[0], NC);
+#if defined(BTKB200_WITH_BTK)
+    BeamformerCore::calcArrayManifoldVectorsN(sampleRate, delaysT, delaysJ, NC);
+#endif
   }
   virtual const btk_vector_complex* getWeights(unsigned fbinX) {
     const unsigned C = chanN(), B = _fftLen / 2 + 1;
@@ -435,6 +711,29 @@ class SubbandDS : public SubbandBeamformer {
     memcpy(_wvec->data, &w[(size_t)fbinX * C * 2], sizeof(double) * 2 * C);
     return _wvec;
   }
+
+ protected:
+  void null_weights(double sampleRate, const btk_vector* delaysT, const double* dj, unsigned NC) {
+    if (delaysT->size != chanN())
+      throw jdimension_error("The number of delays does not match number of channels (%d vs. %d).\n", (int)delaysT->size, (int)chanN());
+    std::vector<double> d(delaysT->size);
+    for (size_t i = 0; i < d.size(); i++) d[i] = delaysT->data[i * delaysT->stride];
+    check(btkb200_set_null_weights(need_plan(), sampleRate, &d[0], (unsigned)d.size(), dj, NC), _plan.get());
+#if !defined(BTKB200_WITH_BTK)
+    _allocBFWeight(1, (int)NC);
+    sync_weight_object();
+#endif
+    _F = -1;
+  }
+#if !defined(BTKB200_WITH_BTK)
+  void sync_weight_object() {
+    const unsigned C = chanN(), B = _fftLen / 2 + 1;
+    std::vector<double> wq((size_t)B * C * 2), ta((size_t)B * C * 2);
+    check(btkb200_get_manifold(_plan.get(), &wq[0]), _plan.get());
+    check(btkb200_get_array_manifold(_plan.get(), &ta[0]), _plan.get());
+    _bfWeightV[0]->fill(&wq[0], &ta[0]);
+  }
+#endif
 };
 
 class SubbandMVDR : public SubbandDS {
@@ -478,8 +777,8 @@ class SubbandMVDR : public SubbandDS {
  public:
   const btk_vector_complex* getMVDRWeights(unsigned fbinX) { return getWeights(fbinX); }
 };
-typedef std::shared_ptr<SubbandDS> SubbandDSPtr;
-typedef std::shared_ptr<SubbandMVDR> SubbandMVDRPtr;
+typedef node_ptr<SubbandDS>::type SubbandDSPtr;
+typedef node_ptr<SubbandMVDR>::type SubbandMVDRPtr;
 
 // SubbandGSC with FIXED active weights (beamformer/beamformer.h:186-210, beamformer.cc:1296-1447); the adaptive
 // subclasses (SubbandGSCRLS, ...) are out of scope.  The effective weights wq - B wa are installed before evaluation.
@@ -523,7 +822,7 @@ class SubbandGSC : public SubbandDS {
   bool _normalizeWeight, _dirty;
   btk_matrix_complex* _bm;
 };
-typedef std::shared_ptr<SubbandGSC> SubbandGSCPtr;
+typedef node_ptr<SubbandGSC>::type SubbandGSCPtr;
 
 // ZelinskiPostFilter (postfilter/postfilter.h:95-126, postfilter.cc:340-500): the node both shipped drivers put between the
 // beamformer and the synthesis bank.  `output` must be the SubbandDS / SubbandMVDR also passed to setBeamformer().
@@ -563,8 +862,8 @@ class ZelinskiPostFilter : public VectorComplexFeatureStream {
 
  private:
   void evaluate() {
-    if (!_bf) throw j_error("set beamformer's weights \n");   // postfilter.cc:449-452
-    if (static_cast<VectorComplexFeatureStream*>(_bf.get()) != _samp.get())
+    if (!pget(_bf)) throw j_error("set beamformer's weights \n");   // postfilter.cc:449-452
+    if (static_cast<VectorComplexFeatureStream*>(pget(_bf)) != pget(_samp))
       throw j_error("the B200 post-filter expects its input stream to be the beamformer given to setBeamformer()");
     _bf->post_filter(_alpha, _type, _minFrames, _Y, _W, _F);
   }
@@ -575,7 +874,7 @@ class ZelinskiPostFilter : public VectorComplexFeatureStream {
   std::vector<float> _Y, _W;
   btk_vector_complex* _wp1;
 };
-typedef std::shared_ptr<ZelinskiPostFilter> ZelinskiPostFilterPtr;
+typedef node_ptr<ZelinskiPostFilter>::type ZelinskiPostFilterPtr;
 
 // ---- OverSampledDFTSynthesisBank ---------------------------------------------------------------------------------
 class OverSampledDFTSynthesisBank : public OverSampledDFTFilterBank, public VectorFloatFeatureStream {
@@ -609,7 +908,7 @@ class OverSampledDFTSynthesisBank : public OverSampledDFTFilterBank, public Vect
     return _vector;
   }
   virtual void reset() {
-    if (_samp) _samp->reset();
+    if (pget(_samp)) _samp->reset();
     VectorFloatFeatureStream::reset();
     _nout = -1;
     _pushed.clear();
@@ -620,7 +919,7 @@ class OverSampledDFTSynthesisBank : public OverSampledDFTFilterBank, public Vect
     if (!_plan || _plan.C() != C) _plan.create(_M, _m, _r, _dct, C, h, &_prototype[0], _gain);
   }
   void evaluate() {
-    SubbandBeamformer* bf = dynamic_cast<SubbandBeamformer*>(_samp.get());
+    SubbandBeamformer* bf = dynamic_cast<SubbandBeamformer*>(pget(_samp));
     unsigned m, r, dct;
     if (bf && bf->frameX() < 0 && bf->fftLen() == _M && bf->all_own_banks(m, r, dct) && m == _m && r == _r && dct == _dct) {
       // ---- analysis -> weights -> synthesis as ONE kernel
@@ -692,7 +991,7 @@ class OverSampledDFTSynthesisBank : public OverSampledDFTFilterBank, public Vect
   int _nout;
   bool _fused;
 };
-typedef std::shared_ptr<OverSampledDFTSynthesisBank> OverSampledDFTSynthesisBankPtr;
+typedef node_ptr<OverSampledDFTSynthesisBank>::type OverSampledDFTSynthesisBankPtr;
 
 }  // namespace btkb200
 #endif  // BTKB200_STREAMS_H

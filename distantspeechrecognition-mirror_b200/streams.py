@@ -238,6 +238,93 @@ class OverSampledDFTAnalysisBankPtr(FeatureStream, _FilterBank):
         self._frames = None
 
 
+class SnapShotArrayPtr:
+    """SnapShotArray (beamformer/spectralinfoarray.h:6-31, beamformer.cc:35-113; SWIG shadow beamformer.i:76-103): the
+    current frame of every channel ([C][M], newSample) transposed into per-bin snapshots ([M][C], update/getSnapShot)."""
+
+    def __init__(self, fftLn: int, nChn: int):
+        self._fftLen, self._nChan = int(fftLn), int(nChn)
+        self._samples = np.zeros((self._nChan, self._fftLen), np.complex128)
+        self._snapshots = np.zeros((self._fftLen, self._nChan), np.complex128)
+
+    def fftLen(self):
+        return self._fftLen
+
+    def nChan(self):
+        return self._nChan
+
+    def newSample(self, samp, chanX: int):
+        v = np.asarray(samp, np.complex128).ravel()
+        if v.size != self._fftLen or not 0 <= chanX < self._nChan:
+            raise jdimension_error(f"newSample: {v.size} bins for channel {chanX} of a {self._fftLen} x {self._nChan} array")
+        self._samples[chanX] = v
+
+    def newSnapShot(self, snapshots, fbinX: int):
+        """beamformer.cc:99-113, its mirror index (fftLen2 - fbinX) included."""
+        v = np.asarray(snapshots, np.complex128).ravel()
+        h = self._fftLen // 2
+        self._snapshots[fbinX] = v
+        if fbinX != 0 and fbinX != h:
+            self._snapshots[h - fbinX] = np.conj(v)
+
+    def getSnapShot(self, fbinX: int):
+        return self._snapshots[fbinX]
+
+    def update(self):
+        self._snapshots[:] = self._samples.T
+
+    def zero(self):
+        self._samples[:] = 0
+        self._snapshots[:] = 0
+
+
+class SpectralMatrixArrayPtr(SnapShotArrayPtr):
+    """SpectralMatrixArray (spectralinfoarray.h:38-54, beamformer.cc:119-163; SWIG shadow beamformer.i:105-114): per bin
+    R <- mu R + (1 - mu) x x^T (no conjugate, :151-159) on every update().
+
+    B200 evaluation: update() only records the frame; getSpecMatrix() folds everything recorded since the last read on
+    the device in ONE weighted Gram launch (btkb200_covariance, tensor cores; frame f of n pending gets the weight
+    (1 - mu) mu^(n-1-f)) and adds mu^n times the previous matrices.  The device works on the half spectrum: bins above
+    M/2 are returned as the element-wise conjugate of their mirror, which is what the analysis bank's Hermitian spectra
+    give (for spectra that are not Hermitian the upper bins differ from the reference's)."""
+
+    def __init__(self, fftLn: int, nChn: int, forgetFact: float = 0.95):
+        super().__init__(fftLn, nChn)
+        self._mu = float(forgetFact)
+        self._B = self._fftLen // 2 + 1
+        self._R = np.zeros((self._B, self._nChan, self._nChan), np.complex128)
+        self._pending = []
+        self._plan = None
+
+    def update(self):
+        super().update()
+        self._pending.append(self._snapshots[:self._B].astype(np.complex64))
+
+    def zero(self):
+        super().zero()
+        self._R[:] = 0
+        self._pending = []
+
+    def _flush(self):
+        n = len(self._pending)
+        if n == 0:
+            return
+        if self._plan is None:
+            self._plan = Plan(self._fftLen, 1, 0, self._nChan)
+        wt = (1.0 - self._mu) * self._mu ** np.arange(n - 1, -1, -1, dtype=np.float64)
+        try:
+            G = self._plan.covariance(np.ascontiguousarray(np.stack(self._pending)), wt, conjugate=False)
+        except BtkError as e:
+            _raise(e)
+        self._R = self._mu ** n * self._R + G
+        self._pending = []
+
+    def getSpecMatrix(self, idx: int):
+        self._flush()
+        h = self._fftLen // 2
+        return self._R[idx] if idx <= h else np.conj(self._R[self._fftLen - idx])
+
+
 class _SubbandBeamformer(FeatureStream):
     """SubbandBeamformer: ordered channel list, snapshot array, weight apply (beamformer.cc:1017-1048, 1137-1200)."""
 
@@ -297,6 +384,37 @@ class _SubbandBeamformer(FeatureStream):
         except BtkError as e:
             _raise(e)
         self._weights_changed()
+
+    def calcArrayManifoldVectors2(self, sampleRate: float, delaysT, delaysJ):
+        """beamformer.cc:1100-1104 -> calcMainlobe2 (:603-623): unit gain on the target, a null on one interferer."""
+        self.calcArrayManifoldVectorsN(sampleRate, delaysT, np.atleast_2d(np.asarray(delaysJ, np.float64)), 2)
+
+    def calcArrayManifoldVectorsN(self, sampleRate: float, delaysT, delaysJ, NC: int = 2):
+        """beamformer.cc:1113-1121 -> calcMainlobeN (:632-735); delaysJ is [NC-1][C]."""
+        dT = np.ascontiguousarray(delaysT, np.float64).ravel()
+        dJ = np.atleast_2d(np.asarray(delaysJ, np.float64))
+        C = self.chanN()
+        if NC < 2 or NC > C or dJ.shape[0] < NC - 1:
+            raise jdimension_error(f"1 < the number of constraints {NC} <= the number of sensors {C}.")
+        if dT.size != C or dJ.shape[1] != C:
+            raise jdimension_error(f"The number of delays does not match number of channels ({dT.size} vs. {C}).")
+        try:
+            self._need_plan().set_null_weights(sampleRate, dT, dJ[:NC - 1])
+        except BtkError as e:
+            _raise(e)
+        self._weights_changed()
+
+    def getSnapShotArray(self):
+        """SubbandBeamformer::getSnapShotArray (beamformer.h:141): the snapshots of the current frame, all M bins."""
+        if self._snap is None or self._frameX < 0:
+            raise j_error("no snapshot yet")
+        sa = SnapShotArrayPtr(self._fftLen, self.chanN())
+        half = self._snap[self._frameX].astype(np.complex128)            # [B][C]
+        M = self._fftLen
+        sa._snapshots[:M // 2 + 1] = half
+        sa._snapshots[M // 2 + 1:] = np.conj(half[1:M // 2][::-1])
+        sa._samples[:] = sa._snapshots.T
+        return sa
 
     def _weights_changed(self):
         self._Y = None

@@ -71,12 +71,28 @@ long btkb200_chain_frames(const btkb200_plan* plan, long T);
 /* SubbandDS::calcArrayManifoldVectors -> beamformerWeights::calcMainlobe, halfBandShift=false
  * (beamformer.cc:1087-1091, 531-594).  EINVAL if n_delays != C (jdimension_error, :533-535). */
 int btkb200_set_ds_weights(btkb200_plan* plan, double sample_rate, const double* delays, unsigned n_delays);
+/* SubbandDS::calcArrayManifoldVectors2 / calcArrayManifoldVectorsN -> beamformerWeights::calcMainlobe2 / calcMainlobeN,
+ * halfBandShift=false (beamformer.cc:1100-1121, 603-735, calcNullBeamformer :315-397): unit gain towards delaysT[C], nulls
+ * towards the NC-1 interferers delaysJ[NC-1][C].  EINVAL if n_delays != C or NC outside [2, C] (jdimension_error,
+ * :634-640).  For NC > 2 the reference inverts C^H C with its single-precision SVD; here in double (differs by the
+ * float SVD's rounding). */
+int btkb200_set_null_weights(btkb200_plan* plan, double sample_rate, const double* delaysT, unsigned n_delays,
+                             const double* delaysJ, unsigned NC);
+/* Far-field delays of the shipped drivers, seconds (src/superdirectiveBeamformer.cc:118-137 calcDelaysPolar2; micpos
+ * [n][3] in mm, the direction cosines and the quotient in single precision as there). */
+int btkb200_calc_delays_polar(float azimuth, float elevation, const double* micpos, unsigned n, double* delays);
+/* calcAllDelays (beamformer.cc:1214-1231): |micpos| / c minus the middle element's; the source position is ignored, as in
+ * the reference. */
+int btkb200_calc_all_delays(double x, double y, double z, const double* micpos, unsigned n, double* delays);
 /* Install arbitrary per-bin weights [B][C] (re,im): what SubbandMVDR::next applies (beamformer.cc:2616-2630). */
 int btkb200_set_weights(btkb200_plan* plan, const double* w);
 /* Weights currently applied by beamform/chain ([B][C] re,im): SubbandDS::getWeights / SubbandMVDR::getMVDRWeights. */
 int btkb200_get_weights(const btkb200_plan* plan, double* w);
 /* The delay-and-sum manifold wq ([B][C]) kept beside MVDR weights (beamformerWeights::wq_f). */
 int btkb200_get_manifold(const btkb200_plan* plan, double* w);
+/* The array manifold ([B][C]): the target's delay-and-sum vector that beamformerWeights keeps as _ta (beamformer.cc:583,
+ * 992-997) and the post-filter time-aligns with; differs from the quiescent weights only after btkb200_set_null_weights. */
+int btkb200_get_array_manifold(const btkb200_plan* plan, double* w);
 
 /* ---- MVDR --------------------------------------------------------------------------------------------- */
 /* SubbandMVDR::setNoiseSpatialSpectralMatrix (beamformer.cc:2454-2477); EINVAL on a shape mismatch (the

@@ -261,6 +261,69 @@ def farfield_delays(micpos_mm: np.ndarray, azimuth: float, elevation: float, ssp
 
 
 # --------------------------------------------------------------------------- whole chain
+def delays_polar2(azimuth: float, elevation: float, micpos_mm: np.ndarray) -> np.ndarray:
+    """calcDelaysPolar2 of the shipped driver (src/superdirectiveBeamformer.cc:118-137): the direction cosines, the
+    coordinates and the sum are float32 there, the quotient by SOUNDSPEED is taken in double and rounded to float32."""
+    f = np.float32
+    az, el = f(azimuth), f(elevation)
+    c = (-(np.sin(el) * np.cos(az)).astype(f), -(np.sin(el) * np.sin(az)).astype(f), (-np.cos(el)).astype(f))
+    mp = np.asarray(micpos_mm, dtype=np.float64).astype(f)
+    s = (c[0] * mp[:, 0]).astype(f)
+    s = (s + (c[1] * mp[:, 1]).astype(f)).astype(f)
+    s = (s + (c[2] * mp[:, 2]).astype(f)).astype(f)
+    return (s.astype(np.float64) / SSPEED).astype(f).astype(np.float64)
+
+
+def all_delays(micpos_mm: np.ndarray) -> np.ndarray:
+    """calcAllDelays (beamformer.cc:1214-1231): |position| / c minus the middle element's; its x, y, z arguments are
+    never read (:1219-1223)."""
+    mp = np.asarray(micpos_mm, dtype=np.float64)
+    d = np.sqrt((mp[:, :3] ** 2).sum(1)) / SSPEED
+    return d - d[mp.shape[0] // 2]
+
+
+def _null_beamformer(wt: np.ndarray, pWj: np.ndarray) -> np.ndarray:
+    """calcNullBeamformer (beamformer.cc:315-397): wt <- Cm (Cm^H Cm)^-1 e0, Cm = [wt | pWj...]; NC = 2 through
+    putInverseMat22 (:202-242), larger NC through a double-precision inverse (the reference: float SVD pseudoinverse)."""
+    Cm = np.column_stack([wt] + [pWj[n] for n in range(pWj.shape[0])])
+    A = Cm.conj().T @ Cm
+    if Cm.shape[1] == 2:
+        m00, m01, m10, m11 = A[0, 0], A[0, 1], A[1, 0], A[1, 1]
+        det = m00 * m11 - m01 * m10
+        if abs(det) < 1.0e-7:
+            m00, m11 = m00 + 0.01, m11 + 0.01
+            det = m00 * m11 - m01 * m10
+        v = np.array([m11 / det, -(m10 / det)])
+    else:
+        v = np.linalg.inv(A)[:, 0]
+    return Cm @ v
+
+
+def null_weights(delaysT: np.ndarray, delaysJ: np.ndarray, fs: float, M: int):
+    """beamformerWeights::calcMainlobeN, halfBandShift = False (beamformer.cc:632-735): (quiescent weights, array manifold),
+    both [B][C].  Statement for statement, the bin-M/2 loop (:722-734) included: element c is overwritten with the last
+    interferer's steering value / C and the null beamformer re-run after EVERY channel, with the interferer vectors of
+    bin M/2 - 1."""
+    delaysT = np.asarray(delaysT, dtype=np.float64)
+    dJ = np.atleast_2d(np.asarray(delaysJ, dtype=np.float64))
+    C = delaysT.shape[0]
+    ta = ds_weights(delaysT, fs, M)
+    w = ta.copy()
+    pWj = np.zeros((dJ.shape[0], C), dtype=np.complex128)
+    for s in range(1, M // 2):
+        vec = w[s] * C
+        pWj = np.exp(1j * (-2.0 * np.pi * s * fs * dJ / M))
+        w[s] = _null_beamformer(vec, pWj)
+    vec = w[M // 2].copy()
+    for c in range(C):
+        vec[c] = vec[c] * C
+        for n in range(dJ.shape[0]):
+            vec[c] = np.exp(1j * (-np.pi * fs * dJ[n, c])) / C
+        vec = _null_beamformer(vec, pWj)
+    w[M // 2] = vec
+    return w, ta
+
+
 def chain(pcm: np.ndarray, h: np.ndarray, g: np.ndarray, geo: BankGeometry, W: np.ndarray, gain: int = 1):
     """analysis (per channel) -> beamform with weights W [B][C] -> synthesis.
     pcm: [T][C] float32.  Returns (X [F][C][M], Y [F][M], out float32 [nblk*D])."""
@@ -475,6 +538,13 @@ class CompiledReference:
         L.btkref_spectral_matrix.argtypes = [vp, cl, ci, vp, ci, ci, ci, ci, cd, vp]
         L.btkref_error_probe.restype = ci
         L.btkref_error_probe.argtypes = [ci]
+        if hasattr(L, "btkref_null_weights"):
+            L.btkref_null_weights.restype = ci
+            L.btkref_null_weights.argtypes = [cd, vp, vp, ci, ci, ci, vp, vp]
+            L.btkref_calc_all_delays.restype = ci
+            L.btkref_calc_all_delays.argtypes = [cd, cd, cd, vp, ci, vp]
+            L.btkref_calc_delays_polar2.restype = ci
+            L.btkref_calc_delays_polar2.argtypes = [ctypes.c_float, ctypes.c_float, vp, ci, vp]
 
     @staticmethod
     def available(path: str | None = None) -> bool:
@@ -604,6 +674,30 @@ class CompiledReference:
         if n < 0:
             raise RuntimeError(f"btkref_spectral_matrix returned {n}")
         return R.view(np.complex128)[..., 0]
+
+    def null_weights(self, delaysT, delaysJ, fs: float, M: int):
+        """SubbandDS::calcArrayManifoldVectors2 / N of the compiled reference: (wq [B][C], array manifold [B][C])."""
+        dT = np.ascontiguousarray(delaysT, dtype=np.float64)
+        dJ = np.ascontiguousarray(np.atleast_2d(delaysJ), dtype=np.float64)
+        C, NC, B = dT.shape[0], dJ.shape[0] + 1, M // 2 + 1
+        w = np.zeros((B, C), dtype=np.complex128)
+        ta = np.zeros((B, C), dtype=np.complex128)
+        rc = self.lib.btkref_null_weights(fs, _dp(dT), _dp(dJ), M, C, NC, _dp(w), _dp(ta))
+        if rc != 0:
+            raise RuntimeError("btkref_null_weights failed")
+        return w, ta
+
+    def all_delays(self, micpos, x=0.0, y=0.0, z=0.0) -> np.ndarray:
+        mp = np.ascontiguousarray(micpos, dtype=np.float64)
+        d = np.zeros(mp.shape[0], dtype=np.float64)
+        self.lib.btkref_calc_all_delays(x, y, z, _dp(mp), mp.shape[0], _dp(d))
+        return d
+
+    def delays_polar2(self, azimuth, elevation, micpos) -> np.ndarray:
+        mp = np.ascontiguousarray(micpos, dtype=np.float64)
+        d = np.zeros(mp.shape[0], dtype=np.float64)
+        self.lib.btkref_calc_delays_polar2(azimuth, elevation, _dp(mp), mp.shape[0], _dp(d))
+        return d
 
     def error_probe(self, which: int) -> int:
         return int(self.lib.btkref_error_probe(which))

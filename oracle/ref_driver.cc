@@ -584,4 +584,63 @@ int btkref_error_probe(int which) {
   return -1;
 }
 
+// Quiescent weights of SubbandDS::calcArrayManifoldVectorsN (beamformer.cc:1113-1121 -> calcMainlobeN :632-735) for bins
+// 0..M/2, and the array manifold the weight object keeps next to them.  delaysJ: [NC-1][C].  w, ta: [M/2+1][C][2].
+int btkref_null_weights(double fs, const double* delaysT, const double* delaysJ, int M, int C, int NC, double* w, double* ta) {
+  try {
+    SubbandDS bf(M, false);
+    static double none = 0;
+    for (int c = 0; c < C; c++) {
+      VectorComplexFeatureStreamPtr ch(new MemoryComplexFeature(&none, 0, M));
+      bf.setChannel(ch);
+    }
+    gsl_vector* dT = make_vector(delaysT, C);
+    gsl_matrix* dJ = gsl_matrix_alloc(NC - 1, C);
+    for (int n = 0; n < NC - 1; n++) for (int c = 0; c < C; c++) gsl_matrix_set(dJ, n, c, delaysJ[(size_t)n * C + c]);
+    if (NC == 2) {
+      gsl_vector* dj = make_vector(delaysJ, C);
+      bf.calcArrayManifoldVectors2(fs, dT, dj);
+      gsl_vector_free(dj);
+    } else {
+      bf.calcArrayManifoldVectorsN(fs, dT, dJ, NC);
+    }
+    beamformerWeights* bw = bf.getBeamformerWeightObject(0);
+    for (int s = 0; s <= M / 2; s++)
+      for (int c = 0; c < C; c++) {
+        gsl_complex z = gsl_vector_complex_get(bw->wq_f(s), c), t = gsl_vector_complex_get(bw->arrayManifold()[s], c);
+        w[2 * ((size_t)s * C + c)] = GSL_REAL(z); w[2 * ((size_t)s * C + c) + 1] = GSL_IMAG(z);
+        ta[2 * ((size_t)s * C + c)] = GSL_REAL(t); ta[2 * ((size_t)s * C + c) + 1] = GSL_IMAG(t);
+      }
+    gsl_vector_free(dT); gsl_matrix_free(dJ);
+    return 0;
+  } catch (std::exception& e) { fprintf(stderr, "btkref_null_weights: %s\n", e.what()); return -1; }
+}
+
+// calcAllDelays (beamformer.cc:1214-1231) as compiled from the reference.
+int btkref_calc_all_delays(double x, double y, double z, const double* micpos, int n, double* delays) {
+  gsl_matrix* mp = gsl_matrix_alloc(n, 3);
+  for (int c = 0; c < n; c++) for (int k = 0; k < 3; k++) gsl_matrix_set(mp, c, k, micpos[3 * c + k]);
+  gsl_vector* d = gsl_vector_alloc(n);
+  calcAllDelays(x, y, z, mp, d);
+  for (int c = 0; c < n; c++) delays[c] = gsl_vector_get(d, c);
+  gsl_vector_free(d); gsl_matrix_free(mp);
+  return 0;
+}
+
+// calcDelaysPolar2 lives in a driver translation unit with a main() (src/superdirectiveBeamformer.cc:118-137); oracle/Makefile
+// extracts exactly those lines (and the SOUNDSPEED definition, :14) from the reference source into
+// _ref/obj/calc_delays_polar2.inc at build time, so the function below is the reference's text, compiled -- not a copy kept
+// in this repository.
+}  // extern "C"
+#include "calc_delays_polar2.inc"
+extern "C" {
+int btkref_calc_delays_polar2(float azimuth, float elevation, const double* micpos, int n, double* delays) {
+  gsl_matrix* mp = gsl_matrix_alloc(n, 3);
+  for (int c = 0; c < n; c++) for (int k = 0; k < 3; k++) gsl_matrix_set(mp, c, k, micpos[3 * c + k]);
+  gsl_vector* d = calcDelaysPolar2(azimuth, elevation, mp);
+  for (int c = 0; c < n; c++) delays[c] = gsl_vector_get(d, c);
+  gsl_vector_free(d); gsl_matrix_free(mp);
+  return 0;
+}
+
 }  // extern "C"

@@ -6,6 +6,10 @@
 //   test_streams chain <in.bin> <out.bin>    DS (mode 0) or MVDR (mode 1) chain through the stream nodes;
 //                                            mode 2: DS -> ZelinskiPostFilter -> synthesis (src/beamformerDS.cc:150-190);
 //                                            mode 3: SubbandGSC with fixed active weights wa[s][k] = 0.05 (cos(s+k) + j sin(2s-k))
+//                                            mode 4: null-steering DS (calcArrayManifoldVectors2, interferer delays = reversed
+//                                                    target delays) -> frames pulled one by one, every frame's snapshots
+//                                                    (getSnapShotArray) folded into a SpectralMatrixArray (mu 0.95), read
+//                                                    after 10 frames and at the end; writes Y[4], R[M][C][C], w[B][C]
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -81,7 +85,7 @@ int main(int argc, char** argv) {
         gsc->setActiveWeights_f(s, &pv);
       }
       if (gsc->getBlockingMatrix(0, 1)->size2 != (size_t)C - 1) return 3;
-    } else {
+    } else if (mode != 4) {
       bf->calcArrayManifoldVectors(fs, &tv);
     }
     if (mode == 2 || mode == 3) {
@@ -107,6 +111,46 @@ int main(int argc, char** argv) {
       fwrite(out.data(), 4, out.size(), o);
       fclose(o);
       printf("chain ok: %zu samples, mode=%d\n", out.size(), mode);
+      return 0;
+    }
+    if (mode == 4) {
+      std::vector<double> tj(tau.rbegin(), tau.rend());
+      btk_vector jv = make_vec(tj);
+      bf->calcArrayManifoldVectors2(fs, &tv, &jv);
+      beamformerWeights* bw = bf->getBeamformerWeightObject(0);
+      if (bw->fftLen() != (unsigned)M || bw->chanN() != (unsigned)C || bw->NC() != 2) return 3;
+      SpectralMatrixArray sma(M, C, 0.95);
+      sma.zero();
+      std::vector<double> Y, R, W;
+      int n = 0;
+      for (;;) {
+        const btk_vector_complex* y;
+        try { y = bf->next(); } catch (jiterator_error&) { break; }
+        if (n < 4) Y.insert(Y.end(), y->data, y->data + 2 * M);
+        SnapShotArrayPtr sa = bf->getSnapShotArray();
+        // the per-bin snapshots the node publishes agree with snapShotArray_f (beamformer.h:140-141)
+        if (sa->getSnapShot(3)->data[0] != bf->snapShotArray_f(3)->data[0]) return 4;
+        // feed the spectral matrix array channel by channel, as the reference's users do (newSample per channel, then update)
+        std::vector<double> col(2 * (size_t)M);
+        btk_vector_complex cv; cv.size = M; cv.stride = 1; cv.data = col.data(); cv.block = 0; cv.owner = 0;
+        for (int c = 0; c < C; c++) {
+          for (int s = 0; s < M; s++) { col[2 * s] = sa->getSnapShot(s)->data[2 * c]; col[2 * s + 1] = sa->getSnapShot(s)->data[2 * c + 1]; }
+          sma.newSample(&cv, c);
+        }
+        sma.update();
+        n++;
+        if (n == 10) sma.getSpecMatrix(1);          // an intermediate read: the recursion continues from the folded state
+      }
+      for (int s = 0; s < M; s++) { const btk_matrix_complex* Rm = sma.getSpecMatrix(s); R.insert(R.end(), Rm->data, Rm->data + 2 * (size_t)C * C); }
+      for (int s = 0; s <= M / 2; s++) { const btk_vector_complex* w = bf->getWeights(s); W.insert(W.end(), w->data, w->data + 2 * C); }
+      FILE* o = fopen(argv[3], "wb");
+      int oh[4] = {n, (int)Y.size(), (int)R.size(), (int)W.size()};
+      fwrite(oh, sizeof(int), 4, o);
+      fwrite(Y.data(), 8, Y.size(), o);
+      fwrite(R.data(), 8, R.size(), o);
+      fwrite(W.data(), 8, W.size(), o);
+      fclose(o);
+      printf("arrays ok: %d frames\n", n);
       return 0;
     }
     if (mode == 1) {
