@@ -444,6 +444,70 @@ __global__ void __launch_bounds__(256) btk_mvdr_solve_kernel(const double2* __re
     }
     __syncthreads();
   }
+  // ---- the reference's rejection rule (pseudoinverse, beamformer.cc:275-283): ANY singular value below dThreshold makes the
+  // inverse "fail" and the caller falls back to the identity (:2425-2427).  A pivot is not a singular value, so
+  // the smallest singular value is estimated from the triangular factor: A = P^T L U with |L_ij| <= 1, hence
+  // sigma_min(A) ~ sigma_min(U) up to the (modest) conditioning of L, and sigma_min(U) = 1 / sqrt(lambda_max((U^H U)^-1)) comes
+  // from four steps of inverse iteration -- two triangular solves each, inside warp 0, rows of U read along the lanes.
+  // Where sigma_min sits within a factor of a few of the threshold the reference's own answer is rounding noise of its
+  // single-precision SVD; away from it the two rules agree (tests/test_mvdr_fallback.py, against the compiled reference).
+  if (!bad && warp == 0 && dThreshold > 0.0) {
+    double2 x[4];
+    double nrm2 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int i = lane + 32 * q;
+      x[q] = i < C ? make_double2((i & 1) ? -1.0 - (double)i / C : 1.0 + (double)i / C, 0.0) : make_double2(0.0, 0.0);
+      nrm2 += x[q].x * x[q].x;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nrm2 += shfl_d(nrm2, lane ^ o);
+    double lam = 0.0;
+    for (int it = 0; it < 4; it++) {
+      const double sc = rsqrt(nrm2);
+#pragma unroll
+      for (int q = 0; q < 4; q++) { x[q].x *= sc; x[q].y *= sc; }
+      // forward substitution with U^H (lower triangular, (U^H)_ir = conj(U_ri)): y_r = x_r / conj(U_rr); x_i -= conj(U_ri) y_r
+      for (int r = 0; r < C; r++) {
+        double2 yr = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int q = 0; q < 4; q++) if ((r >> 5) == q && lane == (r & 31)) { const double2 u = A[r * ld + r]; yr = zdiv(x[q], make_double2(u.x, -u.y)); }
+        yr.x = shfl_d(yr.x, r & 31); yr.y = shfl_d(yr.y, r & 31);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int i = lane + 32 * q;
+          if (i > r && i < C) { const double2 u = A[r * ld + i]; const double2 t = zmul(make_double2(u.x, -u.y), yr); x[q].x -= t.x; x[q].y -= t.y; }
+          if (i == r) x[q] = yr;
+        }
+      }
+      // back substitution with U
+      for (int r = C - 1; r >= 0; r--) {
+        double2 zr = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int q = 0; q < 4; q++) if ((r >> 5) == q && lane == (r & 31)) zr = zdiv(x[q], A[r * ld + r]);
+        zr.x = shfl_d(zr.x, r & 31); zr.y = shfl_d(zr.y, r & 31);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int i = lane + 32 * q;
+          if (i < r) { const double2 t = zmul(A[i * ld + r], zr); x[q].x -= t.x; x[q].y -= t.y; }
+          if (i == r) x[q] = zr;
+        }
+      }
+      nrm2 = 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; q++) nrm2 += x[q].x * x[q].x + x[q].y * x[q].y;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) nrm2 += shfl_d(nrm2, lane ^ o);
+      lam = sqrt(nrm2);                               // ||(U^H U)^-1 x||, x of unit length -> lambda_max estimate (from below)
+      if (!isfinite(lam)) break;
+    }
+    // sigma_min(U) ~ 1 / sqrt(lam)
+    if (!isfinite(lam) || !(lam * dThreshold * dThreshold < 1.0)) s_bidx[0] = -1; else s_bidx[0] = 0;
+  }
+  if (!bad && dThreshold > 0.0) {
+    __syncthreads();
+    if (s_bidx[0] < 0) bad = true;
+  }
   if (bad) {
     // identity fallback (beamformer.cc:2425-2427): t = d
     __syncthreads();
