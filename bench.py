@@ -316,10 +316,11 @@ def measure(wl_cfg, mode, nb, args, rank, world, local_rank, dev, config_id, ste
             dist.barrier()
         torch.cuda.synchronize()
 
-    # this rank's shard: a few distinct signals, reused round-robin
+    # this rank's shard of the job's world * nb utterances (round-robin ownership, btk_b200.sharding -- the same rule
+    # btkb200_chain_batch_multi applies inside one process); a few distinct signals of it, reused round-robin
     distinct = min(nb, 4)
-    first = rank * nb
-    base = [make_recording(wl_cfg, tau, first + i, config_id) for i in range(distinct)]
+    mine = btk_b200.sharding.shard(world * nb, rank, world)
+    base = [make_recording(wl_cfg, tau, mine[i], config_id) for i in range(distinct)]
     n_host = nb if full_host_inputs else distinct
     h_in = torch.empty((n_host, n_in), dtype=torch.float32, pin_memory=True)
     for i in range(n_host):

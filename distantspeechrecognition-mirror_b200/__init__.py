@@ -5,7 +5,7 @@ reference's stream API.
 The directory name carries a hyphen (it mirrors the upstream repository name); import it through the
 ``btk_b200`` shim at the repository root:  ``import btk_b200``.
 """
-from . import _capi, streams, workloads  # noqa: F401
+from . import _capi, sharding, streams, workloads  # noqa: F401
 from ._capi import (BtkError, Plan, calc_all_delays, calc_delays_polar, design_analysis_prototype,  # noqa: F401
                     design_synthesis_prototype, device_count, lib)
 from .streams import (OverSampledDFTAnalysisBankPtr, OverSampledDFTSynthesisBankPtr, SampleFeaturePtr,  # noqa: F401

@@ -1014,6 +1014,11 @@ int btkb200_synthesis(btkb200_plan* p, const float* Y, long F, float* out, long*
 int btkb200_covariance(btkb200_plan* p, const float* snap, long F, const double* frame_weights, int conjugate, double* R) {
   if (!p || !snap || !frame_weights || !R || F < 0) return BTKB200_EINVAL;
   if (p->C > 64) return fail(p, BTKB200_EUNSUPPORTED, "covariance supports at most 64 channels (got %d)", p->C);
+  // the tensor-core kernel scales the rows by sqrt(weight): a negative or non-finite weight has no such factor (the
+  // recursions of the reference only ever produce weights in [0, 1])
+  for (long f = 0; f < F; f++)
+    if (!(frame_weights[f] >= 0.0) || !std::isfinite(frame_weights[f]))
+      return fail(p, BTKB200_EINVAL, "frame weight %ld is negative or not finite (%g)", f, frame_weights[f]);
   CK(p, cudaSetDevice(p->device));
   const int B = p->geo.B, C = p->C;
   const size_t bsnap = (size_t)F * B * C * sizeof(cf), bw = (size_t)F * sizeof(double), bR = (size_t)B * C * C * sizeof(double2);

@@ -732,7 +732,8 @@ BTK_HD void chain_tile(Ctx& ctx, const ChainParams& p, unsigned char* smem, int 
   const int C = p.C;
   const int a_start = wk.j0 + p.pd_s - H;                   // first analysis frame this chunk computes
   const int n_it = (wk.nj + H + K::W - 1) / K::W;
-  const bool vec4 = (C % 4 == 0) && (rec.pcm_off % 4 == 0);
+  // 16-byte loads need the caller's base pointer aligned as well (an offset device view is legal input: scalar path)
+  const bool vec4 = (C % 4 == 0) && (rec.pcm_off % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.pcm) & 15) == 0);
 
   load_tables<K>(ctx, L, smem, p.taps_h, p.twa, p.twb);
   ctx.par([&](int tid, TS&) {

@@ -320,7 +320,11 @@ BTK_HD void chain_ws_compute(Ctx& ctx, const ChainParams& p, unsigned char* smem
         float4* dst = reinterpret_cast<float4*>(stage + S.wts_off);
         for (int i = 0; i < K::CG * M_ / 2; i++) dst[i] = src[i];
       });
+#ifdef BTK_EXP_NOCOMPUTE    // experiment: the producer side alone (no transforms; results are garbage)
+      for (int round = 0; round < 0; round++) {
+#else
       for (int round = 0; round < K::CG / K::NG; round++) {
+#endif
         analysis_round<K>(ctx, L, s_xs, s_taps, s_xbuf, s_twa, s_twb, m, round);
         ctx.par([&](int tid, TS& ts) {
           const int lane = tid & 31, grp = lane / G::L, gl = lane % G::L;

@@ -301,7 +301,9 @@ cudaError_t launch_covariance_tc(const cf* snap, const double* wt, double2* Rout
   const int cap = (int)((F + 63) / 64);
   if (split > cap) split = cap;
   if (split < 1) split = 1;
-  if (split > 64) split = 64;
+  // (no upper cap other than the grid limit: F > 131072 frames must still be cut into slices of at most 2048 frames, the
+  // documented FP32 accumulation span; the slices are merged with fp64 atomics)
+  if (split > 65535) split = 65535;
   if (const char* e = getenv("BTK_COV_SPLIT")) { const int v = atoi(e); if (v >= 1 && v <= 64) split = v; }   // tuning knob (A/B runs)
   const int smem = COV_TC_SMEM;
   cudaError_t e = cudaFuncSetAttribute(btk_covariance_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -199,7 +199,9 @@ __global__ void __launch_bounds__(WsCfg<M, R, MT, PP>::NT + WsCfg<M, R, MT, PP>:
           mbar_expect_tx(bars + WS_BAR_FULL + st, K::CG * M * 8);
           bulk_g2s(stage + S.wts_off, wts + (long long)cg0 * M, K::CG * M * 8, bars + WS_BAR_FULL + st);
         }
+#ifndef BTK_EXP_NOFILL      // experiment: the compute side alone (stages handed over unfilled; results are garbage)
         ws_fill_thread<K, WsProd<M, K::NT, K::LV>::TB>(ptid, L, reinterpret_cast<float*>(stage), pcm, p.C, rec.T, t_lo, cg0, vec4);
+#endif
         mbar_arrive(bars + WS_BAR_FULL + st);
       }
     }

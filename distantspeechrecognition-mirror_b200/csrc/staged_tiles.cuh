@@ -47,7 +47,7 @@ BTK_HD void analysis_tile(Ctx& ctx, const AnalysisParams& p, unsigned char* smem
   cf* snap = p.snap + rec.out_off;
   const int C = p.C, F = rec.nblk;
   const int n_it = (wk.nj + K::W - 1) / K::W;
-  const bool vec4 = (C % 4 == 0) && (rec.pcm_off % 4 == 0);
+  const bool vec4 = (C % 4 == 0) && (rec.pcm_off % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.pcm) & 15) == 0);
 
   load_tables<K>(ctx, L, smem, p.taps_h, p.twa, p.twb);
   ctx.sync();

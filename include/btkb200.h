@@ -125,7 +125,7 @@ int btkb200_beamform(btkb200_plan* plan, const float* snap, long F, float* Y);
 int btkb200_synthesis(btkb200_plan* plan, const float* Y, long F, float* out, long* n_out_frames);
 /* Weighted Gram matrices R[s] = sum_f wt[f] x_f x_f^H (conjugate != 0; lib/subbandBeamforming.py:1170-1175)
  * or x_f x_f^T (conjugate == 0; SpectralMatrixArray::update, beamformer.cc:142-163) for bins 0..M/2.
- * R: [B][C][C] complex128. */
+ * R: [B][C][C] complex128.  EINVAL for a negative or non-finite frame weight. */
 int btkb200_covariance(btkb200_plan* plan, const float* snap, long F, const double* frame_weights, int conjugate,
                        double* R);
 
@@ -230,7 +230,10 @@ int btkb200_chain_batch_multi(btkb200_plan* const* plans, int n_plans, const flo
                               float* const* out);
 
 /* ---- device-resident variants (pointers are DEVICE pointers on the plan's device; stream is a cudaStream_t
- *      passed as void*, NULL = the legacy default stream).  Asynchronous: return after enqueueing. -------- */
+ *      passed as void*, NULL = the legacy default stream).  They return after enqueueing the kernels; the descriptor
+ *      upload before a batch launch waits for earlier work on `stream`.  One stream per plan: the plan owns the
+ *      descriptor and scratch buffers a launch reads, so two streams must not drive the same plan concurrently.
+ *      d_pcm need not be 16-byte aligned (an offset view takes the scalar load path). -------- */
 int btkb200_chain_batch_dev(btkb200_plan* plan, const float* d_pcm, const long long* pcm_off, const long long* T,
                             const long long* out_off, int n, float* d_out, void* stream);
 int btkb200_analysis_dev(btkb200_plan* plan, const float* d_pcm, long T, float* d_snap, void* stream);

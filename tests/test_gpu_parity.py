@@ -305,3 +305,33 @@ def test_large_batch_chunk_model_matches_single_recording_calls(prototypes):
     W = bo.ds_weights(tau, FS, M)
     assert bo.snr_db(outs[5], bo.chain(pcms[5], h, g, geo, W)[2]) >= TOL_SNR
     plan.close()
+
+
+def test_chain_batch_multi_plans(prototypes):
+    """btkb200_chain_batch_multi (the C ABI's multi-GPU entry): recordings round-robin over the plans, one host
+    thread per plan, no inter-GPU traffic.  One plan per device on every visible device (two plans on device 0 when the
+    box has a single GPU, which still drives the threaded path); ragged lengths; each output against the oracle and
+    against the single-plan batch call."""
+    M, m, r, C = 256, 4, 1, 4
+    h, g = proto(prototypes, M, m, r)
+    geo = bo.BankGeometry(M, m, r, 0)
+    tau = wl.farfield_delays(wl.linear_array(C, 41.0), np.deg2rad(30), np.deg2rad(90))
+    ndev = btk_b200.device_count()
+    devs = list(range(ndev)) if ndev >= 2 else [0, 0]
+    plans = [btk_b200.Plan(M, m, r, C, h, g, device=d) for d in devs]
+    for p in plans:
+        p.set_ds_weights(FS, tau)
+    Ts = [5000, 8000, 3001, 6400, 129, 7000, 4096]
+    xs = [np.ascontiguousarray(wl.array_recording(T, tau, seed=40 + i)) for i, T in enumerate(Ts)]
+    outs = [np.zeros(geo.nblk(T) * geo.D, np.float32) for T in Ts]
+    btk_b200._capi.chain_batch_multi(plans, xs, outs)
+    single = plans[0].chain_batch(xs)
+    W = bo.ds_weights(tau, FS, M)
+    for i, x in enumerate(xs):
+        assert np.array_equal(outs[i], single[i])                 # the same kernel on the same data, whatever the device
+        assert bo.snr_db(outs[i], bo.chain(x, h, g, geo, W)[2]) >= TOL_SNR
+    # ownership is the round-robin rule of btk_b200.sharding
+    for d in range(len(plans)):
+        assert btk_b200.sharding.shard(len(xs), d, len(plans)) == [i for i in range(len(xs)) if i % len(plans) == d]
+    for p in plans:
+        p.close()
