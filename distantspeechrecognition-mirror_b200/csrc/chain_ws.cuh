@@ -136,28 +136,32 @@ struct WsWalk {
 
 // One producer thread's share of a stage: CG channels [cg0, cg0 + CG) of the window starting at sample t_lo,
 // pcm [t][C] -> s_xs[c][t mod D][t div D] (residue-major, see chain_tile.cuh::stage_window for the layout and the
-// register transpose).  TB tasks (= TB * LV 16-byte loads) are in flight per thread.
-template <class K, int TB>
-BTK_HD void ws_fill_thread(int ptid, const ChainSmem& L, float* s_xs, const float* pcm, int C, int T, long long t_lo,
-                           int cg0, bool vec4) {
-  constexpr int D = K::D, LV = K::LV;
-  static_assert(K::CG == 4, "one float4 per time step");
-  const int t0 = (int)t_lo;
-  const float* pcm_cg = pcm + cg0;
-  const bool v4 = vec4 && cg0 + K::CG <= C;
-  const int ntask = D * ((L.NB + LV - 1) / LV);
-  const int nbatch = (ntask + K::NPT * TB - 1) / (K::NPT * TB);
-#ifdef BTK_WS_FASTFILL
-  // A/B, OFF by default: interior windows (every sample of the window lies inside the recording) skip the per-sample
-  // range tests -- the guarded loop below spends ~17 instructions per 16-byte load on them (ncu).  Measured on B200 the
-  // lean loop is SLOWER: cfg2 0.3614 -> 0.3657 ms, cfg3 0.8235 -> 0.8747 ms, cfg4 1.887 -> 2.003 ms.  Its loads leave
-  // back to back, and a burst of 32-sector requests in the LSU queue delays the shared-memory accesses of the transform
-  // warps, which are what bounds the kernel; the guarded loop happens to pace the loads.
-  if (v4 && t0 >= 0 && (long long)t0 + (long long)L.NB * D <= (long long)T) {
-    const size_t row = (size_t)D * (unsigned)C;                     // floats between consecutive D-blocks of one residue
-    for (int b = 0; b < nbatch; b++) {
-      const int task0 = ptid + b * (K::NPT * TB);
-      float4 q[TB][LV];
+// register transpose).  A batch is TB tasks (= TB * LV 16-byte loads in flight per thread); the loads and the stores of
+// a batch are separate calls so that the device producer can issue the first batch of a stage BEFORE it waits for the
+// stage to be handed back (the loads only need registers), and so that the load latency of that batch hides behind the
+// wait.
+// (A lean variant of the load loop without the per-sample range tests for interior windows measured SLOWER on every
+// shape -- cfg2 0.3614 -> 0.3657 ms, cfg3 0.8235 -> 0.8747 ms, cfg4 1.887 -> 2.003 ms: its loads leave back to back, and
+// a burst of 32-sector requests in the LSU queue delays the shared-memory accesses of the transform warps.)
+template <class K>
+struct WsFill {
+  const float* pcm_cg;
+  float* s_xs;
+  int t0, T, C, cg0, ntask, nbatch, SB, CS, NB;
+  bool v4;
+  BTK_HD WsFill(const ChainSmem& L, float* xs, const float* pcm, int C_, int T_, long long t_lo, int cg0_, bool vec4, int tb)
+      : pcm_cg(pcm + cg0_), s_xs(xs), t0((int)t_lo), T(T_), C(C_), cg0(cg0_), SB(L.SB), CS(L.CS), NB(L.NB) {
+    v4 = vec4 && cg0_ + K::CG <= C_;
+    ntask = K::D * ((L.NB + K::LV - 1) / K::LV);
+    nbatch = (ntask + K::NPT * tb - 1) / (K::NPT * tb);
+  }
+  template <int TB>
+  BTK_HD void load(int ptid, int b, float (&x)[TB][K::LV][K::CG]) const {
+    constexpr int D = K::D, LV = K::LV;
+    const int task0 = ptid + b * (K::NPT * TB);
+#ifdef BTK_WS_FASTFILL       // A/B knob: interior windows without the per-sample range tests (see the note above)
+    if (v4 && t0 >= 0 && (long long)t0 + (long long)NB * D <= (long long)T) {
+      const size_t row = (size_t)D * (unsigned)C;
       BTK_UNROLL
       for (int k = 0; k < TB; k++) {
         const int task = task0 + k * K::NPT;
@@ -165,42 +169,14 @@ BTK_HD void ws_fill_thread(int ptid, const ChainSmem& L, float* s_xs, const floa
         const float* src = pcm_cg + (size_t)((unsigned)(t0 + res)) * (unsigned)C + (size_t)(bg * LV) * row;
         BTK_UNROLL
         for (int i = 0; i < LV; i++) {
-          q[k][i].x = 0.f; q[k][i].y = 0.f; q[k][i].z = 0.f; q[k][i].w = 0.f;
-          if (task < ntask && bg * LV + i < L.NB) q[k][i] = *reinterpret_cast<const float4*>(src + i * row);
+          float4 q; q.x = 0.f; q.y = 0.f; q.z = 0.f; q.w = 0.f;
+          if (task < ntask && bg * LV + i < NB) q = *reinterpret_cast<const float4*>(src + i * row);
+          x[k][i][0] = q.x; x[k][i][1] = q.y; x[k][i][2] = q.z; x[k][i][3] = q.w;
         }
       }
-      BTK_UNROLL
-      for (int k = 0; k < TB; k++) {
-        const int task = task0 + k * K::NPT;
-        if (task < ntask) {
-          const int res = task % D, bg = task / D;
-          float* dst = s_xs + xs_off<LV>(res, bg, L.SB);
-          if (LV == 4) {
-            float4 v;
-            v.x = q[k][0].x; v.y = q[k][1].x; v.z = q[k][LV > 2 ? 2 : 0].x; v.w = q[k][LV - 1].x;
-            *reinterpret_cast<float4*>(dst) = v;
-            v.x = q[k][0].y; v.y = q[k][1].y; v.z = q[k][LV > 2 ? 2 : 0].y; v.w = q[k][LV - 1].y;
-            *reinterpret_cast<float4*>(dst + L.CS) = v;
-            v.x = q[k][0].z; v.y = q[k][1].z; v.z = q[k][LV > 2 ? 2 : 0].z; v.w = q[k][LV - 1].z;
-            *reinterpret_cast<float4*>(dst + 2 * L.CS) = v;
-            v.x = q[k][0].w; v.y = q[k][1].w; v.z = q[k][LV > 2 ? 2 : 0].w; v.w = q[k][LV - 1].w;
-            *reinterpret_cast<float4*>(dst + 3 * L.CS) = v;
-          } else {
-            float2 v;
-            v.x = q[k][0].x; v.y = q[k][1].x; *reinterpret_cast<float2*>(dst) = v;
-            v.x = q[k][0].y; v.y = q[k][1].y; *reinterpret_cast<float2*>(dst + L.CS) = v;
-            v.x = q[k][0].z; v.y = q[k][1].z; *reinterpret_cast<float2*>(dst + 2 * L.CS) = v;
-            v.x = q[k][0].w; v.y = q[k][1].w; *reinterpret_cast<float2*>(dst + 3 * L.CS) = v;
-          }
-        }
-      }
+      return;
     }
-    return;
-  }
 #endif
-  for (int b = 0; b < nbatch; b++) {
-    const int task0 = ptid + b * (K::NPT * TB);
-    float x[TB][LV][K::CG];
     BTK_UNROLL
     for (int k = 0; k < TB; k++) {
       const int task = task0 + k * K::NPT;
@@ -211,10 +187,15 @@ BTK_HD void ws_fill_thread(int ptid, const ChainSmem& L, float* s_xs, const floa
         const int t = t0 + blk * D + res;
         BTK_UNROLL
         for (int c = 0; c < K::CG; c++) x[k][i][c] = 0.f;
-        if (task < ntask && blk < L.NB && (unsigned)t < (unsigned)T) {
+        if (task < ntask && blk < NB && (unsigned)t < (unsigned)T) {
           const float* src = pcm_cg + (size_t)((unsigned)t) * (unsigned)C;
           if (v4) {
+#if defined(__CUDA_ARCH__) && defined(BTK_WS_LDG_NOALLOC)
+            float4 q;
+            asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "l"(src));
+#else
             const float4 q = *reinterpret_cast<const float4*>(src);
+#endif
             x[k][i][0] = q.x; x[k][i][1] = q.y; x[k][i][2] = q.z; x[k][i][3] = q.w;
           } else {
             BTK_UNROLL
@@ -223,24 +204,41 @@ BTK_HD void ws_fill_thread(int ptid, const ChainSmem& L, float* s_xs, const floa
         }
       }
     }
+  }
+  template <int TB>
+  BTK_HD void store(int ptid, int b, const float (&x)[TB][K::LV][K::CG]) const {
+    constexpr int D = K::D, LV = K::LV;
+    const int task0 = ptid + b * (K::NPT * TB);
     BTK_UNROLL
     for (int k = 0; k < TB; k++) {
       const int task = task0 + k * K::NPT;
       if (task < ntask) {
         const int res = task % D, bg = task / D;
-        float* dst = s_xs + xs_off<LV>(res, bg, L.SB);
+        float* dst = s_xs + xs_off<LV>(res, bg, SB);
         BTK_UNROLL
         for (int c = 0; c < K::CG; c++) {
           if (LV == 4) {
             float4 v; v.x = x[k][0][c]; v.y = x[k][1][c]; v.z = x[k][LV > 2 ? 2 : 0][c]; v.w = x[k][LV - 1][c];
-            *reinterpret_cast<float4*>(dst + c * L.CS) = v;
+            *reinterpret_cast<float4*>(dst + c * CS) = v;
           } else {
             float2 v; v.x = x[k][0][c]; v.y = x[k][1][c];
-            *reinterpret_cast<float2*>(dst + c * L.CS) = v;
+            *reinterpret_cast<float2*>(dst + c * CS) = v;
           }
         }
       }
     }
+  }
+};
+
+// the whole share of one producer thread in one call (host emulation; the device producer drives WsFill itself)
+template <class K, int TB>
+BTK_HD void ws_fill_thread(int ptid, const ChainSmem& L, float* s_xs, const float* pcm, int C, int T, long long t_lo,
+                           int cg0, bool vec4) {
+  const WsFill<K> f(L, s_xs, pcm, C, T, t_lo, cg0, vec4, TB);
+  for (int b = 0; b < f.nbatch; b++) {
+    float x[TB][K::LV][K::CG];
+    f.template load<TB>(ptid, b, x);
+    f.template store<TB>(ptid, b, x);
   }
 }
 

@@ -130,7 +130,13 @@ template <int M, int NT> struct WsRegs {
 // loads in flight per producer thread follow its register budget (a task is LV 16-byte loads)
 template <int M, int NT, int LV> struct WsProd {
   static constexpr int RP = WsRegs<M, NT>::split ? WsRegs<M, NT>::RP : 255;
-  static constexpr int LOADS = RP >= 112 ? 12 : (RP >= 64 ? 8 : 4);
+#ifndef BTK_WS_LOADS_HI
+#define BTK_WS_LOADS_HI 8        // measured: 8 loads in flight beat 12 (cfg2 0.3479 -> 0.3419 ms) and 4 (0.3854 ms): a gentler producer disturbs the transform warps less
+#endif
+#ifndef BTK_WS_LOADS_MID
+#define BTK_WS_LOADS_MID 8
+#endif
+  static constexpr int LOADS = RP >= 112 ? BTK_WS_LOADS_HI : (RP >= 64 ? BTK_WS_LOADS_MID : 4);
   static constexpr int TB = LOADS / LV;
 };
 
@@ -183,13 +189,40 @@ __global__ void __launch_bounds__(WsCfg<M, R, MT, PP>::NT + WsCfg<M, R, MT, PP>:
     const float* pcm = p.pcm + rec.pcm_off;
     const cf* wts = p.wts + (long long)wk.rec * p.wts_stride;
     const bool vec4 = (p.C % 4 == 0) && (rec.pcm_off % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.pcm) & 15) == 0);
+    constexpr int TB = WsProd<M, K::NT, K::LV>::TB;
     int g = 0;
     for (int it = 0; it < walk.n_it; it++) {
       const long long t_lo = ws_window_start<K>(walk, it, p.laN, N);
+#ifdef BTK_WS_L2PF          // A/B, OFF by default: measured neutral (cfg2 0.3465 -> 0.3468 ms, cfg3 0.8292 -> 0.8308 ms)
+      // The rows the NEXT iteration adds to the window (W D time steps, every channel: one contiguous run of the
+      // interleaved recording) are asked into L2 now, by the bulk-prefetch engine: no registers, no scoreboard, any number
+      // in flight.  The register loads of the next iteration's stages then run at L2 latency instead of DRAM latency
+      // (a stage is 3-4 dependent batches of loads).  Skipped for many-channel inputs, where the windows in flight
+      // already fill L2 (p.no_prefetch).
+      if (!p.no_prefetch && it + 1 < walk.n_it && ptid < 32) {
+        long long lo = t_lo + (long long)L.NB * K::D, hi = lo + (long long)K::W * K::D;
+        if (lo < 0) lo = 0;
+        if (hi > rec.T) hi = rec.T;
+        const long long b0 = lo * p.C * 4, b1 = hi * p.C * 4;                 // byte range inside the recording
+        constexpr long long CH = 4096;
+        const char* base = reinterpret_cast<const char*>(pcm);
+        for (long long o = (b0 & ~15ll) + (long long)ptid * CH; o < b1; o += 32 * CH) {
+          long long n = b1 - o < CH ? b1 - o : CH;
+          n = (n + 15) & ~15ll;
+          if ((reinterpret_cast<uintptr_t>(base + o) & 15) == 0)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + o), "r"((uint32_t)n) : "memory");
+        }
+      }
+#endif
       for (int cgi = 0; cgi < walk.ncg; cgi++, g++) {
         const int st = g % K::NS;
         unsigned char* stage = smem + S.stage0 + st * S.stage_bytes;
         const int cg0 = (walk.cg_base + cgi) * K::CG;
+        const WsFill<K> fill(L, reinterpret_cast<float*>(stage), pcm, p.C, rec.T, t_lo, cg0, vec4, TB);
+        float x[TB][K::LV][K::CG];
+#ifdef BTK_WS_EARLY         // A/B, OFF by default: cfg2 0.3465 -> 0.3447 ms, but cfg3 0.8292 -> 0.8357 ms and cfg4 1.877 -> 1.942 ms
+        fill.template load<TB>(ptid, 0, x);          // in flight while the stage is still with the transform warps
+#endif
 #ifdef BTK_WS_NO_BACKOFF
         mbar_wait(bars + WS_BAR_EMPTY + st, ((g / K::NS) & 1) ^ 1);
 #else
@@ -200,7 +233,13 @@ __global__ void __launch_bounds__(WsCfg<M, R, MT, PP>::NT + WsCfg<M, R, MT, PP>:
           bulk_g2s(stage + S.wts_off, wts + (long long)cg0 * M, K::CG * M * 8, bars + WS_BAR_FULL + st);
         }
 #ifndef BTK_EXP_NOFILL      // experiment: the compute side alone (stages handed over unfilled; results are garbage)
-        ws_fill_thread<K, WsProd<M, K::NT, K::LV>::TB>(ptid, L, reinterpret_cast<float*>(stage), pcm, p.C, rec.T, t_lo, cg0, vec4);
+        for (int b = 0; b < fill.nbatch; b++) {
+#ifdef BTK_WS_EARLY
+          if (b > 0)
+#endif
+            fill.template load<TB>(ptid, b, x);
+          fill.template store<TB>(ptid, b, x);
+        }
 #endif
         mbar_arrive(bars + WS_BAR_FULL + st);
       }
