@@ -32,7 +32,8 @@ SYMBOLS = [
     "btkb200_chain_batch_multi", "btkb200_chain_batch_dev", "btkb200_analysis_dev", "btkb200_beamform_dev",
     "btkb200_synthesis_dev", "btkb200_launch_count", "btkb200_sync", "btkb200_host_alloc", "btkb200_host_free",
     "btkb200_plan_tune", "btkb200_plan_tuning", "btkb200_set_null_weights", "btkb200_calc_delays_polar",
-    "btkb200_calc_all_delays", "btkb200_get_array_manifold",
+    "btkb200_calc_all_delays", "btkb200_get_array_manifold", "btkb200_design_analysis_nyquist",
+    "btkb200_design_synthesis_nyquist",
 ]
 
 
@@ -539,6 +540,34 @@ def design_synthesis_prototype(h, M: int, m: int, r: int, v: float = 1.0, wp_fac
     if rc != OK:
         raise BtkError(rc, (L.btkb200_last_error(None) or b"").decode())
     return g, err
+
+
+def design_analysis_nyquist(M: int, m: int, r: int, wp_factor: float = 1.0, tau: int = -1, tolerance: float = 1e-7,
+                            device: int = 0):
+    """AnalysisNyquistMDesign(M, m, r, wpFactor, tau).design(tolerance) on the device.  Returns (h, path)."""
+    L = lib()
+    h = np.zeros(M * m, dtype=np.float64)
+    path = c_int(0)
+    rc = L.btkb200_design_analysis_nyquist(M, m, r, c_double(wp_factor), tau, c_double(tolerance), device, _p(h), ctypes.byref(path))
+    if rc != OK:
+        raise BtkError(rc, (L.btkb200_last_error(None) or b"").decode())
+    return h, int(path.value)
+
+
+def design_synthesis_nyquist(h, M: int, m: int, r: int, wp_factor: float = 1.0, tau: int = -1, tolerance: float = 1e-7,
+                             device: int = 0):
+    """SynthesisNyquistMDesign(h, M, m, r, wpFactor, tau).design(tolerance) on the device.  Returns (g, path)."""
+    L = lib()
+    hh = np.ascontiguousarray(h, dtype=np.float64)
+    if hh.size != M * m:
+        raise BtkError(EINVAL, f"Prototype sizes do not match ({hh.size} vs. {M * m}).")
+    g = np.zeros(M * m, dtype=np.float64)
+    path = c_int(0)
+    rc = L.btkb200_design_synthesis_nyquist(_p(hh), M, m, r, c_double(wp_factor), tau, c_double(tolerance), device, _p(g),
+                                            ctypes.byref(path))
+    if rc != OK:
+        raise BtkError(rc, (L.btkb200_last_error(None) or b"").decode())
+    return g, int(path.value)
 
 
 def calc_delays_polar(azimuth: float, elevation: float, micpos_mm) -> np.ndarray:

@@ -397,6 +397,33 @@ int btkb200_design_synthesis_prototype(const double* h, unsigned M, unsigned m, 
   return design_common(1, h, M, m, r, v, wp_factor, tau, tolerance, device, g, err);
 }
 
+static int design_nyquist_common(int kind, const double* h, unsigned M, unsigned m, unsigned r, double wp_factor, int tau,
+                                 double tolerance, int device, double* out, int* path) {
+  if (!out || M == 0 || m == 0 || r > 8 || (M >> r) == 0 || ((M >> r) << r) != M || !(wp_factor > 0.0) || !(tolerance > 0.0))
+    return fail(nullptr, BTKB200_EINVAL, "bad design arguments M=%u m=%u r=%u", M, m, r);
+  if ((size_t)M * m > 4096) return fail(nullptr, BTKB200_EUNSUPPORTED, "prototype length M*m = %u too large (max 4096)", M * m);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return fail(nullptr, BTKB200_ECUDA, "no CUDA device available (this library has no CPU path)");
+  if (device < 0 || device >= ndev) return fail(nullptr, BTKB200_EINVAL, "device %d out of range (%d visible)", device, ndev);
+  cudaError_t e = cudaSetDevice(device);
+  int sweeps = 0;
+  if (e == cudaSuccess) e = design_prototype_nyquist(kind, h, (int)M, (int)m, (int)r, wp_factor, tau, tolerance, out, path, &sweeps);
+  if (e != cudaSuccess) return fail(nullptr, BTKB200_ECUDA, "prototype design failed: %s", cudaGetErrorString(e));
+  return BTKB200_OK;
+}
+
+int btkb200_design_analysis_nyquist(unsigned M, unsigned m, unsigned r, double wp_factor, int tau, double tolerance, int device,
+                                    double* h, int* path) {
+  return design_nyquist_common(0, nullptr, M, m, r, wp_factor, tau, tolerance, device, h, path);
+}
+
+int btkb200_design_synthesis_nyquist(const double* h, unsigned M, unsigned m, unsigned r, double wp_factor, int tau, double tolerance,
+                                     int device, double* g, int* path) {
+  if (!h) return fail(nullptr, BTKB200_EINVAL, "analysis prototype is NULL");
+  return design_nyquist_common(1, h, M, m, r, wp_factor, tau, tolerance, device, g, path);
+}
+
 // ------------------------------------------------------------------------------------------- GSC (fixed active weights)
 int btkb200_gsc_calc_weights(btkb200_plan* p, double fs, const double* delays, unsigned n) {
   if (!p || !delays) return BTKB200_EINVAL;

@@ -53,6 +53,10 @@ cudaError_t launch_beamform_zelinski(const cf* snap, const cf* w, const cf* ta, 
 cudaError_t design_prototype(int kind, const double* h_in, int M, int m, int r, double v, double wp_factor, int tau, double tolerance,
                              double* proto_out, double* err, int* sweeps_out);
 
+// Nyquist(M)-constrained designs (prototypeDesign.cc:955-1119): kind 0 analysis, 1 synthesis from h_in; *path = 3 | 4
+cudaError_t design_prototype_nyquist(int kind, const double* h_in, int M, int m, int r, double wp_factor, int tau, double tolerance,
+                                     double* proto_out, int* path_out, int* sweeps_out);
+
 // device-resident MVDR adaptation helpers (kern_misc.cu): diagonal loading, chain weight table from device weights
 cudaError_t launch_diag_load(double2* Rn, int B, int C, float load_abs, double load_rel, cudaStream_t st);
 cudaError_t launch_weight_table(const double2* w, const int* binmap, cf* gam, int M, int C, int Cpad, cudaStream_t st, int n = 1);

@@ -677,6 +677,39 @@ class SynthesisOversampledDFTDesignPtr(AnalysisOversampledDFTDesignPtr):
         return self._err
 
 
+class AnalysisNyquistMDesignPtr(AnalysisOversampledDFTDesignPtr):
+    """modulated/modulated.i:366-385 shadow of AnalysisNyquistMDesign (prototypeDesign.h:221-235, .cc:955-1001)."""
+
+    def design(self, tolerance: float = 1.0e-07):
+        try:
+            self._proto, self._path = _capi.design_analysis_nyquist(self._M, self._m, self._r, self._wp, self._tau, tolerance)
+        except BtkError as e:
+            _raise(e)
+        return self._proto
+
+    def solutionPath(self) -> int:
+        """3 or 4: which of the reference's "alternate solutions" the last design() took (it prints the number)."""
+        return self._path
+
+    def calcError(self, doPrint: bool = True):
+        raise j_error("calcError() is not provided for the Nyquist(M) designs")
+
+
+class SynthesisNyquistMDesignPtr(AnalysisNyquistMDesignPtr):
+    """prototypeDesign.h:242-264, .cc:1003-1119: SynthesisNyquistMDesign(h, M, m, r, wpFactor, tau_g)."""
+
+    def __init__(self, h, M: int = 512, m: int = 2, r: int = 1, wpFactor: float = 1.0, tau_g: int = -1):
+        super().__init__(M, m, r, wpFactor, tau_g)
+        self._h = np.ascontiguousarray(h, np.float64).ravel().copy()
+
+    def design(self, tolerance: float = 1.0e-07):
+        try:
+            self._proto, self._path = _capi.design_synthesis_nyquist(self._h, self._M, self._m, self._r, self._wp, self._tau, tolerance)
+        except BtkError as e:
+            _raise(e)
+        return self._proto
+
+
 TYPE_ZELINSKI1_REAL, TYPE_ZELINSKI1_ABS, TYPE_APAB, TYPE_ZELINSKI2, NO_USE_POST_FILTER = 0x01, 0x02, 0x04, 0x08, 0x00
 
 

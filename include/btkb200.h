@@ -149,6 +149,17 @@ int btkb200_design_analysis_prototype(unsigned M, unsigned m, unsigned r, double
 int btkb200_design_synthesis_prototype(const double* h, unsigned M, unsigned m, unsigned r, double v, double wp_factor,
                                        int tau, double tolerance, int device, double* g, double* err);
 
+/* AnalysisNyquistMDesign(M, m, r, wpFactor, tau_h).design(tolerance) (prototypeDesign.cc:955-1001): the in-band aliasing
+ * h^T C h minimised subject to the Nyquist(M) constraint h[n M] = delta(n - m/2) / M ("alternate solution 4", :361-470), or --
+ * when cond([F^T; C]) >= 1/tolerance (:579-609) -- the passband error minimised inside the numerical null space of the
+ * stacked constraints ("alternate solution 3", :481-577).  *path (or NULL) receives 3 or 4.  fp64 on the device. */
+int btkb200_design_analysis_nyquist(unsigned M, unsigned m, unsigned r, double wp_factor, int tau, double tolerance,
+                                    int device, double* h, int* path);
+/* SynthesisNyquistMDesign(h, M, m, r, wpFactor, tau_g).design(tolerance) (prototypeDesign.cc:1003-1119): the residual
+ * aliasing g^T P g minimised subject to the 2 m total-response constraints H^T g = c0 (:1073-1089); same two paths. */
+int btkb200_design_synthesis_nyquist(const double* h, unsigned M, unsigned m, unsigned r, double wp_factor, int tau,
+                                     double tolerance, int device, double* g, int* path);
+
 /* ---- SubbandGSC with fixed active weights ------------------------------------------------------- */
 /* SubbandGSC::calcGSCWeights (beamformer.cc:1373-1377): delay-and-sum quiescent vectors + one blocking matrix per bin
  * (_calcBlockingMatrix, :398-479, NC = 1); the active weights start at zero.  EINVAL for a single channel (:536-539). */

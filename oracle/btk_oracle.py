@@ -389,6 +389,116 @@ def design_synthesis_dehaan(h: np.ndarray, M: int, m: int, r: int, v: float = 1.
     return _pinv_solve(E + v * P, f, tol)
 
 
+def _design_matrices_analysis(M, m, r, wp_factor, tau):
+    L, D = M * m, M >> r
+    wp = np.pi / (wp_factor * M)
+    tau = L // 2 if tau < 0 else tau
+    idx = np.arange(L)
+    d = idx[None, :] - idx[:, None]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        A = np.where(d == 0, 1.0, np.sin(wp * d) / (wp * d))
+        t = tau - idx
+        b = np.where(t == 0, 1.0, np.sin(wp * t) / (wp * t))
+        f = np.where(d % D == 0, D - 1.0, -1.0)
+        C = np.where(d == 0, f / D, f * np.sin(np.pi * d / D) / (np.pi * D * d))
+    return A, b, C
+
+
+def _design_matrix_P(h, M, m, r):
+    L, D = M * m, M >> r
+    idx = np.arange(L)
+    rr = np.correlate(h, h, mode="full")
+    d = idx[:, None] - idx[None, :]
+    fac = np.where(d % D == 0, D - 1.0, -1.0)
+    return fac * rr[L - 1 + np.abs(d)] * (M / (float(D) * float(D)))
+
+
+def _svd_full(At: np.ndarray):
+    """Singular values (decreasing) and right singular vectors V (all N of them, orthonormal) of At [rows x N] -- what
+    PrototypeDesignBase::_svd hands back for either shape (prototypeDesign.cc:276-293)."""
+    _, s, Vt = np.linalg.svd(At, full_matrices=True)
+    N = At.shape[1]
+    sv = np.zeros(N)
+    sv[: s.size] = s
+    return sv, Vt.T
+
+
+def _constrained_design(Hc, c0, Q, A, b, tol):
+    """The two solution paths of the Nyquist(M) designs (prototypeDesign.cc:361-470, 481-577, 579-609).
+    Hc [L x k]: constraint columns (Hc^T x = c0), Q [L x L]: the matrix of the quadratic to minimise.
+    cond([Hc^T; Q]) < 1/tol  -> "alternate solution 4" (_solveNonSingular): x = x_pt - B pinv_tol(B^T Q B) B^T Q x_pt over the
+                                null space B of Hc^T;
+    otherwise                -> "alternate solution 3" (_solveSingular): constraints K = [Hc Q] (K^T x = [c0; 0]), then
+                                x = x_pt + B pinv'(B^T A B) B^T (b - A x_pt) over the numerical null space B of K^T, where
+                                pinv' divides the components above the tolerance and LEAVES the others as they are (:556-558).
+    Returns (x, path)."""
+    L = Hc.shape[0]
+    Kt = np.vstack([Hc.T, Q])
+    sv, V = _svd_full(Kt)
+    cond = sv[0] / sv[L - 1] if sv[L - 1] > 0 else np.inf
+    if cond < 1.0 / tol:
+        s, Vh = _svd_full(Hc.T)
+        U = np.linalg.svd(Hc.T, full_matrices=False)[0]                 # [k x k]
+        keep = (s / s[0]) >= tol
+        coef = np.zeros(L)
+        k = Hc.shape[1]
+        coef[:k] = np.where(keep[:k], (U.T @ c0) / np.where(keep[:k], s[:k], 1.0), 0.0)
+        x_pt = Vh @ coef
+        B = Vh[:, L - int(np.sum((s / s[0]) < tol)):]
+        Qt = B.T @ Q @ B
+        Uq, sq, Vqt = np.linalg.svd(Qt)
+        y = Uq.T @ (B.T @ (Q @ x_pt))
+        y = np.where((sq / sq[0]) > tol, y / np.where(sq > 0, sq, 1.0), 0.0)
+        return x_pt - B @ (Vqt.T @ y), 4
+    # singular branch
+    dp = np.concatenate([c0, np.zeros(L)])
+    Uk, sk, Vkt = np.linalg.svd(Kt, full_matrices=False)                  # Kt: [(k + L) x L]
+    keep = (sk / sk[0]) >= tol
+    x_pt = Vkt.T @ np.where(keep, (Uk.T @ dp) / np.where(keep, sk, 1.0), 0.0)
+    nnull = int(np.sum((sk / sk[0]) < tol))
+    B = Vkt.T[:, L - nnull:]
+    At_ = B.T @ A @ B
+    Ua, sa, Vat = np.linalg.svd(At_)
+    y = Ua.T @ (B.T @ (b - A @ x_pt))
+    y = np.where((sa / sa[0]) > tol, y / np.where(sa > 0, sa, 1.0), y)
+    return x_pt + B @ (Vat.T @ y), 3
+
+
+def design_analysis_nyquist(M: int, m: int, r: int, wp_factor: float = 1.0, tau: int = -1, tol: float = 1e-7,
+                            want_path: bool = False):
+    """AnalysisNyquistMDesign::design (prototypeDesign.cc:955-1001): minimise the in-band aliasing h^T C h (or, when the
+    constraints are numerically dependent, the passband error h^T A h - 2 h^T b inside their null space) subject to the
+    Nyquist(M) constraint h[n M] = delta(n - m/2) / M  (F [L x m], F[n M, n] = 1; d[m/2] = 1/M, :982-989)."""
+    L = M * m
+    A, b, C = _design_matrices_analysis(M, m, r, wp_factor, tau)
+    F = np.zeros((L, m))
+    d = np.zeros(m)
+    for n in range(m):
+        F[n * M, n] = 1.0
+    d[m // 2] = 1.0 / M
+    x, path = _constrained_design(F, d, C, A, b, tol)
+    return (x, path) if want_path else x
+
+
+def design_synthesis_nyquist(h: np.ndarray, M: int, m: int, r: int, wp_factor: float = 1.0, tau: int = -1,
+                             tol: float = 1e-7, want_path: bool = False):
+    """SynthesisNyquistMDesign::design (prototypeDesign.cc:1003-1119): minimise the residual aliasing g^T P g subject to the
+    2 m total-response constraints  H^T g = c0,  H[k, n] = h[n M - k] for max(0, 1 + (n - m) M) <= k <= min(n M, m M - 1)
+    (:1073-1089), c0[m] = D / M; singular branch as in the analysis design with the passband matrices A, b."""
+    h = np.asarray(h, dtype=np.float64)
+    L, D = M * m, M >> r
+    A, b, _ = _design_matrices_analysis(M, m, r, wp_factor, tau)
+    P = _design_matrix_P(h, M, m, r)
+    H = np.zeros((L, 2 * m))
+    for n in range(2 * m):
+        for k in range(max(0, 1 + (n - m) * M), min(n * M, m * M - 1) + 1):
+            H[k, n] = h[n * M - k]
+    c0 = np.zeros(2 * m)
+    c0[m] = float(D) / M
+    x, path = _constrained_design(H, c0, P, A, b, tol)
+    return (x, path) if want_path else x
+
+
 # --------------------------------------------------------------------------- SubbandGSC (fixed active weights)
 def blocking_matrix(v: np.ndarray, NC: int = 1) -> np.ndarray:
     """_calcBlockingMatrix (beamformer/beamformer.cc:398-479), loop for loop: P = I - conj(v) v^T / ||v||^2 (zgeru), then
@@ -538,6 +648,9 @@ class CompiledReference:
         L.btkref_spectral_matrix.argtypes = [vp, cl, ci, vp, ci, ci, ci, ci, cd, vp]
         L.btkref_error_probe.restype = ci
         L.btkref_error_probe.argtypes = [ci]
+        if hasattr(L, "btkref_design_nyquist"):
+            L.btkref_design_nyquist.restype = ci
+            L.btkref_design_nyquist.argtypes = [ci, ci, ci, cd, cd, vp, vp, vp, vp]
         if hasattr(L, "btkref_null_weights"):
             L.btkref_null_weights.restype = ci
             L.btkref_null_weights.argtypes = [cd, vp, vp, ci, ci, ci, vp, vp]
@@ -664,6 +777,15 @@ class CompiledReference:
         if rc != 0:
             raise RuntimeError(f"btkref_design_dehaan returned {rc}")
         return h, g, eh, eg
+
+    def design_nyquist(self, M, m, r, wp_factor=1.0, tol=1e-7):
+        """AnalysisNyquistMDesign then SynthesisNyquistMDesign of the compiled reference: (h, g)."""
+        L = M * m
+        h, g = np.zeros(L), np.zeros(L)
+        eh, eg = np.zeros(3), np.zeros(3)
+        if self.lib.btkref_design_nyquist(M, m, r, wp_factor, tol, _dp(h), _dp(g), _dp(eh), _dp(eg)) != 0:
+            raise RuntimeError("btkref_design_nyquist failed")
+        return h, g
 
     def spectral_matrix(self, pcm, h, geo: BankGeometry, mu=0.95) -> np.ndarray:
         pcm = np.ascontiguousarray(pcm, dtype=np.float32)

@@ -350,10 +350,39 @@ static inline int gsl_linalg_SV_decomp(gsl_matrix* A, gsl_matrix* V, gsl_vector*
     }
     if (off < 1e-15) break;
   }
+  double svmax = 0;
   for (size_t j = 0; j < N; j++) {
     double n2 = 0; for (size_t i = 0; i < M; i++) n2 += A->data[i * A->tda + j] * A->data[i * A->tda + j];
     const double sv = sqrt(n2); S->data[j * S->stride] = sv;
-    if (sv > 0) for (size_t i = 0; i < M; i++) A->data[i * A->tda + j] /= sv;
+    if (sv > svmax) svmax = sv;
+  }
+  /* U.  GSL delivers a U with orthonormal columns whatever the rank (its U is a product of orthogonal transformations;
+   * prototypeDesign.cc:280-287 relies on it: for a wide matrix it decomposes the transpose and takes this U as "V", whose
+   * trailing columns are the null space).  Hestenes' u_j = g_j / s_j is rounding noise for a vanishing s_j, so those
+   * columns are rebuilt: unit vectors, orthogonalised twice against every other column. */
+  std::vector<size_t> nullcols;
+  for (size_t j = 0; j < N; j++) {
+    const double sv = S->data[j * S->stride];
+    if (sv > 1e-13 * svmax && sv > 0) for (size_t i = 0; i < M; i++) A->data[i * A->tda + j] /= sv;
+    else { nullcols.push_back(j); for (size_t i = 0; i < M; i++) A->data[i * A->tda + j] = 0.0; }
+  }
+  if (!nullcols.empty() && M >= N) {
+    size_t cand = 0;
+    std::vector<double> v(M);
+    for (size_t q = 0; q < nullcols.size(); q++) {
+      const size_t j = nullcols[q];
+      for (; cand < M; cand++) {
+        for (size_t i = 0; i < M; i++) v[i] = (i == cand) ? 1.0 : 0.0;
+        for (int pass = 0; pass < 2; pass++)
+          for (size_t k = 0; k < N; k++) {
+            if (k == j) continue;
+            double d = 0; for (size_t i = 0; i < M; i++) d += v[i] * A->data[i * A->tda + k];
+            if (d != 0.0) for (size_t i = 0; i < M; i++) v[i] -= d * A->data[i * A->tda + k];
+          }
+        double n2 = 0; for (size_t i = 0; i < M; i++) n2 += v[i] * v[i];
+        if (n2 > 0.25) { const double nn = sqrt(n2); for (size_t i = 0; i < M; i++) A->data[i * A->tda + j] = v[i] / nn; cand++; break; }
+      }
+    }
   }
   for (size_t j = 0; j + 1 < N; j++) {          /* selection sort, decreasing */
     size_t best = j;

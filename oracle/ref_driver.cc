@@ -209,6 +209,41 @@ gsl_vector* make_vector(const double* src, size_t n) {
 
 }  // namespace
 
+// Nyquist(M)-constrained designs (prototypeDesign.cc:955-1119): AnalysisNyquistMDesign, then SynthesisNyquistMDesign from its
+// h.  The synthesis class inherits the unallocated work vectors of SynthesisOversampledDFTDesign (see above).
+class SynthesisNyquistWithWorkspace : public SynthesisNyquistMDesign {
+ public:
+  SynthesisNyquistWithWorkspace(const gsl_vector* h, int M, int m, int r, double wp, int tau)
+      : SynthesisNyquistMDesign(h, M, m, r, wp, tau) {
+    _singularVals = gsl_vector_calloc(M * m);
+    _scratch = gsl_vector_calloc(M * m);
+    _workSpace = gsl_vector_calloc(M * m);
+  }
+  ~SynthesisNyquistWithWorkspace() { gsl_vector_free(_singularVals); gsl_vector_free(_scratch); gsl_vector_free(_workSpace); }
+};
+
+extern "C" int btkref_design_nyquist(int M, int m, int r, double wpFactor, double tolerance, double* h, double* g,
+                                     double* err_h, double* err_g) {
+  try {
+    const int L = M * m;
+    AnalysisNyquistMDesign ana(M, m, r, wpFactor, -1);
+    const gsl_vector* hv = ana.design(tolerance);
+    for (int n = 0; n < L; n++) h[n] = gsl_vector_get(hv, n);
+    const gsl_vector* eh = ana.calcError(false);
+    if (err_h) for (int k = 0; k < 3; k++) err_h[k] = gsl_vector_get(eh, k);
+    if (g) {
+      gsl_vector* hc = make_vector(h, L);
+      SynthesisNyquistWithWorkspace syn(hc, M, m, r, wpFactor, -1);
+      const gsl_vector* gv = syn.design(tolerance);
+      for (int n = 0; n < L; n++) g[n] = gsl_vector_get(gv, n);
+      const gsl_vector* eg = syn.calcError(false);
+      if (err_g) for (int k = 0; k < 2; k++) err_g[k] = gsl_vector_get(eg, k);
+      gsl_vector_free(hc);
+    }
+    return 0;
+  } catch (std::exception& e) { fprintf(stderr, "btkref_design_nyquist: %s\n", e.what()); return -1; }
+}
+
 extern "C" {
 
 struct btkref_chain_cfg {

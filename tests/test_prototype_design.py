@@ -12,7 +12,10 @@ import btk_oracle as bo
 from conftest import GOLDEN
 
 wl = btk_b200.workloads
-CASES = sorted(f[len("design_"):-4] for f in os.listdir(GOLDEN) if f.startswith("design_") and f.endswith(".npz"))
+CASES = sorted(f[len("design_"):-4] for f in os.listdir(GOLDEN)
+               if f.startswith("design_") and f.endswith(".npz") and not f.startswith("design_nyquist_"))
+# Nyquist(M)-constrained designs of the compiled reference (make_golden_nyquist.py): design_nyquist_<M>_<m>_<r>_<tol>.npz
+NYQ = sorted(f[len("design_nyquist_"):-4] for f in os.listdir(GOLDEN) if f.startswith("design_nyquist_") and f.endswith(".npz"))
 
 
 def _load(name):
@@ -80,3 +83,43 @@ def test_device_design_full_size_and_in_the_filter_bank():
     # f = M/(pi D) h[2 tau - m] (prototypeDesign.cc:866) fixes the pair's overall gain at D/(pi D) = 1/pi
     assert abs(scale * np.pi - 1.0) < 0.05 and snr > 25.0, (scale, snr)
     plan.close()
+
+
+# ------------------------------------------------------------------------------------------ Nyquist(M)-constrained designs
+def _load_nyq(name):
+    Z = np.load(os.path.join(GOLDEN, f"design_nyquist_{name}.npz"))
+    return {k: Z[k] for k in Z.files}
+
+
+@pytest.mark.parametrize("name", NYQ)
+def test_oracle_matches_reference_nyquist_design(name):
+    """AnalysisNyquistMDesign / SynthesisNyquistMDesign (prototypeDesign.cc:955-1119): numpy restatement against the
+    compiled reference, both solution paths (the fixture with tolerance 0.2 takes "alternate solution 3" for g)."""
+    G = _load_nyq(name)
+    M, m, r = [int(v) for v in G["geo"]]
+    tol = float(G["tol"])
+    if M * m > 512:
+        pytest.skip("L = 1024 restatement takes a minute of numpy SVDs: covered on the GPU tier")
+    h, ph = bo.design_analysis_nyquist(M, m, r, 1.0, -1, tol, want_path=True)
+    assert _rel(h, G["h"]) <= 1e-9 and ph == 4
+    assert np.abs(h[::M] * M - (np.arange(m) == m // 2)).max() <= 1e-12         # the Nyquist(M) constraint itself
+    g, pg = bo.design_synthesis_nyquist(G["h"], M, m, r, 1.0, -1, tol, want_path=True)
+    assert _rel(g, G["g"]) <= 1e-9
+    assert pg == (3 if tol > 0.1 else 4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NYQ)
+def test_device_nyquist_design_matches_reference(name):
+    """The device designs (rectangular one-sided Jacobi decompositions, null-space projection) against the compiled
+    reference's prototypes, (256, 4, 1) and (512, 2, 2) of the BASELINE geometries included: <= 1e-8 of the largest tap."""
+    G = _load_nyq(name)
+    M, m, r = [int(v) for v in G["geo"]]
+    tol = float(G["tol"])
+    h, ph = btk_b200.design_analysis_nyquist(M, m, r, 1.0, -1, tol)
+    assert _rel(h, G["h"]) <= 1e-8 and ph == 4
+    g, pg = btk_b200.design_synthesis_nyquist(G["h"], M, m, r, 1.0, -1, tol)
+    assert _rel(g, G["g"]) <= 1e-8
+    assert pg == (3 if tol > 0.1 else 4)
+    d = btk_b200.streams.SynthesisNyquistMDesignPtr(G["h"], M, m, r, 1.0)
+    assert np.array_equal(d.design(tol), g) and d.solutionPath() == pg
