@@ -60,7 +60,13 @@ def prototypes(M, m, r):
     key = f"h_{M}_{m}_{r}"
     if key in P.files:
         return P[key], P[f"g_{M}_{m}_{r}"]
-    return btk_b200.workloads.kaiser_prototype(M, m, r)
+    # no shipped fixture for this geometry (M = 128, 1024, ...): design the pair on the device with the reference's own
+    # procedure; the CPU reference arm has no device and keeps the Kaiser stand-in (it is only ever run on
+    # the fixture geometries)
+    try:
+        return btk_b200.workloads.designed_prototype(M, m, r)
+    except btk_b200.BtkError:
+        return btk_b200.workloads.kaiser_prototype(M, m, r)
 
 
 def geometry(wl_cfg):

@@ -8,7 +8,8 @@ The directory name carries a hyphen (it mirrors the upstream repository name); i
 from . import _capi, sharding, streams, workloads  # noqa: F401
 from ._capi import (BtkError, Plan, calc_all_delays, calc_delays_polar, design_analysis_nyquist,  # noqa: F401
                     design_analysis_prototype, design_synthesis_nyquist, design_synthesis_prototype, device_count, lib)
-from .streams import (OverSampledDFTAnalysisBankPtr, OverSampledDFTSynthesisBankPtr, SampleFeaturePtr,  # noqa: F401
+from .streams import (ChannelExtractionFeaturePtr, Conversion24bit2FloatPtr, IterativeSampleFeaturePtr,  # noqa: F401
+                      OverSampledDFTAnalysisBankPtr, OverSampledDFTSynthesisBankPtr, SampleFeaturePtr,  # noqa: F401
                       SnapShotArrayPtr, SpectralMatrixArrayPtr, SubbandDSPtr, SubbandGSCPtr, SubbandMVDRPtr,
                       ZelinskiPostFilterPtr)
 

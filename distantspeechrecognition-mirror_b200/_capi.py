@@ -168,6 +168,13 @@ class Plan:
             self._L.btkb200_plan_destroy(self._h)
             self._h = c_void_p()
 
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
     def __del__(self):
         try:
             self.close()

@@ -36,6 +36,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <exception>
 #include <list>
 #include <memory>
@@ -49,12 +50,14 @@
 #include <gsl/gsl_vector.h>
 #include "stream/stream.h"
 #include "beamformer/beamformer.h"
+typedef gsl_vector_char btk_vector_char;
 typedef gsl_vector_float btk_vector_float;
 typedef gsl_vector_complex btk_vector_complex;
 typedef gsl_vector btk_vector;
 typedef gsl_matrix btk_matrix;
 typedef gsl_matrix_complex btk_matrix_complex;
 #else
+struct btk_vector_char { size_t size, stride; char* data; void* block; int owner; };
 struct btk_vector_float { size_t size, stride; float* data; void* block; int owner; };
 struct btk_vector_complex { size_t size, stride; double* data; void* block; int owner; };   // (re, im) pairs
 struct btk_vector { size_t size, stride; double* data; void* block; int owner; };
@@ -71,6 +74,9 @@ using ::j_error;
 using ::jiterator_error;
 using ::jconsistency_error;
 using ::jdimension_error;
+using ::jio_error;
+using ::VectorCharFeatureStream;
+using ::VectorCharFeatureStreamPtr;
 using ::VectorFloatFeatureStream;
 using ::VectorComplexFeatureStream;
 using ::VectorFloatFeatureStreamPtr;
@@ -110,6 +116,7 @@ class j_error : public std::exception {
 BTKB200_DEFINE_ERROR(jiterator_error, JITERATOR)       // doubles as end of stream (-> StopIteration in Python)
 BTKB200_DEFINE_ERROR(jconsistency_error, JCONSISTENCY)
 BTKB200_DEFINE_ERROR(jdimension_error, JDIMENSION)
+BTKB200_DEFINE_ERROR(jio_error, JIO)
 #undef BTKB200_DEFINE_ERROR
 
 // ---- FeatureStream (stream/stream.h:35-75) ------------------------------------------------------------------------
@@ -146,6 +153,11 @@ class FeatureStream {
   const String _name;
 };
 
+class VectorCharFeatureStream : public FeatureStream<btk_vector_char, char> {
+ protected:
+  VectorCharFeatureStream(unsigned sz, const String& nm) : FeatureStream<btk_vector_char, char>(sz, nm, 1) {}
+};
+typedef std::shared_ptr<VectorCharFeatureStream> VectorCharFeatureStreamPtr;
 class VectorFloatFeatureStream : public FeatureStream<btk_vector_float, float> {
  protected:
   VectorFloatFeatureStream(unsigned sz, const String& nm) : FeatureStream<btk_vector_float, float>(sz, nm, 1) {}
@@ -243,6 +255,210 @@ class PlanHandle {
   btkb200_plan* _p;
 };
 
+// ---- raw-PCM ingest nodes -------------------------------------------------------------------------------
+// byte block source over memory (what the Mark-III driver node delivers: packed big-endian 24-bit samples)
+class MemoryCharFeature : public VectorCharFeatureStream {
+ public:
+  MemoryCharFeature(const char* data, size_t n, unsigned blockLen, const String& nm = "MemoryChar")
+      : VectorCharFeatureStream(blockLen, nm), _d(data, data + n), _cur(0) {}
+  virtual const btk_vector_char* next(int frameX = -5) {
+    if (frameX == _frameX) return _vector;
+    if (_cur + _size > _d.size()) { _endOfSamples = true; throw jiterator_error("end of samples!"); }
+    memcpy(_vector->data, &_d[_cur], _size);
+    _cur += _size;
+    _increment();
+    return _vector;
+  }
+  virtual void reset() { VectorCharFeatureStream::reset(); _cur = 0; }
+ private:
+  std::vector<char> _d;
+  size_t _cur;
+};
+
+// Conversion24bit2Float (feature/feature.h:148-158, feature.cc:190-217): 3 bytes, most significant first, -> float.  The byte
+// stream is drained once and widened on the device in one call (btkb200_convert_pcm, bit-exact), then served in blocks.
+class Conversion24bit2Float : public VectorFloatFeatureStream {
+ public:
+  Conversion24bit2Float(VectorCharFeatureStreamPtr& src, const String& nm = "Conversion from 24 bit integer to Float")
+      : VectorFloatFeatureStream(src->size() / 3, nm), _src(src), _ready(false) {}
+  virtual void reset() { _src->reset(); VectorFloatFeatureStream::reset(); _ready = false; }
+  virtual const btk_vector_float* next(int frameX = -5) {
+    if (frameX == _frameX && _frameX >= 0) return _vector;
+    if (frameX >= 0 && frameX - 1 != _frameX)
+      throw jconsistency_error("Problem in Feature %s: %d != %d\n", name().c_str(), frameX - 1, _frameX);
+    if (!_ready) {
+      std::vector<char> raw;
+      for (;;) {
+        const btk_vector_char* b;
+        try { b = _src->next(); } catch (jiterator_error&) { break; }
+        raw.insert(raw.end(), b->data, b->data + b->size);
+      }
+      const long n = (long)(raw.size() / 3);
+      _all.assign((size_t)n + 1, 0.f);
+      if (n > 0) {
+        PlanHandle plan;
+        plan.create(64, 1, 0, 0, 1, 0, 0, 1);
+        check(btkb200_convert_pcm(plan.get(), &raw[0], BTKB200_PCM_S24BE, n, &_all[0]), plan.get());
+      }
+      _all.resize((size_t)n);
+      _ready = true;
+    }
+    const size_t t = (size_t)(_frameX + 1);
+    if ((t + 1) * _size > _all.size()) { _endOfSamples = true; throw jiterator_error("end of samples!"); }
+    memcpy(_vector->data, &_all[t * _size], sizeof(float) * _size);
+    _increment();
+    return _vector;
+  }
+ private:
+  VectorCharFeatureStreamPtr _src;
+  std::vector<float> _all;
+  bool _ready;
+};
+
+// ChannelExtractionFeature (feature/feature.h:1823-1841, feature.cc:3885-3900): out[i] = in[i chN + chX]
+class ChannelExtractionFeature : public VectorFloatFeatureStream {
+ public:
+  ChannelExtractionFeature(const VectorFloatFeatureStreamPtr& src, unsigned chX = 0, unsigned chN = 1, const String& nm = "ChannelExtraction")
+      : VectorFloatFeatureStream(src->size() / chN, nm), _src(src), _chX(chX), _chN(chN) {
+    if (chX >= chN || src->size() % chN != 0) throw jdimension_error("channel %d of %d out of blocks of %d", (int)chX, (int)chN, (int)src->size());
+  }
+  virtual void reset() { _src->reset(); VectorFloatFeatureStream::reset(); }
+  virtual const btk_vector_float* next(int frameX = -5) {
+    if (frameX == _frameX && _frameX >= 0) return _vector;
+    if (frameX >= 0 && frameX - 1 != _frameX)
+      throw jconsistency_error("Problem in Feature %s: %d != %d\n", name().c_str(), frameX - 1, _frameX);
+    _increment();
+    const btk_vector_float* all = _src->next(_frameX);
+    for (unsigned i = 0; i < _size; i++) _vector->data[i] = all->data[(i * _chN + _chX) * all->stride];
+    return _vector;
+  }
+ private:
+  VectorFloatFeatureStreamPtr _src;
+  unsigned _chX, _chN;
+};
+
+// IterativeSampleFeature (feature/feature.h:301-335, feature.cc:803-896): one node per channel of ONE interleaved file.  The
+// nodes share the file image (process-wide, like the reference's static members) and are pulled in lock step; the node of
+// channel firstChanX refills a 30-s buffer when its block counter wraps, so the stream is a whole number of buffers long,
+// zero padded, and ends at the first wrap after a short read (:880-892).  read() decodes RIFF/WAVE 16-bit PCM (or a
+// headerless 16-bit file with the given channel count) and widens it on the device (bit-exact; SFC_SET_NORM_FLOAT is off in
+// the reference, :849).  An analysis bank fed by such a node takes the channel's complete stream from whole_stream().
+class IterativeSampleFeature : public VectorFloatFeatureStream {
+ public:
+  IterativeSampleFeature(unsigned chX, unsigned blockLen = 320, unsigned firstChanX = 0, const String& nm = "Iterative Sample")
+      : VectorFloatFeatureStream(blockLen, nm), _blockLen(blockLen), _chanX(chX), _firstChanX(firstChanX), _cur(0), _last(false), _cto(-1) {}
+  void read(const String& fileName, int /*format*/ = 0, int samplerate = 44100, int chN = 1, int cfrom = 0, int cto = -1) {
+    if (_chanX != _firstChanX) return;
+    FILE* fp = fopen(fileName.c_str(), "rb");
+    if (!fp) throw jio_error("Could not open file %s.", fileName.c_str());
+    std::vector<unsigned char> bytes;
+    unsigned char buf[65536];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof buf, fp)) > 0) bytes.insert(bytes.end(), buf, buf + n);
+    fclose(fp);
+    size_t off = 0, len = bytes.size();
+    if (len >= 12 && !memcmp(&bytes[0], "RIFF", 4) && !memcmp(&bytes[8], "WAVE", 4)) {
+      size_t p = 12;
+      bool have_fmt = false;
+      off = len = 0;
+      while (p + 8 <= bytes.size()) {
+        const unsigned sz = bytes[p + 4] | (bytes[p + 5] << 8) | (bytes[p + 6] << 16) | ((unsigned)bytes[p + 7] << 24);
+        if (!memcmp(&bytes[p], "fmt ", 4) && sz >= 16) {
+          const unsigned fmt = bytes[p + 8] | (bytes[p + 9] << 8), bits = bytes[p + 22] | (bytes[p + 23] << 8);
+          chN = bytes[p + 10] | (bytes[p + 11] << 8);
+          samplerate = (int)(bytes[p + 12] | (bytes[p + 13] << 8) | (bytes[p + 14] << 16) | ((unsigned)bytes[p + 15] << 24));
+          if (fmt != 1 || bits != 16) throw jio_error("Could not open file %s: only 16-bit PCM WAVE files are decoded", fileName.c_str());
+          have_fmt = true;
+        } else if (!memcmp(&bytes[p], "data", 4)) {
+          off = p + 8; len = sz < bytes.size() - off ? sz : bytes.size() - off;
+          break;
+        }
+        p += 8 + sz + (sz & 1);
+      }
+      if (!have_fmt || off == 0) throw jio_error("sndfile error: %s.", "no fmt / data chunk");
+    }
+    readRaw(reinterpret_cast<const short*>(&bytes[off]), (long)(len / 2), samplerate, chN, cfrom, cto);
+  }
+  // the same with the interleaved 16-bit samples already in memory (n = number of int16 values)
+  void readRaw(const short* raw, long n, int samplerate, int chN, int cfrom = 0, int cto = -1) {
+    if (_chanX != _firstChanX) return;
+    if (cto > 0 && cto < cfrom) throw jconsistency_error("Segment cannot start at %d and end at %d", cfrom, cto);
+    Shared& S = shared();
+    n = n / chN * chN;
+    S.pcm.assign((size_t)n + 1, 0.f);
+    if (n > 0) {
+      PlanHandle plan;
+      plan.create(64, 1, 0, 0, 1, 0, 0, 1);
+      check(btkb200_convert_pcm(plan.get(), raw, BTKB200_PCM_S16, n, &S.pcm[0]), plan.get());
+    }
+    S.pcm.resize((size_t)n);
+    S.chN = chN; S.samplerate = samplerate; S.pos = cfrom; S.cfrom = cfrom;
+    S.blockN = S.interval * (unsigned)samplerate / _blockLen + 1;
+    S.sampleN = S.blockN * _blockLen;
+    S.buf.assign((size_t)S.sampleN * chN, 0.f);
+    _cto = cto - cfrom;
+  }
+  unsigned samplesN() const { return shared().ttl; }
+  void changeFirstChannelID(unsigned firstChanX) { _firstChanX = firstChanX; }
+  virtual void reset() { shared().ttl = 0; _cur = 0; _last = false; VectorFloatFeatureStream::reset(); }
+  virtual const btk_vector_float* next(int frameX = -5) {
+    if (frameX == _frameX && _frameX >= 0) return _vector;
+    Shared& S = shared();
+    if (S.buf.empty()) throw jio_error("no file has been read");
+    const unsigned currentFrame = _cur % S.blockN;
+    if (_chanX == _firstChanX && currentFrame == 0) {
+      if (_last || (_cto > 0 && (long)_cur * _blockLen > _cto)) { _endOfSamples = true; throw jiterator_error("end of samples!"); }
+      std::fill(S.buf.begin(), S.buf.end(), 0.f);
+      const long frames = (long)(S.pcm.size() / S.chN), left = frames - S.pos;
+      const unsigned readN = left <= 0 ? 0u : (left < (long)S.sampleN ? (unsigned)left : S.sampleN);
+      if (readN) memcpy(&S.buf[0], &S.pcm[(size_t)S.pos * S.chN], sizeof(float) * (size_t)readN * S.chN);
+      S.pos += readN;
+      S.ttl += readN;
+      if (readN < S.sampleN) _last = true;
+    }
+    const size_t offset = (size_t)currentFrame * S.chN * _blockLen;
+    for (unsigned i = 0; i < _blockLen; i++) _vector->data[i] = S.buf[offset + (size_t)i * S.chN + _chanX];
+    _cur++;
+    _increment();
+    return _vector;
+  }
+  // every sample this channel serves from reset() to the end of the stream under lock-step pulling; leaves the shared
+  // read position alone
+  void whole_stream(std::vector<float>& x) const {
+    const Shared& S = shared();
+    x.clear();
+    if (S.buf.empty()) throw jio_error("no file has been read");
+    const long frames = (long)(S.pcm.size() / S.chN);
+    long pos = S.cfrom, cur = 0;
+    bool last = false;
+    while (!(last || (_cto > 0 && cur * (long)_blockLen > _cto))) {
+      const long left = frames - pos;
+      const long n = left <= 0 ? 0 : (left < (long)S.sampleN ? left : (long)S.sampleN);
+      const size_t base = x.size();
+      x.resize(base + S.sampleN, 0.f);
+      for (long i = 0; i < n; i++) x[base + i] = S.pcm[(size_t)(pos + i) * S.chN + _chanX];
+      pos += n;
+      cur += S.blockN;
+      last = n < (long)S.sampleN;
+    }
+  }
+  bool unread() const { return _frameX < 0; }
+
+ private:
+  struct Shared {
+    std::vector<float> pcm, buf;
+    int chN, samplerate;
+    long pos, cfrom;
+    unsigned interval, blockN, sampleN, ttl;
+    Shared() : chN(0), samplerate(0), pos(0), cfrom(0), interval(30), blockN(0), sampleN(0), ttl(0) {}
+  };
+  static Shared& shared() { static Shared s; return s; }
+  const unsigned _blockLen, _chanX;
+  unsigned _firstChanX, _cur;
+  bool _last;
+  int _cto;
+};
+
 // ---- OverSampledDFTFilterBank geometry (modulated/modulated.cc:262-300) -------------------------------------------
 class OverSampledDFTFilterBank {
  public:
@@ -292,6 +508,9 @@ class OverSampledDFTAnalysisBank : public OverSampledDFTFilterBank, public Vecto
     x.clear();
     MemorySampleFeature* ms = dynamic_cast<MemorySampleFeature*>(pget(_samp));
     if (ms && ms->shiftLen() == _D && ms->padZeros() && ms->frameX() < 0) { x = ms->samples(); return; }
+    // the channels of one interleaved file share their read buffer and advance in lock step: take the whole stream at once
+    IterativeSampleFeature* it = dynamic_cast<IterativeSampleFeature*>(pget(_samp));
+    if (it && it->size() == _D && it->unread()) { it->whole_stream(x); return; }
     for (;;) {
       const btk_vector_float* b;
       try { b = _samp->next(); } catch (std::exception&) { break; }

@@ -136,6 +136,191 @@ class SampleFeaturePtr(FeatureStream):
         return self._vector
 
 
+class jio_error(j_error, IOError):
+    """common/jexception.h: jio_error (code JIO = 7 -> IOError in Python, include/jexception.i:66-68)."""
+
+
+class IterativeSampleFeaturePtr(FeatureStream):
+    """IterativeSampleFeature (feature/feature.h:301-335, feature.cc:803-896): one node per channel of ONE interleaved
+    multichannel file; the nodes share the file image (class-level state, as the reference's static members) and are
+    pulled in lock step.  The node of channel ``firstChanX`` refills a 30-s buffer whenever its block counter wraps; the
+    stream is therefore a whole number of buffers long, zero padded, and ends at the first wrap after a short read.
+
+    B200 evaluation: read() decodes the file once -- 16-bit PCM goes to the device as raw bytes and is widened there
+    (btkb200_convert_pcm, bit-exact; SFC_SET_NORM_FLOAT is off in the reference, feature.cc:849, so samples stay in the
+    int16 range).  Analysis banks fed by these nodes take the channel's complete stream in one piece (whole_stream())."""
+
+    _shared = {"pcm": None, "fs": 0, "chN": 0, "pos": 0, "buf": None, "blockN": 0, "sampleN": 0, "ttl": 0, "cfrom": 0}
+    _interval = 30
+
+    def __init__(self, chX: int, blockLen: int = 320, firstChanX: int = 0, nm: str = "Iterative Sample"):
+        super().__init__(blockLen, nm)
+        self._blockLen, self._chanX, self._firstChanX = int(blockLen), int(chX), int(firstChanX)
+        self._cur, self._last, self._cto = 0, False, -1
+        self._vector = np.zeros(blockLen, np.float32)
+
+    @staticmethod
+    def _decode(fileName, samplerate, chN):
+        """(raw int16 interleaved, samplerate, channels) of a RIFF/WAVE file with 16-bit PCM, or of a headerless file."""
+        import wave
+        with open(fileName, "rb") as f:
+            head = f.read(12)
+        if head[:4] == b"RIFF" and head[8:12] == b"WAVE":
+            with wave.open(fileName, "rb") as w:
+                if w.getsampwidth() != 2:
+                    raise jio_error(f"Could not open file {fileName}: only 16-bit PCM WAVE files are decoded")
+                raw = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2")
+                return raw, w.getframerate(), w.getnchannels()
+        return np.fromfile(fileName, dtype="<i2"), samplerate, chN
+
+    def read(self, fileName: str, format: int = 0, samplerate: int = 44100, chN: int = 1, cfrom: int = 0, cto: int = -1):
+        """feature.cc:826-866."""
+        if self._chanX != self._firstChanX:
+            return
+        try:
+            raw, fs, ch = self._decode(fileName, samplerate, chN)
+        except OSError as e:
+            raise jio_error(f"Could not open file {fileName}.") from e
+        self.readRaw(raw, fs, ch, cfrom, cto)
+
+    def readRaw(self, raw_s16, samplerate: int, chN: int, cfrom: int = 0, cto: int = -1):
+        """The same with the interleaved 16-bit samples already in memory."""
+        if self._chanX != self._firstChanX:
+            return
+        raw = np.ascontiguousarray(raw_s16, dtype=np.int16).ravel()
+        raw = raw[: raw.size // chN * chN]
+        try:
+            with Plan(64, 1, 0, 1) as plan:
+                pcm = plan.convert_pcm(raw, _capi.PCM_S16).reshape(-1, chN)
+        except BtkError as e:
+            _raise(e)
+        if cto > 0 and cto < cfrom:
+            raise jconsistency_error(f"Segment cannot start at {cfrom} and end at {cto}")
+        S = IterativeSampleFeaturePtr._shared
+        S["pcm"], S["fs"], S["chN"], S["pos"], S["cfrom"] = pcm, int(samplerate), int(chN), int(cfrom), int(cfrom)
+        S["blockN"] = self._interval * int(samplerate) // self._blockLen + 1
+        S["sampleN"] = S["blockN"] * self._blockLen
+        S["buf"] = np.zeros((S["sampleN"], chN), np.float32)
+        self._cto = cto - cfrom
+
+    def samplesN(self):
+        return IterativeSampleFeaturePtr._shared["ttl"]
+
+    def changeFirstChannelID(self, firstChanX: int):
+        self._firstChanX = int(firstChanX)
+
+    def reset(self):
+        super().reset()
+        IterativeSampleFeaturePtr._shared["ttl"] = 0
+        self._cur, self._last = 0, False
+
+    def next(self, frameX: int = -5):
+        if frameX == self._frameX:
+            return self._vector
+        S = IterativeSampleFeaturePtr._shared
+        if S["pcm"] is None:
+            raise jio_error("no file has been read")
+        cf = self._cur % S["blockN"]
+        if self._chanX == self._firstChanX and cf == 0:
+            if self._last or (self._cto > 0 and self._cur * self._blockLen > self._cto):
+                raise jiterator_error("end of samples!")
+            S["buf"][:] = 0.0
+            n = max(0, min(S["sampleN"], S["pcm"].shape[0] - S["pos"]))
+            S["buf"][:n] = S["pcm"][S["pos"]:S["pos"] + n]
+            S["pos"] += n
+            S["ttl"] += n
+            if n < S["sampleN"]:
+                self._last = True
+        self._vector[:] = S["buf"][cf * self._blockLen:(cf + 1) * self._blockLen, self._chanX]
+        self._cur += 1
+        self._frameX += 1
+        return self._vector
+
+    def whole_stream(self) -> np.ndarray:
+        """Every sample this channel's node serves from reset() to end of stream when all channels are pulled in lock step
+        (the reference's use): the segment from cfrom, zero padded to whole buffers, ending at the first wrap after a short
+        read or past cto.  Does not touch the shared read position."""
+        S = IterativeSampleFeaturePtr._shared
+        if S["pcm"] is None:
+            raise jio_error("no file has been read")
+        T = S["pcm"].shape[0]
+        pos, cur, last, pieces = S["cfrom"], 0, False, []
+        while not (last or (self._cto > 0 and cur * self._blockLen > self._cto)):
+            n = max(0, min(S["sampleN"], T - pos))
+            seg = np.zeros(S["sampleN"], np.float32)
+            seg[:n] = S["pcm"][pos:pos + n, self._chanX]
+            pieces.append(seg)
+            pos += n
+            cur += S["blockN"]
+            last = n < S["sampleN"]
+        return np.concatenate(pieces) if pieces else np.zeros(0, np.float32)
+
+
+class ChannelExtractionFeaturePtr(FeatureStream):
+    """ChannelExtractionFeature (feature/feature.h:1823-1841, feature.cc:3885-3900): channel chX of chN out of a stream of
+    interleaved blocks; output block i = input[i * chN + chX]."""
+
+    def __init__(self, src, chX: int = 0, chN: int = 1, nm: str = "ChannelExtraction"):
+        if chX >= chN or src.size() % chN != 0:
+            raise jdimension_error(f"channel {chX} of {chN} out of blocks of {src.size()}")
+        super().__init__(src.size() // chN, nm)
+        self._src, self._chX, self._chN = src, int(chX), int(chN)
+        self._vector = np.zeros(self._size, np.float32)
+
+    def reset(self):
+        self._src.reset()
+        super().reset()
+
+    def next(self, frameX: int = -5):
+        if frameX == self._frameX:
+            return self._vector
+        if frameX >= 0 and frameX - 1 != self._frameX:
+            raise jconsistency_error(f"Problem in Feature {self._name}: {frameX - 1} != {self._frameX}")
+        self._frameX += 1
+        allch = np.asarray(self._src.next(self._frameX), np.float32)
+        self._vector[:] = allch[self._chX::self._chN][: self._size]
+        return self._vector
+
+
+class Conversion24bit2FloatPtr(FeatureStream):
+    """Conversion24bit2Float (feature/feature.h:148-158, feature.cc:190-217): packed big-endian 24-bit samples (the
+    Mark-III/IV wire format, 3 bytes per sample) -> float.  B200 evaluation: the byte stream is drained once and widened on
+    the device in one call (btkb200_convert_pcm, BTKB200_PCM_S24BE; bit-exact), then served block by block."""
+
+    def __init__(self, src, nm: str = "Conversion from 24 bit integer to Float"):
+        super().__init__(src.size() // 3, nm)
+        self._src = src
+        self._all = None
+        self._vector = np.zeros(self._size, np.float32)
+
+    def reset(self):
+        self._src.reset()
+        super().reset()
+        self._all = None
+
+    def next(self, frameX: int = -5):
+        if frameX == self._frameX:
+            return self._vector
+        if frameX >= 0 and frameX - 1 != self._frameX:
+            raise jconsistency_error(f"Problem in Feature {self._name}: {frameX - 1} != {self._frameX}")
+        if self._all is None:
+            blocks = _drain(self._src)
+            raw = np.concatenate([np.asarray(b).astype(np.uint8) for b in blocks]) if blocks else np.zeros(0, np.uint8)
+            raw = raw[: raw.size // 3 * 3].reshape(-1, 3)
+            try:
+                with Plan(64, 1, 0, 1) as plan:
+                    self._all = plan.convert_pcm(raw, _capi.PCM_S24BE) if raw.size else np.zeros(0, np.float32)
+            except BtkError as e:
+                _raise(e)
+        t = self._frameX + 1
+        if (t + 1) * self._size > self._all.size:
+            self._endOfSamples = True
+            raise jiterator_error("end of samples!")
+        self._vector[:] = self._all[t * self._size:(t + 1) * self._size]
+        self._frameX = t
+        return self._vector
+
+
 def _drain(stream) -> list:
     """Pull every remaining frame of an upstream node or plain iterator (copies: upstream reuses its buffer)."""
     frames = []
@@ -193,6 +378,10 @@ class OverSampledDFTAnalysisBankPtr(FeatureStream, _FilterBank):
         s = self._samp
         if isinstance(s, SampleFeaturePtr) and s.size() == self._D and s._shift == self._D and s._pad:
             return s.samples()
+        if isinstance(s, IterativeSampleFeaturePtr) and s.size() == self._D and s._frameX == FrameResetX:
+            # the channels of one interleaved file share their read buffer and have to advance in lock step; a bank takes
+            # its channel's complete stream in one piece instead
+            return s.whole_stream()
         return None
 
     def _pull_source(self) -> np.ndarray:

@@ -59,6 +59,23 @@ def noise_recording(T: int, C: int, seed: int, sigma: float = 1000.0) -> np.ndar
     return (sigma * rng.standard_normal((T, C))).astype(np.float32)
 
 
+_DESIGNED = {}
+
+
+def designed_prototype(M: int, m: int, r: int) -> tuple[np.ndarray, np.ndarray]:
+    """Analysis/synthesis prototypes for an (M, m, r) without a reference fixture, DESIGNED on the device with the
+    reference's de Haan procedure (btkb200_design_analysis_prototype / _synthesis_prototype: h = pinv(A + C) b,
+    g = pinv(E + v P) f, modulated/prototypeDesign.cc:611-951, v = 1, wpFactor = 1, tolerance 1e-7).  Cached per process;
+    needs a CUDA device (the stand-in below is what the CPU-only tests use)."""
+    key = (int(M), int(m), int(r))
+    if key not in _DESIGNED:
+        from . import _capi
+        h, _ = _capi.design_analysis_prototype(M, m, r)
+        g, _ = _capi.design_synthesis_prototype(h, M, m, r, 1.0)
+        _DESIGNED[key] = (h, g)
+    return _DESIGNED[key]
+
+
 def kaiser_prototype(M: int, m: int, r: int, beta: float = 8.0) -> tuple[np.ndarray, np.ndarray]:
     """Stand-in analysis/synthesis prototypes for (M, m, r) without a reference fixture: Kaiser-windowed
     sinc low-pass with cut-off pi/M, unit DC gain for h and D-scaled for g.  Throughput does not depend on

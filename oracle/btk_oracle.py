@@ -648,6 +648,13 @@ class CompiledReference:
         L.btkref_spectral_matrix.argtypes = [vp, cl, ci, vp, ci, ci, ci, ci, cd, vp]
         L.btkref_error_probe.restype = ci
         L.btkref_error_probe.argtypes = [ci]
+        if hasattr(L, "btkref_iterative_sample"):
+            L.btkref_iterative_sample.restype = cl
+            L.btkref_iterative_sample.argtypes = [vp, cl, ci, ci, ci, ci, ci, vp, cl, ctypes.POINTER(cl)]
+            L.btkref_conversion24.restype = cl
+            L.btkref_conversion24.argtypes = [vp, cl, ci, vp]
+            L.btkref_channel_extraction.restype = cl
+            L.btkref_channel_extraction.argtypes = [vp, cl, ci, ci, ci, vp]
         if hasattr(L, "btkref_design_nyquist"):
             L.btkref_design_nyquist.restype = ci
             L.btkref_design_nyquist.argtypes = [ci, ci, ci, cd, cd, vp, vp, vp, vp]
@@ -778,6 +785,33 @@ class CompiledReference:
             raise RuntimeError(f"btkref_design_dehaan returned {rc}")
         return h, g, eh, eg
 
+    def iterative_sample(self, pcm, samplerate, blockLen, cfrom=0, cto=-1):
+        """IterativeSampleFeature::next of the reference (extracted from feature/feature.cc at build time), one node per
+        channel pulled in lock step: (blocks [n][C][blockLen], samples read)."""
+        x = np.ascontiguousarray(pcm, dtype=np.float32)
+        T, C = x.shape
+        blockN = 30 * samplerate // blockLen + 1
+        cap = (T // (blockN * blockLen) + 2) * blockN
+        out = np.zeros((cap, C, blockLen), np.float32)
+        ttl = ctypes.c_long(0)
+        n = self.lib.btkref_iterative_sample(_dp(x), T, samplerate, C, blockLen, cfrom, cto, _dp(out), cap, ctypes.byref(ttl))
+        if n < 0 or n > cap:
+            raise RuntimeError(f"btkref_iterative_sample returned {n}")
+        return out[:n], int(ttl.value)
+
+    def conversion24(self, raw, block):
+        """Conversion24bit2Float::next of the reference over packed big-endian 24-bit bytes (uint8 [n][3])."""
+        b = np.ascontiguousarray(raw, dtype=np.uint8).reshape(-1)
+        out = np.zeros(b.size // 3, np.float32)
+        n = self.lib.btkref_conversion24(_dp(b), b.size, block, _dp(out))
+        return out[:n]
+
+    def channel_extraction(self, data, chX, chN, block):
+        x = np.ascontiguousarray(data, dtype=np.float32).reshape(-1)
+        out = np.zeros(x.size // chN, np.float32)
+        n = self.lib.btkref_channel_extraction(_dp(x), x.size, chX, chN, block, _dp(out))
+        return out[:n]
+
     def design_nyquist(self, M, m, r, wp_factor=1.0, tol=1e-7):
         """AnalysisNyquistMDesign then SynthesisNyquistMDesign of the compiled reference: (h, g)."""
         L = M * m
@@ -840,6 +874,36 @@ def ingest_s24be(raw: np.ndarray) -> np.ndarray:
     v = (b[..., 0] << 16) | (b[..., 1] << 8) | b[..., 2]
     v = np.where(b[..., 0] & 128, v - (1 << 24), v)
     return v.astype(np.float32)
+
+
+def iterative_sample_blocks(pcm: np.ndarray, samplerate: int, blockLen: int, cfrom: int = 0, cto: int = -1, interval: int = 30):
+    """IterativeSampleFeature (feature/feature.cc:803-896) for every channel of an interleaved recording pulled in lock step:
+    the node of channel `firstChanX` refills a shared buffer of _blockN = interval * samplerate / blockLen + 1 blocks
+    (zeroed first, :886-888) whenever its block counter wraps; a short read sets _last and the stream ends at the NEXT wrap
+    (:880-884) -- so the stream is a whole number of 30-s buffers long, zero padded.  With cto > 0 the end test is
+    cur * blockLen > cto - cfrom, evaluated only at a wrap.  pcm: [T][C].  Returns (blocks [n][C][blockLen], samples read)."""
+    pcm = np.asarray(pcm, dtype=np.float32)
+    T, C = pcm.shape
+    blockN = interval * samplerate // blockLen + 1
+    sampleN = blockN * blockLen
+    pos, ctor, cur, last, ttl = cfrom, cto - cfrom, 0, False, 0
+    buf = np.zeros((sampleN, C), np.float32)
+    out = []
+    while True:
+        cf = cur % blockN
+        if cf == 0:
+            if last or (ctor > 0 and cur * blockLen > ctor):
+                break
+            buf[:] = 0
+            n = max(0, min(sampleN, T - pos))
+            buf[:n] = pcm[pos:pos + n]
+            pos += n
+            ttl += n
+            if n < sampleN:
+                last = True
+        out.append(buf[cf * blockLen:(cf + 1) * blockLen].T.copy())
+        cur += 1
+    return (np.stack(out) if out else np.zeros((0, C, blockLen), np.float32)), ttl
 
 
 def rel_l2(a: np.ndarray, b: np.ndarray) -> float:

@@ -667,6 +667,181 @@ int btkref_calc_all_delays(double x, double y, double z, const double* micpos, i
 // _ref/obj/calc_delays_polar2.inc at build time, so the function below is the reference's text, compiled -- not a copy kept
 // in this repository.
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Ingest nodes: IterativeSampleFeature::next (feature/feature.cc:868-896), Conversion24bit2Float::next
+// (:190-217), ChannelExtractionFeature::next (:3885-3900).  feature.cc itself needs libsndfile and much of GSL, so
+// oracle/Makefile extracts exactly those three definitions into _ref/obj/ingest_next.inc; they are compiled here, verbatim,
+// as members of classes that DECLARE the same members as feature/feature.h:148-158, 301-335, 1823-1841 (constructors and
+// read() restated from :803-866: the interval buffer of 30 s, _blockN = interval * samplerate / blockLen + 1).  The only
+// stand-in is sf_readf_float, which reads interleaved floats from memory (libsndfile with SFC_SET_NORM_FLOAT off hands
+// the integer sample values over unscaled, :849).
+namespace ingest_ref {
+namespace sndfile {
+struct SNDFILE { const float* data; long frames; long pos; int channels; };
+struct SF_INFO { long frames; int samplerate, channels, format; };
+}
+static unsigned sf_readf_float(sndfile::SNDFILE* f, float* dst, unsigned n) {
+  long left = f->frames - f->pos;
+  unsigned got = left <= 0 ? 0 : (left < (long)n ? (unsigned)left : n);
+  memcpy(dst, f->data + f->pos * f->channels, sizeof(float) * (size_t)got * f->channels);
+  f->pos += got;
+  return got;
+}
+
+class IterativeSampleFeature : public VectorFloatFeatureStream {
+ public:
+  IterativeSampleFeature(unsigned chX, unsigned blockLen = 320, unsigned firstChanX = 0, const String& nm = "Iterative Sample")
+      : VectorFloatFeatureStream(blockLen, nm), _blockLen(blockLen), _chanX(chX), _firstChanX(firstChanX), _cur(0) {}
+  // read() of the reference with the file replaced by a memory image (:826-866)
+  void read_memory(const float* data, long frames, int samplerate, int chN, int cfrom, int cto) {
+    if (_chanX != _firstChanX) return;
+    delete[] _allSamples; _allSamples = NULL;
+    delete _sndfile;
+    _sfinfo.channels = chN; _sfinfo.samplerate = samplerate; _sfinfo.format = 0;
+    _sndfile = new sndfile::SNDFILE();
+    _sndfile->data = data; _sndfile->frames = frames; _sndfile->pos = 0; _sndfile->channels = chN;
+    _blockN = _interval * _sfinfo.samplerate / _blockLen + 1;
+    _sampleN = _blockN * _blockLen;
+    _allSampleN = _sampleN * _sfinfo.channels;
+    _allSamples = new float[_allSampleN];
+    _sndfile->pos = cfrom;
+    _cto = cto - cfrom;
+  }
+  unsigned samplesN() const { return _ttlSamples; }
+  virtual const gsl_vector_float* next(int frameX = -5);
+  virtual void reset() { _ttlSamples = _cur = 0; _last = false; VectorFloatFeatureStream::reset(); }
+
+ private:
+  static float* _allSamples;
+  static sndfile::SNDFILE* _sndfile;
+  static sndfile::SF_INFO _sfinfo;
+  static unsigned _interval, _blockN, _sampleN, _allSampleN, _ttlSamples;
+  const unsigned _blockLen;
+  const unsigned _chanX;
+  unsigned _firstChanX;
+  unsigned _cur;
+  bool _last;
+  int _cto;
+};
+float* IterativeSampleFeature::_allSamples = NULL;
+sndfile::SNDFILE* IterativeSampleFeature::_sndfile = NULL;
+sndfile::SF_INFO IterativeSampleFeature::_sfinfo;
+unsigned IterativeSampleFeature::_interval = 30;
+unsigned IterativeSampleFeature::_blockN;
+unsigned IterativeSampleFeature::_sampleN;
+unsigned IterativeSampleFeature::_allSampleN;
+unsigned IterativeSampleFeature::_ttlSamples;
+
+class Conversion24bit2Float : public VectorFloatFeatureStream {
+ public:
+  Conversion24bit2Float(VectorCharFeatureStreamPtr& src, const String& nm = "Conversion from 24 bit integer to Float")
+      : VectorFloatFeatureStream(src->size() / 3, nm), _src(src) {}
+  virtual void reset() { _src->reset(); VectorFloatFeatureStream::reset(); }
+  virtual const gsl_vector_float* next(int frameX = -5);
+ private:
+  VectorCharFeatureStreamPtr _src;
+};
+
+class ChannelExtractionFeature : public VectorFloatFeatureStream {
+ public:
+  ChannelExtractionFeature(const VectorFloatFeatureStreamPtr& src, unsigned chX = 0, unsigned chN = 1, const String& nm = "ChannelExtraction")
+      : VectorFloatFeatureStream(src->size() / chN, nm), _src(src), _chX(chX), _chN(chN) {}
+  virtual const gsl_vector_float* next(int frameX = -5);
+  virtual void reset() { _src->reset(); VectorFloatFeatureStream::reset(); }
+ private:
+  VectorFloatFeatureStreamPtr _src;
+  unsigned _chX, _chN;
+};
+
+#include "ingest_next.inc"
+
+// block sources over memory for the two wrappers
+class MemoryCharFeature : public VectorCharFeatureStream {
+ public:
+  MemoryCharFeature(const char* data, long n, unsigned block) : VectorCharFeatureStream(block, "MemoryChar"), _d(data), _n(n), _cur(0) {}
+  virtual const gsl_vector_char* next(int frameX = -5) {
+    if (frameX == _frameX) return _vector;
+    if (_cur + (long)size() > _n) throw jiterator_error("end of samples!");
+    for (unsigned i = 0; i < size(); i++) gsl_vector_char_set(_vector, i, _d[_cur + i]);
+    _cur += size();
+    _increment();
+    return _vector;
+  }
+  virtual void reset() { _cur = 0; VectorCharFeatureStream::reset(); }
+ private:
+  const char* _d; long _n, _cur;
+};
+class MemoryFloatBlocks : public VectorFloatFeatureStream {
+ public:
+  MemoryFloatBlocks(const float* data, long n, unsigned block) : VectorFloatFeatureStream(block, "MemoryFloat"), _d(data), _n(n), _cur(0) {}
+  virtual const gsl_vector_float* next(int frameX = -5) {
+    if (frameX == _frameX) return _vector;
+    if (_cur + (long)size() > _n) throw jiterator_error("end of samples!");
+    for (unsigned i = 0; i < size(); i++) gsl_vector_float_set(_vector, i, _d[_cur + i]);
+    _cur += size();
+    _increment();
+    return _vector;
+  }
+  virtual void reset() { _cur = 0; VectorFloatFeatureStream::reset(); }
+ private:
+  const float* _d; long _n, _cur;
+};
+}  // namespace ingest_ref
+
+extern "C" {
+// All channels of an interleaved recording through chN IterativeSampleFeature nodes pulled in lock step, the way the
+// multichannel drivers do (channel `firstChanX` first).  out: [cap_blocks][chN][blockLen]; returns blocks served per channel.
+long btkref_iterative_sample(const float* data, long frames, int samplerate, int chN, int blockLen, int cfrom, int cto,
+                             float* out, long cap_blocks, long* ttl_samples) {
+  try {
+    std::vector<VectorFloatFeatureStreamPtr> nodes;
+    std::vector<ingest_ref::IterativeSampleFeature*> raw;
+    for (int c = 0; c < chN; c++) {
+      ingest_ref::IterativeSampleFeature* f = new ingest_ref::IterativeSampleFeature(c, blockLen, 0);
+      raw.push_back(f); nodes.push_back(VectorFloatFeatureStreamPtr(f));
+    }
+    for (int c = 0; c < chN; c++) { raw[c]->reset(); raw[c]->read_memory(data, frames, samplerate, chN, cfrom, cto); }
+    long n = 0;
+    try {
+      for (;;) {
+        for (int c = 0; c < chN; c++) {
+          const gsl_vector_float* b = nodes[c]->next();
+          if (n < cap_blocks) for (int i = 0; i < blockLen; i++) out[((size_t)n * chN + c) * blockLen + i] = gsl_vector_float_get(b, i);
+        }
+        n++;
+        if (n > cap_blocks + 8) break;
+      }
+    } catch (jiterator_error&) {}
+    if (ttl_samples) *ttl_samples = raw[0]->samplesN();
+    return n;
+  } catch (std::exception& e) { fprintf(stderr, "btkref_iterative_sample: %s\n", e.what()); return -1; }
+}
+
+// Conversion24bit2Float over a byte stream cut into blocks of 3 * block bytes.  Returns samples written.
+long btkref_conversion24(const char* bytes, long nbytes, int block, float* out) {
+  try {
+    VectorCharFeatureStreamPtr src(new ingest_ref::MemoryCharFeature(bytes, nbytes, 3 * block));
+    ingest_ref::Conversion24bit2Float conv(src);
+    long n = 0;
+    try { for (;;) { const gsl_vector_float* b = conv.next(); for (int i = 0; i < block; i++) out[n++] = gsl_vector_float_get(b, i); } }
+    catch (jiterator_error&) {}
+    return n;
+  } catch (std::exception& e) { fprintf(stderr, "btkref_conversion24: %s\n", e.what()); return -1; }
+}
+
+// ChannelExtractionFeature(chX of chN) over interleaved blocks of chN * block floats.  Returns samples written.
+long btkref_channel_extraction(const float* data, long n, int chX, int chN, int block, float* out) {
+  try {
+    VectorFloatFeatureStreamPtr src(new ingest_ref::MemoryFloatBlocks(data, n, chN * block));
+    ingest_ref::ChannelExtractionFeature ext(src, chX, chN);
+    long k = 0;
+    try { for (;;) { const gsl_vector_float* b = ext.next(); for (int i = 0; i < block; i++) out[k++] = gsl_vector_float_get(b, i); } }
+    catch (jiterator_error&) {}
+    return k;
+  } catch (std::exception& e) { fprintf(stderr, "btkref_channel_extraction: %s\n", e.what()); return -1; }
+}
+}  // extern "C"
 #include "calc_delays_polar2.inc"
 extern "C" {
 int btkref_calc_delays_polar2(float azimuth, float elevation, const double* micpos, int n, double* delays) {

@@ -10,6 +10,9 @@
 //                                                    target delays) -> frames pulled one by one, every frame's snapshots
 //                                                    (getSnapShotArray) folded into a SpectralMatrixArray (mu 0.95), read
 //                                                    after 10 frames and at the end; writes Y[4], R[M][C][C], w[B][C]
+//   test_streams chain <in.bin> <out.bin> <file.wav>   mode 5: the channels come from ONE interleaved 16-bit WAVE file through
+//                                            IterativeSampleFeature nodes (feature.cc:803-896), DS chain as in mode 0; the first
+//                                            two blocks of channel 1 pulled in lock step are appended to the output
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -68,10 +71,29 @@ int main(int argc, char** argv) {
   try {
     btk_vector hv = make_vec(h), gv = make_vec(g), tv = make_vec(tau);
     std::shared_ptr<SubbandDS> bf(mode == 1 ? new SubbandMVDR(M) : mode == 3 ? new SubbandGSC(M) : new SubbandDS(M));
+    std::vector<float> lockstep;
+    if (mode == 5) {
+      if (argc < 5) return 2;
+      // lock-step pulling, the reference's use: every channel's node, block after block
+      std::vector<std::shared_ptr<IterativeSampleFeature> > nodes;
+      for (int c = 0; c < C; c++) nodes.push_back(std::shared_ptr<IterativeSampleFeature>(new IterativeSampleFeature(c, D, 0)));
+      for (int c = 0; c < C; c++) { nodes[c]->reset(); nodes[c]->read(argv[4]); }
+      for (int b = 0; b < 2; b++)
+        for (int c = 0; c < C; c++) { const btk_vector_float* v = nodes[c]->next(); if (c == 1 % C) lockstep.insert(lockstep.end(), v->data, v->data + v->size); }
+      if (nodes[0]->samplesN() == 0) return 3;
+    }
     for (int c = 0; c < C; c++) {
       std::vector<float> x(T);
       for (int t = 0; t < T; t++) x[t] = pcm[(size_t)t * C + c];
-      VectorFloatFeatureStreamPtr sample(new MemorySampleFeature(x.data(), x.size(), D, D, true));
+      VectorFloatFeatureStreamPtr sample;
+      if (mode == 5) {
+        std::shared_ptr<IterativeSampleFeature> it(new IterativeSampleFeature(c, D, 0));
+        it->reset();
+        it->read(argv[4]);
+        sample = it;
+      } else {
+        sample.reset(new MemorySampleFeature(x.data(), x.size(), D, D, true));
+      }
       VectorComplexFeatureStreamPtr analysis(new OverSampledDFTAnalysisBank(sample, &hv, M, m, r, dct));
       bf->setChannel(analysis);
     }
@@ -185,6 +207,7 @@ int main(int argc, char** argv) {
       try { const btk_vector_float* b = push.next(); pushed.insert(pushed.end(), b->data, b->data + b->size); }
       catch (jiterator_error&) {}      // still priming: not enough frames yet
     }
+    if (mode == 5) pushed = lockstep;
     FILE* o = fopen(argv[3], "wb");
     int oh[4] = {(int)out.size(), fused, (int)Y.size(), (int)pushed.size()};
     fwrite(oh, sizeof(int), 4, o);

@@ -19,7 +19,7 @@ dev = torch.device("cuda", 0)
 
 def run(M, m, r, C, nb, steps=10):
     key = f"h_{M}_{m}_{r}"
-    h, g = (P[key], P[f"g_{M}_{m}_{r}"]) if key in P.files else wl.kaiser_prototype(M, m, r)
+    h, g = (P[key], P[f"g_{M}_{m}_{r}"]) if key in P.files else wl.designed_prototype(M, m, r)   # no fixture: designed on the device (de Haan)
     plan = btk_b200.Plan(M, m, r, C, h, g)
     tau = wl.farfield_delays(wl.linear_array(C, 20.0), np.deg2rad(30), np.deg2rad(90))
     plan.set_ds_weights(FS, tau)
