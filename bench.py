@@ -436,7 +436,7 @@ def measure(wl_cfg, mode, nb, args, rank, world, local_rank, dev, config_id, ste
             plan.chain_zelinski_batch_into(xs, outs, 0.6, 2, 0)
         torch.cuda.synchronize()
         res["pf_s"] = (time.perf_counter() - t0) / e2e_steps
-    res.update(nblk=nblk, D=D, T=T, n_in=n_in, n_out=n_out, nb=nb, first=first)
+    res.update(nblk=nblk, D=D, T=T, n_in=n_in, n_out=n_out, nb=nb, first=mine[0])
     plan.close()
     del d_in, d_out, h_in, h_out
     torch.cuda.empty_cache()

@@ -9,6 +9,8 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>
+
 #include "../../include/btkb200.h"
 #include "host_tables.h"
 #include "launch.h"
@@ -67,6 +69,9 @@ struct btkb200_plan {
   cf* d_ta = nullptr;          // [B][C] array manifold (time alignment of the post-filter)
   // scratch
   DevBuf d_recs, d_work, d_in, d_out, d_aux, d_aux2, d_raw, d_adapt;
+  DevBuf d_tmaps;                         // one CUtensorMap per recording of the prepared batch (warp-specialised chain)
+  std::vector<long long> tmap_sig;        // batch signature + base pointer the maps were built for
+  int tma_rows = 0;
   PinBuf h_desc;
   std::vector<long long> sig;  // signature of the cached chain work list
   int cached_n_work = 0;
@@ -255,7 +260,7 @@ void btkb200_plan_destroy(btkb200_plan* p) {
   cudaSetDevice(p->device);
   if (p->stream) cudaStreamSynchronize(p->stream);
   cudaFree(p->d_taps_h); cudaFree(p->d_taps_g); cudaFree(p->d_twa); cudaFree(p->d_twb); cudaFree(p->d_wts_chain); cudaFree(p->d_w); cudaFree(p->d_ta);
-  p->d_recs.release(); p->d_work.release(); p->d_in.release(); p->d_out.release(); p->d_aux.release(); p->d_aux2.release(); p->d_raw.release(); p->d_adapt.release();
+  p->d_recs.release(); p->d_work.release(); p->d_in.release(); p->d_out.release(); p->d_aux.release(); p->d_aux2.release(); p->d_raw.release(); p->d_adapt.release(); p->d_tmaps.release();
   p->h_desc.release();
   if (p->stream) cudaStreamDestroy(p->stream);
   if (p->s_in) cudaStreamDestroy(p->s_in);
@@ -704,23 +709,26 @@ static int chain_prepare(btkb200_plan* p, const long long* pcm_off, const long l
   {
     static const int ws_env = getenv("BTK_CHAIN_WS") ? atoi(getenv("BTK_CHAIN_WS")) : -1;
     const int Wws = chain_ws_frames_per_iter(p->geo.M, p->geo.R, p->geo.m);
-    // automatic choice: from M = 256 up (M = 128 measured 4 % slower than the first sessions' kernel with two CTAs per SM)
-    p->use_ws = (Wws > 0 && (p->tune_ws >= 0 ? p->tune_ws != 0 : (ws_env >= 0 ? ws_env != 0 : p->geo.M >= 256))) ? 1 : 0;
+    // automatic choice: from M = 128 up (M = 128: 0.2711 ms against 0.2727 ms for the first sessions' kernel with two CTAs per
+    // SM once the tensor-copy producer feeds it; M = 64 stays with the old kernel)
+    p->use_ws = (Wws > 0 && (p->tune_ws >= 0 ? p->tune_ws != 0 : (ws_env >= 0 ? ws_env != 0 : p->geo.M >= 128))) ? 1 : 0;
     p->cluster = 1;
     if (p->use_ws) {
       // Channel split over a thread-block cluster: S CTAs share a work item, each stages only its own channel groups and
       // the partial beamformer outputs are summed through distributed shared memory.  Without it one CTA walks the rows
       // of interleaved PCM (all channels per row) Cpad/4 times out of L2, and the windows of 148 CTAs have to survive
       // there: 111 MB at 64 channels (M = 512), 189 MB for M = 256.  The split costs a rendezvous and two
-      // exchanges per iteration while the transforms per CTA shrink by S, so the smallest power of two that brings the
-      // windows in flight under 0.45 x L2 is used (measured: M = 256, 64 channels 0.90 -> 0.81 ms at S = 4 and 1.12 ms at
-      // S = 8; M = 512, 64 channels 1.88 ms at S = 1 and 2, 2.48 at 4, 3.27 at 8; 16 channels always best unsplit).
+      // exchanges per iteration while the transforms per CTA shrink by S.  With the tensor-copy producer (which fetches
+      // full 128-byte lines into L2 and keeps the load/store unit out of it) the unsplit kernel stays ahead until the
+      // windows in flight exceed L2 itself: measured M = 512, 64 channels (111 MB) 1.25 ms at S = 1, 1.36 at 2, 1.91 at 4;
+      // M = 256, 64 channels (189 MB) 0.473 / 0.427 / 0.505 ms; 32 channels (95 MB) 0.403 / 0.454 ms.  So: the smallest power
+      // of two that brings the windows in flight under 1.2 x L2.
       static const int cl_env = getenv("BTK_CLUSTER") ? atoi(getenv("BTK_CLUSTER")) : 0;
       const int n_groups = p->Cpad / 4;
       const double window_all = (double)(Wws - 1 + p->geo.m * p->geo.R) * p->geo.D * p->Cpad * sizeof(float);
       int S = 1;
       while (S < 8 && n_groups % (2 * S) == 0 && chain_ws_cluster_ok(p->geo.M, p->geo.R, p->geo.m, 2 * S) &&
-             148.0 * window_all / S > 0.45 * l2)
+             148.0 * window_all / S > 1.2 * l2)
         S *= 2;
       if (cl_env > 0 && n_groups % cl_env == 0 && chain_ws_cluster_ok(p->geo.M, p->geo.R, p->geo.m, cl_env)) S = cl_env;
       if (p->tune_cluster > 0) S = p->tune_cluster;     // validated by btkb200_plan_tune
@@ -768,6 +776,59 @@ static int chain_prepare(btkb200_plan* p, const long long* pcm_off, const long l
   return BTKB200_OK;
 }
 
+// ---- tensor maps of the prepared batch (warp-specialised chain with the raw window layout) -----------------------------
+// Recording i of the batch is described to the tensor copy engine as a 2-D float tensor [T_i][C] at d_pcm + pcm_off_i with
+// boxes of (4 channels x rows time steps).  One map per recording: time steps outside [0, T_i) are then outside the tensor
+// and come back as zeros -- the zero history and zero tail of the analysis bank -- instead of the neighbouring recording.
+typedef CUresult (*btk_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static btk_encode_tiled_fn tensor_map_encoder() {
+  static btk_encode_tiled_fn fn = [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      ptr = nullptr;
+    return (btk_encode_tiled_fn)ptr;
+  }();
+  return fn;
+}
+
+// Returns the device array of maps, or NULL when this batch goes through the register-load producer (channel count not a
+// multiple of 4, unaligned buffer, BTK_WS_TMA=0).
+static const void* chain_tensor_maps(btkb200_plan* p, const float* d_pcm, cudaStream_t st) {
+  static const int tma_env = getenv("BTK_WS_TMA") ? atoi(getenv("BTK_WS_TMA")) : 1;
+  if (!BTK_WS_RAW || !tma_env || !p->use_ws || p->C % 4 != 0 || (reinterpret_cast<uintptr_t>(d_pcm) & 15) != 0 || p->sig.empty()) return nullptr;
+  btk_encode_tiled_fn enc = tensor_map_encoder();
+  if (!enc) return nullptr;
+  const int n = (int)p->sig[0];
+  for (int i = 0; i < n; i++) if (p->sig[1 + 3 * i] % 4 != 0) return nullptr;
+  std::vector<long long> key(p->sig);
+  key.push_back((long long)reinterpret_cast<uintptr_t>(d_pcm));
+  if (key == p->tmap_sig && p->d_tmaps.p) return p->d_tmaps.p;
+  const int rows = p->geo.D < 256 ? p->geo.D : 256;
+  std::vector<CUtensorMap> maps(n > 0 ? n : 1);
+  memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
+  for (int i = 0; i < n; i++) {
+    const long long off = p->sig[1 + 3 * i], T = p->sig[2 + 3 * i];
+    if (T <= 0) continue;                                      // no work item refers to an empty recording
+    const cuuint64_t gdim[2] = {(cuuint64_t)p->C, (cuuint64_t)T};
+    const cuuint64_t gstr[1] = {(cuuint64_t)p->C * sizeof(float)};
+    const cuuint32_t box[2] = {4u, (cuuint32_t)rows};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = enc(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)(d_pcm + off), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return nullptr;
+  }
+  if (cudaStreamSynchronize(st) != cudaSuccess) return nullptr;              // earlier launches may still read the old maps
+  if (p->d_tmaps.reserve(maps.size() * sizeof(CUtensorMap)) != cudaSuccess) return nullptr;
+  if (cudaMemcpy(p->d_tmaps.p, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+  p->tmap_sig = key;
+  p->tma_rows = rows;
+  return p->d_tmaps.p;
+}
+
 // Launch the work items [w0, w1) of the prepared batch.
 static int chain_launch(btkb200_plan* p, const float* d_pcm, float* d_out, int w0, int w1, cudaStream_t st,
                         const cf* wts = nullptr, long long wts_stride = 0) {
@@ -780,6 +841,8 @@ static int chain_launch(btkb200_plan* p, const float* d_pcm, float* d_out, int w
   c.no_prefetch = p->no_prefetch;
   c.C = p->C; c.Cpad = p->Cpad; c.m = p->geo.m; c.pd_s = p->geo.pd_s; c.laN = p->geo.laN; c.gain = p->gain;
   c.cluster = p->use_ws ? p->cluster : 1;
+  c.tmaps = p->use_ws ? chain_tensor_maps(p, d_pcm, st) : nullptr;
+  c.tma_rows = p->tma_rows;
   if (p->use_ws) CK(p, launch_chain_ws(p->geo.M, p->geo.R, c, w1 - w0, st));
   else CK(p, launch_chain(p->geo.M, p->geo.R, c, w1 - w0, st));
   p->launched_chain = true;

@@ -29,6 +29,12 @@
 
 #include "fb_core.cuh"
 
+// Staged-window layout of the warp-specialised chain (chain_ws.cuh, WsCfg::RAW): 1 = the layout of the interleaved input,
+// which is what the tensor copy engine delivers; 0 = residue-major per channel (register transpose in the producer warps).
+#ifndef BTK_WS_RAW
+#define BTK_WS_RAW 1
+#endif
+
 namespace btk {
 
 struct RecDesc {
@@ -64,6 +70,10 @@ struct ChainParams {
   int gain;              // synthesis gainFactor
   int cluster;           // warp-specialised chain only (chain_ws.cuh): CTAs per work item, the channel groups are split
                          // across the CTAs of a thread-block cluster (0 / 1 = no cluster)
+  const void* tmaps;     // warp-specialised chain only: one 128-byte tensor map (CUtensorMap) per recording describing its
+                         // interleaved PCM as a [T][C] tensor with boxes of (4 channels x tma_rows time steps); NULL = the
+                         // producer warps load the window with 16-byte register loads
+  int tma_rows;          // time steps per box (min(D, 256))
 };
 
 template <int M_, int R_, int MT_ = 0, int PP_ = 1>
@@ -88,6 +98,7 @@ struct ChainCfg {
                                                      // span starts at block FW*warp: 16- or 8-byte aligned)
   static constexpr int W = FW * NW;            // analysis frames per iteration
   static constexpr int CG = 4;                 // channels staged per pass (one float4 per time step)
+  static constexpr bool RAW = false;           // staged window layout: residue-major per channel (see chain_ws.cuh for the raw one)
   static constexpr int NG = G::NG;             // lane groups per warp = channels processed concurrently
   static constexpr int XS = PP_;               // exchange buffers per lane group (one per frame pair)
   static constexpr int E = G::Ra / R_;         // registers between members of one residue class
@@ -226,9 +237,15 @@ BTK_HD void polyphase_pairs(cf* z, int gl, const float* xch, int warp, const flo
         constexpr int NX = mR + 1 + 2 * (PP - 1);          // samples needed; read as float2 (the row is padded to even)
         constexpr int NV = (NX + K::LV - 1) / K::LV;       // vector loads
         float xb[NV * K::LV], h[mR];
-        BTK_UNROLL
-        for (int i = 0; i < NV; i++)
-          load_floats<K::LV, K::LV>(xb + i * K::LV, xch + xs_off<K::LV>(res, (K::FW / K::LV) * warp + i, L.SB));
+        if (K::RAW) {
+          // raw window [time step][CG]: sample (block b, residue res) of this channel is one float, D * CG floats per block
+          BTK_UNROLL
+          for (int i = 0; i < NX; i++) xb[i] = xch[((K::FW * warp + i) * K::D + res) * K::CG];
+        } else {
+          BTK_UNROLL
+          for (int i = 0; i < NV; i++)
+            load_floats<K::LV, K::LV>(xb + i * K::LV, xch + xs_off<K::LV>(res, (K::FW / K::LV) * warp + i, L.SB));
+        }
         load_floats<mR, tap_vec(mR)>(h, hp);
         // (u_{i0}, u_{i1}) += h_t (s_{t+1}, s_t) = h_t (xb[2pp+mR-t-1], xb[2pp+mR-t]): where that is an aligned pair of the
         // float2 loads (mR-t-1 even) it is one packed FFMA2, otherwise two scalar ones
@@ -249,6 +266,7 @@ BTK_HD void polyphase_pairs(cf* z, int gl, const float* xch, int warp, const flo
         const int mR = m * R_;
         auto xs_at = [&](int b) {        // block b of this warp's span
           const int blk = K::FW * warp + b;
+          if (K::RAW) return xch[(blk * K::D + res) * K::CG];
           return xch[xs_off<K::LV>(res, blk / K::LV, L.SB) + blk % K::LV];
         };
         for (int k = 0; k < m; k++) {
@@ -509,7 +527,7 @@ BTK_HD void analysis_round(Ctx& ctx, const ChainSmem& L, const float* s_xs, cons
     ctx.par([&](int tid, TS& ts) {
       const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
       const int c_local = round * K::NG + grp;
-      polyphase_pairs<K>(ts.z, gl, s_xs + c_local * L.CS, warp, s_taps, L, m);
+      polyphase_pairs<K>(ts.z, gl, K::RAW ? s_xs + c_local : s_xs + c_local * L.CS, warp, s_taps, L, m);
       GroupFFT<M_, +1>::template step1_twiddle<K::PP>(ts.z, gl, s_twa);
       GroupFFT<M_, +1>::step1_scatter(ts.z, gl, slot(warp, grp));
     });
@@ -537,7 +555,7 @@ BTK_HD void analysis_round(Ctx& ctx, const ChainSmem& L, const float* s_xs, cons
   ctx.par([&](int tid, TS& ts) {
     const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
     const int c_local = round * K::NG + grp;
-    polyphase_pairs<K>(ts.z, gl, s_xs + c_local * L.CS, warp, s_taps, L, m);
+    polyphase_pairs<K>(ts.z, gl, K::RAW ? s_xs + c_local : s_xs + c_local * L.CS, warp, s_taps, L, m);
     GroupFFT<M_, +1>::template step1_multi<K::PP>(ts.z, gl, slot(warp, grp), s_twa);
   });
   ctx.syncwarp();

@@ -51,6 +51,10 @@ struct WsCfg {
   static constexpr int LV = (FW % 4 == 0) ? 4 : 2;
   static constexpr int W = FW * NW;
   static constexpr int CG = 4;
+  // RAW: the staged window keeps the layout of the interleaved input, [time step][CG] (16 bytes per time step) -- the
+  // producer's 16-byte load goes out as ONE 16-byte store, no register transpose; the polyphase reads single floats,
+  // D * CG floats apart, instead of vectors of consecutive blocks.  (This is also the layout a tensor bulk copy delivers.)
+  static constexpr bool RAW = BTK_WS_RAW != 0;
   static constexpr int NG = G::NG;
   // exchange buffers per lane group: the two frame pairs of M = 256 take turns on one (analysis_round), which is what
   // lets two 4-channel stages of the 32-frame window fit next to the buffers of eight warps
@@ -214,6 +218,17 @@ struct WsFill {
       const int task = task0 + k * K::NPT;
       if (task < ntask) {
         const int res = task % D, bg = task / D;
+        if (K::RAW) {
+          BTK_UNROLL
+          for (int i = 0; i < LV; i++) {
+            const int blk = bg * LV + i;
+            if (blk < NB) {
+              float4 v; v.x = x[k][i][0]; v.y = x[k][i][1]; v.z = x[k][i][2]; v.w = x[k][i][3];
+              *reinterpret_cast<float4*>(s_xs + (size_t)(blk * D + res) * K::CG) = v;
+            }
+          }
+          continue;
+        }
         float* dst = s_xs + xs_off<LV>(res, bg, SB);
         BTK_UNROLL
         for (int c = 0; c < K::CG; c++) {

@@ -73,6 +73,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
+// One box of the staged window by the tensor copy engine (SASS UTMALDG): 4 channels x `rows` time steps of the recording's
+// [T][C] tensor, starting at (channel c0, time step t0), land as [time step][4] at dst and complete their bytes on the
+// mbarrier.  Time steps before 0 or past T are outside the tensor: the engine fills zeros, which is exactly the bank's
+// zero history / zero tail (modulated.cc:461-516).
+__device__ __forceinline__ void tma_box_g2s(void* dst, const void* tmap, int c0, int t0, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   ws_smem_u32(dst)),
+               "l"(tmap), "r"(c0), "r"(t0), "r"(ws_smem_u32(bar))
+               : "memory");
+}
+
 template <int M, int PP, int NT> struct DevCtxWS {
   ChainThreadState<M, PP> ts;
   uint64_t* bars;
@@ -155,7 +166,7 @@ __global__ void __launch_bounds__(WsCfg<M, R, MT, PP>::NT + WsCfg<M, R, MT, PP>:
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < K::NS; s++) {
-      mbar_init(bars + WS_BAR_FULL + s, K::NPT);
+      mbar_init(bars + WS_BAR_FULL + s, p.tmaps ? 1 : K::NPT);
       mbar_init(bars + WS_BAR_EMPTY + s, K::NW);
     }
     mbar_init(bars + WS_BAR_TABLES, 1);
@@ -189,6 +200,32 @@ __global__ void __launch_bounds__(WsCfg<M, R, MT, PP>::NT + WsCfg<M, R, MT, PP>:
     const float* pcm = p.pcm + rec.pcm_off;
     const cf* wts = p.wts + (long long)wk.rec * p.wts_stride;
     const bool vec4 = (p.C % 4 == 0) && (rec.pcm_off % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.pcm) & 15) == 0);
+    if (p.tmaps) {
+      // ---- tensor-copy producer: ONE thread.  Per stage it waits for the stage, announces the bytes and issues the
+      // boxes of the window (NB D / rows of them) plus the weight rows; the copies run in the async proxy, no register
+      // and no load/store-unit slot of this SM is involved, and the transform warps see the window in the layout of the
+      // input ([time step][4 channels], WsCfg::RAW).
+      if (ptid == 0) {
+        const char* tmap = reinterpret_cast<const char*>(p.tmaps) + (size_t)wk.rec * 128;
+        asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap) : "memory");
+        const int rows = p.tma_rows, nbox = (L.NB * K::D) / rows;
+        const uint32_t stage_tx = (uint32_t)(L.NB * K::D * K::CG * 4 + K::CG * M * 8);
+        int g = 0;
+        for (int it = 0; it < walk.n_it; it++) {
+          const int t_lo = (int)ws_window_start<K>(walk, it, p.laN, N);
+          for (int cgi = 0; cgi < walk.ncg; cgi++, g++) {
+            const int st = g % K::NS;
+            unsigned char* stage = smem + S.stage0 + st * S.stage_bytes;
+            const int cg0 = (walk.cg_base + cgi) * K::CG;
+            mbar_wait_backoff(bars + WS_BAR_EMPTY + st, ((g / K::NS) & 1) ^ 1);
+            mbar_arrive_expect_tx(bars + WS_BAR_FULL + st, stage_tx);
+            bulk_g2s(stage + S.wts_off, wts + (long long)cg0 * M, K::CG * M * 8, bars + WS_BAR_FULL + st);
+            for (int b = 0; b < nbox; b++)
+              tma_box_g2s(stage + (size_t)b * rows * K::CG * 4, tmap, cg0, t_lo + b * rows, bars + WS_BAR_FULL + st);
+          }
+        }
+      }
+    } else {
     constexpr int TB = WsProd<M, K::NT, K::LV>::TB;
     int g = 0;
     for (int it = 0; it < walk.n_it; it++) {
@@ -243,6 +280,7 @@ __global__ void __launch_bounds__(WsCfg<M, R, MT, PP>::NT + WsCfg<M, R, MT, PP>:
 #endif
         mbar_arrive(bars + WS_BAR_FULL + st);
       }
+    }
     }
   } else {
     // ------------------------------------------------------------------ compute warps

@@ -21,7 +21,9 @@ def emu(tmp_path_factory):
     out = tmp_path_factory.mktemp("emu") / "libbtk_emu.so"
     src = os.path.join(ROOT, "tests", "emu", "emu_chain.cc")
     inc = os.path.join(ROOT, "distantspeechrecognition-mirror_b200", "csrc")
-    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", f"-I{inc}", "-x", "c++", src, "-o", str(out)],
+    # BTK_EMU_FLAGS: extra -D switches, to run the same tests on a tuning variant of the tile programs before GPU time is spent
+    extra = os.environ.get("BTK_EMU_FLAGS", "").split()
+    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", f"-I{inc}"] + extra + ["-x", "c++", src, "-o", str(out)],
                    check=True)
     return ctypes.CDLL(str(out))
 
