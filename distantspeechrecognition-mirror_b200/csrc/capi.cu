@@ -806,7 +806,13 @@ static const void* chain_tensor_maps(btkb200_plan* p, const float* d_pcm, cudaSt
   std::vector<long long> key(p->sig);
   key.push_back((long long)reinterpret_cast<uintptr_t>(d_pcm));
   if (key == p->tmap_sig && p->d_tmaps.p) return p->d_tmaps.p;
-  const int rows = p->geo.D < 256 ? p->geo.D : 256;
+  int rows = p->geo.D < 256 ? p->geo.D : 256;
+  // A/B knobs (read once): box height and L2 promotion of the maps
+  static const int rows_env = getenv("BTK_TMA_ROWS") ? atoi(getenv("BTK_TMA_ROWS")) : 0;
+  static const int promo_env = getenv("BTK_TMA_L2PROMO") ? atoi(getenv("BTK_TMA_L2PROMO")) : -1;
+  if (rows_env >= 8 && rows_env <= 256 && p->geo.D % rows_env == 0) rows = rows_env;
+  const CUtensorMapL2promotion promo = promo_env == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo_env == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                     : promo_env == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
   std::vector<CUtensorMap> maps(n > 0 ? n : 1);
   memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
   for (int i = 0; i < n; i++) {
@@ -817,8 +823,7 @@ static const void* chain_tensor_maps(btkb200_plan* p, const float* d_pcm, cudaSt
     const cuuint32_t box[2] = {4u, (cuuint32_t)rows};
     const cuuint32_t estr[2] = {1u, 1u};
     const CUresult r = enc(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)(d_pcm + off), gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return nullptr;
   }
   if (cudaStreamSynchronize(st) != cudaSuccess) return nullptr;              // earlier launches may still read the old maps
