@@ -468,7 +468,12 @@ def summarise(wl_cfg, mode, res, world, steps, peak, peak_src, traffic):
                           "peak_source": "148 SMs x 128 lanes x 2 flop x 1.965 GHz (SURVEY 8d)"},
         "e2e": {"value": world * units / res["e2e_s"], "unit": UNIT, "h2d_bytes_per_step": int(nb * res["n_in"] * 4),
                 "d2h_bytes_per_step": int(nb * res["n_out"] * 4), "ms_per_step": res["e2e_s"] * 1e3,
-                "per_gpu": units / res["e2e_s"], "matches_device_resident_output": res["same"]},
+                "per_gpu": units / res["e2e_s"], "matches_device_resident_output": res["same"],
+                # what bounds this leg: bytes over the host link per rank and second, and the fraction of the one-GPU
+                # end-to-end rate each rank keeps (one GPU moves 553 MB in 9.3 ms = 59 GB/s both ways; the host side of the
+                # box saturates at 110 / 212 / 184 GB/s of pinned uploads for 2 / 4 / 8 ranks, tools/pcie_probe_multi.py)
+                "host_link_gbs_per_gpu": (nb * res["n_in"] * 4 + nb * res["n_out"] * 4) / res["e2e_s"] / 1e9,
+                "efficiency_vs_one_gpu_824k": (units / res["e2e_s"]) / 824e3 if C == 8 and M == 256 else None},
         "gpu_launches": int(res["launches"]),
     }
     if res["e2e16_s"] > 0:
