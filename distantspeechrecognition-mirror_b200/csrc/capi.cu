@@ -75,6 +75,8 @@ struct btkb200_plan {
   PinBuf h_desc;
   std::vector<long long> sig;  // signature of the cached chain work list
   int cached_n_work = 0;
+  bool persist = false;        // warp-specialised chain: d_work holds the item prefix (WsSegs), the grid is one CTA per SM
+  int item_q = 0, n_sm = 148;
   int no_prefetch = 0;         // fused chain: no L2 prefetch of the next window (chain_prepare, same footprint estimate)
   int one_cta = 0;             // fused chain: keep one CTA per SM (chain_prepare decides from the L2 footprint)
   int use_ws = 0;              // fused chain: the warp-specialised producer / consumer kernel (chain_ws.cuh) runs this shape
@@ -734,11 +736,36 @@ static int chain_prepare(btkb200_plan* p, const long long* pcm_off, const long l
       if (p->tune_cluster > 0) S = p->tune_cluster;     // validated by btkb200_plan_tune
       p->cluster = S;
     }
+    p->persist = false;
     if (p->use_ws) {
+      // Persistent schedule (chain_ws.cuh::WsSegs): one CTA (cluster) per SM, each takes a contiguous share of the batch's
+      // iterations -- no wave quantisation (cfg3: 640 chunk CTAs were 4.32 waves), one table load and one cold stage per
+      // SM, one history warm-up per (CTA, recording) instead of one per chunk.  BTK_WS_PERSIST=0 keeps the chunk list.
+      static const int persist_env = getenv("BTK_WS_PERSIST") ? atoi(getenv("BTK_WS_PERSIST")) : 1;
+      p->one_cta = 1; p->no_prefetch = 1;
+      if (persist_env && !getenv("BTK_CHUNK_WAVES")) {
+        CK(p, cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, p->device));
+        std::vector<int> prefix(n + 1, 0);
+        for (int i = 0; i < n; i++) prefix[i + 1] = prefix[i] + (recs[i].nblk + Wws - 1) / Wws;
+        const size_t br = recs.size() * sizeof(RecDesc), bw = prefix.size() * sizeof(int);
+        CK(p, p->d_recs.reserve(br));
+        CK(p, p->d_work.reserve(bw));
+        CK(p, p->h_desc.reserve(br + bw));
+        memcpy(p->h_desc.p, recs.data(), br);
+        memcpy((char*)p->h_desc.p + br, prefix.data(), bw);
+        CK(p, cudaMemcpyAsync(p->d_recs.p, p->h_desc.p, br, cudaMemcpyHostToDevice, st));
+        CK(p, cudaMemcpyAsync(p->d_work.p, (char*)p->h_desc.p + br, bw, cudaMemcpyHostToDevice, st));
+        CK(p, cudaStreamSynchronize(st));
+        p->rec_work_begin = prefix;               // callers launch recording ranges [r0, r1) as item ranges
+        p->persist = true;
+        p->item_q = Wws;
+        p->sig = sig;
+        p->cached_n_work = prefix[n];
+        return BTKB200_OK;
+      }
       int slots = 148 / p->cluster;
       if (getenv("BTK_CHUNK_WAVES")) build_work(recs, choose_chunk(total, H, Wws), work);
       else build_work(recs, choose_chunk_model(recs, H, Wws, slots), work);
-      p->one_cta = 1; p->no_prefetch = 1;
     }
   }
   const int W = chain_frames_per_iter(p->geo.M, p->geo.R, p->geo.m);
@@ -848,7 +875,14 @@ static int chain_launch(btkb200_plan* p, const float* d_pcm, float* d_out, int w
   c.cluster = p->use_ws ? p->cluster : 1;
   c.tmaps = p->use_ws ? chain_tensor_maps(p, d_pcm, st) : nullptr;
   c.tma_rows = p->tma_rows;
-  if (p->use_ws) CK(p, launch_chain_ws(p->geo.M, p->geo.R, c, w1 - w0, st));
+  c.item_begin = nullptr; c.item_q = 0; c.item0 = 0; c.n_items = 0; c.n_rec = p->sig.empty() ? 0 : (int)p->sig[0];
+  int n_cta = w1 - w0;
+  if (p->use_ws && p->persist) {
+    c.work = nullptr;
+    c.item_begin = (const int*)p->d_work.p; c.item_q = p->item_q; c.item0 = w0; c.n_items = w1 - w0;
+    n_cta = c.n_items;           // the launcher clamps the grid to the CTAs (clusters) resident at once
+  }
+  if (p->use_ws) CK(p, launch_chain_ws(p->geo.M, p->geo.R, c, n_cta, st));
   else CK(p, launch_chain(p->geo.M, p->geo.R, c, w1 - w0, st));
   p->launched_chain = true;
   p->launches++;
@@ -1418,7 +1452,13 @@ int btkb200_mvdr_chain_batch(btkb200_plan* p, const float* const* pcm, const lon
       CK(p, launch_diag_load(dR, ng * B, C, (float)cfg->load_abs, cfg->load_rel, p->stream));
       p->launches++;
     }
-    CK(p, launch_mvdr_solve(dR, (const double2*)(base + o_d), dw, dfb + (size_t)r0 * B, B, C, cfg->dThreshold, p->stream, ng));
+    // x x^H covariances (+ loading) are Hermitian: the L D L^H kernel; the complex-symmetric x x^T flavour of
+    // SpectralMatrixArray::update (conjugate = 0) keeps the general pivoted elimination.  BTK_MVDR_CHOL=0: A/B runs.
+    static const int chol_env = getenv("BTK_MVDR_CHOL") ? atoi(getenv("BTK_MVDR_CHOL")) : 1;
+    if (cfg->conjugate && chol_env)
+      CK(p, launch_mvdr_chol(dR, (const double2*)(base + o_d), dw, dfb + (size_t)r0 * B, B, C, cfg->dThreshold, p->stream, ng));
+    else
+      CK(p, launch_mvdr_solve(dR, (const double2*)(base + o_d), dw, dfb + (size_t)r0 * B, B, C, cfg->dThreshold, p->stream, ng));
     CK(p, launch_weight_table(dw, (const int*)(base + o_map), dtab + (size_t)r0 * Cpad * M, M, C, Cpad, p->stream, ng));
     p->launches += 2;
     // the fused chain of this group, every recording with its own weight table, then its outputs go home

@@ -74,6 +74,13 @@ struct ChainParams {
                          // interleaved PCM as a [T][C] tensor with boxes of (4 channels x tma_rows time steps); NULL = the
                          // producer warps load the window with 16-byte register loads
   int tma_rows;          // time steps per box (min(D, 256))
+  // warp-specialised chain, persistent schedule (chain_ws.cuh::WsSegs): the launch covers items [item0, item0 + n_items),
+  // an item = W consecutive output frames of one recording; item_begin[r] = first item of recording r (prefix sums).
+  // Every CTA takes a contiguous share of the items.  NULL = one work item per CTA (p.work).
+  const int* item_begin;
+  int item_q;            // output frames per item (W)
+  int item0, n_items;
+  int n_rec;             // recordings of the batch (item_begin has n_rec + 1 entries)
 };
 
 template <int M_, int R_, int MT_ = 0, int PP_ = 1>

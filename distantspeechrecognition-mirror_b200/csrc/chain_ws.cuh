@@ -109,7 +109,8 @@ BTK_HD constexpr WsSmem ws_smem_layout(int m) {
   s.L.taps = off; off += K::D * s.L.TS * 4;             off = (off + 15) & ~15;
   s.L.twa = off;  off += FT::TWA_WORDS * 8;             off = (off + 15) & ~15;
   s.L.twb = off;  off += FT::TWB_WORDS * 8;             off = (off + 127) & ~127;
-  const int win = K::CG * cs * 4;
+  // the raw window is exactly NB D time steps of CG channels; the residue-major one pads its rows
+  const int win = K::RAW ? s.L.NB * K::D * K::CG * 4 : K::CG * cs * 4;
   s.wts_off = (win + 127) & ~127;
   s.stage_bytes = (s.wts_off + K::CG * M_ * 8 + 127) & ~127;
   s.stage0 = off; off += K::NS * s.stage_bytes;
@@ -131,6 +132,50 @@ BTK_HD constexpr bool ws_cluster_ok(int S) {
   return S >= 1 && (K::NW * K::PP) % S == 0 && K::D % S == 0 &&
          K::NW * K::PP * K::M * 8 <= K::NW * K::NG * K::XS * K::G::XBUF * 8 && K::NG <= 2;
 }
+
+// Persistent schedule.  The launch is a run of items (an item = W consecutive output frames of one recording, numbered
+// across the recordings of the batch by the prefix sums p.item_begin); CTA `cta` of `ncta` takes the contiguous share
+// [n cta / ncta, n (cta + 1) / ncta) and walks it as SEGMENTS: the items of one recording that follow each other are one
+// WorkItem, so the synthesis history is warmed up once per segment and not once per item, every CTA runs the same number
+// of iterations to within two, the tables are loaded once per SM and the producer runs ahead across segment boundaries.
+// With p.item_begin == NULL the CTA has exactly one segment, p.work[cta] (the chunk list of the first sessions).
+struct WsSegs {
+  const ChainParams& p;
+  int cta, i, i1, r;
+  bool one_shot;
+  BTK_HD WsSegs(const ChainParams& p_, int cta_, int ncta) : p(p_), cta(cta_), i(0), i1(0), r(0), one_shot(false) {
+    if (!p.item_begin) { one_shot = true; return; }
+    const long long n = p.n_items;
+    i = p.item0 + (int)(n * cta / ncta);
+    i1 = p.item0 + (int)(n * (cta + 1) / ncta);
+    if (i >= i1) return;
+    // last recording whose first item is <= i: item_begin is non-decreasing, item_begin[0] = 0
+    int lo = 0, hi = p.n_rec;                                    // item_begin[n_rec] (the total) > i
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) / 2;
+      if (p.item_begin[mid] <= i) lo = mid; else hi = mid;
+    }
+    r = lo;
+  }
+  BTK_HD bool next(WorkItem& wk) {
+    if (one_shot) {
+      if (i1) return false;
+      i1 = 1;
+      wk = p.work[cta];
+      return true;
+    }
+    if (i >= i1) return false;
+    while (p.item_begin[r + 1] <= i) r++;                        // recordings without frames have no items
+    const int b = p.item_begin[r], e = p.item_begin[r + 1] < i1 ? p.item_begin[r + 1] : i1;
+    const long long j1 = (long long)(e - b) * p.item_q;
+    const int nblk = p.recs[r].nblk;
+    wk.rec = r;
+    wk.j0 = (i - b) * p.item_q;
+    wk.nj = (int)(j1 < nblk ? j1 : nblk) - wk.j0;
+    i = e;
+    return true;
+  }
+};
 
 // The window one producer pass stages: iteration `it`, channel group `cgi` of this CTA.
 struct WsWalk {
@@ -257,6 +302,16 @@ BTK_HD void ws_fill_thread(int ptid, const ChainSmem& L, float* s_xs, const floa
   }
 }
 
+template <class K>
+BTK_HD WsWalk ws_walk(const ChainParams& p, const WorkItem& wk, int H, int csz, int rank) {
+  WsWalk w;
+  w.a_start = wk.j0 + p.pd_s - H;
+  w.n_it = (wk.nj + H + K::W - 1) / K::W;
+  w.ncg = (p.Cpad / K::CG) / csz;
+  w.cg_base = rank * w.ncg;
+  return w;
+}
+
 // oldest sample of the window of iteration `it`: frame i = tau_base + laN needs x[(i+1) D - N .. (i+1) D - 1]
 template <class K>
 BTK_HD long long ws_window_start(const WsWalk& w, int it, int laN, int N) {
@@ -278,7 +333,7 @@ BTK_HD long long ws_window_start(const WsWalk& w, int it, int laN, int N) {
 //     cl_wait(k)                      everything expected on receive barrier k has landed
 // ---------------------------------------------------------------------------------------------
 template <int M_, int R_, int MT_, int PP_, class Ctx>
-BTK_HD void chain_ws_compute(Ctx& ctx, const ChainParams& p, unsigned char* smem, const WorkItem wk, const RecDesc rec) {
+BTK_HD void chain_ws_compute(Ctx& ctx, const ChainParams& p, unsigned char* smem, const WorkItem wk, const RecDesc rec, int& g) {
   typedef WsCfg<M_, R_, MT_, PP_> K;
   typedef typename K::G G;
   typedef ChainThreadState<M_, PP_> TS;
@@ -298,11 +353,7 @@ BTK_HD void chain_ws_compute(Ctx& ctx, const ChainParams& p, unsigned char* smem
   const int C = p.C;
   const int csz = p.cluster > 1 ? p.cluster : 1;
   const int rank = csz > 1 ? ctx.cl_rank() : 0;
-  WsWalk walk;
-  walk.a_start = wk.j0 + p.pd_s - H;
-  walk.n_it = (wk.nj + H + K::W - 1) / K::W;
-  walk.ncg = (p.Cpad / K::CG) / csz;
-  walk.cg_base = rank * walk.ncg;
+  const WsWalk walk = ws_walk<K>(p, wk, H, csz, rank);
   const bool vec4 = (C % 4 == 0) && (rec.pcm_off % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.pcm) & 15) == 0);
   const cf* wts = p.wts + (long long)wk.rec * p.wts_stride;
 
@@ -312,7 +363,7 @@ BTK_HD void chain_ws_compute(Ctx& ctx, const ChainParams& p, unsigned char* smem
   ctx.wait_tables();
   ctx.sync();
 
-  int g = 0;                                                  // stages consumed so far
+  // g: stages consumed so far by this CTA (it runs on across the segments of a persistent CTA, like the producer's)
   for (int it = 0; it < walk.n_it; it++) {
     const int tau_base = walk.a_start + it * K::W;
     const long long t_lo = ws_window_start<K>(walk, it, p.laN, N);

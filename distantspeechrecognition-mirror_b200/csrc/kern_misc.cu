@@ -552,6 +552,203 @@ __global__ void __launch_bounds__(256) btk_mvdr_solve_kernel(const double2* __re
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// MVDR weights for HERMITIAN matrices (the adaptive batch: x x^H covariances + diagonal loading), one CTA of 128 threads per
+// (recording, bin), C <= 64.  Same result as btk_mvdr_solve_kernel (beamformer.cc:2392-2446:  t = (R^H)^-1 d, lam = t^H d,
+// w = t / (lam C), identity fallback when pseudoinverse() would drop a singular value, :275-283 / :2425-2427), different
+// route: the general kernel is a pivoted LU with three CTA barriers per column, four steps of inverse iteration in one warp
+// and a complex division inside every step of its triangular solves -- 1 us per bin at 64 channels, 263 ms for the 1 024
+// utterances of BASELINE configs[3], eight times their chain.  A Hermitian positive definite matrix needs none of that:
+//   * R = L D L^H without pivoting on the packed lower triangle (35 KB at 64 channels: five CTAs per SM), in PANELS of
+//     eight columns -- inside a panel every row is one thread, the trailing matrix then takes one rank-8 update (one
+//     read-modify-write of an entry per eight multiply-adds, multipliers conj(c_jp) / D_p broadcast from a small table);
+//   * the right-hand sides ride along as two extra ROWS of the matrix: row C = d^H gives the forward substitution for t,
+//     row C + 1 = x0^H the one for the singular-value probe, both finished when the factorisation is;
+//   * one back substitution in warp 0 for both, D real: reciprocals are taken once per column, no division in the chain;
+//   * sigma_min(R) <= |x| / |R^-1 x| for x = x0 and x = d (one step of inverse iteration each): below dThreshold the bin
+//     is rejected, as is a pivot that is not positive -- the semidefinite covariance of fewer frames than channels ends
+//     there, which is the bin the reference's SVD rejects too.
+// ---------------------------------------------------------------------------------------------
+#define BTK_CHOL_PANEL 8
+__device__ __forceinline__ int chol_row_off(int i, int C) { return i <= C ? (i * (i + 1)) / 2 : (C * (C + 1)) / 2 + (i - C) * C; }
+
+__global__ void __launch_bounds__(128) btk_mvdr_chol_kernel(const double2* __restrict__ Rn, const double2* __restrict__ dvec,
+                                                           double2* __restrict__ w, int* __restrict__ fallback, int C,
+                                                           double dThreshold, int B) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NP = BTK_CHOL_PANEL;
+  const int NR = C + 2;                                          // matrix rows + the two right-hand-side rows
+  double2* A = reinterpret_cast<double2*>(smem_raw);             // packed rows: (i, j), j <= min(i, C - 1)
+  double2* Wm = A + chol_row_off(NR, C);                         // [NR][NP] multipliers of the current panel
+  double* Dinv = reinterpret_cast<double*>(Wm + NR * NP);        // [C]
+  __shared__ int s_bad;
+  const int sb = blockIdx.x, s = sb % B, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const double2* d = dvec + (long long)s * C;
+  double2* ws = w + (long long)sb * C;
+  fallback += sb - s;
+  if (s == 0) {   // w[0] = (1, ..., 1), beamformer.cc:2410-2415
+    for (int c = tid; c < C; c += nt) ws[c] = make_double2(1.0, 0.0);
+    if (tid == 0) fallback[0] = 0;
+    return;
+  }
+  const double2* Rs = Rn + (long long)sb * C * C;
+  for (int i = warp; i < C; i += (nt >> 5)) {                    // lower triangle of R (= R^H for a Hermitian R), row by row
+    const int o = chol_row_off(i, C);
+    for (int j = lane; j <= i; j += 32) A[o + j] = Rs[(long long)i * C + j];
+  }
+  for (int j = tid; j < C; j += nt) {
+    A[chol_row_off(C, C) + j] = make_double2(d[j].x, -d[j].y);
+    A[chol_row_off(C + 1, C) + j] = make_double2((j & 1) ? -1.0 - (double)j / C : 1.0 + (double)j / C, 0.0);   // x0 is real
+  }
+  if (tid == 0) s_bad = 0;
+  __syncthreads();
+  bool bad = false;
+  for (int kp = 0; kp < C && !bad; kp += NP) {
+    const int pw = C - kp < NP ? C - kp : NP;
+    // ---- panel: columns kp .. kp+pw-1, one row per thread
+    for (int p = 0; p < pw; p++) {
+      const int k = kp + p;
+      const double Dk = A[chol_row_off(k, C) + k].x;
+      if (!(Dk > dThreshold) || !isfinite(Dk)) { bad = true; break; }          // uniform: every thread reads the same pivot
+      const double rD = 1.0 / Dk;
+      const int i = k + 1 + tid;
+      if (i < NR && p + 1 < pw) {
+        const int oi = chol_row_off(i, C);
+        const double2 ci = A[oi + k];
+        const double2 f = make_double2(ci.x * rD, ci.y * rD);
+        const int jhi = (i < C ? i : C - 1) < kp + pw - 1 ? (i < C ? i : C - 1) : kp + pw - 1;
+        for (int j = k + 1; j <= jhi; j++) {
+          const double2 cj = A[chol_row_off(j, C) + k];
+          double2 a = A[oi + j];
+          a.x -= f.x * cj.x + f.y * cj.y;                                      // f conj(c_j)
+          a.y -= f.y * cj.x - f.x * cj.y;
+          A[oi + j] = a;
+        }
+      }
+      __syncthreads();
+    }
+    if (bad) break;
+    // ---- multipliers W[j][p] = conj(c_jp) / D_p of the rows below the panel, reciprocal pivots
+    const int r0 = kp + pw;
+    for (int e = tid; e < (NR - r0) * pw; e += nt) {
+      const int j = r0 + e / pw, p = e % pw;
+      const double rD = 1.0 / A[chol_row_off(kp + p, C) + kp + p].x;
+      const double2 c = A[chol_row_off(j, C) + kp + p];
+      Wm[j * NP + p] = make_double2(c.x * rD, -c.y * rD);
+    }
+    if (tid < pw) Dinv[kp + tid] = 1.0 / A[chol_row_off(kp + tid, C) + kp + tid].x;
+    __syncthreads();
+    // ---- rank-pw update of the trailing rows r0 .. NR-1, columns r0 .. min(i, C-1): task = (row, block of four columns)
+    const int nrows = NR - r0, ncb = (C - r0 + 3) / 4;
+    for (int task = tid; task < nrows * ncb; task += nt) {
+      const int i = r0 + task % nrows, j0 = r0 + 4 * (task / nrows);
+      const int jmax = i < C ? i : C - 1;
+      if (j0 > jmax) continue;
+      const int oi = chol_row_off(i, C);
+      double2 c[NP];
+#pragma unroll
+      for (int p = 0; p < NP; p++) c[p] = p < pw ? A[oi + kp + p] : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int j = j0 + q;
+        if (j <= jmax) {
+          double2 a = A[oi + j];
+#pragma unroll
+          for (int p = 0; p < NP; p++) {
+            const double2 wv = p < pw ? Wm[j * NP + p] : make_double2(0.0, 0.0);
+            a.x -= c[p].x * wv.x - c[p].y * wv.y;
+            a.y -= c[p].x * wv.y + c[p].y * wv.x;
+          }
+          A[oi + j] = a;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (!bad && warp == 0) {
+    // ---- back substitution L^H t = D^-1 z for z = conj(row C) (from d) and conj(row C+1) (from x0); lane owns rows lane, lane+32
+    const int od = chol_row_off(C, C), ox = chol_row_off(C + 1, C);
+    double2 rt[2], ru[2];
+    double di[2];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const int i = lane + 32 * q;
+      di[q] = i < C ? Dinv[i] : 0.0;
+      const double2 zd = i < C ? A[od + i] : make_double2(0.0, 0.0), zx = i < C ? A[ox + i] : make_double2(0.0, 0.0);
+      rt[q] = make_double2(zd.x * di[q], -zd.y * di[q]);
+      ru[q] = make_double2(zx.x * di[q], -zx.y * di[q]);
+    }
+    for (int r = C - 1; r > 0; r--) {
+      const int q0 = r >> 5, src = r & 31;
+      double2 tr = q0 ? rt[1] : rt[0], ur = q0 ? ru[1] : ru[0];
+      tr.x = shfl_d(tr.x, src); tr.y = shfl_d(tr.y, src); ur.x = shfl_d(ur.x, src); ur.y = shfl_d(ur.y, src);
+      const int orow = chol_row_off(r, C);
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const int i = lane + 32 * q;
+        if (i < r) {
+          const double2 c = A[orow + i];                         // c_ri = L_ri D_i;  conj(L_ri) = conj(c_ri) / D_i
+          const double lx = c.x * di[q], ly = -c.y * di[q];
+          rt[q].x -= lx * tr.x - ly * tr.y; rt[q].y -= lx * tr.y + ly * tr.x;
+          ru[q].x -= lx * ur.x - ly * ur.y; ru[q].y -= lx * ur.y + ly * ur.x;
+        }
+      }
+    }
+    // lam = t^H d, |t|^2, |d|^2, |u|^2, |x0|^2
+    double2 lam = make_double2(0.0, 0.0);
+    double nt2 = 0.0, nd2 = 0.0, nu2 = 0.0, nx2 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const int c = lane + 32 * q;
+      if (c < C) {
+        const double2 dc = d[c];
+        lam.x += rt[q].x * dc.x + rt[q].y * dc.y; lam.y += rt[q].x * dc.y - rt[q].y * dc.x;
+        nt2 += rt[q].x * rt[q].x + rt[q].y * rt[q].y; nd2 += dc.x * dc.x + dc.y * dc.y;
+        nu2 += ru[q].x * ru[q].x + ru[q].y * ru[q].y;
+        const double x0 = (c & 1) ? -1.0 - (double)c / C : 1.0 + (double)c / C;
+        nx2 += x0 * x0;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lam.x += shfl_d(lam.x, lane ^ o); lam.y += shfl_d(lam.y, lane ^ o);
+      nt2 += shfl_d(nt2, lane ^ o); nd2 += shfl_d(nd2, lane ^ o); nu2 += shfl_d(nu2, lane ^ o); nx2 += shfl_d(nx2, lane ^ o);
+    }
+    // sigma_min <= |x| / |R^-1 x|: reject when either probe puts it below the threshold
+    const double thr2 = dThreshold * dThreshold;
+    const bool rej = dThreshold > 0.0 && (!(nx2 >= thr2 * nu2) || !(nd2 >= thr2 * nt2) || !isfinite(nu2) || !isfinite(nt2));
+    if (rej || !isfinite(lam.x) || !isfinite(lam.y) || (lam.x == 0.0 && lam.y == 0.0)) {
+      if (lane == 0) s_bad = 1;
+    } else {
+      const double2 nrm = make_double2(lam.x * C, lam.y * C);
+#pragma unroll
+      for (int q = 0; q < 2; q++) { const int c = lane + 32 * q; if (c < C) ws[c] = zdiv(rt[q], nrm); }
+      if (lane == 0) fallback[s] = 0;
+    }
+  }
+  __syncthreads();
+  if (bad || s_bad) {
+    // identity fallback (beamformer.cc:2425-2427): t = d
+    if (tid == 0) {
+      double lr = 0.0;
+      for (int c = 0; c < C; c++) lr += d[c].x * d[c].x + d[c].y * d[c].y;
+      for (int c = 0; c < C; c++) ws[c] = make_double2(d[c].x / (lr * C), d[c].y / (lr * C));
+      fallback[s] = 1;
+    }
+  }
+}
+
+cudaError_t launch_mvdr_chol(const double2* Rn, const double2* d, double2* w, int* fallback, int B, int C, double dThreshold,
+                             cudaStream_t st, int n) {
+  if (C > 64) return cudaErrorInvalidValue;
+  const int NR = C + 2;
+  const size_t smem = ((size_t)(C * (C + 1)) / 2 + 2 * C + (size_t)NR * BTK_CHOL_PANEL) * sizeof(double2) + (size_t)C * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(btk_mvdr_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  btk_mvdr_chol_kernel<<<B * n, 128, smem, st>>>(Rn, d, w, fallback, C, dThreshold, B);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_mvdr_solve(const double2* Rn, const double2* d, double2* w, int* fallback, int B, int C,
                               double dThreshold, cudaStream_t st, int n) {
   const size_t smem = (size_t)C * (C + 1) * sizeof(double2);

@@ -161,8 +161,7 @@ __global__ void __launch_bounds__(WsCfg<M, R, MT, PP>::NT + WsCfg<M, R, MT, PP>:
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S.bars);
   const int csz = p.cluster > 1 ? p.cluster : 1;
   const int crank = csz > 1 ? (int)cg::this_cluster().block_rank() : 0;
-  const WorkItem wk = p.work[blockIdx.x / csz];
-  const RecDesc rec = p.recs[wk.rec];
+  const int cta = (int)blockIdx.x / csz, ncta = (int)gridDim.x / csz;      // this CTA's (cluster's) share of the launch
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < K::NS; s++) {
@@ -192,25 +191,21 @@ __global__ void __launch_bounds__(WsCfg<M, R, MT, PP>::NT + WsCfg<M, R, MT, PP>:
       if (b_twb) bulk_g2s(smem + L.twb, p.twb, b_twb, bars + WS_BAR_TABLES);
     }
     const int N = M * m;
-    WsWalk walk;
-    walk.a_start = wk.j0 + p.pd_s - L.H;
-    walk.n_it = (wk.nj + L.H + K::W - 1) / K::W;
-    walk.ncg = (p.Cpad / K::CG) / csz;
-    walk.cg_base = crank * walk.ncg;
-    const float* pcm = p.pcm + rec.pcm_off;
-    const cf* wts = p.wts + (long long)wk.rec * p.wts_stride;
-    const bool vec4 = (p.C % 4 == 0) && (rec.pcm_off % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.pcm) & 15) == 0);
+    WsSegs segs(p, cta, ncta);
+    WorkItem wk;
+    int g = 0;                                   // stages filled so far by this CTA, across its segments
     if (p.tmaps) {
       // ---- tensor-copy producer: ONE thread.  Per stage it waits for the stage, announces the bytes and issues the
       // boxes of the window (NB D / rows of them) plus the weight rows; the copies run in the async proxy, no register
       // and no load/store-unit slot of this SM is involved, and the transform warps see the window in the layout of the
       // input ([time step][4 channels], WsCfg::RAW).
-      if (ptid == 0) {
+      if (ptid == 0) while (segs.next(wk)) {
+        const WsWalk walk = ws_walk<K>(p, wk, L.H, csz, crank);
+        const cf* wts = p.wts + (long long)wk.rec * p.wts_stride;
         const char* tmap = reinterpret_cast<const char*>(p.tmaps) + (size_t)wk.rec * 128;
         asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap) : "memory");
         const int rows = p.tma_rows, nbox = (L.NB * K::D) / rows;
         const uint32_t stage_tx = (uint32_t)(L.NB * K::D * K::CG * 4 + K::CG * M * 8);
-        int g = 0;
         for (int it = 0; it < walk.n_it; it++) {
           const int t_lo = (int)ws_window_start<K>(walk, it, p.laN, N);
           for (int cgi = 0; cgi < walk.ncg; cgi++, g++) {
@@ -225,9 +220,13 @@ __global__ void __launch_bounds__(WsCfg<M, R, MT, PP>::NT + WsCfg<M, R, MT, PP>:
           }
         }
       }
-    } else {
+    } else while (segs.next(wk)) {
     constexpr int TB = WsProd<M, K::NT, K::LV>::TB;
-    int g = 0;
+    const RecDesc rec = p.recs[wk.rec];
+    const WsWalk walk = ws_walk<K>(p, wk, L.H, csz, crank);
+    const float* pcm = p.pcm + rec.pcm_off;
+    const cf* wts = p.wts + (long long)wk.rec * p.wts_stride;
+    const bool vec4 = (p.C % 4 == 0) && (rec.pcm_off % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.pcm) & 15) == 0);
     for (int it = 0; it < walk.n_it; it++) {
       const long long t_lo = ws_window_start<K>(walk, it, p.laN, N);
 #ifdef BTK_WS_L2PF          // A/B, OFF by default: measured neutral (cfg2 0.3465 -> 0.3468 ms, cfg3 0.8292 -> 0.8308 ms)
@@ -287,7 +286,10 @@ __global__ void __launch_bounds__(WsCfg<M, R, MT, PP>::NT + WsCfg<M, R, MT, PP>:
     if (RG::split) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(RG::RC));
     DevCtxWS<M, PP, K::NT> ctx;
     ctx.bars = bars; ctx.csz = csz; ctx.crank = crank; ctx.cl_phase = 0;
-    chain_ws_compute<M, R, MT, PP>(ctx, p, smem, wk, rec);
+    WsSegs segs(p, cta, ncta);
+    WorkItem wk;
+    int g = 0;                                   // stages consumed so far by this CTA, across its segments
+    while (segs.next(wk)) chain_ws_compute<M, R, MT, PP>(ctx, p, smem, wk, p.recs[wk.rec], g);
   }
   // no CTA of a cluster leaves while a peer may still write into its shared memory
   if (csz > 1) cg::this_cluster().sync();
@@ -319,6 +321,20 @@ static cudaError_t launch_ws_one(const ChainParams& p, int n_work, cudaStream_t 
   attr[0].val.clusterDim.x = (unsigned)csz; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (p.item_begin) {
+    // persistent schedule: as many CTAs (clusters) as are resident at once -- one per SM; with a cluster size the GPC
+    // shapes decide (not every SM pairs up), so ask the occupancy calculator rather than dividing the SM count
+    static int slots[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (csz > 8) return cudaErrorInvalidValue;
+    if (!slots[csz]) {
+      int nc = 0;
+      e = cudaOccupancyMaxActiveClusters(&nc, kern, &cfg);
+      if (e != cudaSuccess) return e;
+      slots[csz] = nc > 0 ? nc : 1;
+    }
+    const int n_cta = n_work < slots[csz] ? n_work : slots[csz];
+    cfg.gridDim = dim3((unsigned)(n_cta * csz), 1, 1);
+  }
   return cudaLaunchKernelEx(&cfg, kern, p);
 }
 

@@ -40,6 +40,9 @@ cudaError_t launch_covariance_tc_batch(const cf* snap, const double* wt, double2
 // fallback[n][B] flags.  One CTA per (recording, bin): n = 1 is the single-recording call.
 cudaError_t launch_mvdr_solve(const double2* Rn, const double2* d, double2* w, int* fallback, int B, int C,
                               double dThreshold, cudaStream_t st, int n = 1);
+// Hermitian positive (semi)definite matrices only (the adaptive batch): L D L^H on the packed lower triangle, see kern_misc.cu
+cudaError_t launch_mvdr_chol(const double2* Rn, const double2* d, double2* w, int* fallback, int B, int C, double dThreshold,
+                             cudaStream_t st, int n);
 
 // Beamformer output + Zelinski post-filter on stored snapshots (postfilter/postfilter.cc:30-222, 428-500): Y [F][B]
 // post-filtered in place semantics (Y is written, then scaled), Wout [F][B] or NULL; stat = scratch of

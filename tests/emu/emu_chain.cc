@@ -207,6 +207,7 @@ static int run_chain_ws(int m, int dct, int C, int n_rec, const long long* Ts, c
   p.pcm = pcm; p.out = out; p.recs = recs.data(); p.work = work.data();
   p.taps_h = hf.data(); p.taps_g = gp.data(); p.wts = gam.data(); p.wts_stride = 0; p.one_cta = 0; p.no_prefetch = 0; p.twa = twa.data(); p.twb = twb.data();
   p.C = C; p.Cpad = Cpad; p.m = m; p.pd_s = geo.pd_s; p.laN = geo.laN; p.gain = gain; p.cluster = 1;
+  p.tmaps = nullptr; p.tma_rows = 0; p.item_begin = nullptr; p.item_q = 0; p.item0 = 0; p.n_items = 0; p.n_rec = n_rec;
   const WsSmem S = ws_smem_layout<M, R, PP>(m);
   if (S.total > 227 * 1024) return -2;
   std::vector<unsigned char> smem(S.total + 64, 0xA5);
@@ -217,7 +218,8 @@ static int run_chain_ws(int m, int dct, int C, int n_rec, const long long* Ts, c
     memcpy(smem.data() + S.L.taps, hf.data(), (size_t)K::D * S.L.TS * 4);
     memcpy(smem.data() + S.L.twa, twa.data(), (size_t)FT::TWA_WORDS * 8);
     if (FT::TWB_WORDS) memcpy(smem.data() + S.L.twb, twb.data(), (size_t)FT::TWB_WORDS * 8);
-    chain_ws_compute<M, R, MT, PP>(ctx, p, smem.data(), work[wi], recs[work[wi].rec]);
+    int g = 0;
+    chain_ws_compute<M, R, MT, PP>(ctx, p, smem.data(), work[wi], recs[work[wi].rec], g);
   }
   return (int)work.size();
 }
@@ -242,4 +244,27 @@ extern "C" int emu_chain_ws(int M, int m, int r, int dct, int C, int n_rec, cons
 #undef CASE
 #undef ARGS
   return -1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent schedule of the warp-specialised chain (chain_ws.cuh::WsSegs): the segments CTA `cta` of `ncta` walks for a
+// launch of the recordings [r0, r1) of a batch with nblk[i] output frames each.  Writes (rec, j0, nj) triples.
+extern "C" int emu_ws_segments(int n_rec, const int* nblk, int W, int r0, int r1, int cta, int ncta, int* out, int cap) {
+  std::vector<RecDesc> recs(n_rec);
+  std::vector<int> prefix(n_rec + 1, 0);
+  for (int i = 0; i < n_rec; i++) {
+    recs[i].pcm_off = 0; recs[i].out_off = 0; recs[i].T = 0; recs[i].nblk = nblk[i];
+    prefix[i + 1] = prefix[i] + (nblk[i] + W - 1) / W;
+  }
+  ChainParams p = ChainParams();
+  p.recs = recs.data(); p.item_begin = prefix.data(); p.item_q = W; p.item0 = prefix[r0]; p.n_items = prefix[r1] - prefix[r0];
+  p.n_rec = n_rec;
+  WsSegs segs(p, cta, ncta);
+  WorkItem wk;
+  int n = 0;
+  while (segs.next(wk)) {
+    if (n < cap) { out[3 * n] = wk.rec; out[3 * n + 1] = wk.j0; out[3 * n + 2] = wk.nj; }
+    n++;
+  }
+  return n;
 }

@@ -103,3 +103,33 @@ def test_emulated_staged_tiles_match_oracle(case, fast, emu, prototypes):
     out = np.zeros(geo.synthesis_frames(F) * geo.D, np.float32)
     emu.emu_synthesis(M, m, r, dct, F, vp(Yh), vp(out), vp(g), 1, chunk, fast)
     assert bo.snr_db(out, ref) > 100.0
+
+
+@pytest.mark.parametrize("ncta", [1, 7, 148])
+def test_persistent_schedule_covers_every_frame_once(emu, ncta):
+    """chain_ws.cuh::WsSegs: the contiguous item shares of the CTAs of a launch, walked as per-recording segments, cover the
+    output frames of the launched recordings exactly once, in order, and no CTA has more than one item above its share."""
+    rng = np.random.default_rng(3)
+    W = 32
+    nblk = np.array([0, 1, 31, 32, 33, 7500, 0, 1250, 64, 5, 0], np.int32)
+    nblk = np.concatenate([nblk, rng.integers(0, 400, 40).astype(np.int32)])
+    n = len(nblk)
+    for r0, r1 in [(0, n), (3, 9), (5, 6), (6, 7), (10, n)]:
+        cover = [np.zeros(int(b), np.int32) for b in nblk]
+        out = np.zeros(3 * 64, np.int32)
+        items = []
+        for cta in range(ncta):
+            k = emu.emu_ws_segments(n, vp(nblk), W, r0, r1, cta, ncta, vp(out), 64)
+            assert 0 <= k <= 64
+            its = 0
+            last = (-1, -1)
+            for rec, j0, nj in out[:3 * k].reshape(-1, 3):
+                assert r0 <= rec < r1 and nj > 0 and j0 % W == 0
+                assert (rec, j0) > last          # ascending, one segment per recording
+                last = (rec, j0)
+                cover[rec][j0:j0 + nj] += 1
+                its += -(-nj // W)
+            items.append(its)
+        for r in range(n):
+            assert np.all(cover[r] == (1 if r0 <= r < r1 else 0))
+        assert max(items) - min(items) <= 1
