@@ -560,8 +560,9 @@ __global__ void __launch_bounds__(256) btk_mvdr_solve_kernel(const double2* __re
 // and a complex division inside every step of its triangular solves -- 1 us per bin at 64 channels, 263 ms for the 1 024
 // utterances of BASELINE configs[3], eight times their chain.  A Hermitian positive definite matrix needs none of that:
 //   * R = L D L^H without pivoting on the packed lower triangle (35 KB at 64 channels: five CTAs per SM), in PANELS of
-//     eight columns -- inside a panel every row is one thread, the trailing matrix then takes one rank-8 update (one
-//     read-modify-write of an entry per eight multiply-adds, multipliers conj(c_jp) / D_p broadcast from a small table);
+//     eight columns: the 8 x 8 diagonal block inside one warp, the rows below it one thread each with their panel entries
+//     in registers, then ONE rank-8 update of the trailing matrix (one read-modify-write of an entry per eight
+//     multiply-adds, the multipliers conj(c_jp) / D_p broadcast from a small table) -- three CTA barriers per panel;
 //   * the right-hand sides ride along as two extra ROWS of the matrix: row C = d^H gives the forward substitution for t,
 //     row C + 1 = x0^H the one for the singular-value probe, both finished when the factorisation is;
 //   * one back substitution in warp 0 for both, D real: reciprocals are taken once per column, no division in the chain;
@@ -579,8 +580,9 @@ __global__ void __launch_bounds__(128) btk_mvdr_chol_kernel(const double2* __res
   constexpr int NP = BTK_CHOL_PANEL;
   const int NR = C + 2;                                          // matrix rows + the two right-hand-side rows
   double2* A = reinterpret_cast<double2*>(smem_raw);             // packed rows: (i, j), j <= min(i, C - 1)
-  double2* Wm = A + chol_row_off(NR, C);                         // [NR][NP] multipliers of the current panel
-  double* Dinv = reinterpret_cast<double*>(Wm + NR * NP);        // [C]
+  double2* Wm = A + chol_row_off(NR, C);                         // [NR][NP] multipliers conj(c_jp) / D_p of the current panel
+  double2* Bm = Wm + NR * NP;                                    // [NP][NP] conj(L_pq) of the panel's diagonal block
+  double* Dinv = reinterpret_cast<double*>(Bm + NP * NP);        // [C]
   __shared__ int s_bad;
   const int sb = blockIdx.x, s = sb % B, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const double2* d = dvec + (long long)s * C;
@@ -592,9 +594,16 @@ __global__ void __launch_bounds__(128) btk_mvdr_chol_kernel(const double2* __res
     return;
   }
   const double2* Rs = Rn + (long long)sb * C * C;
-  for (int i = warp; i < C; i += (nt >> 5)) {                    // lower triangle of R (= R^H for a Hermitian R), row by row
-    const int o = chol_row_off(i, C);
-    for (int j = lane; j <= i; j += 32) A[o + j] = Rs[(long long)i * C + j];
+  // lower triangle of R (= R^H for a Hermitian R): coalesced walk over the full rows, eight loads in flight per thread
+  for (int e0 = 0; e0 < C * C; e0 += 8 * nt) {
+    double2 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) { const int e = e0 + u * nt + tid; v[u] = e < C * C ? Rs[e] : make_double2(0.0, 0.0); }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int e = e0 + u * nt + tid, i = e / C, j = e - i * C;
+      if (e < C * C && j <= i) A[chol_row_off(i, C) + j] = v[u];
+    }
   }
   for (int j = tid; j < C; j += nt) {
     A[chol_row_off(C, C) + j] = make_double2(d[j].x, -d[j].y);
@@ -602,69 +611,116 @@ __global__ void __launch_bounds__(128) btk_mvdr_chol_kernel(const double2* __res
   }
   if (tid == 0) s_bad = 0;
   __syncthreads();
-  bool bad = false;
-  for (int kp = 0; kp < C && !bad; kp += NP) {
-    const int pw = C - kp < NP ? C - kp : NP;
-    // ---- panel: columns kp .. kp+pw-1, one row per thread
-    for (int p = 0; p < pw; p++) {
-      const int k = kp + p;
-      const double Dk = A[chol_row_off(k, C) + k].x;
-      if (!(Dk > dThreshold) || !isfinite(Dk)) { bad = true; break; }          // uniform: every thread reads the same pivot
-      const double rD = 1.0 / Dk;
-      const int i = k + 1 + tid;
-      if (i < NR && p + 1 < pw) {
-        const int oi = chol_row_off(i, C);
-        const double2 ci = A[oi + k];
-        const double2 f = make_double2(ci.x * rD, ci.y * rD);
-        const int jhi = (i < C ? i : C - 1) < kp + pw - 1 ? (i < C ? i : C - 1) : kp + pw - 1;
-        for (int j = k + 1; j <= jhi; j++) {
-          const double2 cj = A[chol_row_off(j, C) + k];
-          double2 a = A[oi + j];
-          a.x -= f.x * cj.x + f.y * cj.y;                                      // f conj(c_j)
+  for (int kp = 0; kp < C; kp += NP) {
+    const int pw = C - kp < NP ? C - kp : NP, r0 = kp + pw;
+    // ---- (1) the panel's diagonal block, rows kp .. kp+pw-1, inside warp 0 (lane p = row kp + p)
+    if (warp == 0) {
+      // lane < 28 owns one entry (bi, bj), 1 <= bj <= bi <= 7, of the block's lower triangle (column 0 is never updated):
+      // a step is ONE multiply-add per lane, not a loop per row
+      int bi = 0, bj = 0;                                        // bj = 0: no entry (lanes 28 .. 31)
+      {
+        int l = lane, b = 1;
+        while (b < NP && l >= NP - b) { l -= NP - b; b++; }
+        if (b < NP) { bj = b; bi = b + l; }
+      }
+      const int oi = chol_row_off(kp + bi < C ? kp + bi : 0, C), oj = chol_row_off(kp + bj < C ? kp + bj : 0, C);
+      bool bad = false;
+      for (int p = 0; p < pw; p++) {
+        const int k = kp + p;
+        const double Dk = A[chol_row_off(k, C) + k].x;
+        if (!(Dk > dThreshold) || !isfinite(Dk)) { bad = true; break; }          // same value in every lane
+        if (bj > p && bi < pw) {
+          const double rD = 1.0 / Dk;
+          const double2 ci = A[oi + k], cj = A[oj + k];
+          const double2 f = make_double2(ci.x * rD, ci.y * rD);
+          double2 a = A[oi + kp + bj];
+          a.x -= f.x * cj.x + f.y * cj.y;                                        // f conj(c_jk)
           a.y -= f.y * cj.x - f.x * cj.y;
-          A[oi + j] = a;
+          A[oi + kp + bj] = a;
+        }
+        __syncwarp();
+      }
+      if (bad) {
+        if (lane == 0) s_bad = 1;
+      } else {
+        if (lane < pw) Dinv[kp + lane] = 1.0 / A[chol_row_off(kp + lane, C) + kp + lane].x;
+        __syncwarp();
+        // conj(L_pq) = conj(c_pq) / D_q for q < p, zero elsewhere (the rows below read the whole table)
+        for (int e = lane; e < NP * NP; e += 32) {
+          const int pp = e / NP, q = e % NP;
+          double2 v = make_double2(0.0, 0.0);
+          if (q < pp && pp < pw) { const double2 c = A[chol_row_off(kp + pp, C) + kp + q]; const double r = Dinv[kp + q]; v = make_double2(c.x * r, -c.y * r); }
+          Bm[e] = v;
         }
       }
-      __syncthreads();
     }
-    if (bad) break;
-    // ---- multipliers W[j][p] = conj(c_jp) / D_p of the rows below the panel, reciprocal pivots
-    const int r0 = kp + pw;
-    for (int e = tid; e < (NR - r0) * pw; e += nt) {
-      const int j = r0 + e / pw, p = e % pw;
-      const double rD = 1.0 / A[chol_row_off(kp + p, C) + kp + p].x;
-      const double2 c = A[chol_row_off(j, C) + kp + p];
-      Wm[j * NP + p] = make_double2(c.x * rD, -c.y * rD);
-    }
-    if (tid < pw) Dinv[kp + tid] = 1.0 / A[chol_row_off(kp + tid, C) + kp + tid].x;
     __syncthreads();
-    // ---- rank-pw update of the trailing rows r0 .. NR-1, columns r0 .. min(i, C-1): task = (row, block of four columns)
-    const int nrows = NR - r0, ncb = (C - r0 + 3) / 4;
-    for (int task = tid; task < nrows * ncb; task += nt) {
-      const int i = r0 + task % nrows, j0 = r0 + 4 * (task / nrows);
-      const int jmax = i < C ? i : C - 1;
-      if (j0 > jmax) continue;
+    if (s_bad) break;
+    // ---- (2) rows below the block, one thread per row: c_ip -= sum_{q<p} c_iq conj(L_pq); multipliers W_ip = conj(c_ip) / D_p
+    {
+      const int i = r0 + tid;
+      if (i < NR) {
+        const int oi = chol_row_off(i, C);
+        double2 c[NP];
+#pragma unroll
+        for (int p = 0; p < NP; p++) c[p] = p < pw ? A[oi + kp + p] : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int p = 1; p < NP; p++) {
+#pragma unroll
+          for (int q = 0; q < p; q++) {
+            const double2 l = Bm[p * NP + q];
+            c[p].x -= c[q].x * l.x - c[q].y * l.y;
+            c[p].y -= c[q].x * l.y + c[q].y * l.x;
+          }
+        }
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+          if (p < pw) {
+            A[oi + kp + p] = c[p];
+            const double r = Dinv[kp + p];
+            Wm[i * NP + p] = make_double2(c[p].x * r, -c[p].y * r);
+          } else {
+            Wm[i * NP + p] = make_double2(0.0, 0.0);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- (3) rank-pw update of the trailing rows r0 .. NR-1, columns r0 .. min(i, C-1): lanes across the rows, warps across
+    // blocks of four columns (the multipliers of a column are a broadcast load, a row's panel entries stay in registers)
+    for (int ib = r0 + lane; ib < NR; ib += 32) {
+      const int i = ib, jmax = i < C ? i : C - 1;
       const int oi = chol_row_off(i, C);
       double2 c[NP];
 #pragma unroll
       for (int p = 0; p < NP; p++) c[p] = p < pw ? A[oi + kp + p] : make_double2(0.0, 0.0);
+      for (int j0 = r0 + 4 * warp; j0 <= jmax; j0 += 4 * (nt >> 5)) {
+        // four columns at a time: eight independent accumulation chains per lane (columns past the row's diagonal run on
+        // column jmax's multipliers and are not stored)
+        double2 a[4];
+        const double2* wj[4];
 #pragma unroll
-      for (int q = 0; q < 4; q++) {
-        const int j = j0 + q;
-        if (j <= jmax) {
-          double2 a = A[oi + j];
-#pragma unroll
-          for (int p = 0; p < NP; p++) {
-            const double2 wv = p < pw ? Wm[j * NP + p] : make_double2(0.0, 0.0);
-            a.x -= c[p].x * wv.x - c[p].y * wv.y;
-            a.y -= c[p].x * wv.y + c[p].y * wv.x;
-          }
-          A[oi + j] = a;
+        for (int q = 0; q < 4; q++) {
+          const int j = j0 + q <= jmax ? j0 + q : jmax;
+          a[q] = A[oi + j];
+          wj[q] = Wm + j * NP;
         }
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const double2 wv = wj[q][p];
+            a[q].x -= c[p].x * wv.x - c[p].y * wv.y;
+            a[q].y -= c[p].x * wv.y + c[p].y * wv.x;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) if (j0 + q <= jmax) A[oi + j0 + q] = a[q];
       }
     }
     __syncthreads();
   }
+  const bool bad = s_bad != 0;
   if (!bad && warp == 0) {
     // ---- back substitution L^H t = D^-1 z for z = conj(row C) (from d) and conj(row C+1) (from x0); lane owns rows lane, lane+32
     const int od = chol_row_off(C, C), ox = chol_row_off(C + 1, C);
@@ -679,8 +735,8 @@ __global__ void __launch_bounds__(128) btk_mvdr_chol_kernel(const double2* __res
       ru[q] = make_double2(zx.x * di[q], -zx.y * di[q]);
     }
     for (int r = C - 1; r > 0; r--) {
-      const int q0 = r >> 5, src = r & 31;
-      double2 tr = q0 ? rt[1] : rt[0], ur = q0 ? ru[1] : ru[0];
+      const int src = r & 31;
+      double2 tr = r >= 32 ? rt[1] : rt[0], ur = r >= 32 ? ru[1] : ru[0];
       tr.x = shfl_d(tr.x, src); tr.y = shfl_d(tr.y, src); ur.x = shfl_d(ur.x, src); ur.y = shfl_d(ur.y, src);
       const int orow = chol_row_off(r, C);
 #pragma unroll
@@ -727,7 +783,7 @@ __global__ void __launch_bounds__(128) btk_mvdr_chol_kernel(const double2* __res
     }
   }
   __syncthreads();
-  if (bad || s_bad) {
+  if (s_bad) {
     // identity fallback (beamformer.cc:2425-2427): t = d
     if (tid == 0) {
       double lr = 0.0;
@@ -742,7 +798,8 @@ cudaError_t launch_mvdr_chol(const double2* Rn, const double2* d, double2* w, in
                              cudaStream_t st, int n) {
   if (C > 64) return cudaErrorInvalidValue;
   const int NR = C + 2;
-  const size_t smem = ((size_t)(C * (C + 1)) / 2 + 2 * C + (size_t)NR * BTK_CHOL_PANEL) * sizeof(double2) + (size_t)C * sizeof(double);
+  const size_t smem = ((size_t)(C * (C + 1)) / 2 + 2 * C + (size_t)NR * BTK_CHOL_PANEL + BTK_CHOL_PANEL * BTK_CHOL_PANEL) * sizeof(double2) +
+                      (size_t)C * sizeof(double);
   cudaError_t e = cudaFuncSetAttribute(btk_mvdr_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   btk_mvdr_chol_kernel<<<B * n, 128, smem, st>>>(Rn, d, w, fallback, C, dThreshold, B);
