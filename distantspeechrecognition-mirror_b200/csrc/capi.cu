@@ -876,6 +876,8 @@ static int chain_launch(btkb200_plan* p, const float* d_pcm, float* d_out, int w
   c.tmaps = p->use_ws ? chain_tensor_maps(p, d_pcm, st) : nullptr;
   c.tma_rows = p->tma_rows;
   c.item_begin = nullptr; c.item_q = 0; c.item0 = 0; c.n_items = 0; c.n_rec = p->sig.empty() ? 0 : (int)p->sig[0];
+  static const int syn_env = getenv("BTK_WS_SYN") ? atoi(getenv("BTK_WS_SYN")) : 1;   // A/B runs
+  c.no_syn = syn_env ? 0 : 1;
   int n_cta = w1 - w0;
   if (p->use_ws && p->persist) {
     c.work = nullptr;

@@ -81,6 +81,7 @@ struct ChainParams {
   int item_q;            // output frames per item (W)
   int item0, n_items;
   int n_rec;             // recordings of the batch (item_begin has n_rec + 1 entries)
+  int no_syn;            // warp-specialised chain, A/B knob (BTK_WS_SYN=0): the transform warps keep the synthesis side
 };
 
 template <int M_, int R_, int MT_ = 0, int PP_ = 1>
@@ -357,12 +358,18 @@ BTK_HD void synth_transform_store(Ctx& ctx, cf* s_xbuf, const cf* s_twa, const c
         const int tau0 = tau_base + f;
         // v of frames before the stream start is zero (the synthesis buffer starts zeroed, modulated.cc:666-674)
         const float k0 = tau0 >= 0 ? 1.f : 0.f, k1 = tau0 + 1 >= 0 ? 1.f : 0.f;
-        float* v0 = s_vcur + f * M_;
-        BTK_UNROLL
-        for (int r = 0; r < G::V; r++) {
-          const int q = G::index_of(gl, r);
-          v0[q] = ts.g[pp * G::V + r].x * k0;
-          v0[M_ + q] = ts.g[pp * G::V + r].y * k1;
+        if (s_vcur) {
+          float* v0 = s_vcur + f * M_;
+          BTK_UNROLL
+          for (int r = 0; r < G::V; r++) {
+            const int q = G::index_of(gl, r);
+            v0[q] = ts.g[pp * G::V + r].x * k0;
+            v0[M_ + q] = ts.g[pp * G::V + r].y * k1;
+          }
+        } else {
+          // the caller parks the frames itself (chain_ws.cuh: tensor memory): leave them scaled in the registers
+          BTK_UNROLL
+          for (int r = 0; r < G::V; r++) ts.g[pp * G::V + r] = mk(ts.g[pp * G::V + r].x * k0, ts.g[pp * G::V + r].y * k1);
         }
       }
     }

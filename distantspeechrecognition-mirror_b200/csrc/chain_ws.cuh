@@ -63,9 +63,27 @@ struct WsCfg {
   static constexpr int FPT_RAW = (W * D) / NT;
   static constexpr int FPT = FPT_RAW >= 8 ? 8 : (FPT_RAW >= 4 ? 4 : (FPT_RAW >= 2 ? 2 : 1));
   static constexpr int NS = 2;                 // stages
+  // Overlap-add warps (tensor-copy mode): one warpgroup next to the producer's takes the synthesis side's polyphase with
+  // g, the overlap-add and the output stores off the transform warps.  The v frames of an iteration travel through TENSOR
+  // MEMORY: a transform warp parks the 2 V values per lane its forward transform leaves in registers (tcgen05.st, its own
+  // 32 lanes of the 128, NVAL columns), the overlap-add warp of the same lane quarter (warp index mod 4) takes them out
+  // chunk by chunk (tcgen05.ld) into a small ring of frames in shared memory.  256 KB of tensor memory sit idle in
+  // this kernel otherwise; shared memory has no 32 KB left for a second set of v frames.
+  static constexpr int NSY = 4;
+  static constexpr int NST = NSY * 32;
+  static constexpr int NVAL = 2 * G::V;                                  // floats a lane parks per iteration
+  static constexpr int CHF = 4;                                          // frames per chunk of the overlap-add warps
+  static constexpr int TM_COLS = 4 * NVAL < 32 ? 32 : 4 * NVAL;          // 2 slots x 2 warps per lane quarter x NVAL
   static_assert(G::Ra % R_ == 0, "decimation factor must divide the first radix");
   static_assert(CG % NG == 0, "channel group must be a multiple of the lane groups per warp");
   static_assert(W % FPT == 0, "frames per thread must divide the iteration");
+};
+
+// what the overlap-add warps see of the configuration: their own thread count
+template <int M_, int R_, int MT_ = 0, int PP_ = 1>
+struct WsSynCfg : WsCfg<M_, R_, MT_, PP_> {
+  typedef WsCfg<M_, R_, MT_, PP_> B;
+  static constexpr int NT = B::NST;
 };
 
 struct WsSmem {
@@ -77,10 +95,13 @@ struct WsSmem {
   int xbuf, vhist, vcur;
   int rbuf;             // cluster receive buffer (aliases the exchange buffers: they are idle during the reduction)
   int valias;           // current-v frames alias the window of a stage
+  int ring;             // overlap-add warps: ring of NRF v frames (aliases the history frames: they own both), FS floats apart
+  int NRF, FS;          // 0 = no room for the ring: the transform warps keep the synthesis side
   int total;
 };
 
-enum { WS_BAR_FULL = 0, WS_BAR_EMPTY = 2, WS_BAR_TABLES = 4, WS_BAR_READY = 5, WS_BAR_RX0 = 6, WS_BAR_RX1 = 7, WS_NBARS = 8 };
+enum { WS_BAR_FULL = 0, WS_BAR_EMPTY = 2, WS_BAR_TABLES = 4, WS_BAR_READY = 5, WS_BAR_RX0 = 6, WS_BAR_RX1 = 7, WS_BAR_VFULL = 8,
+       WS_BAR_VEMPTY = 10, WS_NBARS = 12 };
 
 template <int M_, int R_, int PP_>
 BTK_HD constexpr WsSmem ws_smem_layout(int m) {
@@ -119,6 +140,17 @@ BTK_HD constexpr WsSmem ws_smem_layout(int m) {
   s.valias = (K::W * M_ * 4 <= win) ? 1 : 0;
   s.vcur = off;
   if (!s.valias) off += K::W * M_ * 4;
+  {
+    // ring of the overlap-add warps: the H history frames + one chunk, in whole chunks; frames 8 floats further apart
+    // than M so that the two lane groups of a warp (frames two apart) store into different banks
+    const int nrf = ((s.L.H + K::CHF - 1) / K::CHF + 1) * K::CHF, fs = M_ + 8;
+    const int ring_end = ((s.vhist + nrf * fs * 4) + 15) & ~15;
+    s.ring = s.vhist; s.NRF = 0; s.FS = fs;
+    if (K::NG == 2 && K::W % K::CHF == 0 && nrf / K::CHF <= 8 && (ring_end > off ? ring_end : off) <= 227 * 1024 - 1024) {
+      s.NRF = nrf;
+      if (ring_end > off) off = ring_end;
+    }
+  }
   s.rbuf = s.xbuf;
   s.L.xs = s.stage0; s.L.wts = s.stage0 + s.wts_off; s.L.xbuf = s.xbuf; s.L.vhist = s.vhist;
   s.total = off;
@@ -320,6 +352,131 @@ BTK_HD long long ws_window_start(const WsWalk& w, int it, int laN, int N) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Overlap-add warps.  Active when the window comes by tensor copies (the producer is then one thread of another
+// warpgroup), without a cluster, with a compile-time prototype length and two lane groups per warp (M = 128 .. 512).
+// Protocol per iteration (slot = iteration counter of the CTA & 1, the counter runs on across segments):
+//   transform warp w   wait VEMPTY[slot] -> park NVAL floats per lane at columns (slot * 2 + w / 4) * NVAL of its lane
+//                      quarter -> arrive VFULL[slot] (count NW);  nothing else: no CTA barrier, no shared memory
+//   overlap-add warps  wait VFULL[slot]; for every chunk of CHF = 4 frames, in frame order: the warp(s) of the lane
+//                      quarter(s) holding it copy it into the next slot of the ring, barrier, ALL overlap-add threads emit
+//                      the chunk's output frames (modulated.cc:646-661) from the ring (the history is the chunks before
+//                      it), barrier; after its last copy of the iteration every warp arrives on VEMPTY[slot] (count NSY)
+// ---------------------------------------------------------------------------------------------
+template <class K>
+BTK_HD bool ws_syn_mode(const WsSmem& S, bool ctx_ok, int csz) {
+  return ctx_ok && csz <= 1 && S.NRF > 0 && K::MT > 0 && K::NG == 2;
+}
+
+struct WsSynState {
+  int rs;        // ring slot (chunk index mod NRF / CHF) the next chunk goes to
+};
+
+template <int M_, int R_, int MT_, int PP_, class Ctx>
+BTK_HD void chain_ws_synth_begin(Ctx& sctx, unsigned char* smem, const WsSmem& S, WsSynState& st) {
+  typedef WsSynCfg<M_, R_, MT_, PP_> KS;
+  typedef ChainThreadState<M_, PP_> TS;
+  float* ring = reinterpret_cast<float*>(smem + S.ring);
+  sctx.par([&](int tid, TS&) {
+    for (int i = tid; i < S.NRF * S.FS; i += KS::NT) ring[i] = 0.f;       // zero history (modulated.cc:666-674)
+  });
+  st.rs = 0;
+  sctx.sync();
+}
+
+// One iteration of the overlap-add warps: W / CHF chunks.  sctx.tmem_load(slot, w, vals) hands a thread of the overlap-add
+// warp (w mod 4) the NVAL floats lane (tid mod 32) of transform warp w parked: value 2 r = v_{f0}[q_r], 2 r + 1 =
+// v_{f0 + 1}[q_r], q_r = index_of(gl, r), f0 = FW w + 2 grp for two frame pairs per warp, 2 w for one (group 0 only).
+template <int M_, int R_, int MT_, int PP_, class Ctx>
+BTK_HD void chain_ws_synth_iter(Ctx& sctx, const ChainParams& p, unsigned char* smem, const WsSmem& S, const WorkItem wk,
+                                const RecDesc rec, int it, int slot, WsSynState& st) {
+  typedef WsSynCfg<M_, R_, MT_, PP_> KS;
+  typedef typename KS::G G;
+  typedef ChainThreadState<M_, PP_> TS;
+  constexpr int CHF = KS::CHF, NCH = KS::W / CHF, D = KS::D, mm = MT_ > 0 ? MT_ : 1;
+  constexpr int WPC = CHF / KS::FW;                              // transform warps per chunk (1, or 2 with one pair per warp)
+  static_assert(WPC >= 1 && CHF % KS::FW == 0, "a chunk is whole transform warps");
+  const ChainSmem& L = S.L;
+  const int NRS = S.NRF / CHF, FS = S.FS;
+  float* ring = reinterpret_cast<float*>(smem + S.ring);
+  float* out = p.out + rec.out_off;
+  const int tau_base = wk.j0 + p.pd_s - L.H + it * KS::W;
+  const float gf = p.gain > 0 ? (float)p.gain : 1.f;
+  for (int c = 0; c < NCH; c++) {
+    float* cur = ring + st.rs * CHF * FS;
+    // ---- the chunk's frames out of tensor memory into the ring
+    sctx.par([&](int tid, TS&) {
+      const int sw = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+      BTK_UNROLL
+      for (int k = 0; k < WPC; k++) {
+        const int w = c * WPC + k;
+        if ((w & 3) != sw) continue;
+        // in pieces of at most 32 floats: the overlap-add warps run on a small register budget
+        constexpr int PC = KS::NVAL < 32 ? KS::NVAL : 32;
+        float* v0 = cur + (KS::FW * k + (PP_ == 2 ? 2 * grp : 0)) * FS;
+        BTK_UNROLL
+        for (int h = 0; h < KS::NVAL / PC; h++) {
+          float vals[PC];
+          sctx.template tmem_load<PC>(slot, w, h * PC, tid, vals);
+          if (PP_ == 1 && grp != 0) continue;                    // one pair per warp: lane group 0 holds it
+          BTK_UNROLL
+          for (int r2 = 0; r2 < PC / 2; r2++) {
+            const int q = G::index_of(gl, h * (PC / 2) + r2);
+            v0[q] = vals[2 * r2];
+            v0[FS + q] = vals[2 * r2 + 1];
+          }
+        }
+      }
+    });
+    if (c + 1 == NCH) sctx.v_release(slot);                      // this warp's last copy of the iteration is done
+    sctx.sync();
+    // ---- output frames jb .. jb + CHF - 1 from the ring: frame e of the chunk (e < 0: the chunks before it) sits in slot
+    // (rs - k) mod NRS with k = (CHF - 1 - e) / CHF chunks back
+    {
+      const int jb = tau_base + c * CHF - p.pd_s;
+      sctx.par([&](int tid, TS&) {
+        if (jb + CHF <= wk.j0 || jb >= wk.j0 + wk.nj) return;
+        const float* base[8];
+        BTK_UNROLL
+        for (int k = 0; k < 8; k++) base[k] = ring + ((st.rs + (NRS - (k % NRS))) % NRS) * CHF * FS;
+        for (int d = tid; d < D; d += KS::NT) {
+          float acc[CHF];
+          BTK_UNROLL
+          for (int f = 0; f < CHF; f++) acc[f] = 0.f;
+          BTK_UNROLL
+          for (int s = 0; s < R_; s++) {
+            const int back = R_ - 1 - s, q = d + s * D;
+            constexpr int NV = CHF + R_ * (mm - 1);
+            float g[mm], v[NV];
+            BTK_UNROLL
+            for (int k = 0; k < mm; k++) g[k] = p.taps_g[k * M_ + q];
+            BTK_UNROLL
+            for (int i = 0; i < NV; i++) {
+              const int e = i - back - R_ * (mm - 1);            // chunk-relative frame, compile time
+              const int kb = e >= 0 ? 0 : (CHF - 1 - e) / CHF;
+              v[i] = base[kb][(e + kb * CHF) * FS + q];
+            }
+            BTK_UNROLL
+            for (int f = 0; f < CHF; f++) {
+              float w = 0.f;
+              BTK_UNROLL
+              for (int k = 0; k < mm; k++) w = fmaf(g[k], v[f + R_ * (mm - 1) - R_ * k], w);
+              if (jb + f - back >= 0) acc[f] += w;
+            }
+          }
+          BTK_UNROLL
+          for (int f = 0; f < CHF; f++) {
+            const int j = jb + f;
+            if (j >= wk.j0 && j < wk.j0 + wk.nj) out[(long long)j * D + (D - 1 - d)] = acc[f] * gf;
+          }
+        }
+      });
+    }
+    sctx.sync();
+    st.rs = st.rs + 1 == NRS ? 0 : st.rs + 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // The compute side of the tile program.  Ctx provides, besides par / sync / syncwarp of chain_tile.cuh (sync = barrier
 // of the COMPUTE threads only):
 //   acquire(stage, parity, fill)    wait until the producer has filled `stage`; the host context runs fill() instead
@@ -356,10 +513,16 @@ BTK_HD void chain_ws_compute(Ctx& ctx, const ChainParams& p, unsigned char* smem
   const WsWalk walk = ws_walk<K>(p, wk, H, csz, rank);
   const bool vec4 = (C % 4 == 0) && (rec.pcm_off % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.pcm) & 15) == 0);
   const cf* wts = p.wts + (long long)wk.rec * p.wts_stride;
+  // overlap-add warps take the v frames of every iteration out of tensor memory: no synthesis side here (ws_syn_mode)
+  const bool syn = ws_syn_mode<K>(S, ctx.syn_ok(p), csz);
 
-  ctx.par([&](int tid, TS&) {
-    for (int i = tid; i < H * M_; i += K::NT) s_vhist[i] = 0.f;
-  });
+  if (!syn) {
+    ctx.par([&](int tid, TS&) {
+      for (int i = tid; i < H * M_; i += K::NT) s_vhist[i] = 0.f;
+    });
+  } else {
+    ctx.syn_begin_segment([&](auto& sctx, WsSynState& st) { chain_ws_synth_begin<M_, R_, MT_, PP_>(sctx, smem, S, st); });
+  }
   ctx.wait_tables();
   ctx.sync();
 
@@ -407,7 +570,25 @@ BTK_HD void chain_ws_compute(Ctx& ctx, const ChainParams& p, unsigned char* smem
       }
       s_last = st;
       // the stage whose window the v frames alias stays with the compute warps until the overlap-add is done
-      if (!(S.valias && cgi + 1 == walk.ncg)) ctx.release(st);
+      if (syn || !(S.valias && cgi + 1 == walk.ncg)) ctx.release(st);
+    }
+    if (syn) {
+      // ---- forward transforms of this warp's pairs, the two frames of each left in registers; park them in tensor memory
+      // for the overlap-add warps and go on with the next iteration
+      synth_gather_pairs<K>(ctx, s_xbuf);
+      synth_transform_store<K>(ctx, s_xbuf, s_twa, s_twb, (float*)nullptr, tau_base, 1, 0);
+      const int slot = ctx.v_slot();
+      ctx.v_acquire(slot);
+      ctx.par([&](int tid, TS& ts) {
+        float vals[K::NVAL];
+        BTK_UNROLL
+        for (int r = 0; r < G::V; r++) { vals[2 * r] = ts.g[r].x; vals[2 * r + 1] = ts.g[r].y; }
+        ctx.tmem_store(slot, tid, vals);
+      });
+      ctx.v_publish(slot, [&](auto& sctx, WsSynState& st) {
+        chain_ws_synth_iter<M_, R_, MT_, PP_>(sctx, p, smem, S, wk, rec, it, slot, st);
+      });
+      continue;
     }
     float* s_vcur = S.valias ? reinterpret_cast<float*>(smem + S.stage0 + s_last * S.stage_bytes)
                              : reinterpret_cast<float*>(smem + S.vcur);

@@ -84,6 +84,52 @@ __device__ __forceinline__ void tma_box_g2s(void* dst, const void* tmap, int c0,
                : "memory");
 }
 
+// tensor memory as a parking area (32x32b shape: lane t of the warp <-> lane 32 (warp mod 4) + t, N consecutive columns)
+template <int N> struct TmemIO;
+#define BTK_TM_R8(a, o) "%" #a ", %" #a "+1"
+template <> struct TmemIO<16> {
+  static __device__ __forceinline__ void st(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+                 "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]), "f"(v[10]),
+                 "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+                 : "memory");
+  }
+  static __device__ __forceinline__ void ld(uint32_t taddr, float* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]),
+                   "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+                 : "r"(taddr)
+                 : "memory");
+  }
+};
+template <> struct TmemIO<32> {
+  static __device__ __forceinline__ void st(uint32_t taddr, const float* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]),
+        "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]), "f"(v[18]), "f"(v[19]), "f"(v[20]), "f"(v[21]), "f"(v[22]),
+        "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31])
+        : "memory");
+  }
+  static __device__ __forceinline__ void ld(uint32_t taddr, float* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]), "=f"(v[10]),
+          "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]), "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]),
+          "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]),
+          "=f"(v[31])
+        : "r"(taddr)
+        : "memory");
+  }
+};
+template <> struct TmemIO<64> {
+  static __device__ __forceinline__ void st(uint32_t taddr, const float* v) { TmemIO<32>::st(taddr, v); TmemIO<32>::st(taddr + 32, v + 32); }
+  static __device__ __forceinline__ void ld(uint32_t taddr, float* v) { TmemIO<32>::ld(taddr, v); TmemIO<32>::ld(taddr + 32, v + 32); }
+};
+#undef BTK_TM_R8
+
 template <int M, int PP, int NT> struct DevCtxWS {
   ChainThreadState<M, PP> ts;
   uint64_t* bars;
@@ -98,6 +144,26 @@ template <int M, int PP, int NT> struct DevCtxWS {
     if ((threadIdx.x & 31) == 0) mbar_arrive(bars + WS_BAR_EMPTY + stage);
   }
   __device__ __forceinline__ void wait_tables() { mbar_wait(bars + WS_BAR_TABLES, 0); }
+  // ---- hand-over of the v frames to the overlap-add warps through tensor memory (chain_ws.cuh)
+  uint32_t tmem;        // base address of the CTA's allocation
+  int itc;              // iterations this CTA has published (runs on across segments)
+  bool syn;
+  static constexpr int NVAL = 2 * FFTGeom<M>::V;
+  __device__ __forceinline__ bool syn_ok(const ChainParams&) const { return syn; }
+  template <class F> __device__ __forceinline__ void syn_begin_segment(F) {}          // the overlap-add warps zero their ring themselves
+  __device__ __forceinline__ int v_slot() const { return itc & 1; }
+  __device__ __forceinline__ void v_acquire(int slot) { mbar_wait(bars + WS_BAR_VEMPTY + slot, ((itc >> 1) & 1) ^ 1); }
+  __device__ __forceinline__ void tmem_store(int slot, int tid, const float* vals) {
+    const int warp = tid >> 5;
+    TmemIO<NVAL>::st(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((slot * 2 + (warp >> 2)) * NVAL), vals);
+  }
+  template <class F> __device__ __forceinline__ void v_publish(int slot, F) {
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bars + WS_BAR_VFULL + slot);
+    itc++;
+  }
   __device__ __forceinline__ int cl_rank() const { return crank; }
   // Rendezvous of the compute warps of the whole cluster: every warp arrives on the READY barrier of every rank and waits
   // on its own.  Plain (CTA-scope release) remote arrives: the rendezvous only orders this CTA's earlier shared-memory
@@ -126,21 +192,54 @@ template <int M, int PP, int NT> struct DevCtxWS {
   }
 };
 
+// context of the overlap-add warps: threads [NT, NT + NST) of the CTA, their own named barrier
+template <int M, int PP, int NT, int NST> struct DevCtxSyn {
+  ChainThreadState<M, PP> ts;      // never touched (the overlap-add programs keep no transform state)
+  uint64_t* bars;
+  uint32_t tmem;
+  int itc;
+  static constexpr int NVAL = 2 * FFTGeom<M>::V;
+  template <class F> __device__ __forceinline__ void par(F f) { f((int)threadIdx.x - NT, ts); }
+  __device__ __forceinline__ void sync() { asm volatile("bar.sync 2, %0;" ::"n"(NST) : "memory"); }
+  __device__ __forceinline__ void syncwarp() { __syncwarp(); }
+  __device__ __forceinline__ void v_wait(int slot) {
+    mbar_wait(bars + WS_BAR_VFULL + slot, (itc >> 1) & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  // the NVAL floats lane (tid mod 32) of transform warp w parked; this warp is warp (w mod 4) of its warpgroup
+  template <int N> __device__ __forceinline__ void tmem_load(int slot, int w, int col0, int tid, float* vals) {
+    TmemIO<N>::ld(tmem + ((uint32_t)((w & 3) * 32) << 16) + (uint32_t)((slot * 2 + (w >> 2)) * NVAL + col0), vals);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  }
+  __device__ __forceinline__ void v_release(int slot) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bars + WS_BAR_VEMPTY + slot);
+  }
+};
+
 // Registers per thread of the two roles.  The CTA is launched with LR registers per thread (what __launch_bounds__ of
 // NT + 128 threads, one CTA per SM, allows); setmaxnreg.inc of the compute warpgroups can only take what setmaxnreg.dec of
 // the producer warpgroup has returned to the CTA's pool, so 128 (LR - RP) >= NT (RC - LR) must hold or the compute warps
 // spin in the allocation for ever.  RC covers the largest register program of each size (cuobjdump: 187 registers for
 // M <= 256 with two frame pairs per warp, 209 for M = 512); the producers keep the rest for loads in flight.
 template <int M, int NT> struct WsRegs {
-  static constexpr bool split = NT + 128 > 256;
-  static constexpr int LR = 65536 / (NT + 128) / 8 * 8;
+  // CTA = NT transform threads + the overlap-add warpgroup + the producer warpgroup
+  static constexpr int NTH = NT + 256;
+  static constexpr bool split = true;
+  static constexpr int LR = 65536 / NTH / 8 * 8;
   static constexpr int RC = M >= 512 ? 216 : 192;
-  static constexpr int RP = LR - ((NT * (RC - LR) + 127) / 128 + 7) / 8 * 8;
-  static_assert(!split || (RC > LR && RP >= 24 && 128 * (LR - RP) >= NT * (RC - LR)), "register pool balance");
+  static constexpr int RMIN = 24;                                // a warpgroup that only polls a barrier or leaves at once
+  // what the other working warpgroup gets: the pool minus the transform warps and the idle warpgroup, below the launch value
+  static constexpr int RREST_RAW = (65536 - NT * RC - 128 * RMIN) / 128 / 8 * 8;
+  static constexpr int RREST = RREST_RAW < LR ? RREST_RAW : LR - 8;
+  static constexpr int RP = RREST;                               // producer warps (register-load mode)
+  static constexpr int RS = RREST;                               // overlap-add warps (tensor-copy mode)
+  static_assert(RC > LR && RREST >= 40 && NT * RC + 128 * RREST + 128 * RMIN <= 65536, "register pool balance");
 };
 // loads in flight per producer thread follow its register budget (a task is LV 16-byte loads)
 template <int M, int NT, int LV> struct WsProd {
-  static constexpr int RP = WsRegs<M, NT>::split ? WsRegs<M, NT>::RP : 255;
+  static constexpr int RP = WsRegs<M, NT>::RP;
 #ifndef BTK_WS_LOADS_HI
 #define BTK_WS_LOADS_HI 8        // measured: 8 loads in flight beat 12 (cfg2 0.3479 -> 0.3419 ms) and 4 (0.3854 ms): a gentler producer disturbs the transform warps less
 #endif
@@ -152,7 +251,7 @@ template <int M, int NT, int LV> struct WsProd {
 };
 
 template <int M, int R, int MT, int PP>
-__global__ void __launch_bounds__(WsCfg<M, R, MT, PP>::NT + WsCfg<M, R, MT, PP>::NPT, 1) btk_chain_ws_kernel(const ChainParams p) {
+__global__ void __launch_bounds__(WsCfg<M, R, MT, PP>::NT + 256, 1) btk_chain_ws_kernel(const ChainParams p) {
   typedef WsCfg<M, R, MT, PP> K;
   typedef WsRegs<M, K::NT> RG;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -162,6 +261,9 @@ __global__ void __launch_bounds__(WsCfg<M, R, MT, PP>::NT + WsCfg<M, R, MT, PP>:
   const int csz = p.cluster > 1 ? p.cluster : 1;
   const int crank = csz > 1 ? (int)cg::this_cluster().block_rank() : 0;
   const int cta = (int)blockIdx.x / csz, ncta = (int)gridDim.x / csz;      // this CTA's (cluster's) share of the launch
+  // overlap-add warps + tensor memory hand-over (chain_ws.cuh::ws_syn_mode); uniform over the CTA
+  const bool syn = ws_syn_mode<K>(S, p.tmaps != nullptr && !p.no_syn, csz);
+  __shared__ uint32_t s_tmem;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < K::NS; s++) {
@@ -172,15 +274,53 @@ __global__ void __launch_bounds__(WsCfg<M, R, MT, PP>::NT + WsCfg<M, R, MT, PP>:
     mbar_init(bars + WS_BAR_READY, csz * K::NW);
     mbar_init(bars + WS_BAR_RX0, 1);
     mbar_init(bars + WS_BAR_RX1, 1);
+    for (int s = 0; s < 2; s++) {
+      mbar_init(bars + WS_BAR_VFULL + s, K::NW);
+      mbar_init(bars + WS_BAR_VEMPTY + s, K::NSY);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (syn && (int)threadIdx.x / 32 == K::NT / 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ws_smem_u32(&s_tmem)), "n"(K::TM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   if (csz > 1) cg::this_cluster().sync();      // nobody arrives on a remote barrier before it is initialised
 
-  if (threadIdx.x >= K::NT) {
+  if (threadIdx.x >= K::NT && threadIdx.x < K::NT + K::NST) {
+    // ------------------------------------------------------------------ overlap-add warpgroup
+    if (!syn) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RG::RMIN));
+    } else {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RG::RS));
+      DevCtxSyn<M, PP, K::NT, K::NST> sctx;
+      sctx.bars = bars; sctx.tmem = s_tmem; sctx.itc = 0;
+      WsSegs segs(p, cta, ncta);
+      WorkItem wk;
+      WsSynState st;
+      while (segs.next(wk)) {
+        const RecDesc rec = p.recs[wk.rec];
+        const int n_it = (wk.nj + S.L.H + K::W - 1) / K::W;
+        chain_ws_synth_begin<M, R, MT, PP>(sctx, smem, S, st);
+        for (int it = 0; it < n_it; it++, sctx.itc++) {
+          const int slot = sctx.itc & 1;
+          sctx.v_wait(slot);
+          chain_ws_synth_iter<M, R, MT, PP>(sctx, p, smem, S, wk, rec, it, slot, st);
+        }
+      }
+      // the allocation goes back when nobody touches tensor memory any more
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("bar.sync 3, %0;" ::"n"(K::NT + K::NST) : "memory");
+      if ((int)threadIdx.x / 32 == K::NT / 32)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sctx.tmem), "n"(K::TM_COLS) : "memory");
+    }
+  } else if (threadIdx.x >= K::NT + K::NST) {
     // ------------------------------------------------------------------ producer warpgroup
-    if (RG::split) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RG::RP));
-    const int ptid = (int)threadIdx.x - K::NT;
+    if (p.tmaps) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RG::RMIN));
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RG::RP));
+    const int ptid = (int)threadIdx.x - K::NT - K::NST;
     const ChainSmem& L = S.L;
     if (ptid == 0) {
       typedef FFTTables<M> FT;
@@ -283,13 +423,18 @@ __global__ void __launch_bounds__(WsCfg<M, R, MT, PP>::NT + WsCfg<M, R, MT, PP>:
     }
   } else {
     // ------------------------------------------------------------------ compute warps
-    if (RG::split) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(RG::RC));
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(RG::RC));
     DevCtxWS<M, PP, K::NT> ctx;
     ctx.bars = bars; ctx.csz = csz; ctx.crank = crank; ctx.cl_phase = 0;
+    ctx.tmem = syn ? s_tmem : 0u; ctx.itc = 0; ctx.syn = syn;
     WsSegs segs(p, cta, ncta);
     WorkItem wk;
     int g = 0;                                   // stages consumed so far by this CTA, across its segments
     while (segs.next(wk)) chain_ws_compute<M, R, MT, PP>(ctx, p, smem, wk, p.recs[wk.rec], g);
+    if (syn) {
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("bar.sync 3, %0;" ::"n"(K::NT + K::NST) : "memory");
+    }
   }
   // no CTA of a cluster leaves while a peer may still write into its shared memory
   if (csz > 1) cg::this_cluster().sync();
@@ -313,7 +458,7 @@ static cudaError_t launch_ws_one(const ChainParams& p, int n_work, cudaStream_t 
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(n_work * csz), 1, 1);
-  cfg.blockDim = dim3(K::NT + K::NPT, 1, 1);
+  cfg.blockDim = dim3(K::NT + 256, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

@@ -166,7 +166,29 @@ extern "C" int emu_synthesis(int M, int m, int r, int dct, int F, const float* Y
 template <int M, int PP> struct HostCtxWS {
   std::vector<ChainThreadState<M, PP> > ts;
   int nt;
+  // overlap-add warps (chain_ws.cuh): the host runs their program inline where the transform warps publish an iteration;
+  // "tensor memory" is an array [slot][transform warp][lane][value]
+  static constexpr int NVAL = 2 * FFTGeom<M>::V;
+  bool syn = false;
+  int nst = 0, itc = 0;
+  std::vector<float>* tm = nullptr;
+  WsSynState* sst = nullptr;
   explicit HostCtxWS(int n) : ts(n), nt(n) {}
+  bool syn_ok(const ChainParams&) const { return syn; }
+  HostCtxWS sub() const { HostCtxWS s(nst); s.tm = tm; return s; }
+  template <class F> void syn_begin_segment(F f) { HostCtxWS s = sub(); f(s, *sst); }
+  int v_slot() const { return itc & 1; }
+  void v_acquire(int) {}
+  void tmem_store(int slot, int tid, const float* vals) {
+    float* d = tm->data() + ((size_t)(slot * 8 + (tid >> 5)) * 32 + (tid & 31)) * NVAL;
+    for (int i = 0; i < NVAL; i++) d[i] = vals[i];
+  }
+  template <class F> void v_publish(int slot, F f) { (void)slot; HostCtxWS s = sub(); f(s, *sst); itc++; }
+  template <int N> void tmem_load(int slot, int w, int col0, int tid, float* vals) const {
+    const float* d = tm->data() + ((size_t)(slot * 8 + w) * 32 + (tid & 31)) * NVAL + col0;
+    for (int i = 0; i < N; i++) vals[i] = d[i];
+  }
+  void v_release(int) {}
   template <class F> void par(F f) { for (int t = 0; t < nt; t++) f(t, ts[t]); }
   void sync() {}
   void syncwarp() {}
@@ -183,7 +205,7 @@ template <int M, int PP> struct HostCtxWS {
 template <int M, int R, int MT, int PP>
 static int run_chain_ws(int m, int dct, int C, int n_rec, const long long* Ts, const float* pcm, const long long* pcm_off,
                         float* out, const long long* out_off, const double* h, const double* g, const double* w_re_im,
-                        int gain, int chunk) {
+                        int gain, int chunk, int syn) {
   typedef WsCfg<M, R, MT, PP> K;
   typedef FFTTables<M> FT;
   int r = 0; for (int x = R; x > 1; x >>= 1) r++;
@@ -208,11 +230,16 @@ static int run_chain_ws(int m, int dct, int C, int n_rec, const long long* Ts, c
   p.taps_h = hf.data(); p.taps_g = gp.data(); p.wts = gam.data(); p.wts_stride = 0; p.one_cta = 0; p.no_prefetch = 0; p.twa = twa.data(); p.twb = twb.data();
   p.C = C; p.Cpad = Cpad; p.m = m; p.pd_s = geo.pd_s; p.laN = geo.laN; p.gain = gain; p.cluster = 1;
   p.tmaps = nullptr; p.tma_rows = 0; p.item_begin = nullptr; p.item_q = 0; p.item0 = 0; p.n_items = 0; p.n_rec = n_rec;
+  p.no_syn = syn ? 0 : 1;
   const WsSmem S = ws_smem_layout<M, R, PP>(m);
   if (S.total > 227 * 1024) return -2;
   std::vector<unsigned char> smem(S.total + 64, 0xA5);
   for (size_t wi = 0; wi < work.size(); wi++) {
     HostCtxWS<M, PP> ctx(K::NT);
+    std::vector<float> tm((size_t)2 * 8 * 32 * HostCtxWS<M, PP>::NVAL, 1e30f);
+    WsSynState sst;
+    sst.rs = 0;
+    ctx.syn = syn != 0; ctx.nst = K::NST; ctx.tm = &tm; ctx.sst = &sst;
     memset(smem.data(), 0xA5, smem.size());   // poison: every read must have been written
     // what the bulk copies of the producer bring at CTA start
     memcpy(smem.data() + S.L.taps, hf.data(), (size_t)K::D * S.L.TS * 4);
@@ -227,7 +254,7 @@ static int run_chain_ws(int m, int dct, int C, int n_rec, const long long* Ts, c
 extern "C" int emu_chain_ws(int M, int m, int r, int dct, int C, int n_rec, const long long* Ts, const float* pcm,
                             const long long* pcm_off, float* out, const long long* out_off, const double* h,
                             const double* g, const double* w_re_im, int gain, int chunk, int fast) {
-#define ARGS m, dct, C, n_rec, Ts, pcm, pcm_off, out, out_off, h, g, w_re_im, gain, chunk
+#define ARGS m, dct, C, n_rec, Ts, pcm, pcm_off, out, out_off, h, g, w_re_im, gain, chunk, (fast & 4) ? 0 : 1
 #define CASE(MM, RR) \
   if (M == MM && (1 << r) == RR) { \
     if ((fast & 2) && MM <= 256) { \

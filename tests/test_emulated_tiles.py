@@ -63,10 +63,11 @@ def test_emulated_chain_matches_oracle(case, fast, emu, prototypes):
     assert bo.snr_db(out, ref) > 100.0   # north_star gate is 70 dB
 
 
-@pytest.mark.parametrize("fast", [3, 1, 0])
+@pytest.mark.parametrize("fast", [3, 1, 0, 7, 5])   # bit 2: the transform warps keep the synthesis side (no overlap-add warps)
 @pytest.mark.parametrize("case", CASES)
 def test_emulated_ws_chain_matches_oracle(case, fast, emu, prototypes):
-    """The warp-specialised tile program (csrc/chain_ws.cuh): producer fill + stage rotation + compute side."""
+    """The warp-specialised tile program (csrc/chain_ws.cuh): producer fill + stage rotation + compute side + the overlap-add
+    warps' program (frames parked per lane, ring of chunks) where the shape has one (compile-time m, two lane groups)."""
     M, m, r, dct, C, T, chunk = case
     h, g = proto(prototypes, M, m, r)
     geo = bo.BankGeometry(M, m, r, dct)
