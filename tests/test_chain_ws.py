@@ -94,6 +94,41 @@ def test_ws_chain_long_ragged_batch(prototypes):
     plan.close()
 
 
+@pytest.mark.parametrize("cfg", [(256, 4, 1, 8), (512, 2, 2, 16), (128, 2, 1, 4), (256, 2, 1, 12), (128, 4, 1, 8)])
+def test_ws_chain_many_short_recordings(cfg, prototypes):
+    """Persistent schedule + overlap-add warpgroup (chain_ws.cuh 'WsSegs', 'chain_ws_synth_iter'): hundreds of short recordings
+    make every CTA walk several segments -- history ring zeroed per segment, stage counters and the tensor-memory slots
+    running on across them, transform warps an iteration ahead of the overlap-add warps -- and a few long ones are cut
+    between CTAs.  Every output against the oracle, and the same bits on a second run."""
+    M, m, r, C = cfg
+    D = M >> r
+    try:
+        h, g = proto(prototypes, M, m, r)
+    except Exception:
+        h, g = wl.kaiser_prototype(M, m, r)
+    geo = bo.BankGeometry(M, m, r, 0)
+    rng = np.random.default_rng(M + C)
+    plan = btk_b200.Plan(M, m, r, C, h, g)
+    W = _weights(rng, geo, C, M)
+    plan.set_weights(W)
+    Ts = [int(v) for v in rng.integers(1, 40 * D, 300)] + [0, 0, 5000 * D + 3, 1, 2500 * D]
+    rng.shuffle(Ts)
+    pcms = [wl.noise_recording(T, C, seed=1000 + i, sigma=500.0) for i, T in enumerate(Ts)]
+    outs = plan.chain_batch(pcms)
+    assert plan.tuning()["chain_ws"] == 1
+    for i in list(range(0, len(Ts), 7)) + [Ts.index(5000 * D + 3), Ts.index(2500 * D)]:
+        x, out = pcms[i], outs[i]
+        if x.shape[0] == 0:
+            assert out.size == 0
+            continue
+        ref = bo.chain(x, h, g, geo, W)[2]
+        assert out.shape == ref.shape and bo.snr_db(out, ref) >= 70.0, f"recording {i} of {Ts[i]} samples"
+    again = plan.chain_batch(pcms)
+    for a, b in zip(outs, again):
+        assert np.array_equal(a, b)
+    plan.close()
+
+
 def test_ws_chain_unaligned_and_odd_channels(prototypes):
     """Channel counts that are not multiples of four take the scalar staging path; zero-length recordings emit nothing."""
     M, m, r = 512, 2, 2
