@@ -611,97 +611,90 @@ __global__ void __launch_bounds__(128) btk_mvdr_chol_kernel(const double2* __res
   }
   if (tid == 0) s_bad = 0;
   __syncthreads();
-  for (int kp = 0; kp < C; kp += NP) {
-    const int pw = C - kp < NP ? C - kp : NP, r0 = kp + pw;
-    // ---- (1) the panel's diagonal block, rows kp .. kp+pw-1, inside warp 0 (lane p = row kp + p)
-    if (warp == 0) {
-      // lane < 28 owns one entry (bi, bj), 1 <= bj <= bi <= 7, of the block's lower triangle (column 0 is never updated):
-      // a step is ONE multiply-add per lane, not a loop per row
-      int bi = 0, bj = 0;                                        // bj = 0: no entry (lanes 28 .. 31)
-      {
-        int l = lane, b = 1;
-        while (b < NP && l >= NP - b) { l -= NP - b; b++; }
-        if (b < NP) { bj = b; bi = b + l; }
-      }
-      const int oi = chol_row_off(kp + bi < C ? kp + bi : 0, C), oj = chol_row_off(kp + bj < C ? kp + bj : 0, C);
-      bool bad = false;
-      for (int p = 0; p < pw; p++) {
-        const int k = kp + p;
-        const double Dk = A[chol_row_off(k, C) + k].x;
-        if (!(Dk > dThreshold) || !isfinite(Dk)) { bad = true; break; }          // same value in every lane
-        if (bj > p && bi < pw) {
-          const double rD = 1.0 / Dk;
-          const double2 ci = A[oi + k], cj = A[oj + k];
-          const double2 f = make_double2(ci.x * rD, ci.y * rD);
-          double2 a = A[oi + kp + bj];
-          a.x -= f.x * cj.x + f.y * cj.y;                                        // f conj(c_jk)
-          a.y -= f.y * cj.x - f.x * cj.y;
-          A[oi + kp + bj] = a;
-        }
-        __syncwarp();
-      }
-      if (bad) {
-        if (lane == 0) s_bad = 1;
-      } else {
-        if (lane < pw) Dinv[kp + lane] = 1.0 / A[chol_row_off(kp + lane, C) + kp + lane].x;
-        __syncwarp();
-        // conj(L_pq) = conj(c_pq) / D_q for q < p, zero elsewhere (the rows below read the whole table)
-        for (int e = lane; e < NP * NP; e += 32) {
-          const int pp = e / NP, q = e % NP;
-          double2 v = make_double2(0.0, 0.0);
-          if (q < pp && pp < pw) { const double2 c = A[chol_row_off(kp + pp, C) + kp + q]; const double r = Dinv[kp + q]; v = make_double2(c.x * r, -c.y * r); }
-          Bm[e] = v;
-        }
-      }
-    }
-    __syncthreads();
-    if (s_bad) break;
-    // ---- (2) rows below the block, one thread per row: c_ip -= sum_{q<p} c_iq conj(L_pq); multipliers W_ip = conj(c_ip) / D_p
+  // (1) the diagonal block of the panel at kp (rows kp .. kp+pw-1), inside warp 0: lane < 28 owns one entry (bi, bj),
+  // 1 <= bj <= bi <= 7, of the block's lower triangle (column 0 is never updated), a step is ONE multiply-add per lane
+  auto block_factor = [&](int kp, int pw) {
+    int bi = 0, bj = 0;                                          // bj = 0: no entry (lanes 28 .. 31)
     {
-      const int i = r0 + tid;
-      if (i < NR) {
-        const int oi = chol_row_off(i, C);
-        double2 c[NP];
+      int l = lane, b = 1;
+      while (b < NP && l >= NP - b) { l -= NP - b; b++; }
+      if (b < NP) { bj = b; bi = b + l; }
+    }
+    const int oi = chol_row_off(kp + bi < C ? kp + bi : 0, C), oj = chol_row_off(kp + bj < C ? kp + bj : 0, C);
+    bool bad = false;
+    for (int p = 0; p < pw; p++) {
+      const int k = kp + p;
+      const double Dk = A[chol_row_off(k, C) + k].x;
+      if (!(Dk > dThreshold) || !isfinite(Dk)) { bad = true; break; }            // same value in every lane
+      if (bj > p && bi < pw) {
+        const double rD = 1.0 / Dk;
+        const double2 ci = A[oi + k], cj = A[oj + k];
+        const double2 f = make_double2(ci.x * rD, ci.y * rD);
+        double2 a = A[oi + kp + bj];
+        a.x -= f.x * cj.x + f.y * cj.y;                                          // f conj(c_jk)
+        a.y -= f.y * cj.x - f.x * cj.y;
+        A[oi + kp + bj] = a;
+      }
+      __syncwarp();
+    }
+    if (bad) {
+      if (lane == 0) s_bad = 1;
+      return;
+    }
+    if (lane < pw) Dinv[kp + lane] = 1.0 / A[chol_row_off(kp + lane, C) + kp + lane].x;
+    __syncwarp();
+    // conj(L_pq) = conj(c_pq) / D_q for q < p, zero elsewhere (the rows below read the whole table)
+    for (int e = lane; e < NP * NP; e += 32) {
+      const int pp = e / NP, q = e % NP;
+      double2 v = make_double2(0.0, 0.0);
+      if (q < pp && pp < pw) { const double2 c = A[chol_row_off(kp + pp, C) + kp + q]; const double r = Dinv[kp + q]; v = make_double2(c.x * r, -c.y * r); }
+      Bm[e] = v;
+    }
+  };
+  // (2) rows below the block, one thread per row: c_ip -= sum_{q<p} c_iq conj(L_pq); multipliers W_ip = conj(c_ip) / D_p
+  auto rows_below = [&](int kp, int pw) {
+    const int i = kp + pw + tid;
+    if (i >= NR) return;
+    const int oi = chol_row_off(i, C);
+    double2 c[NP];
 #pragma unroll
-        for (int p = 0; p < NP; p++) c[p] = p < pw ? A[oi + kp + p] : make_double2(0.0, 0.0);
+    for (int p = 0; p < NP; p++) c[p] = p < pw ? A[oi + kp + p] : make_double2(0.0, 0.0);
 #pragma unroll
-        for (int p = 1; p < NP; p++) {
+    for (int p = 1; p < NP; p++) {
 #pragma unroll
-          for (int q = 0; q < p; q++) {
-            const double2 l = Bm[p * NP + q];
-            c[p].x -= c[q].x * l.x - c[q].y * l.y;
-            c[p].y -= c[q].x * l.y + c[q].y * l.x;
-          }
-        }
-#pragma unroll
-        for (int p = 0; p < NP; p++) {
-          if (p < pw) {
-            A[oi + kp + p] = c[p];
-            const double r = Dinv[kp + p];
-            Wm[i * NP + p] = make_double2(c[p].x * r, -c[p].y * r);
-          } else {
-            Wm[i * NP + p] = make_double2(0.0, 0.0);
-          }
-        }
+      for (int q = 0; q < p; q++) {
+        const double2 l = Bm[p * NP + q];
+        c[p].x -= c[q].x * l.x - c[q].y * l.y;
+        c[p].y -= c[q].x * l.y + c[q].y * l.x;
       }
     }
-    __syncthreads();
-    // ---- (3) rank-pw update of the trailing rows r0 .. NR-1, columns r0 .. min(i, C-1): lanes across the rows, warps across
-    // blocks of four columns (the multipliers of a column are a broadcast load, a row's panel entries stay in registers)
-    for (int ib = r0 + lane; ib < NR; ib += 32) {
-      const int i = ib, jmax = i < C ? i : C - 1;
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+      if (p < pw) {
+        A[oi + kp + p] = c[p];
+        const double r = Dinv[kp + p];
+        Wm[i * NP + p] = make_double2(c[p].x * r, -c[p].y * r);
+      } else {
+        Wm[i * NP + p] = make_double2(0.0, 0.0);
+      }
+    }
+  };
+  // (3) rank-pw update of the rows from `rlo` on, columns [jlo, jhi) (clipped to the row's lower triangle): lanes across the
+  // rows, the `nwp` participating warps (this one is number `wp`) across blocks of four columns -- the multipliers of a column
+  // are a broadcast load, a row's panel entries stay in registers, eight independent accumulation chains per lane
+  auto trailing = [&](int kp, int pw, int rlo, int jlo, int jhi, int wp, int nwp) {
+    for (int i = rlo + lane; i < NR; i += 32) {
+      const int jtop = i < C ? i : C - 1, jmax = jtop < jhi - 1 ? jtop : jhi - 1;
       const int oi = chol_row_off(i, C);
       double2 c[NP];
 #pragma unroll
       for (int p = 0; p < NP; p++) c[p] = p < pw ? A[oi + kp + p] : make_double2(0.0, 0.0);
-      for (int j0 = r0 + 4 * warp; j0 <= jmax; j0 += 4 * (nt >> 5)) {
-        // four columns at a time: eight independent accumulation chains per lane (columns past the row's diagonal run on
-        // column jmax's multipliers and are not stored)
+      for (int j0 = jlo + 4 * wp; j0 <= jmax; j0 += 4 * nwp) {
         double2 a[4];
         const double2* wj[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-          const int j = j0 + q <= jmax ? j0 + q : jmax;
+          const int j = j0 + q <= jmax ? j0 + q : jmax;          // columns past the clip run on column jmax and are not stored
           a[q] = A[oi + j];
           wj[q] = Wm + j * NP;
         }
@@ -718,6 +711,35 @@ __global__ void __launch_bounds__(128) btk_mvdr_chol_kernel(const double2* __res
         for (int q = 0; q < 4; q++) if (j0 + q <= jmax) A[oi + j0 + q] = a[q];
       }
     }
+  };
+  // Panels with a look-ahead of one: the columns of the NEXT panel are updated first (3a), then warp 0 factors the next
+  // diagonal block while the other warps finish the trailing update (3b) -- the serial 8 x 8 block was half of the stall
+  // samples when everybody waited for it -- then the rows below the next block (2).  Three CTA barriers per panel.
+  {
+    const int pw0 = C < NP ? C : NP;
+    if (warp == 0) block_factor(0, pw0);
+    __syncthreads();
+    if (!s_bad) rows_below(0, pw0);
+    __syncthreads();
+  }
+  for (int kp = 0; kp < C && !s_bad; kp += NP) {
+    const int pw = C - kp < NP ? C - kp : NP, r0 = kp + pw;
+    const int pwn = r0 >= C ? 0 : (C - r0 < NP ? C - r0 : NP);   // width of the next panel
+    const int nwarp = nt >> 5;
+    if (pwn == 0) {
+      // last panel: only the right-hand-side rows are left below it, and they have no columns past C
+      break;
+    }
+    // (3a) the next panel's columns of every row below this panel
+    trailing(kp, pw, r0, r0, r0 + pwn, warp, nwarp);
+    __syncthreads();
+    // (3b) the rest of the trailing matrix (warps 1 ..) | (1) the next diagonal block (warp 0)
+    if (warp == 0) block_factor(r0, pwn);
+    else trailing(kp, pw, r0 + pwn, r0 + pwn, C, warp - 1, nwarp - 1);
+    __syncthreads();
+    if (s_bad) break;
+    // (2) rows below the next block
+    rows_below(r0, pwn);
     __syncthreads();
   }
   const bool bad = s_bad != 0;
