@@ -12,8 +12,14 @@
 //     cp.async.bulk per stage for the 4 channels' weight rows, completing on the stage's "full" mbarrier.
 //   * NS = 2 stages.  The window of the next channel group (or of the next iteration's first group) lands while the
 //     transforms of the current one run, so global-load latency never sits on a transform warp.
-//   * the synthesis side's current-v frames alias the window of the LAST stage of an iteration where they fit; that
-//     stage is handed back after the overlap-add instead of after the last transform.
+//   * the window arrives by tensor copies (cp.async.bulk.tensor, one thread) in the layout of the input where the
+//     batch allows it (WsCfg::RAW; kern_ws.cuh); the producer warps with register loads are the fallback.
+//   * synthesis side, tensor-copy mode: the two v frames of every frame pair leave the transform warps through TENSOR
+//     MEMORY and an overlap-add warpgroup turns them into output frames (ws_syn_mode, chain_ws_synth_iter below) -- the
+//     transform warps run from one iteration into the next without a CTA barrier.  Otherwise the transform warps keep
+//     the synthesis side: the current-v frames alias the window of the LAST stage of an iteration where they fit, and
+//     that stage is handed back after the overlap-add instead of after the last transform.
+//   * persistent schedule: a CTA walks a contiguous share of the launch as per-recording segments (WsSegs below).
 //
 // Thread-block clusters (channel split): with p.cluster = S > 1 the S CTAs of a cluster share one work item and CTA
 // `rank` takes channel groups [rank * ncg, (rank + 1) * ncg).  A row of interleaved PCM is then read by S CTAs, each

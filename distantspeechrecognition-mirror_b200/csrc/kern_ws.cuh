@@ -1,12 +1,17 @@
 // kern_ws.cuh -- __global__ wrapper, device context and launch dispatch of the warp-specialised fused chain
 // (chain_ws.cuh).  Included by kern_ws_m<M>.cu with one transform size per translation unit.
 //
-// Roles inside a CTA of NT + 128 threads:
-//   threads [0, NT)        compute warps   (setmaxnreg.inc: the transform register program needs 230-240 registers)
-//   threads [NT, NT + 128) producer warps  (setmaxnreg.dec: 16-byte loads, register transpose, shared stores)
-// Synchronisation: mbarriers in shared memory (full / empty per stage, one for the tables), a named barrier for the
-// compute warps, cluster-scope mbarriers for the channel-split reduction.  Bulk asynchronous copies (cp.async.bulk,
-// SASS UBLKCP) bring the tap / twiddle tables at CTA start and the weight rows of every stage.
+// Roles inside a CTA of NT + 256 threads (one CTA per SM, launched with 128 registers per thread, setmaxnreg on every warpgroup):
+//   threads [0, NT)              transform warps       up to 192 / 216 registers: polyphase, transforms, weight accumulate
+//   threads [NT, NT + 128)       overlap-add warpgroup 104 / 56 registers (tensor-copy mode): takes the v frames of every
+//                                iteration out of tensor memory and runs the synthesis polyphase + overlap-add + stores
+//   threads [NT + 128, NT + 256) producer warpgroup    tensor-copy mode: ONE thread issues cp.async.bulk.tensor boxes and the
+//                                weight rows (24 registers); register-load mode: four warps of 16-byte loads
+// Synchronisation: mbarriers in shared memory (full / empty per stage, one for the tables, full / empty per tensor-memory
+// slot), named barriers for the transform warps (1) and the overlap-add warps (2), cluster-scope mbarriers for the
+// channel-split reduction.  Bulk asynchronous copies (cp.async.bulk, SASS UBLKCP) bring the tap / twiddle tables once per
+// CTA and the weight rows of every stage; tcgen05.alloc / st / ld / dealloc (UTCATOMSWS, STTM, LDTM) carry the v frames.
+// The CTA is persistent: it walks its share of the launch as segments (chain_ws.cuh::WsSegs).
 #pragma once
 
 #include <cooperative_groups.h>
