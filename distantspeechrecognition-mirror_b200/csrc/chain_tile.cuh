@@ -110,6 +110,10 @@ struct ChainCfg {
   static constexpr int NG = G::NG;             // lane groups per warp = channels processed concurrently
   static constexpr int XS = PP_;               // exchange buffers per lane group (one per frame pair)
   static constexpr int E = G::Ra / R_;         // registers between members of one residue class
+  // lane <-> (lane group, lane inside the group): groups are runs of L consecutive lanes here (chain_ws.cuh interleaves them)
+  static BTK_HD int lane_grp(int lane) { return lane / G::L; }
+  static BTK_HD int lane_gl(int lane) { return lane % G::L; }
+  static constexpr int XPAD = 0;               // complex words between the exchange buffers of consecutive lane groups
   // emit: frames per thread (register blocking of the synthesis polyphase)
   static constexpr int FPT_RAW = (W * D) / NT;
   static constexpr int FPT = FPT_RAW >= 8 ? 8 : (FPT_RAW >= 4 ? 4 : (FPT_RAW >= 2 ? 2 : 1));
@@ -320,9 +324,9 @@ BTK_HD void synth_transform_store(Ctx& ctx, cf* s_xbuf, const cf* s_twa, const c
     return pair_mod <= 1 || (warp * K::PP + (K::NG == 1 ? 0 : grp)) % pair_mod == pair_rem;
   };
   static_assert(K::NG > 1 || K::XS == K::PP, "a lane owning PP transforms needs PP exchange buffers");
-  auto slot = [&](int warp, int grp) { return s_xbuf + ((warp * K::NG + grp) * K::XS) * G::XBUF; };
+  auto slot = [&](int warp, int grp) { return s_xbuf + ((warp * K::NG + grp) * K::XS) * G::XBUF + (warp * K::NG + grp) * K::XPAD; };
   ctx.par([&](int tid, TS& ts) {
-    const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+    const int warp = tid >> 5, lane = tid & 31, grp = K::lane_grp(lane), gl = K::lane_gl(lane);
     if (owns(warp, grp)) {
       if (G::ASYM) GroupFFT<M_, -1>::template inv_step1_multi<NP>(ts.g, gl, slot(warp, grp), s_twa);
       else GroupFFT<M_, -1>::template step1_multi<NP>(ts.g, gl, slot(warp, grp), s_twa);
@@ -331,7 +335,7 @@ BTK_HD void synth_transform_store(Ctx& ctx, cf* s_xbuf, const cf* s_twa, const c
   ctx.syncwarp();
   if (G::Rb > 1) {
     ctx.par([&](int tid, TS& ts) {
-      const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+      const int warp = tid >> 5, lane = tid & 31, grp = K::lane_grp(lane), gl = K::lane_gl(lane);
       if (owns(warp, grp)) {
         BTK_UNROLL
         for (int pp = 0; pp < NP; pp++) GroupFFT<M_, -1>::step2_load(ts.g + pp * G::V, gl, slot(warp, grp) + pp * G::XBUF, s_twb);
@@ -339,7 +343,7 @@ BTK_HD void synth_transform_store(Ctx& ctx, cf* s_xbuf, const cf* s_twa, const c
     });
     ctx.syncwarp();
     ctx.par([&](int tid, TS& ts) {
-      const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+      const int warp = tid >> 5, lane = tid & 31, grp = K::lane_grp(lane), gl = K::lane_gl(lane);
       if (owns(warp, grp)) {
         BTK_UNROLL
         for (int pp = 0; pp < NP; pp++) GroupFFT<M_, -1>::step2_store(ts.g + pp * G::V, gl, slot(warp, grp) + pp * G::XBUF);
@@ -348,7 +352,7 @@ BTK_HD void synth_transform_store(Ctx& ctx, cf* s_xbuf, const cf* s_twa, const c
     ctx.syncwarp();
   }
   ctx.par([&](int tid, TS& ts) {
-    const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+    const int warp = tid >> 5, lane = tid & 31, grp = K::lane_grp(lane), gl = K::lane_gl(lane);
     if (owns(warp, grp)) {
       BTK_UNROLL
       for (int pp = 0; pp < NP; pp++) {
@@ -386,9 +390,11 @@ BTK_HD void synth_gather_pairs(Ctx& ctx, cf* s_xbuf) {
   if (K::NG == 1) return;
   // with one exchange buffer per lane group (XS == 1 < PP) every group parks exactly one partial: needs NG == PP == 2
   static_assert(K::XS == K::PP || (K::XS == 1 && K::NG == 2 && K::PP == 2), "exchange buffers per lane group");
-  auto slot = [&](int warp, int grp, int pp) { return s_xbuf + ((warp * K::NG + grp) * K::XS + (K::XS == K::PP ? pp : 0)) * G::XBUF; };
+  auto slot = [&](int warp, int grp, int pp) {
+    return s_xbuf + ((warp * K::NG + grp) * K::XS + (K::XS == K::PP ? pp : 0)) * G::XBUF + (warp * K::NG + grp) * K::XPAD;
+  };
   ctx.par([&](int tid, TS& ts) {
-    const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+    const int warp = tid >> 5, lane = tid & 31, grp = K::lane_grp(lane), gl = K::lane_gl(lane);
     BTK_UNROLL
     for (int pp = 0; pp < K::PP; pp++) {
       if (grp != pp) {
@@ -400,7 +406,7 @@ BTK_HD void synth_gather_pairs(Ctx& ctx, cf* s_xbuf) {
   });
   ctx.syncwarp();
   ctx.par([&](int tid, TS& ts) {
-    const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+    const int warp = tid >> 5, lane = tid & 31, grp = K::lane_grp(lane), gl = K::lane_gl(lane);
     if (grp < K::PP) {
       cf acc[G::V];
       BTK_UNROLL
@@ -534,12 +540,12 @@ BTK_HD void analysis_round(Ctx& ctx, const ChainSmem& L, const float* s_xs, cons
   typedef typename K::G G;
   constexpr int M_ = K::M;
   typedef ChainThreadState<M_, K::PP> TS;
-  auto slot = [&](int warp, int grp) { return s_xbuf + ((warp * K::NG + grp) * K::XS) * G::XBUF; };
+  auto slot = [&](int warp, int grp) { return s_xbuf + ((warp * K::NG + grp) * K::XS) * G::XBUF + (warp * K::NG + grp) * K::XPAD; };
   if constexpr (K::XS < K::PP) {
     // the frame pairs of a lane take turns on one exchange buffer: pass A of all pairs (one set of twiddles), then
     // scatter / gather pair by pair, then the final radix passes
     ctx.par([&](int tid, TS& ts) {
-      const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+      const int warp = tid >> 5, lane = tid & 31, grp = K::lane_grp(lane), gl = K::lane_gl(lane);
       const int c_local = round * K::NG + grp;
       polyphase_pairs<K>(ts.z, gl, K::RAW ? s_xs + c_local : s_xs + c_local * L.CS, warp, s_taps, L, m);
       GroupFFT<M_, +1>::template step1_twiddle<K::PP>(ts.z, gl, s_twa);
@@ -548,13 +554,13 @@ BTK_HD void analysis_round(Ctx& ctx, const ChainSmem& L, const float* s_xs, cons
     ctx.syncwarp();
     for (int pp = 0; pp < K::PP; pp++) {
       ctx.par([&](int tid, TS& ts) {
-        const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+        const int warp = tid >> 5, lane = tid & 31, grp = K::lane_grp(lane), gl = K::lane_gl(lane);
         GroupFFT<M_, +1>::step3_gather(ts.z + pp * G::V, gl, slot(warp, grp));
       });
       ctx.syncwarp();
       if (pp + 1 < K::PP) {
         ctx.par([&](int tid, TS& ts) {
-          const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+          const int warp = tid >> 5, lane = tid & 31, grp = K::lane_grp(lane), gl = K::lane_gl(lane);
           GroupFFT<M_, +1>::step1_scatter(ts.z + (pp + 1) * G::V, gl, slot(warp, grp));
         });
         ctx.syncwarp();
@@ -567,7 +573,7 @@ BTK_HD void analysis_round(Ctx& ctx, const ChainSmem& L, const float* s_xs, cons
     return;
   }
   ctx.par([&](int tid, TS& ts) {
-    const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+    const int warp = tid >> 5, lane = tid & 31, grp = K::lane_grp(lane), gl = K::lane_gl(lane);
     const int c_local = round * K::NG + grp;
     polyphase_pairs<K>(ts.z, gl, K::RAW ? s_xs + c_local : s_xs + c_local * L.CS, warp, s_taps, L, m);
     GroupFFT<M_, +1>::template step1_multi<K::PP>(ts.z, gl, slot(warp, grp), s_twa);
@@ -575,20 +581,20 @@ BTK_HD void analysis_round(Ctx& ctx, const ChainSmem& L, const float* s_xs, cons
   ctx.syncwarp();
   if (G::Rb > 1) {
     ctx.par([&](int tid, TS& ts) {
-      const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+      const int warp = tid >> 5, lane = tid & 31, grp = K::lane_grp(lane), gl = K::lane_gl(lane);
       BTK_UNROLL
       for (int pp = 0; pp < K::PP; pp++) GroupFFT<M_, +1>::step2_load(ts.z + pp * G::V, gl, slot(warp, grp) + pp * G::XBUF, s_twb);
     });
     ctx.syncwarp();
     ctx.par([&](int tid, TS& ts) {
-      const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+      const int warp = tid >> 5, lane = tid & 31, grp = K::lane_grp(lane), gl = K::lane_gl(lane);
       BTK_UNROLL
       for (int pp = 0; pp < K::PP; pp++) GroupFFT<M_, +1>::step2_store(ts.z + pp * G::V, gl, slot(warp, grp) + pp * G::XBUF);
     });
     ctx.syncwarp();
   }
   ctx.par([&](int tid, TS& ts) {
-    const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+    const int warp = tid >> 5, lane = tid & 31, grp = K::lane_grp(lane), gl = K::lane_gl(lane);
     BTK_UNROLL
     for (int pp = 0; pp < K::PP; pp++) GroupFFT<M_, +1>::step3(ts.z + pp * G::V, gl, slot(warp, grp) + pp * G::XBUF);
   });
@@ -793,7 +799,7 @@ BTK_HD void chain_tile(Ctx& ctx, const ChainParams& p, unsigned char* smem, int 
       for (int round = 0; round < K::CG / K::NG; round++) {
         analysis_round<K>(ctx, L, s_xs, s_taps, s_xbuf, s_twa, s_twb, m, round);
         ctx.par([&](int tid, TS& ts) {
-          const int lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+          const int lane = tid & 31, grp = K::lane_grp(lane), gl = K::lane_gl(lane);
           const float4* w4 = s_wts + (round * K::NG + grp) * (G::V / 2) * G::L + gl;
           BTK_UNROLL
           for (int r2 = 0; r2 < G::V / 2; r2++) {

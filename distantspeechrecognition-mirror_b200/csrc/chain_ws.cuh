@@ -39,6 +39,10 @@
 
 #include "chain_tile.cuh"
 
+#ifndef BTK_WS_ILV
+#define BTK_WS_ILV 1      // A/B: 0 keeps the lane groups in runs of 16 lanes
+#endif
+
 namespace btk {
 
 template <int M_, int R_, int MT_ = 0, int PP_ = 1>
@@ -66,6 +70,14 @@ struct WsCfg {
   // lets two 4-channel stages of the 32-frame window fit next to the buffers of eight warps
   static constexpr int XS = (PP_ == 2 && G::Rb == 1 && G::Ra <= 16 && G::NG == 2) ? 1 : PP_;
   static constexpr int E = G::Ra / R_;
+  // Lane <-> (lane group, lane inside the group).  With two groups of 16 lanes the groups are INTERLEAVED in runs of eight
+  // lanes (lanes 0-7: group 0, 8-15: group 1, 16-23: group 0, 24-31: group 1), so that a half-warp -- the unit an 8-byte
+  // shared-memory access is served in -- holds eight lanes of EACH group: the two groups' exchange buffers are then kept 16
+  // banks apart (XPAD), and an access that takes two channels per lane out of the raw window uses whole 16-byte granules.
+  static constexpr bool ILV = BTK_WS_ILV != 0 && G::NG == 2 && G::L == 16;
+  static BTK_HD int lane_grp(int lane) { return ILV ? (lane >> 3) & 1 : lane / G::L; }
+  static BTK_HD int lane_gl(int lane) { return ILV ? (lane & 7) | ((lane >> 4) << 3) : lane % G::L; }
+  static constexpr int XPAD = ILV ? 8 : 0;
   static constexpr int FPT_RAW = (W * D) / NT;
   static constexpr int FPT = FPT_RAW >= 8 ? 8 : (FPT_RAW >= 4 ? 4 : (FPT_RAW >= 2 ? 2 : 1));
   static constexpr int NS = 2;                 // stages
@@ -141,7 +153,7 @@ BTK_HD constexpr WsSmem ws_smem_layout(int m) {
   s.wts_off = (win + 127) & ~127;
   s.stage_bytes = (s.wts_off + K::CG * M_ * 8 + 127) & ~127;
   s.stage0 = off; off += K::NS * s.stage_bytes;
-  s.xbuf = off;   off += K::NW * K::NG * K::XS * K::G::XBUF * 8;   off = (off + 15) & ~15;
+  s.xbuf = off;   off += K::NW * K::NG * (K::XS * K::G::XBUF + K::XPAD) * 8;   off = (off + 15) & ~15;
   s.vhist = off;  off += (s.L.H > 0 ? s.L.H : 1) * M_ * 4;          off = (off + 15) & ~15;
   s.valias = (K::W * M_ * 4 <= win) ? 1 : 0;
   s.vcur = off;
@@ -411,7 +423,7 @@ BTK_HD void chain_ws_synth_iter(Ctx& sctx, const ChainParams& p, unsigned char* 
     float* cur = ring + st.rs * CHF * FS;
     // ---- the chunk's frames out of tensor memory into the ring
     sctx.par([&](int tid, TS&) {
-      const int sw = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+      const int sw = tid >> 5, lane = tid & 31, grp = KS::lane_grp(lane), gl = KS::lane_gl(lane);
       BTK_UNROLL
       for (int k = 0; k < WPC; k++) {
         const int w = c * WPC + k;
@@ -560,7 +572,7 @@ BTK_HD void chain_ws_compute(Ctx& ctx, const ChainParams& p, unsigned char* smem
 #endif
         analysis_round<K>(ctx, L, s_xs, s_taps, s_xbuf, s_twa, s_twb, m, round);
         ctx.par([&](int tid, TS& ts) {
-          const int lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+          const int lane = tid & 31, grp = K::lane_grp(lane), gl = K::lane_gl(lane);
           const float4* w4 = s_wts + (round * K::NG + grp) * (G::V / 2) * G::L + gl;
           BTK_UNROLL
           for (int r2 = 0; r2 < G::V / 2; r2++) {
@@ -615,7 +627,7 @@ BTK_HD void chain_ws_compute(Ctx& ctx, const ChainParams& p, unsigned char* smem
       ctx.cl_expect(0, (unsigned)((csz - 1) * own * PW * 8));
       ctx.cl_expect(1, (unsigned)((K::NW * K::PP - own) * 2 * M_ * 4));
       ctx.par([&](int tid, TS& ts) {
-        const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+        const int warp = tid >> 5, lane = tid & 31, grp = K::lane_grp(lane), gl = K::lane_gl(lane);
         const bool has = K::NG == 1 ? grp == 0 : grp < K::PP;
         if (!has) return;
         BTK_UNROLL
@@ -634,7 +646,7 @@ BTK_HD void chain_ws_compute(Ctx& ctx, const ChainParams& p, unsigned char* smem
       });
       ctx.cl_wait(0);                                       // the partials of the pairs this rank owns have landed
       ctx.par([&](int tid, TS& ts) {
-        const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+        const int warp = tid >> 5, lane = tid & 31, grp = K::lane_grp(lane), gl = K::lane_gl(lane);
         const bool has = K::NG == 1 ? grp == 0 : grp < K::PP;
         if (!has) return;
         BTK_UNROLL

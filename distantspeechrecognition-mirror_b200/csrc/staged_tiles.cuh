@@ -63,14 +63,14 @@ BTK_HD void analysis_tile(Ctx& ctx, const AnalysisParams& p, unsigned char* smem
         ctx.syncwarp();
         // Z = X_f0 + j X_f1 in natural order through the exchange buffer, so every lane can reach Z[M-k]
         ctx.par([&](int tid, TS& ts) {
-          const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+          const int warp = tid >> 5, lane = tid & 31, grp = K::lane_grp(lane), gl = K::lane_gl(lane);
           cf* xb = s_xbuf + (warp * K::NG + grp) * G::XBUF;
           BTK_UNROLL
           for (int r = 0; r < G::V; r++) xb[G::index_of_spec(gl, r)] = ts.z[r];
         });
         ctx.syncwarp();
         ctx.par([&](int tid, TS& ts) {
-          const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+          const int warp = tid >> 5, lane = tid & 31, grp = K::lane_grp(lane), gl = K::lane_gl(lane);
           const cf* xb = s_xbuf + (warp * K::NG + grp) * G::XBUF;
           const int c = cg0 + round * K::NG + grp;
           const int f0 = f_base + 2 * warp, f1 = f0 + 1;
@@ -137,7 +137,7 @@ BTK_HD void synthesis_tile(Ctx& ctx, const SynthesisParams& p, unsigned char* sm
     const int tau_base = a_start + it * K::W;
     // G = Y_tau0 + j Y_tau1 over all M bins, Hermitian-extended, real at k = 0 and M/2
     ctx.par([&](int tid, TS& ts) {
-      const int warp = tid >> 5, lane = tid & 31, grp = lane / G::L, gl = lane % G::L;
+      const int warp = tid >> 5, lane = tid & 31, grp = K::lane_grp(lane), gl = K::lane_gl(lane);
       if (grp != 0) return;
       const int tau0 = tau_base + 2 * warp, tau1 = tau0 + 1;
       const bool ok0 = tau0 >= 0 && tau0 < F, ok1 = tau1 >= 0 && tau1 < F;
