@@ -879,7 +879,8 @@ static int chain_launch(btkb200_plan* p, const float* d_pcm, float* d_out, int w
   c.tma_rows = p->tma_rows;
   c.item_begin = nullptr; c.item_q = 0; c.item0 = 0; c.n_items = 0; c.n_rec = p->sig.empty() ? 0 : (int)p->sig[0];
   static const int syn_env = getenv("BTK_WS_SYN") ? atoi(getenv("BTK_WS_SYN")) : 1;   // A/B runs
-  c.no_syn = syn_env ? 0 : 1;
+  static const int dual_env = getenv("BTK_WS_DUAL") ? atoi(getenv("BTK_WS_DUAL")) : 1;   // A/B: two-channel windowing (bit 1)
+  c.no_syn = (syn_env ? 0 : 1) | (dual_env ? 0 : 2);
   int n_cta = w1 - w0;
   if (p->use_ws && p->persist) {
     c.work = nullptr;

@@ -81,7 +81,8 @@ struct ChainParams {
   int item_q;            // output frames per item (W)
   int item0, n_items;
   int n_rec;             // recordings of the batch (item_begin has n_rec + 1 entries)
-  int no_syn;            // warp-specialised chain, A/B knob (BTK_WS_SYN=0): the transform warps keep the synthesis side
+  int no_syn;            // warp-specialised chain, A/B knobs: bit 0 (BTK_WS_SYN=0) the transform warps keep the synthesis side,
+                         // bit 1 (BTK_WS_DUAL=0) one channel per windowing pass instead of two
 };
 
 template <int M_, int R_, int MT_ = 0, int PP_ = 1>
@@ -298,6 +299,95 @@ BTK_HD void polyphase_pairs(cf* z, int gl, const float* xch, int warp, const flo
       for (int pp = 0; pp < PP; pp++) {
         BTK_UNROLL
         for (int a = 0; a < R_; a++) z[pp * G::V + rep * G::Ra + e0 + K::E * a] = u[pp][a];
+      }
+    }
+  }
+}
+
+// The same windowing for TWO channels at once out of the raw window (chain_ws.cuh, [time step][CG]): the samples of
+// channels (A, B) = (2 grp, 2 grp + 1) of the stage are neighbours, so ONE 8-byte load brings both -- a warp-wide load then
+// uses every byte of the 16-byte granules it touches (two lane groups x two channels) where the one-channel loads of
+// polyphase_pairs use half of them and pay a 2-way bank conflict for it; the taps are loaded once for both channels.
+// Channel A's windowed frames go to z like in polyphase_pairs; channel B's are handed, residue by residue, to
+// park(step, vals) -- 2 PP R floats: (pp, a) -> vals[(pp R + a) 2 + {0, 1}] = (u_{i0}, u_{i1})[rho + D a] -- and come back
+// as a whole through polyphase_unpark's `fetch` when their round starts.  Compile-time prototype length only.
+template <class K, class Park>
+BTK_HD void polyphase_pairs2(cf* z, int gl, const float* xch2, int warp, const float* taps, const ChainSmem& L, Park park) {
+  typedef typename K::G G;
+  constexpr int R_ = K::R, PP = K::PP;
+  constexpr int mR = (K::MT > 0 ? K::MT : 1) * R_;
+  constexpr int NX = mR + 1 + 2 * (PP - 1);
+  static_assert(K::MT > 0 && K::CG % 2 == 0, "compile-time prototype length, channel pairs");
+  BTK_UNROLL
+  for (int rep = 0; rep < G::RepA; rep++) {
+    BTK_UNROLL
+    for (int e0 = 0; e0 < K::E; e0++) {
+      const int rho = gl + G::L * rep + G::JA * e0;
+      const int res = K::D - 1 - rho;
+      const float* hp = taps + rho * L.TS;
+      float xa[NX], xb[NX], h[mR];
+      BTK_UNROLL
+      for (int i = 0; i < NX; i++) {
+        const float2 v = *reinterpret_cast<const float2*>(xch2 + ((K::FW * warp + i) * K::D + res) * K::CG);
+        xa[i] = v.x; xb[i] = v.y;
+      }
+      load_floats<mR, tap_vec(mR)>(h, hp);
+      cf ua[PP][R_], ub[PP][R_];
+      BTK_UNROLL
+      for (int pp = 0; pp < PP; pp++) {
+        BTK_UNROLL
+        for (int a = 0; a < R_; a++) { ua[pp][a] = mk(0.f, 0.f); ub[pp][a] = mk(0.f, 0.f); }
+      }
+      BTK_UNROLL
+      for (int t = 0; t < mR; t++) {
+        BTK_UNROLL
+        for (int pp = 0; pp < PP; pp++) {
+          const int i0 = 2 * pp + mR - t - 1;
+          if ((i0 & 1) == 0) {
+            ua[pp][t % R_] = cfma_real(mk(xa[i0], xa[i0 + 1]), h[t], ua[pp][t % R_]);
+            ub[pp][t % R_] = cfma_real(mk(xb[i0], xb[i0 + 1]), h[t], ub[pp][t % R_]);
+          } else {
+            ua[pp][t % R_].y = fmaf(h[t], xa[i0 + 1], ua[pp][t % R_].y);
+            ua[pp][t % R_].x = fmaf(h[t], xa[i0], ua[pp][t % R_].x);
+            ub[pp][t % R_].y = fmaf(h[t], xb[i0 + 1], ub[pp][t % R_].y);
+            ub[pp][t % R_].x = fmaf(h[t], xb[i0], ub[pp][t % R_].x);
+          }
+        }
+      }
+      float pk[2 * PP * R_];
+      BTK_UNROLL
+      for (int pp = 0; pp < PP; pp++) {
+        BTK_UNROLL
+        for (int a = 0; a < R_; a++) {
+          z[pp * G::V + rep * G::Ra + e0 + K::E * a] = ua[pp][a];
+          pk[(pp * R_ + a) * 2] = ub[pp][a].x;
+          pk[(pp * R_ + a) * 2 + 1] = ub[pp][a].y;
+        }
+      }
+      park(rep * K::E + e0, pk);
+    }
+  }
+}
+
+// Channel B's windowed frames back into z: fetch(col0, vals) delivers PC consecutive parked floats (step-major, see above).
+template <class K, class Fetch>
+BTK_HD void polyphase_unpark(cf* z, Fetch fetch) {
+  typedef typename K::G G;
+  constexpr int R_ = K::R, PP = K::PP, NPK = 2 * PP * R_, NSTEP = G::RepA * K::E, TOT = NPK * NSTEP;
+  constexpr int PC = TOT < 32 ? TOT : 32;                       // floats per fetch
+  static_assert(PC % NPK == 0 && TOT % PC == 0, "whole steps per fetch");
+  BTK_UNROLL
+  for (int c0 = 0; c0 < TOT; c0 += PC) {
+    float vals[PC];
+    fetch(c0, vals);
+    BTK_UNROLL
+    for (int s = 0; s < PC / NPK; s++) {
+      const int step = c0 / NPK + s, rep = step / K::E, e0 = step % K::E;
+      BTK_UNROLL
+      for (int pp = 0; pp < PP; pp++) {
+        BTK_UNROLL
+        for (int a = 0; a < R_; a++)
+          z[pp * G::V + rep * G::Ra + e0 + K::E * a] = mk(vals[s * NPK + (pp * R_ + a) * 2], vals[s * NPK + (pp * R_ + a) * 2 + 1]);
       }
     }
   }
@@ -534,9 +624,10 @@ BTK_HD void synth_roll_history(Ctx& ctx, const ChainSmem& L, float* s_vhist, con
 // One analysis round of a warp: polyphase of the staged channel + backward transforms, leaving
 // Z = X_{tau0} + j X_{tau0+1} of channel (round*NG + grp), for each of the warp's PP frame pairs, in ts.z[pp][V]
 // (canonical layout).
-template <class K, class Ctx>
-BTK_HD void analysis_round(Ctx& ctx, const ChainSmem& L, const float* s_xs, const float* s_taps, cf* s_xbuf,
-                           const cf* s_twa, const cf* s_twb, int m, int round) {
+// (fill(z, tid, grp, gl) puts the windowed frame pairs of the lane's channel into z: polyphase_pairs by default, see
+// analysis_round below; the two-channel variant of chain_ws.cuh windows or fetches them itself)
+template <class K, class Ctx, class Fill>
+BTK_HD void analysis_round_fill(Ctx& ctx, cf* s_xbuf, const cf* s_twa, const cf* s_twb, Fill fill) {
   typedef typename K::G G;
   constexpr int M_ = K::M;
   typedef ChainThreadState<M_, K::PP> TS;
@@ -546,8 +637,7 @@ BTK_HD void analysis_round(Ctx& ctx, const ChainSmem& L, const float* s_xs, cons
     // scatter / gather pair by pair, then the final radix passes
     ctx.par([&](int tid, TS& ts) {
       const int warp = tid >> 5, lane = tid & 31, grp = K::lane_grp(lane), gl = K::lane_gl(lane);
-      const int c_local = round * K::NG + grp;
-      polyphase_pairs<K>(ts.z, gl, K::RAW ? s_xs + c_local : s_xs + c_local * L.CS, warp, s_taps, L, m);
+      fill(ts.z, tid, grp, gl);
       GroupFFT<M_, +1>::template step1_twiddle<K::PP>(ts.z, gl, s_twa);
       GroupFFT<M_, +1>::step1_scatter(ts.z, gl, slot(warp, grp));
     });
@@ -574,8 +664,7 @@ BTK_HD void analysis_round(Ctx& ctx, const ChainSmem& L, const float* s_xs, cons
   }
   ctx.par([&](int tid, TS& ts) {
     const int warp = tid >> 5, lane = tid & 31, grp = K::lane_grp(lane), gl = K::lane_gl(lane);
-    const int c_local = round * K::NG + grp;
-    polyphase_pairs<K>(ts.z, gl, K::RAW ? s_xs + c_local : s_xs + c_local * L.CS, warp, s_taps, L, m);
+    fill(ts.z, tid, grp, gl);
     GroupFFT<M_, +1>::template step1_multi<K::PP>(ts.z, gl, slot(warp, grp), s_twa);
   });
   ctx.syncwarp();
@@ -597,6 +686,15 @@ BTK_HD void analysis_round(Ctx& ctx, const ChainSmem& L, const float* s_xs, cons
     const int warp = tid >> 5, lane = tid & 31, grp = K::lane_grp(lane), gl = K::lane_gl(lane);
     BTK_UNROLL
     for (int pp = 0; pp < K::PP; pp++) GroupFFT<M_, +1>::step3(ts.z + pp * G::V, gl, slot(warp, grp) + pp * G::XBUF);
+  });
+}
+
+template <class K, class Ctx>
+BTK_HD void analysis_round(Ctx& ctx, const ChainSmem& L, const float* s_xs, const float* s_taps, cf* s_xbuf,
+                           const cf* s_twa, const cf* s_twb, int m, int round) {
+  analysis_round_fill<K>(ctx, s_xbuf, s_twa, s_twb, [&](cf* z, int tid, int grp, int gl) {
+    const int c_local = round * K::NG + grp;
+    polyphase_pairs<K>(z, gl, K::RAW ? s_xs + c_local : s_xs + c_local * L.CS, tid >> 5, s_taps, L, m);
   });
 }
 

@@ -42,6 +42,9 @@
 #ifndef BTK_WS_ILV
 #define BTK_WS_ILV 1      // A/B: 0 keeps the lane groups in runs of 16 lanes
 #endif
+#ifndef BTK_WS_DUAL
+#define BTK_WS_DUAL 1     // A/B: 0 windows one channel per pass also where the overlap-add warps (tensor memory) are there
+#endif
 
 namespace btk {
 
@@ -91,7 +94,14 @@ struct WsCfg {
   static constexpr int NST = NSY * 32;
   static constexpr int NVAL = 2 * G::V;                                  // floats a lane parks per iteration
   static constexpr int CHF = 4;                                          // frames per chunk of the overlap-add warps
-  static constexpr int TM_COLS = 4 * NVAL < 32 ? 32 : 4 * NVAL;          // 2 slots x 2 warps per lane quarter x NVAL
+  // Tensor memory also holds, for the time between the two rounds of a stage, the windowed frames of the SECOND channel
+  // of each lane's channel pair (chain_tile.cuh::polyphase_pairs2): ZBW = 2 PP V floats per lane and transform warp
+  static constexpr int ZBW = 2 * PP_ * G::V;
+  static constexpr int NPK = 2 * PP_ * R_;                               // floats parked per residue step
+  static constexpr int ZB0 = 4 * NVAL;                                   // first column of that area (2 warps per lane quarter)
+  static constexpr int TM_NEED = 4 * NVAL + 2 * ZBW;                     // v frames: 2 slots x 2 warps per lane quarter x NVAL
+  static constexpr int TM_COLS = TM_NEED <= 32 ? 32 : (TM_NEED <= 64 ? 64 : (TM_NEED <= 128 ? 128 : (TM_NEED <= 256 ? 256 : 512)));
+  static constexpr bool DUAL_OK = NG == 2 && CG == 4 && RAW && MT_ > 0 && TM_NEED <= 512 && (NPK == 8 || NPK == 16 || NPK == 32);
   static_assert(G::Ra % R_ == 0, "decimation factor must divide the first radix");
   static_assert(CG % NG == 0, "channel group must be a multiple of the lane groups per warp");
   static_assert(W % FPT == 0, "frames per thread must divide the iteration");
@@ -507,7 +517,9 @@ BTK_HD void chain_ws_synth_iter(Ctx& sctx, const ChainParams& p, unsigned char* 
 //     cl_send16(ptr, rank, v, k)      store 16 bytes at the same shared-memory address in CTA `rank`, counted on ITS barrier k
 //     cl_wait(k)                      everything expected on receive barrier k has landed
 // ---------------------------------------------------------------------------------------------
-template <int M_, int R_, int MT_, int PP_, class Ctx>
+// SYNM: the synthesis side is with the overlap-add warps (1), with the transform warps (0) -- the device kernels are built
+// once for each, so that neither carries the other's code -- or decided at run time (-1, host emulation).
+template <int M_, int R_, int MT_, int PP_, class Ctx, int SYNM = -1>
 BTK_HD void chain_ws_compute(Ctx& ctx, const ChainParams& p, unsigned char* smem, const WorkItem wk, const RecDesc rec, int& g) {
   typedef WsCfg<M_, R_, MT_, PP_> K;
   typedef typename K::G G;
@@ -526,13 +538,13 @@ BTK_HD void chain_ws_compute(Ctx& ctx, const ChainParams& p, unsigned char* smem
   const float* pcm = p.pcm + rec.pcm_off;
   float* out = p.out + rec.out_off;
   const int C = p.C;
-  const int csz = p.cluster > 1 ? p.cluster : 1;
+  const int csz = SYNM == 1 ? 1 : (p.cluster > 1 ? p.cluster : 1);
   const int rank = csz > 1 ? ctx.cl_rank() : 0;
   const WsWalk walk = ws_walk<K>(p, wk, H, csz, rank);
   const bool vec4 = (C % 4 == 0) && (rec.pcm_off % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.pcm) & 15) == 0);
   const cf* wts = p.wts + (long long)wk.rec * p.wts_stride;
   // overlap-add warps take the v frames of every iteration out of tensor memory: no synthesis side here (ws_syn_mode)
-  const bool syn = ws_syn_mode<K>(S, ctx.syn_ok(p), csz);
+  const bool syn = SYNM >= 0 ? SYNM == 1 : ws_syn_mode<K>(S, ctx.syn_ok(p), csz);
 
   if (!syn) {
     ctx.par([&](int tid, TS&) {
@@ -570,10 +582,28 @@ BTK_HD void chain_ws_compute(Ctx& ctx, const ChainParams& p, unsigned char* smem
 #else
       for (int round = 0; round < K::CG / K::NG; round++) {
 #endif
-        analysis_round<K>(ctx, L, s_xs, s_taps, s_xbuf, s_twa, s_twb, m, round);
+        // two-channel mode (with the overlap-add warps, i.e. with tensor memory): lane group grp windows channels 2 grp and
+        // 2 grp + 1 of the stage together in round 0 -- one 8-byte load per sample pair -- transforms the first and parks
+        // the second in tensor memory until round 1; otherwise channel round * NG + grp is windowed in its own round
+        const bool dual = K::DUAL_OK && syn && (SYNM == 1 ? BTK_WS_DUAL != 0 : !(p.no_syn & 2));
+        if (!dual) {
+          analysis_round<K>(ctx, L, s_xs, s_taps, s_xbuf, s_twa, s_twb, m, round);
+        } else if constexpr (K::DUAL_OK) {
+          analysis_round_fill<K>(ctx, s_xbuf, s_twa, s_twb, [&](cf* z, int tid, int grp, int gl) {
+            const int warp = tid >> 5;
+            if (round == 0) {
+              polyphase_pairs2<K>(z, gl, s_xs + 2 * grp, warp, s_taps, L,
+                                  [&](int step, const float* pk) { ctx.template zb_park_n<K::NPK>(tid, step, pk); });
+              ctx.zb_parked();
+            } else {
+              constexpr int PC = K::ZBW < 32 ? K::ZBW : 32;
+              polyphase_unpark<K>(z, [&](int col0, float* vals) { ctx.template zb_fetch_n<PC>(tid, col0, vals); });
+            }
+          });
+        }
         ctx.par([&](int tid, TS& ts) {
           const int lane = tid & 31, grp = K::lane_grp(lane), gl = K::lane_gl(lane);
-          const float4* w4 = s_wts + (round * K::NG + grp) * (G::V / 2) * G::L + gl;
+          const float4* w4 = s_wts + (dual ? 2 * grp + round : round * K::NG + grp) * (G::V / 2) * G::L + gl;
           BTK_UNROLL
           for (int r2 = 0; r2 < G::V / 2; r2++) {
             const float4 w = w4[r2 * G::L];

@@ -92,6 +92,19 @@ __device__ __forceinline__ void tma_box_g2s(void* dst, const void* tmap, int c0,
 // tensor memory as a parking area (32x32b shape: lane t of the warp <-> lane 32 (warp mod 4) + t, N consecutive columns)
 template <int N> struct TmemIO;
 #define BTK_TM_R8(a, o) "%" #a ", %" #a "+1"
+template <> struct TmemIO<8> {
+  static __device__ __forceinline__ void st(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                 "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+  }
+  static __device__ __forceinline__ void ld(uint32_t taddr, float* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+  }
+};
 template <> struct TmemIO<16> {
   static __device__ __forceinline__ void st(uint32_t taddr, const float* v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
@@ -161,6 +174,19 @@ template <int M, int PP, int NT> struct DevCtxWS {
   __device__ __forceinline__ void tmem_store(int slot, int tid, const float* vals) {
     const int warp = tid >> 5;
     TmemIO<NVAL>::st(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((slot * 2 + (warp >> 2)) * NVAL), vals);
+  }
+  // second channel of the lane's pair, parked per residue step between the rounds of a stage (polyphase_pairs2): columns
+  // zb0 + (warp / 4) * zbw + step * npk of the warp's lane quarter
+  int zb0, zbw;
+  template <int NPKV> __device__ __forceinline__ void zb_park_n(int tid, int step, const float* pk) {
+    const int warp = tid >> 5;
+    TmemIO<NPKV>::st(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(zb0 + (warp >> 2) * zbw + step * NPKV), pk);
+  }
+  __device__ __forceinline__ void zb_parked() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+  template <int PC> __device__ __forceinline__ void zb_fetch_n(int tid, int col0, float* vals) {
+    const int warp = tid >> 5;
+    TmemIO<PC>::ld(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(zb0 + (warp >> 2) * zbw + col0), vals);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
   }
   template <class F> __device__ __forceinline__ void v_publish(int slot, F) {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -255,7 +281,7 @@ template <int M, int NT, int LV> struct WsProd {
   static constexpr int TB = LOADS / LV;
 };
 
-template <int M, int R, int MT, int PP>
+template <int M, int R, int MT, int PP, bool SYNT>
 __global__ void __launch_bounds__(WsCfg<M, R, MT, PP>::NT + 256, 1) btk_chain_ws_kernel(const ChainParams p) {
   typedef WsCfg<M, R, MT, PP> K;
   typedef WsRegs<M, K::NT> RG;
@@ -263,16 +289,19 @@ __global__ void __launch_bounds__(WsCfg<M, R, MT, PP>::NT + 256, 1) btk_chain_ws
   const int m = MT > 0 ? MT : p.m;
   const WsSmem S = ws_smem_layout<M, R, PP>(m);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S.bars);
-  const int csz = p.cluster > 1 ? p.cluster : 1;
+  // SYNT: overlap-add warps + tensor memory hand-over (chain_ws.cuh::ws_syn_mode, decided by the launcher): tensor-copy
+  // producer, no cluster.  The other build carries the register-load producer, the cluster exchange and the synthesis
+  // side on the transform warps.
+  const int csz = SYNT ? 1 : (p.cluster > 1 ? p.cluster : 1);
   const int crank = csz > 1 ? (int)cg::this_cluster().block_rank() : 0;
   const int cta = (int)blockIdx.x / csz, ncta = (int)gridDim.x / csz;      // this CTA's (cluster's) share of the launch
-  // overlap-add warps + tensor memory hand-over (chain_ws.cuh::ws_syn_mode); uniform over the CTA
-  const bool syn = ws_syn_mode<K>(S, p.tmaps != nullptr && !p.no_syn, csz);
+  constexpr bool syn = SYNT;
+  const bool tma = SYNT || p.tmaps != nullptr;
   __shared__ uint32_t s_tmem;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < K::NS; s++) {
-      mbar_init(bars + WS_BAR_FULL + s, p.tmaps ? 1 : K::NPT);
+      mbar_init(bars + WS_BAR_FULL + s, tma ? 1 : K::NPT);
       mbar_init(bars + WS_BAR_EMPTY + s, K::NW);
     }
     mbar_init(bars + WS_BAR_TABLES, 1);
@@ -323,7 +352,7 @@ __global__ void __launch_bounds__(WsCfg<M, R, MT, PP>::NT + 256, 1) btk_chain_ws
     }
   } else if (threadIdx.x >= K::NT + K::NST) {
     // ------------------------------------------------------------------ producer warpgroup
-    if (p.tmaps) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RG::RMIN));
+    if (tma) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RG::RMIN));
     else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RG::RP));
     const int ptid = (int)threadIdx.x - K::NT - K::NST;
     const ChainSmem& L = S.L;
@@ -339,7 +368,7 @@ __global__ void __launch_bounds__(WsCfg<M, R, MT, PP>::NT + 256, 1) btk_chain_ws
     WsSegs segs(p, cta, ncta);
     WorkItem wk;
     int g = 0;                                   // stages filled so far by this CTA, across its segments
-    if (p.tmaps) {
+    if (tma) {
       // ---- tensor-copy producer: ONE thread.  Per stage it waits for the stage, announces the bytes and issues the
       // boxes of the window (NB D / rows of them) plus the weight rows; the copies run in the async proxy, no register
       // and no load/store-unit slot of this SM is involved, and the transform warps see the window in the layout of the
@@ -365,7 +394,7 @@ __global__ void __launch_bounds__(WsCfg<M, R, MT, PP>::NT + 256, 1) btk_chain_ws
           }
         }
       }
-    } else while (segs.next(wk)) {
+    } else if constexpr (!SYNT) while (segs.next(wk)) {
     constexpr int TB = WsProd<M, K::NT, K::LV>::TB;
     const RecDesc rec = p.recs[wk.rec];
     const WsWalk walk = ws_walk<K>(p, wk, L.H, csz, crank);
@@ -431,11 +460,11 @@ __global__ void __launch_bounds__(WsCfg<M, R, MT, PP>::NT + 256, 1) btk_chain_ws
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(RG::RC));
     DevCtxWS<M, PP, K::NT> ctx;
     ctx.bars = bars; ctx.csz = csz; ctx.crank = crank; ctx.cl_phase = 0;
-    ctx.tmem = syn ? s_tmem : 0u; ctx.itc = 0; ctx.syn = syn;
+    ctx.tmem = syn ? s_tmem : 0u; ctx.itc = 0; ctx.syn = syn; ctx.zb0 = K::ZB0; ctx.zbw = K::ZBW;
     WsSegs segs(p, cta, ncta);
     WorkItem wk;
     int g = 0;                                   // stages consumed so far by this CTA, across its segments
-    while (segs.next(wk)) chain_ws_compute<M, R, MT, PP>(ctx, p, smem, wk, p.recs[wk.rec], g);
+    while (segs.next(wk)) chain_ws_compute<M, R, MT, PP, DevCtxWS<M, PP, K::NT>, SYNT ? 1 : 0>(ctx, p, smem, wk, p.recs[wk.rec], g);
     if (syn) {
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       asm volatile("bar.sync 3, %0;" ::"n"(K::NT + K::NST) : "memory");
@@ -455,9 +484,15 @@ template <int M, int R> static int chain_ws_pp(int m) {
 template <int M, int R, int MT, int PP>
 static cudaError_t launch_ws_one(const ChainParams& p, int n_work, cudaStream_t st) {
   typedef WsCfg<M, R, MT, PP> K;
-  auto kern = btk_chain_ws_kernel<M, R, MT, PP>;
-  const int smem = ws_smem_layout<M, R, PP>(p.m).total;
+  const WsSmem S = ws_smem_layout<M, R, PP>(p.m);
+  const int smem = S.total;
   const int csz = p.cluster > 1 ? p.cluster : 1;
+  // two builds of the kernel: with the overlap-add warpgroup (tensor-copy producer, no cluster) and without
+  const bool syn = ws_syn_mode<K>(S, p.tmaps != nullptr && !(p.no_syn & 1), csz);
+  auto kern = btk_chain_ws_kernel<M, R, MT, PP, false>;
+  if constexpr (K::NG == 2 && MT > 0) {
+    if (syn) kern = btk_chain_ws_kernel<M, R, MT, PP, true>;
+  }
   if (csz > 1 && !ws_cluster_ok<K>(csz)) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;

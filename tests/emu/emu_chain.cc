@@ -189,6 +189,12 @@ template <int M, int PP> struct HostCtxWS {
     for (int i = 0; i < N; i++) vals[i] = d[i];
   }
   void v_release(int) {}
+  // second channel of a lane's pair, parked between the rounds of a stage: [thread][column]
+  std::vector<float>* zb = nullptr;
+  int zbw = 0;
+  template <int NPKV> void zb_park_n(int tid, int step, const float* pk) { for (int i = 0; i < NPKV; i++) (*zb)[(size_t)tid * zbw + step * NPKV + i] = pk[i]; }
+  void zb_parked() {}
+  template <int PC> void zb_fetch_n(int tid, int col0, float* vals) { for (int i = 0; i < PC; i++) vals[i] = (*zb)[(size_t)tid * zbw + col0 + i]; }
   template <class F> void par(F f) { for (int t = 0; t < nt; t++) f(t, ts[t]); }
   void sync() {}
   void syncwarp() {}
@@ -239,7 +245,8 @@ static int run_chain_ws(int m, int dct, int C, int n_rec, const long long* Ts, c
     std::vector<float> tm((size_t)2 * 8 * 32 * HostCtxWS<M, PP>::NVAL, 1e30f);
     WsSynState sst;
     sst.rs = 0;
-    ctx.syn = syn != 0; ctx.nst = K::NST; ctx.tm = &tm; ctx.sst = &sst;
+    std::vector<float> zb((size_t)K::NT * K::ZBW, 1e30f);
+    ctx.syn = syn != 0; ctx.nst = K::NST; ctx.tm = &tm; ctx.sst = &sst; ctx.zb = &zb; ctx.zbw = K::ZBW;
     memset(smem.data(), 0xA5, smem.size());   // poison: every read must have been written
     // what the bulk copies of the producer bring at CTA start
     memcpy(smem.data() + S.L.taps, hf.data(), (size_t)K::D * S.L.TS * 4);
