@@ -76,7 +76,7 @@ struct btkb200_plan {
   std::vector<long long> sig;  // signature of the cached chain work list
   int cached_n_work = 0;
   bool persist = false;        // warp-specialised chain: d_work holds the item prefix (WsSegs), the grid is one CTA per SM
-  int item_q = 0, n_sm = 148;
+  int item_q = 0, n_sm = 148, cta_n = 0;
   int no_prefetch = 0;         // fused chain: no L2 prefetch of the next window (chain_prepare, same footprint estimate)
   int one_cta = 0;             // fused chain: keep one CTA per SM (chain_prepare decides from the L2 footprint)
   int use_ws = 0;              // fused chain: the warp-specialised producer / consumer kernel (chain_ws.cuh) runs this shape
@@ -747,8 +747,19 @@ static int chain_prepare(btkb200_plan* p, const long long* pcm_off, const long l
       // chunks in several waves against 0.479 ms with one persistent cluster per SM pair)
       if (persist_env && p->cluster == 1 && !getenv("BTK_CHUNK_WAVES")) {
         CK(p, cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, p->device));
+        // items of W / 8 frames; for the launch of the whole batch the CTAs' first items are balanced by ITERATIONS
+        // (host_tables.h::balance_ctas), launches of a recording range split their items evenly
+        const int q = Wws >= 8 ? Wws / 8 : 1;
         std::vector<int> prefix(n + 1, 0);
-        for (int i = 0; i < n; i++) prefix[i + 1] = prefix[i] + (recs[i].nblk + Wws - 1) / Wws;
+        for (int i = 0; i < n; i++) prefix[i + 1] = prefix[i] + (recs[i].nblk + q - 1) / q;
+        static const int bal_env = getenv("BTK_WS_BALANCE") ? atoi(getenv("BTK_WS_BALANCE")) : 1;   // A/B runs
+        p->cta_n = 0;
+        if (bal_env && prefix[n] > 0) {
+          std::vector<int> begin;
+          balance_ctas(recs, prefix, q, Wws, H, p->n_sm, begin);
+          p->cta_n = p->n_sm;
+          prefix.insert(prefix.end(), begin.begin(), begin.end());     // uploaded behind the prefix sums
+        }
         const size_t br = recs.size() * sizeof(RecDesc), bw = prefix.size() * sizeof(int);
         CK(p, p->d_recs.reserve(br));
         CK(p, p->d_work.reserve(bw));
@@ -758,11 +769,11 @@ static int chain_prepare(btkb200_plan* p, const long long* pcm_off, const long l
         CK(p, cudaMemcpyAsync(p->d_recs.p, p->h_desc.p, br, cudaMemcpyHostToDevice, st));
         CK(p, cudaMemcpyAsync(p->d_work.p, (char*)p->h_desc.p + br, bw, cudaMemcpyHostToDevice, st));
         CK(p, cudaStreamSynchronize(st));
-        p->rec_work_begin = prefix;               // callers launch recording ranges [r0, r1) as item ranges
+        p->rec_work_begin.assign(prefix.begin(), prefix.begin() + n + 1);   // callers launch recording ranges [r0, r1) as item ranges
         p->persist = true;
-        p->item_q = Wws;
+        p->item_q = q;
         p->sig = sig;
-        p->cached_n_work = prefix[n];
+        p->cached_n_work = p->rec_work_begin[n];
         return BTKB200_OK;
       }
       int slots = 148 / p->cluster;
@@ -878,6 +889,7 @@ static int chain_launch(btkb200_plan* p, const float* d_pcm, float* d_out, int w
   c.tmaps = p->use_ws ? chain_tensor_maps(p, d_pcm, st) : nullptr;
   c.tma_rows = p->tma_rows;
   c.item_begin = nullptr; c.item_q = 0; c.item0 = 0; c.n_items = 0; c.n_rec = p->sig.empty() ? 0 : (int)p->sig[0];
+  c.cta_begin = nullptr; c.cta_n = 0;
   static const int syn_env = getenv("BTK_WS_SYN") ? atoi(getenv("BTK_WS_SYN")) : 1;   // A/B runs
   static const int dual_env = getenv("BTK_WS_DUAL") ? atoi(getenv("BTK_WS_DUAL")) : 1;   // A/B: two-channel windowing (bit 1)
   c.no_syn = (syn_env ? 0 : 1) | (dual_env ? 0 : 2);
@@ -886,6 +898,11 @@ static int chain_launch(btkb200_plan* p, const float* d_pcm, float* d_out, int w
     c.work = nullptr;
     c.item_begin = (const int*)p->d_work.p; c.item_q = p->item_q; c.item0 = w0; c.n_items = w1 - w0;
     n_cta = c.n_items;           // the launcher clamps the grid to the CTAs (clusters) resident at once
+    if (p->cta_n > 0 && w0 == 0 && w1 == p->cached_n_work) {     // the whole batch: iteration-balanced CTA boundaries
+      c.cta_begin = c.item_begin + (c.n_rec + 1);
+      c.cta_n = p->cta_n;
+      n_cta = p->cta_n;
+    }
   }
   if (p->use_ws) CK(p, launch_chain_ws(p->geo.M, p->geo.R, c, n_cta, st));
   else CK(p, launch_chain(p->geo.M, p->geo.R, c, w1 - w0, st));

@@ -81,6 +81,10 @@ struct ChainParams {
   int item_q;            // output frames per item (W)
   int item0, n_items;
   int n_rec;             // recordings of the batch (item_begin has n_rec + 1 entries)
+  // optional: first item of every CTA of the launch (cta_n + 1 entries, chosen on the host so that every CTA runs the
+  // same number of ITERATIONS, host_tables.h::balance_ctas); NULL = equal item counts
+  const int* cta_begin;
+  int cta_n;
   int no_syn;            // warp-specialised chain, A/B knobs: bit 0 (BTK_WS_SYN=0) the transform warps keep the synthesis side,
                          // bit 1 (BTK_WS_DUAL=0) one channel per windowing pass instead of two
 };

@@ -198,6 +198,10 @@ BTK_HD constexpr bool ws_cluster_ok(int S) {
 // [n cta / ncta, n (cta + 1) / ncta) and walks it as SEGMENTS: the items of one recording that follow each other are one
 // WorkItem, so the synthesis history is warmed up once per segment and not once per item, every CTA runs the same number
 // of iterations to within two, the tables are loaded once per SM and the producer runs ahead across segment boundaries.
+// An item is a few frames (W / 8), not an iteration: a segment of nj frames costs ceil((nj + H) / W) iterations (H = m R - 1
+// warm-up frames), so equal ITEM counts leave the CTAs one or two iterations apart -- 27 against 25.3 at cfg2.  For a
+// launch of the whole batch the host therefore hands over the first item of every CTA (p.cta_begin,
+// host_tables.h::balance_ctas: the smallest iteration budget under which a greedy walk needs no more CTAs than there are).
 // With p.item_begin == NULL the CTA has exactly one segment, p.work[cta] (the chunk list of the first sessions).
 struct WsSegs {
   const ChainParams& p;
@@ -206,8 +210,13 @@ struct WsSegs {
   BTK_HD WsSegs(const ChainParams& p_, int cta_, int ncta) : p(p_), cta(cta_), i(0), i1(0), r(0), one_shot(false) {
     if (!p.item_begin) { one_shot = true; return; }
     const long long n = p.n_items;
-    i = p.item0 + (int)(n * cta / ncta);
-    i1 = p.item0 + (int)(n * (cta + 1) / ncta);
+    if (p.cta_begin) {
+      i = p.cta_begin[cta];
+      i1 = p.cta_begin[cta + 1];
+    } else {
+      i = p.item0 + (int)(n * cta / ncta);
+      i1 = p.item0 + (int)(n * (cta + 1) / ncta);
+    }
     if (i >= i1) return;
     // last recording whose first item is <= i: item_begin is non-decreasing, item_begin[0] = 0
     int lo = 0, hi = p.n_rec;                                    // item_begin[n_rec] (the total) > i

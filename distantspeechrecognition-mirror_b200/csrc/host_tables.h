@@ -318,6 +318,55 @@ inline void diffuse_model(const double* micpos, int C, double fs, double sspeed,
   }
 }
 
+// Persistent schedule of the warp-specialised chain (chain_ws.cuh::WsSegs): first item of each of `ncta` CTAs such that no
+// CTA runs more than B iterations, B minimal.  Recording r has prefix[r+1] - prefix[r] items of q frames (the last one
+// may be shorter); a segment of nj frames costs ceil((nj + H) / W) iterations; a CTA walks on into the next recording
+// while its budget lasts.  Returns B; `begin` gets ncta + 1 item indices (trailing CTAs may be empty).
+inline int balance_ctas(const std::vector<RecDesc>& recs, const std::vector<int>& prefix, int q, int W, int H, int ncta,
+                        std::vector<int>& begin) {
+  const int n = (int)recs.size();
+  auto walk = [&](long long B, std::vector<int>* out) -> int {
+    int used = 0, r = 0, j = 0;                      // next recording / next frame inside it
+    while (r < n && recs[r].nblk == 0) r++;
+    if (out) out->assign(1, r < n ? prefix[r] : prefix[n]);
+    while (r < n) {
+      long long b = B;
+      for (;;) {
+        // frames this CTA can still take from recording r: whole items, b W - H frames at most
+        const long long room = b * W - H;
+        if (room < 1) break;
+        const int rem = recs[r].nblk - j;
+        long long take = rem <= room ? rem : room / q * q;
+        if (take < 1) break;
+        b -= (take + H + W - 1) / W;
+        j += (int)take;
+        if (j >= recs[r].nblk) {
+          r++; j = 0;
+          while (r < n && recs[r].nblk == 0) r++;
+          if (r >= n) break;
+        } else {
+          break;                                      // budget exhausted inside the recording
+        }
+      }
+      used++;
+      if (out) out->push_back(r < n ? prefix[r] + j / q : prefix[n]);
+      if (used > 2 * ncta + 8) break;                // budget too small to ever finish
+    }
+    return used;
+  };
+  long long total = 0;
+  for (int r = 0; r < n; r++) total += recs[r].nblk;
+  long long lo = 1, hi = (total + H + W - 1) / W + n + 1;      // hi: one CTA takes everything
+  while (walk(hi, nullptr) > ncta) hi *= 2;
+  while (lo < hi) {
+    const long long mid = (lo + hi) / 2;
+    if (walk(mid, nullptr) <= ncta) hi = mid; else lo = mid + 1;
+  }
+  walk(lo, &begin);
+  begin.resize((size_t)ncta + 1, prefix[n]);
+  return (int)lo;
+}
+
 // Split every recording's nblk output frames into chunks of at most `chunk` frames.
 inline void build_work(const std::vector<RecDesc>& recs, int chunk, std::vector<WorkItem>& work) {
   work.clear();

@@ -517,7 +517,18 @@ static cudaError_t launch_ws_one(const ChainParams& p, int n_work, cudaStream_t 
       if (e != cudaSuccess) return e;
       slots[csz] = nc > 0 ? nc : 1;
     }
-    const int n_cta = n_work < slots[csz] ? n_work : slots[csz];
+    int n_cta = n_work < slots[csz] ? n_work : slots[csz];
+    if (p.cta_begin) {
+      // host-balanced boundaries were made for p.cta_n CTAs, all resident at once; if this kernel cannot have that many,
+      // split the items evenly instead
+      if (p.cta_n > slots[csz]) {
+        ChainParams q = p;
+        q.cta_begin = nullptr; q.cta_n = 0;
+        cfg.gridDim = dim3((unsigned)(n_cta * csz), 1, 1);
+        return cudaLaunchKernelEx(&cfg, kern, q);
+      }
+      n_cta = p.cta_n;
+    }
     cfg.gridDim = dim3((unsigned)(n_cta * csz), 1, 1);
   }
   return cudaLaunchKernelEx(&cfg, kern, p);

@@ -236,6 +236,7 @@ static int run_chain_ws(int m, int dct, int C, int n_rec, const long long* Ts, c
   p.taps_h = hf.data(); p.taps_g = gp.data(); p.wts = gam.data(); p.wts_stride = 0; p.one_cta = 0; p.no_prefetch = 0; p.twa = twa.data(); p.twb = twb.data();
   p.C = C; p.Cpad = Cpad; p.m = m; p.pd_s = geo.pd_s; p.laN = geo.laN; p.gain = gain; p.cluster = 1;
   p.tmaps = nullptr; p.tma_rows = 0; p.item_begin = nullptr; p.item_q = 0; p.item0 = 0; p.n_items = 0; p.n_rec = n_rec;
+  p.cta_begin = nullptr; p.cta_n = 0;
   p.no_syn = syn ? 0 : 1;
   const WsSmem S = ws_smem_layout<M, R, PP>(m);
   if (S.total > 227 * 1024) return -2;
@@ -293,6 +294,40 @@ extern "C" int emu_ws_segments(int n_rec, const int* nblk, int W, int r0, int r1
   ChainParams p = ChainParams();
   p.recs = recs.data(); p.item_begin = prefix.data(); p.item_q = W; p.item0 = prefix[r0]; p.n_items = prefix[r1] - prefix[r0];
   p.n_rec = n_rec;
+  WsSegs segs(p, cta, ncta);
+  WorkItem wk;
+  int n = 0;
+  while (segs.next(wk)) {
+    if (n < cap) { out[3 * n] = wk.rec; out[3 * n + 1] = wk.j0; out[3 * n + 2] = wk.nj; }
+    n++;
+  }
+  return n;
+}
+
+// Iteration-balanced CTA boundaries of the persistent schedule (host_tables.h::balance_ctas) and the segments CTA `cta`
+// walks under them.  begin gets ncta + 1 item indices; returns the iteration budget B.
+extern "C" int emu_ws_balance(int n_rec, const int* nblk, int q, int W, int H, int ncta, int* begin_out) {
+  std::vector<RecDesc> recs(n_rec);
+  std::vector<int> prefix(n_rec + 1, 0);
+  for (int i = 0; i < n_rec; i++) {
+    recs[i].pcm_off = 0; recs[i].out_off = 0; recs[i].T = 0; recs[i].nblk = nblk[i];
+    prefix[i + 1] = prefix[i] + (nblk[i] + q - 1) / q;
+  }
+  std::vector<int> begin;
+  const int B = balance_ctas(recs, prefix, q, W, H, ncta, begin);
+  for (int i = 0; i <= ncta; i++) begin_out[i] = begin[i];
+  return B;
+}
+extern "C" int emu_ws_segments_balanced(int n_rec, const int* nblk, int q, const int* begin, int cta, int ncta, int* out, int cap) {
+  std::vector<RecDesc> recs(n_rec);
+  std::vector<int> prefix(n_rec + 1, 0);
+  for (int i = 0; i < n_rec; i++) {
+    recs[i].pcm_off = 0; recs[i].out_off = 0; recs[i].T = 0; recs[i].nblk = nblk[i];
+    prefix[i + 1] = prefix[i] + (nblk[i] + q - 1) / q;
+  }
+  ChainParams p = ChainParams();
+  p.recs = recs.data(); p.item_begin = prefix.data(); p.item_q = q; p.item0 = 0; p.n_items = prefix[n_rec]; p.n_rec = n_rec;
+  p.cta_begin = begin; p.cta_n = ncta;
   WsSegs segs(p, cta, ncta);
   WorkItem wk;
   int n = 0;

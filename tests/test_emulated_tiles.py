@@ -134,3 +134,36 @@ def test_persistent_schedule_covers_every_frame_once(emu, ncta):
         for r in range(n):
             assert np.all(cover[r] == (1 if r0 <= r < r1 else 0))
         assert max(items) - min(items) <= 1
+
+
+@pytest.mark.parametrize("shape", [([7500] * 16, 32, 7, 148), ([1250] * 64, 16, 7, 148), ([0, 3, 40, 5000, 0, 1, 77] * 9, 32, 7, 148),
+                                   ([300] * 3, 16, 3, 148), ([100000], 32, 15, 148), ([5] * 1000, 32, 7, 148)])
+def test_balanced_schedule(emu, shape):
+    """host_tables.h::balance_ctas + WsSegs with explicit CTA boundaries: every frame once, every CTA within the iteration
+    budget B, and B - 1 would not have been enough for the equal-item split either (cfg2: 26 iterations instead of 27)."""
+    nblk, W, H, ncta = shape
+    nblk = np.array(nblk, np.int32)
+    n = len(nblk)
+    q = max(W // 8, 1)
+    begin = np.zeros(ncta + 1, np.int32)
+    B = emu.emu_ws_balance(n, vp(nblk), q, W, H, ncta, vp(begin))
+    assert B >= 1 and np.all(np.diff(begin) >= 0) and begin[-1] == sum(-(-int(b) // q) for b in nblk)
+    cover = [np.zeros(int(b), np.int32) for b in nblk]
+    out = np.zeros(3 * 2048, np.int32)
+    worst = 0
+    for cta in range(ncta):
+        k = emu.emu_ws_segments_balanced(n, vp(nblk), q, vp(begin), cta, ncta, vp(out), 2048)
+        assert 0 <= k <= 2048
+        its = 0
+        for rec, j0, nj in out[:3 * k].reshape(-1, 3):
+            assert nj > 0
+            cover[rec][j0:j0 + nj] += 1
+            its += -(-(nj + H) // W)
+        worst = max(worst, its)
+    for r in range(n):
+        assert np.all(cover[r] == 1)
+    assert worst <= B
+    total = int(nblk.sum())
+    assert B >= -(-(total // ncta + H) // W) or total < ncta      # no budget below the average share can work
+    if list(nblk) == [7500] * 16:
+        assert B == 26
