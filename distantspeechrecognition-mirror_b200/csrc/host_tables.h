@@ -367,6 +367,30 @@ inline int balance_ctas(const std::vector<RecDesc>& recs, const std::vector<int>
   return (int)lo;
 }
 
+// Largest number of iterations any CTA runs when the items of the launch are split evenly (what WsSegs does without
+// p.cta_begin): the yardstick for balance_ctas.
+inline long long even_split_iterations(const std::vector<RecDesc>& recs, const std::vector<int>& prefix, int q, int W, int H, int ncta) {
+  const int n = (int)recs.size();
+  const long long total = prefix[n];
+  long long worst = 0;
+  int r = 0;
+  for (int c = 0; c < ncta; c++) {
+    long long i = total * c / ncta;
+    const long long i1 = total * (c + 1) / ncta;
+    long long its = 0;
+    while (i < i1) {
+      while (prefix[r + 1] <= i) r++;
+      const long long e = prefix[r + 1] < i1 ? prefix[r + 1] : i1;
+      const long long j0 = (i - prefix[r]) * q, j1 = (e - prefix[r]) * q;
+      const long long nj = (j1 < recs[r].nblk ? j1 : recs[r].nblk) - j0;
+      its += (nj + H + W - 1) / W;
+      i = e;
+    }
+    if (its > worst) worst = its;
+  }
+  return worst;
+}
+
 // Split every recording's nblk output frames into chunks of at most `chunk` frames.
 inline void build_work(const std::vector<RecDesc>& recs, int chunk, std::vector<WorkItem>& work) {
   work.clear();
