@@ -75,6 +75,35 @@ BTK_HD void analysis_tile(Ctx& ctx, const AnalysisParams& p, unsigned char* smem
           const int c = cg0 + round * K::NG + grp;
           const int f0 = f_base + 2 * warp, f1 = f0 + 1;
           const bool ok0 = c < C && f0 < wk.j0 + wk.nj && f0 < F, ok1 = c < C && f1 < wk.j0 + wk.nj && f1 < F;
+#if defined(__CUDA_ARCH__)
+          // Two lane groups = two NEIGHBOURING channels of the same bins: the groups swap one frame each (lane ^ L), so that
+          // group 0 stores (c, c+1) of frame f0 and group 1 (c-1, c) of frame f1 as ONE 16-byte word -- half the store
+          // instructions and half the sector writes of the 8-byte stores below (each of which lands in a sector of its own:
+          // consecutive lanes are consecutive BINS, C channels apart)
+          const bool pair16 = K::NG == 2 && (C & 1) == 0 && (cg0 + K::CG <= C) &&
+                              ((reinterpret_cast<uintptr_t>(snap) & 15) == 0);      // uniform over the warp
+          if (pair16) {
+            const bool both0 = f0 < wk.j0 + wk.nj && f0 < F, both1 = f1 < wk.j0 + wk.nj && f1 < F;
+            BTK_UNROLL
+            for (int r = 0; r < G::V; r++) {
+              const int k = G::index_of_spec(gl, r);
+              const cf zk = ts.z[r];
+              const cf zm = xb[(M_ - k) & (M_ - 1)];
+              const cf x0 = mk(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y)), x1 = mk(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x));
+              const cf give = grp == 0 ? x1 : x0;
+              cf got;
+              got.x = __shfl_xor_sync(0xffffffffu, give.x, G::L);
+              got.y = __shfl_xor_sync(0xffffffffu, give.y, G::L);
+              if (k > M_ / 2) continue;
+              if (grp == 0) {
+                if (both0) *reinterpret_cast<float4*>(snap + ((long long)f0 * B + k) * C + c) = make_float4(x0.x, x0.y, got.x, got.y);
+              } else {
+                if (both1) *reinterpret_cast<float4*>(snap + ((long long)f1 * B + k) * C + c - 1) = make_float4(got.x, got.y, x1.x, x1.y);
+              }
+            }
+            return;
+          }
+#endif
           BTK_UNROLL
           for (int r = 0; r < G::V; r++) {
             const int k = G::index_of_spec(gl, r);
