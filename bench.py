@@ -9,7 +9,10 @@ One "step" = one pass of the fused chain over this rank's batch of synthetic arr
 Recordings are independent, so ranks share nothing on the data path (weak scaling: fixed batch per GPU);
 torch.distributed is only used for the barrier and the max-over-ranks time.
 
-  value      device-resident: inputs already in HBM, CUDA events around K launches on the launching stream
+  value      device-resident: inputs already in HBM, CUDA events around the K timed steps on the launching stream; the K
+             steps are ONE CUDA graph of K launches of btkb200_chain_batch_dev (captured once, one untimed replay, then
+             the timed replay), so that a slow host is not measured in place of 0.25-ms kernels; kernel_ms = total / K;
+             --no-graph times K direct launches with an event pair each ("timed_as" in the line says which)
   e2e        through the host-buffer C-ABI call (btkb200_chain_batch): pinned host buffers, H2D of every
              input and D2H of every output inside the timed region
   roofline   algorithmic bytes of the fused chain (4 C T + 4 nblk D per recording) / launch time,
